@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference.
+
+Runs only in the build container (needs /root/reference).  It imports the reference's own modules
+(renderer.py, utils.py, model_*.py) read-only with stub modules for the absent, off-path
+dependencies (matplotlib), executes the hot-path functions on seeded synthetic inputs, and stores
+inputs + outputs + gradients as small .npz files.  tests/test_oracle_golden.py pins oracle/oracle.py
+against them; the -m gpu tests pin the CUDA kernels against the same files.
+
+Usage: python tools/make_golden.py            (rewrites tests/golden/*.npz)
+"""
+import hashlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/src"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+sys.modules.setdefault("matplotlib", types.ModuleType("matplotlib"))
+sys.path.insert(0, REF)
+sys.path.insert(0, ROOT)
+
+import model_autorf  # noqa: E402  (reference)
+import model_codenerf  # noqa: E402
+import model_supnerf  # noqa: E402
+import renderer as ref_renderer  # noqa: E402
+import utils as ref_utils  # noqa: E402
+
+from oracle import oracle  # noqa: E402
+
+
+def state_hash(sd):
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(sd[k].detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def npy(t):
+    return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+
+def save(name, **arrs):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **{k: npy(v) for k, v in arrs.items()})
+    print(f"wrote {path}  ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+def losses(rgb, acc, tgt, occ):
+    return oracle.refine_losses(rgb, acc, tgt, occ)[0]
+
+
+# ---------------------------------------------------------------------------------------------------
+def golden_stages():
+    """Stage-level vectors: ray gen, slab test (edge cases), stratified z, PE, compositing variants."""
+    torch.manual_seed(7)
+    np.random.seed(7)
+    obj = oracle.synthetic_object(3, im_sz=12)
+    K, c2w, roi = obj["K"], obj["cam_pose"], obj["roi"]
+    ro, vd = ref_utils.get_rays(K, c2w, roi, uv_steps=[12, 12])
+    ro_full, vd_full = ref_utils.get_rays(K, c2w, torch.tensor([100, 50, 109, 57], dtype=torch.int32))
+    xv = np.asarray([0, 3, 5, 7], dtype=np.int64)
+    yv = np.asarray([1, 2, 4, 6], dtype=np.int64)
+    ro_s, vd_s = ref_utils.get_rays_specified(K, c2w, xv + roi[0].numpy(), yv + roi[1].numpy())
+
+    # slab-test edge cases in the normalised box frame
+    half = np.asarray([0.9, 0.4, 0.3], dtype=np.float32)
+    o = [[-3, 0, 0], [-3, 0, 0], [0, 0, 0], [-3, 0.4, 0], [-3, 0.41, 0], [3, 0, 0], [-3, 0, 0], [0.9, 0, 0],
+         [-3, 0.39999, 0.2999], [2, 2, 2]]
+    d = [[1, 0, 0], [-1, 0, 0], [0.6, 0.8, 0], [1, 0, 0], [1, 0, 0], [1, 0, 0], [0, 1, 0], [1, 0, 0],
+         [1, 0, 0], [-0.57735026, -0.57735026, -0.57735026]]
+    rnd_o = (np.random.randn(200, 3) * 2).astype(np.float32)
+    rnd_d = np.random.randn(200, 3).astype(np.float32)
+    rnd_d /= np.linalg.norm(rnd_d, axis=1, keepdims=True)
+    eo = np.concatenate([np.asarray(o, np.float32), rnd_o])
+    ed = np.concatenate([np.asarray(d, np.float32), rnd_d])
+    amin = np.repeat(-half[None], eo.shape[0], 0)
+    amax = np.repeat(half[None], eo.shape[0], 0)
+    with np.errstate(all="ignore"):
+        zi_np, zo_np, hit_np = ref_utils.ray_box_intersection(eo, ed, amin, amax)
+    zi_t, zo_t, hit_t = ref_utils.ray_box_intersection_tensor(torch.from_numpy(eo), torch.from_numpy(ed),
+                                                             torch.from_numpy(amin), torch.from_numpy(amax))
+    # default unit box
+    zi_u, zo_u, hit_u = ref_utils.ray_box_intersection_tensor(torch.from_numpy(eo), torch.from_numpy(ed))
+
+    # stratified z
+    S = 16
+    rays = torch.cat([torch.from_numpy(eo), torch.from_numpy(ed), torch.rand(eo.shape[0], 1), 1 + torch.rand(eo.shape[0], 1)], -1)
+    torch.manual_seed(11)
+    jit = torch.rand(eo.shape[0], S)
+    torch.manual_seed(11)
+    z_ref = ref_renderer.NeRFRenderer(n_samples=S).sample_from_ray(rays)
+    torch.manual_seed(11)
+    z_ref2 = ref_utils.sample_from_rays_v2(rays, S)
+    assert torch.equal(z_ref, z_ref2)
+
+    # shell sampler
+    torch.manual_seed(12)
+    jit_shell = torch.rand(S)
+    torch.manual_seed(12)
+    xyz_sh, vd_sh, z_sh = ref_utils.sample_from_rays(ro, vd, 5.25, 9.75, S)
+    xyz_fx, vd_fx, z_fx = ref_utils.sample_from_rays(ro, vd, 5.25, 9.75, S, z_fixed=True)
+
+    # PE
+    x = (torch.rand(50, 3) * 2 - 1) * 1.7
+    pe10 = model_codenerf.PE(x, 10)
+    pe4 = model_codenerf.PE(x, 4)
+
+    # compositing: per-ray z, incl. opaque samples, negative sigmas, miss-ray style constant z
+    N = 37
+    sig = torch.randn(N, S) * 3
+    sig[3] = 1e4  # opaque
+    sig[4] = -1.0  # all empty
+    rgbs = torch.rand(N, S, 3) * 1.5 - 0.25
+    zv = torch.sort(torch.rand(N, S) * 4 + 2, -1)[0]
+    zv[5] = 2.5  # miss ray: all samples at one point
+    outs = {}
+    for wb in (False, True):
+        r = ref_renderer.NeRFRenderer(n_samples=S, white_bkgd=wb)
+        s_, c_, z_ = sig.clone().requires_grad_(), rgbs.clone().requires_grad_(), zv.clone().requires_grad_()
+        rgb, dep, acc = r.volume_render(s_, c_, z_)
+        g = torch.Generator().manual_seed(5)
+        g_rgb, g_dep, g_acc = torch.randn(N, 3, generator=g), torch.randn(N, generator=g), torch.randn(N, generator=g)
+        (rgb * g_rgb).sum().add((dep * g_dep).sum()).add((acc * g_acc).sum()).backward()
+        rgb3, dep3, acc3 = ref_renderer.volume_rendering3(sig.unsqueeze(-1), rgbs, zv, white_bkgd=wb)
+        assert torch.equal(rgb3, rgb) and torch.equal(dep3, dep) and torch.equal(acc3, acc)
+        outs.update({f"vr_rgb_wb{int(wb)}": rgb, f"vr_depth_wb{int(wb)}": dep, f"vr_acc_wb{int(wb)}": acc,
+                     f"vr_gsig_wb{int(wb)}": s_.grad, f"vr_grgb_wb{int(wb)}": c_.grad, f"vr_gz_wb{int(wb)}": z_.grad,
+                     "vr_up_rgb": g_rgb, "vr_up_depth": g_dep, "vr_up_acc": g_acc})
+    # shared z (S,)
+    z1 = zv[0].clone()
+    rgb2, dep2, acc2 = ref_utils.volume_rendering2(sig.unsqueeze(-1), rgbs, z1)
+    rgb1, dep1 = ref_utils.volume_rendering(torch.relu(sig).unsqueeze(-1), rgbs, z1)
+    # batch (B,n,S) with z (B,S)
+    Bb, nb = 3, 5
+    sigb, rgbb, zb = sig[:Bb * nb].reshape(Bb, nb, S, 1), rgbs[:Bb * nb].reshape(Bb, nb, S, 3), zv[:Bb]
+    rgbB, depB, accB = ref_utils.volume_rendering_batch(sigb, rgbb, zb)
+
+    save("stages",
+         K=K, c2w=c2w, roi=roi, rays_o=ro, viewdir=vd, rays_o_full=ro_full, viewdir_full=vd_full,
+         x_vec=xv, y_vec=yv, rays_o_spec=ro_s, viewdir_spec=vd_s,
+         box_o=eo, box_d=ed, box_half=half, box_hit_np=hit_np, box_zin_np=zi_np, box_zout_np=zo_np,
+         box_hit_t=hit_t, box_zin_t=zi_t, box_zout_t=zo_t, box_hit_unit=hit_u, box_zin_unit=zi_u, box_zout_unit=zo_u,
+         strat_rays=rays, strat_jitter=jit, strat_z=z_ref,
+         shell_jitter=jit_shell, shell_xyz=xyz_sh, shell_z=z_sh, shell_z_fixed=z_fx,
+         pe_x=x, pe10=pe10, pe4=pe4,
+         vr_sig=sig, vr_rgbs=rgbs, vr_z=zv, vr2_rgb=rgb2, vr2_depth=dep2, vr2_acc=acc2, vr1_rgb=rgb1, vr1_depth=dep1,
+         vrb_rgb=rgbB, vrb_depth=depB, vrb_acc=accB, **outs)
+
+
+def golden_render_box():
+    """Config-1 shape, scaled down: NeRFRenderer.render_rays (renderer.py:117) fwd + bwd, CodeNeRF()
+    defaults, weights as shipped (requires_grad=True)."""
+    seed, im_sz, S = 0, 12, 16
+    sd = oracle.init_codenerf_state(seed=seed)
+    torch.manual_seed(seed)
+    model = model_codenerf.CodeNeRF()
+    ref_sd = {k: v for k, v in model.state_dict().items()}
+    assert all(torch.equal(ref_sd[k], sd[k]) for k in ref_sd), "oracle weight init != reference init"
+    obj = oracle.synthetic_object(1, im_sz=im_sz)
+    shp, tex = oracle.synthetic_latents(1, 1)
+    cam = obj["cam_pose"].clone().requires_grad_()
+    shp.requires_grad_(), tex.requires_grad_()
+    r = ref_renderer.NeRFRenderer(n_samples=S)
+    torch.manual_seed(100)
+    jitter = torch.rand(im_sz * im_sz, S)
+    torch.manual_seed(100)
+    rgb, dep, acc, tgt, occ = r.render_rays(model, "cpu", obj["img"], obj["mask_occ"], cam, obj["wlh"], obj["K"], obj["roi"],
+                                            shp, tex, im_sz=im_sz)
+    loss = losses(rgb, acc, tgt, occ)
+    loss.backward()
+    # hit mask straight from the reference's sampler on the same rays
+    ro, vd = ref_utils.get_rays(obj["K"], obj["cam_pose"], obj["roi"], uv_steps=[im_sz, im_sz])
+    torch.manual_seed(100)
+    xyz, vdr, zv, hit = r.prepare_sampled_rays(ro, vd, obj["wlh"])
+    g = {k: p.grad for k, p in model.named_parameters()}
+    save("render_box_c1",
+         seed=seed, im_sz=im_sz, n_samples=S, weights_sha256=np.frombuffer(state_hash(sd).encode(), dtype=np.uint8),
+         K=obj["K"], cam_pose=obj["cam_pose"], wlh=obj["wlh"], roi=obj["roi"], img=obj["img"], mask_occ=obj["mask_occ"],
+         shapecode=shp, texturecode=tex, jitter=jitter,
+         rgb=rgb, depth=dep, acc=acc, rgb_tgt=tgt, occ_pixels=occ, hit=hit, xyz=xyz, z_vals=zv, loss=loss,
+         g_cam_pose=cam.grad, g_shapecode=shp.grad, g_texturecode=tex.grad,
+         **{"gw_" + k: v for k, v in g.items()})
+
+
+def golden_render_shell():
+    """Config-3 shape, scaled down: utils.render_rays_v2 (utils.py:435) fwd + bwd with the SUPNeRF
+    decoder (3/1/256), shapenet_obj_cood=1, the refine losses."""
+    seed, im_sz, S = 2, 8, 16
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=seed)
+    model = model_supnerf.SUPNeRF(shape_blocks=3, texture_blocks=1, pose_blocks=3, regress_blocks=3, latent_dim=256)
+    missing = model.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys
+    obj = oracle.synthetic_object(5, im_sz=im_sz)
+    shp, tex = oracle.synthetic_latents(5, 1)
+    cam = obj["cam_pose"].clone().requires_grad_()
+    shp.requires_grad_(), tex.requires_grad_()
+    diag = np.linalg.norm(obj["wlh"]).astype(np.float32)
+    torch.manual_seed(200)
+    jitter = torch.rand(S)
+    torch.manual_seed(200)
+    rgb, dep, acc, tgt, occ = ref_utils.render_rays_v2(model, "cpu", obj["img"], obj["mask_occ"], cam, diag, obj["K"], obj["roi"],
+                                                       S, shp, tex, 1, 0, im_sz=im_sz, n_rays=None)
+    loss = losses(rgb, acc, tgt, occ)
+    loss.backward()
+    save("render_shell_c3",
+         seed=seed, im_sz=im_sz, n_samples=S, weights_sha256=np.frombuffer(state_hash(sd).encode(), dtype=np.uint8),
+         K=obj["K"], cam_pose=obj["cam_pose"], wlh=obj["wlh"], obj_diag=diag, roi=obj["roi"], img=obj["img"],
+         mask_occ=obj["mask_occ"], shapecode=shp, texturecode=tex, jitter=jitter,
+         rgb=rgb, depth=dep, acc=acc, rgb_tgt=tgt, occ_pixels=occ, loss=loss,
+         g_cam_pose=cam.grad, g_shapecode=shp.grad, g_texturecode=tex.grad,
+         gw_encoding_xyz_0_weight=model.encoding_xyz[0].weight.grad, gw_rgb_2_weight=model.rgb[2].weight.grad,
+         gw_shape_latent_layer_2_0_weight=model.shape_latent_layer_2[0].weight.grad,
+         gw_encoding_viewdir_0_weight=model.encoding_viewdir[0].weight.grad,
+         gw_sigma_0_bias=model.sigma[0].bias.grad)
+
+
+def golden_decoder_batch():
+    """Config-2/5 shape, scaled down: AutoRFMix(3,1,256) decoder on B=2 objects, explicit xyz/viewdir
+    (the trainer's call, trainer_unified_nuscenes.py:120-129), volume_rendering_batch, all grads."""
+    seed, B, n, S = 3, 2, 24, 8
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=seed)
+    model = model_autorf.AutoRFMix(shape_blocks=3, texture_blocks=1, latent_dim=256)
+    assert not model.load_state_dict(sd, strict=False).unexpected_keys
+    g = torch.Generator().manual_seed(seed)
+    xyz = (torch.rand(B, n, S, 3, generator=g) - 0.5).requires_grad_()
+    vd = torch.nn.functional.normalize(torch.randn(B, n, 1, 3, generator=g), dim=-1).repeat(1, 1, S, 1).requires_grad_()
+    zv = torch.sort(torch.rand(B, S, generator=g) * 4 + 6, -1)[0]
+    shp, tex = oracle.synthetic_latents(seed, B)
+    shp.requires_grad_(), tex.requires_grad_()
+    sig, rgbs = model(xyz.flatten(0, 1), vd.flatten(0, 1), shp, tex)
+    rgb, dep, acc = ref_utils.volume_rendering_batch(sig.reshape(B, n, S, 1), rgbs.reshape(B, n, S, 3), zv)
+    tgt = torch.rand(B, n, 3, generator=g)
+    occ = torch.sign(torch.randn(B, n, 1, generator=g))
+    loss = losses(rgb, acc, tgt, occ)
+    loss.backward()
+    save("decoder_batch_c5",
+         seed=seed, weights_sha256=np.frombuffer(state_hash(sd).encode(), dtype=np.uint8),
+         xyz=xyz, viewdir=vd, z_vals=zv, shapecode=shp, texturecode=tex, rgb_tgt=tgt, occ_pixels=occ,
+         sigmas=sig, rgbs=rgbs, rgb=rgb, depth=dep, acc=acc, loss=loss,
+         g_xyz=xyz.grad, g_viewdir=vd.grad, g_shapecode=shp.grad, g_texturecode=tex.grad,
+         **{"gw_" + k: p.grad for k, p in model.named_parameters() if p.grad is not None})
+
+
+def golden_autorf():
+    """The non-mix AutoRF decoder (model_autorf.py:156-186), class defaults 5/5/128."""
+    seed, B, n, S = 4, 2, 10, 6
+    sd = oracle.init_autorf_state(seed=seed)
+    model = model_autorf.AutoRF()
+    assert not model.load_state_dict(sd, strict=False).unexpected_keys
+    g = torch.Generator().manual_seed(seed)
+    xyz = (torch.rand(B * n, S, 3, generator=g) - 0.5).requires_grad_()
+    vd = torch.nn.functional.normalize(torch.randn(B * n, 1, 3, generator=g), dim=-1).repeat(1, S, 1).requires_grad_()
+    shp, tex = oracle.synthetic_latents(seed, B, 128)
+    shp.requires_grad_(), tex.requires_grad_()
+    sig, rgbs = model(xyz, vd, shp, tex)
+    up_s = torch.randn(sig.shape, generator=g)
+    up_c = torch.randn(rgbs.shape, generator=g)
+    ((sig * up_s).sum() + (rgbs * up_c).sum()).backward()
+    save("autorf_decoder",
+         seed=seed, weights_sha256=np.frombuffer(state_hash(sd).encode(), dtype=np.uint8),
+         xyz=xyz, viewdir=vd, shapecode=shp, texturecode=tex, up_sigma=up_s, up_rgb=up_c, sigmas=sig, rgbs=rgbs,
+         g_xyz=xyz.grad, g_viewdir=vd.grad, g_shapecode=shp.grad, g_texturecode=tex.grad,
+         **{"gw_" + k: p.grad for k, p in model.named_parameters() if p.grad is not None and not k.startswith("img_encoder")})
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    golden_stages()
+    golden_render_box()
+    golden_render_shell()
+    golden_decoder_batch()
+    golden_autorf()
