@@ -1,0 +1,150 @@
+/* supnerf_b200 — C ABI of the B200-native SUP-NeRF object-centric render hot path.
+ *
+ * The reference (abhi1kumar/SUP-NeRF) has no FFI: its boundary is the Python call API of
+ * src/renderer.py, src/utils.py:94-672 and src/model_{codenerf,autorf,supnerf}.py.  These entry
+ * points are what a ctypes binding for that path binds (INTEGRATION.md shows the stub); each one
+ * cites the reference function it replaces.  Conventions:
+ *   - every pointer is a DEVICE pointer to fp32 row-major data unless stated; borrowed for the call;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises;
+ *   - return 0 on success, non-zero on error; snb_last_error() gives the message (thread-local);
+ *   - no global mutable state besides the per-handle weight tables; one handle per (device, model).
+ * There is NO CPU fallback: without a CUDA device every compute call returns an error.
+ */
+#ifndef SUPNERF_B200_H
+#define SUPNERF_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNB_ABI_VERSION 1
+
+/* flags for the compositing kernels */
+#define SNB_WHITE_BKGD 1 /* renderer.py:60-63 */
+#define SNB_SIGMA_RELU 2 /* renderer.py:52; cleared only for utils.volume_rendering (utils.py:191) */
+
+/* decoder families */
+#define SNB_ARCH_CODENERF 0 /* CodeNeRF / AutoRFMix / SUPNeRF decoder: model_codenerf.py:39-63 */
+#define SNB_ARCH_AUTORF 1   /* AutoRF decoder: model_autorf.py:156-186 */
+
+/* MLP arithmetic */
+#define SNB_PREC_FP32 0 /* SIMT FFMA, fp32 everywhere: the 1e-5 parity mode */
+#define SNB_PREC_BF16 1 /* tcgen05 bf16 x bf16 -> fp32 TMEM accumulators: the 2e-2 throughput mode */
+
+typedef struct snb_handle_s* snb_handle;
+
+typedef struct {
+  int32_t arch;           /* SNB_ARCH_* */
+  int32_t shape_blocks;   /* ctor arg of the same name */
+  int32_t texture_blocks; /* ctor arg of the same name */
+  int32_t W;              /* hidden width (CodeNeRF: W; AutoRFMix/SUPNeRF/AutoRF: latent_dim) */
+  int32_t latent_dim;
+  int32_t num_xyz_freq;   /* 10 */
+  int32_t num_dir_freq;   /* 4 */
+} snb_arch;
+
+int snb_abi_version(void);
+const char* snb_last_error(void);
+/* Number of SMs etc. of the current device; fails without a GPU. */
+int snb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- K3 / K3b: alpha compositing -------------------------------------------------------------
+ * Replaces NeRFRenderer.volume_render (renderer.py:43-65), volume_rendering3 (renderer.py:355-379),
+ * utils.volume_rendering2 (utils.py:202-217), utils.volume_rendering_batch (utils.py:220-233) and
+ * utils.volume_rendering (utils.py:187-199).
+ * sigma (N,S); rgb (N,S,3); z: row r(i) = i / rays_per_zrow, i.e. rays_per_zrow = 1 for per-ray
+ * z_vals (N,S), = N for one shared vector (S,), = n for (B,S) against (B,n,S).
+ * out_rgb (N,3), out_depth (N), out_acc (N) (transmittance before the last sample). */
+int snb_composite_fwd(const float* sigma, const float* rgb, const float* z, int64_t rays_per_zrow,
+                      int64_t n_rays, int32_t n_samples, int32_t flags,
+                      float* out_rgb, float* out_depth, float* out_acc, void* stream);
+/* Backward of the above (autograd of renderer.py:50-65).  g_z is per ray (N,S) whatever the z
+ * layout (the caller reduces it for shared rows); g_z may be NULL. */
+int snb_composite_bwd(const float* sigma, const float* rgb, const float* z, int64_t rays_per_zrow,
+                      int64_t n_rays, int32_t n_samples, int32_t flags,
+                      const float* g_rgb, const float* g_depth, const float* g_acc,
+                      float* g_sigma, float* g_rgbs, float* g_z, void* stream);
+
+/* ---- K1 / K1b: ray generation, slab test, stratified sampling ----------------------------------
+ * snb_get_rays: utils.get_rays / get_rays_specified (utils.py:107-151).  px,py (N) pixel coords
+ * (fp32, as produced by torch.linspace); K (3,3) and c2w (3,4) on the device.
+ * Backward gives g_c2w (12 floats, ACCUMULATED with atomics: zero it first). */
+int snb_get_rays_fwd(const float* px, const float* py, int64_t n_rays, const float* K, const float* c2w,
+                     float* rays_o, float* viewdir, void* stream);
+int snb_get_rays_bwd(const float* px, const float* py, int64_t n_rays, const float* K, const float* c2w,
+                     const float* g_rays_o, const float* g_viewdir, float* g_c2w, void* stream);
+/* snb_ray_box: the slab test alone — utils.ray_box_intersection_tensor (utils.py:283-327) and its
+ * numpy twin ray_box_intersection (utils.py:236-280).  aabb_min/aabb_max are per-ray (N,3) or both
+ * NULL for the unit box.  Outputs are UNCOMPACTED: t_near (N), t_far (N), hit (N) uint8; the
+ * reference's `t_near[hit]` compaction is the caller's.  Backward: gradients of the uncompacted
+ * t_near/t_far to ray_o, ray_d (and, if non-NULL, aabb_min/aabb_max), ties split as torch does. */
+int snb_ray_box_fwd(const float* ray_o, const float* ray_d, const float* aabb_min, const float* aabb_max,
+                    int64_t n_rays, float* t_near, float* t_far, uint8_t* hit, void* stream);
+int snb_ray_box_bwd(const float* ray_o, const float* ray_d, const float* aabb_min, const float* aabb_max,
+                    int64_t n_rays, const float* g_near, const float* g_far,
+                    float* g_ray_o, float* g_ray_d, float* g_aabb_min, float* g_aabb_max, void* stream);
+/* snb_sample_box: NeRFRenderer.prepare_sampled_rays (renderer.py:91-115) incl. the slab test
+ * ray_box_intersection_tensor (utils.py:283-327) and sample_from_ray (renderer.py:27-41).
+ * half_diag = diag/2 and aabb_half = (l,w,h)/diag are the reference's host-rounded float32s.
+ * z_steps (S) = torch.linspace(0, 1-1/S, S) (renderer.py:38, kept as an input so its fp32 rounding
+ * is the reference's); jitter (N,S) = the torch.rand_like draw (renderer.py:40).  Outputs: xyz (N,S,3), viewdir_rep (N,S,3, nullable),
+ * z_vals (N,S), hit (N) uint8 — bit-exact with the reference's bool mask. */
+int snb_sample_box_fwd(const float* rays_o, const float* viewdir, const float* z_steps, const float* jitter,
+                       int64_t n_rays, int32_t n_samples, float half_diag, const float* aabb_half_host3,
+                       float* xyz, float* viewdir_rep, float* z_vals, uint8_t* hit, void* stream);
+int snb_sample_box_bwd(const float* rays_o, const float* viewdir, const float* z_steps, const float* jitter,
+                       int64_t n_rays, int32_t n_samples, float half_diag, const float* aabb_half_host3,
+                       const float* g_xyz, const float* g_viewdir_rep, const float* g_z_vals,
+                       float* g_rays_o, float* g_viewdir, void* stream);
+/* snb_sample_shell: utils.sample_from_rays (utils.py:154-167) + `xyz /= obj_diag` (utils.py:472) +
+ * the shapenet axis swap (utils.py:491-495).  z (S) is the shared sample vector (built on the host
+ * exactly as the reference does).  inv_scale = 1 for a plain sample_from_rays. */
+int snb_sample_shell_fwd(const float* rays_o, const float* viewdir, const float* z, int64_t n_rays,
+                         int32_t n_samples, float obj_diag, int32_t shapenet_swap,
+                         float* xyz, float* viewdir_rep, void* stream);
+int snb_sample_shell_bwd(const float* z, int64_t n_rays, int32_t n_samples, float obj_diag, int32_t shapenet_swap,
+                         const float* g_xyz, const float* g_viewdir_rep,
+                         float* g_rays_o, float* g_viewdir, void* stream);
+
+/* ---- K2 / K2b: positional encoding + latent-conditioned decoder MLP -----------------------------
+ * Replaces CodeNeRF.forward (model_codenerf.py:39-63) ≡ AutoRFMix.forward (model_autorf.py:226-250)
+ * ≡ SUPNeRF.forward (model_supnerf.py:241-269), and AutoRF.forward (model_autorf.py:156-186).
+ * Weight ABI = the reference's state_dict order restricted to the decoder:
+ *   CODENERF: encoding_xyz.0, [shape_latent_layer_j.0, shape_layer_j.0]_{j=1..Bs}, encoding_shape,
+ *             sigma.0, encoding_viewdir.0, [texture_latent_layer_j.0, texture_layer_j.0]_{j=1..Bt},
+ *             rgb.0, rgb.2 — each as (weight (out,in) row-major, bias).
+ *   AUTORF:   encoding_xyz.0, shape_layer_{0..Bs-2}.0, sigma.0, texture_layer_{0..Bt-2}.0, rgb.0.
+ * snb_set_weights borrows the fp32 device pointers (2 per layer); they must stay valid until the
+ * next snb_set_weights / snb_destroy. */
+int snb_create(snb_handle* out, const snb_arch* arch);
+int snb_destroy(snb_handle h);
+int snb_num_weight_tensors(snb_handle h);
+int snb_layer_shape(snb_handle h, int32_t layer, int32_t* out_dim, int32_t* in_dim);
+int snb_set_weights(snb_handle h, const float* const* tensors, int32_t n_tensors);
+/* bf16 mode only: re-tile the fp32 weights into the bf16 shared-memory images the tcgen05 kernels
+ * stream with bulk copies.  packed must hold snb_packed_bytes(h).  Call again after weights change. */
+size_t snb_packed_bytes(snb_handle h);
+int snb_pack_weights(snb_handle h, void* packed, void* stream);
+/* Scratch the forward needs (and the backward re-reads): activations in fp32 mode, ReLU masks +
+ * per-sample sigma/rgb in bf16 mode.  n_rows = N*S samples. */
+size_t snb_mlp_workspace_bytes(snb_handle h, int64_t n_rows, int64_t n_objs, int32_t precision);
+/* xyz, viewdir (n_rows,3); latents (n_objs, latent_dim); object b owns rows
+ * [b*n_rows/n_objs, (b+1)*n_rows/n_objs).  sigma (n_rows), rgb (n_rows,3). */
+int snb_mlp_fwd(snb_handle h, int32_t precision, const float* xyz, const float* viewdir, int64_t n_rows,
+                int64_t n_objs, const float* shape_latent, const float* texture_latent,
+                float* sigma, float* rgb, void* workspace, void* stream);
+/* g_xyz / g_viewdir (n_rows,3) may be NULL (no pose gradient wanted).  g_weights: NULL, or
+ * snb_num_weight_tensors device pointers that receive (are overwritten with) the weight grads.
+ * scratch: snb_mlp_bwd_scratch_bytes. */
+size_t snb_mlp_bwd_scratch_bytes(snb_handle h, int64_t n_rows, int64_t n_objs, int32_t precision);
+int snb_mlp_bwd(snb_handle h, int32_t precision, const float* xyz, const float* viewdir, int64_t n_rows,
+                int64_t n_objs, const float* shape_latent, const float* texture_latent,
+                const float* sigma, const float* g_sigma, const float* g_rgb, const void* workspace,
+                void* scratch, float* g_xyz, float* g_viewdir, float* g_shape_latent,
+                float* g_texture_latent, float* const* g_weights, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

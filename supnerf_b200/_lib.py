@@ -1,0 +1,103 @@
+"""ctypes binding of libsupnerf_b200.so (the C ABI declared in include/supnerf_b200.h).
+
+There is no fallback: if the library is missing, or a call fails, this raises."""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsupnerf_b200.so")
+
+c_f = ctypes.c_void_p  # device float*
+c_i64, c_i32, c_flt, c_sz = ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_size_t
+
+
+class SnbArch(ctypes.Structure):
+    _fields_ = [("arch", c_i32), ("shape_blocks", c_i32), ("texture_blocks", c_i32), ("W", c_i32),
+                ("latent_dim", c_i32), ("num_xyz_freq", c_i32), ("num_dir_freq", c_i32)]
+
+
+# name -> (restype, argtypes); mirrors include/supnerf_b200.h one to one
+SIGNATURES = {
+    "snb_abi_version": (c_i32, []),
+    "snb_last_error": (ctypes.c_char_p, []),
+    "snb_device_info": (c_i32, [ctypes.POINTER(c_i32)] * 3),
+    "snb_composite_fwd": (c_i32, [c_f, c_f, c_f, c_i64, c_i64, c_i32, c_i32, c_f, c_f, c_f, c_f]),
+    "snb_composite_bwd": (c_i32, [c_f, c_f, c_f, c_i64, c_i64, c_i32, c_i32, c_f, c_f, c_f, c_f, c_f, c_f, c_f]),
+    "snb_get_rays_fwd": (c_i32, [c_f, c_f, c_i64, c_f, c_f, c_f, c_f, c_f]),
+    "snb_get_rays_bwd": (c_i32, [c_f, c_f, c_i64, c_f, c_f, c_f, c_f, c_f, c_f]),
+    "snb_ray_box_fwd": (c_i32, [c_f, c_f, c_f, c_f, c_i64, c_f, c_f, c_f, c_f]),
+    "snb_ray_box_bwd": (c_i32, [c_f, c_f, c_f, c_f, c_i64, c_f, c_f, c_f, c_f, c_f, c_f, c_f]),
+    "snb_sample_box_fwd": (c_i32, [c_f, c_f, c_f, c_f, c_i64, c_i32, c_flt, ctypes.POINTER(c_flt), c_f, c_f, c_f, c_f, c_f]),
+    "snb_sample_box_bwd": (c_i32, [c_f, c_f, c_f, c_f, c_i64, c_i32, c_flt, ctypes.POINTER(c_flt), c_f, c_f, c_f, c_f, c_f, c_f]),
+    "snb_sample_shell_fwd": (c_i32, [c_f, c_f, c_f, c_i64, c_i32, c_flt, c_i32, c_f, c_f, c_f]),
+    "snb_sample_shell_bwd": (c_i32, [c_f, c_i64, c_i32, c_flt, c_i32, c_f, c_f, c_f, c_f, c_f]),
+    "snb_create": (c_i32, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(SnbArch)]),
+    "snb_destroy": (c_i32, [ctypes.c_void_p]),
+    "snb_num_weight_tensors": (c_i32, [ctypes.c_void_p]),
+    "snb_layer_shape": (c_i32, [ctypes.c_void_p, c_i32, ctypes.POINTER(c_i32), ctypes.POINTER(c_i32)]),
+    "snb_set_weights": (c_i32, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), c_i32]),
+    "snb_packed_bytes": (c_sz, [ctypes.c_void_p]),
+    "snb_pack_weights": (c_i32, [ctypes.c_void_p, c_f, c_f]),
+    "snb_mlp_workspace_bytes": (c_sz, [ctypes.c_void_p, c_i64, c_i64, c_i32]),
+    "snb_mlp_bwd_scratch_bytes": (c_sz, [ctypes.c_void_p, c_i64, c_i64, c_i32]),
+    "snb_mlp_fwd": (c_i32, [ctypes.c_void_p, c_i32, c_f, c_f, c_i64, c_i64, c_f, c_f, c_f, c_f, c_f, c_f]),
+    "snb_mlp_bwd": (c_i32, [ctypes.c_void_p, c_i32, c_f, c_f, c_i64, c_i64, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
+                            c_f, c_f, ctypes.POINTER(ctypes.c_void_p), c_f]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built — there is no CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m supnerf_b200.build` (or __graft_entry__.build()). "
+            "supnerf_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.snb_abi_version() != 1:
+        raise ImportError("libsupnerf_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+class SnbError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != 0:
+        raise SnbError(f"{what} failed (rc={rc}): {load().snb_last_error().decode(errors='replace')}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  Tensors must be CUDA, fp32/uint8, contiguous."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise SnbError("supnerf_b200 kernels need CUDA tensors; there is no CPU fallback")
+
+
+def f32c(t):
+    """contiguous fp32 view/copy on the same device"""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

@@ -1,0 +1,39 @@
+// Per-model handle shared by the MLP back ends.
+#pragma once
+#include <vector>
+#include "../../include/supnerf_b200.h"
+
+struct snb_layer {
+  const float* w = nullptr;  // (out, in) row-major fp32, borrowed
+  const float* b = nullptr;  // (out)
+  int out = 0, in = 0;
+};
+
+struct snb_handle_s {
+  snb_arch arch;
+  std::vector<snb_layer> layers;  // canonical (state_dict) order
+  bool weights_set = false;
+  // bf16 back end
+  const void* packed = nullptr;   // borrowed: caller-owned buffer filled by snb_pack_weights
+  // CodeNeRF-family layer indices
+  int iX = 0, iES = 0, iSG = 0, iEV = 0, iR0 = 0, iR2 = 0;
+  int iSL(int j) const { return 1 + 2 * (j - 1); }       // shape_latent_layer_j, j = 1..Bs
+  int iS(int j) const { return 2 + 2 * (j - 1); }        // shape_layer_j
+  int iTL(int j) const { return iEV + 1 + 2 * (j - 1); } // texture_latent_layer_j
+  int iT(int j) const { return iEV + 2 + 2 * (j - 1); }  // texture_layer_j
+  int d_xyz() const { return 3 + 6 * arch.num_xyz_freq; }
+  int d_dir() const { return 3 + 6 * arch.num_dir_freq; }
+};
+
+namespace snb {
+// fp32 back end (mlp_f32.cu)
+size_t f32_workspace_floats(const snb_handle_s* h, int64_t M, int64_t B);
+size_t f32_bwd_scratch_floats(const snb_handle_s* h, int64_t M, int64_t B);
+int f32_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
+                const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, float* ws,
+                cudaStream_t st);
+int f32_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
+                 const float* shape_latent, const float* texture_latent, const float* sigma, const float* g_sigma,
+                 const float* g_rgb, const float* ws, float* scratch, float* g_xyz, float* g_viewdir,
+                 float* g_shape_latent, float* g_texture_latent, float* const* g_weights, cudaStream_t st);
+}  // namespace snb

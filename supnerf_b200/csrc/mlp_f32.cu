@@ -1,0 +1,358 @@
+// K2 / K2b, SNB_PREC_FP32 back end: the latent-conditioned decoder MLP in true fp32 (FFMA), layer by
+// layer, with the positional encoding, ReLU masks, latent column sums and weight gradients as small
+// fused kernels around one strided SGEMM.  This is the 1e-5 parity mode; the throughput mode is the
+// tcgen05 kernel in mlp_tc.cu.  Restructurings (exact, SURVEY §8(a')3): the latent layers are
+// evaluated once per object and enter as a per-object row offset of the next GEMM's A operand; the
+// `cat([y, PE(viewdir)])` layer is two GEMMs accumulating into one output.
+#include "common.cuh"
+#include "handle.h"
+#include "sgemm.cuh"
+#include <math.h>
+
+namespace snb {
+
+// ---- positional encoding (model_codenerf.py:4-10) -------------------------------------------------
+__global__ void pe_fwd_kernel(const float* __restrict__ x, int64_t M, int deg, float* __restrict__ out, int ld) {
+  const int64_t n = M * 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / 3;
+    const int a = (int)(i - m * 3);
+    const float v = x[i];
+    float* o = out + m * ld;
+    o[a] = v;
+    float sc = 1.f;
+    for (int f = 0; f < deg; ++f) {
+      const float y = sc * v;  // exact: power of two
+      o[3 + 3 * f + a] = sinf(y);
+      o[3 + 3 * deg + 3 * f + a] = cosf(y);
+      sc *= 2.f;
+    }
+  }
+}
+
+// g_x = g_0 + sum_f 2^f (g_sin,f cos(2^f x) - g_cos,f sin(2^f x))
+__global__ void pe_bwd_kernel(const float* __restrict__ g_pe, int ld, const float* __restrict__ x, int64_t M, int deg,
+                              float* __restrict__ g_x) {
+  const int64_t n = M * 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / 3;
+    const int a = (int)(i - m * 3);
+    const float v = x[i];
+    const float* gp = g_pe + m * ld;
+    float acc = gp[a], sc = 1.f;
+    for (int f = 0; f < deg; ++f) {
+      const float y = sc * v;
+      acc += sc * (gp[3 + 3 * f + a] * cosf(y) - gp[3 + 3 * deg + 3 * f + a] * sinf(y));
+      sc *= 2.f;
+    }
+    g_x[i] = acc;
+  }
+}
+
+// nn.Softplus() defaults: beta 1, threshold 20 (model_codenerf.py:30)
+__global__ void softplus_kernel(float* __restrict__ x, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    x[i] = v > 20.f ? v : log1pf(expf(v));
+  }
+}
+
+// d softplus / d pre = sigmoid(pre) = 1 - exp(-softplus(pre)); above the threshold it is 1 (1 - e^-20 rounds to 1).
+__global__ void softplus_bwd_kernel(const float* __restrict__ sigma, const float* __restrict__ g_sigma,
+                                    float* __restrict__ g_pre, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    g_pre[i] = g_sigma[i] * (-expm1f(-sigma[i]));
+}
+
+// In place: optionally accumulate the per-object column sums of g (BEFORE masking), then g *= (h > 0).
+// grid.x = objects * chunks_per_obj, block = 256 threads, each thread owns columns c, c+256, ...
+__global__ void __launch_bounds__(256) mask_colsum_kernel(float* __restrict__ g, const float* __restrict__ h, int ld,
+                                                         int width, int64_t rows_per_obj, int chunks_per_obj,
+                                                         int rows_per_chunk, float* __restrict__ colsum) {
+  const int64_t obj = blockIdx.x / chunks_per_obj;
+  const int chunk = blockIdx.x % chunks_per_obj;
+  const int64_t r0 = obj * rows_per_obj + (int64_t)chunk * rows_per_chunk;
+  int64_t r1 = r0 + rows_per_chunk;
+  const int64_t rend = (obj + 1) * rows_per_obj;
+  if (r1 > rend) r1 = rend;
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+    float s = 0.f;
+    for (int64_t r = r0; r < r1; ++r) {
+      const float v = g[r * ld + c];
+      s += v;
+      if (h != nullptr && !(h[r * ld + c] > 0.f)) g[r * ld + c] = 0.f;
+    }
+    if (colsum != nullptr) atomicAdd(colsum + obj * width + c, s);
+  }
+}
+
+// bias gradient: out[c] += sum_rows g[r][c]
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g, int ld, int width, int64_t rows,
+                                                    int rows_per_block, float* __restrict__ out) {
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+    float s = 0.f;
+    for (int64_t r = r0; r < r1; ++r) s += g[r * ld + c];
+    atomicAdd(out + c, s);
+  }
+}
+
+__global__ void fill_kernel(float* __restrict__ p, int64_t n, float v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+static inline int ew_grid(int64_t n) {
+  int64_t b = ceil_div(n, 256);
+  int64_t cap = (int64_t)sm_count() * 8;
+  if (b > cap) b = cap;
+  return (int)(b > 0 ? b : 1);
+}
+
+struct Bump {
+  float* base;
+  int64_t used = 0;
+  float* take(int64_t n) {
+    float* r = base ? base + used : nullptr;
+    used += (n + 3) & ~int64_t(3);
+    return r;
+  }
+};
+
+static inline int64_t al4(int64_t n) { return (n + 3) & ~int64_t(3); }
+
+// ---- workspace layout (CodeNeRF family) ---------------------------------------------------------------
+struct F32Layout {
+  int W, Bs, Bt, dx, dv, ldx, ldv;
+  int64_t total;
+  float *X0, *V, *E, *VV, *R;
+  float* H[17];   // H[0..Bs]
+  float* T[17];   // T[1..Bt]  (T[0] = VV)
+  float* ZS[17];  // ZS[1..Bs]  (B, W)
+  float* ZT[17];  // ZT[1..Bt]
+};
+
+static F32Layout make_layout(const snb_handle_s* h, int64_t M, int64_t B, float* ws) {
+  F32Layout L;
+  L.W = h->arch.W; L.Bs = h->arch.shape_blocks; L.Bt = h->arch.texture_blocks;
+  L.dx = h->d_xyz(); L.dv = h->d_dir();
+  L.ldx = (L.dx + 3) & ~3; L.ldv = (L.dv + 3) & ~3;
+  Bump b{ws};
+  L.X0 = b.take(M * L.ldx);
+  L.V = b.take(M * L.ldv);
+  for (int j = 0; j <= L.Bs; ++j) L.H[j] = b.take(M * L.W);
+  L.E = b.take(M * L.W);
+  L.VV = b.take(M * L.W);
+  L.T[0] = L.VV;
+  for (int j = 1; j <= L.Bt; ++j) L.T[j] = b.take(M * L.W);
+  L.R = b.take(M * (L.W / 2));
+  for (int j = 1; j <= L.Bs; ++j) L.ZS[j] = b.take(B * L.W);
+  for (int j = 1; j <= L.Bt; ++j) L.ZT[j] = b.take(B * L.W);
+  L.total = b.used;
+  return L;
+}
+
+size_t f32_workspace_floats(const snb_handle_s* h, int64_t M, int64_t B) {
+  return (size_t)make_layout(h, M, B, nullptr).total + 16;
+}
+
+size_t f32_bwd_scratch_floats(const snb_handle_s* h, int64_t M, int64_t B) {
+  const int W = h->arch.W;
+  const int ldx = (h->d_xyz() + 3) & ~3, ldv = (h->d_dir() + 3) & ~3;
+  return (size_t)(2 * al4(M * W) + al4(M * (W / 2)) + al4(M * ldx) + al4(M * ldv) + al4(M) +
+                  (h->arch.shape_blocks + h->arch.texture_blocks) * al4(B * W) + 16);
+}
+
+// Y = act((A [+ rowadd]) W^T + b [+ Y])
+static int fwd_linear(const float* A, int lda, int64_t M, int K, const float* Wt, int ldw, const float* bias, int N,
+                      float* Y, int ldy, int act, int accumulate, const float* rowadd, int64_t rpo, cudaStream_t st) {
+  GemmArgs g{};
+  g.A = A; g.sAi = lda; g.sAk = 1;
+  g.B = Wt; g.sBk = 1; g.sBj = ldw;
+  g.C = Y; g.ldc = ldy; g.M = M; g.N = N; g.K = K;
+  g.a_add = rowadd; g.a_add_ld = K; g.a_rows_per_obj = rpo > 0 ? rpo : 1;
+  g.bias = bias; g.accumulate = accumulate; g.act = act;
+  return launch_sgemm(g, true, true, st);
+}
+
+// dX = dY W  (dY: M x N(out), W: (out, in) with row stride ldw, dX: M x K(in))
+static int bwd_data(const float* dY, int ldy, int64_t M, int N_out, const float* Wt, int ldw, int K_in, float* dX,
+                    int ldx, int accumulate, cudaStream_t st) {
+  GemmArgs g{};
+  g.A = dY; g.sAi = ldy; g.sAk = 1;
+  g.B = Wt; g.sBk = ldw; g.sBj = 1;
+  g.C = dX; g.ldc = ldx; g.M = M; g.N = K_in; g.K = N_out;
+  g.accumulate = accumulate;
+  return launch_sgemm(g, true, false, st);
+}
+
+// dW (out x in, row stride ldw) += dY^T (X [+ rowadd]);  db += colsum dY.  dW/db must be zeroed by the caller.
+static int bwd_weight(const float* dY, int ldy, int64_t M, int N_out, const float* X, int ldx, int K_in, float* dW,
+                      int ldw, float* db, const float* rowadd, int64_t rpo, cudaStream_t st) {
+  if (dW != nullptr) {
+    GemmArgs g{};
+    g.A = dY; g.sAi = 1; g.sAk = ldy;
+    g.B = X; g.sBk = ldx; g.sBj = 1;
+    g.C = dW; g.ldc = ldw; g.M = N_out; g.N = K_in; g.K = M;
+    g.b_add = rowadd; g.b_add_ld = K_in; g.b_rows_per_obj = rpo > 0 ? rpo : 1;
+    g.k_split = 2048;
+    if (launch_sgemm(g, false, false, st)) return 1;
+  }
+  if (db != nullptr && M > 0) {
+    const int rpb = 512;
+    colsum_kernel<<<(unsigned)ceil_div(M, rpb), 256, 0, st>>>(dY, ldy, N_out, M, rpb, db);
+    SNB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+static int mask_colsum(float* g, const float* hmask, int ld, int width, int64_t M, int64_t B, float* colsum,
+                       cudaStream_t st) {
+  if (M == 0) return 0;
+  const int64_t rpo = M / B;
+  const int rows_per_chunk = 64;
+  const int chunks = (int)ceil_div(rpo, rows_per_chunk);
+  mask_colsum_kernel<<<(unsigned)(B * chunks), 256, 0, st>>>(g, hmask, ld, width, rpo, chunks, rows_per_chunk, colsum);
+  SNB_LAUNCH_CHECK();
+  return 0;
+}
+
+static int zero(float* p, int64_t n, cudaStream_t st) {
+  if (n == 0 || p == nullptr) return 0;
+  SNB_CHECK_CUDA(cudaMemsetAsync(p, 0, n * sizeof(float), st));
+  return 0;
+}
+
+#define TRY(x) do { if ((x) != 0) return 1; } while (0)
+
+int f32_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
+                const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, float* ws,
+                cudaStream_t st) {
+  SNB_REQUIRE(h->arch.arch == SNB_ARCH_CODENERF, "f32_forward: arch %d not handled here", h->arch.arch);
+  F32Layout L = make_layout(h, M, B, ws);
+  const int W = L.W, D = h->arch.latent_dim;
+  const int64_t rpo = M / B;
+  const auto& ly = h->layers;
+  pe_fwd_kernel<<<ew_grid(M * 3), 256, 0, st>>>(xyz, M, h->arch.num_xyz_freq, L.X0, L.ldx);
+  SNB_LAUNCH_CHECK();
+  pe_fwd_kernel<<<ew_grid(M * 3), 256, 0, st>>>(viewdir, M, h->arch.num_dir_freq, L.V, L.ldv);
+  SNB_LAUNCH_CHECK();
+  for (int j = 1; j <= L.Bs; ++j)  // shape_latent_layer_j once per object (model_codenerf.py:51)
+    TRY(fwd_linear(shape_latent, D, B, D, ly[h->iSL(j)].w, D, ly[h->iSL(j)].b, W, L.ZS[j], W, 1, 0, nullptr, 0, st));
+  for (int j = 1; j <= L.Bt; ++j)
+    TRY(fwd_linear(texture_latent, D, B, D, ly[h->iTL(j)].w, D, ly[h->iTL(j)].b, W, L.ZT[j], W, 1, 0, nullptr, 0, st));
+  TRY(fwd_linear(L.X0, L.ldx, M, L.dx, ly[h->iX].w, L.dx, ly[h->iX].b, W, L.H[0], W, 1, 0, nullptr, 0, st));
+  for (int j = 1; j <= L.Bs; ++j)
+    TRY(fwd_linear(L.H[j - 1], W, M, W, ly[h->iS(j)].w, W, ly[h->iS(j)].b, W, L.H[j], W, 1, 0, L.ZS[j], rpo, st));
+  TRY(fwd_linear(L.H[L.Bs], W, M, W, ly[h->iES].w, W, ly[h->iES].b, W, L.E, W, 0, 0, nullptr, 0, st));
+  TRY(fwd_linear(L.E, W, M, W, ly[h->iSG].w, W, ly[h->iSG].b, 1, sigma, 1, 0, 0, nullptr, 0, st));
+  softplus_kernel<<<ew_grid(M), 256, 0, st>>>(sigma, M);
+  SNB_LAUNCH_CHECK();
+  // encoding_viewdir on cat([E, PE(viewdir)]) (model_codenerf.py:56-57) as two accumulating GEMMs
+  TRY(fwd_linear(L.E, W, M, W, ly[h->iEV].w, W + L.dv, nullptr, W, L.VV, W, 0, 0, nullptr, 0, st));
+  TRY(fwd_linear(L.V, L.ldv, M, L.dv, ly[h->iEV].w + W, W + L.dv, ly[h->iEV].b, W, L.VV, W, 1, 1, nullptr, 0, st));
+  for (int j = 1; j <= L.Bt; ++j)
+    TRY(fwd_linear(L.T[j - 1], W, M, W, ly[h->iT(j)].w, W, ly[h->iT(j)].b, W, L.T[j], W, 1, 0, L.ZT[j], rpo, st));
+  TRY(fwd_linear(L.T[L.Bt], W, M, W, ly[h->iR0].w, W, ly[h->iR0].b, W / 2, L.R, W / 2, 1, 0, nullptr, 0, st));
+  TRY(fwd_linear(L.R, W / 2, M, W / 2, ly[h->iR2].w, W / 2, ly[h->iR2].b, 3, rgb, 3, 0, 0, nullptr, 0, st));
+  return 0;
+}
+
+int f32_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
+                 const float* shape_latent, const float* texture_latent, const float* sigma, const float* g_sigma,
+                 const float* g_rgb, const float* ws, float* scratch, float* g_xyz, float* g_viewdir,
+                 float* g_shape_latent, float* g_texture_latent, float* const* gw, cudaStream_t st) {
+  SNB_REQUIRE(h->arch.arch == SNB_ARCH_CODENERF, "f32_backward: arch %d not handled here", h->arch.arch);
+  F32Layout L = make_layout(h, M, B, const_cast<float*>(ws));
+  const int W = L.W, D = h->arch.latent_dim, W2 = W / 2;
+  const int64_t rpo = M / B;
+  const auto& ly = h->layers;
+  Bump sb{scratch};
+  float* dA = sb.take(M * W);
+  float* dB = sb.take(M * W);
+  float* dR = sb.take(M * W2);
+  float* dX0 = sb.take(M * L.ldx);
+  float* dV = sb.take(M * L.ldv);
+  float* gsp = sb.take(M);
+  float* dZ = sb.take((int64_t)(L.Bs + L.Bt) * al4(B * W));
+  auto dZS = [&](int j) { return dZ + (int64_t)(j - 1) * al4(B * W); };
+  auto dZT = [&](int j) { return dZ + (int64_t)(L.Bs + j - 1) * al4(B * W); };
+  auto GW = [&](int layer) -> float* { return gw ? gw[2 * layer] : nullptr; };
+  auto GB = [&](int layer) -> float* { return gw ? gw[2 * layer + 1] : nullptr; };
+  if (gw) {
+    for (size_t i = 0; i < ly.size(); ++i) {
+      TRY(zero(gw[2 * i], (int64_t)ly[i].out * ly[i].in, st));
+      TRY(zero(gw[2 * i + 1], ly[i].out, st));
+    }
+  }
+  TRY(zero(dZ, (int64_t)(L.Bs + L.Bt) * al4(B * W), st));
+
+  // rgb head: rgb = R W2^T + b2 ; R = relu(T_Bt W1^T + b1)
+  TRY(bwd_weight(g_rgb, 3, M, 3, L.R, W2, W2, GW(h->iR2), W2, GB(h->iR2), nullptr, 0, st));
+  TRY(bwd_data(g_rgb, 3, M, 3, ly[h->iR2].w, W2, W2, dR, W2, 0, st));
+  TRY(mask_colsum(dR, L.R, W2, W2, M, B, nullptr, st));
+  TRY(bwd_weight(dR, W2, M, W2, L.T[L.Bt], W, W, GW(h->iR0), W, GB(h->iR0), nullptr, 0, st));
+  float* cur = dA;   // gradient w.r.t. the OUTPUT of the layer being unwound
+  float* nxt = dB;
+  TRY(bwd_data(dR, W2, M, W2, ly[h->iR0].w, W, W, cur, W, 0, st));
+  // texture blocks: T_j = relu((T_{j-1} + ZT_j) Wj^T + bj)
+  for (int j = L.Bt; j >= 1; --j) {
+    TRY(mask_colsum(cur, L.T[j], W, W, M, B, nullptr, st));                       // -> grad of pre-activation
+    TRY(bwd_weight(cur, W, M, W, L.T[j - 1], W, W, GW(h->iT(j)), W, GB(h->iT(j)), L.ZT[j], rpo, st));
+    TRY(bwd_data(cur, W, M, W, ly[h->iT(j)].w, W, W, nxt, W, 0, st));             // grad of (T_{j-1} + ZT_j)
+    TRY(mask_colsum(nxt, nullptr, W, W, M, B, dZT(j), st));                       // latent grad = per-object column sum
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  // encoding_viewdir: VV = relu([E, V] Wv^T + bv)
+  TRY(mask_colsum(cur, L.VV, W, W, M, B, nullptr, st));
+  TRY(bwd_weight(cur, W, M, W, L.E, W, W, GW(h->iEV), W + L.dv, GB(h->iEV), nullptr, 0, st));
+  TRY(bwd_weight(cur, W, M, W, L.V, L.ldv, L.dv, gw ? GW(h->iEV) + W : nullptr, W + L.dv, nullptr, nullptr, 0, st));
+  if (g_viewdir) TRY(bwd_data(cur, W, M, W, ly[h->iEV].w + W, W + L.dv, L.dv, dV, L.ldv, 0, st));
+  TRY(bwd_data(cur, W, M, W, ly[h->iEV].w, W + L.dv, W, nxt, W, 0, st));          // dE (texture branch)
+  { float* t = cur; cur = nxt; nxt = t; }
+  // sigma head: sigma = softplus(E wσ + bσ)
+  softplus_bwd_kernel<<<ew_grid(M), 256, 0, st>>>(sigma, g_sigma, gsp, M);
+  SNB_LAUNCH_CHECK();
+  TRY(bwd_weight(gsp, 1, M, 1, L.E, W, W, GW(h->iSG), W, GB(h->iSG), nullptr, 0, st));
+  TRY(bwd_data(gsp, 1, M, 1, ly[h->iSG].w, W, W, cur, W, 1, st));                  // dE += gsp ⊗ wσ
+  // encoding_shape (no activation)
+  TRY(bwd_weight(cur, W, M, W, L.H[L.Bs], W, W, GW(h->iES), W, GB(h->iES), nullptr, 0, st));
+  TRY(bwd_data(cur, W, M, W, ly[h->iES].w, W, W, nxt, W, 0, st));
+  { float* t = cur; cur = nxt; nxt = t; }
+  for (int j = L.Bs; j >= 1; --j) {
+    TRY(mask_colsum(cur, L.H[j], W, W, M, B, nullptr, st));
+    TRY(bwd_weight(cur, W, M, W, L.H[j - 1], W, W, GW(h->iS(j)), W, GB(h->iS(j)), L.ZS[j], rpo, st));
+    TRY(bwd_data(cur, W, M, W, ly[h->iS(j)].w, W, W, nxt, W, 0, st));
+    TRY(mask_colsum(nxt, nullptr, W, W, M, B, dZS(j), st));
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  // encoding_xyz
+  TRY(mask_colsum(cur, L.H[0], W, W, M, B, nullptr, st));
+  TRY(bwd_weight(cur, W, M, W, L.X0, L.ldx, L.dx, GW(h->iX), L.dx, GB(h->iX), nullptr, 0, st));
+  if (g_xyz) {
+    TRY(bwd_data(cur, W, M, W, ly[h->iX].w, L.dx, L.dx, dX0, L.ldx, 0, st));
+    pe_bwd_kernel<<<ew_grid(M * 3), 256, 0, st>>>(dX0, L.ldx, xyz, M, h->arch.num_xyz_freq, g_xyz);
+    SNB_LAUNCH_CHECK();
+  }
+  if (g_viewdir) {
+    pe_bwd_kernel<<<ew_grid(M * 3), 256, 0, st>>>(dV, L.ldv, viewdir, M, h->arch.num_dir_freq, g_viewdir);
+    SNB_LAUNCH_CHECK();
+  }
+  // latent layers (per object): ZS_j = relu(latent Wsl_j^T + b)
+  if (g_shape_latent) TRY(zero(g_shape_latent, B * D, st));
+  if (g_texture_latent) TRY(zero(g_texture_latent, B * D, st));
+  for (int j = 1; j <= L.Bs; ++j) {
+    TRY(mask_colsum(dZS(j), L.ZS[j], W, W, B, B, nullptr, st));
+    TRY(bwd_weight(dZS(j), W, B, W, shape_latent, D, D, GW(h->iSL(j)), D, GB(h->iSL(j)), nullptr, 0, st));
+    if (g_shape_latent) TRY(bwd_data(dZS(j), W, B, W, ly[h->iSL(j)].w, D, D, g_shape_latent, D, 1, st));
+  }
+  for (int j = 1; j <= L.Bt; ++j) {
+    TRY(mask_colsum(dZT(j), L.ZT[j], W, W, B, B, nullptr, st));
+    TRY(bwd_weight(dZT(j), W, B, W, texture_latent, D, D, GW(h->iTL(j)), D, GB(h->iTL(j)), nullptr, 0, st));
+    if (g_texture_latent) TRY(bwd_data(dZT(j), W, B, W, ly[h->iTL(j)].w, D, D, g_texture_latent, D, 1, st));
+  }
+  return 0;
+}
+
+}  // namespace snb

@@ -1,0 +1,333 @@
+"""torch.autograd bindings of the C-ABI kernels.  Each Function cites the reference code it replaces.
+
+All tensors handed to the library are CUDA fp32 contiguous; outputs are fresh tensors attached to the
+autograd graph.  No function here has a CPU or eager-PyTorch fallback."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, f32c, ptr, require_cuda, stream_ptr
+
+WHITE_BKGD, SIGMA_RELU = 1, 2
+PREC = {"fp32": 0, "bf16": 1}
+
+
+# ---------------------------------------------------------------------------------------------------
+# K3 / K3b  — renderer.py:43-65, :355-379; utils.py:187-233
+# ---------------------------------------------------------------------------------------------------
+class _Composite(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sigma, rgb, z, rays_per_zrow, flags):
+        lib = _lib.load()
+        require_cuda(sigma, rgb, z)
+        sigma, rgb, z = f32c(sigma), f32c(rgb), f32c(z)
+        n, s = sigma.shape
+        o_rgb = torch.empty(n, 3, device=sigma.device, dtype=torch.float32)
+        o_dep = torch.empty(n, device=sigma.device, dtype=torch.float32)
+        o_acc = torch.empty(n, device=sigma.device, dtype=torch.float32)
+        with torch.cuda.device(sigma.device):
+            check(lib.snb_composite_fwd(ptr(sigma), ptr(rgb), ptr(z), rays_per_zrow, n, s, flags, ptr(o_rgb), ptr(o_dep),
+                                        ptr(o_acc), stream_ptr()), "snb_composite_fwd")
+        ctx.save_for_backward(sigma, rgb, z)
+        ctx.meta = (rays_per_zrow, flags)
+        return o_rgb, o_dep, o_acc
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_dep, g_acc):
+        lib = _lib.load()
+        sigma, rgb, z = ctx.saved_tensors
+        rays_per_zrow, flags = ctx.meta
+        n, s = sigma.shape
+        g_rgb = f32c(g_rgb) if g_rgb is not None else torch.zeros(n, 3, device=sigma.device)
+        g_dep = f32c(g_dep) if g_dep is not None else torch.zeros(n, device=sigma.device)
+        g_acc = f32c(g_acc) if g_acc is not None else torch.zeros(n, device=sigma.device)
+        g_sigma = torch.empty_like(sigma)
+        g_rgbs = torch.empty_like(rgb)
+        need_z = ctx.needs_input_grad[2]
+        g_z = torch.empty_like(sigma) if need_z else None
+        with torch.cuda.device(sigma.device):
+            check(lib.snb_composite_bwd(ptr(sigma), ptr(rgb), ptr(z), rays_per_zrow, n, s, flags, ptr(g_rgb), ptr(g_dep),
+                                        ptr(g_acc), ptr(g_sigma), ptr(g_rgbs), ptr(g_z), stream_ptr()), "snb_composite_bwd")
+        if need_z and z.shape[0] != n:  # shared rows: reduce the per-ray gradient onto the shared vector(s)
+            g_z = g_z.reshape(z.shape[0], rays_per_zrow, s).sum(1)
+        return g_sigma, g_rgbs, g_z, None, None
+
+
+def composite(sigma, rgb, z, white_bkgd, relu=True):
+    """sigma (N,S), rgb (N,S,3); z (N,S) per ray, (S,) shared, or (B,S) with N = B*n."""
+    n, s = sigma.shape
+    if z.dim() == 1:
+        zz, rpz = z.reshape(1, s), max(n, 1)
+    else:
+        zz, rpz = z, max(n // max(z.shape[0], 1), 1)
+    flags = (WHITE_BKGD if white_bkgd else 0) | (SIGMA_RELU if relu else 0)
+    rgb_o, dep, acc = _Composite.apply(sigma, rgb, zz, rpz, flags)
+    return rgb_o, dep, acc
+
+
+# ---------------------------------------------------------------------------------------------------
+# K1 / K1b — utils.py:107-151 (rays), :283-327 (slab), renderer.py:91-115 (box sampler), utils.py:154-167
+# ---------------------------------------------------------------------------------------------------
+class _GetRays(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, px, py, K, c2w):
+        lib = _lib.load()
+        require_cuda(px, py, K, c2w)
+        px, py, K, c2w = f32c(px), f32c(py), f32c(K), f32c(c2w)
+        n = px.numel()
+        ro = torch.empty(n, 3, device=px.device, dtype=torch.float32)
+        vd = torch.empty(n, 3, device=px.device, dtype=torch.float32)
+        with torch.cuda.device(px.device):
+            check(lib.snb_get_rays_fwd(ptr(px), ptr(py), n, ptr(K), ptr(c2w), ptr(ro), ptr(vd), stream_ptr()), "snb_get_rays_fwd")
+        ctx.save_for_backward(px, py, K, c2w)
+        return ro, vd
+
+    @staticmethod
+    def backward(ctx, g_ro, g_vd):
+        lib = _lib.load()
+        px, py, K, c2w = ctx.saved_tensors
+        n = px.numel()
+        g_ro = f32c(g_ro) if g_ro is not None else torch.zeros(n, 3, device=px.device)
+        g_vd = f32c(g_vd) if g_vd is not None else torch.zeros(n, 3, device=px.device)
+        g_c2w = torch.zeros(3, 4, device=px.device, dtype=torch.float32)
+        with torch.cuda.device(px.device):
+            check(lib.snb_get_rays_bwd(ptr(px), ptr(py), n, ptr(K), ptr(c2w), ptr(g_ro), ptr(g_vd), ptr(g_c2w), stream_ptr()),
+                  "snb_get_rays_bwd")
+        return None, None, None, g_c2w
+
+
+def get_rays_from_pixels(px, py, K, c2w):
+    return _GetRays.apply(px, py, K, c2w)
+
+
+class _RayBox(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ro, rd, amin, amax):
+        lib = _lib.load()
+        require_cuda(ro, rd, amin, amax)
+        ro, rd = f32c(ro), f32c(rd)
+        amin = f32c(amin) if amin is not None else None
+        amax = f32c(amax) if amax is not None else None
+        n = ro.shape[0]
+        tn = torch.empty(n, device=ro.device, dtype=torch.float32)
+        tf = torch.empty(n, device=ro.device, dtype=torch.float32)
+        hit = torch.empty(n, device=ro.device, dtype=torch.uint8)
+        with torch.cuda.device(ro.device):
+            check(lib.snb_ray_box_fwd(ptr(ro), ptr(rd), ptr(amin), ptr(amax), n, ptr(tn), ptr(tf), ptr(hit), stream_ptr()),
+                  "snb_ray_box_fwd")
+        ctx.save_for_backward(ro, rd, amin, amax)
+        hitb = hit.bool()
+        ctx.mark_non_differentiable(hitb)
+        return tn, tf, hitb
+
+    @staticmethod
+    def backward(ctx, g_tn, g_tf, _g_hit):
+        lib = _lib.load()
+        ro, rd, amin, amax = ctx.saved_tensors
+        n = ro.shape[0]
+        g_tn = f32c(g_tn) if g_tn is not None else torch.zeros(n, device=ro.device)
+        g_tf = f32c(g_tf) if g_tf is not None else torch.zeros(n, device=ro.device)
+        g_o, g_d = torch.empty_like(ro), torch.empty_like(rd)
+        g_min = torch.empty_like(ro) if amin is not None and ctx.needs_input_grad[2] else None
+        g_max = torch.empty_like(ro) if amax is not None and ctx.needs_input_grad[3] else None
+        with torch.cuda.device(ro.device):
+            check(lib.snb_ray_box_bwd(ptr(ro), ptr(rd), ptr(amin), ptr(amax), n, ptr(g_tn), ptr(g_tf), ptr(g_o), ptr(g_d),
+                                      ptr(g_min), ptr(g_max), stream_ptr()), "snb_ray_box_bwd")
+        return g_o, g_d, g_min, g_max
+
+
+def ray_box(ro, rd, amin=None, amax=None):
+    """Uncompacted (t_near, t_far, hit)."""
+    return _RayBox.apply(ro, rd, amin, amax)
+
+
+class _SampleBox(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rays_o, viewdir, z_steps, jitter, half_diag, aabb_half):
+        lib = _lib.load()
+        require_cuda(rays_o, viewdir, z_steps, jitter)
+        rays_o, viewdir, z_steps, jitter = f32c(rays_o), f32c(viewdir), f32c(z_steps), f32c(jitter)
+        n, s = jitter.shape
+        dev = rays_o.device
+        xyz = torch.empty(n, s, 3, device=dev, dtype=torch.float32)
+        vrep = torch.empty(n, s, 3, device=dev, dtype=torch.float32)
+        zv = torch.empty(n, s, device=dev, dtype=torch.float32)
+        hit = torch.empty(n, device=dev, dtype=torch.uint8)
+        h3 = (ctypes.c_float * 3)(*[float(v) for v in aabb_half])
+        with torch.cuda.device(dev):
+            check(lib.snb_sample_box_fwd(ptr(rays_o), ptr(viewdir), ptr(z_steps), ptr(jitter), n, s, float(half_diag), h3,
+                                         ptr(xyz), ptr(vrep), ptr(zv), ptr(hit), stream_ptr()), "snb_sample_box_fwd")
+        ctx.save_for_backward(rays_o, viewdir, z_steps, jitter)
+        ctx.meta = (float(half_diag), [float(v) for v in aabb_half])
+        hitb = hit.bool()
+        ctx.mark_non_differentiable(hitb)
+        return xyz, vrep, zv, hitb
+
+    @staticmethod
+    def backward(ctx, g_xyz, g_vrep, g_zv, _g_hit):
+        lib = _lib.load()
+        rays_o, viewdir, z_steps, jitter = ctx.saved_tensors
+        half_diag, half = ctx.meta
+        n, s = jitter.shape
+        g_xyz = f32c(g_xyz) if g_xyz is not None else None
+        g_vrep = f32c(g_vrep) if g_vrep is not None else None
+        g_zv = f32c(g_zv) if g_zv is not None else None
+        g_o, g_d = torch.empty_like(rays_o), torch.empty_like(viewdir)
+        h3 = (ctypes.c_float * 3)(*half)
+        with torch.cuda.device(rays_o.device):
+            check(lib.snb_sample_box_bwd(ptr(rays_o), ptr(viewdir), ptr(z_steps), ptr(jitter), n, s, half_diag, h3, ptr(g_xyz),
+                                         ptr(g_vrep), ptr(g_zv), ptr(g_o), ptr(g_d), stream_ptr()), "snb_sample_box_bwd")
+        return g_o, g_d, None, None, None, None
+
+
+def sample_box(rays_o, viewdir, z_steps, jitter, half_diag, aabb_half):
+    return _SampleBox.apply(rays_o, viewdir, z_steps, jitter, half_diag, aabb_half)
+
+
+class _SampleShell(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rays_o, viewdir, z, obj_diag, swap):
+        lib = _lib.load()
+        require_cuda(rays_o, viewdir, z)
+        rays_o, viewdir, z = f32c(rays_o), f32c(viewdir), f32c(z)
+        n, s = rays_o.shape[0], z.numel()
+        xyz = torch.empty(n, s, 3, device=rays_o.device, dtype=torch.float32)
+        vrep = torch.empty(n, s, 3, device=rays_o.device, dtype=torch.float32)
+        with torch.cuda.device(rays_o.device):
+            check(lib.snb_sample_shell_fwd(ptr(rays_o), ptr(viewdir), ptr(z), n, s, float(obj_diag), int(swap), ptr(xyz),
+                                           ptr(vrep), stream_ptr()), "snb_sample_shell_fwd")
+        ctx.save_for_backward(z)
+        ctx.meta = (n, s, float(obj_diag), int(swap))
+        return xyz, vrep
+
+    @staticmethod
+    def backward(ctx, g_xyz, g_vrep):
+        lib = _lib.load()
+        (z,) = ctx.saved_tensors
+        n, s, obj_diag, swap = ctx.meta
+        g_xyz = f32c(g_xyz) if g_xyz is not None else None
+        g_vrep = f32c(g_vrep) if g_vrep is not None else None
+        g_o = torch.empty(n, 3, device=z.device, dtype=torch.float32)
+        g_d = torch.empty(n, 3, device=z.device, dtype=torch.float32)
+        with torch.cuda.device(z.device):
+            check(lib.snb_sample_shell_bwd(ptr(z), n, s, obj_diag, swap, ptr(g_xyz), ptr(g_vrep), ptr(g_o), ptr(g_d),
+                                           stream_ptr()), "snb_sample_shell_bwd")
+        return g_o, g_d, None, None, None
+
+
+def sample_shell(rays_o, viewdir, z, obj_diag=1.0, shapenet_swap=False):
+    return _SampleShell.apply(rays_o, viewdir, z, obj_diag, shapenet_swap)
+
+
+# ---------------------------------------------------------------------------------------------------
+# K2 / K2b — model_codenerf.py:39-63 ≡ model_autorf.py:226-250 ≡ model_supnerf.py:241-269; model_autorf.py:156-186
+# ---------------------------------------------------------------------------------------------------
+class DecoderHandle:
+    """One C handle per (module, device): borrowed fp32 weight pointers + (bf16 mode) the packed images."""
+
+    def __init__(self, arch, shape_blocks, texture_blocks, W, latent_dim, num_xyz_freq, num_dir_freq):
+        lib = _lib.load()
+        self.arch = _lib.SnbArch(arch, shape_blocks, texture_blocks, W, latent_dim, num_xyz_freq, num_dir_freq)
+        self.h = ctypes.c_void_p()
+        check(lib.snb_create(ctypes.byref(self.h), ctypes.byref(self.arch)), "snb_create")
+        self.n_tensors = lib.snb_num_weight_tensors(self.h)
+        self._packed = None
+        self._packed_key = None
+        self._keep = None
+
+    def __del__(self):
+        try:
+            if self.h:
+                _lib.load().snb_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_weights(self, tensors):
+        lib = _lib.load()
+        assert len(tensors) == self.n_tensors, (len(tensors), self.n_tensors)
+        self._keep = [f32c(t.detach()) for t in tensors]
+        require_cuda(*self._keep)
+        arr = (ctypes.c_void_p * self.n_tensors)(*[t.data_ptr() for t in self._keep])
+        check(lib.snb_set_weights(self.h, arr, self.n_tensors), "snb_set_weights")
+
+    def ensure_packed(self, tensors):
+        """bf16 mode: (re)pack when a parameter was replaced or modified in place."""
+        lib = _lib.load()
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        if key == self._packed_key and self._packed is not None:
+            return
+        nbytes = lib.snb_packed_bytes(self.h)
+        dev = self._keep[0].device
+        if self._packed is None or self._packed.numel() < nbytes or self._packed.device != dev:
+            self._packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.snb_pack_weights(self.h, ptr(self._packed), stream_ptr()), "snb_pack_weights")
+        self._packed_key = key
+
+
+class _Decoder(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, handle, precision, n_objs, xyz, viewdir, shape_latent, texture_latent, *weights):
+        lib = _lib.load()
+        require_cuda(xyz, viewdir, shape_latent, texture_latent)
+        xyz, viewdir = f32c(xyz), f32c(viewdir)
+        shape_latent, texture_latent = f32c(shape_latent), f32c(texture_latent)
+        m = xyz.numel() // 3
+        dev = xyz.device
+        handle.set_weights(weights)
+        if precision == PREC["bf16"]:
+            handle.ensure_packed(weights)
+        ws = torch.empty(lib.snb_mlp_workspace_bytes(handle.h, m, n_objs, precision), dtype=torch.uint8, device=dev)
+        sigma = torch.empty(m, device=dev, dtype=torch.float32)
+        rgb = torch.empty(m, 3, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            check(lib.snb_mlp_fwd(handle.h, precision, ptr(xyz), ptr(viewdir), m, n_objs, ptr(shape_latent), ptr(texture_latent),
+                                  ptr(sigma), ptr(rgb), ptr(ws), stream_ptr()), "snb_mlp_fwd")
+        ctx.save_for_backward(xyz, viewdir, shape_latent, texture_latent, sigma, ws, *weights)
+        ctx.meta = (handle, precision, n_objs)
+        return sigma, rgb
+
+    @staticmethod
+    def backward(ctx, g_sigma, g_rgb):
+        lib = _lib.load()
+        xyz, viewdir, shape_latent, texture_latent, sigma, ws, *weights = ctx.saved_tensors
+        handle, precision, n_objs = ctx.meta
+        m = xyz.numel() // 3
+        dev = xyz.device
+        g_sigma = f32c(g_sigma) if g_sigma is not None else torch.zeros(m, device=dev)
+        g_rgb = f32c(g_rgb) if g_rgb is not None else torch.zeros(m, 3, device=dev)
+        need = ctx.needs_input_grad
+        g_xyz = torch.empty_like(xyz) if need[3] else None
+        g_vd = torch.empty_like(viewdir) if need[4] else None
+        g_sl = torch.empty_like(shape_latent)
+        g_tl = torch.empty_like(texture_latent)
+        need_w = any(need[7:])
+        gws, gw_arr = None, None
+        if need_w:
+            gws = [torch.empty_like(w, dtype=torch.float32).contiguous() for w in weights]
+            gw_arr = (ctypes.c_void_p * len(gws))(*[g.data_ptr() for g in gws])
+        handle.set_weights(weights)
+        scratch = torch.empty(lib.snb_mlp_bwd_scratch_bytes(handle.h, m, n_objs, precision), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.snb_mlp_bwd(handle.h, precision, ptr(xyz), ptr(viewdir), m, n_objs, ptr(shape_latent), ptr(texture_latent),
+                                  ptr(sigma), ptr(g_sigma), ptr(g_rgb), ptr(ws), ptr(scratch), ptr(g_xyz), ptr(g_vd), ptr(g_sl),
+                                  ptr(g_tl), gw_arr, stream_ptr()), "snb_mlp_bwd")
+        out_w = tuple(gws) if need_w else tuple(None for _ in weights)
+        return (None, None, None, g_xyz, g_vd, g_sl if need[5] else None, g_tl if need[6] else None) + out_w
+
+
+def decoder(handle, precision, xyz, viewdir, shape_latent, texture_latent, weights):
+    n_objs = shape_latent.shape[0]
+    return _Decoder.apply(handle, PREC[precision] if isinstance(precision, str) else precision, n_objs, xyz, viewdir,
+                          shape_latent, texture_latent, *weights)
+
+
+def box_constants(obj_sz):
+    """renderer.py:92-100: diag and the AABB half extents (l,w,h)/diag, rounded to float32 on the host."""
+    obj_sz = np.asarray(obj_sz)
+    diag = np.linalg.norm(obj_sz).astype(np.float32)
+    w, l, h = obj_sz
+    half = np.asarray([l / diag, w / diag, h / diag]).astype(np.float32)
+    return diag, half

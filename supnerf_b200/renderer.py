@@ -1,0 +1,204 @@
+"""Drop-in for the reference's ``src/renderer.py``: ``NeRFRenderer`` (same constructor, methods, argument
+orders and return tuples), ``volume_rendering3`` and ``render_rays_v3``.  Ray generation, the ray/AABB
+slab test, stratified sampling, the decoder and the compositing all run in the sm_100a kernels of
+libsupnerf_b200.so and stay differentiable to the pose, the latents and the weights."""
+import random
+
+import numpy as np
+import torch
+
+from . import ops
+from . import utils as U
+from .utils import get_rays, get_rays_specified, ray_box_intersection, ray_box_intersection_tensor  # noqa: F401
+
+
+class NeRFRenderer(torch.nn.Module):
+    def __init__(self, n_samples=64, noise_std=0.0, white_bkgd=True):
+        """renderer.py:16-25 (noise_std is stored and never used, as in the reference)."""
+        super().__init__()
+        self.n_samples = n_samples
+        self.noise_std = noise_std
+        self.white_bkgd = white_bkgd
+
+    def sample_from_ray(self, rays):
+        """renderer.py:27-41."""
+        return U.sample_from_rays_v2(rays, self.n_samples)
+
+    def volume_render(self, sigmas, rgbs, z_vals):
+        """renderer.py:43-65: sigmas (N,S), rgbs (N,S,3), z_vals (N,S)."""
+        return U._composite_any(sigmas, rgbs, z_vals, self.white_bkgd, True)
+
+    def volume_render_batch(self, sigmas, rgbs, z_vals):
+        """renderer.py:67-89: sigmas (B,n,S[,1]), rgbs (B,n,S,3), z_vals (B,n,S).  With white_bkgd the reference sums
+        the pixel alpha over the wrong dimension (renderer.py:86, only shape-valid when n == S); that branch is
+        reproduced literally on top of the kernel's black-background result."""
+        rgb, dep, acc = U._composite_any(sigmas, rgbs, z_vals, False, True)
+        dep = dep.unsqueeze(-1)  # renderer.py:82 keeps a trailing 1
+        if self.white_bkgd:
+            s = sigmas.squeeze(-1) if sigmas.dim() == rgbs.dim() else sigmas
+            deltas = torch.cat([z_vals[..., 1:] - z_vals[..., :-1], torch.ones_like(z_vals[..., :1]) * 1e10], -1)
+            alphas = 1 - torch.exp(-torch.relu(s) * deltas)
+            trans = torch.cat([torch.ones_like(alphas[..., :1]), 1 - alphas + 1e-10], -1)
+            weights = alphas * torch.cumprod(trans, -1)[..., :-1]
+            pix_alpha = weights.sum(dim=1)
+            rgb = rgb + 1 - pix_alpha.unsqueeze(-1)
+        return rgb, dep, acc
+
+    def prepare_sampled_rays(self, rays_o, viewdir, obj_sz):
+        """renderer.py:91-115 -> xyz (N,S,3), viewdir (N,S,3), z_vals (N,S), intersect (N,) bool."""
+        diag, half = ops.box_constants(obj_sz)
+        dev = U._device_of(rays_o, viewdir)
+        n = rays_o.shape[0]
+        step = 1.0 / self.n_samples
+        z_steps = torch.linspace(0, 1 - step, self.n_samples, device=dev)
+        jitter = torch.rand_like(z_steps.unsqueeze(0).repeat(n, 1))  # same call/shape as renderer.py:39-40
+        xyz, vd, z_vals, hit = ops.sample_box(rays_o.to(dev), viewdir.to(dev), z_steps, jitter, diag / 2, half)
+        if not rays_o.is_cuda:
+            xyz, vd, z_vals, hit = xyz.to(rays_o.device), vd.to(rays_o.device), z_vals.to(rays_o.device), hit.to(rays_o.device)
+        return xyz, vd, z_vals, hit
+
+    def _decode_and_render(self, model, device, xyz, viewdir, z_vals, shapecode, texturecode, kitti2nusc):
+        if kitti2nusc:
+            xyz, viewdir = U._kitti2nusc(xyz, viewdir, device)
+        sigmas, rgbs = model(xyz.to(device), viewdir.to(device), shapecode, texturecode)
+        return self.volume_render(sigmas.squeeze(), rgbs, z_vals.to(device))
+
+    def render_rays(self, model, device, img, mask_occ, cam_pose, obj_sz, K, roi, shapecode, texturecode,
+                    kitti2nusc=False, im_sz=64, n_rays=None):
+        """renderer.py:117-167."""
+        rays_o, viewdir = get_rays(K, cam_pose, roi, uv_steps=[im_sz, im_sz])
+        img, mask_occ = U._resize_targets(img, mask_occ, im_sz)
+        rgb_tgt = img.reshape(-1, 3).to(device)
+        occ_pixels = mask_occ.reshape(-1, 1).to(device)
+        if n_rays is not None:
+            n_rays = np.minimum(rays_o.shape[0], n_rays)
+            random_ray_ids = np.random.permutation(rays_o.shape[0])[:n_rays]
+            rays_o = rays_o[random_ray_ids]
+            viewdir = viewdir[random_ray_ids]
+            rgb_tgt = rgb_tgt[random_ray_ids]
+            occ_pixels = occ_pixels[random_ray_ids]
+        xyz, viewdir, z_vals, intersect = self.prepare_sampled_rays(rays_o.to(device), viewdir.to(device), obj_sz)
+        rgb_rays, depth_rays, acc_trans_rays = self._decode_and_render(model, device, xyz, viewdir, z_vals, shapecode,
+                                                                       texturecode, kitti2nusc)
+        return rgb_rays, depth_rays, acc_trans_rays, rgb_tgt, occ_pixels
+
+    def render_rays_specified(self, model, device, img, mask_occ, cam_pose, obj_sz, K, roi, x_vec, y_vec, shapecode,
+                              texturecode, kitti2nusc=False):
+        """renderer.py:169-201."""
+        rays_o, viewdir = get_rays_specified(K, cam_pose, x_vec + roi[0].numpy(), y_vec + roi[1].numpy())
+        rgb_tgt = img[y_vec, x_vec, :].to(device)
+        occ_pixels = mask_occ[y_vec, x_vec, :].to(device)
+        xyz, viewdir, z_vals, intersect = self.prepare_sampled_rays(rays_o.to(device), viewdir.to(device), obj_sz)
+        rgb_rays, depth_rays, acc_trans_rays = self._decode_and_render(model, device, xyz, viewdir, z_vals, shapecode,
+                                                                       texturecode, kitti2nusc)
+        return rgb_rays, depth_rays, acc_trans_rays, rgb_tgt, occ_pixels
+
+    def prepare_pixel_samples(self, img, mask_occ, cam_pose, obj_sz, K, roi, n_rays, im_sz=None):
+        """renderer.py:203-236."""
+        if im_sz is None:
+            rays_o, viewdir = get_rays(K, cam_pose, roi)
+        else:
+            rays_o, viewdir = get_rays(K, cam_pose, roi, uv_steps=[im_sz, im_sz])
+            img, mask_occ = U._resize_targets(img, mask_occ, im_sz)
+        n_rays = np.minimum(rays_o.shape[0], n_rays)
+        random_ray_ids = np.random.permutation(rays_o.shape[0])[:n_rays]
+        rays_o = rays_o[random_ray_ids]
+        viewdir = viewdir[random_ray_ids]
+        rgb_tgt = img.reshape(-1, 3)[random_ray_ids]
+        occ_pixels = mask_occ.reshape(-1, 1)[random_ray_ids]
+        xyz, viewdir, z_vals, intersect = self.prepare_sampled_rays(rays_o, viewdir, obj_sz)
+        return xyz, viewdir, z_vals, rgb_tgt, occ_pixels
+
+    def render_full_img(self, model, device, cam_pose, obj_sz, K, roi, shapecode, texturecode, out_depth=False,
+                        debug_occ=False, kitti2nusc=False):
+        """renderer.py:238-294."""
+        rays_o, viewdir = get_rays(K, cam_pose, roi)
+        xyz, viewdir, z_vals, intersect = self.prepare_sampled_rays(rays_o.to(device), viewdir.to(device), obj_sz)
+        if kitti2nusc:
+            xyz, viewdir = U._kitti2nusc(xyz, viewdir, device)
+        generated_img, generated_depth, generated_acc_trans = [], [], []
+        sample_step = int(np.maximum(int(roi[2]) - int(roi[0]), int(roi[3]) - int(roi[1])))
+        for i in range(0, xyz.shape[0], sample_step):
+            sigmas, rgbs = model(xyz[i:i + sample_step].to(device), viewdir[i:i + sample_step].to(device), shapecode,
+                                 texturecode)
+            rgb_rays, depth_rays, acc_trans_rays = self.volume_render(sigmas.squeeze(), rgbs, z_vals[i:i + sample_step].to(device))
+            generated_img.append(rgb_rays)
+            if out_depth:
+                generated_depth.append(depth_rays)
+            if debug_occ:
+                generated_acc_trans.append(acc_trans_rays)
+        h, w = int(roi[3]) - int(roi[1]), int(roi[2]) - int(roi[0])
+        generated_img = torch.cat(generated_img).reshape(h, w, 3)
+        if debug_occ:
+            import cv2
+            acc = torch.cat(generated_acc_trans).reshape(h, w)
+            cv2.imshow('est_occ', ((torch.ones_like(acc) - acc).cpu().numpy() * 255).astype(np.uint8))
+            cv2.waitKey()
+        if out_depth:
+            return generated_img, torch.cat(generated_depth).reshape(h, w)
+        return generated_img
+
+    def render_virtual_imgs(self, model, device, obj_sz, K, shapecode, texturecode, radius=40., tilt=np.pi / 6,
+                            pan_num=8, img_sz=128, kitti2nusc=False):
+        """renderer.py:296-352 (visualisation helper)."""
+        x_min, x_max = K[0, 2] - img_sz / 2, K[0, 2] + img_sz / 2
+        y_min, y_max = K[1, 2] - img_sz / 2, K[1, 2] + img_sz / 2
+        roi = np.asarray([x_min, y_min, x_max, y_max]).astype(np.int64)
+        out = []
+        for cam_pose in U.virtual_view_poses(radius, tilt, pan_num):
+            img = self.render_full_img(model, device, cam_pose, obj_sz, K, roi, shapecode, texturecode, kitti2nusc=kitti2nusc)
+            out.append(U._draw_axes(img, cam_pose, K, img_sz))
+        return out
+
+
+def volume_rendering3(sigmas, rgbs, z_vals, white_bkgd=False):
+    """renderer.py:355-379: sigmas (N,S,1), rgbs (N,S,3), z_vals (N,S)."""
+    return U._composite_any(sigmas, rgbs, z_vals, white_bkgd, True)
+
+
+def render_rays_v3(model, device, img, mask_occ, cam_pose, obj_wlh, K, roi, n_samples, shapecode, texturecode,
+                   shapenet_obj_cood, sym_aug, kitti2nusc=False, im_sz=64, n_rays=None, adjust_scale=1.0):
+    """renderer.py:382-473.  As in the reference the slab test runs on DETACHED rays (renderer.py:425-432: numpy
+    copies), so near/far carry no pose gradient; and, as there, the sampler uses a default NeRFRenderer()
+    (renderer.py:394), i.e. 64 strata whatever ``n_samples`` says — viewdir is repeated ``n_samples`` times
+    (renderer.py:436), so the two must agree for the shapes to line up."""
+    renderer = NeRFRenderer()
+    rays_o, viewdir = get_rays(K, cam_pose, roi, uv_steps=[im_sz, im_sz])
+    img, mask_occ = U._resize_targets(img, mask_occ, im_sz)
+    rgb_tgt = img.reshape(-1, 3).to(device)
+    occ_pixels = mask_occ.reshape(-1, 1).to(device)
+    if n_rays is not None:
+        n_rays = np.minimum(rays_o.shape[0], n_rays)
+        random_ray_ids = np.random.permutation(rays_o.shape[0])[:n_rays]
+        rays_o = rays_o[random_ray_ids]
+        viewdir = viewdir[random_ray_ids]
+        rgb_tgt = rgb_tgt[random_ray_ids]
+        occ_pixels = occ_pixels[random_ray_ids]
+    obj_diag = np.linalg.norm(obj_wlh).astype(np.float32)
+    obj_w, obj_l, obj_h = obj_wlh
+    # the reference builds the AABB in float64 here (no .astype(np.float32), renderer.py:419-422) and divides the
+    # float32 origins by the float32 half diagonal; the slab test then runs in float64 on the host.  The kernel
+    # evaluates it in fp32 with the fp32-rounded box: identical hit masks except for rays within 1 ulp of an edge.
+    half = np.asarray([obj_l / obj_diag, obj_w / obj_diag, obj_h / obj_diag]).astype(np.float32)
+    ro_d = rays_o.detach().to(device) / (obj_diag / 2)
+    vd_d = viewdir.detach().to(device)
+    amax = torch.from_numpy(half).to(device).reshape(1, 3).repeat(ro_d.shape[0], 1)
+    tn, tf, hit = ops.ray_box(ro_d, vd_d, -amax, amax)
+    minus1 = torch.full_like(tn, -1)
+    bounds = torch.stack([torch.where(hit, tn, minus1), torch.where(hit, tf, minus1)], -1)
+    rays = torch.concat([rays_o.to(device) / (obj_diag / 2), viewdir.to(device), bounds], -1)
+    z_coarse = renderer.sample_from_ray(rays)
+    xyz = rays[:, None, :3] + z_coarse[:, :, None] * rays[:, None, 3:6]
+    viewdir = viewdir.to(device).unsqueeze(-2).repeat(1, n_samples, 1)
+    z_vals = torch.norm((xyz - rays[:, None, :3]) * (obj_diag / 2), p=2, dim=-1)
+    xyz = xyz * adjust_scale
+    if sym_aug and random.uniform(0, 1) > 0.5:
+        xyz = xyz * xyz.new_tensor([1., -1., 1.])
+        viewdir = viewdir * viewdir.new_tensor([1., -1., 1.])
+    if kitti2nusc:
+        xyz, viewdir = U._kitti2nusc(xyz, viewdir, device)
+    if shapenet_obj_cood:
+        xyz, viewdir = U._swap(xyz), U._swap(viewdir)
+    sigmas, rgbs = model(xyz.to(device), viewdir.to(device), shapecode, texturecode)
+    rgb_rays, depth_rays, acc_trans_rays = volume_rendering3(sigmas, rgbs, z_vals.to(device))
+    return rgb_rays, depth_rays, acc_trans_rays, rgb_tgt, occ_pixels

@@ -1,0 +1,341 @@
+"""Drop-in for the render half of the reference's ``src/utils.py`` (lines 94-672): same function names,
+positional orders, defaults and return tuples; the arithmetic runs in the sm_100a kernels of
+libsupnerf_b200.so.  Host-side glue the reference also does on the host (target resize with torchvision,
+the numpy ray permutation, the python-float near/far) is kept as is, because it defines the RNG
+consumption and rounding the results are compared on.
+"""
+import random
+
+import numpy as np
+import torch
+from torchvision.transforms import Resize
+
+from . import ops
+
+
+def _device_of(*ts):
+    for t in ts:
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            return t.device
+    if not torch.cuda.is_available():
+        raise RuntimeError("supnerf_b200 needs a CUDA device (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _pixel_grid(roi, uv_steps=None):
+    """utils.py:121-128: torch.linspace grid, row-major (v outer, u inner), built on the host like the reference."""
+    x0, y0, x1, y1 = [int(v) for v in roi]
+    if uv_steps is not None:
+        us = torch.linspace(x0, x1 - 1, int(uv_steps[0]))
+        vs = torch.linspace(y0, y1 - 1, int(uv_steps[1]))
+    else:
+        us = torch.linspace(x0, x1 - 1, x1 - x0)
+        vs = torch.linspace(y0, y1 - 1, y1 - y0)
+    px = us.unsqueeze(0).expand(vs.numel(), us.numel()).reshape(-1)
+    py = vs.unsqueeze(1).expand(vs.numel(), us.numel()).reshape(-1)
+    return px, py
+
+
+def _rays(K, c2w, px, py):
+    dev = _device_of(c2w, K)
+    ro, vd = ops.get_rays_from_pixels(px.to(dev, torch.float32), py.to(dev, torch.float32), K.to(dev), c2w.to(dev))
+    if not c2w.is_cuda:  # keep the reference's device semantics: rays live where the pose lives
+        ro, vd = ro.to(c2w.device), vd.to(c2w.device)
+    return ro, vd
+
+
+def get_rays(K, c2w, roi, uv_steps=None):
+    """utils.py:107-135."""
+    px, py = _pixel_grid(roi, uv_steps)
+    return _rays(K, c2w, px, py)
+
+
+def get_rays_specified(K, c2w, x_vec, y_vec):
+    """utils.py:138-151."""
+    px = torch.from_numpy(np.asarray(x_vec)).t().reshape(-1)
+    py = torch.from_numpy(np.asarray(y_vec)).t().reshape(-1)
+    return _rays(K, c2w, px, py)
+
+
+def sample_from_rays(ro, vd, near, far, N_samples, z_fixed=False):
+    """utils.py:154-167.  The shared z vector is built on the host with the same torch calls (CPU
+    generator) as the reference; the (N,S,3) expansion is the shell-sampler kernel."""
+    if z_fixed:
+        z_vals = torch.linspace(near, far, N_samples).type_as(ro)
+    else:
+        dist = (far - near) / (2 * N_samples)
+        z_vals = torch.linspace(near + dist, far - dist, N_samples).type_as(ro)
+        z_vals += (torch.rand(N_samples) * (far - near) / (2 * N_samples)).type_as(ro)
+    dev = _device_of(ro, vd)
+    xyz, vdr = ops.sample_shell(ro.to(dev), vd.to(dev), z_vals.to(dev), 1.0, False)
+    if not ro.is_cuda:
+        xyz, vdr = xyz.to(ro.device), vdr.to(ro.device)
+    return xyz, vdr, z_vals
+
+
+def sample_from_rays_v2(rays, n_samples):
+    """utils.py:170-184 (the per-ray stratified sampler; inside prepare_sampled_rays it is fused into the
+    box-sampler kernel, standalone it is three tiny elementwise ops on the rays' device)."""
+    device = rays.device
+    near, far = rays[:, -2:-1], rays[:, -1:]
+    step = 1.0 / n_samples
+    B = rays.shape[0]
+    z_steps = torch.linspace(0, 1 - step, n_samples, device=device)
+    z_steps = z_steps.unsqueeze(0).repeat(B, 1)
+    z_steps += torch.rand_like(z_steps) * step
+    return near * (1 - z_steps) + far * z_steps
+
+
+def _composite_any(sigmas, rgbs, z_vals, white_bkgd, relu):
+    dev = _device_of(sigmas, rgbs, z_vals)
+    s = sigmas.to(dev)
+    if s.dim() >= 2 and s.shape[-1] == 1 and s.dim() == rgbs.dim():
+        s = s.squeeze(-1)
+    lead = s.shape[:-1]
+    S = s.shape[-1]
+    rgb, dep, acc = ops.composite(s.reshape(-1, S), rgbs.to(dev).reshape(-1, S, 3), z_vals.to(dev), white_bkgd, relu)
+    out = rgb.reshape(*lead, 3), dep.reshape(*lead), acc.reshape(*lead)
+    if not sigmas.is_cuda:
+        out = tuple(o.to(sigmas.device) for o in out)
+    return out
+
+
+def volume_rendering(sigmas, rgbs, z_vals):
+    """utils.py:187-199 (no relu on sigma, no accumulated transmittance returned)."""
+    rgb, dep, _ = _composite_any(sigmas, rgbs, z_vals, False, False)
+    return rgb, dep
+
+
+def volume_rendering2(sigmas, rgbs, z_vals):
+    """utils.py:202-217: sigmas (N,S,1), rgbs (N,S,3), z_vals (S,)."""
+    return _composite_any(sigmas, rgbs, z_vals, False, True)
+
+
+def volume_rendering_batch(sigmas, rgbs, z_vals):
+    """utils.py:220-233: sigmas (B,n,S,1), rgbs (B,n,S,3), z_vals (B,S)."""
+    return _composite_any(sigmas, rgbs, z_vals, False, True)
+
+
+def ray_box_intersection_tensor(ray_o, ray_d, aabb_min=None, aabb_max=None):
+    """utils.py:283-327: returns (z_in[hit], z_out[hit], hit)."""
+    if ray_o.shape[0] == 0:
+        return None, None, None
+    dev = _device_of(ray_o, ray_d)
+    amin = aabb_min.to(dev) if aabb_min is not None else None
+    amax = aabb_max.to(dev) if aabb_max is not None else None
+    if (amin is None) != (amax is None):
+        amin = amin if amin is not None else torch.full_like(ray_o, -1.).to(dev)
+        amax = amax if amax is not None else torch.full_like(ray_o, 1.).to(dev)
+    tn, tf, hit = ops.ray_box(ray_o.to(dev), ray_d.to(dev), amin, amax)
+    z_in, z_out = tn[hit], tf[hit]
+    if not ray_o.is_cuda:
+        z_in, z_out, hit = z_in.to(ray_o.device), z_out.to(ray_o.device), hit.to(ray_o.device)
+    return z_in, z_out, hit
+
+
+def ray_box_intersection(ray_o, ray_d, aabb_min=None, aabb_max=None):
+    """utils.py:236-280 — numpy in, numpy out (the reference calls it on detached host copies); the slab
+    test itself runs in the same kernel as the tensor version."""
+    ray_o = np.asarray(ray_o)
+    if ray_o.shape[0] == 0:
+        return None, None, None
+    dev = _device_of()
+    t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    out_dtype = np.result_type(ray_o.dtype, np.asarray(ray_d).dtype)
+    z_in, z_out, hit = ray_box_intersection_tensor(t(ray_o), t(ray_d), t(aabb_min), t(aabb_max))
+    return z_in.cpu().numpy().astype(out_dtype), z_out.cpu().numpy().astype(out_dtype), hit.cpu().numpy()
+
+
+def _resize_targets(img, mask_occ, im_sz):
+    """utils.py:448-453 (identical torchvision calls: they define rgb_tgt / occ_pixels)."""
+    img = img.unsqueeze(0).permute((0, 3, 1, 2))
+    img = Resize((im_sz, im_sz))(img)
+    img = img.permute((0, 2, 3, 1))
+    mask_occ = mask_occ.unsqueeze(0).permute((0, 3, 1, 2))
+    mask_occ = Resize((im_sz, im_sz))(mask_occ).type(torch.int32).type(torch.float32)
+    mask_occ = mask_occ.permute((0, 2, 3, 1))
+    return img, mask_occ
+
+
+def _shell_near_far(cam_pose, obj_diag):
+    n = np.linalg.norm(cam_pose[:, -1].tolist())
+    return n - obj_diag / 2, n + obj_diag / 2
+
+
+def _kitti2nusc(xyz, viewdir, device):
+    R_x = torch.tensor([[1., 0., 0.], [0., 0., 1.], [0., -1., 0.]], dtype=torch.float32).view(1, 1, 3, 3).to(device)
+    xyz = (R_x @ xyz.unsqueeze(-1)).squeeze(-1)
+    viewdir = (R_x @ viewdir.unsqueeze(-1)).squeeze(-1)
+    return xyz, viewdir
+
+
+def _swap(x):
+    x = x[:, :, [1, 0, 2]]
+    x[:, :, 0] *= (-1)
+    return x
+
+
+def _shell_samples(rays_o, viewdir, near, far, n_samples, obj_diag, shapenet_obj_cood, sym_aug, kitti2nusc, device):
+    """sample_from_rays + `xyz /= obj_diag` + sym_aug + kitti2nusc + shapenet swap (utils.py:471-495).
+    The common case (no sym flip, no kitti2nusc) is ONE kernel; the rare switches fall to a few torch ops
+    applied in the reference's order."""
+    dist = (far - near) / (2 * n_samples)
+    z_vals = torch.linspace(near + dist, far - dist, n_samples).type_as(rays_o)
+    z_vals += (torch.rand(n_samples) * (far - near) / (2 * n_samples)).type_as(rays_o)
+    z_dev = z_vals.to(device)
+    flip = bool(sym_aug) and random.uniform(0, 1) > 0.5
+    fused_swap = bool(shapenet_obj_cood) and not flip and not kitti2nusc
+    xyz, vd = ops.sample_shell(rays_o.to(device), viewdir.to(device), z_dev, float(obj_diag), fused_swap)
+    if flip:
+        xyz = xyz * xyz.new_tensor([1., -1., 1.])
+        vd = vd * vd.new_tensor([1., -1., 1.])
+    if kitti2nusc:
+        xyz, vd = _kitti2nusc(xyz, vd, device)
+    if shapenet_obj_cood and not fused_swap:
+        xyz, vd = _swap(xyz), _swap(vd)
+    return xyz, vd, z_dev
+
+
+def prepare_pixel_samples(img, mask_occ, cam_pose, obj_diag, K, roi, n_rays, n_samples, shapenet_obj_cood, sym_aug, im_sz=None):
+    """utils.py:330-377."""
+    near, far = _shell_near_far(cam_pose, obj_diag)
+    if im_sz is None:
+        rays_o, viewdir = get_rays(K, cam_pose, roi)
+    else:
+        rays_o, viewdir = get_rays(K, cam_pose, roi, uv_steps=[im_sz, im_sz])
+        img, mask_occ = _resize_targets(img, mask_occ, im_sz)
+    n_rays = np.minimum(rays_o.shape[0], n_rays)
+    random_ray_ids = np.random.permutation(rays_o.shape[0])[:n_rays]
+    rays_o = rays_o[random_ray_ids]
+    viewdir = viewdir[random_ray_ids]
+    rgb_tgt = img.reshape(-1, 3)[random_ray_ids]
+    occ_pixels = mask_occ.reshape(-1, 1)[random_ray_ids]
+    dev = _device_of(rays_o)
+    xyz, viewdir_s, z_vals = _shell_samples(rays_o, viewdir, near, far, n_samples, obj_diag, shapenet_obj_cood, sym_aug,
+                                            False, dev)
+    if not rays_o.is_cuda:  # the dataset calls this on CPU tensors (data_nuscenes.py:643)
+        xyz, viewdir_s, z_vals = xyz.cpu(), viewdir_s.cpu(), z_vals.cpu()
+    return xyz, viewdir_s, z_vals, rgb_tgt, occ_pixels
+
+
+def render_rays(model, device, img, mask_occ, cam_pose, obj_diag, K, roi, n_samples, shapecode, texturecode,
+                shapenet_obj_cood, sym_aug, kitti2nusc=False, n_rays=2500):
+    """utils.py:380-432."""
+    rays_o, viewdir = get_rays(K, cam_pose, roi)
+    n_rays = np.minimum(rays_o.shape[0], n_rays)
+    random_ray_ids = np.random.permutation(rays_o.shape[0])[:n_rays]
+    rays_o = rays_o[random_ray_ids]
+    viewdir = viewdir[random_ray_ids]
+    rgb_tgt = img.reshape(-1, 3)[random_ray_ids].to(device)
+    occ_pixels = mask_occ.reshape(-1, 1)[random_ray_ids].to(device)
+    near, far = _shell_near_far(cam_pose, obj_diag)
+    xyz, vd, z_vals = _shell_samples(rays_o, viewdir, near, far, n_samples, obj_diag, shapenet_obj_cood, sym_aug,
+                                     kitti2nusc, device)
+    sigmas, rgbs = model(xyz, vd, shapecode, texturecode)
+    rgb_rays, depth_rays, acc_trans_rays = volume_rendering2(sigmas, rgbs, z_vals)
+    return rgb_rays, depth_rays, acc_trans_rays, rgb_tgt, occ_pixels
+
+
+def render_rays_v2(model, device, img, mask_occ, cam_pose, obj_diag, K, roi, n_samples, shapecode, texturecode,
+                   shapenet_obj_cood, sym_aug, kitti2nusc=False, im_sz=64, n_rays=None):
+    """utils.py:435-502 — the render every refine iteration calls (optimizer_nuscenes.py:716-726)."""
+    rays_o, viewdir = get_rays(K, cam_pose, roi, uv_steps=[im_sz, im_sz])
+    img, mask_occ = _resize_targets(img, mask_occ, im_sz)
+    rgb_tgt = img.reshape(-1, 3).to(device)
+    occ_pixels = mask_occ.reshape(-1, 1).to(device)
+    if n_rays is not None:
+        n_rays = np.minimum(rays_o.shape[0], n_rays)
+        random_ray_ids = np.random.permutation(rays_o.shape[0])[:n_rays]
+        rays_o = rays_o[random_ray_ids]
+        viewdir = viewdir[random_ray_ids]
+        rgb_tgt = rgb_tgt[random_ray_ids]
+        occ_pixels = occ_pixels[random_ray_ids]
+    near, far = _shell_near_far(cam_pose, obj_diag)
+    xyz, vd, z_vals = _shell_samples(rays_o, viewdir, near, far, n_samples, obj_diag, shapenet_obj_cood, sym_aug,
+                                     kitti2nusc, device)
+    sigmas, rgbs = model(xyz, vd, shapecode, texturecode)
+    rgb_rays, depth_rays, acc_trans_rays = volume_rendering2(sigmas, rgbs, z_vals)
+    return rgb_rays, depth_rays, acc_trans_rays, rgb_tgt, occ_pixels
+
+
+def render_rays_specified(model, device, img, mask_occ, cam_pose, obj_diag, K, roi, x_vec, y_vec, n_samples, shapecode,
+                          texturecode, shapenet_obj_cood, sym_aug, kitti2nusc=False):
+    """utils.py:504-551."""
+    rays_o, viewdir = get_rays_specified(K, cam_pose, x_vec + roi[0].numpy(), y_vec + roi[1].numpy())
+    rgb_tgt = img[y_vec, x_vec, :].to(device)
+    occ_pixels = mask_occ[y_vec, x_vec, :].to(device)
+    near, far = _shell_near_far(cam_pose, obj_diag)
+    xyz, vd, z_vals = _shell_samples(rays_o, viewdir, near, far, n_samples, obj_diag, shapenet_obj_cood, sym_aug,
+                                     kitti2nusc, device)
+    sigmas, rgbs = model(xyz, vd, shapecode, texturecode)
+    rgb_rays, depth_rays, acc_trans_rays = volume_rendering2(sigmas, rgbs, z_vals)
+    return rgb_rays, depth_rays, acc_trans_rays, rgb_tgt, occ_pixels
+
+
+def render_full_img(model, device, cam_pose, obj_sz, K, roi, n_samples, shapecode, texturecode, shapenet_obj_cood,
+                    out_depth=False, debug_occ=False, kitti2nusc=False):
+    """utils.py:554-616 (row-chunked like the reference: one model call per image row block)."""
+    obj_diag = np.linalg.norm(obj_sz).astype(np.float32)
+    rays_o, viewdir = get_rays(K, cam_pose, roi)
+    near, far = _shell_near_far(cam_pose, obj_diag)
+    xyz, vd, z_vals = _shell_samples(rays_o, viewdir, near, far, n_samples, obj_diag, shapenet_obj_cood, 0, kitti2nusc, device)
+    generated_img, generated_depth, generated_acc_trans = [], [], []
+    sample_step = int(np.maximum(int(roi[2]) - int(roi[0]), int(roi[3]) - int(roi[1])))
+    for i in range(0, xyz.shape[0], sample_step):
+        sigmas, rgbs = model(xyz[i:i + sample_step], vd[i:i + sample_step], shapecode, texturecode)
+        rgb_rays, depth_rays, acc_trans_rays = volume_rendering2(sigmas, rgbs, z_vals)
+        generated_img.append(rgb_rays)
+        if out_depth:
+            generated_depth.append(depth_rays)
+        if debug_occ:
+            generated_acc_trans.append(acc_trans_rays)
+    h, w = int(roi[3]) - int(roi[1]), int(roi[2]) - int(roi[0])
+    generated_img = torch.cat(generated_img).reshape(h, w, 3)
+    if debug_occ:
+        import cv2
+        acc = torch.cat(generated_acc_trans).reshape(h, w)
+        cv2.imshow('est_occ', ((torch.ones_like(acc) - acc).cpu().numpy() * 255).astype(np.uint8))
+        cv2.waitKey()
+    if out_depth:
+        return generated_img, torch.cat(generated_depth).reshape(h, w)
+    return generated_img
+
+
+def virtual_view_poses(radius=40., tilt=np.pi / 6, pan_num=8):
+    """Camera poses of utils.py:629-645 (shared by both render_virtual_imgs variants)."""
+    cam_init = np.asarray([[0, 0, 1, -radius], [-1, 0, 0, 0], [0, -1, 0, 0], [0, 0, 0, 1]]).astype(np.float32)
+    cam_tilt = np.asarray([[np.cos(tilt), 0, np.sin(tilt), 0], [0, 1, 0, 0], [-np.sin(tilt), 0, np.cos(tilt), 0],
+                           [0, 0, 0, 1]]).astype(np.float32) @ cam_init
+    poses = []
+    for pan in np.linspace(0, 2 * np.pi, pan_num, endpoint=False):
+        cam_pose = np.asarray([[np.cos(pan), -np.sin(pan), 0, 0], [np.sin(pan), np.cos(pan), 0, 0], [0, 0, 1, 0],
+                               [0, 0, 0, 1]]).astype(np.float32) @ cam_tilt
+        poses.append(torch.from_numpy(cam_pose[:3, :]))
+    return poses
+
+
+def _draw_axes(generated_img, cam_pose, K, img_sz):
+    import cv2
+    R_w2c = cam_pose[:3, :3].transpose(-1, -2)
+    T_w2c = -torch.matmul(R_w2c, cam_pose[:3, 3:])
+    P_w2c = torch.cat((R_w2c, T_w2c), dim=1).numpy()
+    img = generated_img.cpu().numpy()
+    for axis, color in (([.5, 0., 0., 1.], (1, 0, 0)), ([0., .5, 0., 1.], (0, 1, 0)), ([0., 0., .5, 1.], (0, 0, 1))):
+        a = K @ P_w2c @ torch.asarray(axis).reshape([-1, 1])
+        a = (a[:2] / a[2]).squeeze().numpy() - K[:2, 2].numpy()
+        img = cv2.arrowedLine(img, (int(img_sz / 2), int(img_sz / 2)), (int(img_sz / 2 + a[0]), int(img_sz / 2 + a[1])), color)
+    return torch.from_numpy(img)
+
+
+def render_virtual_imgs(model, device, obj_sz, K, n_samples, shapecode, texturecode, shapenet_obj_cood, radius=40.,
+                        tilt=np.pi / 6, pan_num=8, img_sz=128, kitti2nusc=False):
+    """utils.py:619-672 (visualisation helper)."""
+    x_min, x_max = K[0, 2] - img_sz / 2, K[0, 2] + img_sz / 2
+    y_min, y_max = K[1, 2] - img_sz / 2, K[1, 2] + img_sz / 2
+    roi = np.asarray([x_min, y_min, x_max, y_max]).astype(np.int64)
+    out = []
+    for cam_pose in virtual_view_poses(radius, tilt, pan_num):
+        img = render_full_img(model, device, cam_pose, obj_sz, K, roi, n_samples, shapecode, texturecode,
+                              shapenet_obj_cood, kitti2nusc=kitti2nusc)
+        out.append(_draw_axes(img, cam_pose, K, img_sz))
+    return out

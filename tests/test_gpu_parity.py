@@ -1,0 +1,348 @@
+"""GPU parity tests: every kernel, called through the reference-shaped Python API (=> ctypes => C ABI), against
+the CPU oracle on identical seeded inputs and against the reference-generated golden fixtures.
+
+Tolerances: integers/bools bit-exact; floats per-tensor max|a-b|/max|b| <= 1e-5 in fp32 mode."""
+import contextlib
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import T, load_golden, rel_err
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+DEV = "cuda"
+
+
+def snb():
+    import supnerf_b200
+    return supnerf_b200
+
+
+@contextlib.contextmanager
+def forced_rand_like(value):
+    """Make the next torch.rand_like return `value` (the golden/CPU jitter), so CPU oracle and GPU kernels sample
+    the same strata (parity mode of SURVEY §7.3 #6)."""
+    orig = torch.rand_like
+
+    def fake(t, *a, **k):
+        assert tuple(t.shape) == tuple(value.shape), (t.shape, value.shape)
+        return value.to(t.device, t.dtype)
+    torch.rand_like = fake
+    try:
+        yield
+    finally:
+        torch.rand_like = orig
+
+
+def model_from_state(cls, sd, *args, **kw):
+    m = cls(*args, **kw)
+    m.load_state_dict({k: v.detach().clone() for k, v in sd.items()})
+    return m.to(DEV)
+
+
+# ------------------------------------------------------------------------------------------- compositing
+@pytest.mark.parametrize("N,S", [(1, 1), (5, 7), (1000, 37), (4096, 64), (3000, 128), (257, 200)])
+@pytest.mark.parametrize("white", [False, True])
+def test_composite_vs_oracle(N, S, white):
+    g = torch.Generator().manual_seed(N * 131 + S)
+    sig = torch.randn(N, S, generator=g) * 3
+    rgbs = torch.rand(N, S, 3, generator=g) * 1.5 - 0.25
+    z = torch.sort(torch.rand(N, S, generator=g) * 4 + 2, -1)[0]
+    if N > 4:
+        sig[1] = 1e4      # opaque everywhere: t == 1e-10 exactly
+        sig[2] = -1.0     # empty
+        z[3] = 2.5        # miss-ray layout: all samples at one point
+    up = torch.randn(N, 3, generator=g), torch.randn(N, generator=g), torch.randn(N, generator=g)
+    s_, c_, z_ = sig.clone().requires_grad_(), rgbs.clone().requires_grad_(), z.clone().requires_grad_()
+    o = oracle.composite(s_, c_, z_, white)
+    ((o[0] * up[0]).sum() + (o[1] * up[1]).sum() + (o[2] * up[2]).sum()).backward()
+    sd, cd, zd = sig.to(DEV).requires_grad_(), rgbs.to(DEV).requires_grad_(), z.to(DEV).requires_grad_()
+    r = snb().renderer.NeRFRenderer(n_samples=S, white_bkgd=white).volume_render(sd, cd, zd)
+    ((r[0] * up[0].to(DEV)).sum() + (r[1] * up[1].to(DEV)).sum() + (r[2] * up[2].to(DEV)).sum()).backward()
+    for a, b in zip(r, o):
+        assert rel_err(a, b) < TOL
+    assert rel_err(sd.grad, s_.grad) < TOL and rel_err(cd.grad, c_.grad) < TOL and rel_err(zd.grad, z_.grad) < TOL
+
+
+def test_composite_golden_all_variants():
+    g = load_golden("stages")
+    S = snb()
+    sig, rgbs, z = T(g["vr_sig"], device=DEV), T(g["vr_rgbs"], device=DEV), T(g["vr_z"], device=DEV)
+    for wb in (0, 1):
+        s_, c_, z_ = sig.clone().requires_grad_(), rgbs.clone().requires_grad_(), z.clone().requires_grad_()
+        rgb, dep, acc = S.renderer.volume_rendering3(s_.unsqueeze(-1), c_, z_, white_bkgd=bool(wb))
+        assert rel_err(rgb, g[f"vr_rgb_wb{wb}"]) < TOL and rel_err(dep, g[f"vr_depth_wb{wb}"]) < TOL
+        assert rel_err(acc, g[f"vr_acc_wb{wb}"]) < TOL
+        up = [T(g[k], device=DEV) for k in ("vr_up_rgb", "vr_up_depth", "vr_up_acc")]
+        ((rgb * up[0]).sum() + (dep * up[1]).sum() + (acc * up[2]).sum()).backward()
+        assert rel_err(s_.grad, g[f"vr_gsig_wb{wb}"]) < TOL and rel_err(c_.grad, g[f"vr_grgb_wb{wb}"]) < TOL
+        assert rel_err(z_.grad, g[f"vr_gz_wb{wb}"]) < TOL
+    rgb, dep, acc = S.utils.volume_rendering2(sig.unsqueeze(-1), rgbs, z[0])
+    assert rel_err(rgb, g["vr2_rgb"]) < TOL and rel_err(dep, g["vr2_depth"]) < TOL and rel_err(acc, g["vr2_acc"]) < TOL
+    rgb, dep = S.utils.volume_rendering(torch.relu(sig).unsqueeze(-1), rgbs, z[0])
+    assert rel_err(rgb, g["vr1_rgb"]) < TOL and rel_err(dep, g["vr1_depth"]) < TOL
+    rgb, dep, acc = S.utils.volume_rendering_batch(sig[:15].reshape(3, 5, 16, 1), rgbs[:15].reshape(3, 5, 16, 3), z[:3])
+    assert rel_err(rgb, g["vrb_rgb"]) < TOL and rel_err(dep, g["vrb_depth"]) < TOL and rel_err(acc, g["vrb_acc"]) < TOL
+    assert rgb.shape == (3, 5, 3) and acc.shape == (3, 5)
+
+
+def test_composite_shared_z_gradient():
+    g = torch.Generator().manual_seed(3)
+    N, S = 50, 16
+    sig, rgbs = torch.randn(N, S, generator=g), torch.rand(N, S, 3, generator=g)
+    z = torch.sort(torch.rand(S, generator=g) * 3 + 1)[0]
+    z_ = z.clone().requires_grad_()
+    o = oracle.composite(sig, rgbs, z_, False)
+    (o[0].sum() + 2 * o[1].sum() + o[2].sum()).backward()
+    zd = z.to(DEV).requires_grad_()
+    r = snb().utils.volume_rendering2(sig.to(DEV).unsqueeze(-1), rgbs.to(DEV), zd)
+    (r[0].sum() + 2 * r[1].sum() + r[2].sum()).backward()
+    assert rel_err(zd.grad, z_.grad) < TOL
+
+
+# ------------------------------------------------------------------------------------------- rays / slab / samplers
+def test_get_rays_golden_and_pose_gradient():
+    g = load_golden("stages")
+    S = snb()
+    K, c2w = T(g["K"], device=DEV), T(g["c2w"], device=DEV).requires_grad_()
+    ro, vd = S.utils.get_rays(K, c2w, T(g["roi"]), uv_steps=[12, 12])
+    assert torch.equal(ro.cpu(), T(g["rays_o"])) and rel_err(vd, g["viewdir"]) < 1e-6
+    ro2, vd2 = S.utils.get_rays(K, c2w, torch.tensor([100, 50, 109, 57], dtype=torch.int32))
+    assert rel_err(vd2, g["viewdir_full"]) < 1e-6 and ro2.shape == (63, 3)
+    ro3, vd3 = S.utils.get_rays_specified(K, c2w, g["x_vec"] + g["roi"][0], g["y_vec"] + g["roi"][1])
+    assert rel_err(vd3, g["viewdir_spec"]) < 1e-6
+    w1, w2 = torch.randn(144, 3, generator=torch.Generator().manual_seed(1)), torch.randn(144, 3, generator=torch.Generator().manual_seed(2))
+    ((ro * w1.to(DEV)).sum() + (vd * w2.to(DEV)).sum()).backward()
+    c = T(g["c2w"]).requires_grad_()
+    o = oracle.get_rays(T(g["K"]), c, g["roi"], uv_steps=[12, 12])
+    ((o[0] * w1).sum() + (o[1] * w2).sum()).backward()
+    assert rel_err(c2w.grad, c.grad) < TOL
+
+
+def test_slab_hit_mask_bit_exact_golden():
+    g = load_golden("stages")
+    S = snb()
+    o, d, half = g["box_o"], g["box_d"], g["box_half"]
+    n = o.shape[0]
+    amin, amax = np.repeat(-half[None], n, 0), np.repeat(half[None], n, 0)
+    zi, zo, hit = S.utils.ray_box_intersection_tensor(T(o, device=DEV), T(d, device=DEV), T(amin, device=DEV), T(amax, device=DEV))
+    assert np.array_equal(hit.cpu().numpy(), g["box_hit_t"])
+    assert np.array_equal(zi.cpu().numpy(), g["box_zin_t"]) and np.array_equal(zo.cpu().numpy(), g["box_zout_t"])
+    zi, zo, hit = S.utils.ray_box_intersection(o, d, amin, amax)  # numpy twin
+    assert np.array_equal(hit, g["box_hit_np"]) and np.array_equal(zi, g["box_zin_np"]) and np.array_equal(zo, g["box_zout_np"])
+    zi, zo, hit = S.utils.ray_box_intersection_tensor(T(o, device=DEV), T(d, device=DEV))
+    assert np.array_equal(hit.cpu().numpy(), g["box_hit_unit"]) and np.array_equal(zi.cpu().numpy(), g["box_zin_unit"])
+
+
+def test_slab_bit_exact_large_random_and_gradient():
+    rng = np.random.RandomState(0)
+    n = 200000
+    o = (rng.randn(n, 3) * 2).astype(np.float32)
+    d = rng.randn(n, 3).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[:100, 0] = 0.0  # zero direction components: inf / nan paths
+    o[:50, 0] = 0.5
+    half = np.asarray([0.5, 0.9, 0.3], np.float32)
+    amin, amax = np.repeat(-half[None], n, 0), np.repeat(half[None], n, 0)
+    tn, tf, hit = oracle.ray_box_intersection_np(o, d, amin, amax)
+    S = snb()
+    zi, zo, h = S.utils.ray_box_intersection_tensor(T(o, device=DEV), T(d, device=DEV), T(amin, device=DEV), T(amax, device=DEV))
+    assert np.array_equal(h.cpu().numpy(), hit) and 0.02 < hit.mean() < 0.9
+    assert np.array_equal(zi.cpu().numpy(), tn[hit]) and np.array_equal(zo.cpu().numpy(), tf[hit])
+    # gradient of the compacted outputs
+    m = 4000
+    oc, dc = T(o[100:100 + m]).requires_grad_(), T(d[100:100 + m]).requires_grad_()
+    a, b, hh = oracle.ray_box_intersection(oc, dc, T(amin[:m]), T(amax[:m]))
+    (a[hh].sum() + 2 * b[hh].sum()).backward()
+    og, dg = T(o[100:100 + m], device=DEV).requires_grad_(), T(d[100:100 + m], device=DEV).requires_grad_()
+    zi, zo, _ = S.utils.ray_box_intersection_tensor(og, dg, T(amin[:m], device=DEV), T(amax[:m], device=DEV))
+    (zi.sum() + 2 * zo.sum()).backward()
+    assert rel_err(og.grad, oc.grad) < TOL and rel_err(dg.grad, dc.grad) < TOL
+
+
+@pytest.mark.parametrize("S_", [1, 16, 64, 100])
+def test_box_sampler_vs_oracle(S_):
+    obj = oracle.synthetic_object(11, im_sz=24)
+    ro, vd = oracle.get_rays(obj["K"], obj["cam_pose"], obj["roi"], uv_steps=[24, 24])
+    jit = torch.rand(ro.shape[0], S_, generator=torch.Generator().manual_seed(S_))
+    ro_c, vd_c = ro.clone().requires_grad_(), vd.clone().requires_grad_()
+    xyz, vr, zv, hit = oracle.prepare_sampled_rays(ro_c, vd_c, obj["wlh"], S_, jit)
+    ws = [torch.randn(x.shape, generator=torch.Generator().manual_seed(i)) for i, x in enumerate((xyz, vr, zv))]
+    ((xyz * ws[0]).sum() + (vr * ws[1]).sum() + (zv * ws[2]).sum()).backward()
+    R = snb().renderer.NeRFRenderer(n_samples=S_)
+    ro_g, vd_g = ro.to(DEV).requires_grad_(), vd.to(DEV).requires_grad_()
+    with forced_rand_like(jit):
+        xyz2, vr2, zv2, hit2 = R.prepare_sampled_rays(ro_g, vd_g, obj["wlh"])
+    assert torch.equal(hit2.cpu(), hit) and 0 < hit.sum() < hit.numel()
+    assert torch.equal(xyz2.cpu(), xyz.detach()), "xyz must be bit-exact (same fp32 op order)"
+    assert torch.equal(vr2.cpu(), vr.detach()) and rel_err(zv2, zv) < 1e-6
+    # integer parity: the stratum index of every sample on hit rays, floor((z - near)/(far - near) * S) == k
+    diag, half = oracle.box_constants(obj["wlh"])
+    o_n = ro / (diag / 2)
+    tn, tf, _ = oracle.ray_box_intersection(o_n, vd, -T(half).expand_as(o_n), T(half).expand_as(o_n))
+    zg = ((xyz2.cpu().double() - o_n[:, None].double()) * vd[:, None].double()).sum(-1) / (vd.double() ** 2).sum(-1, keepdim=True)
+    wide = hit & ((tf - tn) > 1e-3)
+    kk = torch.floor((zg - tn[:, None].double()) / (tf - tn)[:, None].double() * S_ + 1e-6).long()[wide]
+    assert (kk == torch.arange(S_)[None]).float().mean() > 0.999
+    ((xyz2 * ws[0].to(DEV)).sum() + (vr2 * ws[1].to(DEV)).sum() + (zv2 * ws[2].to(DEV)).sum()).backward()
+    assert rel_err(ro_g.grad, ro_c.grad) < 2e-5 and rel_err(vd_g.grad, vd_c.grad) < 2e-5
+
+
+def test_box_sampler_golden_c1():
+    g = load_golden("render_box_c1")
+    S = snb()
+    ro, vd = S.utils.get_rays(T(g["K"], device=DEV), T(g["cam_pose"], device=DEV), T(g["roi"]), uv_steps=[int(g["im_sz"])] * 2)
+    ro_c, vd_c = oracle.get_rays(T(g["K"]), T(g["cam_pose"]), g["roi"], uv_steps=[int(g["im_sz"])] * 2)
+    R = S.renderer.NeRFRenderer(n_samples=int(g["n_samples"]))
+    with forced_rand_like(T(g["jitter"])):
+        xyz, vr, zv, hit = R.prepare_sampled_rays(ro_c.to(DEV), vd_c.to(DEV), g["wlh"])  # identical rays => integer parity
+    assert np.array_equal(hit.cpu().numpy(), g["hit"])
+    assert torch.equal(xyz.cpu(), T(g["xyz"])) and rel_err(zv, g["z_vals"]) < 1e-6
+    # stratum index of every sample on hit rays is bit-exact by construction of xyz; check it explicitly
+    assert rel_err(vd, vd_c) < 1e-6 and torch.equal(ro.cpu(), ro_c)
+
+
+def test_shell_sampler_golden():
+    g = load_golden("stages")
+    S = snb()
+    torch.manual_seed(12)
+    xyz, vd, z = S.utils.sample_from_rays(T(g["rays_o"], device=DEV), T(g["viewdir"], device=DEV), 5.25, 9.75, 16)
+    assert torch.equal(z, T(g["shell_z"])) and torch.equal(xyz.cpu(), T(g["shell_xyz"]))
+    _, _, zf = S.utils.sample_from_rays(T(g["rays_o"], device=DEV), T(g["viewdir"], device=DEV), 5.25, 9.75, 16, z_fixed=True)
+    assert torch.equal(zf, T(g["shell_z_fixed"]))
+    rays = T(g["strat_rays"], device=DEV)
+    with forced_rand_like(T(g["strat_jitter"])):
+        zz = S.renderer.NeRFRenderer(n_samples=16).sample_from_ray(rays)
+    assert rel_err(zz, g["strat_z"]) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------- decoder (fp32 mode)
+def _decoder_case(cls, sd, args, B, n, S_, seed, latent_dim=256):
+    g = torch.Generator().manual_seed(seed)
+    xyz = (torch.rand(B * n, S_, 3, generator=g) - 0.5) * 2
+    vd = torch.nn.functional.normalize(torch.randn(B * n, 1, 3, generator=g), dim=-1).repeat(1, S_, 1)
+    shp, tex = oracle.synthetic_latents(seed, B, latent_dim)
+    up_s, up_c = torch.randn(B * n, S_, 1, generator=g), torch.randn(B * n, S_, 3, generator=g)
+    return xyz, vd, shp, tex, up_s, up_c
+
+
+@pytest.mark.parametrize("blocks,B,n,S_", [((2, 1), 1, 64, 16), ((3, 1), 4, 33, 8), ((5, 5), 2, 10, 4), ((3, 1), 1, 1, 1)])
+def test_decoder_fp32_vs_oracle_all_grads(blocks, B, n, S_):
+    sd = oracle.init_codenerf_state(shape_blocks=blocks[0], texture_blocks=blocks[1], seed=blocks[0])
+    xyz, vd, shp, tex, up_s, up_c = _decoder_case(None, sd, None, B, n, S_, seed=blocks[0] * 10 + B)
+    sdg = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    ins = [t.clone().requires_grad_() for t in (xyz, vd, shp, tex)]
+    sig, rgbs = oracle.codenerf_decoder(sdg, *ins)
+    ((sig * up_s).sum() + (rgbs * up_c).sum()).backward()
+    S = snb()
+    m = model_from_state(S.CodeNeRF, sd, shape_blocks=blocks[0], texture_blocks=blocks[1])
+    m.precision = "fp32"
+    gin = [t.to(DEV).requires_grad_() for t in (xyz, vd, shp, tex)]
+    sig2, rgbs2 = m(*gin)
+    assert sig2.shape == sig.shape and rgbs2.shape == rgbs.shape
+    assert rel_err(sig2, sig) < TOL and rel_err(rgbs2, rgbs) < TOL
+    ((sig2 * up_s.to(DEV)).sum() + (rgbs2 * up_c.to(DEV)).sum()).backward()
+    for a, b, name in zip(gin, ins, ("xyz", "viewdir", "shape", "texture")):
+        assert rel_err(a.grad, b.grad) < TOL, name
+    for k, p in m.named_parameters():
+        assert rel_err(p.grad, sdg[k].grad) < TOL, k
+
+
+def test_decoder_golden_batch_c5_with_losses():
+    g = load_golden("decoder_batch_c5")
+    S = snb()
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=int(g["seed"]))
+    m = model_from_state(S.AutoRFMix, sd, 3, 1, 256)
+    xyz, vd = T(g["xyz"], device=DEV).requires_grad_(), T(g["viewdir"], device=DEV).requires_grad_()
+    B, n, S_, _ = xyz.shape
+    shp, tex = T(g["shapecode"], device=DEV).requires_grad_(), T(g["texturecode"], device=DEV).requires_grad_()
+    sig, rgbs = m(xyz.flatten(0, 1), vd.flatten(0, 1), shp, tex)
+    assert rel_err(sig, g["sigmas"]) < TOL and rel_err(rgbs, g["rgbs"]) < TOL
+    rgb, dep, acc = S.utils.volume_rendering_batch(sig.reshape(B, n, S_, 1), rgbs.reshape(B, n, S_, 3), T(g["z_vals"], device=DEV))
+    assert rel_err(rgb, g["rgb"]) < TOL and rel_err(dep, g["depth"]) < TOL and rel_err(acc, g["acc"]) < TOL
+    loss = oracle.refine_losses(rgb, acc, T(g["rgb_tgt"], device=DEV), T(g["occ_pixels"], device=DEV))[0]
+    loss.backward()
+    assert rel_err(loss, g["loss"]) < TOL
+    assert rel_err(xyz.grad, g["g_xyz"]) < TOL and rel_err(vd.grad, g["g_viewdir"]) < TOL
+    assert rel_err(shp.grad, g["g_shapecode"]) < TOL and rel_err(tex.grad, g["g_texturecode"]) < TOL
+    for k, p in m.named_parameters():
+        assert rel_err(p.grad, g["gw_" + k]) < TOL, k
+
+
+# ------------------------------------------------------------------------------------------- end to end
+def test_render_rays_box_golden_c1_end_to_end():
+    """NeRFRenderer.render_rays (renderer.py:117) through the drop-in, CodeNeRF() defaults, fwd + bwd to the pose,
+    the latents and every weight — against the reference's own outputs."""
+    g = load_golden("render_box_c1")
+    S = snb()
+    sd = oracle.init_codenerf_state(seed=int(g["seed"]))
+    m = model_from_state(S.CodeNeRF, sd)
+    cam = T(g["cam_pose"], device=DEV).requires_grad_()
+    shp, tex = T(g["shapecode"], device=DEV).requires_grad_(), T(g["texturecode"], device=DEV).requires_grad_()
+    R = S.renderer.NeRFRenderer(n_samples=int(g["n_samples"]))
+    with forced_rand_like(T(g["jitter"])):
+        rgb, dep, acc, tgt, occ = R.render_rays(m, DEV, T(g["img"]), T(g["mask_occ"]), cam, g["wlh"], T(g["K"], device=DEV),
+                                                T(g["roi"]), shp, tex, im_sz=int(g["im_sz"]))
+    assert rel_err(tgt, g["rgb_tgt"]) < 1e-6 and torch.equal(occ.cpu(), T(g["occ_pixels"]))
+    assert rel_err(rgb, g["rgb"]) < TOL and rel_err(dep, g["depth"]) < TOL and rel_err(acc, g["acc"]) < TOL
+    loss = oracle.refine_losses(rgb, acc, tgt, occ)[0]
+    loss.backward()
+    assert rel_err(loss, g["loss"]) < TOL
+    assert rel_err(cam.grad, g["g_cam_pose"]) < 5e-5  # dominated by 1/d terms of grazing rays; fp32 both sides
+    assert rel_err(shp.grad, g["g_shapecode"]) < TOL and rel_err(tex.grad, g["g_texturecode"]) < TOL
+    for k, p in m.named_parameters():
+        assert rel_err(p.grad, g["gw_" + k]) < TOL, k
+
+
+def test_render_rays_v2_shell_golden_c3_end_to_end():
+    """utils.render_rays_v2 (utils.py:435), SUPNeRF 3/1/256 decoder, the refine-iteration render."""
+    g = load_golden("render_shell_c3")
+    S = snb()
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=int(g["seed"]))
+    m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
+    cam = T(g["cam_pose"], device=DEV).requires_grad_()
+    shp, tex = T(g["shapecode"], device=DEV).requires_grad_(), T(g["texturecode"], device=DEV).requires_grad_()
+    torch.manual_seed(200)  # the CPU generator draws the shared jitter vector, as in the reference
+    rgb, dep, acc, tgt, occ = S.utils.render_rays_v2(m, DEV, T(g["img"]), T(g["mask_occ"]), cam, g["obj_diag"][()], T(g["K"], device=DEV),
+                                                     T(g["roi"]), int(g["n_samples"]), shp, tex, 1, 0, im_sz=int(g["im_sz"]), n_rays=None)
+    assert rel_err(rgb, g["rgb"]) < TOL and rel_err(dep, g["depth"]) < TOL and rel_err(acc, g["acc"]) < TOL
+    loss = oracle.refine_losses(rgb, acc, tgt, occ)[0]
+    loss.backward()
+    assert rel_err(cam.grad, g["g_cam_pose"]) < TOL
+    assert rel_err(shp.grad, g["g_shapecode"]) < TOL and rel_err(tex.grad, g["g_texturecode"]) < TOL
+    assert rel_err(m.encoding_xyz[0].weight.grad, g["gw_encoding_xyz_0_weight"]) < TOL
+    assert rel_err(m.encoding_viewdir[0].weight.grad, g["gw_encoding_viewdir_0_weight"]) < TOL
+    assert rel_err(m.shape_latent_layer_2[0].weight.grad, g["gw_shape_latent_layer_2_0_weight"]) < TOL
+    assert rel_err(m.rgb[2].weight.grad, g["gw_rgb_2_weight"]) < TOL and rel_err(m.sigma[0].bias.grad, g["gw_sigma_0_bias"]) < TOL
+
+
+def test_render_full_size_c1_properties():
+    """Config-1 full size (64x64 rays x 64 samples): size-independent properties — miss rays render exactly the
+    reference's closed form (rgb = last sample colour with white bkgd, depth = diag/2, acc = 1), the hit mask equals the
+    oracle's bit for bit, weights sum <= 1, and the result equals the oracle on a 1/16 ray subsample."""
+    S = snb()
+    obj = oracle.synthetic_object(21, im_sz=64)
+    sd = oracle.init_codenerf_state(seed=21)
+    m = model_from_state(S.CodeNeRF, sd)
+    shp, tex = oracle.synthetic_latents(21, 1)
+    jit = torch.rand(4096, 64, generator=torch.Generator().manual_seed(21))
+    R = S.renderer.NeRFRenderer(n_samples=64)
+    with forced_rand_like(jit), torch.no_grad():
+        rgb, dep, acc, tgt, occ = R.render_rays(m, DEV, obj["img"], obj["mask_occ"], obj["cam_pose"].to(DEV), obj["wlh"],
+                                                obj["K"].to(DEV), obj["roi"], shp.to(DEV), tex.to(DEV), im_sz=64)
+    ids = torch.arange(0, 4096, 16)
+    with torch.no_grad():
+        o_rgb, o_dep, o_acc, o_hit = oracle.render_rays_box(sd, obj["K"], obj["cam_pose"], obj["wlh"], obj["roi"], 64, 64, shp, tex,
+                                                            jit[ids], ray_ids=ids)
+    assert rel_err(rgb[ids], o_rgb) < TOL and rel_err(dep[ids], o_dep) < TOL and rel_err(acc[ids], o_acc) < TOL
+    ro, vd = oracle.get_rays(obj["K"], obj["cam_pose"], obj["roi"], uv_steps=[64, 64])
+    _, _, _, hit = oracle.prepare_sampled_rays(ro, vd, obj["wlh"], 64, jit)
+    miss = ~hit
+    assert 0 < miss.sum() < 4096
+    diag = float(np.linalg.norm(obj["wlh"]).astype(np.float32))
+    assert torch.allclose(dep.cpu()[miss], torch.full((int(miss.sum()),), diag / 2), rtol=1e-6)
+    assert torch.all(acc.cpu()[miss] == 1.0)
