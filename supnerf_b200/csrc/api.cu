@@ -62,7 +62,7 @@ extern "C" int snb_device_info(int* sms, int* major, int* minor) {
 }
 
 static int expected_layers(const snb_arch& a) {
-  if (a.arch == SNB_ARCH_CODENERF) return 7 + 2 * a.shape_blocks + 2 * a.texture_blocks;
+  if (a.arch == SNB_ARCH_CODENERF) return 6 + 2 * a.shape_blocks + 2 * a.texture_blocks;
   return a.shape_blocks + a.texture_blocks + 1;
 }
 

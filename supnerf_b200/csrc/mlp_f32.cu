@@ -76,13 +76,13 @@ __global__ void __launch_bounds__(256) mask_colsum_kernel(float* __restrict__ g,
   const int64_t rend = (obj + 1) * rows_per_obj;
   if (r1 > rend) r1 = rend;
   for (int c = threadIdx.x; c < width; c += blockDim.x) {
-    float s = 0.f;
+    double s = 0.0;  // these sums cancel heavily (latent / bias gradients): keep the per-chunk partial exact
     for (int64_t r = r0; r < r1; ++r) {
       const float v = g[r * ld + c];
-      s += v;
+      s += (double)v;
       if (h != nullptr && !(h[r * ld + c] > 0.f)) g[r * ld + c] = 0.f;
     }
-    if (colsum != nullptr) atomicAdd(colsum + obj * width + c, s);
+    if (colsum != nullptr) atomicAdd(colsum + obj * width + c, (float)s);
   }
 }
 
@@ -93,9 +93,9 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g
   int64_t r1 = r0 + rows_per_block;
   if (r1 > rows) r1 = rows;
   for (int c = threadIdx.x; c < width; c += blockDim.x) {
-    float s = 0.f;
-    for (int64_t r = r0; r < r1; ++r) s += g[r * ld + c];
-    atomicAdd(out + c, s);
+    double s = 0.0;
+    for (int64_t r = r0; r < r1; ++r) s += (double)g[r * ld + c];
+    atomicAdd(out + c, (float)s);
   }
 }
 
@@ -200,7 +200,7 @@ static int bwd_weight(const float* dY, int ldy, int64_t M, int N_out, const floa
     if (launch_sgemm(g, false, false, st)) return 1;
   }
   if (db != nullptr && M > 0) {
-    const int rpb = 512;
+    const int rpb = 2048;
     colsum_kernel<<<(unsigned)ceil_div(M, rpb), 256, 0, st>>>(dY, ldy, N_out, M, rpb, db);
     SNB_LAUNCH_CHECK();
   }
@@ -211,7 +211,7 @@ static int mask_colsum(float* g, const float* hmask, int ld, int width, int64_t 
                        cudaStream_t st) {
   if (M == 0) return 0;
   const int64_t rpo = M / B;
-  const int rows_per_chunk = 64;
+  const int rows_per_chunk = 256;
   const int chunks = (int)ceil_div(rpo, rows_per_chunk);
   mask_colsum_kernel<<<(unsigned)(B * chunks), 256, 0, st>>>(g, hmask, ld, width, rpo, chunks, rows_per_chunk, colsum);
   SNB_LAUNCH_CHECK();
