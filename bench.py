@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Benchmark of the SUP-NeRF render hot path (BASELINE.json metric: rays/s fwd+bwd, CodeNeRF-MLP render).
+
+Workload at N=1 = BASELINE.json configs[1]: AutoRF-mix (3/1/256) render fwd+bwd of a batch of 16 synthetic car
+objects at 128x128 patches (16 384 rays/object, 64 samples/ray).  One STEP = all 16 objects: for each object the
+reference's NeRFRenderer.render_rays pipeline (rays -> slab test -> stratified samples -> decoder -> compositing),
+the refine losses and the backward pass to the camera pose and both latent codes (weights frozen: refine mode).
+N>1: object-parallel, every rank renders its own 16 objects (weak scaling, no collective on the data path).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+
+`value`   : rays/s with every input already resident in HBM (device tensors in, loss stays on device).
+`e2e`     : the same through the public drop-in API NeRFRenderer.render_rays with HOST inputs (pinned img / mask /
+            pose / latents copied H2D every step, loss + gradients read back D2H every step).
+`--impl reference`: the reference's algorithm on the host cores (the CPU oracle port, all threads), same metric, on a
+            bounded sample of the workload (one object, 64x64 rays per step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_OBJ, IM_SZ, N_SAMPLES = 16, 128, 64
+MAC_PER_SAMPLE = 449664  # decoder Bs=3, Bt=1, W=256
+METRIC = "rays/s fwd+bwd, CodeNeRF-MLP render"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), tf_burst=d["bf16_tflops"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_sustained=1400.0, tf_burst=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=3)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = []
+        for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+            if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def make_objects(seed0, n_obj, im_sz):
+    from oracle import oracle  # synthetic-input generators only (shared with the tests so CPU and GPU see the same bits)
+    objs = []
+    for i in range(n_obj):
+        o = oracle.synthetic_object(seed0 + i, im_sz=im_sz)
+        s, t = oracle.synthetic_latents(seed0 + i, 1)
+        o["shapecode"], o["texturecode"] = s, t
+        objs.append(o)
+    return objs
+
+
+def refine_loss(rgb, acc, tgt, occ):
+    """optimizer_nuscenes.py:729-736"""
+    den = torch.sum(torch.abs(occ)) + 1e-9
+    loss_rgb = torch.sum((rgb - tgt) ** 2 * torch.abs(occ)) / den
+    loss_occ = torch.sum(torch.exp(-occ * (0.5 - acc.unsqueeze(-1))) * torch.abs(occ)) / den
+    return loss_rgb + 0.1 * loss_occ
+
+
+# ----------------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import supnerf_b200 as snb
+    from supnerf_b200 import _lib, ops
+    from oracle import oracle
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=0)
+    model = snb.AutoRFMix(shape_blocks=3, texture_blocks=1, latent_dim=256)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    model.precision = args.precision
+    model.requires_grad_(False)  # refine mode: weights frozen (stated in config)
+    R = snb.renderer.NeRFRenderer(n_samples=N_SAMPLES)
+    objs = make_objects(100 + 1000 * rank, N_OBJ, IM_SZ)
+    n_rays = IM_SZ * IM_SZ
+
+    # device-resident copies (for `value`) and pinned host copies (for `e2e`)
+    dobjs, hobjs = [], []
+    for o in objs:
+        tgt = o["img"].reshape(-1, 3).to(dev)          # crop already at im_sz: the reference's Resize is the identity here
+        occ = o["mask_occ"].reshape(-1, 1).to(dev)
+        dobjs.append(dict(K=o["K"].to(dev), cam=o["cam_pose"].to(dev).requires_grad_(), wlh=o["wlh"], roi=o["roi"], tgt=tgt, occ=occ,
+                          shp=o["shapecode"].to(dev).requires_grad_(), tex=o["texturecode"].to(dev).requires_grad_()))
+        hobjs.append(dict(K=o["K"].pin_memory(), cam=o["cam_pose"].pin_memory(), wlh=o["wlh"], roi=o["roi"], img=o["img"].pin_memory(),
+                          mask=o["mask_occ"].pin_memory(), shp=o["shapecode"].pin_memory(), tex=o["texturecode"].pin_memory()))
+
+    kernel_times = {"fwd": [], "bwd": []}
+
+    def step_resident(record=False):
+        for d in dobjs:
+            d["cam"].grad = d["shp"].grad = d["tex"].grad = None
+            rays_o, viewdir = snb.utils.get_rays(d["K"], d["cam"], d["roi"], uv_steps=[IM_SZ, IM_SZ])
+            xyz, vd, z_vals, _ = R.prepare_sampled_rays(rays_o, viewdir, d["wlh"])
+            if record:
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                ops.TIMING_HOOK = lambda which, ev: kernel_times[which].append(ev)
+            sig, rgbs = model(xyz, vd, d["shp"], d["tex"])
+            rgb, dep, acc = R.volume_render(sig.squeeze(-1), rgbs, z_vals)
+            loss = refine_loss(rgb, acc, d["tgt"], d["occ"])
+            loss.backward()
+            ops.TIMING_HOOK = None
+        return loss
+
+    def step_e2e():
+        tot = 0.0
+        for h in hobjs:
+            cam = h["cam"].to(dev, non_blocking=True).requires_grad_()
+            shp = h["shp"].to(dev, non_blocking=True).requires_grad_()
+            tex = h["tex"].to(dev, non_blocking=True).requires_grad_()
+            K = h["K"].to(dev, non_blocking=True)
+            rgb, dep, acc, tgt, occ = R.render_rays(model, dev, h["img"], h["mask"], cam, h["wlh"], K, h["roi"], shp, tex, im_sz=IM_SZ)
+            loss = refine_loss(rgb, acc, tgt, occ)
+            loss.backward()
+            tot += float(loss.item())                                      # D2H read of the step's result
+            _ = (cam.grad.cpu(), shp.grad.cpu(), tex.grad.cpu())            # and of the gradients the refine loop consumes
+        return tot
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, **kw):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn(**kw)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    launches0 = lib.snb_launch_count()
+    with ClockSampler(local) as clk:
+        ms_total = timed(step_resident, args.steps, record=True)
+    launches = lib.snb_launch_count() - launches0
+    torch.cuda.synchronize()
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    rays_per_step = N_OBJ * n_rays * world
+    value = rays_per_step * args.steps / (ms_total / 1e3)
+    e2e_value = rays_per_step * args.steps / (ms_e2e / 1e3)
+    h2d = N_OBJ * (IM_SZ * IM_SZ * 3 * 4 + IM_SZ * IM_SZ * 4 + 12 * 4 + 9 * 4 + 2 * 256 * 4)
+    d2h = N_OBJ * (4 + 12 * 4 + 2 * 256 * 4)
+
+    # roofline of the dominant kernel: the decoder MLP (tensor-pipe bound), from CUDA events recorded around the C-ABI
+    # decoder calls inside the timed region (they bracket the tcgen05 kernel plus ~10 us of per-object latent GEMMs)
+    pk = peaks()
+    rows = n_rays * N_SAMPLES
+    flop_per_launch = 2.0 * MAC_PER_SAMPLE * rows
+    roof = {}
+    for which in ("fwd", "bwd"):
+        ts = [a.elapsed_time(b) for a, b in kernel_times[which]]
+        if ts:
+            avg = float(np.mean(ts))
+            roof[which] = dict(ms=avg, tflops=flop_per_launch / (avg / 1e3) / 1e12, n=len(ts), total_ms=float(np.sum(ts)))
+    dom = max(roof, key=lambda k: roof[k]["total_ms"]) if roof else None
+    peak = pk["tf_sustained"] if args.precision == "bf16" else None
+    roofline = None
+    if dom:
+        roofline = {"bound": "tensor", "kernel": "tc_%s_kernel" % dom if args.precision == "bf16" else "sgemm_kernel (fp32 SIMT)",
+                    "achieved": round(roof[dom]["tflops"], 2), "peak": peak, "unit": "TFLOP/s",
+                    "frac": round(roof[dom]["tflops"] / peak, 4) if peak else None, "traffic": None,
+                    "peak_source": pk["source"] + ", sustained bf16", "flop_per_launch": flop_per_launch,
+                    "avg_launch_ms": round(roof[dom]["ms"], 4),
+                    "other": {k: {"ms": round(v["ms"], 4), "tflops": round(v["tflops"], 2)} for k, v in roof.items()},
+                    "mlp_share_of_step": round(sum(v["total_ms"] for v in roof.values()) / ms_total, 4)}
+
+    if rank != 0:
+        return
+    cpu = cpu_baseline(steps=3, warmup=1)
+    line = {"metric": METRIC, "value": round(value, 1), "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: AutoRF-mix (3/1/256) render fwd+bwd, 16 objects x 128x128 rays x 64 samples per GPU per step",
+                       "objects_per_gpu": N_OBJ, "rays_per_object": n_rays, "samples_per_ray": N_SAMPLES, "weights": "frozen (refine mode)",
+                       "grads": "cam_pose, shapecode, texturecode", "parallelism": "object-parallel x%d, no collective" % world,
+                       "l2": "inputs larger than L2: per object 16.8 MB xyz+viewdir+z and 235 MB of masks stream through HBM",
+                       "precision": args.precision},
+            "e2e": {"value": round(e2e_value, 1), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------- CPU arms
+def cpu_render_step(oracle, sd, obj, jitter):
+    cam = obj["cam_pose"].clone().requires_grad_()
+    shp, tex = obj["shapecode"].clone().requires_grad_(), obj["texturecode"].clone().requires_grad_()
+    im = obj["img"].shape[0]
+    rgb, dep, acc, _ = oracle.render_rays_box(sd, obj["K"], cam, obj["wlh"], obj["roi"], im, N_SAMPLES, shp, tex, jitter)
+    loss = refine_loss(rgb, acc, obj["img"].reshape(-1, 3), obj["mask_occ"].reshape(-1, 1))
+    loss.backward()
+    return loss
+
+
+def cpu_baseline(steps, warmup, im_sz=64):
+    """The reference's algorithm (CPU oracle port) on the host cores: one object, im_sz^2 rays x 64 samples per step."""
+    from oracle import oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=0)
+    obj = make_objects(100, 1, im_sz)[0]
+    jitter = torch.rand(im_sz * im_sz, N_SAMPLES, generator=torch.Generator().manual_seed(0))
+    for _ in range(warmup):
+        cpu_render_step(oracle, sd, obj, jitter)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_render_step(oracle, sd, obj, jitter)
+        ts.append(time.perf_counter() - t0)
+    sec = float(np.median(ts))
+    return {"value": round(im_sz * im_sz / sec, 1), "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": "1 object, %dx%d rays x %d samples, fwd+bwd to pose+latents, weights frozen, %d steps (median %.2f s/step)"
+                      % (im_sz, im_sz, N_SAMPLES, steps, sec)}
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
+    t0 = time.perf_counter()
+    cpu = cpu_baseline(steps=steps, warmup=warmup)
+    wall = time.perf_counter() - t0
+    line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "rays/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
+            "steps": steps, "warmup": warmup, "ms_per_step": round(1e3 * 64 * 64 / cpu["value"], 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1] (AutoRF-mix 3/1/256 render fwd+bwd), bounded sample: " + cpu["sample"]},
+            "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": round(wall, 1)}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

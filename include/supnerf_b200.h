@@ -46,6 +46,8 @@ typedef struct {
 
 int snb_abi_version(void);
 const char* snb_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py reports it as gpu_launches). */
+uint64_t snb_launch_count(void);
 /* Number of SMs etc. of the current device; fails without a GPU. */
 int snb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -125,6 +127,9 @@ int snb_set_weights(snb_handle h, const float* const* tensors, int32_t n_tensors
 /* bf16 mode only: re-tile the fp32 weights into the bf16 shared-memory images the tcgen05 kernels
  * stream with bulk copies.  packed must hold snb_packed_bytes(h).  Call again after weights change. */
 size_t snb_packed_bytes(snb_handle h);
+/* Test hook: when non-NULL, the next bf16 forwards also dump every step's post-epilogue fp32 activations to
+ * acts [n_steps][n_rows][256] (n_steps = shape_blocks + texture_blocks + 4).  Pass NULL to switch it off. */
+int snb_tc_set_debug(float* acts);
 int snb_pack_weights(snb_handle h, void* packed, void* stream);
 /* Scratch the forward needs (and the backward re-reads): activations in fp32 mode, ReLU masks +
  * per-sample sigma/rgb in bf16 mode.  n_rows = N*S samples. */

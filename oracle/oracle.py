@@ -230,6 +230,53 @@ def codenerf_decoder(sd: Dict[str, Tensor], xyz: Tensor, viewdir: Tensor, shape_
     return sigmas, rgbs
 
 
+class _RoundBF16(torch.autograd.Function):
+    """Round to bf16 in the forward AND the backward pass (what a bf16 MMA operand sees in either direction)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().to(g.dtype)
+
+
+def codenerf_decoder_bf16(sd: Dict[str, Tensor], xyz: Tensor, viewdir: Tensor, shape_latent: Tensor,
+                          texture_latent: Tensor, num_xyz_freq: int = 10, num_dir_freq: int = 4):
+    """Restatement of the SNB_PREC_BF16 mode's arithmetic (supnerf_b200/csrc/mlp_tc.cu), NOT of the reference: the
+    same decoder as ``codenerf_decoder`` with every tensor-core operand rounded to bf16 where the kernel rounds it —
+    the weight matrices of the 63/256/283-input layers and rgb.0, the encodings, each layer's A operand (post-ReLU
+    activation plus the per-object latent vector) and, in the backward pass, each pre-activation gradient.  Biases,
+    latent layers, the sigma and rgb.2 heads and all accumulation stay fp32.  Used to separate "the kernel implements
+    its stated rounding" (tight) from "bf16 rounding vs the fp32 reference" (the 2e-2 budget)."""
+    rb = _RoundBF16.apply
+    bs, bt = decoder_blocks(sd)
+
+    def mm(name, x):
+        return torch.nn.functional.linear(x, sd[name + ".weight"].bfloat16().to(x.dtype), sd[name + ".bias"])
+
+    x = rb(positional_encoding(xyz, num_xyz_freq))
+    v = rb(positional_encoding(viewdir, num_dir_freq))
+    B = shape_latent.shape[0]
+    ppi = int(xyz.shape[0] / B)
+    sl = shape_latent.unsqueeze(1).repeat((1, ppi, 1)).reshape((ppi * B, 1, -1))
+    tl = texture_latent.unsqueeze(1).repeat((1, ppi, 1)).reshape((ppi * B, 1, -1))
+    y = torch.relu(mm("encoding_xyz.0", x))
+    for j in range(1, bs + 1):
+        z = torch.relu(_lin(sd, f"shape_latent_layer_{j}.0", sl))
+        y = torch.relu(mm(f"shape_layer_{j}.0", rb(y + z)))
+    e = mm("encoding_shape", rb(y))
+    sigmas = torch.nn.functional.softplus(_lin(sd, "sigma.0", e))
+    y = torch.relu(mm("encoding_viewdir.0", torch.cat([rb(e), v], -1)))
+    for j in range(1, bt + 1):
+        z = torch.relu(_lin(sd, f"texture_latent_layer_{j}.0", tl))
+        y = torch.relu(mm(f"texture_layer_{j}.0", rb(y + z)))
+    h = torch.relu(mm("rgb.0", rb(y)))
+    rgbs = _lin(sd, "rgb.2", h)
+    return sigmas, rgbs
+
+
 def autorf_decoder(sd: Dict[str, Tensor], xyz: Tensor, viewdir: Tensor, shape_feat: Tensor, texture_feat: Tensor,
                    shape_blocks: int = 5, texture_blocks: int = 5, num_xyz_freq: int = 10, num_dir_freq: int = 4):
     """model_autorf.py:156-186 (the non-mix AutoRF decoder, W = latent_dim)."""

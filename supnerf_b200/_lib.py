@@ -22,6 +22,7 @@ class SnbArch(ctypes.Structure):
 SIGNATURES = {
     "snb_abi_version": (c_i32, []),
     "snb_last_error": (ctypes.c_char_p, []),
+    "snb_launch_count": (ctypes.c_uint64, []),
     "snb_device_info": (c_i32, [ctypes.POINTER(c_i32)] * 3),
     "snb_composite_fwd": (c_i32, [c_f, c_f, c_f, c_i64, c_i64, c_i32, c_i32, c_f, c_f, c_f, c_f]),
     "snb_composite_bwd": (c_i32, [c_f, c_f, c_f, c_i64, c_i64, c_i32, c_i32, c_f, c_f, c_f, c_f, c_f, c_f, c_f]),
@@ -39,6 +40,7 @@ SIGNATURES = {
     "snb_layer_shape": (c_i32, [ctypes.c_void_p, c_i32, ctypes.POINTER(c_i32), ctypes.POINTER(c_i32)]),
     "snb_set_weights": (c_i32, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), c_i32]),
     "snb_packed_bytes": (c_sz, [ctypes.c_void_p]),
+    "snb_tc_set_debug": (c_i32, [c_f]),
     "snb_pack_weights": (c_i32, [ctypes.c_void_p, c_f, c_f]),
     "snb_mlp_workspace_bytes": (c_sz, [ctypes.c_void_p, c_i64, c_i64, c_i32]),
     "snb_mlp_bwd_scratch_bytes": (c_sz, [ctypes.c_void_p, c_i64, c_i64, c_i32]),

@@ -9,6 +9,7 @@
 namespace snb {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -32,6 +33,7 @@ int sm_count() {
 // bf16 / tcgen05 back end (mlp_tc.cu)
 size_t tc_packed_bytes(const snb_handle_s* h);
 int tc_pack_weights(snb_handle_s* h, void* packed, cudaStream_t st);
+void tc_set_debug(float* acts);
 size_t tc_workspace_bytes(const snb_handle_s* h, int64_t M, int64_t B);
 size_t tc_bwd_scratch_bytes(const snb_handle_s* h, int64_t M, int64_t B);
 int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
@@ -46,6 +48,7 @@ int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, i
 using namespace snb;
 
 extern "C" int snb_abi_version(void) { return SNB_ABI_VERSION; }
+extern "C" uint64_t snb_launch_count(void) { return g_launches; }
 extern "C" const char* snb_last_error(void) { return g_err; }
 
 extern "C" int snb_device_info(int* sms, int* major, int* minor) {
@@ -128,6 +131,8 @@ extern "C" int snb_set_weights(snb_handle h, const float* const* tensors, int32_
   h->weights_set = true;
   return 0;
 }
+
+extern "C" int snb_tc_set_debug(float* acts) { tc_set_debug(acts); return 0; }
 
 extern "C" size_t snb_packed_bytes(snb_handle h) { return h ? tc_packed_bytes(h) : 0; }
 

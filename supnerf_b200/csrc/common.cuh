@@ -25,7 +25,12 @@ void set_error(const char* fmt, ...);
     }                                  \
   } while (0)
 
-#define SNB_LAUNCH_CHECK() SNB_CHECK_CUDA(cudaGetLastError())
+extern unsigned long long g_launches;  // kernels launched by this library (all threads), for bench.py's gpu_launches
+#define SNB_LAUNCH_CHECK()            \
+  do {                                \
+    ++snb::g_launches;                \
+    SNB_CHECK_CUDA(cudaGetLastError()); \
+  } while (0)
 
 int sm_count();  // cached per device; <=0 on failure
 

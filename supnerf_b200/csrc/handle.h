@@ -36,4 +36,11 @@ int f32_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, 
                  const float* shape_latent, const float* texture_latent, const float* sigma, const float* g_sigma,
                  const float* g_rgb, const float* ws, float* scratch, float* g_xyz, float* g_viewdir,
                  float* g_shape_latent, float* g_texture_latent, float* const* g_weights, cudaStream_t st);
+// per-object latent layers, shared by both back ends.  zlat / dz: [(Bs+Bt)][B][W] (shape slots first).
+int latent_forward(const snb_handle_s* h, int64_t B, const float* shape_latent, const float* texture_latent, float* zlat,
+                   cudaStream_t st);
+// dz holds d loss / d zlat (post-ReLU outputs) and is overwritten by the pre-activation gradient.
+int latent_backward(const snb_handle_s* h, int64_t B, const float* shape_latent, const float* texture_latent,
+                    const float* zlat, float* dz, float* g_shape_latent, float* g_texture_latent, float* const* g_weights,
+                    cudaStream_t st);
 }  // namespace snb

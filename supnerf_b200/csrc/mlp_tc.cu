@@ -1,15 +1,872 @@
-// K2 / K2b, SNB_PREC_BF16 back end (tcgen05 / TMEM / bulk-copy).  Placeholder until the kernel lands.
+// K2 / K2b, SNB_PREC_BF16 back end: the CodeNeRF-family decoder as ONE persistent, warp-specialised
+// tcgen05 kernel per direction.  A 128-sample tile enters as fp32 xyz / viewdir; the positional
+// encoding is built straight into shared memory as bf16 (never to HBM); every layer is a
+// tcgen05.mma (bf16 x bf16 -> fp32 in TMEM, M=128, N<=256) whose A operand is the previous layer's
+// epilogue output kept in shared memory and whose B operand (pre-tiled, pre-swizzled bf16 weight
+// images) is streamed from L2 by the bulk-copy engine (cp.async.bulk + mbarrier) through a 4-stage
+// ring.  Accumulators ping-pong between the two 256-column halves of TMEM so that the epilogue of
+// layer l (bias, ReLU, latent add, mask bits, bf16 pack) overlaps the MMAs of layer l+1 chunk by
+// chunk.  The 256->1 (sigma) and 128->3 (rgb) heads run on CUDA cores inside the epilogues.
+// Backward: same machinery with transposed weight images; ReLU masks come back as 1 bit/unit;
+// latent gradients are per-object column sums reduced by warp butterflies; d(PE) is folded to
+// d xyz / d viewdir in the epilogue.
+//
+// Warp roles (320 threads): warps 0-7 epilogue (warp w owns TMEM lanes 32*(w%4).. and the column
+// half w/4 of every 64-column chunk), warp 8 weight producer (+ TMEM alloc), warp 9 MMA issuer.
 #include "common.cuh"
 #include "handle.h"
+#include <cuda_bf16.h>
+#include <math.h>
+#include <algorithm>
+#include <initializer_list>
+#include <vector>
+
 namespace snb {
-size_t tc_packed_bytes(const snb_handle_s*) { return 16; }
-int tc_pack_weights(snb_handle_s*, void*, cudaStream_t) { set_error("bf16 back end not built yet"); return 3; }
-size_t tc_workspace_bytes(const snb_handle_s*, int64_t, int64_t) { return 0; }
-size_t tc_bwd_scratch_bytes(const snb_handle_s*, int64_t, int64_t) { return 0; }
-int tc_forward(const snb_handle_s*, const float*, const float*, int64_t, int64_t, const float*, const float*, float*, float*,
-               void*, cudaStream_t) { set_error("bf16 back end not built yet"); return 3; }
-int tc_backward(const snb_handle_s*, const float*, const float*, int64_t, int64_t, const float*, const float*, const float*,
-                const float*, const float*, const void*, void*, float*, float*, float*, float*, float* const*, cudaStream_t) {
-  set_error("bf16 back end not built yet"); return 3;
+namespace tc {
+
+constexpr int kTileM = 128;
+constexpr int kStages = 4;
+constexpr uint32_t kStageBytes = 32768;   // [256 n][64 k] bf16
+constexpr uint32_t kChunkBytes = 16384;   // [128 m][64 k] bf16
+constexpr int kMaxSteps = 24;
+constexpr int kThreads = 320;
+constexpr int kEpiThreads = 256;
+constexpr int kMaxLatentSlots = 8;
+
+constexpr uint32_t SM_A = 0;
+constexpr uint32_t SM_AUX = 4 * kChunkBytes;                    // chunk index 4
+constexpr uint32_t SM_W = 5 * kChunkBytes;                      // 81920
+constexpr uint32_t SM_PART = SM_W + kStages * kStageBytes;      // 212992
+constexpr uint32_t SM_PART_BYTES = (2 * 128 * 3 + 2 * 128 + kMaxLatentSlots * 256) * 4;  // 12288
+constexpr uint32_t SM_BARS = SM_PART + SM_PART_BYTES;
+constexpr uint32_t SM_TOTAL = SM_BARS + 32 * 8 + 16;
+constexpr uint32_t SM_ALLOC = SM_TOTAL + 1024;                  // + alignment slack
+
+enum Epi : int { EPI_RELU = 0, EPI_LINEAR_SIGMA = 1, EPI_RGB_HEAD = 2, EPI_B_MASK = 3, EPI_B_EV = 4, EPI_B_XYZ = 5 };
+
+struct Step {
+  uint32_t w_off, w2_off;      // byte offsets of the first weight chunk of MMA group 1 / 2 in the packed buffer
+  uint16_t n_chunks, n_out;    // K chunks (64 wide), N of group 1
+  uint16_t n2_out;             // N of group 2 (0: none); group 2 re-reads the same A chunks
+  uint8_t a_chunk[6];          // shared-memory chunk index per K chunk (0..3 = A, 4 = AUX)
+  int8_t epi, mask_slot, latent_slot, produce_a;
+  const float* bias;           // fp32 bias of the layer (forward)
+};
+
+struct Program {
+  int n_steps, n_mask_slots;
+  Step s[kMaxSteps];
+};
+
+struct Params {
+  const float* xyz; const float* viewdir;
+  int64_t M, rows_per_obj, B;
+  const uint8_t* packed;
+  const float* zlat;            // [(Bs+Bt)][B][256]
+  const float* wsig; const float* bsig; const float* w2; const float* b2;
+  uint32_t* masks;              // [tile][slot][8 words][128 rows]
+  // forward
+  float* sigma; float* rgb; float* dbg;
+  // backward
+  const float* sigma_in; const float* g_sigma; const float* g_rgb;
+  float* g_xyz; float* g_viewdir; float* g_zlat;   // g_zlat [(Bs+Bt)][B][256], accumulated with atomics
+  int r0_mask_slot, n_latent;
+  Program prog;
+};
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: rows 128 B apart, 8-row atoms 1024 B apart (SBO), descriptor version 1.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24.
+__device__ __forceinline__ uint32_t umma_idesc(uint32_t M, uint32_t N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// byte offset of 16-byte unit `unit` (0..7) of row `row` inside a 128B-swizzled [rows][64] bf16 chunk
+__device__ __forceinline__ uint32_t swz(uint32_t row, uint32_t unit) { return row * 128u + ((unit ^ (row & 7u)) << 4); }
+
+// sin/cos(2^f x), f < DEG, by the double-angle recurrence from one accurate sincosf (error ~2^f * 1e-7: far below bf16)
+template <int DEG>
+__device__ __forceinline__ void trig_ladder(const float x[3], float s[DEG][3], float c[DEG][3]) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float sv, cv;
+    sincosf(x[a], &sv, &cv);
+    s[0][a] = sv; c[0][a] = cv;
+#pragma unroll
+    for (int f = 1; f < DEG; ++f) {
+      s[f][a] = 2.f * s[f - 1][a] * c[f - 1][a];
+      c[f][a] = 1.f - 2.f * s[f - 1][a] * s[f - 1][a];
+    }
+  }
+}
+
+// Write PE(x) (model_codenerf.py:4-10 column order) as one bf16 row of the AUX chunk; this thread stores the 4 units of
+// its column half `hh` (columns 32*hh .. 32*hh+31); columns >= 3+6*DEG are zero.
+template <int DEG>
+__device__ __forceinline__ void write_pe_row(uint8_t* aux, uint32_t row, uint32_t hh, const float x[3]) {
+  float s[DEG][3], c[DEG][3];
+  trig_ladder<DEG>(x, s, c);
+  float v[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) v[a] = x[a];
+#pragma unroll
+  for (int f = 0; f < DEG; ++f)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      v[3 + 3 * f + a] = s[f][a];
+      v[3 + 3 * DEG + 3 * f + a] = c[f][a];
+    }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    if ((uint32_t)(u >> 2) == hh) {
+      uint4 q;
+      q.x = pack_bf16(v[8 * u + 0], v[8 * u + 1]);
+      q.y = pack_bf16(v[8 * u + 2], v[8 * u + 3]);
+      q.z = pack_bf16(v[8 * u + 4], v[8 * u + 5]);
+      q.w = pack_bf16(v[8 * u + 6], v[8 * u + 7]);
+      *reinterpret_cast<uint4*>(aux + swz(row, u)) = q;
+    }
+  }
+}
+
+// sum over the 32 lanes (= 32 rows) of each of the 32 per-lane values: lane l ends with column l's sum in v[0]
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], uint32_t lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float keep = upper ? v[i + o] : v[i];
+      const float send = upper ? v[i] : v[i + o];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+struct Smem {
+  uint8_t* base;
+  uint32_t base_u32;
+  __device__ uint8_t* chunk(int c) const { return base + (uint32_t)c * kChunkBytes; }
+  __device__ uint32_t chunk_u32(int c) const { return base_u32 + (uint32_t)c * kChunkBytes; }
+  __device__ uint32_t stage_u32(int s) const { return base_u32 + SM_W + (uint32_t)s * kStageBytes; }
+  __device__ float* part() const { return reinterpret_cast<float*>(base + SM_PART); }
+  __device__ uint32_t bar(int i) const { return base_u32 + SM_BARS + 8u * i; }
+};
+// barrier indices
+constexpr int BAR_WFULL = 0, BAR_WEMPTY = 4, BAR_AREADY = 8, BAR_ACC = 13, BAR_COUNT = 15;
+
+// ------------------------------------------------------------------------------------------ roles shared by fwd / bwd
+__device__ __forceinline__ void producer_loop(const Params& p, const Smem& sm, int64_t n_tiles, uint32_t lane) {
+  uint32_t it = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int si = 0; si < p.prog.n_steps; ++si) {
+      const Step& st = p.prog.s[si];
+      const int groups = st.n2_out ? 2 : 1;
+      for (int g = 0; g < groups; ++g) {
+        const uint32_t bytes = (uint32_t)(g == 0 ? st.n_out : st.n2_out) * 128u;
+        const uint32_t off0 = g == 0 ? st.w_off : st.w2_off;
+        for (int kc = 0; kc < st.n_chunks; ++kc, ++it) {
+          const uint32_t stage = it % kStages, ph = (it / kStages) & 1u;
+          mbar_wait(sm.bar(BAR_WEMPTY + stage), ph ^ 1u);
+          if (lane == 0) {
+            mbar_expect_tx(sm.bar(BAR_WFULL + stage), bytes);
+            bulk_g2s(sm.stage_u32(stage), p.packed + off0 + (size_t)kc * bytes, bytes, sm.bar(BAR_WFULL + stage));
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void mma_loop(const Params& p, const Smem& sm, int64_t n_tiles, uint32_t lane, uint32_t tmem_base) {
+  uint32_t it = 0, gstep = 0;
+  uint32_t a_phase = 0;  // bit c = parity of the next completion of a_ready[c] to wait for
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int si = 0; si < p.prog.n_steps; ++si, ++gstep) {
+      const Step& st = p.prog.s[si];
+      const uint32_t half = gstep & 1u;
+      const int groups = st.n2_out ? 2 : 1;
+      for (int g = 0; g < groups; ++g) {
+        const uint32_t n = g == 0 ? st.n_out : st.n2_out;
+        const uint32_t d_tmem = tmem_base + (g == 0 ? half : (half ^ 1u)) * 256u;
+        const uint32_t idesc = umma_idesc(128, n);
+        for (int kc = 0; kc < st.n_chunks; ++kc, ++it) {
+          const int ac = st.a_chunk[kc];
+          if (g == 0) {
+            mbar_wait(sm.bar(BAR_AREADY + ac), (a_phase >> ac) & 1u);
+            a_phase ^= 1u << ac;
+          }
+          const uint32_t stage = it % kStages, ph = (it / kStages) & 1u;
+          mbar_wait(sm.bar(BAR_WFULL + stage), ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a0 = sm.chunk_u32(ac), b0 = sm.stage_u32(stage);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16(d_tmem, umma_desc(a0 + kk * 32), umma_desc(b0 + kk * 32), idesc, (kc > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(sm.bar(BAR_WEMPTY + stage));
+          }
+          __syncwarp();
+        }
+      }
+      if (lane == 0) umma_commit(sm.bar(BAR_ACC + half));
+      __syncwarp();
+    }
+  }
+}
+
+// after this thread's generic-proxy stores into an A chunk: publish to the async proxy and signal the MMA warp
+__device__ __forceinline__ void publish_chunk(const Smem& sm, int c, uint32_t lane) {
+  tc_fence_before();
+  fence_async_smem();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(sm.bar(BAR_AREADY + c));
+}
+
+__device__ __forceinline__ void store_row32(uint8_t* chunk, uint32_t row, uint32_t hh, const uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    uint4 q = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+    *reinterpret_cast<uint4*>(chunk + swz(row, hh * 4 + u)) = q;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ forward kernel
+__global__ void __launch_bounds__(kThreads, 1) tc_fwd_kernel(const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem sm;
+  {
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
+    sm.base = smem_raw + pad;
+    sm.base_u32 = raw + pad;
+  }
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.base + SM_BARS + 32 * 8);
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(sm.bar(BAR_WFULL + i), 1); mbar_init(sm.bar(BAR_WEMPTY + i), 1); }
+    for (int i = 0; i < 5; ++i) mbar_init(sm.bar(BAR_AREADY + i), 8);
+    for (int i = 0; i < 2; ++i) mbar_init(sm.bar(BAR_ACC + i), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int64_t n_tiles = (p.M + kTileM - 1) / kTileM;
+
+  if (warp == 8) {
+    producer_loop(p, sm, n_tiles, lane);
+  } else if (warp == 9) {
+    mma_loop(p, sm, n_tiles, lane, tmem_base);
+  } else {
+    const uint32_t q = warp & 3u, hh = warp >> 2;
+    const uint32_t row = q * 32u + lane;                 // row inside the tile == TMEM lane
+    const uint32_t lane_field = (q * 32u) << 16;
+    float* sig_part = sm.part();                         // [2][128]
+    float* rgb_part = sm.part() + 256;                   // [2][128][3]
+    uint32_t gstep = 0, acc_cnt[2] = {0, 0};
+    const int nslots = p.prog.n_mask_slots;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t grow = tile * kTileM + row;
+      const bool valid = grow < p.M;
+      const int64_t crow = valid ? grow : p.M - 1;
+      int64_t obj = crow / p.rows_per_obj;
+      if (obj > p.B - 1) obj = p.B - 1;
+      {
+        const float x[3] = {__ldg(p.xyz + 3 * crow), __ldg(p.xyz + 3 * crow + 1), __ldg(p.xyz + 3 * crow + 2)};
+        write_pe_row<10>(sm.chunk(4), row, hh, x);
+        publish_chunk(sm, 4, lane);
+      }
+      uint32_t* mask_tile = p.masks + (size_t)tile * nslots * 8 * 128;
+      float sig_acc = 0.f, rgb_acc[3] = {0.f, 0.f, 0.f};
+      for (int si = 0; si < p.prog.n_steps; ++si, ++gstep) {
+        const Step& st = p.prog.s[si];
+        const uint32_t half = gstep & 1u;
+        mbar_wait(sm.bar(BAR_ACC + half), acc_cnt[half] & 1u);
+        acc_cnt[half]++;
+        tc_fence_after();
+        if (si == 0) {  // layer 0's MMAs are done with PE(xyz): reuse the AUX chunk for PE(viewdir)
+          const float d[3] = {__ldg(p.viewdir + 3 * crow), __ldg(p.viewdir + 3 * crow + 1), __ldg(p.viewdir + 3 * crow + 2)};
+          write_pe_row<4>(sm.chunk(4), row, hh, d);
+          publish_chunk(sm, 4, lane);
+        }
+        const int n_c = st.n_out / 64;
+        const float* zl = st.latent_slot >= 0 ? p.zlat + ((size_t)st.latent_slot * p.B + obj) * 256 : nullptr;
+        for (int c = 0; c < n_c; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + half * 256u + (uint32_t)c * 64u + hh * 32u + lane_field, r);
+          const int col0 = c * 64 + (int)hh * 32;
+          const float4* b4 = reinterpret_cast<const float4*>(st.bias + col0);
+          uint32_t pk[16], mask = 0;
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 bb = __ldg(b4 + i4);
+            float v[4] = {__uint_as_float(r[4 * i4]) + bb.x, __uint_as_float(r[4 * i4 + 1]) + bb.y,
+                          __uint_as_float(r[4 * i4 + 2]) + bb.z, __uint_as_float(r[4 * i4 + 3]) + bb.w};
+            if (st.epi != EPI_LINEAR_SIGMA) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                v[u] = fmaxf(v[u], 0.f);
+                mask |= (v[u] > 0.f ? 1u : 0u) << (4 * i4 + u);
+              }
+            }
+            if (st.epi == EPI_LINEAR_SIGMA) {
+              const float4 ws = __ldg(reinterpret_cast<const float4*>(p.wsig + col0) + i4);
+              sig_acc += v[0] * ws.x + v[1] * ws.y + v[2] * ws.z + v[3] * ws.w;
+            } else if (st.epi == EPI_RGB_HEAD) {
+#pragma unroll
+              for (int k = 0; k < 3; ++k) {
+                const float4 ww = __ldg(reinterpret_cast<const float4*>(p.w2 + k * 128 + col0) + i4);
+                rgb_acc[k] += v[0] * ww.x + v[1] * ww.y + v[2] * ww.z + v[3] * ww.w;
+              }
+            }
+            if (p.dbg != nullptr && valid) {
+              float* d = p.dbg + ((size_t)si * p.M + grow) * 256 + col0 + 4 * i4;
+              d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; d[3] = v[3];
+            }
+            if (zl != nullptr) {
+              const float4 zz = __ldg(reinterpret_cast<const float4*>(zl + col0) + i4);
+              v[0] += zz.x; v[1] += zz.y; v[2] += zz.z; v[3] += zz.w;
+            }
+            pk[2 * i4] = pack_bf16(v[0], v[1]);
+            pk[2 * i4 + 1] = pack_bf16(v[2], v[3]);
+          }
+          if (st.mask_slot >= 0) mask_tile[((size_t)st.mask_slot * 8 + c * 2 + hh) * 128 + row] = mask;
+          if (st.produce_a) {
+            store_row32(sm.chunk(c), row, hh, pk);
+            publish_chunk(sm, c, lane);
+          }
+        }
+        if (st.epi == EPI_LINEAR_SIGMA) sig_part[hh * 128 + row] = sig_acc;
+        if (st.epi == EPI_RGB_HEAD) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) rgb_part[(hh * 128 + row) * 3 + k] = rgb_acc[k];
+        }
+        tc_fence_before();
+      }
+      epi_bar_sync();
+      if (hh == 0 && valid) {
+        const float sp = sig_part[row] + sig_part[128 + row] + __ldg(p.bsig);
+        p.sigma[grow] = sp > 20.f ? sp : log1pf(expf(sp));   // nn.Softplus(): beta 1, threshold 20
+#pragma unroll
+        for (int k = 0; k < 3; ++k) p.rgb[3 * grow + k] = rgb_part[row * 3 + k] + rgb_part[(128 + row) * 3 + k] + __ldg(p.b2 + k);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------ backward kernel
+__device__ __forceinline__ uint32_t mask_word(const uint32_t* mask_tile, int slot, int word, uint32_t row) {
+  return __ldg(mask_tile + ((size_t)slot * 8 + word) * 128 + row);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tc_bwd_kernel(const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem sm;
+  {
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
+    sm.base = smem_raw + pad;
+    sm.base_u32 = raw + pad;
+  }
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.base + SM_BARS + 32 * 8);
+  float* xyz_part = sm.part();                 // [2][128][3]
+  float* colsum = sm.part() + 768 + 256;       // [slots][256]
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(sm.bar(BAR_WFULL + i), 1); mbar_init(sm.bar(BAR_WEMPTY + i), 1); }
+    for (int i = 0; i < 5; ++i) mbar_init(sm.bar(BAR_AREADY + i), 8);
+    for (int i = 0; i < 2; ++i) mbar_init(sm.bar(BAR_ACC + i), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (uint32_t i = tid; i < kMaxLatentSlots * 256; i += kThreads) colsum[i] = 0.f;
+  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int64_t n_tiles = (p.M + kTileM - 1) / kTileM;
+
+  if (warp == 8) {
+    producer_loop(p, sm, n_tiles, lane);
+  } else if (warp == 9) {
+    mma_loop(p, sm, n_tiles, lane, tmem_base);
+  } else {
+    const uint32_t q = warp & 3u, hh = warp >> 2;
+    const uint32_t row = q * 32u + lane;
+    const uint32_t lane_field = (q * 32u) << 16;
+    const uint32_t etid = tid;  // 0..255
+    uint32_t gstep = 0, acc_cnt[2] = {0, 0};
+    const int nslots = p.prog.n_mask_slots;
+    const int n_lat = p.n_latent;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t grow = tile * kTileM + row;
+      const bool valid = grow < p.M;
+      const int64_t crow = valid ? grow : p.M - 1;
+      const int64_t obj = (tile * kTileM) / p.rows_per_obj;  // tiles never straddle objects (checked on the host)
+      const uint32_t* mask_tile = p.masks + (size_t)tile * nslots * 8 * 128;
+      const float gsg = valid ? __ldg(p.g_sigma + grow) : 0.f;
+      const float gsp = gsg * (-expm1f(-__ldg(p.sigma_in + crow)));   // d softplus = 1 - exp(-softplus)
+      // ---- prologue: d pre-activation of rgb.0 = (g_rgb W2) * mask -> A chunks 0,1 (128 columns)
+      {
+        float g3[3] = {0.f, 0.f, 0.f};
+        if (valid) { g3[0] = __ldg(p.g_rgb + 3 * grow); g3[1] = __ldg(p.g_rgb + 3 * grow + 1); g3[2] = __ldg(p.g_rgb + 3 * grow + 2); }
+        for (int c = 0; c < 2; ++c) {
+          const int col0 = c * 64 + (int)hh * 32;
+          const uint32_t mw = mask_word(mask_tile, p.r0_mask_slot, c * 2 + hh, row);
+          uint32_t pk[16];
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w2 + col0) + i4);
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w2 + 128 + col0) + i4);
+            const float4 w2 = __ldg(reinterpret_cast<const float4*>(p.w2 + 256 + col0) + i4);
+            float v[4] = {g3[0] * w0.x + g3[1] * w1.x + g3[2] * w2.x, g3[0] * w0.y + g3[1] * w1.y + g3[2] * w2.y,
+                          g3[0] * w0.z + g3[1] * w1.z + g3[2] * w2.z, g3[0] * w0.w + g3[1] * w1.w + g3[2] * w2.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (!((mw >> (4 * i4 + u)) & 1u)) v[u] = 0.f;
+            pk[2 * i4] = pack_bf16(v[0], v[1]);
+            pk[2 * i4 + 1] = pack_bf16(v[2], v[3]);
+          }
+          store_row32(sm.chunk(c), row, hh, pk);
+          publish_chunk(sm, c, lane);
+        }
+      }
+      for (int si = 0; si < p.prog.n_steps; ++si, ++gstep) {
+        const Step& st = p.prog.s[si];
+        const uint32_t half = gstep & 1u;
+        mbar_wait(sm.bar(BAR_ACC + half), acc_cnt[half] & 1u);
+        acc_cnt[half]++;
+        tc_fence_after();
+        if (st.epi == EPI_B_XYZ) {
+          // acc = d PE(xyz) (64 columns): fold to d xyz.  g_x = g_0 + sum_f 2^f (g_sin,f cos_f - g_cos,f sin_f)
+          uint32_t r[32];
+          tmem_ld32(tmem_base + half * 256u + hh * 32u + lane_field, r);
+          const float x[3] = {__ldg(p.xyz + 3 * crow), __ldg(p.xyz + 3 * crow + 1), __ldg(p.xyz + 3 * crow + 2)};
+          float s[10][3], c[10][3];
+          trig_ladder<10>(x, s, c);
+          float g[3] = {0.f, 0.f, 0.f};
+          if (hh == 0) {  // columns 0..31: x (0-2), sin f=0..8 (3-29), sin f=9 a=0,1 (30,31)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float gv = __uint_as_float(r[i]);
+              if (i < 3) g[i] += gv;
+              else { const int f = (i - 3) / 3, a = (i - 3) % 3; g[a] += gv * (float)(1 << f) * c[f][a]; }
+            }
+          } else {        // columns 32..63: sin f=9 a=2 (32), cos f=0..9 (33-62), pad (63)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float gv = __uint_as_float(r[i]);
+              const int col = 32 + i;
+              if (col == 32) g[2] += gv * 512.f * c[9][2];
+              else if (col < 63) { const int f = (col - 33) / 3, a = (col - 33) % 3; g[a] -= gv * (float)(1 << f) * s[f][a]; }
+            }
+          }
+#pragma unroll
+          for (int a = 0; a < 3; ++a) xyz_part[(hh * 128 + row) * 3 + a] = g[a];
+          tc_fence_before();
+          continue;
+        }
+        if (st.epi == EPI_B_EV && st.n2_out && hh == 0) {
+          // group 2 accumulators (other TMEM half, columns 0..31) = d PE(viewdir): fold to d viewdir (deg 4: 27 columns)
+          uint32_t r[32];
+          tmem_ld32(tmem_base + (half ^ 1u) * 256u + lane_field, r);
+          const float d[3] = {__ldg(p.viewdir + 3 * crow), __ldg(p.viewdir + 3 * crow + 1), __ldg(p.viewdir + 3 * crow + 2)};
+          float s[4][3], c[4][3];
+          trig_ladder<4>(d, s, c);
+          float g[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 27; ++i) {
+            const float gv = __uint_as_float(r[i]);
+            if (i < 3) g[i] += gv;
+            else if (i < 15) { const int f = (i - 3) / 3, a = (i - 3) % 3; g[a] += gv * (float)(1 << f) * c[f][a]; }
+            else { const int f = (i - 15) / 3, a = (i - 15) % 3; g[a] -= gv * (float)(1 << f) * s[f][a]; }
+          }
+          if (valid && p.g_viewdir) { p.g_viewdir[3 * grow] = g[0]; p.g_viewdir[3 * grow + 1] = g[1]; p.g_viewdir[3 * grow + 2] = g[2]; }
+        }
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + half * 256u + (uint32_t)c * 64u + hh * 32u + lane_field, r);
+          const int col0 = c * 64 + (int)hh * 32;
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (st.epi == EPI_B_EV) {   // + sigma-head gradient: d e += g_sigma_pre * w_sigma
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+              const float4 ws = __ldg(reinterpret_cast<const float4*>(p.wsig + col0) + i4);
+              v[4 * i4] += gsp * ws.x; v[4 * i4 + 1] += gsp * ws.y; v[4 * i4 + 2] += gsp * ws.z; v[4 * i4 + 3] += gsp * ws.w;
+            }
+          }
+          if (st.latent_slot >= 0) {  // latent gradient: per-object column sum of the UNMASKED input gradient
+            float t[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = v[i];
+            const float cs = warp_colsum32(t, lane);
+            atomicAdd(colsum + st.latent_slot * 256 + col0 + lane, cs);
+          }
+          if (st.produce_a) {
+            uint32_t mw = 0xffffffffu;
+            if (st.mask_slot >= 0) mw = mask_word(mask_tile, st.mask_slot, c * 2 + hh, row);
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float a = ((mw >> (2 * i)) & 1u) ? v[2 * i] : 0.f;
+              const float b = ((mw >> (2 * i + 1)) & 1u) ? v[2 * i + 1] : 0.f;
+              pk[i] = pack_bf16(a, b);
+            }
+            store_row32(sm.chunk(c), row, hh, pk);
+            publish_chunk(sm, c, lane);
+          }
+        }
+        tc_fence_before();
+      }
+      // ---- tile end: d xyz, and flush the latent column sums when the next tile belongs to another object
+      const int64_t next = tile + gridDim.x;
+      const bool flush = next >= n_tiles || (next * kTileM) / p.rows_per_obj != obj;
+      epi_bar_sync();
+      if (p.g_xyz != nullptr && hh == 0 && valid) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) p.g_xyz[3 * grow + a] = xyz_part[row * 3 + a] + xyz_part[(128 + row) * 3 + a];
+      }
+      if (flush) {
+        for (int sl = 0; sl < n_lat; ++sl) {
+          const float v = colsum[sl * 256 + etid];
+          if (v != 0.f) atomicAdd(p.g_zlat + ((size_t)sl * p.B + obj) * 256 + etid, v);
+          colsum[sl * 256 + etid] = 0.f;
+        }
+      }
+      epi_bar_sync();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------ weight packing
+struct PackJob {
+  const float* src; int ld; int transposed; int n_valid; int n_pad; int k0; int k_limit; uint32_t dst_off;
+};
+constexpr int kJobsPerLaunch = 64;
+struct PackJobs { int n; PackJob j[kJobsPerLaunch]; };
+
+// one block per job: dst[n][k] (128B-swizzled rows of 64 bf16) = src'(n, k0 + k), zero outside the valid range
+__global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackJobs jobs, uint8_t* __restrict__ packed) {
+  const PackJob& jb = jobs.j[blockIdx.x];
+  for (int e = threadIdx.x; e < jb.n_pad * 64; e += blockDim.x) {
+    int n, k;
+    if (jb.transposed) { k = e / jb.n_pad; n = e % jb.n_pad; }  // consecutive threads walk the contiguous source dimension
+    else { n = e / 64; k = e % 64; }
+    const int kg = jb.k0 + k;
+    float v = 0.f;
+    if (n < jb.n_valid && kg < jb.k_limit) v = jb.transposed ? jb.src[(size_t)kg * jb.ld + n] : jb.src[(size_t)n * jb.ld + kg];
+    const uint32_t off = jb.dst_off + (uint32_t)n * 128u + ((((uint32_t)k >> 3) ^ ((uint32_t)n & 7u)) << 4) + ((uint32_t)k & 7u) * 2u;
+    *reinterpret_cast<__nv_bfloat16*>(packed + off) = __float2bfloat16_rn(v);
+  }
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------ host side
+using namespace tc;
+
+static bool tc_supported(const snb_handle_s* h, const char** why) {
+  const snb_arch& a = h->arch;
+  if (a.arch != SNB_ARCH_CODENERF) { *why = "bf16 mode covers the CodeNeRF/AutoRFMix/SUPNeRF decoder only"; return false; }
+  if (a.W != 256) { *why = "bf16 mode needs W == 256"; return false; }
+  if (a.num_xyz_freq != 10 || a.num_dir_freq != 4) { *why = "bf16 mode needs num_xyz_freq == 10 and num_dir_freq == 4"; return false; }
+  if (a.shape_blocks + a.texture_blocks > kMaxLatentSlots) { *why = "bf16 mode needs shape_blocks + texture_blocks <= 8"; return false; }
+  return true;
+}
+
+struct TcPlan {
+  Program fwd, bwd_full, bwd_noxyz;
+  std::vector<PackJob> jobs;
+  uint32_t total_bytes = 0;
+  int r0_slot = 0;
+};
+
+static void add_chunks(TcPlan& pl, const float* src, int ld, bool transposed, int n_valid, int n_pad, int k_limit, int n_chunks,
+                       uint32_t* first_off) {
+  *first_off = pl.total_bytes;
+  for (int c = 0; c < n_chunks; ++c) {
+    PackJob j;
+    j.src = src; j.ld = ld; j.transposed = transposed ? 1 : 0; j.n_valid = n_valid; j.n_pad = n_pad; j.k0 = c * 64;
+    j.k_limit = k_limit; j.dst_off = pl.total_bytes;
+    pl.jobs.push_back(j);
+    pl.total_bytes += (uint32_t)n_pad * 128u;
+  }
+}
+
+static Step make_step(int epi, int n_out, int n_chunks, std::initializer_list<int> chunks, int mask_slot, int latent_slot,
+                      int produce_a, const float* bias) {
+  Step s{};
+  s.epi = (int8_t)epi; s.n_out = (uint16_t)n_out; s.n_chunks = (uint16_t)n_chunks; s.mask_slot = (int8_t)mask_slot;
+  s.latent_slot = (int8_t)latent_slot; s.produce_a = (int8_t)produce_a; s.bias = bias; s.n2_out = 0;
+  int i = 0;
+  for (int c : chunks) s.a_chunk[i++] = (uint8_t)c;
+  return s;
+}
+
+// Builds the forward / backward step programs and the weight-image packing jobs for the handle's current pointers.
+static TcPlan build_plan(const snb_handle_s* h) {
+  TcPlan pl;
+  const int Bs = h->arch.shape_blocks, Bt = h->arch.texture_blocks, W = 256, dv = h->d_dir(), dx = h->d_xyz();
+  const auto& ly = h->layers;
+  const int slot_vv = Bs + 1, slot_r = Bs + Bt + 2;
+  pl.r0_slot = slot_r;
+  Program& f = pl.fwd;
+  f.n_steps = 0; f.n_mask_slots = Bs + Bt + 3;
+  auto push = [](Program& pr, const Step& s) { pr.s[pr.n_steps++] = s; };
+  {  // ---------------- forward
+    Step s = make_step(EPI_RELU, 256, 1, {4}, 0, 0, 1, ly[h->iX].b);
+    add_chunks(pl, ly[h->iX].w, dx, false, 256, 256, dx, 1, &s.w_off);
+    push(f, s);
+    for (int j = 1; j <= Bs; ++j) {
+      s = make_step(EPI_RELU, 256, 4, {0, 1, 2, 3}, j, j < Bs ? j : -1, 1, ly[h->iS(j)].b);
+      add_chunks(pl, ly[h->iS(j)].w, W, false, 256, 256, W, 4, &s.w_off);
+      push(f, s);
+    }
+    s = make_step(EPI_LINEAR_SIGMA, 256, 4, {0, 1, 2, 3}, -1, -1, 1, ly[h->iES].b);
+    add_chunks(pl, ly[h->iES].w, W, false, 256, 256, W, 4, &s.w_off);
+    push(f, s);
+    s = make_step(EPI_RELU, 256, 5, {4, 0, 1, 2, 3}, slot_vv, Bs, 1, ly[h->iEV].b);
+    {  // chunk 0 = the PE(viewdir) columns [W, W+dv) of encoding_viewdir, chunks 1..4 = its first W columns
+      add_chunks(pl, ly[h->iEV].w + W, W + dv, false, 256, 256, dv, 1, &s.w_off);
+      uint32_t dummy;
+      add_chunks(pl, ly[h->iEV].w, W + dv, false, 256, 256, W, 4, &dummy);
+    }
+    push(f, s);
+    for (int j = 1; j <= Bt; ++j) {
+      s = make_step(EPI_RELU, 256, 4, {0, 1, 2, 3}, slot_vv + j, j < Bt ? Bs + j : -1, 1, ly[h->iT(j)].b);
+      add_chunks(pl, ly[h->iT(j)].w, W, false, 256, 256, W, 4, &s.w_off);
+      push(f, s);
+    }
+    s = make_step(EPI_RGB_HEAD, 128, 4, {0, 1, 2, 3}, slot_r, -1, 0, ly[h->iR0].b);
+    add_chunks(pl, ly[h->iR0].w, W, false, 128, 128, W, 4, &s.w_off);
+    push(f, s);
+  }
+  {  // ---------------- backward (B operand = W^T: n = input unit, k = output unit)
+    Program& b = pl.bwd_full;
+    b.n_steps = 0; b.n_mask_slots = f.n_mask_slots;
+    Step s = make_step(EPI_B_MASK, 256, 2, {0, 1}, slot_vv + Bt, -1, 1, nullptr);          // through rgb.0 -> d T_Bt, mask of T_Bt
+    add_chunks(pl, ly[h->iR0].w, W, true, 256, 256, 128, 2, &s.w_off);
+    push(b, s);
+    for (int j = Bt; j >= 1; --j) {                                                        // through texture_layer_j
+      s = make_step(EPI_B_MASK, 256, 4, {0, 1, 2, 3}, slot_vv + j - 1, Bs + j - 1, 1, nullptr);
+      add_chunks(pl, ly[h->iT(j)].w, W, true, 256, 256, W, 4, &s.w_off);
+      push(b, s);
+    }
+    s = make_step(EPI_B_EV, 256, 4, {0, 1, 2, 3}, -1, -1, 1, nullptr);                     // through encoding_viewdir
+    add_chunks(pl, ly[h->iEV].w, W + dv, true, 256, 256, W, 4, &s.w_off);
+    add_chunks(pl, ly[h->iEV].w + W, W + dv, true, dv, 64, W, 4, &s.w2_off);
+    s.n2_out = 64;
+    push(b, s);
+    s = make_step(EPI_B_MASK, 256, 4, {0, 1, 2, 3}, Bs, -1, 1, nullptr);                   // through encoding_shape, mask of H_Bs
+    add_chunks(pl, ly[h->iES].w, W, true, 256, 256, W, 4, &s.w_off);
+    push(b, s);
+    for (int j = Bs; j >= 1; --j) {                                                        // through shape_layer_j
+      s = make_step(EPI_B_MASK, 256, 4, {0, 1, 2, 3}, j - 1, j - 1, 1, nullptr);
+      add_chunks(pl, ly[h->iS(j)].w, W, true, 256, 256, W, 4, &s.w_off);
+      push(b, s);
+    }
+    s = make_step(EPI_B_XYZ, 64, 4, {0, 1, 2, 3}, -1, -1, 0, nullptr);                     // through encoding_xyz -> d PE(xyz)
+    add_chunks(pl, ly[h->iX].w, dx, true, dx, 64, W, 4, &s.w_off);
+    push(b, s);
+    // variant without pose gradients: drop the last step and the d PE(viewdir) group; the new last step feeds nobody
+    pl.bwd_noxyz = b;
+    Program& n = pl.bwd_noxyz;
+    n.n_steps = b.n_steps - 1;
+    n.s[n.n_steps - 1].produce_a = 0;
+    for (int i = 0; i < n.n_steps; ++i) if (n.s[i].epi == EPI_B_EV) n.s[i].n2_out = 0;
+  }
+  return pl;
+}
+
+size_t tc_packed_bytes(const snb_handle_s* h) {
+  const char* why;
+  if (!tc_supported(h, &why)) return 16;
+  return build_plan(h).total_bytes + 1024;
+}
+
+int tc_pack_weights(snb_handle_s* h, void* packed, cudaStream_t st) {
+  const char* why = "";
+  SNB_REQUIRE(tc_supported(h, &why), "snb_pack_weights: %s", why);
+  SNB_REQUIRE(((uintptr_t)packed & 15) == 0, "snb_pack_weights: buffer must be 16-byte aligned");
+  TcPlan pl = build_plan(h);
+  for (size_t i = 0; i < pl.jobs.size(); i += kJobsPerLaunch) {
+    PackJobs jb;
+    jb.n = (int)std::min<size_t>(kJobsPerLaunch, pl.jobs.size() - i);
+    for (int k = 0; k < jb.n; ++k) jb.j[k] = pl.jobs[i + k];
+    pack_kernel<<<jb.n, 256, 0, st>>>(jb, (uint8_t*)packed);
+    SNB_LAUNCH_CHECK();
+  }
+  h->packed = packed;
+  return 0;
+}
+
+static inline int64_t tiles_of(int64_t M) { return (M + kTileM - 1) / kTileM; }
+
+// workspace: [zlat (Bs+Bt)*B*256 fp32][masks tiles*slots*8*128 u32]
+static size_t ws_zlat_bytes(const snb_handle_s* h, int64_t B) {
+  return (size_t)(h->arch.shape_blocks + h->arch.texture_blocks) * B * 256 * sizeof(float);
+}
+size_t tc_workspace_bytes(const snb_handle_s* h, int64_t M, int64_t B) {
+  const int slots = h->arch.shape_blocks + h->arch.texture_blocks + 3;
+  return ws_zlat_bytes(h, B) + (size_t)tiles_of(M) * slots * 8 * 128 * 4 + 256;
+}
+size_t tc_bwd_scratch_bytes(const snb_handle_s* h, int64_t, int64_t B) { return ws_zlat_bytes(h, B) + 256; }
+
+static int tc_common_checks(const snb_handle_s* h, int64_t M, int64_t B, const char* who) {
+  const char* why = "";
+  SNB_REQUIRE(tc_supported(h, &why), "%s: %s", who, why);
+  SNB_REQUIRE(h->packed != nullptr, "%s: weights not packed (call snb_pack_weights)", who);
+  SNB_REQUIRE((M / B) % kTileM == 0, "%s: bf16 mode needs samples-per-object (%lld) to be a multiple of %d; use fp32 mode",
+              who, (long long)(M / B), kTileM);
+  return 0;
+}
+
+static void fill_common(Params& p, const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
+                        const float* zlat, uint32_t* masks) {
+  p = Params{};
+  p.xyz = xyz; p.viewdir = viewdir; p.M = M; p.B = B; p.rows_per_obj = M / B;
+  p.packed = (const uint8_t*)h->packed; p.zlat = zlat; p.masks = masks;
+  p.wsig = h->layers[h->iSG].w; p.bsig = h->layers[h->iSG].b;
+  p.w2 = h->layers[h->iR2].w; p.b2 = h->layers[h->iR2].b;
+}
+
+static int tc_grid(int64_t M) {
+  const int sms = sm_count();
+  const int64_t t = tiles_of(M);
+  return (int)(t < sms ? t : sms);
+}
+
+static float* g_tc_debug_acts = nullptr;  // test hook (snb_tc_set_debug): per-step post-epilogue fp32 activations
+void tc_set_debug(float* acts) { g_tc_debug_acts = acts; }
+
+int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
+               const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, void* ws, cudaStream_t st) {
+  if (tc_common_checks(h, M, B, "mlp_fwd(bf16)")) return 2;
+  float* zlat = (float*)ws;
+  uint32_t* masks = (uint32_t*)((uint8_t*)ws + ((ws_zlat_bytes(h, B) + 255) & ~size_t(255)));
+  if (latent_forward(h, B, shape_latent, texture_latent, zlat, st)) return 1;
+  TcPlan pl = build_plan(h);
+  Params p;
+  fill_common(p, h, xyz, viewdir, M, B, zlat, masks);
+  p.sigma = sigma; p.rgb = rgb; p.dbg = g_tc_debug_acts;
+  p.prog = pl.fwd;
+  SNB_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
+  tc_fwd_kernel<<<tc_grid(M), kThreads, SM_ALLOC, st>>>(p);
+  SNB_LAUNCH_CHECK();
+  return 0;
+}
+
+int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
+                const float* shape_latent, const float* texture_latent, const float* sigma, const float* g_sigma,
+                const float* g_rgb, const void* ws, void* scratch, float* g_xyz, float* g_viewdir, float* g_shape_latent,
+                float* g_texture_latent, float* const* g_weights, cudaStream_t st) {
+  if (tc_common_checks(h, M, B, "mlp_bwd(bf16)")) return 2;
+  SNB_REQUIRE(g_weights == nullptr,
+              "mlp_bwd(bf16): weight gradients are not produced by the bf16 back end; freeze the weights "
+              "(requires_grad_(False)) or use precision='fp32'");
+  SNB_REQUIRE((g_xyz == nullptr) == (g_viewdir == nullptr), "mlp_bwd(bf16): request both g_xyz and g_viewdir or neither");
+  const float* zlat = (const float*)ws;
+  uint32_t* masks = (uint32_t*)((uint8_t*)ws + ((ws_zlat_bytes(h, B) + 255) & ~size_t(255)));
+  float* g_zlat = (float*)scratch;
+  SNB_CHECK_CUDA(cudaMemsetAsync(g_zlat, 0, ws_zlat_bytes(h, B), st));
+  TcPlan pl = build_plan(h);
+  Params p;
+  fill_common(p, h, xyz, viewdir, M, B, zlat, masks);
+  p.sigma_in = sigma; p.g_sigma = g_sigma; p.g_rgb = g_rgb; p.g_xyz = g_xyz; p.g_viewdir = g_viewdir; p.g_zlat = g_zlat;
+  p.r0_mask_slot = pl.r0_slot;
+  p.n_latent = h->arch.shape_blocks + h->arch.texture_blocks;
+  p.prog = g_xyz ? pl.bwd_full : pl.bwd_noxyz;
+  SNB_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
+  tc_bwd_kernel<<<tc_grid(M), kThreads, SM_ALLOC, st>>>(p);
+  SNB_LAUNCH_CHECK();
+  return latent_backward(h, B, shape_latent, texture_latent, zlat, g_zlat, g_shape_latent, g_texture_latent, nullptr, st);
+}
+
 }  // namespace snb

@@ -36,6 +36,23 @@ def _pixel_grid(roi, uv_steps=None):
     return px, py
 
 
+_GRID_CACHE = {}
+
+
+def _pixel_grid_on(dev, roi, uv_steps):
+    """Device copy of the host-built pixel grid, cached per (roi, uv_steps, device): the grid is a pure function of
+    its integer arguments, so re-rendering the same crop (every refine iteration) costs no host->device copy."""
+    key = (tuple(int(v) for v in roi), None if uv_steps is None else (int(uv_steps[0]), int(uv_steps[1])), str(dev))
+    hit = _GRID_CACHE.get(key)
+    if hit is None:
+        if len(_GRID_CACHE) > 256:
+            _GRID_CACHE.clear()
+        px, py = _pixel_grid(roi, uv_steps)
+        hit = (px.to(dev, torch.float32), py.to(dev, torch.float32))
+        _GRID_CACHE[key] = hit
+    return hit
+
+
 def _rays(K, c2w, px, py):
     dev = _device_of(c2w, K)
     ro, vd = ops.get_rays_from_pixels(px.to(dev, torch.float32), py.to(dev, torch.float32), K.to(dev), c2w.to(dev))
@@ -46,7 +63,7 @@ def _rays(K, c2w, px, py):
 
 def get_rays(K, c2w, roi, uv_steps=None):
     """utils.py:107-135."""
-    px, py = _pixel_grid(roi, uv_steps)
+    px, py = _pixel_grid_on(_device_of(c2w, K), roi, uv_steps)
     return _rays(K, c2w, px, py)
 
 
