@@ -25,22 +25,27 @@ namespace snb {
 namespace tc {
 
 constexpr int kTileM = 128;
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr uint32_t kStageBytes = 32768;   // [256 n][64 k] bf16
 constexpr uint32_t kChunkBytes = 16384;   // [128 m][64 k] bf16
-constexpr int kMaxSteps = 24;
+constexpr int kMaxSteps = 16;
+constexpr int kMaxFwdSteps = 12;
 constexpr int kThreads = 320;
-constexpr int kEpiThreads = 256;
 constexpr int kMaxLatentSlots = 8;
 
-constexpr uint32_t SM_A = 0;
-constexpr uint32_t SM_AUX = 4 * kChunkBytes;                    // chunk index 4
-constexpr uint32_t SM_W = 5 * kChunkBytes;                      // 81920
-constexpr uint32_t SM_PART = SM_W + kStages * kStageBytes;      // 212992
-constexpr uint32_t SM_PART_BYTES = (2 * 128 * 3 + 2 * 128 + kMaxLatentSlots * 256) * 4;  // 12288
-constexpr uint32_t SM_BARS = SM_PART + SM_PART_BYTES;
+// shared-memory map (bytes from the 1024-aligned base)
+constexpr uint32_t SM_W = 5 * kChunkBytes;                       // A chunks 0..3, AUX chunk 4, then the weight ring
+constexpr uint32_t SM_TAB = SM_W + kStages * kStageBytes;        // fp32 tables
+constexpr uint32_t TAB_BIAS = 0;                                 // fwd: [kMaxFwdSteps][256]   bwd: colsum [8][256] at the same place
+constexpr uint32_t TAB_Z = TAB_BIAS + kMaxFwdSteps * 256 * 4;    // fwd: [8][256] latent vectors of the current object
+constexpr uint32_t TAB_WSIG = TAB_Z + kMaxLatentSlots * 256 * 4; // [256]
+constexpr uint32_t TAB_W2 = TAB_WSIG + 256 * 4;                  // [3][128]
+constexpr uint32_t TAB_PART = TAB_W2 + 384 * 4;                  // fwd: sig_part [2][128] + rgb_part [2][128][3]; bwd: xyz_part [2][128][3]
+constexpr uint32_t TAB_BYTES = TAB_PART + (256 + 768) * 4;
+constexpr uint32_t SM_BARS = SM_TAB + TAB_BYTES;
 constexpr uint32_t SM_TOTAL = SM_BARS + 32 * 8 + 16;
-constexpr uint32_t SM_ALLOC = SM_TOTAL + 1024;                  // + alignment slack
+constexpr uint32_t SM_ALLOC = SM_TOTAL + 1024;                   // + alignment slack
+static_assert(SM_ALLOC <= 232448, "shared memory budget");
 
 enum Epi : int { EPI_RELU = 0, EPI_LINEAR_SIGMA = 1, EPI_RGB_HEAD = 2, EPI_B_MASK = 3, EPI_B_EV = 4, EPI_B_XYZ = 5 };
 
@@ -70,7 +75,7 @@ struct Params {
   // backward
   const float* sigma_in; const float* g_sigma; const float* g_rgb;
   float* g_xyz; float* g_viewdir; float* g_zlat;   // g_zlat [(Bs+Bt)][B][256], accumulated with atomics
-  int r0_mask_slot, n_latent;
+  int r0_mask_slot, n_latent, ev_step;
   Program prog;
 };
 
@@ -122,7 +127,8 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+// issue a 32-column TMEM load of this thread's lane (no wait)
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -132,7 +138,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  tmem_ld32_issue(taddr, r);
+  tmem_ld_wait();
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -225,11 +235,18 @@ struct Smem {
   __device__ uint8_t* chunk(int c) const { return base + (uint32_t)c * kChunkBytes; }
   __device__ uint32_t chunk_u32(int c) const { return base_u32 + (uint32_t)c * kChunkBytes; }
   __device__ uint32_t stage_u32(int s) const { return base_u32 + SM_W + (uint32_t)s * kStageBytes; }
-  __device__ float* part() const { return reinterpret_cast<float*>(base + SM_PART); }
+  __device__ float* tab(uint32_t off) const { return reinterpret_cast<float*>(base + SM_TAB + off); }
   __device__ uint32_t bar(int i) const { return base_u32 + SM_BARS + 8u * i; }
 };
 // barrier indices
-constexpr int BAR_WFULL = 0, BAR_WEMPTY = 4, BAR_AREADY = 8, BAR_ACC = 13, BAR_COUNT = 15;
+constexpr int BAR_WFULL = 0, BAR_WEMPTY = 4, BAR_AREADY = 8, BAR_ACC = 13;
+
+// per-thread view of the epilogue role
+struct EpiCtx {
+  uint32_t lane, hh, row, lane_field, tmem_base;
+  int64_t grow;      // global sample row of this thread
+  bool valid;
+};
 
 // ------------------------------------------------------------------------------------------ roles shared by fwd / bwd
 __device__ __forceinline__ void producer_loop(const Params& p, const Smem& sm, int64_t n_tiles, uint32_t lane) {
@@ -243,8 +260,8 @@ __device__ __forceinline__ void producer_loop(const Params& p, const Smem& sm, i
         const uint32_t off0 = g == 0 ? st.w_off : st.w2_off;
         for (int kc = 0; kc < st.n_chunks; ++kc, ++it) {
           const uint32_t stage = it % kStages, ph = (it / kStages) & 1u;
-          mbar_wait(sm.bar(BAR_WEMPTY + stage), ph ^ 1u);
           if (lane == 0) {
+            mbar_wait(sm.bar(BAR_WEMPTY + stage), ph ^ 1u);
             mbar_expect_tx(sm.bar(BAR_WFULL + stage), bytes);
             bulk_g2s(sm.stage_u32(stage), p.packed + off0 + (size_t)kc * bytes, bytes, sm.bar(BAR_WFULL + stage));
           }
@@ -269,20 +286,18 @@ __device__ __forceinline__ void mma_loop(const Params& p, const Smem& sm, int64_
         const uint32_t idesc = umma_idesc(128, n);
         for (int kc = 0; kc < st.n_chunks; ++kc, ++it) {
           const int ac = st.a_chunk[kc];
-          if (g == 0) {
-            mbar_wait(sm.bar(BAR_AREADY + ac), (a_phase >> ac) & 1u);
-            a_phase ^= 1u << ac;
-          }
           const uint32_t stage = it % kStages, ph = (it / kStages) & 1u;
-          mbar_wait(sm.bar(BAR_WFULL + stage), ph);
-          tc_fence_after();
           if (lane == 0) {
+            if (g == 0) mbar_wait(sm.bar(BAR_AREADY + ac), (a_phase >> ac) & 1u);
+            mbar_wait(sm.bar(BAR_WFULL + stage), ph);
+            tc_fence_after();
             const uint32_t a0 = sm.chunk_u32(ac), b0 = sm.stage_u32(stage);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
               umma_bf16(d_tmem, umma_desc(a0 + kk * 32), umma_desc(b0 + kk * 32), idesc, (kc > 0 || kk > 0) ? 1u : 0u);
             umma_commit(sm.bar(BAR_WEMPTY + stage));
           }
+          if (g == 0) a_phase ^= 1u << ac;
           __syncwarp();
         }
       }
@@ -308,17 +323,11 @@ __device__ __forceinline__ void store_row32(uint8_t* chunk, uint32_t row, uint32
   }
 }
 
-// ------------------------------------------------------------------------------------------ forward kernel
-__global__ void __launch_bounds__(kThreads, 1) tc_fwd_kernel(const __grid_constant__ Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  Smem sm;
-  {
-    const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
-    sm.base = smem_raw + pad;
-    sm.base_u32 = raw + pad;
-  }
-  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+__device__ __forceinline__ void kernel_prologue(Smem& sm, uint8_t* smem_raw, uint32_t tid, uint32_t warp, uint32_t& tmem_base) {
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
+  sm.base = smem_raw + pad;
+  sm.base_u32 = raw + pad;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.base + SM_BARS + 32 * 8);
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(sm.bar(BAR_WFULL + i), 1); mbar_init(sm.bar(BAR_WEMPTY + i), 1); }
@@ -330,7 +339,107 @@ __global__ void __launch_bounds__(kThreads, 1) tc_fwd_kernel(const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  tmem_base = *tmem_slot;
+}
+
+// ------------------------------------------------------------------------------------------ forward epilogues
+// One layer's epilogue for this thread's row: TMEM -> (+bias, ReLU, mask bits, +latent) -> bf16 -> shared-memory A operand.
+// The TMEM load of chunk c+1 is in flight while chunk c is processed.
+template <int EPI, bool LAT, bool DBG>
+__device__ __forceinline__ void fwd_epilogue(const Params& p, const Smem& sm, const Step& st, int si, uint32_t half, const EpiCtx& e,
+                                             uint32_t* mask_tile, float& sig_acc, float (&rgb_acc)[3]) {
+  constexpr int NC = (EPI == EPI_RGB_HEAD) ? 2 : 4;
+  const float* bias_s = sm.tab(TAB_BIAS) + si * 256;
+  const float* z_s = sm.tab(TAB_Z) + (LAT ? st.latent_slot : 0) * 256;
+  const float* wsig_s = sm.tab(TAB_WSIG);
+  const float* w2_s = sm.tab(TAB_W2);
+  const uint32_t t0 = e.tmem_base + half * 256u + e.hh * 32u + e.lane_field;
+  uint32_t ra[32], rb[32];
+  tmem_ld32_issue(t0, ra);
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    uint32_t (&r)[32] = (c & 1) ? rb : ra;
+    tmem_ld_wait();
+    if (c + 1 < NC) tmem_ld32_issue(t0 + (uint32_t)(c + 1) * 64u, (c & 1) ? ra : rb);
+    const int col0 = c * 64 + (int)e.hh * 32;
+    uint32_t pk[16], mask = 0;
+#pragma unroll
+    for (int i4 = 0; i4 < 8; ++i4) {
+      const float4 bb = *reinterpret_cast<const float4*>(bias_s + col0 + 4 * i4);
+      float v[4] = {__uint_as_float(r[4 * i4]) + bb.x, __uint_as_float(r[4 * i4 + 1]) + bb.y,
+                    __uint_as_float(r[4 * i4 + 2]) + bb.z, __uint_as_float(r[4 * i4 + 3]) + bb.w};
+      if (EPI != EPI_LINEAR_SIGMA) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v[u] = fmaxf(v[u], 0.f);
+          mask |= (v[u] > 0.f ? 1u : 0u) << (4 * i4 + u);
+        }
+      }
+      if (EPI == EPI_LINEAR_SIGMA) {
+        const float4 ws = *reinterpret_cast<const float4*>(wsig_s + col0 + 4 * i4);
+        sig_acc += v[0] * ws.x + v[1] * ws.y + v[2] * ws.z + v[3] * ws.w;
+      }
+      if (EPI == EPI_RGB_HEAD) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float4 ww = *reinterpret_cast<const float4*>(w2_s + k * 128 + col0 + 4 * i4);
+          rgb_acc[k] += v[0] * ww.x + v[1] * ww.y + v[2] * ww.z + v[3] * ww.w;
+        }
+      }
+      if (DBG) {
+        if (e.valid) {
+          float* d = p.dbg + ((size_t)si * p.M + e.grow) * 256 + col0 + 4 * i4;
+          d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; d[3] = v[3];
+        }
+      }
+      if (LAT) {
+        const float4 zz = *reinterpret_cast<const float4*>(z_s + col0 + 4 * i4);
+        v[0] += zz.x; v[1] += zz.y; v[2] += zz.z; v[3] += zz.w;
+      }
+      pk[2 * i4] = pack_bf16(v[0], v[1]);
+      pk[2 * i4 + 1] = pack_bf16(v[2], v[3]);
+    }
+    if (EPI != EPI_LINEAR_SIGMA) mask_tile[((size_t)st.mask_slot * 8 + c * 2 + e.hh) * 128 + e.row] = mask;
+    if (EPI != EPI_RGB_HEAD) {
+      store_row32(sm.chunk(c), e.row, e.hh, pk);
+      publish_chunk(sm, c, e.lane);
+    }
+  }
+}
+
+template <bool DBG>
+__device__ __forceinline__ void fwd_epilogue_dispatch(const Params& p, const Smem& sm, const Step& st, int si, uint32_t half,
+                                                      const EpiCtx& e, uint32_t* mask_tile, float& sig_acc, float (&rgb_acc)[3]) {
+  if (st.epi == EPI_RELU) {
+    if (st.latent_slot >= 0) fwd_epilogue<EPI_RELU, true, DBG>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc);
+    else fwd_epilogue<EPI_RELU, false, DBG>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc);
+  } else if (st.epi == EPI_LINEAR_SIGMA) {
+    fwd_epilogue<EPI_LINEAR_SIGMA, false, DBG>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc);
+  } else {
+    fwd_epilogue<EPI_RGB_HEAD, false, DBG>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ forward kernel
+__global__ void __launch_bounds__(kThreads, 1) tc_fwd_kernel(const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem sm;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t tmem_base;
+  {  // static tables: every layer's bias, the sigma / rgb head weights
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* b = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    float* bias_s = reinterpret_cast<float*>(b + SM_TAB + TAB_BIAS);
+    for (int i = tid; i < p.prog.n_steps * 256; i += kThreads) {
+      const int si = i >> 8, c = i & 255;
+      bias_s[i] = c < p.prog.s[si].n_out ? __ldg(p.prog.s[si].bias + c) : 0.f;
+    }
+    float* wsig_s = reinterpret_cast<float*>(b + SM_TAB + TAB_WSIG);
+    for (int i = tid; i < 256; i += kThreads) wsig_s[i] = __ldg(p.wsig + i);
+    float* w2_s = reinterpret_cast<float*>(b + SM_TAB + TAB_W2);
+    for (int i = tid; i < 384; i += kThreads) w2_s[i] = __ldg(p.w2 + i);
+  }
+  kernel_prologue(sm, smem_raw, tid, warp, tmem_base);
   const int64_t n_tiles = (p.M + kTileM - 1) / kTileM;
 
   if (warp == 8) {
@@ -338,23 +447,41 @@ __global__ void __launch_bounds__(kThreads, 1) tc_fwd_kernel(const __grid_consta
   } else if (warp == 9) {
     mma_loop(p, sm, n_tiles, lane, tmem_base);
   } else {
-    const uint32_t q = warp & 3u, hh = warp >> 2;
-    const uint32_t row = q * 32u + lane;                 // row inside the tile == TMEM lane
-    const uint32_t lane_field = (q * 32u) << 16;
-    float* sig_part = sm.part();                         // [2][128]
-    float* rgb_part = sm.part() + 256;                   // [2][128][3]
+    EpiCtx e;
+    e.lane = lane; e.hh = warp >> 2; e.row = (warp & 3u) * 32u + lane; e.lane_field = ((warp & 3u) * 32u) << 16;
+    e.tmem_base = tmem_base;
+    float* sig_part = sm.tab(TAB_PART);          // [2][128]
+    float* rgb_part = sm.tab(TAB_PART) + 256;    // [2][128][3]
+    float* z_s = sm.tab(TAB_Z);
     uint32_t gstep = 0, acc_cnt[2] = {0, 0};
     const int nslots = p.prog.n_mask_slots;
+    int64_t cur_obj = -1;
+    // PE(xyz) of the first tile; later tiles are encoded one tile ahead (during the encoding_viewdir epilogue)
+    if ((int64_t)blockIdx.x < n_tiles) {
+      int64_t r0 = (int64_t)blockIdx.x * kTileM + e.row;
+      if (r0 > p.M - 1) r0 = p.M - 1;
+      const float x[3] = {__ldg(p.xyz + 3 * r0), __ldg(p.xyz + 3 * r0 + 1), __ldg(p.xyz + 3 * r0 + 2)};
+      write_pe_row<10>(sm.chunk(4), e.row, e.hh, x);
+      publish_chunk(sm, 4, lane);
+    }
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t grow = tile * kTileM + row;
-      const bool valid = grow < p.M;
-      const int64_t crow = valid ? grow : p.M - 1;
-      int64_t obj = crow / p.rows_per_obj;
-      if (obj > p.B - 1) obj = p.B - 1;
-      {
-        const float x[3] = {__ldg(p.xyz + 3 * crow), __ldg(p.xyz + 3 * crow + 1), __ldg(p.xyz + 3 * crow + 2)};
-        write_pe_row<10>(sm.chunk(4), row, hh, x);
-        publish_chunk(sm, 4, lane);
+      e.grow = tile * kTileM + e.row;
+      e.valid = e.grow < p.M;
+      const int64_t crow = e.valid ? e.grow : p.M - 1;
+      const int64_t next_tile = tile + gridDim.x;
+      float xn[3] = {0.f, 0.f, 0.f};
+      if (next_tile < n_tiles) {  // prefetch the next tile's coordinates: consumed ~5 layers from now
+        int64_t rn = next_tile * kTileM + e.row;
+        if (rn > p.M - 1) rn = p.M - 1;
+        xn[0] = __ldg(p.xyz + 3 * rn); xn[1] = __ldg(p.xyz + 3 * rn + 1); xn[2] = __ldg(p.xyz + 3 * rn + 2);
+      }
+      const float dir[3] = {__ldg(p.viewdir + 3 * crow), __ldg(p.viewdir + 3 * crow + 1), __ldg(p.viewdir + 3 * crow + 2)};
+      const int64_t obj = (tile * kTileM) / p.rows_per_obj;   // tiles never straddle objects (checked on the host)
+      if (obj != cur_obj) {  // (re)load the per-object latent vectors; all epilogue warps are between tiles here
+        cur_obj = obj;
+        for (int i = tid; i < p.n_latent * 256; i += 256)
+          z_s[i] = __ldg(p.zlat + ((size_t)(i >> 8) * p.B + obj) * 256 + (i & 255));
+        epi_bar_sync();
       }
       uint32_t* mask_tile = p.masks + (size_t)tile * nslots * 8 * 128;
       float sig_acc = 0.f, rgb_acc[3] = {0.f, 0.f, 0.f};
@@ -364,72 +491,29 @@ __global__ void __launch_bounds__(kThreads, 1) tc_fwd_kernel(const __grid_consta
         mbar_wait(sm.bar(BAR_ACC + half), acc_cnt[half] & 1u);
         acc_cnt[half]++;
         tc_fence_after();
-        if (si == 0) {  // layer 0's MMAs are done with PE(xyz): reuse the AUX chunk for PE(viewdir)
-          const float d[3] = {__ldg(p.viewdir + 3 * crow), __ldg(p.viewdir + 3 * crow + 1), __ldg(p.viewdir + 3 * crow + 2)};
-          write_pe_row<4>(sm.chunk(4), row, hh, d);
+        if (si == 0) {  // layer 0's MMAs are done with PE(xyz): the AUX chunk now takes PE(viewdir)
+          write_pe_row<4>(sm.chunk(4), e.row, e.hh, dir);
+          publish_chunk(sm, 4, lane);
+        } else if (si == p.ev_step && next_tile < n_tiles) {  // encoding_viewdir's MMAs are done with PE(viewdir)
+          write_pe_row<10>(sm.chunk(4), e.row, e.hh, xn);
           publish_chunk(sm, 4, lane);
         }
-        const int n_c = st.n_out / 64;
-        const float* zl = st.latent_slot >= 0 ? p.zlat + ((size_t)st.latent_slot * p.B + obj) * 256 : nullptr;
-        for (int c = 0; c < n_c; ++c) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + half * 256u + (uint32_t)c * 64u + hh * 32u + lane_field, r);
-          const int col0 = c * 64 + (int)hh * 32;
-          const float4* b4 = reinterpret_cast<const float4*>(st.bias + col0);
-          uint32_t pk[16], mask = 0;
-#pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 bb = __ldg(b4 + i4);
-            float v[4] = {__uint_as_float(r[4 * i4]) + bb.x, __uint_as_float(r[4 * i4 + 1]) + bb.y,
-                          __uint_as_float(r[4 * i4 + 2]) + bb.z, __uint_as_float(r[4 * i4 + 3]) + bb.w};
-            if (st.epi != EPI_LINEAR_SIGMA) {
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                v[u] = fmaxf(v[u], 0.f);
-                mask |= (v[u] > 0.f ? 1u : 0u) << (4 * i4 + u);
-              }
-            }
-            if (st.epi == EPI_LINEAR_SIGMA) {
-              const float4 ws = __ldg(reinterpret_cast<const float4*>(p.wsig + col0) + i4);
-              sig_acc += v[0] * ws.x + v[1] * ws.y + v[2] * ws.z + v[3] * ws.w;
-            } else if (st.epi == EPI_RGB_HEAD) {
-#pragma unroll
-              for (int k = 0; k < 3; ++k) {
-                const float4 ww = __ldg(reinterpret_cast<const float4*>(p.w2 + k * 128 + col0) + i4);
-                rgb_acc[k] += v[0] * ww.x + v[1] * ww.y + v[2] * ww.z + v[3] * ww.w;
-              }
-            }
-            if (p.dbg != nullptr && valid) {
-              float* d = p.dbg + ((size_t)si * p.M + grow) * 256 + col0 + 4 * i4;
-              d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; d[3] = v[3];
-            }
-            if (zl != nullptr) {
-              const float4 zz = __ldg(reinterpret_cast<const float4*>(zl + col0) + i4);
-              v[0] += zz.x; v[1] += zz.y; v[2] += zz.z; v[3] += zz.w;
-            }
-            pk[2 * i4] = pack_bf16(v[0], v[1]);
-            pk[2 * i4 + 1] = pack_bf16(v[2], v[3]);
-          }
-          if (st.mask_slot >= 0) mask_tile[((size_t)st.mask_slot * 8 + c * 2 + hh) * 128 + row] = mask;
-          if (st.produce_a) {
-            store_row32(sm.chunk(c), row, hh, pk);
-            publish_chunk(sm, c, lane);
-          }
-        }
-        if (st.epi == EPI_LINEAR_SIGMA) sig_part[hh * 128 + row] = sig_acc;
-        if (st.epi == EPI_RGB_HEAD) {
-#pragma unroll
-          for (int k = 0; k < 3; ++k) rgb_part[(hh * 128 + row) * 3 + k] = rgb_acc[k];
-        }
+        if (p.dbg != nullptr) fwd_epilogue_dispatch<true>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc);
+        else fwd_epilogue_dispatch<false>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc);
         tc_fence_before();
       }
-      epi_bar_sync();
-      if (hh == 0 && valid) {
-        const float sp = sig_part[row] + sig_part[128 + row] + __ldg(p.bsig);
-        p.sigma[grow] = sp > 20.f ? sp : log1pf(expf(sp));   // nn.Softplus(): beta 1, threshold 20
+      sig_part[e.hh * 128 + e.row] = sig_acc;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) p.rgb[3 * grow + k] = rgb_part[row * 3 + k] + rgb_part[(128 + row) * 3 + k] + __ldg(p.b2 + k);
+      for (int k = 0; k < 3; ++k) rgb_part[(e.hh * 128 + e.row) * 3 + k] = rgb_acc[k];
+      epi_bar_sync();
+      if (e.hh == 0 && e.valid) {
+        const float sp = sig_part[e.row] + sig_part[128 + e.row] + __ldg(p.bsig);
+        p.sigma[e.grow] = sp > 20.f ? sp : log1pf(expf(sp));   // nn.Softplus(): beta 1, threshold 20
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          p.rgb[3 * e.grow + k] = rgb_part[e.row * 3 + k] + rgb_part[(128 + e.row) * 3 + k] + __ldg(p.b2 + k);
       }
+      epi_bar_sync();   // sig_part / rgb_part are rewritten at the end of the next tile only, but z_s may be reloaded next
     }
   }
   tc_fence_before();
@@ -437,36 +521,88 @@ __global__ void __launch_bounds__(kThreads, 1) tc_fwd_kernel(const __grid_consta
   if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
-// ------------------------------------------------------------------------------------------ backward kernel
+// ------------------------------------------------------------------------------------------ backward epilogues
 __device__ __forceinline__ uint32_t mask_word(const uint32_t* mask_tile, int slot, int word, uint32_t row) {
   return __ldg(mask_tile + ((size_t)slot * 8 + word) * 128 + row);
 }
 
+// acc = gradient w.r.t. the layer's input.  Optional: per-object column sums of it (latent gradient); then mask by the
+// producing layer's ReLU bits and hand on as the next A operand.  EV: add the sigma-head gradient first, no mask.
+template <bool EV, bool COLSUM, bool MASK, bool PRODUCE>
+__device__ __forceinline__ void bwd_epilogue(const Smem& sm, const Step& st, uint32_t half, const EpiCtx& e,
+                                             const uint32_t* mask_tile, float gsp) {
+  const float* wsig_s = sm.tab(TAB_WSIG);
+  float* colsum = sm.tab(TAB_BIAS);
+  const uint32_t t0 = e.tmem_base + half * 256u + e.hh * 32u + e.lane_field;
+  uint32_t ra[32], rb[32];
+  tmem_ld32_issue(t0, ra);
+  uint32_t mw_next = 0xffffffffu;
+  if (MASK) mw_next = mask_word(mask_tile, st.mask_slot, (int)e.hh, e.row);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t (&r)[32] = (c & 1) ? rb : ra;
+    tmem_ld_wait();
+    if (c + 1 < 4) tmem_ld32_issue(t0 + (uint32_t)(c + 1) * 64u, (c & 1) ? ra : rb);
+    const uint32_t mw = mw_next;
+    if (MASK && c + 1 < 4) mw_next = mask_word(mask_tile, st.mask_slot, (c + 1) * 2 + (int)e.hh, e.row);
+    const int col0 = c * 64 + (int)e.hh * 32;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    if (EV) {
+#pragma unroll
+      for (int i4 = 0; i4 < 8; ++i4) {
+        const float4 ws = *reinterpret_cast<const float4*>(wsig_s + col0 + 4 * i4);
+        v[4 * i4] += gsp * ws.x; v[4 * i4 + 1] += gsp * ws.y; v[4 * i4 + 2] += gsp * ws.z; v[4 * i4 + 3] += gsp * ws.w;
+      }
+    }
+    if (PRODUCE) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float a = (!MASK || ((mw >> (2 * i)) & 1u)) ? v[2 * i] : 0.f;
+        const float b = (!MASK || ((mw >> (2 * i + 1)) & 1u)) ? v[2 * i + 1] : 0.f;
+        pk[i] = pack_bf16(a, b);
+      }
+      store_row32(sm.chunk(c), e.row, e.hh, pk);
+      publish_chunk(sm, c, e.lane);   // the MMA warp can start the next layer on this chunk while we reduce below
+    }
+    if (COLSUM) {
+      const float cs = warp_colsum32(v, e.lane);
+      atomicAdd(colsum + st.latent_slot * 256 + col0 + e.lane, cs);
+    }
+  }
+}
+
+__device__ __forceinline__ void bwd_epilogue_dispatch(const Smem& sm, const Step& st, uint32_t half, const EpiCtx& e,
+                                                      const uint32_t* mask_tile, float gsp) {
+  if (st.epi == EPI_B_EV) {
+    bwd_epilogue<true, false, false, true>(sm, st, half, e, mask_tile, gsp);
+  } else if (st.latent_slot >= 0) {
+    if (st.produce_a) bwd_epilogue<false, true, true, true>(sm, st, half, e, mask_tile, gsp);
+    else bwd_epilogue<false, true, false, false>(sm, st, half, e, mask_tile, gsp);
+  } else {
+    bwd_epilogue<false, false, true, true>(sm, st, half, e, mask_tile, gsp);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ backward kernel
 __global__ void __launch_bounds__(kThreads, 1) tc_bwd_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   Smem sm;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t tmem_base;
   {
     const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
-    sm.base = smem_raw + pad;
-    sm.base_u32 = raw + pad;
+    uint8_t* b = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    float* colsum0 = reinterpret_cast<float*>(b + SM_TAB + TAB_BIAS);
+    for (uint32_t i = tid; i < kMaxLatentSlots * 256; i += kThreads) colsum0[i] = 0.f;
+    float* wsig_s = reinterpret_cast<float*>(b + SM_TAB + TAB_WSIG);
+    for (int i = tid; i < 256; i += kThreads) wsig_s[i] = __ldg(p.wsig + i);
+    float* w2_s = reinterpret_cast<float*>(b + SM_TAB + TAB_W2);
+    for (int i = tid; i < 384; i += kThreads) w2_s[i] = __ldg(p.w2 + i);
   }
-  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.base + SM_BARS + 32 * 8);
-  float* xyz_part = sm.part();                 // [2][128][3]
-  float* colsum = sm.part() + 768 + 256;       // [slots][256]
-  if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(sm.bar(BAR_WFULL + i), 1); mbar_init(sm.bar(BAR_WEMPTY + i), 1); }
-    for (int i = 0; i < 5; ++i) mbar_init(sm.bar(BAR_AREADY + i), 8);
-    for (int i = 0; i < 2; ++i) mbar_init(sm.bar(BAR_ACC + i), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (uint32_t i = tid; i < kMaxLatentSlots * 256; i += kThreads) colsum[i] = 0.f;
-  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  kernel_prologue(sm, smem_raw, tid, warp, tmem_base);
   const int64_t n_tiles = (p.M + kTileM - 1) / kTileM;
 
   if (warp == 8) {
@@ -474,34 +610,36 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_kernel(const __grid_consta
   } else if (warp == 9) {
     mma_loop(p, sm, n_tiles, lane, tmem_base);
   } else {
-    const uint32_t q = warp & 3u, hh = warp >> 2;
-    const uint32_t row = q * 32u + lane;
-    const uint32_t lane_field = (q * 32u) << 16;
-    const uint32_t etid = tid;  // 0..255
+    EpiCtx e;
+    e.lane = lane; e.hh = warp >> 2; e.row = (warp & 3u) * 32u + lane; e.lane_field = ((warp & 3u) * 32u) << 16;
+    e.tmem_base = tmem_base;
+    float* xyz_part = sm.tab(TAB_PART);          // [2][128][3]
+    float* colsum = sm.tab(TAB_BIAS);            // [slots][256]
+    const float* w2_s = sm.tab(TAB_W2);
     uint32_t gstep = 0, acc_cnt[2] = {0, 0};
     const int nslots = p.prog.n_mask_slots;
-    const int n_lat = p.n_latent;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t grow = tile * kTileM + row;
-      const bool valid = grow < p.M;
-      const int64_t crow = valid ? grow : p.M - 1;
+      e.grow = tile * kTileM + e.row;
+      e.valid = e.grow < p.M;
+      const int64_t crow = e.valid ? e.grow : p.M - 1;
       const int64_t obj = (tile * kTileM) / p.rows_per_obj;  // tiles never straddle objects (checked on the host)
       const uint32_t* mask_tile = p.masks + (size_t)tile * nslots * 8 * 128;
-      const float gsg = valid ? __ldg(p.g_sigma + grow) : 0.f;
+      const float gsg = e.valid ? __ldg(p.g_sigma + e.grow) : 0.f;
       const float gsp = gsg * (-expm1f(-__ldg(p.sigma_in + crow)));   // d softplus = 1 - exp(-softplus)
       // ---- prologue: d pre-activation of rgb.0 = (g_rgb W2) * mask -> A chunks 0,1 (128 columns)
       {
         float g3[3] = {0.f, 0.f, 0.f};
-        if (valid) { g3[0] = __ldg(p.g_rgb + 3 * grow); g3[1] = __ldg(p.g_rgb + 3 * grow + 1); g3[2] = __ldg(p.g_rgb + 3 * grow + 2); }
+        if (e.valid) { g3[0] = __ldg(p.g_rgb + 3 * e.grow); g3[1] = __ldg(p.g_rgb + 3 * e.grow + 1); g3[2] = __ldg(p.g_rgb + 3 * e.grow + 2); }
+#pragma unroll
         for (int c = 0; c < 2; ++c) {
-          const int col0 = c * 64 + (int)hh * 32;
-          const uint32_t mw = mask_word(mask_tile, p.r0_mask_slot, c * 2 + hh, row);
+          const int col0 = c * 64 + (int)e.hh * 32;
+          const uint32_t mw = mask_word(mask_tile, p.r0_mask_slot, c * 2 + e.hh, e.row);
           uint32_t pk[16];
 #pragma unroll
           for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w2 + col0) + i4);
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w2 + 128 + col0) + i4);
-            const float4 w2 = __ldg(reinterpret_cast<const float4*>(p.w2 + 256 + col0) + i4);
+            const float4 w0 = *reinterpret_cast<const float4*>(w2_s + col0 + 4 * i4);
+            const float4 w1 = *reinterpret_cast<const float4*>(w2_s + 128 + col0 + 4 * i4);
+            const float4 w2 = *reinterpret_cast<const float4*>(w2_s + 256 + col0 + 4 * i4);
             float v[4] = {g3[0] * w0.x + g3[1] * w1.x + g3[2] * w2.x, g3[0] * w0.y + g3[1] * w1.y + g3[2] * w2.y,
                           g3[0] * w0.z + g3[1] * w1.z + g3[2] * w2.z, g3[0] * w0.w + g3[1] * w1.w + g3[2] * w2.w};
 #pragma unroll
@@ -509,7 +647,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_kernel(const __grid_consta
             pk[2 * i4] = pack_bf16(v[0], v[1]);
             pk[2 * i4 + 1] = pack_bf16(v[2], v[3]);
           }
-          store_row32(sm.chunk(c), row, hh, pk);
+          store_row32(sm.chunk(c), e.row, e.hh, pk);
           publish_chunk(sm, c, lane);
         }
       }
@@ -522,12 +660,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_kernel(const __grid_consta
         if (st.epi == EPI_B_XYZ) {
           // acc = d PE(xyz) (64 columns): fold to d xyz.  g_x = g_0 + sum_f 2^f (g_sin,f cos_f - g_cos,f sin_f)
           uint32_t r[32];
-          tmem_ld32(tmem_base + half * 256u + hh * 32u + lane_field, r);
+          tmem_ld32(e.tmem_base + half * 256u + e.hh * 32u + e.lane_field, r);
           const float x[3] = {__ldg(p.xyz + 3 * crow), __ldg(p.xyz + 3 * crow + 1), __ldg(p.xyz + 3 * crow + 2)};
           float s[10][3], c[10][3];
           trig_ladder<10>(x, s, c);
           float g[3] = {0.f, 0.f, 0.f};
-          if (hh == 0) {  // columns 0..31: x (0-2), sin f=0..8 (3-29), sin f=9 a=0,1 (30,31)
+          if (e.hh == 0) {  // columns 0..31: x (0-2), sin f=0..8 (3-29), sin f=9 a=0,1 (30,31)
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const float gv = __uint_as_float(r[i]);
@@ -544,14 +682,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_kernel(const __grid_consta
             }
           }
 #pragma unroll
-          for (int a = 0; a < 3; ++a) xyz_part[(hh * 128 + row) * 3 + a] = g[a];
+          for (int a = 0; a < 3; ++a) xyz_part[(e.hh * 128 + e.row) * 3 + a] = g[a];
           tc_fence_before();
           continue;
         }
-        if (st.epi == EPI_B_EV && st.n2_out && hh == 0) {
+        if (st.epi == EPI_B_EV && st.n2_out && e.hh == 0) {
           // group 2 accumulators (other TMEM half, columns 0..31) = d PE(viewdir): fold to d viewdir (deg 4: 27 columns)
           uint32_t r[32];
-          tmem_ld32(tmem_base + (half ^ 1u) * 256u + lane_field, r);
+          tmem_ld32(e.tmem_base + (half ^ 1u) * 256u + e.lane_field, r);
           const float d[3] = {__ldg(p.viewdir + 3 * crow), __ldg(p.viewdir + 3 * crow + 1), __ldg(p.viewdir + 3 * crow + 2)};
           float s[4][3], c[4][3];
           trig_ladder<4>(d, s, c);
@@ -563,58 +701,24 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_kernel(const __grid_consta
             else if (i < 15) { const int f = (i - 3) / 3, a = (i - 3) % 3; g[a] += gv * (float)(1 << f) * c[f][a]; }
             else { const int f = (i - 15) / 3, a = (i - 15) % 3; g[a] -= gv * (float)(1 << f) * s[f][a]; }
           }
-          if (valid && p.g_viewdir) { p.g_viewdir[3 * grow] = g[0]; p.g_viewdir[3 * grow + 1] = g[1]; p.g_viewdir[3 * grow + 2] = g[2]; }
+          if (e.valid && p.g_viewdir) { p.g_viewdir[3 * e.grow] = g[0]; p.g_viewdir[3 * e.grow + 1] = g[1]; p.g_viewdir[3 * e.grow + 2] = g[2]; }
         }
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + half * 256u + (uint32_t)c * 64u + hh * 32u + lane_field, r);
-          const int col0 = c * 64 + (int)hh * 32;
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          if (st.epi == EPI_B_EV) {   // + sigma-head gradient: d e += g_sigma_pre * w_sigma
-#pragma unroll
-            for (int i4 = 0; i4 < 8; ++i4) {
-              const float4 ws = __ldg(reinterpret_cast<const float4*>(p.wsig + col0) + i4);
-              v[4 * i4] += gsp * ws.x; v[4 * i4 + 1] += gsp * ws.y; v[4 * i4 + 2] += gsp * ws.z; v[4 * i4 + 3] += gsp * ws.w;
-            }
-          }
-          if (st.latent_slot >= 0) {  // latent gradient: per-object column sum of the UNMASKED input gradient
-            float t[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) t[i] = v[i];
-            const float cs = warp_colsum32(t, lane);
-            atomicAdd(colsum + st.latent_slot * 256 + col0 + lane, cs);
-          }
-          if (st.produce_a) {
-            uint32_t mw = 0xffffffffu;
-            if (st.mask_slot >= 0) mw = mask_word(mask_tile, st.mask_slot, c * 2 + hh, row);
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float a = ((mw >> (2 * i)) & 1u) ? v[2 * i] : 0.f;
-              const float b = ((mw >> (2 * i + 1)) & 1u) ? v[2 * i + 1] : 0.f;
-              pk[i] = pack_bf16(a, b);
-            }
-            store_row32(sm.chunk(c), row, hh, pk);
-            publish_chunk(sm, c, lane);
-          }
-        }
+        bwd_epilogue_dispatch(sm, st, half, e, mask_tile, gsp);
         tc_fence_before();
       }
       // ---- tile end: d xyz, and flush the latent column sums when the next tile belongs to another object
       const int64_t next = tile + gridDim.x;
       const bool flush = next >= n_tiles || (next * kTileM) / p.rows_per_obj != obj;
       epi_bar_sync();
-      if (p.g_xyz != nullptr && hh == 0 && valid) {
+      if (p.g_xyz != nullptr && e.hh == 0 && e.valid) {
 #pragma unroll
-        for (int a = 0; a < 3; ++a) p.g_xyz[3 * grow + a] = xyz_part[row * 3 + a] + xyz_part[(128 + row) * 3 + a];
+        for (int a = 0; a < 3; ++a) p.g_xyz[3 * e.grow + a] = xyz_part[e.row * 3 + a] + xyz_part[(128 + e.row) * 3 + a];
       }
       if (flush) {
-        for (int sl = 0; sl < n_lat; ++sl) {
-          const float v = colsum[sl * 256 + etid];
-          if (v != 0.f) atomicAdd(p.g_zlat + ((size_t)sl * p.B + obj) * 256 + etid, v);
-          colsum[sl * 256 + etid] = 0.f;
+        for (int sl = 0; sl < p.n_latent; ++sl) {
+          const float v = colsum[sl * 256 + tid];
+          if (v != 0.f) atomicAdd(p.g_zlat + ((size_t)sl * p.B + obj) * 256 + tid, v);
+          colsum[sl * 256 + tid] = 0.f;
         }
       }
       epi_bar_sync();
@@ -814,6 +918,8 @@ static void fill_common(Params& p, const snb_handle_s* h, const float* xyz, cons
   p.xyz = xyz; p.viewdir = viewdir; p.M = M; p.B = B; p.rows_per_obj = M / B;
   p.packed = (const uint8_t*)h->packed; p.zlat = zlat; p.masks = masks;
   p.wsig = h->layers[h->iSG].w; p.bsig = h->layers[h->iSG].b;
+  p.n_latent = h->arch.shape_blocks + h->arch.texture_blocks;
+  p.ev_step = h->arch.shape_blocks + 2;  // forward step index of encoding_viewdir
   p.w2 = h->layers[h->iR2].w; p.b2 = h->layers[h->iR2].b;
 }
 
@@ -861,7 +967,6 @@ int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, i
   fill_common(p, h, xyz, viewdir, M, B, zlat, masks);
   p.sigma_in = sigma; p.g_sigma = g_sigma; p.g_rgb = g_rgb; p.g_xyz = g_xyz; p.g_viewdir = g_viewdir; p.g_zlat = g_zlat;
   p.r0_mask_slot = pl.r0_slot;
-  p.n_latent = h->arch.shape_blocks + h->arch.texture_blocks;
   p.prog = g_xyz ? pl.bwd_full : pl.bwd_noxyz;
   SNB_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
   tc_bwd_kernel<<<tc_grid(M), kThreads, SM_ALLOC, st>>>(p);
