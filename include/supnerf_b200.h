@@ -130,6 +130,11 @@ size_t snb_packed_bytes(snb_handle h);
 /* Test hook: when non-NULL, the next bf16 forwards also dump every step's post-epilogue fp32 activations to
  * acts [n_steps][n_rows][256] (n_steps = shape_blocks + texture_blocks + 4).  Pass NULL to switch it off. */
 int snb_tc_set_debug(float* acts);
+/* Measurement hook (bench.py roofline): while enabled, every bf16 decoder call records a CUDA-event pair on its
+ * launch stream around the tcgen05 kernel alone.  snb_kernel_timing_read (after a synchronize) copies up to max_n
+ * durations in ms to HOST memory and returns how many; which = 0 forward, 1 backward.  Enabling clears old events. */
+int snb_kernel_timing_enable(int32_t on);
+int snb_kernel_timing_read(int32_t which, float* ms_host, int32_t max_n);
 int snb_pack_weights(snb_handle h, void* packed, void* stream);
 /* Scratch the forward needs (and the backward re-reads): activations in fp32 mode, ReLU masks +
  * per-sample sigma/rgb in bf16 mode.  n_rows = N*S samples. */

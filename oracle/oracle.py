@@ -246,8 +246,9 @@ def codenerf_decoder_bf16(sd: Dict[str, Tensor], xyz: Tensor, viewdir: Tensor, s
                           texture_latent: Tensor, num_xyz_freq: int = 10, num_dir_freq: int = 4):
     """Restatement of the SNB_PREC_BF16 mode's arithmetic (supnerf_b200/csrc/mlp_tc.cu), NOT of the reference: the
     same decoder as ``codenerf_decoder`` with every tensor-core operand rounded to bf16 where the kernel rounds it —
-    the weight matrices of the 63/256/283-input layers and rgb.0, the encodings, each layer's A operand (post-ReLU
-    activation plus the per-object latent vector) and, in the backward pass, each pre-activation gradient.  Biases,
+    the weight matrices of the 63/256/283-input layers and rgb.0, the encodings, each layer's A operand (the post-ReLU
+    activation; the per-object latent vector enters as an fp32 effective bias  z W^T + b) and, in the backward pass, each
+    pre-activation gradient.  Biases,
     latent layers, the sigma and rgb.2 heads and all accumulation stay fp32.  Used to separate "the kernel implements
     its stated rounding" (tight) from "bf16 rounding vs the fp32 reference" (the 2e-2 budget)."""
     rb = _RoundBF16.apply
@@ -262,16 +263,21 @@ def codenerf_decoder_bf16(sd: Dict[str, Tensor], xyz: Tensor, viewdir: Tensor, s
     ppi = int(xyz.shape[0] / B)
     sl = shape_latent.unsqueeze(1).repeat((1, ppi, 1)).reshape((ppi * B, 1, -1))
     tl = texture_latent.unsqueeze(1).repeat((1, ppi, 1)).reshape((ppi * B, 1, -1))
+    def mm_lat(name, y, z):
+        # (y + z) W^T + b  evaluated as  bf16(y) bf16(W)^T + (z W^T + b): the latent term is a per-object fp32 bias
+        w = sd[name + ".weight"]
+        return torch.nn.functional.linear(rb(y), w.bfloat16().to(y.dtype)) + torch.nn.functional.linear(z, w, sd[name + ".bias"])
+
     y = torch.relu(mm("encoding_xyz.0", x))
     for j in range(1, bs + 1):
         z = torch.relu(_lin(sd, f"shape_latent_layer_{j}.0", sl))
-        y = torch.relu(mm(f"shape_layer_{j}.0", rb(y + z)))
+        y = torch.relu(mm_lat(f"shape_layer_{j}.0", y, z))
     e = mm("encoding_shape", rb(y))
     sigmas = torch.nn.functional.softplus(_lin(sd, "sigma.0", e))
     y = torch.relu(mm("encoding_viewdir.0", torch.cat([rb(e), v], -1)))
     for j in range(1, bt + 1):
         z = torch.relu(_lin(sd, f"texture_latent_layer_{j}.0", tl))
-        y = torch.relu(mm(f"texture_layer_{j}.0", rb(y + z)))
+        y = torch.relu(mm_lat(f"texture_layer_{j}.0", y, z))
     h = torch.relu(mm("rgb.0", rb(y)))
     rgbs = _lin(sd, "rgb.2", h)
     return sigmas, rgbs

@@ -39,6 +39,14 @@ int f32_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, 
 // per-object latent layers, shared by both back ends.  zlat / dz: [(Bs+Bt)][B][W] (shape slots first).
 int latent_forward(const snb_handle_s* h, int64_t B, const float* shape_latent, const float* texture_latent, float* zlat,
                    cudaStream_t st);
+// ebias[slot][b][:] = bias + W z  of the layer that consumes latent slot `slot` (shape_layer_j / texture_layer_j): the
+// latent add folded through the layer, exact in fp32 (SURVEY 8(a')3).
+int latent_effective_bias(const snb_handle_s* h, int64_t B, const float* zlat, float* ebias, cudaStream_t st);
+// single-launch versions (latent.cu): forward of all slots (+ effective biases if ebias != NULL); backward to the latents only
+int latent_forward_fused(const snb_handle_s* h, int64_t B, const float* shape_latent, const float* texture_latent, float* zlat,
+                         float* ebias, cudaStream_t st);
+int latent_backward_fused(const snb_handle_s* h, int64_t B, const float* zlat, const float* dz, float* g_shape_latent,
+                          float* g_texture_latent, cudaStream_t st);
 // dz holds d loss / d zlat (post-ReLU outputs) and is overwritten by the pre-activation gradient.
 int latent_backward(const snb_handle_s* h, int64_t B, const float* shape_latent, const float* texture_latent,
                     const float* zlat, float* dz, float* g_shape_latent, float* g_texture_latent, float* const* g_weights,

@@ -238,10 +238,9 @@ int f32_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, i
   SNB_LAUNCH_CHECK();
   pe_fwd_kernel<<<ew_grid(M * 3), 256, 0, st>>>(viewdir, M, h->arch.num_dir_freq, L.V, L.ldv);
   SNB_LAUNCH_CHECK();
-  for (int j = 1; j <= L.Bs; ++j)  // shape_latent_layer_j once per object (model_codenerf.py:51)
-    TRY(fwd_linear(shape_latent, D, B, D, ly[h->iSL(j)].w, D, ly[h->iSL(j)].b, W, L.ZS[j], W, 1, 0, nullptr, 0, st));
-  for (int j = 1; j <= L.Bt; ++j)
-    TRY(fwd_linear(texture_latent, D, B, D, ly[h->iTL(j)].w, D, ly[h->iTL(j)].b, W, L.ZT[j], W, 1, 0, nullptr, 0, st));
+  // shape/texture_latent_layer_j once per object (model_codenerf.py:51,59): one launch; ZS[1..Bs], ZT[1..Bt] are contiguous
+  TRY(latent_forward_fused(h, B, shape_latent, texture_latent, L.ZS[1], nullptr, st));
+  (void)D;
   TRY(fwd_linear(L.X0, L.ldx, M, L.dx, ly[h->iX].w, L.dx, ly[h->iX].b, W, L.H[0], W, 1, 0, nullptr, 0, st));
   for (int j = 1; j <= L.Bs; ++j)
     TRY(fwd_linear(L.H[j - 1], W, M, W, ly[h->iS(j)].w, W, ly[h->iS(j)].b, W, L.H[j], W, 1, 0, L.ZS[j], rpo, st));
@@ -365,6 +364,17 @@ int latent_forward(const snb_handle_s* h, int64_t B, const float* shape_latent, 
   for (int j = 1; j <= Bt; ++j)
     TRY(fwd_linear(texture_latent, D, B, D, ly[h->iTL(j)].w, D, ly[h->iTL(j)].b, W, zlat + (int64_t)(Bs + j - 1) * B * W, W, 1,
                    0, nullptr, 0, st));
+  return 0;
+}
+
+int latent_effective_bias(const snb_handle_s* h, int64_t B, const float* zlat, float* ebias, cudaStream_t st) {
+  const int W = h->arch.W, Bs = h->arch.shape_blocks, Bt = h->arch.texture_blocks;
+  const auto& ly = h->layers;
+  for (int j = 1; j <= Bs + Bt; ++j) {
+    const int li = j <= Bs ? h->iS(j) : h->iT(j - Bs);
+    TRY(fwd_linear(zlat + (int64_t)(j - 1) * B * W, W, B, W, ly[li].w, W, ly[li].b, W, ebias + (int64_t)(j - 1) * B * W, W, 0, 0,
+                   nullptr, 0, st));
+  }
   return 0;
 }
 

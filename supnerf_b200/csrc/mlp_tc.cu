@@ -18,7 +18,9 @@
 #include <cuda_bf16.h>
 #include <math.h>
 #include <algorithm>
+#include <stdlib.h>
 #include <initializer_list>
+#include <utility>
 #include <vector>
 
 namespace snb {
@@ -67,7 +69,7 @@ struct Params {
   const float* xyz; const float* viewdir;
   int64_t M, rows_per_obj, B;
   const uint8_t* packed;
-  const float* zlat;            // [(Bs+Bt)][B][256]
+  const float* zlat;            // fwd: per-object effective biases b + W z, [(Bs+Bt)][B][256]; bwd: unused
   const float* wsig; const float* bsig; const float* w2; const float* b2;
   uint32_t* masks;              // [tile][slot][8 words][128 rows]
   // forward
@@ -76,6 +78,7 @@ struct Params {
   const float* sigma_in; const float* g_sigma; const float* g_rgb;
   float* g_xyz; float* g_viewdir; float* g_zlat;   // g_zlat [(Bs+Bt)][B][256], accumulated with atomics
   int r0_mask_slot, n_latent, ev_step;
+  int exp_flags;   // timing experiments only (env SNB_TC_EXP): 1 = producer skips the weight copies, 2 = epilogues skip their math
   Program prog;
 };
 
@@ -163,6 +166,16 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+
+// relu + round-to-nearest pack of two fp32 into one bf16x2 word (first argument -> low half = lower column)
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// ReLU mask words hold element i of a 32-column group at bit (31 - i): the forward builds them with one funnel shift per
+// element from the sign bit of the pre-activation (1 = active).
+__device__ __forceinline__ bool mask_bit(uint32_t mw, int i) { return (mw >> (31 - i)) & 1u; }
 
 // byte offset of 16-byte unit `unit` (0..7) of row `row` inside a 128B-swizzled [rows][64] bf16 chunk
 __device__ __forceinline__ uint32_t swz(uint32_t row, uint32_t unit) { return row * 128u + ((unit ^ (row & 7u)) << 4); }
@@ -262,8 +275,12 @@ __device__ __forceinline__ void producer_loop(const Params& p, const Smem& sm, i
           const uint32_t stage = it % kStages, ph = (it / kStages) & 1u;
           if (lane == 0) {
             mbar_wait(sm.bar(BAR_WEMPTY + stage), ph ^ 1u);
-            mbar_expect_tx(sm.bar(BAR_WFULL + stage), bytes);
-            bulk_g2s(sm.stage_u32(stage), p.packed + off0 + (size_t)kc * bytes, bytes, sm.bar(BAR_WFULL + stage));
+            if ((p.exp_flags & 1) && it >= (uint32_t)kStages) {
+              mbar_arrive(sm.bar(BAR_WFULL + stage));
+            } else {
+              mbar_expect_tx(sm.bar(BAR_WFULL + stage), bytes);
+              bulk_g2s(sm.stage_u32(stage), p.packed + off0 + (size_t)kc * bytes, bytes, sm.bar(BAR_WFULL + stage));
+            }
           }
           __syncwarp();
         }
@@ -349,8 +366,8 @@ template <int EPI, bool LAT, bool DBG>
 __device__ __forceinline__ void fwd_epilogue(const Params& p, const Smem& sm, const Step& st, int si, uint32_t half, const EpiCtx& e,
                                              uint32_t* mask_tile, float& sig_acc, float (&rgb_acc)[3]) {
   constexpr int NC = (EPI == EPI_RGB_HEAD) ? 2 : 4;
-  const float* bias_s = sm.tab(TAB_BIAS) + si * 256;
-  const float* z_s = sm.tab(TAB_Z) + (LAT ? st.latent_slot : 0) * 256;
+  // latent-conditioned layers read their per-object EFFECTIVE bias  b + W z_obj  (the latent add folded through the layer)
+  const float* bias_s = LAT ? sm.tab(TAB_Z) + st.latent_slot * 256 : sm.tab(TAB_BIAS) + si * 256;
   const float* wsig_s = sm.tab(TAB_WSIG);
   const float* w2_s = sm.tab(TAB_W2);
   const uint32_t t0 = e.tmem_base + half * 256u + e.hh * 32u + e.lane_field;
@@ -362,7 +379,7 @@ __device__ __forceinline__ void fwd_epilogue(const Params& p, const Smem& sm, co
     tmem_ld_wait();
     if (c + 1 < NC) tmem_ld32_issue(t0 + (uint32_t)(c + 1) * 64u, (c & 1) ? ra : rb);
     const int col0 = c * 64 + (int)e.hh * 32;
-    uint32_t pk[16], mask = 0;
+    uint32_t pk[16], nmask = 0;   // nmask collects SIGN bits (1 = negative pre-activation); stored inverted
 #pragma unroll
     for (int i4 = 0; i4 < 8; ++i4) {
       const float4 bb = *reinterpret_cast<const float4*>(bias_s + col0 + 4 * i4);
@@ -370,10 +387,7 @@ __device__ __forceinline__ void fwd_epilogue(const Params& p, const Smem& sm, co
                     __uint_as_float(r[4 * i4 + 2]) + bb.z, __uint_as_float(r[4 * i4 + 3]) + bb.w};
       if (EPI != EPI_LINEAR_SIGMA) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          v[u] = fmaxf(v[u], 0.f);
-          mask |= (v[u] > 0.f ? 1u : 0u) << (4 * i4 + u);
-        }
+        for (int u = 0; u < 4; ++u) nmask = __funnelshift_l(__float_as_uint(v[u]), nmask, 1);
       }
       if (EPI == EPI_LINEAR_SIGMA) {
         const float4 ws = *reinterpret_cast<const float4*>(wsig_s + col0 + 4 * i4);
@@ -383,22 +397,25 @@ __device__ __forceinline__ void fwd_epilogue(const Params& p, const Smem& sm, co
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           const float4 ww = *reinterpret_cast<const float4*>(w2_s + k * 128 + col0 + 4 * i4);
-          rgb_acc[k] += v[0] * ww.x + v[1] * ww.y + v[2] * ww.z + v[3] * ww.w;
+          rgb_acc[k] += fmaxf(v[0], 0.f) * ww.x + fmaxf(v[1], 0.f) * ww.y + fmaxf(v[2], 0.f) * ww.z + fmaxf(v[3], 0.f) * ww.w;
         }
       }
       if (DBG) {
         if (e.valid) {
           float* d = p.dbg + ((size_t)si * p.M + e.grow) * 256 + col0 + 4 * i4;
-          d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; d[3] = v[3];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) d[u] = (EPI == EPI_LINEAR_SIGMA) ? v[u] : fmaxf(v[u], 0.f);
         }
       }
-      if (LAT) {
-        const float4 zz = *reinterpret_cast<const float4*>(z_s + col0 + 4 * i4);
-        v[0] += zz.x; v[1] += zz.y; v[2] += zz.z; v[3] += zz.w;
+      if (EPI == EPI_LINEAR_SIGMA) {
+        pk[2 * i4] = pack_bf16(v[0], v[1]);
+        pk[2 * i4 + 1] = pack_bf16(v[2], v[3]);
+      } else if (EPI == EPI_RELU) {
+        pk[2 * i4] = pack_bf16_relu(v[0], v[1]);
+        pk[2 * i4 + 1] = pack_bf16_relu(v[2], v[3]);
       }
-      pk[2 * i4] = pack_bf16(v[0], v[1]);
-      pk[2 * i4 + 1] = pack_bf16(v[2], v[3]);
     }
+    const uint32_t mask = ~nmask;
     if (EPI != EPI_LINEAR_SIGMA) mask_tile[((size_t)st.mask_slot * 8 + c * 2 + e.hh) * 128 + e.row] = mask;
     if (EPI != EPI_RGB_HEAD) {
       store_row32(sm.chunk(c), e.row, e.hh, pk);
@@ -498,7 +515,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_fwd_kernel(const __grid_consta
           write_pe_row<10>(sm.chunk(4), e.row, e.hh, xn);
           publish_chunk(sm, 4, lane);
         }
-        if (p.dbg != nullptr) fwd_epilogue_dispatch<true>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc);
+        if (p.exp_flags & 2) {
+          if (st.produce_a) for (int c = 0; c < 4; ++c) publish_chunk(sm, c, lane);
+        } else if (p.dbg != nullptr) fwd_epilogue_dispatch<true>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc);
         else fwd_epilogue_dispatch<false>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc);
         tc_fence_before();
       }
@@ -560,8 +579,8 @@ __device__ __forceinline__ void bwd_epilogue(const Smem& sm, const Step& st, uin
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float a = (!MASK || ((mw >> (2 * i)) & 1u)) ? v[2 * i] : 0.f;
-        const float b = (!MASK || ((mw >> (2 * i + 1)) & 1u)) ? v[2 * i + 1] : 0.f;
+        const float a = (!MASK || mask_bit(mw, 2 * i)) ? v[2 * i] : 0.f;
+        const float b = (!MASK || mask_bit(mw, 2 * i + 1)) ? v[2 * i + 1] : 0.f;
         pk[i] = pack_bf16(a, b);
       }
       store_row32(sm.chunk(c), e.row, e.hh, pk);
@@ -643,7 +662,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_kernel(const __grid_consta
             float v[4] = {g3[0] * w0.x + g3[1] * w1.x + g3[2] * w2.x, g3[0] * w0.y + g3[1] * w1.y + g3[2] * w2.y,
                           g3[0] * w0.z + g3[1] * w1.z + g3[2] * w2.z, g3[0] * w0.w + g3[1] * w1.w + g3[2] * w2.w};
 #pragma unroll
-            for (int u = 0; u < 4; ++u) if (!((mw >> (4 * i4 + u)) & 1u)) v[u] = 0.f;
+            for (int u = 0; u < 4; ++u) if (!mask_bit(mw, 4 * i4 + u)) v[u] = 0.f;
             pk[2 * i4] = pack_bf16(v[0], v[1]);
             pk[2 * i4 + 1] = pack_bf16(v[2], v[3]);
           }
@@ -805,18 +824,18 @@ static TcPlan build_plan(const snb_handle_s* h) {
   f.n_steps = 0; f.n_mask_slots = Bs + Bt + 3;
   auto push = [](Program& pr, const Step& s) { pr.s[pr.n_steps++] = s; };
   {  // ---------------- forward
-    Step s = make_step(EPI_RELU, 256, 1, {4}, 0, 0, 1, ly[h->iX].b);
+    Step s = make_step(EPI_RELU, 256, 1, {4}, 0, -1, 1, ly[h->iX].b);
     add_chunks(pl, ly[h->iX].w, dx, false, 256, 256, dx, 1, &s.w_off);
     push(f, s);
     for (int j = 1; j <= Bs; ++j) {
-      s = make_step(EPI_RELU, 256, 4, {0, 1, 2, 3}, j, j < Bs ? j : -1, 1, ly[h->iS(j)].b);
+      s = make_step(EPI_RELU, 256, 4, {0, 1, 2, 3}, j, j - 1, 1, ly[h->iS(j)].b);   // effective bias slot j-1 = b + W zs_j
       add_chunks(pl, ly[h->iS(j)].w, W, false, 256, 256, W, 4, &s.w_off);
       push(f, s);
     }
     s = make_step(EPI_LINEAR_SIGMA, 256, 4, {0, 1, 2, 3}, -1, -1, 1, ly[h->iES].b);
     add_chunks(pl, ly[h->iES].w, W, false, 256, 256, W, 4, &s.w_off);
     push(f, s);
-    s = make_step(EPI_RELU, 256, 5, {4, 0, 1, 2, 3}, slot_vv, Bs, 1, ly[h->iEV].b);
+    s = make_step(EPI_RELU, 256, 5, {4, 0, 1, 2, 3}, slot_vv, -1, 1, ly[h->iEV].b);
     {  // chunk 0 = the PE(viewdir) columns [W, W+dv) of encoding_viewdir, chunks 1..4 = its first W columns
       add_chunks(pl, ly[h->iEV].w + W, W + dv, false, 256, 256, dv, 1, &s.w_off);
       uint32_t dummy;
@@ -824,7 +843,7 @@ static TcPlan build_plan(const snb_handle_s* h) {
     }
     push(f, s);
     for (int j = 1; j <= Bt; ++j) {
-      s = make_step(EPI_RELU, 256, 4, {0, 1, 2, 3}, slot_vv + j, j < Bt ? Bs + j : -1, 1, ly[h->iT(j)].b);
+      s = make_step(EPI_RELU, 256, 4, {0, 1, 2, 3}, slot_vv + j, Bs + j - 1, 1, ly[h->iT(j)].b);
       add_chunks(pl, ly[h->iT(j)].w, W, false, 256, 256, W, 4, &s.w_off);
       push(f, s);
     }
@@ -897,9 +916,11 @@ static inline int64_t tiles_of(int64_t M) { return (M + kTileM - 1) / kTileM; }
 static size_t ws_zlat_bytes(const snb_handle_s* h, int64_t B) {
   return (size_t)(h->arch.shape_blocks + h->arch.texture_blocks) * B * 256 * sizeof(float);
 }
+// workspace: [zlat][effective biases][masks]
+static size_t ws_masks_off(const snb_handle_s* h, int64_t B) { return (2 * ws_zlat_bytes(h, B) + 255) & ~size_t(255); }
 size_t tc_workspace_bytes(const snb_handle_s* h, int64_t M, int64_t B) {
   const int slots = h->arch.shape_blocks + h->arch.texture_blocks + 3;
-  return ws_zlat_bytes(h, B) + (size_t)tiles_of(M) * slots * 8 * 128 * 4 + 256;
+  return ws_masks_off(h, B) + (size_t)tiles_of(M) * slots * 8 * 128 * 4 + 256;
 }
 size_t tc_bwd_scratch_bytes(const snb_handle_s* h, int64_t, int64_t B) { return ws_zlat_bytes(h, B) + 256; }
 
@@ -920,6 +941,7 @@ static void fill_common(Params& p, const snb_handle_s* h, const float* xyz, cons
   p.wsig = h->layers[h->iSG].w; p.bsig = h->layers[h->iSG].b;
   p.n_latent = h->arch.shape_blocks + h->arch.texture_blocks;
   p.ev_step = h->arch.shape_blocks + 2;  // forward step index of encoding_viewdir
+  { const char* ev = getenv("SNB_TC_EXP"); p.exp_flags = ev ? atoi(ev) : 0; }
   p.w2 = h->layers[h->iR2].w; p.b2 = h->layers[h->iR2].b;
 }
 
@@ -929,6 +951,27 @@ static int tc_grid(int64_t M) {
   return (int)(t < sms ? t : sms);
 }
 
+// optional kernel-only timing (bench.py roofline): CUDA events recorded on the launch stream around the tcgen05 kernels
+static bool g_timing_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_ev_fwd, g_ev_bwd;
+void tc_timing_enable(int on) {
+  g_timing_on = on != 0;
+  for (auto* v : {&g_ev_fwd, &g_ev_bwd}) { for (auto& e : *v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } v->clear(); }
+}
+int tc_timing_read(int which, float* ms, int max_n) {   // call after a stream/device synchronize
+  auto& v = which == 0 ? g_ev_fwd : g_ev_bwd;
+  int n = 0;
+  for (auto& e : v) { if (n >= max_n) break; float t = 0.f; if (cudaEventElapsedTime(&t, e.first, e.second) == cudaSuccess) ms[n++] = t; }
+  return n;
+}
+struct ScopedKernelTimer {
+  cudaStream_t st; std::pair<cudaEvent_t, cudaEvent_t> ev; bool on;
+  ScopedKernelTimer(cudaStream_t s, bool enable) : st(s), on(enable) {
+    if (on) { cudaEventCreate(&ev.first); cudaEventCreate(&ev.second); cudaEventRecord(ev.first, st); }
+  }
+  void stop(std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& into) { if (on) { cudaEventRecord(ev.second, st); into.push_back(ev); } }
+};
+
 static float* g_tc_debug_acts = nullptr;  // test hook (snb_tc_set_debug): per-step post-epilogue fp32 activations
 void tc_set_debug(float* acts) { g_tc_debug_acts = acts; }
 
@@ -936,15 +979,18 @@ int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, in
                const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, void* ws, cudaStream_t st) {
   if (tc_common_checks(h, M, B, "mlp_fwd(bf16)")) return 2;
   float* zlat = (float*)ws;
-  uint32_t* masks = (uint32_t*)((uint8_t*)ws + ((ws_zlat_bytes(h, B) + 255) & ~size_t(255)));
-  if (latent_forward(h, B, shape_latent, texture_latent, zlat, st)) return 1;
+  float* ebias = (float*)((uint8_t*)ws + ws_zlat_bytes(h, B));
+  uint32_t* masks = (uint32_t*)((uint8_t*)ws + ws_masks_off(h, B));
+  if (latent_forward_fused(h, B, shape_latent, texture_latent, zlat, ebias, st)) return 1;
   TcPlan pl = build_plan(h);
   Params p;
-  fill_common(p, h, xyz, viewdir, M, B, zlat, masks);
+  fill_common(p, h, xyz, viewdir, M, B, ebias, masks);
   p.sigma = sigma; p.rgb = rgb; p.dbg = g_tc_debug_acts;
   p.prog = pl.fwd;
   SNB_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
+  ScopedKernelTimer tm(st, g_timing_on);
   tc_fwd_kernel<<<tc_grid(M), kThreads, SM_ALLOC, st>>>(p);
+  tm.stop(g_ev_fwd);
   SNB_LAUNCH_CHECK();
   return 0;
 }
@@ -959,7 +1005,7 @@ int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, i
               "(requires_grad_(False)) or use precision='fp32'");
   SNB_REQUIRE((g_xyz == nullptr) == (g_viewdir == nullptr), "mlp_bwd(bf16): request both g_xyz and g_viewdir or neither");
   const float* zlat = (const float*)ws;
-  uint32_t* masks = (uint32_t*)((uint8_t*)ws + ((ws_zlat_bytes(h, B) + 255) & ~size_t(255)));
+  uint32_t* masks = (uint32_t*)((uint8_t*)ws + ws_masks_off(h, B));
   float* g_zlat = (float*)scratch;
   SNB_CHECK_CUDA(cudaMemsetAsync(g_zlat, 0, ws_zlat_bytes(h, B), st));
   TcPlan pl = build_plan(h);
@@ -969,9 +1015,11 @@ int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, i
   p.r0_mask_slot = pl.r0_slot;
   p.prog = g_xyz ? pl.bwd_full : pl.bwd_noxyz;
   SNB_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
+  ScopedKernelTimer tm(st, g_timing_on);
   tc_bwd_kernel<<<tc_grid(M), kThreads, SM_ALLOC, st>>>(p);
+  tm.stop(g_ev_bwd);
   SNB_LAUNCH_CHECK();
-  return latent_backward(h, B, shape_latent, texture_latent, zlat, g_zlat, g_shape_latent, g_texture_latent, nullptr, st);
+  return latent_backward_fused(h, B, zlat, g_zlat, g_shape_latent, g_texture_latent, st);
 }
 
 }  // namespace snb
