@@ -130,6 +130,10 @@ size_t snb_packed_bytes(snb_handle h);
 /* Test hook: when non-NULL, the next bf16 forwards also dump every step's post-epilogue fp32 activations to
  * acts [n_steps][n_rows][256] (n_steps = shape_blocks + texture_blocks + 4).  Pass NULL to switch it off. */
 int snb_tc_set_debug(float* acts);
+/* Tuning hook: when non-NULL (device memory, >= 8 B x 4 x 2 x steps x tile pairs of CTA 0), CTA 0 of the next bf16 decoder
+ * kernels writes clock64 stamps [pair][step][slot][4] = {operand-ready seen by the MMA warp, MMAs issued, accumulator-ready
+ * seen by the epilogue, epilogue published}.  tools/trace_pipeline.py prints the timeline.  Pass NULL to switch it off. */
+int snb_tc_set_trace(long long* stamps);
 /* Measurement hook (bench.py roofline): while enabled, every bf16 decoder call records a CUDA-event pair on its
  * launch stream around the tcgen05 kernel alone.  snb_kernel_timing_read (after a synchronize) copies up to max_n
  * durations in ms to HOST memory and returns how many; which = 0 forward, 1 backward.  Enabling clears old events. */

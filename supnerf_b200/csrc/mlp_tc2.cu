@@ -1,0 +1,811 @@
+// K2 / K2b, SNB_PREC_BF16 back end, second generation: TWO 128-sample tiles in flight per CTA.
+//
+// Measured on B200 (profiles/r1_ubench_mma_latency.txt): a tcgen05.mma batch costs ~450-600 cycles of issue -> commit ->
+// mbarrier -> waiting-warp latency on top of its 128 cycles per M128xN256xK16 instruction, and the first-generation kernel
+// (mlp_tc.cu, one tile per CTA) serialises that latency AND most of each layer's epilogue behind the layer's MMAs
+// (ncu: tensor pipe 39 % active, epilogue warps 37 % of their time waiting for the accumulator).  Here every CTA owns
+// two tile slots with their own shared-memory A operand (4 x 16 KB chunks), their own 256-column TMEM accumulator and
+// their own group of 8 epilogue warps; the single MMA-issuer warp alternates  slot 0 layer l, slot 1 layer l, slot 0
+// layer l+1, ...  so the tensor pipe always has the other slot's layer to run while one slot is in its epilogue.
+//
+// Warp roles (576 threads): warps 0-7 epilogue group of slot 0, warps 8-15 of slot 1 (warp w owns TMEM lanes
+// 32*(w%4).. and the column half (w/4)%2 of every 64-column chunk), warp 16 weight producer (+ TMEM alloc), warp 17
+// MMA issuer.  Weights: pre-tiled bf16 images, [N rows][32 k] per stage (64-byte swizzle, K-major), streamed L2 ->
+// smem by cp.async.bulk through a 5-stage mbarrier ring.  No AUX operand buffer: PE(xyz) is written into the slot's
+// chunk 0, and encoding_viewdir runs as two accumulating steps (y part, then PE(viewdir) written into chunk 0).
+#include "common.cuh"
+#include "handle.h"
+#include "tc_ptx.cuh"
+#include <algorithm>
+#include <stdlib.h>
+#include <utility>
+#include <vector>
+
+namespace snb {
+namespace tc2 {
+using namespace tc;
+
+constexpr int kThreads = 576;
+constexpr int kRing = 5;
+constexpr uint32_t kStageBytes = 16384;   // [256 n][32 k] bf16
+constexpr int kMaxSteps = 12;
+constexpr int kMaxLat = 4;                // shape_blocks + texture_blocks <= 4 (every shipped config: 3 + 1)
+
+constexpr uint32_t SM_RING = 8 * kChunkBytes;                    // A chunks [slot][4]
+constexpr uint32_t SM_TAB = SM_RING + kRing * kStageBytes;
+constexpr uint32_t TAB_BIAS = 0;                                 // fwd: [4][256] biases of encoding_xyz, encoding_shape, encoding_viewdir, rgb.0
+constexpr uint32_t TAB_LAT = TAB_BIAS + 4 * 1024;                // fwd: [slot][kMaxLat][256] effective biases; bwd: latent column sums
+constexpr uint32_t TAB_WSIG = TAB_LAT + 2 * kMaxLat * 1024;      // [256]
+constexpr uint32_t TAB_W2 = TAB_WSIG + 1024;                     // [3][128]
+constexpr uint32_t TAB_BYTES = TAB_W2 + 1536;
+constexpr uint32_t SM_BARS = SM_TAB + TAB_BYTES;
+constexpr uint32_t SM_TOTAL = SM_BARS + 256;
+constexpr uint32_t SM_ALLOC = SM_TOTAL + 1024;                   // + alignment slack
+static_assert(SM_ALLOC <= 232448, "shared memory budget");
+
+enum Epi : int { F_RELU = 0, F_SIGMA = 1, F_PEV = 2, F_RGB = 3, B_MASK = 4, B_VD = 5, B_EV = 6, B_XYZ = 7 };
+constexpr int BAR_WFULL = 0, BAR_WEMPTY = kRing, BAR_READY = 2 * kRing, BAR_ACC = 2 * kRing + 2;
+
+struct Step {
+  uint32_t w_off;            // byte offset of the step's first weight stage in the packed buffer
+  uint16_t n_stages, n_out;  // K / 32, N
+  int8_t epi, mask_slot, latent_slot, bias_row, dbg_idx, accumulate, produce_a, colsum;
+};
+
+struct Program {
+  int n_steps, n_mask_slots;
+  Step s[kMaxSteps];
+};
+
+struct Params {
+  const float* xyz; const float* viewdir;
+  int64_t M, rows_per_obj, B;
+  const uint8_t* packed;
+  const float* zlat;            // fwd: per-object effective biases [(Bs+Bt)][B][256]
+  const float* bias4[4];        // fwd: static biases (X, ES, EV, R0)
+  const float* wsig; const float* bsig; const float* w2; const float* b2;
+  uint32_t* masks;              // [tile][slot][8 words][128 rows]
+  float* sigma; float* rgb; float* dbg;
+  const float* sigma_in; const float* g_sigma; const float* g_rgb;
+  float* g_xyz; float* g_viewdir; float* g_zlat;   // g_zlat [(Bs+Bt)][B][256], accumulated with atomics
+  int r0_mask_slot, n_latent;
+  long long* trace;   // timing experiments only: CTA 0 writes clock64 stamps [pair][step][slot][4] = READY seen, MMAs issued, ACC seen, published
+  int exp_flags;   // timing experiments only (env SNB_TC_EXP): 1 = producer skips the weight copies, 4 = every stage copies the same image
+  Program prog;
+};
+
+// K-major, 64-byte-swizzled operand tile: rows 64 B apart, 8-row atoms 512 B apart (SBO), descriptor version 1.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+
+struct Smem {
+  uint8_t* base;
+  uint32_t base_u32;
+  __device__ uint8_t* chunk(uint32_t slot, int c) const { return base + (slot * 4u + (uint32_t)c) * kChunkBytes; }
+  __device__ uint32_t chunk_u32(uint32_t slot, int c) const { return base_u32 + (slot * 4u + (uint32_t)c) * kChunkBytes; }
+  __device__ uint32_t stage_u32(uint32_t s) const { return base_u32 + SM_RING + s * kStageBytes; }
+  __device__ float* tab(uint32_t off) const { return reinterpret_cast<float*>(base + SM_TAB + off); }
+  __device__ uint32_t bar(int i) const { return base_u32 + SM_BARS + 8u * i; }
+};
+
+struct EpiCtx {
+  uint32_t lane, hh, row, lane_field, tmem, slot;
+  int64_t grow;
+  bool valid;
+};
+
+__device__ __forceinline__ uint32_t mask_word(const uint32_t* mask_tile, int slot, int word, uint32_t row) {
+  return __ldg(mask_tile + ((size_t)slot * 8 + word) * 128 + row);
+}
+
+__device__ __forceinline__ void store_row32(uint8_t* chunk, uint32_t row, uint32_t hh, const uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    uint4 q = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+    *reinterpret_cast<uint4*>(chunk + swz(row, hh * 4 + u)) = q;
+  }
+}
+
+__device__ __forceinline__ void group_bar(uint32_t slot) { asm volatile("bar.sync %0, 256;" ::"r"(slot + 1) : "memory"); }
+
+// this thread's smem writes (generic proxy) and TMEM reads are done: make them visible to the tensor core and tell the MMA warp
+__device__ __forceinline__ void publish(const Smem& sm, uint32_t slot, uint32_t lane) {
+  tc_fence_before();
+  fence_async_smem();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(sm.bar(BAR_READY + slot));
+}
+
+// ------------------------------------------------------------------------------------------ producer / MMA roles
+// Both roles run WARP-UNIFORMLY (all 32 lanes execute the loops; one elected lane issues the async instruction inside the
+// asm block).  With the instructions inside an `if (lane == 0)` region nvcc keeps descriptors in vector registers and wraps
+// every UTCHMMA / UBLKCP in an ELECT + 7 x R2UR + BRA.U.ANY waterfall: ~65 dependent instructions per two MMAs, which made
+// the MMA issuer itself the bottleneck (580 cycles per 256-cycle stage, profiles/r1_trace_v2_first.txt).
+__device__ __forceinline__ void bulk_g2s_elect(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n"
+      "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+      "}" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_elect(uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+      "}" ::"r"(bar) : "memory");
+}
+// two K=16 MMAs of one 32-k weight stage (A and B advance by 32 bytes = 2 descriptor units), then release the stage
+__device__ __forceinline__ void umma_stage_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate,
+                                                 uint32_t empty_bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e, p, t;\n"
+      ".reg .b64 a1, b1;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.eq.b32 t, 0, 0;\n"
+      "add.s64 a1, %1, 2;\n"
+      "add.s64 b1, %2, 2;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(empty_bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void producer_loop(const Params& p, const Smem& sm, int64_t n_pairs) {
+  uint32_t stage = 0, ph = 0, it = 0;
+  for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    for (int si = 0; si < p.prog.n_steps; ++si) {
+      const Step& st = p.prog.s[si];
+      const uint32_t bytes = (uint32_t)st.n_out * 64u;
+      for (int slot = 0; slot < 2; ++slot) {
+        const uint8_t* src = p.packed + ((p.exp_flags & 4) ? 0 : st.w_off);
+        for (int j = 0; j < st.n_stages; ++j, ++it) {
+          mbar_wait(sm.bar(BAR_WEMPTY + stage), ph ^ 1u);
+          if ((p.exp_flags & 1) && it >= (uint32_t)kRing) mbar_arrive_elect(sm.bar(BAR_WFULL + stage));
+          else bulk_g2s_elect(sm.stage_u32(stage), src, bytes, sm.bar(BAR_WFULL + stage));
+          if (!(p.exp_flags & 4)) src += bytes;
+          if (++stage == (uint32_t)kRing) { stage = 0; ph ^= 1u; }
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void mma_loop(const Params& p, const Smem& sm, int64_t n_pairs, uint32_t tmem_base) {
+  uint32_t stage = 0, ph = 0, ready_ph = 0;
+  const bool trace = p.trace != nullptr && blockIdx.x == 0;
+  int64_t tr = 0;
+  for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    for (int si = 0; si < p.prog.n_steps; ++si) {
+      const Step& st = p.prog.s[si];
+      const uint32_t idesc = umma_idesc(128, st.n_out);
+      const int n_stages = st.n_stages;
+#pragma unroll
+      for (uint32_t slot = 0; slot < 2; ++slot, tr += 4) {
+        mbar_wait(sm.bar(BAR_READY + slot), (ready_ph >> slot) & 1u);   // A operand written, accumulator drained
+        ready_ph ^= 1u << slot;
+        tc_fence_after();
+        if (trace) p.trace[tr] = clock64();
+        const uint32_t d_tmem = tmem_base + slot * 256u;
+        uint64_t a_desc = umma_desc(sm.chunk_u32(slot, 0));
+        uint32_t acc = (uint32_t)st.accumulate;
+        for (int j = 0; j < n_stages; ++j) {
+          mbar_wait(sm.bar(BAR_WFULL + stage), ph);
+          tc_fence_after();
+          umma_stage_elect(d_tmem, a_desc, umma_desc_sw64(sm.stage_u32(stage)), idesc, acc, sm.bar(BAR_WEMPTY + stage));
+          acc = 1u;
+          a_desc += (j & 1) ? (uint64_t)((kChunkBytes - 64u) >> 4) : (uint64_t)(64u >> 4);   // next 32-k half of the chunk / next chunk
+          if (++stage == (uint32_t)kRing) { stage = 0; ph ^= 1u; }
+        }
+        umma_commit_elect(sm.bar(BAR_ACC + slot));
+        if (trace) p.trace[tr + 1] = clock64();
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void kernel_prologue(Smem& sm, uint32_t tid, uint32_t warp, uint32_t& tmem_base) {
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.base + SM_BARS + 128);
+  if (tid == 0) {
+    for (int i = 0; i < kRing; ++i) { mbar_init(sm.bar(BAR_WFULL + i), 1); mbar_init(sm.bar(BAR_WEMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(sm.bar(BAR_READY + i), 8); mbar_init(sm.bar(BAR_ACC + i), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 16) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  tmem_base = *tmem_slot;
+}
+
+__device__ __forceinline__ void smem_base(Smem& sm, uint8_t* smem_raw) {
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
+  sm.base = smem_raw + pad;
+  sm.base_u32 = raw + pad;
+}
+
+// ------------------------------------------------------------------------------------------ forward epilogue
+// One layer's epilogue for this thread's row: TMEM -> (+bias, ReLU, mask bits) -> bf16 -> the slot's A chunks.
+template <int EPI, bool DBG>
+__device__ __forceinline__ void fwd_epilogue(const Params& p, const Smem& sm, const Step& st, const EpiCtx& e, const float* bias_s,
+                                             uint32_t* mask_tile, bool tile_ok, float& sig_acc, float (&rgb_acc)[3]) {
+  constexpr int NC = (EPI == F_RGB) ? 2 : 4;
+  const float* wsig_s = sm.tab(TAB_WSIG);
+  const float* w2_s = sm.tab(TAB_W2);
+  const uint32_t t0 = e.tmem + e.hh * 32u + e.lane_field;
+  uint32_t r[32];
+  tmem_ld32_issue(t0, r);
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    tmem_ld_wait();
+    const int col0 = c * 64 + (int)e.hh * 32;
+    uint32_t pk[16], mm[4] = {0u, 0u, 0u, 0u};   // mm: SIGN bits (1 = negative pre-activation), four independent 8-element chains
+#pragma unroll
+    for (int i4 = 0; i4 < 8; ++i4) {
+      const float4 bb = *reinterpret_cast<const float4*>(bias_s + col0 + 4 * i4);
+      float v[4] = {__uint_as_float(r[4 * i4]) + bb.x, __uint_as_float(r[4 * i4 + 1]) + bb.y,
+                    __uint_as_float(r[4 * i4 + 2]) + bb.z, __uint_as_float(r[4 * i4 + 3]) + bb.w};
+      if (EPI != F_SIGMA) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mm[i4 >> 1] = __funnelshift_l(__float_as_uint(v[u]), mm[i4 >> 1], 1);
+      }
+      if (EPI == F_SIGMA) {
+        const float4 ws = *reinterpret_cast<const float4*>(wsig_s + col0 + 4 * i4);
+        sig_acc += v[0] * ws.x + v[1] * ws.y + v[2] * ws.z + v[3] * ws.w;
+      }
+      if (EPI == F_RGB) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float4 ww = *reinterpret_cast<const float4*>(w2_s + k * 128 + col0 + 4 * i4);
+          rgb_acc[k] += fmaxf(v[0], 0.f) * ww.x + fmaxf(v[1], 0.f) * ww.y + fmaxf(v[2], 0.f) * ww.z + fmaxf(v[3], 0.f) * ww.w;
+        }
+      }
+      if (DBG) {
+        if (e.valid && st.dbg_idx >= 0) {
+          float* d = p.dbg + ((size_t)st.dbg_idx * p.M + e.grow) * 256 + col0 + 4 * i4;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) d[u] = (EPI == F_SIGMA) ? v[u] : fmaxf(v[u], 0.f);
+        }
+      }
+      if (EPI == F_SIGMA) {
+        pk[2 * i4] = pack_bf16(v[0], v[1]);
+        pk[2 * i4 + 1] = pack_bf16(v[2], v[3]);
+      } else if (EPI == F_RELU) {
+        pk[2 * i4] = pack_bf16_relu(v[0], v[1]);
+        pk[2 * i4 + 1] = pack_bf16_relu(v[2], v[3]);
+      }
+    }
+    if (c + 1 < NC) tmem_ld32_issue(t0 + (uint32_t)(c + 1) * 64u, r);   // r is dead: the next chunk loads while this one is stored
+    if (EPI != F_SIGMA) {
+      const uint32_t nmask = (mm[0] << 24) | (mm[1] << 16) | (mm[2] << 8) | mm[3];
+      if (tile_ok) mask_tile[((size_t)st.mask_slot * 8 + c * 2 + e.hh) * 128 + e.row] = ~nmask;
+    }
+    if (EPI != F_RGB) store_row32(sm.chunk(e.slot, c), e.row, e.hh, pk);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ forward kernel
+template <bool DBG>
+__global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem sm;
+  smem_base(sm, smem_raw);
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  {  // static tables
+    float* bias_s = sm.tab(TAB_BIAS);
+    for (int i = tid; i < 4 * 256; i += kThreads) {
+      const int r = i >> 8, c = i & 255;
+      bias_s[i] = (r < 3 || c < 128) ? __ldg(p.bias4[r] + c) : 0.f;
+    }
+    float* wsig_s = sm.tab(TAB_WSIG);
+    for (int i = tid; i < 256; i += kThreads) wsig_s[i] = __ldg(p.wsig + i);
+    float* w2_s = sm.tab(TAB_W2);
+    for (int i = tid; i < 384; i += kThreads) w2_s[i] = __ldg(p.w2 + i);
+  }
+  uint32_t tmem_base;
+  kernel_prologue(sm, tid, warp, tmem_base);
+  const int64_t n_tiles = (p.M + kTileM - 1) / kTileM;
+  const int64_t n_pairs = (n_tiles + 1) / 2;
+
+  if (warp == 16) {
+    producer_loop(p, sm, n_pairs);
+  } else if (warp == 17) {
+    mma_loop(p, sm, n_pairs, tmem_base);
+  } else {
+    const uint32_t slot = warp >> 3, gw = warp & 7u, gtid = tid & 255u;
+    EpiCtx e;
+    e.lane = lane; e.hh = gw >> 2; e.row = (gw & 3u) * 32u + lane; e.lane_field = ((gw & 3u) * 32u) << 16;
+    e.tmem = tmem_base + slot * 256u; e.slot = slot;
+    float* lat_s = sm.tab(TAB_LAT) + slot * kMaxLat * 256;
+    float* sig_part = reinterpret_cast<float*>(sm.chunk(slot, 3));   // tile-end scratch: [2][128] + [2][128][3]
+    float* rgb_part = sig_part + 256;
+    const int nslots = p.prog.n_mask_slots;
+    uint32_t acc_cnt = 0;
+    int64_t cur_obj = -1;
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int64_t tile = 2 * pair + slot;
+      const bool tile_ok = tile < n_tiles;
+      e.grow = tile * kTileM + e.row;
+      e.valid = tile_ok && e.grow < p.M;
+      const int64_t crow = e.valid ? e.grow : p.M - 1;
+      const float x[3] = {__ldg(p.xyz + 3 * crow), __ldg(p.xyz + 3 * crow + 1), __ldg(p.xyz + 3 * crow + 2)};
+      const float dir[3] = {__ldg(p.viewdir + 3 * crow), __ldg(p.viewdir + 3 * crow + 1), __ldg(p.viewdir + 3 * crow + 2)};
+      const int64_t obj = tile_ok ? (tile * kTileM) / p.rows_per_obj : (cur_obj < 0 ? 0 : cur_obj);   // tiles never straddle objects
+      if (obj != cur_obj) {   // (re)load this slot's per-object effective biases; the group is between tiles here
+        cur_obj = obj;
+        for (int i = gtid; i < p.n_latent * 256; i += 256)
+          lat_s[i] = __ldg(p.zlat + ((size_t)(i >> 8) * p.B + obj) * 256 + (i & 255));
+        group_bar(slot);
+      }
+      write_pe_row<10>(sm.chunk(slot, 0), e.row, e.hh, x);
+      publish(sm, slot, lane);
+      uint32_t* mask_tile = p.masks + (size_t)(tile_ok ? tile : 0) * nslots * 8 * 128;
+      float sig_acc = 0.f, rgb_acc[3] = {0.f, 0.f, 0.f};
+      for (int si = 0; si < p.prog.n_steps; ++si) {
+        const Step& st = p.prog.s[si];
+        mbar_wait(sm.bar(BAR_ACC + slot), acc_cnt & 1u);
+        acc_cnt++;
+        tc_fence_after();
+        if (p.trace && blockIdx.x == 0 && gtid == 0) p.trace[(((pair / gridDim.x) * p.prog.n_steps + si) * 2 + slot) * 4 + 2] = clock64();
+        const float* bias_s = st.latent_slot >= 0 ? lat_s + st.latent_slot * 256 : sm.tab(TAB_BIAS) + st.bias_row * 256;
+        if (st.epi == F_RELU) fwd_epilogue<F_RELU, DBG>(p, sm, st, e, bias_s, mask_tile, tile_ok, sig_acc, rgb_acc);
+        else if (st.epi == F_SIGMA) fwd_epilogue<F_SIGMA, DBG>(p, sm, st, e, bias_s, mask_tile, tile_ok, sig_acc, rgb_acc);
+        else if (st.epi == F_PEV) write_pe_row<4>(sm.chunk(slot, 0), e.row, e.hh, dir);   // accumulator untouched: the next step adds to it
+        else fwd_epilogue<F_RGB, DBG>(p, sm, st, e, bias_s, mask_tile, tile_ok, sig_acc, rgb_acc);
+        if (si + 1 < p.prog.n_steps) publish(sm, slot, lane);
+        else tc_fence_before();
+        if (p.trace && blockIdx.x == 0 && gtid == 0) p.trace[(((pair / gridDim.x) * p.prog.n_steps + si) * 2 + slot) * 4 + 3] = clock64();
+      }
+      // tile end: combine the two column halves of the sigma / rgb heads (the A chunks are free: rgb.0's MMAs are complete)
+      sig_part[e.hh * 128 + e.row] = sig_acc;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) rgb_part[(e.hh * 128 + e.row) * 3 + k] = rgb_acc[k];
+      group_bar(slot);
+      if (e.hh == 0 && e.valid) {
+        const float sp = sig_part[e.row] + sig_part[128 + e.row] + __ldg(p.bsig);
+        p.sigma[e.grow] = sp > 20.f ? sp : log1pf(expf(sp));   // nn.Softplus(): beta 1, threshold 20
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          p.rgb[3 * e.grow + k] = rgb_part[e.row * 3 + k] + rgb_part[(128 + e.row) * 3 + k] + __ldg(p.b2 + k);
+      }
+      // no second barrier: chunk 3 is next written by encoding_xyz's epilogue, which needs every warp's READY arrive first
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------ backward epilogue
+// acc = gradient w.r.t. the layer's input.  Optional: per-object column sums of it (latent gradient); then mask by the
+// producing layer's ReLU bits and hand on as the next A operand.  EV: add the sigma-head gradient first, no mask.
+template <bool EV, bool COLSUM, bool MASK, bool PRODUCE>
+__device__ __forceinline__ void bwd_epilogue(const Smem& sm, const Step& st, const EpiCtx& e, const uint32_t (&mw)[4], float gsp,
+                                             float* colsum) {
+  const float* wsig_s = sm.tab(TAB_WSIG);
+  const uint32_t t0 = e.tmem + e.hh * 32u + e.lane_field;
+  uint32_t r[32];
+  tmem_ld32_issue(t0, r);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    tmem_ld_wait();
+    const int col0 = c * 64 + (int)e.hh * 32;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    if (c + 1 < 4) tmem_ld32_issue(t0 + (uint32_t)(c + 1) * 64u, r);
+    if (EV) {
+#pragma unroll
+      for (int i4 = 0; i4 < 8; ++i4) {
+        const float4 ws = *reinterpret_cast<const float4*>(wsig_s + col0 + 4 * i4);
+        v[4 * i4] += gsp * ws.x; v[4 * i4 + 1] += gsp * ws.y; v[4 * i4 + 2] += gsp * ws.z; v[4 * i4 + 3] += gsp * ws.w;
+      }
+    }
+    if (PRODUCE) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float a = (!MASK || mask_bit(mw[c], 2 * i)) ? v[2 * i] : 0.f;
+        const float b = (!MASK || mask_bit(mw[c], 2 * i + 1)) ? v[2 * i + 1] : 0.f;
+        pk[i] = pack_bf16(a, b);
+      }
+      store_row32(sm.chunk(e.slot, c), e.row, e.hh, pk);
+    }
+    if (COLSUM) {
+      const float cs = warp_colsum32(v, e.lane);
+      atomicAdd(colsum + st.latent_slot * 256 + col0 + e.lane, cs);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ backward kernel
+__global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem sm;
+  smem_base(sm, smem_raw);
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  {
+    float* colsum0 = sm.tab(TAB_LAT);
+    for (uint32_t i = tid; i < 2 * kMaxLat * 256; i += kThreads) colsum0[i] = 0.f;
+    float* wsig_s = sm.tab(TAB_WSIG);
+    for (int i = tid; i < 256; i += kThreads) wsig_s[i] = __ldg(p.wsig + i);
+    float* w2_s = sm.tab(TAB_W2);
+    for (int i = tid; i < 384; i += kThreads) w2_s[i] = __ldg(p.w2 + i);
+  }
+  uint32_t tmem_base;
+  kernel_prologue(sm, tid, warp, tmem_base);
+  const int64_t n_tiles = (p.M + kTileM - 1) / kTileM;
+  const int64_t n_pairs = (n_tiles + 1) / 2;
+
+  if (warp == 16) {
+    producer_loop(p, sm, n_pairs);
+  } else if (warp == 17) {
+    mma_loop(p, sm, n_pairs, tmem_base);
+  } else {
+    const uint32_t slot = warp >> 3, gw = warp & 7u, gtid = tid & 255u;
+    EpiCtx e;
+    e.lane = lane; e.hh = gw >> 2; e.row = (gw & 3u) * 32u + lane; e.lane_field = ((gw & 3u) * 32u) << 16;
+    e.tmem = tmem_base + slot * 256u; e.slot = slot;
+    float* colsum = sm.tab(TAB_LAT) + slot * kMaxLat * 256;
+    float* xyz_part = reinterpret_cast<float*>(sm.chunk(slot, 3));   // tile-end scratch [2][128][3]; chunk 3 is next written by a step epilogue
+    const float* w2_s = sm.tab(TAB_W2);
+    const int nslots = p.prog.n_mask_slots;
+    uint32_t acc_cnt = 0;
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int64_t tile = 2 * pair + slot;
+      const bool tile_ok = tile < n_tiles;
+      e.grow = tile * kTileM + e.row;
+      e.valid = tile_ok && e.grow < p.M;
+      const int64_t crow = e.valid ? e.grow : p.M - 1;
+      const int64_t obj = tile_ok ? (tile * kTileM) / p.rows_per_obj : 0;
+      const uint32_t* mask_tile = p.masks + (size_t)(tile_ok ? tile : 0) * nslots * 8 * 128;
+      const float gsg = e.valid ? __ldg(p.g_sigma + e.grow) : 0.f;
+      const float gsp = gsg * (-expm1f(-__ldg(p.sigma_in + crow)));   // d softplus = 1 - exp(-softplus)
+      // ---- prologue: d pre-activation of rgb.0 = (g_rgb W2) * mask -> A chunks 0,1 (128 columns)
+      {
+        float g3[3] = {0.f, 0.f, 0.f};
+        if (e.valid) { g3[0] = __ldg(p.g_rgb + 3 * e.grow); g3[1] = __ldg(p.g_rgb + 3 * e.grow + 1); g3[2] = __ldg(p.g_rgb + 3 * e.grow + 2); }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col0 = c * 64 + (int)e.hh * 32;
+          const uint32_t mw = mask_word(mask_tile, p.r0_mask_slot, c * 2 + e.hh, e.row);
+          uint32_t pk[16];
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 w0 = *reinterpret_cast<const float4*>(w2_s + col0 + 4 * i4);
+            const float4 w1 = *reinterpret_cast<const float4*>(w2_s + 128 + col0 + 4 * i4);
+            const float4 w2 = *reinterpret_cast<const float4*>(w2_s + 256 + col0 + 4 * i4);
+            float v[4] = {g3[0] * w0.x + g3[1] * w1.x + g3[2] * w2.x, g3[0] * w0.y + g3[1] * w1.y + g3[2] * w2.y,
+                          g3[0] * w0.z + g3[1] * w1.z + g3[2] * w2.z, g3[0] * w0.w + g3[1] * w1.w + g3[2] * w2.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (!mask_bit(mw, 4 * i4 + u)) v[u] = 0.f;
+            pk[2 * i4] = pack_bf16(v[0], v[1]);
+            pk[2 * i4 + 1] = pack_bf16(v[2], v[3]);
+          }
+          store_row32(sm.chunk(slot, c), e.row, e.hh, pk);
+        }
+      }
+      publish(sm, slot, lane);
+      for (int si = 0; si < p.prog.n_steps; ++si) {
+        const Step& st = p.prog.s[si];
+        uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        if (st.epi == B_MASK && st.mask_slot >= 0) {   // fetched before the wait: the L2 latency hides behind the layer's MMAs
+#pragma unroll
+          for (int c = 0; c < 4; ++c) mw[c] = mask_word(mask_tile, st.mask_slot, c * 2 + (int)e.hh, e.row);
+        }
+        mbar_wait(sm.bar(BAR_ACC + slot), acc_cnt & 1u);
+        acc_cnt++;
+        tc_fence_after();
+        if (p.trace && blockIdx.x == 0 && gtid == 0) p.trace[(((pair / gridDim.x) * p.prog.n_steps + si) * 2 + slot) * 4 + 2] = clock64();
+        if (st.epi == B_XYZ) {
+          // acc = d PE(xyz) (64 columns): fold to d xyz.  g_x = g_0 + sum_f 2^f (g_sin,f cos_f - g_cos,f sin_f)
+          uint32_t r[32];
+          tmem_ld32(e.tmem + e.hh * 32u + e.lane_field, r);
+          const float x[3] = {__ldg(p.xyz + 3 * crow), __ldg(p.xyz + 3 * crow + 1), __ldg(p.xyz + 3 * crow + 2)};
+          float s[10][3], c[10][3];
+          trig_ladder<10>(x, s, c);
+          float g[3] = {0.f, 0.f, 0.f};
+          if (e.hh == 0) {  // columns 0..31: x (0-2), sin f=0..8 (3-29), sin f=9 a=0,1 (30,31)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float gv = __uint_as_float(r[i]);
+              if (i < 3) g[i] += gv;
+              else { const int f = (i - 3) / 3, a = (i - 3) % 3; g[a] += gv * (float)(1 << f) * c[f][a]; }
+            }
+          } else {        // columns 32..63: sin f=9 a=2 (32), cos f=0..9 (33-62), pad (63)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float gv = __uint_as_float(r[i]);
+              const int col = 32 + i;
+              if (col == 32) g[2] += gv * 512.f * c[9][2];
+              else if (col < 63) { const int f = (col - 33) / 3, a = (col - 33) % 3; g[a] -= gv * (float)(1 << f) * s[f][a]; }
+            }
+          }
+#pragma unroll
+          for (int a = 0; a < 3; ++a) xyz_part[(e.hh * 128 + e.row) * 3 + a] = g[a];
+        } else if (st.epi == B_VD) {
+          // acc columns 0..26 = d PE(viewdir): fold to d viewdir (deg 4)
+          if (e.hh == 0) {
+            uint32_t r[32];
+            tmem_ld32(e.tmem + e.lane_field, r);
+            const float d[3] = {__ldg(p.viewdir + 3 * crow), __ldg(p.viewdir + 3 * crow + 1), __ldg(p.viewdir + 3 * crow + 2)};
+            float s[4][3], c[4][3];
+            trig_ladder<4>(d, s, c);
+            float g[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 27; ++i) {
+              const float gv = __uint_as_float(r[i]);
+              if (i < 3) g[i] += gv;
+              else if (i < 15) { const int f = (i - 3) / 3, a = (i - 3) % 3; g[a] += gv * (float)(1 << f) * c[f][a]; }
+              else { const int f = (i - 15) / 3, a = (i - 15) % 3; g[a] -= gv * (float)(1 << f) * s[f][a]; }
+            }
+            if (e.valid && p.g_viewdir) { p.g_viewdir[3 * e.grow] = g[0]; p.g_viewdir[3 * e.grow + 1] = g[1]; p.g_viewdir[3 * e.grow + 2] = g[2]; }
+          }
+        } else if (st.epi == B_EV) {
+          bwd_epilogue<true, false, false, true>(sm, st, e, mw, gsp, colsum);
+        } else if (st.colsum) {
+          if (st.produce_a) bwd_epilogue<false, true, true, true>(sm, st, e, mw, gsp, colsum);
+          else bwd_epilogue<false, true, false, false>(sm, st, e, mw, gsp, colsum);
+        } else {
+          bwd_epilogue<false, false, true, true>(sm, st, e, mw, gsp, colsum);
+        }
+        if (si + 1 < p.prog.n_steps) publish(sm, slot, lane);
+        else tc_fence_before();
+        if (p.trace && blockIdx.x == 0 && gtid == 0) p.trace[(((pair / gridDim.x) * p.prog.n_steps + si) * 2 + slot) * 4 + 3] = clock64();
+      }
+      // ---- tile end: d xyz, and flush the latent column sums when this slot's next tile belongs to another object
+      const int64_t next = tile + 2 * (int64_t)gridDim.x;
+      const bool flush = tile_ok && (next >= n_tiles || (next * kTileM) / p.rows_per_obj != obj);
+      group_bar(slot);
+      if (p.g_xyz != nullptr && e.hh == 0 && e.valid) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) p.g_xyz[3 * e.grow + a] = xyz_part[e.row * 3 + a] + xyz_part[(128 + e.row) * 3 + a];
+      }
+      if (flush) {
+        for (int sl = 0; sl < p.n_latent; ++sl) {
+          const float v = colsum[sl * 256 + gtid];
+          if (v != 0.f) atomicAdd(p.g_zlat + ((size_t)sl * p.B + obj) * 256 + gtid, v);
+          colsum[sl * 256 + gtid] = 0.f;
+        }
+        group_bar(slot);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------ weight packing
+struct PackJob {
+  const float* src; int ld; int transposed; int n_valid; int n_pad; int k0; int k_limit; uint32_t dst_off;
+};
+constexpr int kJobsPerLaunch = 64;
+struct PackJobs { int n; PackJob j[kJobsPerLaunch]; };
+
+// one block per stage image: dst[n][k] (64B-swizzled rows of 32 bf16) = src'(n, k0 + k), zero outside the valid range
+__global__ void __launch_bounds__(256) pack2_kernel(const __grid_constant__ PackJobs jobs, uint8_t* __restrict__ packed) {
+  const PackJob& jb = jobs.j[blockIdx.x];
+  for (int e = threadIdx.x; e < jb.n_pad * 32; e += blockDim.x) {
+    int n, k;
+    if (jb.transposed) { k = e / jb.n_pad; n = e % jb.n_pad; }  // consecutive threads walk the contiguous source dimension
+    else { n = e / 32; k = e % 32; }
+    const int kg = jb.k0 + k;
+    float v = 0.f;
+    if (n < jb.n_valid && kg < jb.k_limit) v = jb.transposed ? jb.src[(size_t)kg * jb.ld + n] : jb.src[(size_t)n * jb.ld + kg];
+    const uint32_t off = jb.dst_off + (uint32_t)n * 64u + ((((uint32_t)k >> 3) ^ (((uint32_t)n >> 1) & 3u)) << 4) + ((uint32_t)k & 7u) * 2u;
+    *reinterpret_cast<__nv_bfloat16*>(packed + off) = __float2bfloat16_rn(v);
+  }
+}
+
+}  // namespace tc2
+
+// ------------------------------------------------------------------------------------------ host side
+using namespace tc2;
+
+bool tc2_supported(const snb_handle_s* h) {
+  const snb_arch& a = h->arch;
+  return a.arch == SNB_ARCH_CODENERF && a.W == 256 && a.num_xyz_freq == 10 && a.num_dir_freq == 4 &&
+         a.shape_blocks + a.texture_blocks <= kMaxLat;
+}
+
+struct Tc2Plan {
+  tc2::Program fwd, bwd_full, bwd_noxyz;
+  std::vector<tc2::PackJob> jobs;
+  uint32_t total_bytes = 0;
+  int r0_slot = 0;
+};
+
+// src'(n, k): n < n_valid rows, k < k_limit columns of the (possibly transposed) fp32 matrix; n_stages stages of 32 k
+static void add_stages(Tc2Plan& pl, const float* src, int ld, bool transposed, int n_valid, int n_pad, int k_limit, int n_stages,
+                       uint32_t* first_off) {
+  *first_off = pl.total_bytes;
+  for (int c = 0; c < n_stages; ++c) {
+    tc2::PackJob j;
+    j.src = src; j.ld = ld; j.transposed = transposed ? 1 : 0; j.n_valid = n_valid; j.n_pad = n_pad; j.k0 = c * 32;
+    j.k_limit = k_limit; j.dst_off = pl.total_bytes;
+    pl.jobs.push_back(j);
+    pl.total_bytes += (uint32_t)n_pad * 64u;
+  }
+}
+
+static tc2::Step mk(int epi, int n_out, int n_stages, int mask_slot, int latent_slot, int bias_row, int dbg_idx) {
+  tc2::Step s{};
+  s.epi = (int8_t)epi; s.n_out = (uint16_t)n_out; s.n_stages = (uint16_t)n_stages; s.mask_slot = (int8_t)mask_slot;
+  s.latent_slot = (int8_t)latent_slot; s.bias_row = (int8_t)bias_row; s.dbg_idx = (int8_t)dbg_idx;
+  s.accumulate = 0; s.produce_a = 1; s.colsum = 0;
+  return s;
+}
+
+static Tc2Plan build_plan2(const snb_handle_s* h) {
+  Tc2Plan pl;
+  const int Bs = h->arch.shape_blocks, Bt = h->arch.texture_blocks, W = 256, dv = h->d_dir(), dx = h->d_xyz();
+  const auto& ly = h->layers;
+  const int slot_vv = Bs + 1, slot_r = Bs + Bt + 2;
+  pl.r0_slot = slot_r;
+  auto push = [](tc2::Program& pr, const tc2::Step& s) { pr.s[pr.n_steps++] = s; };
+  {  // ---------------- forward
+    tc2::Program& f = pl.fwd;
+    f.n_steps = 0; f.n_mask_slots = Bs + Bt + 3;
+    tc2::Step s = mk(F_RELU, 256, 2, 0, -1, 0, 0);                                         // encoding_xyz: K = 64 (63 valid)
+    add_stages(pl, ly[h->iX].w, dx, false, 256, 256, dx, 2, &s.w_off);
+    push(f, s);
+    for (int j = 1; j <= Bs; ++j) {
+      s = mk(F_RELU, 256, 8, j, j - 1, -1, j);                                             // shape_layer_j, effective bias slot j-1
+      add_stages(pl, ly[h->iS(j)].w, W, false, 256, 256, W, 8, &s.w_off);
+      push(f, s);
+    }
+    s = mk(F_SIGMA, 256, 8, -1, -1, 1, Bs + 1);                                            // encoding_shape (+ sigma head)
+    add_stages(pl, ly[h->iES].w, W, false, 256, 256, W, 8, &s.w_off);
+    push(f, s);
+    s = mk(F_PEV, 256, 8, -1, -1, -1, -1);                                                 // encoding_viewdir, y columns
+    add_stages(pl, ly[h->iEV].w, W + dv, false, 256, 256, W, 8, &s.w_off);
+    push(f, s);
+    s = mk(F_RELU, 256, 2, slot_vv, -1, 2, Bs + 2);                                        // + PE(viewdir) columns [W, W+dv)
+    s.accumulate = 1;
+    add_stages(pl, ly[h->iEV].w + W, W + dv, false, 256, 256, dv, 2, &s.w_off);
+    push(f, s);
+    for (int j = 1; j <= Bt; ++j) {
+      s = mk(F_RELU, 256, 8, slot_vv + j, Bs + j - 1, -1, Bs + 2 + j);
+      add_stages(pl, ly[h->iT(j)].w, W, false, 256, 256, W, 8, &s.w_off);
+      push(f, s);
+    }
+    s = mk(F_RGB, 128, 8, slot_r, -1, 3, Bs + Bt + 3);                                     // rgb.0 (+ rgb.2 head)
+    s.produce_a = 0;
+    add_stages(pl, ly[h->iR0].w, W, false, 128, 128, W, 8, &s.w_off);
+    push(f, s);
+  }
+  {  // ---------------- backward (B operand = W^T: n = input unit, k = output unit)
+    for (int full = 0; full < 2; ++full) {
+      tc2::Program& b = full ? pl.bwd_full : pl.bwd_noxyz;
+      b.n_steps = 0; b.n_mask_slots = Bs + Bt + 3;
+      tc2::Step s = mk(B_MASK, 256, 4, slot_vv + Bt, -1, -1, -1);                          // through rgb.0 -> d T_Bt, mask of T_Bt
+      add_stages(pl, ly[h->iR0].w, W, true, 256, 256, 128, 4, &s.w_off);
+      push(b, s);
+      for (int j = Bt; j >= 1; --j) {                                                      // through texture_layer_j
+        s = mk(B_MASK, 256, 8, slot_vv + j - 1, Bs + j - 1, -1, -1);
+        s.colsum = 1;
+        add_stages(pl, ly[h->iT(j)].w, W, true, 256, 256, W, 8, &s.w_off);
+        push(b, s);
+      }
+      if (full) {                                                                          // d PE(viewdir) = g_ev W_dir
+        s = mk(B_VD, 64, 8, -1, -1, -1, -1);
+        s.produce_a = 0;
+        add_stages(pl, ly[h->iEV].w + W, W + dv, true, dv, 64, W, 8, &s.w_off);
+        push(b, s);
+      }
+      s = mk(B_EV, 256, 8, -1, -1, -1, -1);                                                // through encoding_viewdir (y columns)
+      add_stages(pl, ly[h->iEV].w, W + dv, true, 256, 256, W, 8, &s.w_off);
+      push(b, s);
+      s = mk(B_MASK, 256, 8, Bs, -1, -1, -1);                                              // through encoding_shape, mask of H_Bs
+      add_stages(pl, ly[h->iES].w, W, true, 256, 256, W, 8, &s.w_off);
+      push(b, s);
+      for (int j = Bs; j >= 1; --j) {                                                      // through shape_layer_j
+        s = mk(B_MASK, 256, 8, j - 1, j - 1, -1, -1);
+        s.colsum = 1;
+        if (!full && j == 1) s.produce_a = 0;                                              // feeds nobody without pose gradients
+        add_stages(pl, ly[h->iS(j)].w, W, true, 256, 256, W, 8, &s.w_off);
+        push(b, s);
+      }
+      if (full) {
+        s = mk(B_XYZ, 64, 8, -1, -1, -1, -1);                                              // through encoding_xyz -> d PE(xyz)
+        s.produce_a = 0;
+        add_stages(pl, ly[h->iX].w, dx, true, dx, 64, W, 8, &s.w_off);
+        push(b, s);
+      }
+    }
+  }
+  return pl;
+}
+
+size_t tc2_packed_bytes(const snb_handle_s* h) {
+  if (!tc2_supported(h)) return 0;
+  return build_plan2(h).total_bytes + 1024;
+}
+
+int tc2_pack_weights(const snb_handle_s* h, void* packed, cudaStream_t st) {
+  Tc2Plan pl = build_plan2(h);
+  for (size_t i = 0; i < pl.jobs.size(); i += kJobsPerLaunch) {
+    tc2::PackJobs jb;
+    jb.n = (int)std::min<size_t>(kJobsPerLaunch, pl.jobs.size() - i);
+    for (int k = 0; k < jb.n; ++k) jb.j[k] = pl.jobs[i + k];
+    pack2_kernel<<<jb.n, 256, 0, st>>>(jb, (uint8_t*)packed);
+    SNB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+static long long* g_trace = nullptr;   // test / tuning hook (snb_tc_set_trace)
+void tc2_set_trace(long long* buf) { g_trace = buf; }
+
+static void fill_common2(tc2::Params& p, const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M,
+                         int64_t B, const float* zlat, uint32_t* masks) {
+  p = tc2::Params{};
+  p.xyz = xyz; p.viewdir = viewdir; p.M = M; p.B = B; p.rows_per_obj = M / B;
+  p.packed = (const uint8_t*)packed2; p.zlat = zlat; p.masks = masks;
+  p.bias4[0] = h->layers[h->iX].b; p.bias4[1] = h->layers[h->iES].b; p.bias4[2] = h->layers[h->iEV].b; p.bias4[3] = h->layers[h->iR0].b;
+  p.wsig = h->layers[h->iSG].w; p.bsig = h->layers[h->iSG].b;
+  p.w2 = h->layers[h->iR2].w; p.b2 = h->layers[h->iR2].b;
+  p.n_latent = h->arch.shape_blocks + h->arch.texture_blocks;
+  { const char* ev = getenv("SNB_TC_EXP"); p.exp_flags = ev ? atoi(ev) : 0; }
+  p.trace = g_trace;
+}
+
+static int tc2_grid(int64_t M) {
+  const int sms = sm_count();
+  const int64_t pairs = ((M + kTileM - 1) / kTileM + 1) / 2;
+  return (int)(pairs < sms ? pairs : sms);
+}
+
+int tc2_launch_fwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
+                   const float* ebias, uint32_t* masks, float* sigma, float* rgb, float* dbg, cudaStream_t st) {
+  Tc2Plan pl = build_plan2(h);
+  tc2::Params p;
+  fill_common2(p, h, packed2, xyz, viewdir, M, B, ebias, masks);
+  p.sigma = sigma; p.rgb = rgb; p.dbg = dbg;
+  p.prog = pl.fwd;
+  if (dbg) {
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
+    tc2_fwd_kernel<true><<<tc2_grid(M), tc2::kThreads, SM_ALLOC, st>>>(p);
+  } else {
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
+    tc2_fwd_kernel<false><<<tc2_grid(M), tc2::kThreads, SM_ALLOC, st>>>(p);
+  }
+  return 0;
+}
+
+int tc2_launch_bwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
+                   const uint32_t* masks, const float* sigma, const float* g_sigma, const float* g_rgb, float* g_xyz,
+                   float* g_viewdir, float* g_zlat, cudaStream_t st) {
+  Tc2Plan pl = build_plan2(h);
+  tc2::Params p;
+  fill_common2(p, h, packed2, xyz, viewdir, M, B, nullptr, const_cast<uint32_t*>(masks));
+  p.sigma_in = sigma; p.g_sigma = g_sigma; p.g_rgb = g_rgb; p.g_xyz = g_xyz; p.g_viewdir = g_viewdir; p.g_zlat = g_zlat;
+  p.r0_mask_slot = pl.r0_slot;
+  p.prog = g_xyz ? pl.bwd_full : pl.bwd_noxyz;
+  SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
+  tc2_bwd_kernel<<<tc2_grid(M), tc2::kThreads, SM_ALLOC, st>>>(p);
+  return 0;
+}
+
+}  // namespace snb

@@ -13,6 +13,7 @@ tot = {r: 0 for r in reasons}
 total = 0
 for k, r in enumerate(rows[2:]):
     if len(r) < len(hdr): continue
+    if not (r[iSamp] or '0').isdigit(): continue
     s = int(r[iSamp] or 0)
     total += s
     for q in reasons: tot[q] += int(r[ridx[q]] or 0)
