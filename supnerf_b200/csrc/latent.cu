@@ -15,74 +15,73 @@ struct LatentLayers {
   const float* wc[kMaxSlots]; const float* bc[kMaxSlots];   // consuming layers (W, W), (W)
 };
 
-// grid (slots, B), 256 threads.  zlat / ebias: [slot][b][W].
+// One warp per output unit, 8 outputs per 256-thread block: grid (slots, B, W/8) so even one object fills the machine
+// (the single-block-per-slot version took ~250 us per launch: 20 % of a refine step, profiles/r1_launches_v5.md).
+// PHASE 0: zlat[slot][b][o] = ReLU(W_lat[o,:] . latent[b,:] + b_lat[o]).
+// PHASE 1: ebias[slot][b][o] = W_layer[o,:] . zlat[slot][b][:] + b_layer[o].
+template <int PHASE>
 __global__ void __launch_bounds__(256) latent_fwd_kernel(const __grid_constant__ LatentLayers L, int64_t B,
                                                         const float* __restrict__ shape_latent,
                                                         const float* __restrict__ texture_latent,
                                                         float* __restrict__ zlat, float* __restrict__ ebias) {
-  extern __shared__ float sh[];   // [D] latent, [W] z
-  float* lat = sh;
-  float* z = sh + L.D;
   const int slot = blockIdx.x;
   const int64_t b = blockIdx.y;
-  const float* src = (slot < L.n_shape ? shape_latent : texture_latent) + b * L.D;
-  for (int i = threadIdx.x; i < L.D; i += blockDim.x) lat[i] = src[i];
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int o = warp; o < L.W; o += nw) {
-    const float* w = L.wl[slot] + (size_t)o * L.D;
-    float acc = 0.f;
-    for (int k = lane; k < L.D; k += 32) acc = fmaf(__ldg(w + k), lat[k], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      const float v = fmaxf(acc + __ldg(L.bl[slot] + o), 0.f);
-      z[o] = v;
-      zlat[((size_t)slot * B + b) * L.W + o] = v;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int o = blockIdx.z * 8 + warp;
+  if (o >= L.W) return;
+  const int K = PHASE == 0 ? L.D : L.W;
+  const float* x = PHASE == 0 ? (slot < L.n_shape ? shape_latent : texture_latent) + b * L.D
+                              : zlat + ((size_t)slot * B + b) * L.W;
+  const float* w = (PHASE == 0 ? L.wl[slot] : L.wc[slot]) + (size_t)o * K;
+  float acc = 0.f;
+  if ((((uintptr_t)w | (uintptr_t)x) & 15) == 0) {
+    for (int k = lane * 4; k < K; k += 128) {   // K is a multiple of 4 (checked on the host)
+      const float4 a = __ldg(reinterpret_cast<const float4*>(w + k));
+      const float4 v = *reinterpret_cast<const float4*>(x + k);
+      acc = fmaf(a.x, v.x, acc); acc = fmaf(a.y, v.y, acc); acc = fmaf(a.z, v.z, acc); acc = fmaf(a.w, v.w, acc);
     }
+  } else {   // caller handed an unaligned view
+    for (int k = lane; k < K; k += 32) acc = fmaf(__ldg(w + k), x[k], acc);
   }
-  if (ebias == nullptr) return;
-  __syncthreads();
-  for (int o = warp; o < L.W; o += nw) {
-    const float* w = L.wc[slot] + (size_t)o * L.W;
-    float acc = 0.f;
-    for (int k = lane; k < L.W; k += 32) acc = fmaf(__ldg(w + k), z[k], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) ebias[((size_t)slot * B + b) * L.W + o] = acc + __ldg(L.bc[slot] + o);
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    if (PHASE == 0) zlat[((size_t)slot * B + b) * L.W + o] = fmaxf(acc + __ldg(L.bl[slot] + o), 0.f);
+    else ebias[((size_t)slot * B + b) * L.W + o] = acc + __ldg(L.bc[slot] + o);
   }
 }
 
-// grid (2, B): type 0 = shape slots, 1 = texture slots.  dz [slot][b][W] = d loss / d z (post-ReLU).
+// grid (2, B, D/32): type 0 = shape slots, 1 = texture slots; the block owns 32 latent units, its 8 warps split the W
+// hidden units of every slot, partial sums meet in shared memory.  dz [slot][b][W] = d loss / d z (post-ReLU).
 __global__ void __launch_bounds__(256) latent_bwd_kernel(const __grid_constant__ LatentLayers L, int64_t B,
                                                         const float* __restrict__ zlat, const float* __restrict__ dz,
                                                         float* __restrict__ g_shape, float* __restrict__ g_texture) {
-  extern __shared__ float sh[];   // [W] masked gradient of the current slot
+  __shared__ float part[8][32];
   const int type = blockIdx.x;
   const int64_t b = blockIdx.y;
   float* out = type == 0 ? g_shape : g_texture;
   if (out == nullptr) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = blockIdx.z * 32 + lane;
   const int s0 = type == 0 ? 0 : L.n_shape, s1 = type == 0 ? L.n_shape : L.n_total;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};   // thread t owns latent units t, t+256, ... (D <= 1024)
-  for (int slot = s0; slot < s1; ++slot) {
-    __syncthreads();
-    for (int o = threadIdx.x; o < L.W; o += blockDim.x) {
-      const size_t i = ((size_t)slot * B + b) * L.W + o;
-      sh[o] = zlat[i] > 0.f ? dz[i] : 0.f;
-    }
-    __syncthreads();
-    for (int o = 0; o < L.W; ++o) {
-      const float g = sh[o];
-      const float* w = L.wl[slot] + (size_t)o * L.D;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int k = threadIdx.x + u * 256;
-        if (k < L.D) acc[u] = fmaf(g, __ldg(w + k), acc[u]);
+  float acc = 0.f;
+  if (k < L.D) {
+    for (int slot = s0; slot < s1; ++slot) {
+      const float* z = zlat + ((size_t)slot * B + b) * L.W;
+      const float* g = dz + ((size_t)slot * B + b) * L.W;
+      const float* w = L.wl[slot] + k;
+      for (int o = warp; o < L.W; o += 8) {
+        const float gm = z[o] > 0.f ? g[o] : 0.f;
+        acc = fmaf(gm, __ldg(w + (size_t)o * L.D), acc);
       }
     }
   }
+  part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && k < L.D) {
+    float v = 0.f;
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int k = threadIdx.x + u * 256;
-    if (k < L.D) out[b * L.D + k] = acc[u];
+    for (int i = 0; i < 8; ++i) v += part[i][lane];
+    out[b * L.D + k] = v;
   }
 }
 
@@ -104,9 +103,14 @@ int latent_forward_fused(const snb_handle_s* h, int64_t B, const float* shape_la
                          float* zlat, float* ebias, cudaStream_t st) {
   LatentLayers L;
   if (fill_layers(h, L)) return 2;
-  dim3 grid(L.n_total, (unsigned)B);
-  latent_fwd_kernel<<<grid, 256, (L.D + L.W) * sizeof(float), st>>>(L, B, shape_latent, texture_latent, zlat, ebias);
+  SNB_REQUIRE(L.D % 4 == 0 && L.W % 4 == 0, "latent layers: latent_dim and W must be multiples of 4");
+  dim3 grid(L.n_total, (unsigned)B, (unsigned)((L.W + 7) / 8));
+  latent_fwd_kernel<0><<<grid, 256, 0, st>>>(L, B, shape_latent, texture_latent, zlat, ebias);
   SNB_LAUNCH_CHECK();
+  if (ebias != nullptr) {
+    latent_fwd_kernel<1><<<grid, 256, 0, st>>>(L, B, shape_latent, texture_latent, zlat, ebias);
+    SNB_LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -114,8 +118,8 @@ int latent_backward_fused(const snb_handle_s* h, int64_t B, const float* zlat, c
                           float* g_texture_latent, cudaStream_t st) {
   LatentLayers L;
   if (fill_layers(h, L)) return 2;
-  dim3 grid(2, (unsigned)B);
-  latent_bwd_kernel<<<grid, 256, L.W * sizeof(float), st>>>(L, B, zlat, dz, g_shape_latent, g_texture_latent);
+  dim3 grid(2, (unsigned)B, (unsigned)((L.D + 31) / 32));
+  latent_bwd_kernel<<<grid, 256, 0, st>>>(L, B, zlat, dz, g_shape_latent, g_texture_latent);
   SNB_LAUNCH_CHECK();
   return 0;
 }

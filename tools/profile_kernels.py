@@ -78,6 +78,6 @@ best = [1e9, 1e9]
 for _ in range(5):
     f, b = composite_pass()
     best = [min(best[0], f), min(best[1], b)]
-bf, bb = n * (20 * S + 20), n * (40 * S + 20 + 20 * S)
+bf, bb = n * (20 * S + 20), n * (40 * S + 20)   # fwd reads 20S writes 20; bwd re-reads 20S + 20, writes 20S
 print(f"composite rays={n} S={S}: fwd {best[0]:.3f} ms ({bf / best[0] / 1e6:.0f} GB/s)  bwd {best[1]:.3f} ms ({bb / best[1] / 1e6:.0f} GB/s)  "
       f"fwd+bwd {(bf + bb) / (best[0] + best[1]) / 1e6:.0f} GB/s  [python autograd call; kernel + output allocation]")
