@@ -44,23 +44,53 @@ def peaks():
 
 
 class ClockSampler:
-    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock + throttle reasons sampled DURING the timed region (NVML, 20 ms period; nvidia-smi fallback)."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.index, self.sm, self.mx, self.reasons, self.n = index, [], None, set(), 0
+        self.stop = threading.Event()
         self.t = threading.Thread(target=self.run, daemon=True)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def sample(self):
+        if self.nvml is not None:
+            self.sm.append(float(self.nvml.nvmlDeviceGetClockInfo(self.h, self.nvml.NVML_CLOCK_SM)))
+            r = int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(self.nvml, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            for name, bit in self.BAD.items():
+                if r & bit:
+                    self.reasons.add(name)
+        else:
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=5).stdout.strip()
+            c = [x.strip() for x in out.split(",")]
+            self.sm.append(float(c[0]))
+            self.mx = float(c[1])
+            for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+                if c[2 + i].lower().startswith("active"):
+                    self.reasons.add(name)
+        self.n += 1
 
     def run(self):
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                self.sample()
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.02 if self.nvml is not None else 0.2)
 
     def __enter__(self):
         self.t.start()
@@ -71,14 +101,9 @@ class ClockSampler:
         self.t.join(timeout=3)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        reasons = []
-        for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
-            if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows):
-                reasons.append(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_min_mhz": float(min(self.sm)) if self.sm else None,
+                "sm_max_mhz": self.mx, "reasons": sorted(self.reasons), "samples": self.n,
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def make_objects(seed0, n_obj, im_sz):
@@ -153,9 +178,11 @@ def run_ours(args):
             ops.TIMING_HOOK = None
         return loss
 
+    # pinned result buffers: per object the loss (1) + d cam_pose (12) + d shapecode (256) + d texturecode (256)
+    res_host = torch.empty(N_OBJ, 1 + 12 + 512, dtype=torch.float32).pin_memory()
+
     def step_e2e():
-        tot = 0.0
-        for h in hobjs:
+        for i, h in enumerate(hobjs):
             cam = h["cam"].to(dev, non_blocking=True).requires_grad_()
             shp = h["shp"].to(dev, non_blocking=True).requires_grad_()
             tex = h["tex"].to(dev, non_blocking=True).requires_grad_()
@@ -163,9 +190,10 @@ def run_ours(args):
             rgb, dep, acc, tgt, occ = R.render_rays(model, dev, h["img"], h["mask"], cam, h["wlh"], K, h["roi"], shp, tex, im_sz=IM_SZ)
             loss = refine_loss(rgb, acc, tgt, occ)
             loss.backward()
-            tot += float(loss.item())                                      # D2H read of the step's result
-            _ = (cam.grad.cpu(), shp.grad.cpu(), tex.grad.cpu())            # and of the gradients the refine loop consumes
-        return tot
+            # D2H read of the step's result: the loss and the gradients the refine loop consumes, into pinned memory
+            res_host[i].copy_(torch.cat([loss.reshape(1), cam.grad.reshape(-1), shp.grad.reshape(-1), tex.grad.reshape(-1)]), non_blocking=True)
+        torch.cuda.synchronize()   # every object's result is on the host when the step ends
+        return float(res_host[:, 0].sum())
 
     def barrier():
         if world > 1:
@@ -205,13 +233,14 @@ def run_ours(args):
     lib.snb_kernel_timing_enable(0)
     for _ in range(2):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    with ClockSampler(local) as clk2:
+        ms_e2e = timed(step_e2e, args.steps)
 
     rays_per_step = N_OBJ * n_rays * world
     value = rays_per_step * args.steps / (ms_total / 1e3)
     e2e_value = rays_per_step * args.steps / (ms_e2e / 1e3)
     h2d = N_OBJ * (IM_SZ * IM_SZ * 3 * 4 + IM_SZ * IM_SZ * 4 + 12 * 4 + 9 * 4 + 2 * 256 * 4)
-    d2h = N_OBJ * (4 + 12 * 4 + 2 * 256 * 4)
+    d2h = N_OBJ * (1 + 12 + 512) * 4
 
     # roofline of the dominant kernel: the decoder MLP (tensor-pipe bound), from CUDA events recorded around the C-ABI
     # decoder calls inside the timed region (they bracket the tcgen05 kernel plus ~10 us of per-object latent GEMMs)
@@ -227,10 +256,17 @@ def run_ours(args):
     dom = max(roof, key=lambda k: roof[k]["total_ms"]) if roof else None
     peak = pk["tf_sustained"] if args.precision == "bf16" else None
     roofline = None
+    traffic = None
+    try:   # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture (scaled by samples per launch)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+        k = tj["tc2_%s_kernel" % dom]
+        traffic = int((k["dram_read_bytes"] + k["dram_write_bytes"]) * rows / tj["samples_per_captured_launch"])
+    except Exception:
+        traffic = None
     if dom:
-        roofline = {"bound": "tensor", "kernel": "tc_%s_kernel" % dom if args.precision == "bf16" else "sgemm_kernel (fp32 SIMT)",
+        roofline = {"bound": "tensor", "kernel": "tc2_%s_kernel" % dom if args.precision == "bf16" else "sgemm_kernel (fp32 SIMT)",
                     "achieved": round(roof[dom]["tflops"], 2), "peak": peak, "unit": "TFLOP/s",
-                    "frac": round(roof[dom]["tflops"] / peak, 4) if peak else None, "traffic": None,
+                    "frac": round(roof[dom]["tflops"] / peak, 4) if peak else None, "traffic": traffic if args.precision == "bf16" else None,
                     "peak_source": pk["source"] + ", sustained bf16", "flop_per_launch": flop_per_launch,
                     "avg_launch_ms": round(roof[dom]["ms"], 4),
                     "other": {k: {"ms": round(v["ms"], 4), "tflops": round(v["tflops"], 2)} for k, v in roof.items()},
@@ -251,7 +287,7 @@ def run_ours(args):
                        "precision": args.precision},
             "e2e": {"value": round(e2e_value, 1), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
-            "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": int(launches), "clocks": dict(clk.summary(), e2e_region=clk2.summary()), "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
 
 
