@@ -107,11 +107,11 @@ class ClockSampler:
 
 
 def make_objects(seed0, n_obj, im_sz):
-    from oracle import oracle  # synthetic-input generators only (shared with the tests so CPU and GPU see the same bits)
+    from supnerf_b200 import synthetic  # seeded input generators shared with the tests: CPU and GPU arms see the same bits
     objs = []
     for i in range(n_obj):
-        o = oracle.synthetic_object(seed0 + i, im_sz=im_sz)
-        s, t = oracle.synthetic_latents(seed0 + i, 1)
+        o = synthetic.synthetic_object(seed0 + i, im_sz=im_sz)
+        s, t = synthetic.synthetic_latents(seed0 + i, 1)
         o["shapecode"], o["texturecode"] = s, t
         objs.append(o)
     return objs
@@ -128,8 +128,7 @@ def refine_loss(rgb, acc, tgt, occ):
 # ----------------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import supnerf_b200 as snb
-    from supnerf_b200 import _lib, ops
-    from oracle import oracle
+    from supnerf_b200 import _lib, ops, synthetic
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -141,7 +140,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
-    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=0)
+    sd = synthetic.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=0)
     model = snb.AutoRFMix(shape_blocks=3, texture_blocks=1, latent_dim=256)
     model.load_state_dict(sd)
     model = model.to(dev)
@@ -154,28 +153,22 @@ def run_ours(args):
     # device-resident copies (for `value`) and pinned host copies (for `e2e`)
     dobjs, hobjs = [], []
     for o in objs:
-        tgt = o["img"].reshape(-1, 3).to(dev)          # crop already at im_sz: the reference's Resize is the identity here
-        occ = o["mask_occ"].reshape(-1, 1).to(dev)
-        dobjs.append(dict(K=o["K"].to(dev), cam=o["cam_pose"].to(dev).requires_grad_(), wlh=o["wlh"], roi=o["roi"], tgt=tgt, occ=occ,
+        # crop already at im_sz: the reference's Resize is the identity here
+        dobjs.append(dict(K=o["K"].to(dev), cam=o["cam_pose"].to(dev).requires_grad_(), wlh=o["wlh"], roi=o["roi"],
+                          img=o["img"].to(dev), mask=o["mask_occ"].to(dev),
                           shp=o["shapecode"].to(dev).requires_grad_(), tex=o["texturecode"].to(dev).requires_grad_()))
         hobjs.append(dict(K=o["K"].pin_memory(), cam=o["cam_pose"].pin_memory(), wlh=o["wlh"], roi=o["roi"], img=o["img"].pin_memory(),
                           mask=o["mask_occ"].pin_memory(), shp=o["shapecode"].pin_memory(), tex=o["texturecode"].pin_memory()))
 
-    kernel_times = {"fwd": [], "bwd": []}
-
-    def step_resident(record=False):
+    def step_resident():
+        """One pass over the batch through the public API (NeRFRenderer.render_rays -> fused C-ABI render) with every input
+        already resident in HBM; the loss and its backward to pose + latents close the step."""
         for d in dobjs:
             d["cam"].grad = d["shp"].grad = d["tex"].grad = None
-            rays_o, viewdir = snb.utils.get_rays(d["K"], d["cam"], d["roi"], uv_steps=[IM_SZ, IM_SZ])
-            xyz, vd, z_vals, _ = R.prepare_sampled_rays(rays_o, viewdir, d["wlh"])
-            if record:
-                e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-                ops.TIMING_HOOK = lambda which, ev: kernel_times[which].append(ev)
-            sig, rgbs = model(xyz, vd, d["shp"], d["tex"])
-            rgb, dep, acc = R.volume_render(sig.squeeze(-1), rgbs, z_vals)
-            loss = refine_loss(rgb, acc, d["tgt"], d["occ"])
+            rgb, dep, acc, tgt, occ = R.render_rays(model, dev, d["img"], d["mask"], d["cam"], d["wlh"], d["K"], d["roi"], d["shp"], d["tex"],
+                                                    im_sz=IM_SZ)
+            loss = snb.losses.refine_loss(rgb, acc, tgt, occ, 0.1)[0]
             loss.backward()
-            ops.TIMING_HOOK = None
         return loss
 
     # pinned result buffers: per object the loss (1) + d cam_pose (12) + d shapecode (256) + d texturecode (256)
@@ -188,12 +181,12 @@ def run_ours(args):
             tex = h["tex"].to(dev, non_blocking=True).requires_grad_()
             K = h["K"].to(dev, non_blocking=True)
             rgb, dep, acc, tgt, occ = R.render_rays(model, dev, h["img"], h["mask"], cam, h["wlh"], K, h["roi"], shp, tex, im_sz=IM_SZ)
-            loss = refine_loss(rgb, acc, tgt, occ)
+            loss = snb.losses.refine_loss(rgb, acc, tgt, occ, 0.1)[0]
             loss.backward()
             # D2H read of the step's result: the loss and the gradients the refine loop consumes, into pinned memory
-            res_host[i].copy_(torch.cat([loss.reshape(1), cam.grad.reshape(-1), shp.grad.reshape(-1), tex.grad.reshape(-1)]), non_blocking=True)
+            res_host[i].copy_(torch.cat([loss.detach().reshape(1), cam.grad.reshape(-1), shp.grad.reshape(-1), tex.grad.reshape(-1)]), non_blocking=True)
         torch.cuda.synchronize()   # every object's result is on the host when the step ends
-        return float(res_host[:, 0].sum())
+        return float(res_host[:, 0].sum().item())
 
     def barrier():
         if world > 1:
@@ -221,7 +214,7 @@ def run_ours(args):
     launches0 = lib.snb_launch_count()
     lib.snb_kernel_timing_enable(1)   # CUDA events on the launch stream around the tcgen05 kernels alone
     with ClockSampler(local) as clk:
-        ms_total = timed(step_resident, args.steps, record=True)
+        ms_total = timed(step_resident, args.steps)
     launches = lib.snb_launch_count() - launches0
     torch.cuda.synchronize()
     import ctypes
@@ -249,7 +242,7 @@ def run_ours(args):
     flop_per_launch = 2.0 * MAC_PER_SAMPLE * rows
     roof = {}
     for which in ("fwd", "bwd"):
-        ts = kern[which] if kern.get(which) else [a.elapsed_time(b) for a, b in kernel_times[which]]
+        ts = kern.get(which) or []
         if ts:
             avg = float(np.mean(ts))
             roof[which] = dict(ms=avg, tflops=flop_per_launch / (avg / 1e3) / 1e12, n=len(ts), total_ms=float(np.sum(ts)))

@@ -158,6 +158,51 @@ int snb_mlp_bwd(snb_handle h, int32_t precision, const float* xyz, const float* 
                 void* scratch, float* g_xyz, float* g_viewdir, float* g_shape_latent,
                 float* g_texture_latent, float* const* g_weights, void* stream);
 
+/* ---- fused render: rays -> slab test + stratified samples -> decoder -> compositing, one object per call ----------
+ * Replaces the body of NeRFRenderer.render_rays / render_rays_specified between the target resize and the return
+ * (renderer.py:125-165, :178-199: get_rays -> prepare_sampled_rays -> model(...) -> volume_render) and, for
+ * snb_render_bwd, the autograd backward of that chain (optimizer_nuscenes.py:737 `loss.backward()`).
+ * Same operands as the stage calls above (px, py, K, c2w, z_steps, jitter; latents (1, latent_dim)).  All
+ * intermediates live in `workspace` (snb_render_workspace_bytes, 256-byte aligned, kept by the caller until the
+ * backward has run) and `scratch` (snb_render_bwd_scratch_bytes).  Outputs: out_rgb (N,3), out_depth (N), out_acc (N),
+ * out_hit (N) uint8.  Backward: g_c2w (12 floats, overwritten; NULL = no pose gradient, which also skips the d xyz /
+ * d viewdir part of the decoder backward), g_shape_latent / g_texture_latent (latent_dim each, overwritten),
+ * g_weights as in snb_mlp_bwd (NULL = frozen weights). */
+typedef struct {
+  int64_t n_rays;
+  int32_t n_samples;
+  int32_t precision;  /* SNB_PREC_* */
+  int32_t flags;      /* SNB_WHITE_BKGD | SNB_SIGMA_RELU */
+  float half_diag;    /* diag / 2, the reference's host-rounded float32 (renderer.py:92) */
+  float aabb_half[3]; /* (l, w, h) / diag (renderer.py:97-100) */
+} snb_render_desc;
+size_t snb_render_workspace_bytes(snb_handle h, const snb_render_desc* d);
+size_t snb_render_bwd_scratch_bytes(snb_handle h, const snb_render_desc* d);
+int snb_render_fwd(snb_handle h, const snb_render_desc* d, const float* px, const float* py, const float* K,
+                   const float* c2w, const float* z_steps, const float* jitter, const float* shape_latent,
+                   const float* texture_latent, float* out_rgb, float* out_depth, float* out_acc, uint8_t* out_hit,
+                   void* workspace, void* stream);
+int snb_render_bwd(snb_handle h, const snb_render_desc* d, const float* px, const float* py, const float* K,
+                   const float* c2w, const float* z_steps, const float* jitter, const float* shape_latent,
+                   const float* texture_latent, const void* workspace, const float* g_rgb, const float* g_depth,
+                   const float* g_acc, void* scratch, float* g_c2w, float* g_shape_latent, float* g_texture_latent,
+                   float* const* g_weights, void* stream);
+
+/* ---- refine-iteration loss (the caller just above the render) -------------------------------
+ * Replaces the inline loss of optimizer_nuscenes.py:729-736 (= optimizer_kitti.py / optimizer_waymo.py, and the render
+ * losses of trainer_unified_nuscenes.py:316-332):
+ *   den = sum|occ| + 1e-9; loss_rgb = sum((rgb - tgt)^2 |occ|) / den; loss_occ = sum(exp(-occ (0.5 - acc)) |occ|) / den;
+ *   loss = loss_rgb + occ_coef * loss_occ.
+ * rgb, tgt (N,3); acc (N); occ (N) in {-1,0,+1}.  den: NULL, or a device float holding a caller-computed denominator (the
+ * ray-sharded mode passes the GLOBAL sum|occ| + 1e-9).  out3 = {loss, loss_rgb, loss_occ}.  scratch:
+ * snb_refine_loss_scratch_bytes(), kept until the backward.  Backward: g_loss = device float (NULL = 1), writes
+ * g_rgb (N,3) and g_acc (N). */
+size_t snb_refine_loss_scratch_bytes(void);
+int snb_refine_loss_fwd(const float* rgb, const float* acc, const float* tgt, const float* occ, int64_t n_rays,
+                        float occ_coef, const float* den, float* out3, void* scratch, void* stream);
+int snb_refine_loss_bwd(const float* rgb, const float* acc, const float* tgt, const float* occ, int64_t n_rays,
+                        float occ_coef, const void* scratch, const float* g_loss, float* g_rgb, float* g_acc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

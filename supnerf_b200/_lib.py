@@ -18,6 +18,11 @@ class SnbArch(ctypes.Structure):
                 ("latent_dim", c_i32), ("num_xyz_freq", c_i32), ("num_dir_freq", c_i32)]
 
 
+class SnbRenderDesc(ctypes.Structure):
+    _fields_ = [("n_rays", c_i64), ("n_samples", c_i32), ("precision", c_i32), ("flags", c_i32), ("half_diag", c_flt),
+                ("aabb_half", c_flt * 3)]
+
+
 # name -> (restype, argtypes); mirrors include/supnerf_b200.h one to one
 SIGNATURES = {
     "snb_abi_version": (c_i32, []),
@@ -50,6 +55,13 @@ SIGNATURES = {
     "snb_mlp_fwd": (c_i32, [ctypes.c_void_p, c_i32, c_f, c_f, c_i64, c_i64, c_f, c_f, c_f, c_f, c_f, c_f]),
     "snb_mlp_bwd": (c_i32, [ctypes.c_void_p, c_i32, c_f, c_f, c_i64, c_i64, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
                             c_f, c_f, ctypes.POINTER(ctypes.c_void_p), c_f]),
+    "snb_refine_loss_scratch_bytes": (c_sz, []),
+    "snb_refine_loss_fwd": (c_i32, [c_f, c_f, c_f, c_f, c_i64, c_flt, c_f, c_f, c_f, c_f]),
+    "snb_refine_loss_bwd": (c_i32, [c_f, c_f, c_f, c_f, c_i64, c_flt, c_f, c_f, c_f, c_f, c_f]),
+    "snb_render_workspace_bytes": (c_sz, [ctypes.c_void_p, ctypes.POINTER(SnbRenderDesc)]),
+    "snb_render_bwd_scratch_bytes": (c_sz, [ctypes.c_void_p, ctypes.POINTER(SnbRenderDesc)]),
+    "snb_render_fwd": (c_i32, [ctypes.c_void_p, ctypes.POINTER(SnbRenderDesc)] + [c_f] * 14),
+    "snb_render_bwd": (c_i32, [ctypes.c_void_p, ctypes.POINTER(SnbRenderDesc)] + [c_f] * 16 + [ctypes.POINTER(ctypes.c_void_p), c_f]),
 }
 
 _lib = None

@@ -50,12 +50,13 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const __grid_constant__
   }
 }
 
-// grid (2, B, D/32): type 0 = shape slots, 1 = texture slots; the block owns 32 latent units, its 8 warps split the W
-// hidden units of every slot, partial sums meet in shared memory.  dz [slot][b][W] = d loss / d z (post-ReLU).
-__global__ void __launch_bounds__(256) latent_bwd_kernel(const __grid_constant__ LatentLayers L, int64_t B,
-                                                        const float* __restrict__ zlat, const float* __restrict__ dz,
-                                                        float* __restrict__ g_shape, float* __restrict__ g_texture) {
-  __shared__ float part[8][32];
+// grid (2, B, D/32): type 0 = shape slots, 1 = texture slots; the block owns 32 latent units, its 32 warps split the W
+// hidden units of every slot (8 independent loads in flight per lane), partial sums meet in shared memory.
+// dz [slot][b][W] = d loss / d z (post-ReLU).
+__global__ void __launch_bounds__(1024) latent_bwd_kernel(const __grid_constant__ LatentLayers L, int64_t B,
+                                                         const float* __restrict__ zlat, const float* __restrict__ dz,
+                                                         float* __restrict__ g_shape, float* __restrict__ g_texture) {
+  __shared__ float part[32][33];
   const int type = blockIdx.x;
   const int64_t b = blockIdx.y;
   float* out = type == 0 ? g_shape : g_texture;
@@ -69,9 +70,17 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const __grid_constant__
       const float* z = zlat + ((size_t)slot * B + b) * L.W;
       const float* g = dz + ((size_t)slot * B + b) * L.W;
       const float* w = L.wl[slot] + k;
-      for (int o = warp; o < L.W; o += 8) {
-        const float gm = z[o] > 0.f ? g[o] : 0.f;
-        acc = fmaf(gm, __ldg(w + (size_t)o * L.D), acc);
+      for (int o0 = warp; o0 < L.W; o0 += 32 * 8) {
+        float wv[8], gm[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int o = o0 + 32 * u;
+          const bool ok = o < L.W;
+          wv[u] = ok ? __ldg(w + (size_t)o * L.D) : 0.f;
+          gm[u] = (ok && z[o] > 0.f) ? g[o] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = fmaf(gm[u], wv[u], acc);
       }
     }
   }
@@ -80,7 +89,7 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const __grid_constant__
   if (warp == 0 && k < L.D) {
     float v = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v += part[i][lane];
+    for (int i = 0; i < 32; ++i) v += part[i][lane];
     out[b * L.D + k] = v;
   }
 }
@@ -119,7 +128,7 @@ int latent_backward_fused(const snb_handle_s* h, int64_t B, const float* zlat, c
   LatentLayers L;
   if (fill_layers(h, L)) return 2;
   dim3 grid(2, (unsigned)B, (unsigned)((L.D + 31) / 32));
-  latent_bwd_kernel<<<grid, 256, 0, st>>>(L, B, zlat, dz, g_shape_latent, g_texture_latent);
+  latent_bwd_kernel<<<grid, 1024, 0, st>>>(L, B, zlat, dz, g_shape_latent, g_texture_latent);
   SNB_LAUNCH_CHECK();
   return 0;
 }

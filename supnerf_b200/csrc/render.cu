@@ -1,0 +1,123 @@
+// Fused render entry points: one C call enqueues the whole box-render of one object (rays -> slab test + stratified
+// samples -> decoder -> compositing) on the caller's stream, and one call its backward.  Replaces the body of
+// NeRFRenderer.render_rays between the target resize and the return (renderer.py:125-165) and its autograd backward.
+// Every intermediate lives in ONE caller-provided workspace (no allocation, no synchronisation here), so a refine
+// iteration costs two host calls per object instead of ~50 autograd-node launches.
+#include "common.cuh"
+#include "handle.h"
+
+using namespace snb;
+
+namespace {
+
+inline size_t al(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+
+// forward workspace (kept for the backward): rays_o, viewdir (N,3) | xyz, vrep (M,3) | z_vals (M) | sigma (M) | rgb (M,3) | mlp ws
+struct FwdLayout {
+  size_t rays_o, viewdir, xyz, vrep, z, sigma, rgb, mlp, total;
+  FwdLayout(snb_handle h, const snb_render_desc& d) {
+    const size_t N = (size_t)d.n_rays, M = N * (size_t)d.n_samples;
+    size_t o = 0;
+    rays_o = o; o += al(N * 12);
+    viewdir = o; o += al(N * 12);
+    xyz = o; o += al(M * 12);
+    vrep = o; o += al(M * 12);
+    z = o; o += al(M * 4);
+    sigma = o; o += al(M * 4);
+    rgb = o; o += al(M * 12);
+    mlp = o; o += al(snb_mlp_workspace_bytes(h, (int64_t)M, 1, d.precision));
+    total = o;
+  }
+};
+
+// backward scratch: g_sigma (M) | g_rgbs (M,3) | g_z (M) | g_xyz, g_vrep (M,3) | g_rays_o, g_viewdir (N,3) | mlp scratch
+struct BwdLayout {
+  size_t g_sigma, g_rgbs, g_z, g_xyz, g_vrep, g_rays_o, g_viewdir, mlp, total;
+  BwdLayout(snb_handle h, const snb_render_desc& d) {
+    const size_t N = (size_t)d.n_rays, M = N * (size_t)d.n_samples;
+    size_t o = 0;
+    g_sigma = o; o += al(M * 4);
+    g_rgbs = o; o += al(M * 12);
+    g_z = o; o += al(M * 4);
+    g_xyz = o; o += al(M * 12);
+    g_vrep = o; o += al(M * 12);
+    g_rays_o = o; o += al(N * 12);
+    g_viewdir = o; o += al(N * 12);
+    mlp = o; o += al(snb_mlp_bwd_scratch_bytes(h, (int64_t)M, 1, d.precision));
+    total = o;
+  }
+};
+
+int check_desc(snb_handle h, const snb_render_desc* d, const char* who) {
+  SNB_REQUIRE(h != nullptr && d != nullptr, "%s: null handle or descriptor", who);
+  SNB_REQUIRE(d->n_rays >= 0 && d->n_samples >= 1, "%s: bad sizes", who);
+  SNB_REQUIRE(d->precision == SNB_PREC_FP32 || d->precision == SNB_PREC_BF16, "%s: unknown precision %d", who, d->precision);
+  return 0;
+}
+
+inline float* F(void* base, size_t off) { return reinterpret_cast<float*>(static_cast<uint8_t*>(base) + off); }
+inline const float* F(const void* base, size_t off) { return reinterpret_cast<const float*>(static_cast<const uint8_t*>(base) + off); }
+
+}  // namespace
+
+extern "C" size_t snb_render_workspace_bytes(snb_handle h, const snb_render_desc* d) {
+  if (!h || !d || d->n_rays < 0 || d->n_samples < 1) return 0;
+  return FwdLayout(h, *d).total + 256;
+}
+
+extern "C" size_t snb_render_bwd_scratch_bytes(snb_handle h, const snb_render_desc* d) {
+  if (!h || !d || d->n_rays < 0 || d->n_samples < 1) return 0;
+  return BwdLayout(h, *d).total + 256;
+}
+
+extern "C" int snb_render_fwd(snb_handle h, const snb_render_desc* d, const float* px, const float* py, const float* K,
+                              const float* c2w, const float* z_steps, const float* jitter, const float* shape_latent,
+                              const float* texture_latent, float* out_rgb, float* out_depth, float* out_acc, uint8_t* out_hit,
+                              void* workspace, void* stream) {
+  if (check_desc(h, d, "render_fwd")) return 2;
+  if (d->n_rays == 0) return 0;
+  SNB_REQUIRE(px && py && K && c2w && z_steps && jitter && shape_latent && texture_latent && out_rgb && out_depth && out_acc &&
+              out_hit && workspace, "render_fwd: null pointer");
+  SNB_REQUIRE(((uintptr_t)workspace & 255) == 0, "render_fwd: workspace must be 256-byte aligned");
+  const FwdLayout L(h, *d);
+  const int64_t N = d->n_rays, M = N * d->n_samples;
+  void* ws = workspace;
+  if (snb_get_rays_fwd(px, py, N, K, c2w, F(ws, L.rays_o), F(ws, L.viewdir), stream)) return 1;
+  if (snb_sample_box_fwd(F(ws, L.rays_o), F(ws, L.viewdir), z_steps, jitter, N, d->n_samples, d->half_diag, d->aabb_half,
+                         F(ws, L.xyz), F(ws, L.vrep), F(ws, L.z), out_hit, stream)) return 1;
+  if (snb_mlp_fwd(h, d->precision, F(ws, L.xyz), F(ws, L.vrep), M, 1, shape_latent, texture_latent, F(ws, L.sigma), F(ws, L.rgb),
+                  static_cast<uint8_t*>(ws) + L.mlp, stream)) return 1;
+  return snb_composite_fwd(F(ws, L.sigma), F(ws, L.rgb), F(ws, L.z), 1, N, d->n_samples, d->flags, out_rgb, out_depth, out_acc,
+                           stream);
+}
+
+extern "C" int snb_render_bwd(snb_handle h, const snb_render_desc* d, const float* px, const float* py, const float* K,
+                              const float* c2w, const float* z_steps, const float* jitter, const float* shape_latent,
+                              const float* texture_latent, const void* workspace, const float* g_rgb, const float* g_depth,
+                              const float* g_acc, void* scratch, float* g_c2w, float* g_shape_latent, float* g_texture_latent,
+                              float* const* g_weights, void* stream) {
+  if (check_desc(h, d, "render_bwd")) return 2;
+  SNB_REQUIRE(g_shape_latent && g_texture_latent, "render_bwd: latent gradient outputs are required");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_c2w) SNB_CHECK_CUDA(cudaMemsetAsync(g_c2w, 0, 12 * sizeof(float), st));
+  if (d->n_rays == 0) return 0;
+  SNB_REQUIRE(px && py && K && c2w && z_steps && jitter && shape_latent && texture_latent && workspace && g_rgb && g_depth &&
+              g_acc && scratch, "render_bwd: null pointer");
+  SNB_REQUIRE((((uintptr_t)workspace | (uintptr_t)scratch) & 255) == 0, "render_bwd: workspace/scratch must be 256-byte aligned");
+  const FwdLayout L(h, *d);
+  const BwdLayout G(h, *d);
+  const int64_t N = d->n_rays, M = N * d->n_samples;
+  const void* ws = workspace;
+  void* sc = scratch;
+  const bool pose = g_c2w != nullptr;
+  if (snb_composite_bwd(F(ws, L.sigma), F(ws, L.rgb), F(ws, L.z), 1, N, d->n_samples, d->flags, g_rgb, g_depth, g_acc,
+                        F(sc, G.g_sigma), F(sc, G.g_rgbs), pose ? F(sc, G.g_z) : nullptr, stream)) return 1;
+  if (snb_mlp_bwd(h, d->precision, F(ws, L.xyz), F(ws, L.vrep), M, 1, shape_latent, texture_latent, F(ws, L.sigma),
+                  F(sc, G.g_sigma), F(sc, G.g_rgbs), static_cast<const uint8_t*>(ws) + L.mlp, static_cast<uint8_t*>(sc) + G.mlp,
+                  pose ? F(sc, G.g_xyz) : nullptr, pose ? F(sc, G.g_vrep) : nullptr, g_shape_latent, g_texture_latent, g_weights,
+                  stream)) return 1;
+  if (!pose) return 0;
+  if (snb_sample_box_bwd(F(ws, L.rays_o), F(ws, L.viewdir), z_steps, jitter, N, d->n_samples, d->half_diag, d->aabb_half,
+                         F(sc, G.g_xyz), F(sc, G.g_vrep), F(sc, G.g_z), F(sc, G.g_rays_o), F(sc, G.g_viewdir), stream)) return 1;
+  return snb_get_rays_bwd(px, py, N, K, c2w, F(sc, G.g_rays_o), F(sc, G.g_viewdir), g_c2w, stream);
+}

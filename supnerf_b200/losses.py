@@ -1,0 +1,59 @@
+"""The refine-iteration losses, one CUDA launch per direction.
+
+The reference has no function for them: the same five lines are written inline in every optimiser / trainer
+(optimizer_nuscenes.py:729-736, optimizer_kitti.py, optimizer_waymo.py, trainer_unified_nuscenes.py:316-332):
+
+    loss_rgb = torch.sum((rgb_rays - rgb_tgt) ** 2 * torch.abs(occ_pixels)) / (torch.sum(torch.abs(occ_pixels)) + 1e-9)
+    loss_occ = torch.sum(torch.exp(-occ_pixels * (0.5 - acc_trans_rays.unsqueeze(-1))) * torch.abs(occ_pixels)) / (torch.sum(torch.abs(occ_pixels)) + 1e-9)
+    loss = loss_rgb + self.hpams['loss_occ_coef'] * loss_occ
+
+``refine_loss`` computes exactly that with the kernels of csrc/loss.cu; no CPU fallback."""
+import torch
+
+from . import _lib
+from ._lib import check, f32c, ptr, require_cuda, stream_ptr
+
+
+class _RefineLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rgb, acc, tgt, occ, coef, den):
+        lib = _lib.load()
+        require_cuda(rgb, acc, tgt, occ, den)
+        rgb, acc, tgt, occ = f32c(rgb), f32c(acc), f32c(tgt), f32c(occ)
+        den = f32c(den).reshape(1) if den is not None else None
+        n = acc.numel()
+        dev = rgb.device
+        out = torch.empty(3, device=dev, dtype=torch.float32)
+        scratch = torch.empty(lib.snb_refine_loss_scratch_bytes(), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.snb_refine_loss_fwd(ptr(rgb), ptr(acc), ptr(tgt), ptr(occ), n, float(coef), ptr(den), ptr(out), ptr(scratch),
+                                          stream_ptr()), "snb_refine_loss_fwd")
+        ctx.save_for_backward(rgb, acc, tgt, occ, scratch)
+        ctx.coef = float(coef)
+        loss, parts = out[0], out[1:]
+        ctx.mark_non_differentiable(parts)
+        return loss, parts
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_parts):
+        lib = _lib.load()
+        rgb, acc, tgt, occ, scratch = ctx.saved_tensors
+        n = acc.numel()
+        g_rgb = torch.empty_like(rgb)
+        g_acc = torch.empty_like(acc)
+        g_loss = f32c(g_loss)
+        with torch.cuda.device(rgb.device):
+            check(lib.snb_refine_loss_bwd(ptr(rgb), ptr(acc), ptr(tgt), ptr(occ), n, ctx.coef, ptr(scratch), ptr(g_loss), ptr(g_rgb),
+                                          ptr(g_acc), stream_ptr()), "snb_refine_loss_bwd")
+        return g_rgb, g_acc, None, None, None, None
+
+
+def refine_loss(rgb_rays, acc_trans_rays, rgb_tgt, occ_pixels, loss_occ_coef=0.1, den=None):
+    """-> (loss, loss_rgb, loss_occ), 0-dim CUDA tensors; ``loss`` is differentiable to rgb_rays and acc_trans_rays.
+    rgb_rays, rgb_tgt (N,3); acc_trans_rays (N,); occ_pixels (N,1).  ``den``: optional caller-computed denominator
+    (a 1-element tensor; the ray-sharded mode passes the global ``sum|occ| + 1e-9``)."""
+    n = acc_trans_rays.numel()
+    if tuple(rgb_rays.shape) != (n, 3) or tuple(rgb_tgt.shape) != (n, 3) or occ_pixels.numel() != n:
+        raise ValueError("refine_loss: expected rgb (N,3), acc (N,), tgt (N,3), occ (N,1)")
+    loss, parts = _RefineLoss.apply(rgb_rays, acc_trans_rays.reshape(-1), rgb_tgt, occ_pixels.reshape(-1), loss_occ_coef, den)
+    return loss, parts[0], parts[1]

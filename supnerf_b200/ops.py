@@ -345,6 +345,79 @@ def decoder(handle, precision, xyz, viewdir, shape_latent, texture_latent, weigh
                           shape_latent, texture_latent, *weights)
 
 
+# ---------------------------------------------------------------------------------------------------
+# fused box render of one object — renderer.py:125-165 (get_rays -> prepare_sampled_rays -> model -> volume_render)
+# ---------------------------------------------------------------------------------------------------
+class _RenderBox(torch.autograd.Function):
+    """One autograd node for the whole per-object render: two C-ABI calls (snb_render_fwd / snb_render_bwd), every
+    intermediate in one workspace tensor.  Differentiable to cam_pose, the latents and (fp32 back end) the weights."""
+
+    @staticmethod
+    def forward(ctx, handle, precision, n_samples, flags, half_diag, aabb_half, px, py, K, c2w, z_steps, jitter, shape_latent,
+                texture_latent, *weights):
+        lib = _lib.load()
+        require_cuda(px, py, K, c2w, z_steps, jitter, shape_latent, texture_latent)
+        px, py, K, c2w, z_steps, jitter = f32c(px), f32c(py), f32c(K), f32c(c2w), f32c(z_steps), f32c(jitter)
+        shape_latent, texture_latent = f32c(shape_latent), f32c(texture_latent)
+        n = px.numel()
+        dev = px.device
+        desc = _lib.SnbRenderDesc(n, int(n_samples), int(precision), int(flags), float(half_diag),
+                                  (ctypes.c_float * 3)(*[float(v) for v in aabb_half]))
+        handle.set_weights(weights)
+        if precision == PREC["bf16"]:
+            handle.ensure_packed(weights)
+        ws = torch.empty(lib.snb_render_workspace_bytes(handle.h, ctypes.byref(desc)), dtype=torch.uint8, device=dev)
+        o_rgb = torch.empty(n, 3, device=dev, dtype=torch.float32)
+        o_dep = torch.empty(n, device=dev, dtype=torch.float32)
+        o_acc = torch.empty(n, device=dev, dtype=torch.float32)
+        hit = torch.empty(n, device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev):
+            check(lib.snb_render_fwd(handle.h, ctypes.byref(desc), ptr(px), ptr(py), ptr(K), ptr(c2w), ptr(z_steps), ptr(jitter),
+                                     ptr(shape_latent), ptr(texture_latent), ptr(o_rgb), ptr(o_dep), ptr(o_acc), ptr(hit), ptr(ws),
+                                     stream_ptr()), "snb_render_fwd")
+        ctx.save_for_backward(px, py, K, c2w, z_steps, jitter, shape_latent, texture_latent, ws, *weights)
+        ctx.meta = (handle, desc)
+        hitb = hit.bool()
+        ctx.mark_non_differentiable(hitb)
+        return o_rgb, o_dep, o_acc, hitb
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_dep, g_acc, _g_hit):
+        lib = _lib.load()
+        px, py, K, c2w, z_steps, jitter, shape_latent, texture_latent, ws, *weights = ctx.saved_tensors
+        handle, desc = ctx.meta
+        n = px.numel()
+        dev = px.device
+        g_rgb = f32c(g_rgb) if g_rgb is not None else torch.zeros(n, 3, device=dev)
+        g_dep = f32c(g_dep) if g_dep is not None else torch.zeros(n, device=dev)
+        g_acc = f32c(g_acc) if g_acc is not None else torch.zeros(n, device=dev)
+        need = ctx.needs_input_grad
+        g_c2w = torch.empty(3, 4, device=dev, dtype=torch.float32) if need[9] else None
+        g_sl = torch.empty_like(shape_latent)
+        g_tl = torch.empty_like(texture_latent)
+        need_w = any(need[14:])
+        gws, gw_arr = None, None
+        if need_w:
+            gws = [torch.empty_like(w, dtype=torch.float32).contiguous() for w in weights]
+            gw_arr = (ctypes.c_void_p * len(gws))(*[g.data_ptr() for g in gws])
+        handle.set_weights(weights)
+        scratch = torch.empty(lib.snb_render_bwd_scratch_bytes(handle.h, ctypes.byref(desc)), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.snb_render_bwd(handle.h, ctypes.byref(desc), ptr(px), ptr(py), ptr(K), ptr(c2w), ptr(z_steps), ptr(jitter),
+                                     ptr(shape_latent), ptr(texture_latent), ptr(ws), ptr(g_rgb), ptr(g_dep), ptr(g_acc),
+                                     ptr(scratch), ptr(g_c2w), ptr(g_sl), ptr(g_tl), gw_arr, stream_ptr()), "snb_render_bwd")
+        out_w = tuple(gws) if need_w else tuple(None for _ in weights)
+        return (None,) * 9 + (g_c2w, None, None, g_sl if need[12] else None, g_tl if need[13] else None) + out_w
+
+
+def render_box(handle, precision, n_samples, white_bkgd, half_diag, aabb_half, px, py, K, c2w, z_steps, jitter, shape_latent,
+               texture_latent, weights):
+    """-> rgb (N,3), depth (N,), acc (N,), hit (N,) bool for one object (latents (1,D))."""
+    flags = (WHITE_BKGD if white_bkgd else 0) | SIGMA_RELU
+    return _RenderBox.apply(handle, PREC[precision] if isinstance(precision, str) else precision, n_samples, flags, half_diag,
+                            aabb_half, px, py, K, c2w, z_steps, jitter, shape_latent, texture_latent, *weights)
+
+
 def box_constants(obj_sz):
     """renderer.py:92-100: diag and the AABB half extents (l,w,h)/diag, rounded to float32 on the host."""
     obj_sz = np.asarray(obj_sz)

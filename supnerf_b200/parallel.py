@@ -1,0 +1,109 @@
+"""Multi-GPU sharding of the render hot path.  One process per GPU (``torch.distributed``; NCCL over
+NVLink on the B200 box, gloo in the CPU tests).  The reference has no equivalent: it only wraps the model in
+``nn.DataParallel`` (trainer_nerf_nuscenes.py:24-60), so nothing here mirrors a reference signature.
+
+* **object-parallel** (configs C2/C3): objects are independent (own pose, latents, rays, loss, optimiser state):
+  rank r takes objects r, r+G, ...  No collective on the data path.
+* **ray-sharded** (config C4): one object, contiguous ray tiles per rank, weights / pose / latents replicated.  Loss
+  denominators depend only on the input mask, so every rank evaluates the GLOBAL denominator locally; each rank's partial
+  ``d cam_pose (12) | d shapecode (D) | d texturecode (D) | loss (1)`` go into ONE flat fp32 buffer and ONE
+  ``all_reduce(sum)``; afterwards every rank holds identical gradients and applies the identical optimiser step.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import utils as U
+
+TILE_ROWS = 128  # the tcgen05 decoder works on 128-sample tiles; shards keep ray*sample rows tile-aligned
+
+
+def object_shard(n_objects, rank, world):
+    """Indices of the objects rank `rank` owns: r, r+G, r+2G, ... (object-parallel)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    return list(range(rank, n_objects, world))
+
+
+def ray_shard(n_rays, n_samples, rank, world):
+    """[start, end) of the contiguous ray tile of `rank`.  Tile boundaries are multiples of 128/gcd(128, S) rays so every
+    shard's N*S sample rows are a whole number of 128-row decoder tiles (except the tail shard, which takes the rest)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    align = TILE_ROWS // math.gcd(TILE_ROWS, int(n_samples))
+    units = -(-n_rays // align)                      # ceil
+    per = -(-units // world)
+    start = min(rank * per * align, n_rays)
+    end = min((rank + 1) * per * align, n_rays)
+    return start, end
+
+
+def refine_loss_sharded(rgb_rays, acc_rays, rgb_tgt, occ_pixels, occ_all, loss_occ_coef=0.1):
+    """This rank's PARTIAL of the refine loss (optimizer_nuscenes.py:729-736): local numerators over the GLOBAL
+    denominator sum|occ_all| + 1e-9 (a function of the input mask only, so every rank evaluates it locally), so that the
+    partials of all ranks add up to the single-GPU loss.  Runs the fused loss kernel (losses.refine_loss); CUDA only."""
+    from . import losses
+    den = torch.sum(torch.abs(occ_all)) + 1e-9
+    return losses.refine_loss(rgb_rays, acc_rays, rgb_tgt, occ_pixels, loss_occ_coef, den=den)[0]
+
+
+def allreduce_grads(params, loss=None, group=None):
+    """Sum the gradients of `params` (cam_pose, shapecode, texturecode, ...) and, if given, the partial loss over all ranks
+    with ONE all_reduce of one flat fp32 buffer (2.1 KB for 12 + 256 + 256 + 1 floats).  Writes the sums back into
+    ``p.grad`` and returns the global loss (a 0-dim tensor) or None."""
+    flat = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params]
+    if loss is not None:
+        flat.append(loss.detach().reshape(1).float())
+    buf = torch.cat(flat)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for p in params:
+        n = p.numel()
+        g = buf[off:off + n].reshape(p.shape).to(p.dtype)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += n
+    return buf[off] if loss is not None else None
+
+
+def render_rays_sharded(renderer, model, device, img, mask_occ, cam_pose, obj_sz, K, roi, shapecode, texturecode, im_sz=64,
+                        rank=None, world=None):
+    """Ray-sharded NeRFRenderer.render_rays (renderer.py:117-167 semantics, `n_rays=None`): renders only this rank's
+    contiguous ray tile.  The (N,S) jitter is drawn in full on every rank (same generator state => same numbers as the
+    single-GPU call) and sliced, so the union of the shards is bit-identical to the unsharded render.
+    -> rgb, depth, acc, rgb_tgt, occ_pixels of the shard, plus occ_all (N,1) for the global loss denominator."""
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    device = torch.device(device)
+    px, py = U._pixel_grid_on(device, roi, [im_sz, im_sz])
+    img, mask_occ = U._resize_targets(img, mask_occ, im_sz)
+    n = px.numel()
+    a, b = ray_shard(n, renderer.n_samples, rank, world)
+    rgb_tgt = img.reshape(-1, 3)[a:b].to(device, non_blocking=True)
+    occ_all = mask_occ.reshape(-1, 1).to(device, non_blocking=True)
+    jitter = torch.rand_like(torch.empty(n, renderer.n_samples, device=device))[a:b]
+    rgb, dep, acc = renderer._render_fused(model, device, px[a:b], py[a:b], K, cam_pose, obj_sz, shapecode, texturecode,
+                                           jitter=jitter.contiguous())
+    return rgb, dep, acc, rgb_tgt, occ_all[a:b], occ_all
+
+
+def gather_rays(t, n_rays, n_samples, group=None):
+    """Optional: assemble the full (N, ...) image from the per-rank shards (an all_gather of 20 B/ray; only when the caller
+    wants the whole render on every rank)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return t
+    world = dist.get_world_size(group)
+    sizes = [ray_shard(n_rays, n_samples, r, world) for r in range(world)]
+    width = max(b - a for a, b in sizes)
+    pad = torch.zeros((width,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    outs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(outs, pad, group=group)
+    return torch.cat([o[:b - a] for o, (a, b) in zip(outs, sizes)], 0)

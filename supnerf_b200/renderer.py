@@ -7,9 +7,11 @@ import random
 import numpy as np
 import torch
 
-from . import ops
+from . import models, ops
 from . import utils as U
 from .utils import get_rays, get_rays_specified, ray_box_intersection, ray_box_intersection_tensor  # noqa: F401
+
+FUSED_RENDER = True  # render_rays / render_rays_specified go through ops.render_box (one autograd node); False = staged ops
 
 
 class NeRFRenderer(torch.nn.Module):
@@ -57,6 +59,28 @@ class NeRFRenderer(torch.nn.Module):
             xyz, vd, z_vals, hit = xyz.to(rays_o.device), vd.to(rays_o.device), z_vals.to(rays_o.device), hit.to(rays_o.device)
         return xyz, vd, z_vals, hit
 
+    def _render_fused(self, model, device, px, py, K, cam_pose, obj_sz, shapecode, texturecode, jitter=None):
+        """get_rays -> prepare_sampled_rays -> model -> volume_render (renderer.py:125,153-165) as ONE autograd node /
+        two C-ABI calls (ops.render_box).  Same RNG consumption as the staged path: one torch.rand_like of (N,S)."""
+        device = torch.device(device)
+        diag, half = ops.box_constants(obj_sz)
+        n = px.numel()
+        step = 1.0 / self.n_samples
+        z_steps = torch.linspace(0, 1 - step, self.n_samples, device=device)
+        if jitter is None:
+            jitter = torch.rand_like(torch.empty(n, self.n_samples, device=device))  # renderer.py:39-40
+        prec = model.precision or models.get_default_precision()
+        rgb, dep, acc, _hit = ops.render_box(model._handle(device), prec, self.n_samples, self.white_bkgd, diag / 2, half,
+                                             px, py, K.to(device, non_blocking=True), cam_pose.to(device, non_blocking=True),
+                                             z_steps, jitter, shapecode.to(device, non_blocking=True),
+                                             texturecode.to(device, non_blocking=True), model._weights())
+        return rgb, dep, acc
+
+    @staticmethod
+    def _can_fuse(model, device, kitti2nusc, shapecode):
+        return (FUSED_RENDER and not kitti2nusc and isinstance(model, models._DecoderBase) and shapecode.shape[0] == 1
+                and torch.device(device).type == "cuda")
+
     def _decode_and_render(self, model, device, xyz, viewdir, z_vals, shapecode, texturecode, kitti2nusc):
         if kitti2nusc:
             xyz, viewdir = U._kitti2nusc(xyz, viewdir, device)
@@ -66,10 +90,24 @@ class NeRFRenderer(torch.nn.Module):
     def render_rays(self, model, device, img, mask_occ, cam_pose, obj_sz, K, roi, shapecode, texturecode,
                     kitti2nusc=False, im_sz=64, n_rays=None):
         """renderer.py:117-167."""
+        if self._can_fuse(model, device, kitti2nusc, shapecode):
+            px, py = U._pixel_grid_on(torch.device(device), roi, [im_sz, im_sz])
+            img, mask_occ = U._resize_targets(img, mask_occ, im_sz)
+            rgb_tgt = img.reshape(-1, 3).to(device, non_blocking=True)
+            occ_pixels = mask_occ.reshape(-1, 1).to(device, non_blocking=True)
+            if n_rays is not None:
+                n_rays = np.minimum(px.numel(), n_rays)
+                random_ray_ids = np.random.permutation(px.numel())[:n_rays]
+                px, py = px[random_ray_ids], py[random_ray_ids]
+                rgb_tgt = rgb_tgt[random_ray_ids]
+                occ_pixels = occ_pixels[random_ray_ids]
+            rgb_rays, depth_rays, acc_trans_rays = self._render_fused(model, device, px, py, K, cam_pose, obj_sz, shapecode,
+                                                                      texturecode)
+            return rgb_rays, depth_rays, acc_trans_rays, rgb_tgt, occ_pixels
         rays_o, viewdir = get_rays(K, cam_pose, roi, uv_steps=[im_sz, im_sz])
         img, mask_occ = U._resize_targets(img, mask_occ, im_sz)
-        rgb_tgt = img.reshape(-1, 3).to(device)
-        occ_pixels = mask_occ.reshape(-1, 1).to(device)
+        rgb_tgt = img.reshape(-1, 3).to(device, non_blocking=True)
+        occ_pixels = mask_occ.reshape(-1, 1).to(device, non_blocking=True)
         if n_rays is not None:
             n_rays = np.minimum(rays_o.shape[0], n_rays)
             random_ray_ids = np.random.permutation(rays_o.shape[0])[:n_rays]
@@ -85,6 +123,15 @@ class NeRFRenderer(torch.nn.Module):
     def render_rays_specified(self, model, device, img, mask_occ, cam_pose, obj_sz, K, roi, x_vec, y_vec, shapecode,
                               texturecode, kitti2nusc=False):
         """renderer.py:169-201."""
+        if self._can_fuse(model, device, kitti2nusc, shapecode):
+            dev = torch.device(device)
+            px = torch.from_numpy(np.asarray(x_vec + roi[0].numpy())).t().reshape(-1).to(dev, torch.float32)
+            py = torch.from_numpy(np.asarray(y_vec + roi[1].numpy())).t().reshape(-1).to(dev, torch.float32)
+            rgb_tgt = img[y_vec, x_vec, :].to(device)
+            occ_pixels = mask_occ[y_vec, x_vec, :].to(device)
+            rgb_rays, depth_rays, acc_trans_rays = self._render_fused(model, device, px, py, K, cam_pose, obj_sz, shapecode,
+                                                                      texturecode)
+            return rgb_rays, depth_rays, acc_trans_rays, rgb_tgt, occ_pixels
         rays_o, viewdir = get_rays_specified(K, cam_pose, x_vec + roi[0].numpy(), y_vec + roi[1].numpy())
         rgb_tgt = img[y_vec, x_vec, :].to(device)
         occ_pixels = mask_occ[y_vec, x_vec, :].to(device)
@@ -165,8 +212,8 @@ def render_rays_v3(model, device, img, mask_occ, cam_pose, obj_wlh, K, roi, n_sa
     renderer = NeRFRenderer()
     rays_o, viewdir = get_rays(K, cam_pose, roi, uv_steps=[im_sz, im_sz])
     img, mask_occ = U._resize_targets(img, mask_occ, im_sz)
-    rgb_tgt = img.reshape(-1, 3).to(device)
-    occ_pixels = mask_occ.reshape(-1, 1).to(device)
+    rgb_tgt = img.reshape(-1, 3).to(device, non_blocking=True)
+    occ_pixels = mask_occ.reshape(-1, 1).to(device, non_blocking=True)
     if n_rays is not None:
         n_rays = np.minimum(rays_o.shape[0], n_rays)
         random_ray_ids = np.random.permutation(rays_o.shape[0])[:n_rays]

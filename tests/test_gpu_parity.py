@@ -372,3 +372,98 @@ def test_render_full_size_c1_properties():
     diag = float(np.linalg.norm(obj["wlh"]).astype(np.float32))
     assert torch.allclose(dep.cpu()[miss], torch.full((int(miss.sum()),), diag / 2), rtol=1e-6)
     assert torch.all(acc.cpu()[miss] == 1.0)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("n_rays", [None, 512])
+def test_fused_render_equals_staged_ops(prec, n_rays):
+    """renderer.render_rays through the fused C-ABI entry points (snb_render_fwd/bwd: one autograd node) must give the
+    same bits as the staged path (one autograd node per stage): same kernels, same order."""
+    S = snb()
+    obj = oracle.synthetic_object(31, im_sz=32)
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=31)
+    m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
+    m.precision = prec
+    if prec == "bf16":
+        m.requires_grad_(False)
+    shp0, tex0 = oracle.synthetic_latents(31, 1)
+    n = n_rays or 1024
+    jit = torch.rand(n, 64, generator=torch.Generator().manual_seed(31))
+    R = S.renderer.NeRFRenderer(n_samples=64)
+    out = {}
+    for fused in (True, False):
+        S.renderer.FUSED_RENDER = fused
+        try:
+            cam = obj["cam_pose"].to(DEV).requires_grad_()
+            shp, tex = shp0.to(DEV).requires_grad_(), tex0.to(DEV).requires_grad_()
+            m.zero_grad()
+            np.random.seed(5)
+            with forced_rand_like(jit):
+                rgb, dep, acc, tgt, occ = R.render_rays(m, DEV, obj["img"], obj["mask_occ"], cam, obj["wlh"], obj["K"].to(DEV),
+                                                        obj["roi"], shp, tex, im_sz=32, n_rays=n_rays)
+            oracle.refine_losses(rgb, acc, tgt, occ)[0].backward()
+            out[fused] = [rgb, dep, acc, tgt, occ, cam.grad, shp.grad, tex.grad]
+            if prec == "fp32":
+                out[fused] += [p.grad.clone() for p in m.parameters()]
+        finally:
+            S.renderer.FUSED_RENDER = True
+    for a, b in zip(out[True][:5], out[False][:5]):
+        assert torch.equal(a, b)
+    for a, b in zip(out[True][5:], out[False][5:]):   # gradients: atomics in the pose / weight reductions reorder the sums
+        assert rel_err(a, b) < 1e-5
+
+
+def test_fused_render_specified_equals_staged():
+    S = snb()
+    obj = oracle.synthetic_object(33, im_sz=48)
+    sd = oracle.init_codenerf_state(seed=33)
+    m = model_from_state(S.CodeNeRF, sd)
+    shp0, tex0 = oracle.synthetic_latents(33, 1)
+    rng = np.random.RandomState(3)
+    x_vec, y_vec = rng.randint(0, 48, size=100), rng.randint(0, 48, size=100)
+    jit = torch.rand(100, 64, generator=torch.Generator().manual_seed(33))
+    R = S.renderer.NeRFRenderer(n_samples=64)
+    roi = obj["roi"].clone()
+    roi[2:] = roi[:2] + 48
+    out = {}
+    for fused in (True, False):
+        S.renderer.FUSED_RENDER = fused
+        try:
+            cam = obj["cam_pose"].to(DEV).requires_grad_()
+            with forced_rand_like(jit):
+                r = R.render_rays_specified(m, DEV, obj["img"], obj["mask_occ"], cam, obj["wlh"], obj["K"].to(DEV), roi, x_vec, y_vec,
+                                            shp0.to(DEV), tex0.to(DEV))
+            (r[0].sum() + r[1].sum() + r[2].sum()).backward()
+            out[fused] = list(r) + [cam.grad]
+        finally:
+            S.renderer.FUSED_RENDER = True
+    for a, b in zip(out[True][:5], out[False][:5]):
+        assert torch.equal(a, b)
+    assert rel_err(out[True][5], out[False][5]) < 1e-5
+
+
+@pytest.mark.parametrize("n", [1, 257, 16384])
+def test_refine_loss_kernel_vs_oracle(n):
+    """losses.refine_loss (csrc/loss.cu) against the reference's inline loss (optimizer_nuscenes.py:729-736, restated in
+    oracle.refine_losses): values and gradients, incl. a caller-supplied denominator."""
+    S = snb()
+    g = torch.Generator().manual_seed(n)
+    rgb, tgt = torch.rand(n, 3, generator=g), torch.rand(n, 3, generator=g)
+    acc = torch.rand(n, generator=g)
+    occ = torch.randint(-1, 2, (n, 1), generator=g).float()
+    if n == 1:
+        occ[:] = 1.0
+    r64, a64 = rgb.double().requires_grad_(), acc.double().requires_grad_()
+    l64 = oracle.refine_losses(r64, a64, tgt.double(), occ.double())
+    l64[0].backward()
+    r, a = rgb.to(DEV).requires_grad_(), acc.to(DEV).requires_grad_()
+    loss, l_rgb, l_occ = S.losses.refine_loss(r, a, tgt.to(DEV), occ.to(DEV), 0.1)
+    (3.0 * loss).backward()
+    assert rel_err(loss, l64[0]) < TOL and rel_err(l_rgb, l64[1]) < TOL and rel_err(l_occ, l64[2]) < TOL
+    assert rel_err(r.grad, 3.0 * r64.grad) < TOL and rel_err(a.grad, 3.0 * a64.grad) < TOL
+    # caller-supplied (global) denominator: the ray-sharded partial loss
+    den = torch.tensor([2.0 * occ.abs().sum().item() + 1e-9], device=DEV)
+    half = S.losses.refine_loss(rgb.to(DEV), acc.to(DEV), tgt.to(DEV), occ.to(DEV), 0.1, den=den)[0]
+    assert rel_err(half, 0.5 * l64[0]) < TOL
+    with pytest.raises(S._lib.SnbError):
+        S.losses.refine_loss(rgb, acc, tgt, occ)   # CPU tensors: no fallback

@@ -1,0 +1,108 @@
+"""Host-side logic of the multi-GPU modes (supnerf_b200/parallel.py), on CPU with the gloo backend and world_size 2:
+shard arithmetic, the global-denominator partial loss, the single flat all_reduce of pose/latent gradients, and the
+ray all_gather.  The CPU oracle stands in for the CUDA render (the kernels cannot run here); the N>1 GPU path itself is
+exercised by tests/test_gpu_multi.py and bench.py --gpus N on the B200 box."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT  # noqa: F401  (sys.path)
+from oracle import oracle
+from supnerf_b200 import parallel
+
+IM, S = 16, 16
+
+
+def test_ray_shards_tile_aligned_and_cover():
+    for n, s in ((262144, 128), (4096, 64), (1000, 64), (1024, 37), (6, 64), (0, 64)):
+        for world in (1, 2, 3, 4, 8):
+            spans = [parallel.ray_shard(n, s, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a0, b0), (a1, b1) in zip(spans, spans[1:]):
+                assert b0 == a1 and a0 <= b0
+            for a, b in spans[:-1]:
+                assert (a * s) % 128 == 0 and (b * s) % 128 == 0 or b == n
+    with pytest.raises(ValueError):
+        parallel.ray_shard(10, 64, 2, 2)
+
+
+def test_object_shards_partition():
+    for n in (0, 1, 16, 32, 33):
+        for world in (1, 2, 8):
+            got = sorted(sum((parallel.object_shard(n, r, world) for r in range(world)), []))
+            assert got == list(range(n))
+    assert parallel.object_shard(32, 3, 8) == [3, 11, 19, 27]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _full_reference():
+    obj = oracle.synthetic_object(5, im_sz=IM)
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=5)
+    shp, tex = oracle.synthetic_latents(5, 1)
+    jit = torch.rand(IM * IM, S, generator=torch.Generator().manual_seed(5))
+    return obj, sd, shp, tex, jit
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(1)
+        obj, sd, shp0, tex0, jit = _full_reference()
+        n = IM * IM
+        a, b = parallel.ray_shard(n, S, rank, world)
+        ids = torch.arange(a, b)
+        cam = obj["cam_pose"].clone().requires_grad_()
+        shp, tex = shp0.clone().requires_grad_(), tex0.clone().requires_grad_()
+        rgb, dep, acc, _ = oracle.render_rays_box(sd, obj["K"], cam, obj["wlh"], obj["roi"], IM, S, shp, tex, jit[ids], ray_ids=ids)
+        tgt_all, occ_all = obj["img"].reshape(-1, 3), obj["mask_occ"].reshape(-1, 1)
+        # partial loss over the GLOBAL denominator (what parallel.refine_loss_sharded evaluates with the CUDA loss kernel)
+        den = occ_all.abs().sum() + 1e-9
+        occ = occ_all[a:b]
+        part = ((rgb - tgt_all[a:b]) ** 2 * occ.abs()).sum() / den + 0.1 * (torch.exp(-occ * (0.5 - acc.unsqueeze(-1))) * occ.abs()).sum() / den
+        part.backward()
+        loss = parallel.allreduce_grads([cam, shp, tex], part)
+        full_rgb = parallel.gather_rays(rgb.detach(), n, S)
+        q.put((rank, float(loss), cam.grad.clone(), shp.grad.clone(), tex.grad.clone(), full_rgb))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ray_sharded_allreduce_matches_single_process():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process truth
+    obj, sd, shp0, tex0, jit = _full_reference()
+    cam = obj["cam_pose"].clone().requires_grad_()
+    shp, tex = shp0.clone().requires_grad_(), tex0.clone().requires_grad_()
+    rgb, dep, acc, _ = oracle.render_rays_box(sd, obj["K"], cam, obj["wlh"], obj["roi"], IM, S, shp, tex, jit)
+    loss = oracle.refine_losses(rgb, acc, obj["img"].reshape(-1, 3), obj["mask_occ"].reshape(-1, 1))[0]
+    loss.backward()
+
+    def rel(x, y):
+        return ((x - y).abs().max() / y.abs().max()).item()
+    for rank, l, g_cam, g_shp, g_tex, full_rgb in res:
+        assert abs(l - loss.item()) <= 1e-5 * abs(loss.item())
+        assert rel(g_cam, cam.grad) < 1e-4 and rel(g_shp, shp.grad) < 1e-4 and rel(g_tex, tex.grad) < 1e-4
+        assert rel(full_rgb, rgb.detach()) < 1e-6
+    # every rank ends with identical bits (so identical optimiser steps)
+    for t0, t1 in zip(res[0][2:5], res[1][2:5]):
+        assert torch.equal(t0, t1)
