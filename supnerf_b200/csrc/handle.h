@@ -43,10 +43,13 @@ int latent_forward(const snb_handle_s* h, int64_t B, const float* shape_latent, 
 // latent add folded through the layer, exact in fp32 (SURVEY 8(a')3).
 int latent_effective_bias(const snb_handle_s* h, int64_t B, const float* zlat, float* ebias, cudaStream_t st);
 // single-launch versions (latent.cu): forward of all slots (+ effective biases if ebias != NULL); backward to the latents only
+// eimg != NULL: also write every effective bias as a tcgen05 bias-stage row (32 B each, [(Bs+Bt)][B][W]; tc_ptx.cuh)
 int latent_forward_fused(const snb_handle_s* h, int64_t B, const float* shape_latent, const float* texture_latent, float* zlat,
-                         float* ebias, cudaStream_t st);
+                         float* ebias, cudaStream_t st, uint8_t* eimg = nullptr);
+// fold_tmp != NULL: dz holds the column sums of the consuming layers' pre-activation gradients (two-tile tcgen05 backward);
+// they are first folded through W_layer^T into fold_tmp (same size as dz).
 int latent_backward_fused(const snb_handle_s* h, int64_t B, const float* zlat, const float* dz, float* g_shape_latent,
-                          float* g_texture_latent, cudaStream_t st);
+                          float* g_texture_latent, cudaStream_t st, float* fold_tmp = nullptr);
 // dz holds d loss / d zlat (post-ReLU outputs) and is overwritten by the pre-activation gradient.
 int latent_backward(const snb_handle_s* h, int64_t B, const float* shape_latent, const float* texture_latent,
                     const float* zlat, float* dz, float* g_shape_latent, float* g_texture_latent, float* const* g_weights,

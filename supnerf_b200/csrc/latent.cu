@@ -5,6 +5,7 @@
 // the backward (ReLU mask, then d latent = sum_slots W_lat^T d_pre).
 #include "common.cuh"
 #include "handle.h"
+#include "tc_ptx.cuh"
 
 namespace snb {
 
@@ -23,7 +24,8 @@ template <int PHASE>
 __global__ void __launch_bounds__(256) latent_fwd_kernel(const __grid_constant__ LatentLayers L, int64_t B,
                                                         const float* __restrict__ shape_latent,
                                                         const float* __restrict__ texture_latent,
-                                                        float* __restrict__ zlat, float* __restrict__ ebias) {
+                                                        float* __restrict__ zlat, float* __restrict__ ebias,
+                                                        uint8_t* __restrict__ eimg) {
   const int slot = blockIdx.x;
   const int64_t b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -46,7 +48,11 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const __grid_constant__
   acc = warp_sum(acc);
   if (lane == 0) {
     if (PHASE == 0) zlat[((size_t)slot * B + b) * L.W + o] = fmaxf(acc + __ldg(L.bl[slot] + o), 0.f);
-    else ebias[((size_t)slot * B + b) * L.W + o] = acc + __ldg(L.bc[slot] + o);
+    else {
+      const float eb = acc + __ldg(L.bc[slot] + o);
+      ebias[((size_t)slot * B + b) * L.W + o] = eb;
+      if (eimg != nullptr) tc::bias_stage_row(eimg + (((size_t)slot * B + b) * L.W + o) * 32, eb);   // tcgen05 bias-stage image
+    }
   }
 }
 
@@ -94,6 +100,43 @@ __global__ void __launch_bounds__(1024) latent_bwd_kernel(const __grid_constant_
   }
 }
 
+// The two-tile tcgen05 backward hands over s[slot][b][o] = sum_samples d loss / d pre-activation of the CONSUMING layer
+// (column sums of its A operand).  Fold it through that layer once per object:  dz[slot][b][i] = sum_o Wc[o][i] s[o]
+// (= sum_samples d loss / d (x + z), what latent_bwd_kernel expects).  grid (slots, B, W/32), 32 warps split o.
+__global__ void __launch_bounds__(1024) latent_fold_kernel(const __grid_constant__ LatentLayers L, int64_t B,
+                                                          const float* __restrict__ s, float* __restrict__ dz) {
+  __shared__ float part[32][33];
+  const int slot = blockIdx.x;
+  const int64_t b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.z * 32 + lane;
+  const float* sv = s + ((size_t)slot * B + b) * L.W;
+  const float* w = L.wc[slot] + i;
+  float acc = 0.f;
+  if (i < L.W) {
+    for (int o0 = warp; o0 < L.W; o0 += 32 * 8) {
+      float wv[8], gv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int o = o0 + 32 * u;
+        const bool ok = o < L.W;
+        wv[u] = ok ? __ldg(w + (size_t)o * L.W) : 0.f;
+        gv[u] = ok ? sv[o] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc = fmaf(gv[u], wv[u], acc);
+    }
+  }
+  part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && i < L.W) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v += part[k][lane];
+    dz[((size_t)slot * B + b) * L.W + i] = v;
+  }
+}
+
 static int fill_layers(const snb_handle_s* h, LatentLayers& L) {
   L.n_shape = h->arch.shape_blocks;
   L.n_total = h->arch.shape_blocks + h->arch.texture_blocks;
@@ -109,24 +152,30 @@ static int fill_layers(const snb_handle_s* h, LatentLayers& L) {
 }
 
 int latent_forward_fused(const snb_handle_s* h, int64_t B, const float* shape_latent, const float* texture_latent,
-                         float* zlat, float* ebias, cudaStream_t st) {
+                         float* zlat, float* ebias, cudaStream_t st, uint8_t* eimg) {
   LatentLayers L;
   if (fill_layers(h, L)) return 2;
   SNB_REQUIRE(L.D % 4 == 0 && L.W % 4 == 0, "latent layers: latent_dim and W must be multiples of 4");
   dim3 grid(L.n_total, (unsigned)B, (unsigned)((L.W + 7) / 8));
-  latent_fwd_kernel<0><<<grid, 256, 0, st>>>(L, B, shape_latent, texture_latent, zlat, ebias);
+  latent_fwd_kernel<0><<<grid, 256, 0, st>>>(L, B, shape_latent, texture_latent, zlat, ebias, nullptr);
   SNB_LAUNCH_CHECK();
   if (ebias != nullptr) {
-    latent_fwd_kernel<1><<<grid, 256, 0, st>>>(L, B, shape_latent, texture_latent, zlat, ebias);
+    latent_fwd_kernel<1><<<grid, 256, 0, st>>>(L, B, shape_latent, texture_latent, zlat, ebias, eimg);
     SNB_LAUNCH_CHECK();
   }
   return 0;
 }
 
 int latent_backward_fused(const snb_handle_s* h, int64_t B, const float* zlat, const float* dz, float* g_shape_latent,
-                          float* g_texture_latent, cudaStream_t st) {
+                          float* g_texture_latent, cudaStream_t st, float* fold_tmp) {
   LatentLayers L;
   if (fill_layers(h, L)) return 2;
+  if (fold_tmp != nullptr) {   // dz holds pre-activation column sums of the consuming layers: fold through W^T first
+    dim3 gridf(L.n_total, (unsigned)B, (unsigned)((L.W + 31) / 32));
+    latent_fold_kernel<<<gridf, 1024, 0, st>>>(L, B, dz, fold_tmp);
+    SNB_LAUNCH_CHECK();
+    dz = fold_tmp;
+  }
   dim3 grid(2, (unsigned)B, (unsigned)((L.D + 31) / 32));
   latent_bwd_kernel<<<grid, 1024, 0, st>>>(L, B, zlat, dz, g_shape_latent, g_texture_latent);
   SNB_LAUNCH_CHECK();

@@ -731,7 +731,7 @@ bool tc2_supported(const snb_handle_s* h);
 size_t tc2_packed_bytes(const snb_handle_s* h);
 int tc2_pack_weights(const snb_handle_s* h, void* packed, cudaStream_t st);
 int tc2_launch_fwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
-                   const float* ebias, uint32_t* masks, float* sigma, float* rgb, float* dbg, cudaStream_t st);
+                   const uint8_t* eimg, uint32_t* masks, float* sigma, float* rgb, float* dbg, cudaStream_t st);
 int tc2_launch_bwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                    const uint32_t* masks, const float* sigma, const float* g_sigma, const float* g_rgb, float* g_xyz,
                    float* g_viewdir, float* g_zlat, cudaStream_t st);
@@ -771,13 +771,14 @@ static inline int64_t tiles_of(int64_t M) { return (M + kTileM - 1) / kTileM; }
 static size_t ws_zlat_bytes(const snb_handle_s* h, int64_t B) {
   return (size_t)(h->arch.shape_blocks + h->arch.texture_blocks) * B * 256 * sizeof(float);
 }
-// workspace: [zlat][effective biases][masks]
-static size_t ws_masks_off(const snb_handle_s* h, int64_t B) { return (2 * ws_zlat_bytes(h, B) + 255) & ~size_t(255); }
+// workspace: [zlat][effective biases fp32][effective-bias stage images, 32 B per unit][masks]
+static size_t ws_eimg_off(const snb_handle_s* h, int64_t B) { return (2 * ws_zlat_bytes(h, B) + 255) & ~size_t(255); }
+static size_t ws_masks_off(const snb_handle_s* h, int64_t B) { return (ws_eimg_off(h, B) + 8 * ws_zlat_bytes(h, B) + 255) & ~size_t(255); }
 size_t tc_workspace_bytes(const snb_handle_s* h, int64_t M, int64_t B) {
   const int slots = h->arch.shape_blocks + h->arch.texture_blocks + 3;
   return ws_masks_off(h, B) + (size_t)tiles_of(M) * slots * 8 * 128 * 4 + 256;
 }
-size_t tc_bwd_scratch_bytes(const snb_handle_s* h, int64_t, int64_t B) { return ws_zlat_bytes(h, B) + 256; }
+size_t tc_bwd_scratch_bytes(const snb_handle_s* h, int64_t, int64_t B) { return 2 * ws_zlat_bytes(h, B) + 256; }   // column sums + their W^T fold
 
 static int tc_common_checks(const snb_handle_s* h, int64_t M, int64_t B, const char* who) {
   const char* why = "";
@@ -836,10 +837,11 @@ int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, in
   float* zlat = (float*)ws;
   float* ebias = (float*)((uint8_t*)ws + ws_zlat_bytes(h, B));
   uint32_t* masks = (uint32_t*)((uint8_t*)ws + ws_masks_off(h, B));
-  if (latent_forward_fused(h, B, shape_latent, texture_latent, zlat, ebias, st)) return 1;
+  uint8_t* eimg = (uint8_t*)ws + ws_eimg_off(h, B);
+  if (latent_forward_fused(h, B, shape_latent, texture_latent, zlat, ebias, st, use_v2(h) ? eimg : nullptr)) return 1;
   if (use_v2(h)) {
     ScopedKernelTimer tm2(st, g_timing_on);
-    if (tc2_launch_fwd(h, (const uint8_t*)h->packed + v1_packed_bytes(h), xyz, viewdir, M, B, ebias, masks, sigma, rgb,
+    if (tc2_launch_fwd(h, (const uint8_t*)h->packed + v1_packed_bytes(h), xyz, viewdir, M, B, eimg, masks, sigma, rgb,
                        g_tc_debug_acts, st)) return 1;
     tm2.stop(g_ev_fwd);
     SNB_LAUNCH_CHECK();
@@ -877,7 +879,8 @@ int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, i
                        g_viewdir, g_zlat, st)) return 1;
     tm2.stop(g_ev_bwd);
     SNB_LAUNCH_CHECK();
-    return latent_backward_fused(h, B, zlat, g_zlat, g_shape_latent, g_texture_latent, st);
+    return latent_backward_fused(h, B, zlat, g_zlat, g_shape_latent, g_texture_latent, st,
+                                 (float*)((uint8_t*)scratch + ws_zlat_bytes(h, B)));
   }
   TcPlan pl = build_plan(h);
   Params p;

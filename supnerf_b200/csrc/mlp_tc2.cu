@@ -26,6 +26,9 @@ namespace tc2 {
 using namespace tc;
 
 constexpr int kThreads = 576;
+constexpr int kCluster = 2;               // CTAs per cluster: every weight stage is fetched from L2 ONCE per cluster (each CTA loads
+                                          // 1/kCluster of it and multicasts it to all): L2 -> SM weight traffic / kCluster
+constexpr uint16_t kClusterMask = (uint16_t)((1u << kCluster) - 1u);
 constexpr int kRing = 5;
 constexpr uint32_t kStageBytes = 16384;   // [256 n][32 k] bf16
 constexpr int kMaxSteps = 12;
@@ -33,8 +36,9 @@ constexpr int kMaxLat = 4;                // shape_blocks + texture_blocks <= 4 
 
 constexpr uint32_t SM_RING = 8 * kChunkBytes;                    // A chunks [slot][4]
 constexpr uint32_t SM_TAB = SM_RING + kRing * kStageBytes;
-constexpr uint32_t TAB_BIAS = 0;                                 // fwd: [4][256] biases of encoding_xyz, encoding_shape, encoding_viewdir, rgb.0
-constexpr uint32_t TAB_LAT = TAB_BIAS + 4 * 1024;                // fwd: [slot][kMaxLat][256] effective biases; bwd: latent column sums
+constexpr uint32_t TAB_BIAS = 0;                                 // (unused since the biases ride on the tensor core; kept for layout stability)
+constexpr uint32_t TAB_LAT = TAB_BIAS + 4 * 1024;                // fwd: [128][16] bf16 all-ones A tile (4 KB); bwd: [slot][kMaxLat][256] latent column sums
+constexpr uint32_t kBiasStageRowBytes = 32;                       // bias stage: [N rows][16 k] bf16, 32-byte swizzle
 constexpr uint32_t TAB_WSIG = TAB_LAT + 2 * kMaxLat * 1024;      // [256]
 constexpr uint32_t TAB_W2 = TAB_WSIG + 1024;                     // [3][128]
 constexpr uint32_t TAB_BYTES = TAB_W2 + 1536;
@@ -50,6 +54,8 @@ struct Step {
   uint32_t w_off;            // byte offset of the step's first weight stage in the packed buffer
   uint16_t n_stages, n_out;  // K / 32, N
   int8_t epi, mask_slot, latent_slot, bias_row, dbg_idx, accumulate, produce_a, colsum;
+  int8_t bias_stage;         // 0 none; 1 static image right after the step's weight stages; 2 per-object image of latent_slot (fwd only)
+  uint8_t pad_[3];
 };
 
 struct Program {
@@ -61,8 +67,7 @@ struct Params {
   const float* xyz; const float* viewdir;
   int64_t M, rows_per_obj, B;
   const uint8_t* packed;
-  const float* zlat;            // fwd: per-object effective biases [(Bs+Bt)][B][256]
-  const float* bias4[4];        // fwd: static biases (X, ES, EV, R0)
+  const uint8_t* eimg;          // fwd: per-object effective-bias stage images [(Bs+Bt)][B][256 x 32 B] (latent.cu)
   const float* wsig; const float* bsig; const float* w2; const float* b2;
   uint32_t* masks;              // [tile][slot][8 words][128 rows]
   float* sigma; float* rgb; float* dbg;
@@ -81,6 +86,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
   d |= (uint64_t)(512u >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)4 << 61;
+  return d;
+}
+
+// K-major, 32-byte-swizzled tile of K = 16: rows 32 B apart, 8-row atoms 256 B apart (SBO).  Used for the bias stage (B) and
+// the all-ones A tile, both invariant under the swizzle's exchange of a row's two 16-byte units.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;
   return d;
 }
 
@@ -112,6 +128,15 @@ __device__ __forceinline__ void store_row32(uint8_t* chunk, uint32_t row, uint32
   }
 }
 
+// 16 columns (two 16-byte units, `unit0` and `unit0 + 1`) of one row
+__device__ __forceinline__ void store_row16(uint8_t* chunk, uint32_t row, uint32_t unit0, const uint32_t (&pk)[8]) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    uint4 q = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+    *reinterpret_cast<uint4*>(chunk + swz(row, unit0 + u)) = q;
+  }
+}
+
 __device__ __forceinline__ void group_bar(uint32_t slot) { asm volatile("bar.sync %0, 256;" ::"r"(slot + 1) : "memory"); }
 
 // this thread's smem writes (generic proxy) and TMEM reads are done: make them visible to the tensor core and tell the MMA warp
@@ -136,6 +161,26 @@ __device__ __forceinline__ void bulk_g2s_elect(uint32_t dst, const void* src, ui
       "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
       "}" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Weight stage shared by the cluster: this CTA expects the WHOLE stage on its own full barrier, fetches its 1/kCluster part and
+// multicasts it to the same smem offset (and the same barrier offset) of every CTA of the cluster.
+__device__ __forceinline__ void bulk_g2s_multicast_elect(uint32_t dst, const void* src, uint32_t part_bytes, uint32_t total_bytes,
+                                                         uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%4], %3;\n"
+      "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%4], %5;\n"
+      "}" ::"r"(dst), "l"(src), "r"(part_bytes), "r"(total_bytes), "r"(bar), "h"(cta_mask) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_elect(uint32_t bar) {
   asm volatile(
       "{\n"
@@ -158,8 +203,19 @@ __device__ __forceinline__ void umma_stage_elect(uint32_t d_tmem, uint64_t a_des
       "add.s64 b1, %2, 2;\n"
       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n"
-      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n"
-      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(empty_bar) : "memory");
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%5], %6;\n"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(empty_bar), "h"(kClusterMask) : "memory");
+}
+// one accumulating K=16 MMA (the bias stage: ones x [bias_hi, bias_mid, bias_lo, 0...]), then release the stage
+__device__ __forceinline__ void umma_bias_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t empty_bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e, t;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "setp.eq.b32 t, 0, 0;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, t;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%4], %5;\n"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(empty_bar), "h"(kClusterMask) : "memory");
 }
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
   asm volatile(
@@ -171,18 +227,32 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
 }
 
 __device__ __forceinline__ void producer_loop(const Params& p, const Smem& sm, int64_t n_pairs) {
-  uint32_t stage = 0, ph = 0, it = 0;
-  for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+  uint32_t stage = 0, ph = 0;
+  const int64_t n_tiles = (p.M + kTileM - 1) / kTileM;
+  const uint32_t crank = cluster_ctarank();
+  // every CTA of a cluster runs the same number of iterations (a CTA past the last pair still streams its share of the weights)
+  for (int64_t pair0 = (int64_t)blockIdx.x - crank; pair0 < n_pairs; pair0 += gridDim.x) {
+    const int64_t pair = pair0 + crank;
     for (int si = 0; si < p.prog.n_steps; ++si) {
       const Step& st = p.prog.s[si];
-      const uint32_t bytes = (uint32_t)st.n_out * 64u;
+      const uint32_t bytes = (uint32_t)st.n_out * 64u, part = bytes / kCluster;
       for (int slot = 0; slot < 2; ++slot) {
-        const uint8_t* src = p.packed + ((p.exp_flags & 4) ? 0 : st.w_off);
-        for (int j = 0; j < st.n_stages; ++j, ++it) {
+        const uint8_t* src = p.packed + st.w_off + crank * part;
+        for (int j = 0; j < st.n_stages; ++j) {
+          mbar_wait(sm.bar(BAR_WEMPTY + stage), ph ^ 1u);   // released by the MMA warps of ALL CTAs of the cluster
+          bulk_g2s_multicast_elect(sm.stage_u32(stage) + crank * part, src, part, bytes, sm.bar(BAR_WFULL + stage), kClusterMask);
+          src += bytes;
+          if (++stage == (uint32_t)kRing) { stage = 0; ph ^= 1u; }
+        }
+        if (st.bias_stage) {   // CTA-local (not multicast): static image after the weight stages, or this tile's object's image
+          const uint8_t* bsrc = p.packed + st.w_off + (uint32_t)st.n_stages * bytes;
+          if (st.bias_stage == 2) {
+            const int64_t tile = 2 * pair + slot;
+            const int64_t obj = (pair < n_pairs && tile < n_tiles) ? (tile * kTileM) / p.rows_per_obj : 0;
+            bsrc = p.eimg + ((size_t)st.latent_slot * p.B + obj) * (256u * kBiasStageRowBytes);
+          }
           mbar_wait(sm.bar(BAR_WEMPTY + stage), ph ^ 1u);
-          if ((p.exp_flags & 1) && it >= (uint32_t)kRing) mbar_arrive_elect(sm.bar(BAR_WFULL + stage));
-          else bulk_g2s_elect(sm.stage_u32(stage), src, bytes, sm.bar(BAR_WFULL + stage));
-          if (!(p.exp_flags & 4)) src += bytes;
+          bulk_g2s_elect(sm.stage_u32(stage), bsrc, (uint32_t)st.n_out * kBiasStageRowBytes, sm.bar(BAR_WFULL + stage));
           if (++stage == (uint32_t)kRing) { stage = 0; ph ^= 1u; }
         }
       }
@@ -192,9 +262,10 @@ __device__ __forceinline__ void producer_loop(const Params& p, const Smem& sm, i
 
 __device__ __forceinline__ void mma_loop(const Params& p, const Smem& sm, int64_t n_pairs, uint32_t tmem_base) {
   uint32_t stage = 0, ph = 0, ready_ph = 0;
+  const uint64_t ones_desc = umma_desc_sw32(sm.base_u32 + SM_TAB + TAB_LAT);
   const bool trace = p.trace != nullptr && blockIdx.x == 0;
   int64_t tr = 0;
-  for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+  for (int64_t pair0 = (int64_t)blockIdx.x - cluster_ctarank(); pair0 < n_pairs; pair0 += gridDim.x) {
     for (int si = 0; si < p.prog.n_steps; ++si) {
       const Step& st = p.prog.s[si];
       const uint32_t idesc = umma_idesc(128, st.n_out);
@@ -216,6 +287,12 @@ __device__ __forceinline__ void mma_loop(const Params& p, const Smem& sm, int64_
           a_desc += (j & 1) ? (uint64_t)((kChunkBytes - 64u) >> 4) : (uint64_t)(64u >> 4);   // next 32-k half of the chunk / next chunk
           if (++stage == (uint32_t)kRing) { stage = 0; ph ^= 1u; }
         }
+        if (st.bias_stage) {
+          mbar_wait(sm.bar(BAR_WFULL + stage), ph);
+          tc_fence_after();
+          umma_bias_elect(d_tmem, ones_desc, umma_desc_sw32(sm.stage_u32(stage)), idesc, sm.bar(BAR_WEMPTY + stage));
+          if (++stage == (uint32_t)kRing) { stage = 0; ph ^= 1u; }
+        }
         umma_commit_elect(sm.bar(BAR_ACC + slot));
         if (trace) p.trace[tr + 1] = clock64();
       }
@@ -226,13 +303,14 @@ __device__ __forceinline__ void mma_loop(const Params& p, const Smem& sm, int64_
 __device__ __forceinline__ void kernel_prologue(Smem& sm, uint32_t tid, uint32_t warp, uint32_t& tmem_base) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.base + SM_BARS + 128);
   if (tid == 0) {
-    for (int i = 0; i < kRing; ++i) { mbar_init(sm.bar(BAR_WFULL + i), 1); mbar_init(sm.bar(BAR_WEMPTY + i), 1); }
+    for (int i = 0; i < kRing; ++i) { mbar_init(sm.bar(BAR_WFULL + i), 1); mbar_init(sm.bar(BAR_WEMPTY + i), kCluster); }
     for (int i = 0; i < 2; ++i) { mbar_init(sm.bar(BAR_READY + i), 8); mbar_init(sm.bar(BAR_ACC + i), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 16) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();   // every CTA's barriers are initialised before a peer multicasts data / arrivals into them
   tc_fence_after();
   tmem_base = *tmem_slot;
 }
@@ -245,62 +323,74 @@ __device__ __forceinline__ void smem_base(Smem& sm, uint8_t* smem_raw) {
 }
 
 // ------------------------------------------------------------------------------------------ forward epilogue
-// One layer's epilogue for this thread's row: TMEM -> (+bias, ReLU, mask bits) -> bf16 -> the slot's A chunks.
+// 16 accumulator columns of this thread's row: (+bias, sign bits, heads) -> bf16 -> two 16-byte units of the slot's A chunk.
+// Returns the 16 SIGN bits (1 = negative pre-activation), element i at bit (15 - i).
 template <int EPI, bool DBG>
-__device__ __forceinline__ void fwd_epilogue(const Params& p, const Smem& sm, const Step& st, const EpiCtx& e, const float* bias_s,
-                                             uint32_t* mask_tile, bool tile_ok, float& sig_acc, float (&rgb_acc)[3]) {
-  constexpr int NC = (EPI == F_RGB) ? 2 : 4;
+__device__ __forceinline__ uint32_t fwd_half(const Params& p, const Smem& sm, const Step& st, const EpiCtx& e,
+                                             const uint32_t (&r)[16], int c, int h, float& sig_acc, float (&rgb_acc)[3]) {
   const float* wsig_s = sm.tab(TAB_WSIG);
   const float* w2_s = sm.tab(TAB_W2);
+  const int col0 = c * 64 + (int)e.hh * 32 + h * 16;
+  uint32_t pk[8], mm[2] = {0u, 0u};   // two independent 8-element funnel-shift chains
+#pragma unroll
+  for (int i4 = 0; i4 < 4; ++i4) {
+    float v[4] = {__uint_as_float(r[4 * i4]), __uint_as_float(r[4 * i4 + 1]), __uint_as_float(r[4 * i4 + 2]),
+                  __uint_as_float(r[4 * i4 + 3])};   // the bias is already in the accumulator (bias stage)
+    if (EPI != F_SIGMA) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) mm[i4 >> 1] = __funnelshift_l(__float_as_uint(v[u]), mm[i4 >> 1], 1);
+    }
+    if (EPI == F_SIGMA) {
+      const float4 ws = *reinterpret_cast<const float4*>(wsig_s + col0 + 4 * i4);
+      sig_acc += v[0] * ws.x + v[1] * ws.y + v[2] * ws.z + v[3] * ws.w;
+    }
+    if (EPI == F_RGB) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float4 ww = *reinterpret_cast<const float4*>(w2_s + k * 128 + col0 + 4 * i4);
+        rgb_acc[k] += fmaxf(v[0], 0.f) * ww.x + fmaxf(v[1], 0.f) * ww.y + fmaxf(v[2], 0.f) * ww.z + fmaxf(v[3], 0.f) * ww.w;
+      }
+    }
+    if (DBG) {
+      if (e.valid && st.dbg_idx >= 0) {
+        float* d = p.dbg + ((size_t)st.dbg_idx * p.M + e.grow) * 256 + col0 + 4 * i4;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) d[u] = (EPI == F_SIGMA) ? v[u] : fmaxf(v[u], 0.f);
+      }
+    }
+    if (EPI == F_SIGMA) {
+      pk[2 * i4] = pack_bf16(v[0], v[1]);
+      pk[2 * i4 + 1] = pack_bf16(v[2], v[3]);
+    } else if (EPI == F_RELU) {
+      pk[2 * i4] = pack_bf16_relu(v[0], v[1]);
+      pk[2 * i4 + 1] = pack_bf16_relu(v[2], v[3]);
+    }
+  }
+  if (EPI != F_RGB) store_row16(sm.chunk(e.slot, c), e.row, e.hh * 4u + (uint32_t)h * 2u, pk);
+  return ((mm[0] & 0xffu) << 8) | (mm[1] & 0xffu);
+}
+
+// One layer's epilogue for this thread's row: TMEM -> (+bias, ReLU, mask bits) -> bf16 -> the slot's A chunks.  The
+// accumulator is read in 16-column pieces into two register sets: while one set is consumed the other one's tcgen05.ld is
+// in flight (tcgen05.wait::ld waits for every outstanding load, so exactly one is kept outstanding across each compute).
+template <int EPI, bool DBG>
+__device__ __forceinline__ void fwd_epilogue(const Params& p, const Smem& sm, const Step& st, const EpiCtx& e,
+                                             uint32_t* mask_tile, bool tile_ok, float& sig_acc, float (&rgb_acc)[3]) {
+  constexpr int NC = (EPI == F_RGB) ? 2 : 4;
   const uint32_t t0 = e.tmem + e.hh * 32u + e.lane_field;
-  uint32_t r[32];
-  tmem_ld32_issue(t0, r);
+  uint32_t ra[16], rb[16];
+  tmem_ld16_issue(t0, ra);
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     tmem_ld_wait();
-    const int col0 = c * 64 + (int)e.hh * 32;
-    uint32_t pk[16], mm[4] = {0u, 0u, 0u, 0u};   // mm: SIGN bits (1 = negative pre-activation), four independent 8-element chains
-#pragma unroll
-    for (int i4 = 0; i4 < 8; ++i4) {
-      const float4 bb = *reinterpret_cast<const float4*>(bias_s + col0 + 4 * i4);
-      float v[4] = {__uint_as_float(r[4 * i4]) + bb.x, __uint_as_float(r[4 * i4 + 1]) + bb.y,
-                    __uint_as_float(r[4 * i4 + 2]) + bb.z, __uint_as_float(r[4 * i4 + 3]) + bb.w};
-      if (EPI != F_SIGMA) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) mm[i4 >> 1] = __funnelshift_l(__float_as_uint(v[u]), mm[i4 >> 1], 1);
-      }
-      if (EPI == F_SIGMA) {
-        const float4 ws = *reinterpret_cast<const float4*>(wsig_s + col0 + 4 * i4);
-        sig_acc += v[0] * ws.x + v[1] * ws.y + v[2] * ws.z + v[3] * ws.w;
-      }
-      if (EPI == F_RGB) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const float4 ww = *reinterpret_cast<const float4*>(w2_s + k * 128 + col0 + 4 * i4);
-          rgb_acc[k] += fmaxf(v[0], 0.f) * ww.x + fmaxf(v[1], 0.f) * ww.y + fmaxf(v[2], 0.f) * ww.z + fmaxf(v[3], 0.f) * ww.w;
-        }
-      }
-      if (DBG) {
-        if (e.valid && st.dbg_idx >= 0) {
-          float* d = p.dbg + ((size_t)st.dbg_idx * p.M + e.grow) * 256 + col0 + 4 * i4;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) d[u] = (EPI == F_SIGMA) ? v[u] : fmaxf(v[u], 0.f);
-        }
-      }
-      if (EPI == F_SIGMA) {
-        pk[2 * i4] = pack_bf16(v[0], v[1]);
-        pk[2 * i4 + 1] = pack_bf16(v[2], v[3]);
-      } else if (EPI == F_RELU) {
-        pk[2 * i4] = pack_bf16_relu(v[0], v[1]);
-        pk[2 * i4 + 1] = pack_bf16_relu(v[2], v[3]);
-      }
-    }
-    if (c + 1 < NC) tmem_ld32_issue(t0 + (uint32_t)(c + 1) * 64u, r);   // r is dead: the next chunk loads while this one is stored
+    tmem_ld16_issue(t0 + (uint32_t)c * 64u + 16u, rb);
+    const uint32_t s_lo = fwd_half<EPI, DBG>(p, sm, st, e, ra, c, 0, sig_acc, rgb_acc);
+    tmem_ld_wait();
+    if (c + 1 < NC) tmem_ld16_issue(t0 + (uint32_t)(c + 1) * 64u, ra);
+    const uint32_t s_hi = fwd_half<EPI, DBG>(p, sm, st, e, rb, c, 1, sig_acc, rgb_acc);
     if (EPI != F_SIGMA) {
-      const uint32_t nmask = (mm[0] << 24) | (mm[1] << 16) | (mm[2] << 8) | mm[3];
-      if (tile_ok) mask_tile[((size_t)st.mask_slot * 8 + c * 2 + e.hh) * 128 + e.row] = ~nmask;
+      if (tile_ok) mask_tile[((size_t)st.mask_slot * 8 + c * 2 + e.hh) * 128 + e.row] = ~((s_lo << 16) | s_hi);
     }
-    if (EPI != F_RGB) store_row32(sm.chunk(e.slot, c), e.row, e.hh, pk);
   }
 }
 
@@ -312,11 +402,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_const
   smem_base(sm, smem_raw);
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   {  // static tables
-    float* bias_s = sm.tab(TAB_BIAS);
-    for (int i = tid; i < 4 * 256; i += kThreads) {
-      const int r = i >> 8, c = i & 255;
-      bias_s[i] = (r < 3 || c < 128) ? __ldg(p.bias4[r] + c) : 0.f;
-    }
+    uint32_t* ones = reinterpret_cast<uint32_t*>(sm.tab(TAB_LAT));   // [128][16] bf16 1.0: the A operand of every bias stage
+    for (int i = tid; i < 1024; i += kThreads) ones[i] = 0x3F803F80u;
+    fence_async_smem();
     float* wsig_s = sm.tab(TAB_WSIG);
     for (int i = tid; i < 256; i += kThreads) wsig_s[i] = __ldg(p.wsig + i);
     float* w2_s = sm.tab(TAB_W2);
@@ -336,27 +424,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_const
     EpiCtx e;
     e.lane = lane; e.hh = gw >> 2; e.row = (gw & 3u) * 32u + lane; e.lane_field = ((gw & 3u) * 32u) << 16;
     e.tmem = tmem_base + slot * 256u; e.slot = slot;
-    float* lat_s = sm.tab(TAB_LAT) + slot * kMaxLat * 256;
     float* sig_part = reinterpret_cast<float*>(sm.chunk(slot, 3));   // tile-end scratch: [2][128] + [2][128][3]
     float* rgb_part = sig_part + 256;
     const int nslots = p.prog.n_mask_slots;
     uint32_t acc_cnt = 0;
-    int64_t cur_obj = -1;
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    const uint32_t crank = cluster_ctarank();
+    for (int64_t pair0 = (int64_t)blockIdx.x - crank; pair0 < n_pairs; pair0 += gridDim.x) {
+      const int64_t pair = pair0 + crank;
       const int64_t tile = 2 * pair + slot;
-      const bool tile_ok = tile < n_tiles;
+      const bool tile_ok = pair < n_pairs && tile < n_tiles;
       e.grow = tile * kTileM + e.row;
       e.valid = tile_ok && e.grow < p.M;
       const int64_t crow = e.valid ? e.grow : p.M - 1;
       const float x[3] = {__ldg(p.xyz + 3 * crow), __ldg(p.xyz + 3 * crow + 1), __ldg(p.xyz + 3 * crow + 2)};
       const float dir[3] = {__ldg(p.viewdir + 3 * crow), __ldg(p.viewdir + 3 * crow + 1), __ldg(p.viewdir + 3 * crow + 2)};
-      const int64_t obj = tile_ok ? (tile * kTileM) / p.rows_per_obj : (cur_obj < 0 ? 0 : cur_obj);   // tiles never straddle objects
-      if (obj != cur_obj) {   // (re)load this slot's per-object effective biases; the group is between tiles here
-        cur_obj = obj;
-        for (int i = gtid; i < p.n_latent * 256; i += 256)
-          lat_s[i] = __ldg(p.zlat + ((size_t)(i >> 8) * p.B + obj) * 256 + (i & 255));
-        group_bar(slot);
-      }
       write_pe_row<10>(sm.chunk(slot, 0), e.row, e.hh, x);
       publish(sm, slot, lane);
       uint32_t* mask_tile = p.masks + (size_t)(tile_ok ? tile : 0) * nslots * 8 * 128;
@@ -367,11 +448,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_const
         acc_cnt++;
         tc_fence_after();
         if (p.trace && blockIdx.x == 0 && gtid == 0) p.trace[(((pair / gridDim.x) * p.prog.n_steps + si) * 2 + slot) * 4 + 2] = clock64();
-        const float* bias_s = st.latent_slot >= 0 ? lat_s + st.latent_slot * 256 : sm.tab(TAB_BIAS) + st.bias_row * 256;
-        if (st.epi == F_RELU) fwd_epilogue<F_RELU, DBG>(p, sm, st, e, bias_s, mask_tile, tile_ok, sig_acc, rgb_acc);
-        else if (st.epi == F_SIGMA) fwd_epilogue<F_SIGMA, DBG>(p, sm, st, e, bias_s, mask_tile, tile_ok, sig_acc, rgb_acc);
+        if (st.epi == F_RELU) fwd_epilogue<F_RELU, DBG>(p, sm, st, e, mask_tile, tile_ok, sig_acc, rgb_acc);
+        else if (st.epi == F_SIGMA) fwd_epilogue<F_SIGMA, DBG>(p, sm, st, e, mask_tile, tile_ok, sig_acc, rgb_acc);
         else if (st.epi == F_PEV) write_pe_row<4>(sm.chunk(slot, 0), e.row, e.hh, dir);   // accumulator untouched: the next step adds to it
-        else fwd_epilogue<F_RGB, DBG>(p, sm, st, e, bias_s, mask_tile, tile_ok, sig_acc, rgb_acc);
+        else fwd_epilogue<F_RGB, DBG>(p, sm, st, e, mask_tile, tile_ok, sig_acc, rgb_acc);
         if (si + 1 < p.prog.n_steps) publish(sm, slot, lane);
         else tc_fence_before();
         if (p.trace && blockIdx.x == 0 && gtid == 0) p.trace[(((pair / gridDim.x) * p.prog.n_steps + si) * 2 + slot) * 4 + 3] = clock64();
@@ -393,49 +473,87 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();   // no CTA leaves while a peer can still multicast into its shared memory / barriers
   if (warp == 16) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------ backward epilogue
-// acc = gradient w.r.t. the layer's input.  Optional: per-object column sums of it (latent gradient); then mask by the
-// producing layer's ReLU bits and hand on as the next A operand.  EV: add the sigma-head gradient first, no mask.
-template <bool EV, bool COLSUM, bool MASK, bool PRODUCE>
-__device__ __forceinline__ void bwd_epilogue(const Smem& sm, const Step& st, const EpiCtx& e, const uint32_t (&mw)[4], float gsp,
-                                             float* colsum) {
+// acc = gradient w.r.t. the layer's input; mask it by the producing layer's ReLU bits and hand it on as the next A operand.
+// EV: add the sigma-head gradient first, no mask.  16-column pieces, two register sets (see fwd_epilogue).
+template <bool EV, bool MASK>
+__device__ __forceinline__ void bwd_half(const Smem& sm, const EpiCtx& e, const uint32_t (&r)[16], int c, int h, uint32_t mw, float gsp) {
   const float* wsig_s = sm.tab(TAB_WSIG);
+  const int col0 = c * 64 + (int)e.hh * 32 + h * 16;
+  uint32_t pk[8];
+#pragma unroll
+  for (int i4 = 0; i4 < 4; ++i4) {
+    float v[4] = {__uint_as_float(r[4 * i4]), __uint_as_float(r[4 * i4 + 1]), __uint_as_float(r[4 * i4 + 2]), __uint_as_float(r[4 * i4 + 3])};
+    if (EV) {
+      const float4 ws = *reinterpret_cast<const float4*>(wsig_s + col0 + 4 * i4);
+      v[0] += gsp * ws.x; v[1] += gsp * ws.y; v[2] += gsp * ws.z; v[3] += gsp * ws.w;
+    }
+    if (MASK) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (!mask_bit(mw, h * 16 + 4 * i4 + u)) v[u] = 0.f;
+    }
+    pk[2 * i4] = pack_bf16(v[0], v[1]);
+    pk[2 * i4 + 1] = pack_bf16(v[2], v[3]);
+  }
+  store_row16(sm.chunk(e.slot, c), e.row, e.hh * 4u + (uint32_t)h * 2u, pk);
+}
+
+template <bool EV, bool MASK>
+__device__ __forceinline__ void bwd_epilogue(const Smem& sm, const EpiCtx& e, const uint32_t (&mw)[4], float gsp) {
   const uint32_t t0 = e.tmem + e.hh * 32u + e.lane_field;
-  uint32_t r[32];
-  tmem_ld32_issue(t0, r);
+  uint32_t ra[16], rb[16];
+  tmem_ld16_issue(t0, ra);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     tmem_ld_wait();
-    const int col0 = c * 64 + (int)e.hh * 32;
-    float v[32];
+    tmem_ld16_issue(t0 + (uint32_t)c * 64u + 16u, rb);
+    bwd_half<EV, MASK>(sm, e, ra, c, 0, mw[c], gsp);
+    tmem_ld_wait();
+    if (c + 1 < 4) tmem_ld16_issue(t0 + (uint32_t)(c + 1) * 64u, ra);
+    bwd_half<EV, MASK>(sm, e, rb, c, 1, mw[c], gsp);
+  }
+}
+
+// Column sums over the 128 rows of the slot's A operand (4 chunks x 64 bf16 columns, 128-byte swizzled), run by the slot's
+// epilogue warps WHILE the step's MMAs execute (the warps would otherwise spin on the accumulator barrier), so the latent
+// gradient reduction is off the MMA -> epilogue -> MMA critical path.  Warp gw owns the 32 columns [32 gw, 32 gw + 32): one
+// conflict-free LDS.128 covers 8 rows x 4 units (quarter-warps read rows r and r + 4, whose swizzles differ in bit 2);
+// fp32 accumulation, then a 3-step transposing butterfly over the 8 lanes that share a unit.  `colsum` [256] is private to the
+// slot's group and each column to one lane: plain read-modify-write.  Latent gradient: sum_samples d loss / d (x + z) =
+// W^T (column sums of the layer's pre-activation gradient); the W^T fold runs once per object in latent.cu.
+// (A legacy mma.sync ones^T x tile version was 10x fewer instructions but its HMMAs queue behind the in-flight tcgen05 MMAs
+// of BOTH slots: +3600 cycles per step, profiles/r1_trace_v9_v10.md.)
+__device__ __forceinline__ void colsum_a_operand(const Smem& sm, uint32_t slot, uint32_t gw, uint32_t lane, float* colsum) {
+  const uint32_t c = gw >> 1, unit = (gw & 1u) * 4u + (lane & 3u);
+  const uint32_t rsub = ((lane >> 3) & 3u) + 4u * ((lane >> 2) & 1u);
+  const uint8_t* base = sm.chunk(slot, (int)c);
+  float acc[8];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-    if (c + 1 < 4) tmem_ld32_issue(t0 + (uint32_t)(c + 1) * 64u, r);
-    if (EV) {
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 4
+  for (uint32_t it = 0; it < 16; ++it) {
+    const uint4 q = *reinterpret_cast<const uint4*>(base + swz(it * 8u + rsub, unit));
+    acc[0] += __uint_as_float(q.x << 16); acc[1] += __uint_as_float(q.x & 0xffff0000u);
+    acc[2] += __uint_as_float(q.y << 16); acc[3] += __uint_as_float(q.y & 0xffff0000u);
+    acc[4] += __uint_as_float(q.z << 16); acc[5] += __uint_as_float(q.z & 0xffff0000u);
+    acc[6] += __uint_as_float(q.w << 16); acc[7] += __uint_as_float(q.w & 0xffff0000u);
+  }
 #pragma unroll
-      for (int i4 = 0; i4 < 8; ++i4) {
-        const float4 ws = *reinterpret_cast<const float4*>(wsig_s + col0 + 4 * i4);
-        v[4 * i4] += gsp * ws.x; v[4 * i4 + 1] += gsp * ws.y; v[4 * i4 + 2] += gsp * ws.z; v[4 * i4 + 3] += gsp * ws.w;
-      }
-    }
-    if (PRODUCE) {
-      uint32_t pk[16];
+  for (int o = 4; o >= 1; o >>= 1) {   // lane bits 4, 3, 2 <-> value index bits 2, 1, 0
+    const bool upper = (lane & (uint32_t)(4 * o)) != 0;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float a = (!MASK || mask_bit(mw[c], 2 * i)) ? v[2 * i] : 0.f;
-        const float b = (!MASK || mask_bit(mw[c], 2 * i + 1)) ? v[2 * i + 1] : 0.f;
-        pk[i] = pack_bf16(a, b);
-      }
-      store_row32(sm.chunk(e.slot, c), e.row, e.hh, pk);
-    }
-    if (COLSUM) {
-      const float cs = warp_colsum32(v, e.lane);
-      atomicAdd(colsum + st.latent_slot * 256 + col0 + e.lane, cs);
+    for (int i = 0; i < o; ++i) {
+      const float keep = upper ? acc[i + o] : acc[i];
+      const float send = upper ? acc[i] : acc[i + o];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4 * o);
     }
   }
+  const uint32_t idx = ((lane >> 4) & 1u) * 4u + ((lane >> 3) & 1u) * 2u + ((lane >> 2) & 1u);
+  colsum[c * 64u + unit * 8u + idx] += acc[0];
 }
 
 // ------------------------------------------------------------------------------------------ backward kernel
@@ -471,9 +589,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_const
     const float* w2_s = sm.tab(TAB_W2);
     const int nslots = p.prog.n_mask_slots;
     uint32_t acc_cnt = 0;
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    const uint32_t crank = cluster_ctarank();
+    for (int64_t pair0 = (int64_t)blockIdx.x - crank; pair0 < n_pairs; pair0 += gridDim.x) {
+      const int64_t pair = pair0 + crank;
       const int64_t tile = 2 * pair + slot;
-      const bool tile_ok = tile < n_tiles;
+      const bool tile_ok = pair < n_pairs && tile < n_tiles;
       e.grow = tile * kTileM + e.row;
       e.valid = tile_ok && e.grow < p.M;
       const int64_t crow = e.valid ? e.grow : p.M - 1;
@@ -513,9 +633,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_const
 #pragma unroll
           for (int c = 0; c < 4; ++c) mw[c] = mask_word(mask_tile, st.mask_slot, c * 2 + (int)e.hh, e.row);
         }
+        if (st.colsum) {   // column sums of this step's A operand (published by the whole group last step), while its MMAs run
+          group_bar(slot);
+          colsum_a_operand(sm, slot, gw, lane, colsum + st.latent_slot * 256);
+        }
         mbar_wait(sm.bar(BAR_ACC + slot), acc_cnt & 1u);
         acc_cnt++;
         tc_fence_after();
+        if (st.colsum) group_bar(slot);   // every warp is done reading the chunks this step's epilogue overwrites
         if (p.trace && blockIdx.x == 0 && gtid == 0) p.trace[(((pair / gridDim.x) * p.prog.n_steps + si) * 2 + slot) * 4 + 2] = clock64();
         if (st.epi == B_XYZ) {
           // acc = d PE(xyz) (64 columns): fold to d xyz.  g_x = g_0 + sum_f 2^f (g_sin,f cos_f - g_cos,f sin_f)
@@ -562,12 +687,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_const
             if (e.valid && p.g_viewdir) { p.g_viewdir[3 * e.grow] = g[0]; p.g_viewdir[3 * e.grow + 1] = g[1]; p.g_viewdir[3 * e.grow + 2] = g[2]; }
           }
         } else if (st.epi == B_EV) {
-          bwd_epilogue<true, false, false, true>(sm, st, e, mw, gsp, colsum);
-        } else if (st.colsum) {
-          if (st.produce_a) bwd_epilogue<false, true, true, true>(sm, st, e, mw, gsp, colsum);
-          else bwd_epilogue<false, true, false, false>(sm, st, e, mw, gsp, colsum);
-        } else {
-          bwd_epilogue<false, false, true, true>(sm, st, e, mw, gsp, colsum);
+          bwd_epilogue<true, false>(sm, e, mw, gsp);
+        } else if (st.produce_a) {
+          bwd_epilogue<false, true>(sm, e, mw, gsp);
         }
         if (si + 1 < p.prog.n_steps) publish(sm, slot, lane);
         else tc_fence_before();
@@ -593,19 +715,27 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();   // no CTA leaves while a peer can still multicast into its shared memory / barriers
   if (warp == 16) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------ weight packing
 struct PackJob {
   const float* src; int ld; int transposed; int n_valid; int n_pad; int k0; int k_limit; uint32_t dst_off;
+  int bias;   // 1: src is a bias vector (n_valid entries); dst is a bias stage [n_pad][16 k] (see bias_stage_row)
 };
+
 constexpr int kJobsPerLaunch = 64;
 struct PackJobs { int n; PackJob j[kJobsPerLaunch]; };
 
 // one block per stage image: dst[n][k] (64B-swizzled rows of 32 bf16) = src'(n, k0 + k), zero outside the valid range
 __global__ void __launch_bounds__(256) pack2_kernel(const __grid_constant__ PackJobs jobs, uint8_t* __restrict__ packed) {
   const PackJob& jb = jobs.j[blockIdx.x];
+  if (jb.bias) {
+    for (int n = threadIdx.x; n < jb.n_pad; n += blockDim.x)
+      bias_stage_row(packed + jb.dst_off + (uint32_t)n * kBiasStageRowBytes, n < jb.n_valid ? jb.src[n] : 0.f);
+    return;
+  }
   for (int e = threadIdx.x; e < jb.n_pad * 32; e += blockDim.x) {
     int n, k;
     if (jb.transposed) { k = e / jb.n_pad; n = e % jb.n_pad; }  // consecutive threads walk the contiguous source dimension
@@ -643,17 +773,26 @@ static void add_stages(Tc2Plan& pl, const float* src, int ld, bool transposed, i
   for (int c = 0; c < n_stages; ++c) {
     tc2::PackJob j;
     j.src = src; j.ld = ld; j.transposed = transposed ? 1 : 0; j.n_valid = n_valid; j.n_pad = n_pad; j.k0 = c * 32;
-    j.k_limit = k_limit; j.dst_off = pl.total_bytes;
+    j.k_limit = k_limit; j.dst_off = pl.total_bytes; j.bias = 0;
     pl.jobs.push_back(j);
     pl.total_bytes += (uint32_t)n_pad * 64u;
   }
+}
+
+// static bias stage of a step: must directly follow the step's weight stages in the packed image
+static void add_bias_stage(Tc2Plan& pl, tc2::Step& s, const float* bias, int n_valid, int n_pad) {
+  tc2::PackJob j{};
+  j.src = bias; j.n_valid = n_valid; j.n_pad = n_pad; j.dst_off = pl.total_bytes; j.bias = 1;
+  pl.jobs.push_back(j);
+  pl.total_bytes += (uint32_t)n_pad * tc2::kBiasStageRowBytes;
+  s.bias_stage = 1;
 }
 
 static tc2::Step mk(int epi, int n_out, int n_stages, int mask_slot, int latent_slot, int bias_row, int dbg_idx) {
   tc2::Step s{};
   s.epi = (int8_t)epi; s.n_out = (uint16_t)n_out; s.n_stages = (uint16_t)n_stages; s.mask_slot = (int8_t)mask_slot;
   s.latent_slot = (int8_t)latent_slot; s.bias_row = (int8_t)bias_row; s.dbg_idx = (int8_t)dbg_idx;
-  s.accumulate = 0; s.produce_a = 1; s.colsum = 0;
+  s.accumulate = 0; s.produce_a = 1; s.colsum = 0; s.bias_stage = 0;
   return s;
 }
 
@@ -669,14 +808,17 @@ static Tc2Plan build_plan2(const snb_handle_s* h) {
     f.n_steps = 0; f.n_mask_slots = Bs + Bt + 3;
     tc2::Step s = mk(F_RELU, 256, 2, 0, -1, 0, 0);                                         // encoding_xyz: K = 64 (63 valid)
     add_stages(pl, ly[h->iX].w, dx, false, 256, 256, dx, 2, &s.w_off);
+    add_bias_stage(pl, s, ly[h->iX].b, 256, 256);
     push(f, s);
     for (int j = 1; j <= Bs; ++j) {
       s = mk(F_RELU, 256, 8, j, j - 1, -1, j);                                             // shape_layer_j, effective bias slot j-1
       add_stages(pl, ly[h->iS(j)].w, W, false, 256, 256, W, 8, &s.w_off);
+      s.bias_stage = 2;
       push(f, s);
     }
     s = mk(F_SIGMA, 256, 8, -1, -1, 1, Bs + 1);                                            // encoding_shape (+ sigma head)
     add_stages(pl, ly[h->iES].w, W, false, 256, 256, W, 8, &s.w_off);
+    add_bias_stage(pl, s, ly[h->iES].b, 256, 256);
     push(f, s);
     s = mk(F_PEV, 256, 8, -1, -1, -1, -1);                                                 // encoding_viewdir, y columns
     add_stages(pl, ly[h->iEV].w, W + dv, false, 256, 256, W, 8, &s.w_off);
@@ -684,15 +826,18 @@ static Tc2Plan build_plan2(const snb_handle_s* h) {
     s = mk(F_RELU, 256, 2, slot_vv, -1, 2, Bs + 2);                                        // + PE(viewdir) columns [W, W+dv)
     s.accumulate = 1;
     add_stages(pl, ly[h->iEV].w + W, W + dv, false, 256, 256, dv, 2, &s.w_off);
+    add_bias_stage(pl, s, ly[h->iEV].b, 256, 256);
     push(f, s);
     for (int j = 1; j <= Bt; ++j) {
       s = mk(F_RELU, 256, 8, slot_vv + j, Bs + j - 1, -1, Bs + 2 + j);
       add_stages(pl, ly[h->iT(j)].w, W, false, 256, 256, W, 8, &s.w_off);
+      s.bias_stage = 2;
       push(f, s);
     }
     s = mk(F_RGB, 128, 8, slot_r, -1, 3, Bs + Bt + 3);                                     // rgb.0 (+ rgb.2 head)
     s.produce_a = 0;
     add_stages(pl, ly[h->iR0].w, W, false, 128, 128, W, 8, &s.w_off);
+    add_bias_stage(pl, s, ly[h->iR0].b, 128, 128);
     push(f, s);
   }
   {  // ---------------- backward (B operand = W^T: n = input unit, k = output unit)
@@ -723,8 +868,11 @@ static Tc2Plan build_plan2(const snb_handle_s* h) {
       for (int j = Bs; j >= 1; --j) {                                                      // through shape_layer_j
         s = mk(B_MASK, 256, 8, j - 1, j - 1, -1, -1);
         s.colsum = 1;
-        if (!full && j == 1) s.produce_a = 0;                                              // feeds nobody without pose gradients
-        add_stages(pl, ly[h->iS(j)].w, W, true, 256, 256, W, 8, &s.w_off);
+        if (!full && j == 1) {   // without pose gradients only the column sums of this step's A operand are needed: no MMAs
+          s.produce_a = 0; s.n_stages = 0; s.w_off = 0;
+        } else {
+          add_stages(pl, ly[h->iS(j)].w, W, true, 256, 256, W, 8, &s.w_off);
+        }
         push(b, s);
       }
       if (full) {
@@ -759,11 +907,10 @@ static long long* g_trace = nullptr;   // test / tuning hook (snb_tc_set_trace)
 void tc2_set_trace(long long* buf) { g_trace = buf; }
 
 static void fill_common2(tc2::Params& p, const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M,
-                         int64_t B, const float* zlat, uint32_t* masks) {
+                         int64_t B, const uint8_t* eimg, uint32_t* masks) {
   p = tc2::Params{};
   p.xyz = xyz; p.viewdir = viewdir; p.M = M; p.B = B; p.rows_per_obj = M / B;
-  p.packed = (const uint8_t*)packed2; p.zlat = zlat; p.masks = masks;
-  p.bias4[0] = h->layers[h->iX].b; p.bias4[1] = h->layers[h->iES].b; p.bias4[2] = h->layers[h->iEV].b; p.bias4[3] = h->layers[h->iR0].b;
+  p.packed = (const uint8_t*)packed2; p.eimg = eimg; p.masks = masks;
   p.wsig = h->layers[h->iSG].w; p.bsig = h->layers[h->iSG].b;
   p.w2 = h->layers[h->iR2].w; p.b2 = h->layers[h->iR2].b;
   p.n_latent = h->arch.shape_blocks + h->arch.texture_blocks;
@@ -771,25 +918,57 @@ static void fill_common2(tc2::Params& p, const snb_handle_s* h, const void* pack
   p.trace = g_trace;
 }
 
-static int tc2_grid(int64_t M) {
-  const int sms = sm_count();
+// Grid = a whole number of clusters, at most as many as can be co-resident (persistent kernel, 1 CTA per SM; clusters cannot
+// span GPCs, so a GPC with an odd SM count leaves one SM idle), at most one CTA per tile pair (rounded up to a full cluster).
+template <typename K>
+static int tc2_grid(K kernel, int64_t M) {
+  static int max_ctas = 0;   // same answer for both kernels of this file (same block size / shared memory)
+  if (max_ctas == 0) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(sm_count() / kCluster * kCluster), 1, 1);
+    cfg.blockDim = dim3(tc2::kThreads, 1, 1);
+    cfg.dynamicSmemBytes = SM_ALLOC;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = kCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = sm_count() / kCluster; }
+    max_ctas = n * kCluster;
+    if (max_ctas > sm_count()) max_ctas = sm_count() / kCluster * kCluster;
+  }
   const int64_t pairs = ((M + kTileM - 1) / kTileM + 1) / 2;
-  return (int)(pairs < sms ? pairs : sms);
+  const int64_t want = (pairs + kCluster - 1) / kCluster * kCluster;
+  return (int)(want < max_ctas ? want : max_ctas);
+}
+
+template <typename K>
+static cudaError_t tc2_launch(K kernel, int grid, cudaStream_t st, const tc2::Params& p) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(tc2::kThreads, 1, 1);
+  cfg.dynamicSmemBytes = SM_ALLOC;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, p);
 }
 
 int tc2_launch_fwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
-                   const float* ebias, uint32_t* masks, float* sigma, float* rgb, float* dbg, cudaStream_t st) {
+                   const uint8_t* eimg, uint32_t* masks, float* sigma, float* rgb, float* dbg, cudaStream_t st) {
   Tc2Plan pl = build_plan2(h);
   tc2::Params p;
-  fill_common2(p, h, packed2, xyz, viewdir, M, B, ebias, masks);
+  fill_common2(p, h, packed2, xyz, viewdir, M, B, eimg, masks);
   p.sigma = sigma; p.rgb = rgb; p.dbg = dbg;
   p.prog = pl.fwd;
   if (dbg) {
     SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
-    tc2_fwd_kernel<true><<<tc2_grid(M), tc2::kThreads, SM_ALLOC, st>>>(p);
+    SNB_CHECK_CUDA(tc2_launch(tc2_fwd_kernel<true>, tc2_grid(tc2_fwd_kernel<true>, M), st, p));
   } else {
     SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
-    tc2_fwd_kernel<false><<<tc2_grid(M), tc2::kThreads, SM_ALLOC, st>>>(p);
+    SNB_CHECK_CUDA(tc2_launch(tc2_fwd_kernel<false>, tc2_grid(tc2_fwd_kernel<false>, M), st, p));
   }
   return 0;
 }
@@ -804,7 +983,7 @@ int tc2_launch_bwd(const snb_handle_s* h, const void* packed2, const float* xyz,
   p.r0_mask_slot = pl.r0_slot;
   p.prog = g_xyz ? pl.bwd_full : pl.bwd_noxyz;
   SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
-  tc2_bwd_kernel<<<tc2_grid(M), tc2::kThreads, SM_ALLOC, st>>>(p);
+  SNB_CHECK_CUDA(tc2_launch(tc2_bwd_kernel, tc2_grid(tc2_bwd_kernel, M), st, p));
   return 0;
 }
 

@@ -72,6 +72,25 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr) : "memory");
 }
+// issue a 16-column TMEM load of this thread's lane (no wait)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+// legacy warp-level tensor-core ops, used for the column sums of a shared-memory operand tile (ones^T x tile)
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t saddr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr) : "memory");
+}
+__device__ __forceinline__ void mma_ones_bf16(float (&d)[4], uint32_t b0, uint32_t b1) {
+  const uint32_t one2 = 0x3F803F80u;   // bf16x2 (1.0, 1.0)
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %4, %4, %4}, {%5, %6}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(one2), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   tmem_ld32_issue(taddr, r);
@@ -155,6 +174,22 @@ __device__ __forceinline__ void write_pe_row(uint8_t* aux, uint32_t row, uint32_
       *reinterpret_cast<uint4*>(aux + swz(row, u)) = q;
     }
   }
+}
+
+// One 32-byte row of a bias stage: both 16-byte units hold {hi, mid, lo, 0, 0, 0, 0, 0}, the bf16 split of bias / 2, so the
+// row is invariant under the 32-byte swizzle and  ones(16) . row = bias  to fp32 accuracy.
+__device__ __forceinline__ void bias_stage_row(uint8_t* row, float bias) {
+  const float x = 0.5f * bias;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(hi);
+  const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+  uint4 q;
+  q.x = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(mid) << 16);
+  q.y = (uint32_t)__bfloat16_as_ushort(lo);
+  q.z = 0u; q.w = 0u;
+  reinterpret_cast<uint4*>(row)[0] = q;
+  reinterpret_cast<uint4*>(row)[1] = q;
 }
 
 // sum over the 32 lanes (= 32 rows) of each of the 32 per-lane values: lane l ends with column l's sum in v[0]
