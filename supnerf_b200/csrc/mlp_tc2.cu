@@ -424,26 +424,39 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_const
     EpiCtx e;
     e.lane = lane; e.hh = gw >> 2; e.row = (gw & 3u) * 32u + lane; e.lane_field = ((gw & 3u) * 32u) << 16;
     e.tmem = tmem_base + slot * 256u; e.slot = slot;
-    float* sig_part = reinterpret_cast<float*>(sm.chunk(slot, 3));   // tile-end scratch: [2][128] + [2][128][3]
-    float* rgb_part = sig_part + 256;
+    // tile-end scratch outside the A chunks (so the next tile can start before it is read): the hh == 1 half of every row
+    // leaves its partial sigma / rgb heads here, the hh == 0 half adds its own and stores.  [128][4] floats per slot.
+    float* part = sm.tab(TAB_BIAS) + slot * 512u;
     const int nslots = p.prog.n_mask_slots;
     uint32_t acc_cnt = 0;
     const uint32_t crank = cluster_ctarank();
-    for (int64_t pair0 = (int64_t)blockIdx.x - crank; pair0 < n_pairs; pair0 += gridDim.x) {
+    const int64_t pair_first = (int64_t)blockIdx.x - crank;
+    float x[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 1.f};
+    auto load_coords = [&](int64_t pr, float (&xo)[3], float (&dro)[3]) {   // clamped: tiles past the end redo row M-1, never stored
+      int64_t r = (2 * pr + slot) * kTileM + e.row;
+      if (pr >= n_pairs || r >= p.M) r = p.M - 1;
+      xo[0] = __ldg(p.xyz + 3 * r); xo[1] = __ldg(p.xyz + 3 * r + 1); xo[2] = __ldg(p.xyz + 3 * r + 2);
+      dro[0] = __ldg(p.viewdir + 3 * r); dro[1] = __ldg(p.viewdir + 3 * r + 1); dro[2] = __ldg(p.viewdir + 3 * r + 2);
+    };
+    if (pair_first < n_pairs) {   // first tile of this CTA: PE(xyz) -> chunk 0
+      load_coords(pair_first + crank, x, dir);
+      write_pe_row<10>(sm.chunk(slot, 0), e.row, e.hh, x);
+      publish(sm, slot, lane);
+    }
+    for (int64_t pair0 = pair_first; pair0 < n_pairs; pair0 += gridDim.x) {
       const int64_t pair = pair0 + crank;
       const int64_t tile = 2 * pair + slot;
       const bool tile_ok = pair < n_pairs && tile < n_tiles;
+      const bool has_next = pair0 + (int64_t)gridDim.x < n_pairs;   // cluster-uniform
       e.grow = tile * kTileM + e.row;
       e.valid = tile_ok && e.grow < p.M;
-      const int64_t crow = e.valid ? e.grow : p.M - 1;
-      const float x[3] = {__ldg(p.xyz + 3 * crow), __ldg(p.xyz + 3 * crow + 1), __ldg(p.xyz + 3 * crow + 2)};
-      const float dir[3] = {__ldg(p.viewdir + 3 * crow), __ldg(p.viewdir + 3 * crow + 1), __ldg(p.viewdir + 3 * crow + 2)};
-      write_pe_row<10>(sm.chunk(slot, 0), e.row, e.hh, x);
-      publish(sm, slot, lane);
       uint32_t* mask_tile = p.masks + (size_t)(tile_ok ? tile : 0) * nslots * 8 * 128;
       float sig_acc = 0.f, rgb_acc[3] = {0.f, 0.f, 0.f};
+      float xn[3] = {0.f, 0.f, 0.f}, dn[3] = {0.f, 0.f, 1.f};
       for (int si = 0; si < p.prog.n_steps; ++si) {
         const Step& st = p.prog.s[si];
+        const bool last = si + 1 == p.prog.n_steps;
+        if (last && has_next) load_coords(pair + gridDim.x, xn, dn);   // the global latency hides behind rgb.0's MMAs
         mbar_wait(sm.bar(BAR_ACC + slot), acc_cnt & 1u);
         acc_cnt++;
         tc_fence_after();
@@ -452,23 +465,27 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_const
         else if (st.epi == F_SIGMA) fwd_epilogue<F_SIGMA, DBG>(p, sm, st, e, mask_tile, tile_ok, sig_acc, rgb_acc);
         else if (st.epi == F_PEV) write_pe_row<4>(sm.chunk(slot, 0), e.row, e.hh, dir);   // accumulator untouched: the next step adds to it
         else fwd_epilogue<F_RGB, DBG>(p, sm, st, e, mask_tile, tile_ok, sig_acc, rgb_acc);
-        if (si + 1 < p.prog.n_steps) publish(sm, slot, lane);
-        else tc_fence_before();
+        if (!last) publish(sm, slot, lane);
+        else if (has_next) {   // rgb.0's MMAs are complete and its accumulator is drained: hand the NEXT tile's PE(xyz) to the MMA warp
+          write_pe_row<10>(sm.chunk(slot, 0), e.row, e.hh, xn);   // before the tile-end bookkeeping below
+          publish(sm, slot, lane);
+        } else tc_fence_before();
         if (p.trace && blockIdx.x == 0 && gtid == 0) p.trace[(((pair / gridDim.x) * p.prog.n_steps + si) * 2 + slot) * 4 + 3] = clock64();
       }
-      // tile end: combine the two column halves of the sigma / rgb heads (the A chunks are free: rgb.0's MMAs are complete)
-      sig_part[e.hh * 128 + e.row] = sig_acc;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) rgb_part[(e.hh * 128 + e.row) * 3 + k] = rgb_acc[k];
+      // tile end: combine the two column halves of the sigma / rgb heads
+      if (e.hh == 1) *reinterpret_cast<float4*>(part + 4 * e.row) = make_float4(sig_acc, rgb_acc[0], rgb_acc[1], rgb_acc[2]);
       group_bar(slot);
       if (e.hh == 0 && e.valid) {
-        const float sp = sig_part[e.row] + sig_part[128 + e.row] + __ldg(p.bsig);
+        const float4 o = *reinterpret_cast<const float4*>(part + 4 * e.row);
+        const float sp = sig_acc + o.x + __ldg(p.bsig);
         p.sigma[e.grow] = sp > 20.f ? sp : log1pf(expf(sp));   // nn.Softplus(): beta 1, threshold 20
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-          p.rgb[3 * e.grow + k] = rgb_part[e.row * 3 + k] + rgb_part[(128 + e.row) * 3 + k] + __ldg(p.b2 + k);
+        p.rgb[3 * e.grow] = rgb_acc[0] + o.y + __ldg(p.b2);
+        p.rgb[3 * e.grow + 1] = rgb_acc[1] + o.z + __ldg(p.b2 + 1);
+        p.rgb[3 * e.grow + 2] = rgb_acc[2] + o.w + __ldg(p.b2 + 2);
       }
-      // no second barrier: chunk 3 is next written by encoding_xyz's epilogue, which needs every warp's READY arrive first
+      // `part` is rewritten one tile later, after every warp of the group has passed (at least) the next tile's first publish
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { x[a] = xn[a]; dir[a] = dn[a]; }
     }
   }
   tc_fence_before();
@@ -585,47 +602,69 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_const
     e.lane = lane; e.hh = gw >> 2; e.row = (gw & 3u) * 32u + lane; e.lane_field = ((gw & 3u) * 32u) << 16;
     e.tmem = tmem_base + slot * 256u; e.slot = slot;
     float* colsum = sm.tab(TAB_LAT) + slot * kMaxLat * 256;
-    float* xyz_part = reinterpret_cast<float*>(sm.chunk(slot, 3));   // tile-end scratch [2][128][3]; chunk 3 is next written by a step epilogue
+    // tile-end scratch outside the A chunks: the hh == 1 half of every row leaves its partial d xyz here.  [128][4] floats per slot.
+    float* part = sm.tab(TAB_BIAS) + slot * 512u;
     const float* w2_s = sm.tab(TAB_W2);
     const int nslots = p.prog.n_mask_slots;
     uint32_t acc_cnt = 0;
     const uint32_t crank = cluster_ctarank();
-    for (int64_t pair0 = (int64_t)blockIdx.x - crank; pair0 < n_pairs; pair0 += gridDim.x) {
+    const int64_t pair_first = (int64_t)blockIdx.x - crank;
+    // upstream gradients of one tile row: d softplus-input of sigma, d rgb, and the rgb.0 ReLU mask words of this thread's columns
+    auto load_upstream = [&](int64_t pr, float& gsp_o, float (&g3o)[3], uint32_t (&mwo)[2]) {
+      const int64_t t = 2 * pr + slot;
+      const bool ok = pr < n_pairs && t < n_tiles;
+      const int64_t r = t * kTileM + e.row;
+      const bool valid = ok && r < p.M;
+      const int64_t cr = valid ? r : p.M - 1;
+      const float gsg = valid ? __ldg(p.g_sigma + r) : 0.f;
+      gsp_o = gsg * (-expm1f(-__ldg(p.sigma_in + cr)));   // d softplus = 1 - exp(-softplus)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) g3o[k] = valid ? __ldg(p.g_rgb + 3 * r + k) : 0.f;
+      const uint32_t* mt = p.masks + (size_t)(ok ? t : 0) * nslots * 8 * 128;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) mwo[c] = mask_word(mt, p.r0_mask_slot, c * 2 + (int)e.hh, e.row);
+    };
+    // d pre-activation of rgb.0 = (g_rgb W2) * mask -> A chunks 0,1 (128 columns)
+    auto prologue = [&](const float (&g3)[3], const uint32_t (&mw2)[2]) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = c * 64 + (int)e.hh * 32;
+        const uint32_t mw = mw2[c];
+        uint32_t pk[16];
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 w0 = *reinterpret_cast<const float4*>(w2_s + col0 + 4 * i4);
+          const float4 w1 = *reinterpret_cast<const float4*>(w2_s + 128 + col0 + 4 * i4);
+          const float4 w2 = *reinterpret_cast<const float4*>(w2_s + 256 + col0 + 4 * i4);
+          float v[4] = {g3[0] * w0.x + g3[1] * w1.x + g3[2] * w2.x, g3[0] * w0.y + g3[1] * w1.y + g3[2] * w2.y,
+                        g3[0] * w0.z + g3[1] * w1.z + g3[2] * w2.z, g3[0] * w0.w + g3[1] * w1.w + g3[2] * w2.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) if (!mask_bit(mw, 4 * i4 + u)) v[u] = 0.f;
+          pk[2 * i4] = pack_bf16(v[0], v[1]);
+          pk[2 * i4 + 1] = pack_bf16(v[2], v[3]);
+        }
+        store_row32(sm.chunk(slot, c), e.row, e.hh, pk);
+      }
+    };
+    float gsp = 0.f;
+    if (pair_first < n_pairs) {   // first tile of this CTA
+      float g3[3]; uint32_t mw2[2];
+      load_upstream(pair_first + crank, gsp, g3, mw2);
+      prologue(g3, mw2);
+      publish(sm, slot, lane);
+    }
+    for (int64_t pair0 = pair_first; pair0 < n_pairs; pair0 += gridDim.x) {
       const int64_t pair = pair0 + crank;
       const int64_t tile = 2 * pair + slot;
       const bool tile_ok = pair < n_pairs && tile < n_tiles;
+      const bool has_next = pair0 + (int64_t)gridDim.x < n_pairs;   // cluster-uniform
       e.grow = tile * kTileM + e.row;
       e.valid = tile_ok && e.grow < p.M;
       const int64_t crow = e.valid ? e.grow : p.M - 1;
       const int64_t obj = tile_ok ? (tile * kTileM) / p.rows_per_obj : 0;
       const uint32_t* mask_tile = p.masks + (size_t)(tile_ok ? tile : 0) * nslots * 8 * 128;
-      const float gsg = e.valid ? __ldg(p.g_sigma + e.grow) : 0.f;
-      const float gsp = gsg * (-expm1f(-__ldg(p.sigma_in + crow)));   // d softplus = 1 - exp(-softplus)
-      // ---- prologue: d pre-activation of rgb.0 = (g_rgb W2) * mask -> A chunks 0,1 (128 columns)
-      {
-        float g3[3] = {0.f, 0.f, 0.f};
-        if (e.valid) { g3[0] = __ldg(p.g_rgb + 3 * e.grow); g3[1] = __ldg(p.g_rgb + 3 * e.grow + 1); g3[2] = __ldg(p.g_rgb + 3 * e.grow + 2); }
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int col0 = c * 64 + (int)e.hh * 32;
-          const uint32_t mw = mask_word(mask_tile, p.r0_mask_slot, c * 2 + e.hh, e.row);
-          uint32_t pk[16];
-#pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 w0 = *reinterpret_cast<const float4*>(w2_s + col0 + 4 * i4);
-            const float4 w1 = *reinterpret_cast<const float4*>(w2_s + 128 + col0 + 4 * i4);
-            const float4 w2 = *reinterpret_cast<const float4*>(w2_s + 256 + col0 + 4 * i4);
-            float v[4] = {g3[0] * w0.x + g3[1] * w1.x + g3[2] * w2.x, g3[0] * w0.y + g3[1] * w1.y + g3[2] * w2.y,
-                          g3[0] * w0.z + g3[1] * w1.z + g3[2] * w2.z, g3[0] * w0.w + g3[1] * w1.w + g3[2] * w2.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) if (!mask_bit(mw, 4 * i4 + u)) v[u] = 0.f;
-            pk[2 * i4] = pack_bf16(v[0], v[1]);
-            pk[2 * i4 + 1] = pack_bf16(v[2], v[3]);
-          }
-          store_row32(sm.chunk(slot, c), e.row, e.hh, pk);
-        }
-      }
-      publish(sm, slot, lane);
+      float gsp_n = 0.f, g3n[3] = {0.f, 0.f, 0.f}, gx[3] = {0.f, 0.f, 0.f};
+      uint32_t mwn[2] = {0u, 0u};
       for (int si = 0; si < p.prog.n_steps; ++si) {
         const Step& st = p.prog.s[si];
         uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
@@ -633,6 +672,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_const
 #pragma unroll
           for (int c = 0; c < 4; ++c) mw[c] = mask_word(mask_tile, st.mask_slot, c * 2 + (int)e.hh, e.row);
         }
+        const bool last = si + 1 == p.prog.n_steps;
+        if (last && has_next) load_upstream(pair + gridDim.x, gsp_n, g3n, mwn);   // global latency hides behind the last MMAs
         if (st.colsum) {   // column sums of this step's A operand (published by the whole group last step), while its MMAs run
           group_bar(slot);
           colsum_a_operand(sm, slot, gw, lane, colsum + st.latent_slot * 256);
@@ -667,7 +708,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_const
             }
           }
 #pragma unroll
-          for (int a = 0; a < 3; ++a) xyz_part[(e.hh * 128 + e.row) * 3 + a] = g[a];
+          for (int a = 0; a < 3; ++a) gx[a] = g[a];
         } else if (st.epi == B_VD) {
           // acc columns 0..26 = d PE(viewdir): fold to d viewdir (deg 4)
           if (e.hh == 0) {
@@ -691,18 +732,25 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_const
         } else if (st.produce_a) {
           bwd_epilogue<false, true>(sm, e, mw, gsp);
         }
-        if (si + 1 < p.prog.n_steps) publish(sm, slot, lane);
-        else tc_fence_before();
+        if (!last) publish(sm, slot, lane);
+        else if (has_next) {   // the last MMAs are complete and their accumulator is drained: hand the NEXT tile's first operand over
+          prologue(g3n, mwn);  // before the tile-end bookkeeping below
+          publish(sm, slot, lane);
+        } else tc_fence_before();
         if (p.trace && blockIdx.x == 0 && gtid == 0) p.trace[(((pair / gridDim.x) * p.prog.n_steps + si) * 2 + slot) * 4 + 3] = clock64();
       }
       // ---- tile end: d xyz, and flush the latent column sums when this slot's next tile belongs to another object
       const int64_t next = tile + 2 * (int64_t)gridDim.x;
       const bool flush = tile_ok && (next >= n_tiles || (next * kTileM) / p.rows_per_obj != obj);
+      if (p.g_xyz != nullptr && e.hh == 1) *reinterpret_cast<float4*>(part + 4 * e.row) = make_float4(gx[0], gx[1], gx[2], 0.f);
       group_bar(slot);
       if (p.g_xyz != nullptr && e.hh == 0 && e.valid) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) p.g_xyz[3 * e.grow + a] = xyz_part[e.row * 3 + a] + xyz_part[(128 + e.row) * 3 + a];
+        const float4 o = *reinterpret_cast<const float4*>(part + 4 * e.row);
+        p.g_xyz[3 * e.grow] = gx[0] + o.x;
+        p.g_xyz[3 * e.grow + 1] = gx[1] + o.y;
+        p.g_xyz[3 * e.grow + 2] = gx[2] + o.z;
       }
+      gsp = gsp_n;
       if (flush) {
         for (int sl = 0; sl < p.n_latent; ++sl) {
           const float v = colsum[sl * 256 + gtid];
