@@ -267,6 +267,9 @@ def run_ours(args):
                     "timed": "CUDA events on the launch stream around the kernel alone, inside the timed region" if kern.get("fwd") else
                              "CUDA events around the decoder C-ABI call"}
 
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return
     cpu = cpu_baseline(steps=3, warmup=1)

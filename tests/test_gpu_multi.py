@@ -1,0 +1,96 @@
+"""N>1 GPU path of the ray-sharded mode (SURVEY §8e, config C4 shape scaled down): two ranks over NCCL render disjoint ray
+tiles of ONE object, all-reduce the flat pose/latent gradient buffer, and must reproduce the single-GPU result.
+Needs >= 2 GPUs (run with `gpurun --gpus 2`); skipped otherwise."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from conftest import ROOT  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+IM, S = 64, 64
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _setup(dev, prec):
+    import supnerf_b200 as snb
+    from supnerf_b200 import synthetic
+    obj = synthetic.synthetic_object(41, im_sz=IM)
+    sd = synthetic.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=41)
+    m = snb.SUPNeRF(3, 1, 3, 3, 256)
+    m.load_state_dict(sd)
+    m = m.to(dev)
+    m.precision = prec
+    m.requires_grad_(False)
+    shp, tex = synthetic.synthetic_latents(41, 1)
+    return snb, obj, m, shp, tex
+
+
+def _worker(rank, world, port, prec, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        snb, obj, m, shp0, tex0 = _setup(dev, prec)
+        R = snb.renderer.NeRFRenderer(n_samples=S)
+        cam = obj["cam_pose"].to(dev).requires_grad_()
+        shp, tex = shp0.to(dev).requires_grad_(), tex0.to(dev).requires_grad_()
+        torch.manual_seed(7)
+        torch.cuda.manual_seed(7)   # same device generator state on every rank => same full jitter
+        rgb, dep, acc, tgt, occ, occ_all = snb.parallel.render_rays_sharded(R, m, dev, obj["img"], obj["mask_occ"], cam, obj["wlh"],
+                                                                           obj["K"], obj["roi"], shp, tex, im_sz=IM)
+        part = snb.parallel.refine_loss_sharded(rgb, acc, tgt, occ, occ_all)
+        part.backward()
+        loss = snb.parallel.allreduce_grads([cam, shp, tex], part)
+        full = snb.parallel.gather_rays(rgb.detach(), IM * IM, S)
+        q.put((rank, float(loss), cam.grad.cpu(), shp.grad.cpu(), tex.grad.cpu(), full.cpu()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+def test_ray_sharded_two_gpus_matches_one(prec, tol):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, prec, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-GPU reference: the public render_rays with the same generator state
+    dev = torch.device("cuda", 0)
+    snb, obj, m, shp0, tex0 = _setup(dev, prec)
+    R = snb.renderer.NeRFRenderer(n_samples=S)
+    cam = obj["cam_pose"].to(dev).requires_grad_()
+    shp, tex = shp0.to(dev).requires_grad_(), tex0.to(dev).requires_grad_()
+    torch.manual_seed(7)
+    torch.cuda.manual_seed(7)
+    rgb, dep, acc, tgt, occ = R.render_rays(m, dev, obj["img"], obj["mask_occ"], cam, obj["wlh"], obj["K"], obj["roi"], shp, tex, im_sz=IM)
+    loss = snb.losses.refine_loss(rgb, acc, tgt, occ, 0.1)[0]
+    loss.backward()
+
+    def rel(a, b):
+        a, b = a.double().cpu(), b.double().cpu()
+        return ((a - b).abs().max() / b.abs().max()).item()
+    for rank, l, g_cam, g_shp, g_tex, full in res:
+        assert abs(l - loss.item()) <= 1e-5 * abs(loss.item()) + 1e-7
+        assert torch.equal(full, rgb.detach().cpu())            # the union of the shards is bit-identical to the unsharded render
+        assert rel(g_shp, shp.grad) < max(tol, 1e-4) and rel(g_tex, tex.grad) < max(tol, 1e-4)
+        assert rel(g_cam, cam.grad) < max(tol, 1e-3)            # fp32 sums in a different order (ill-conditioned reduction)
+    for t0, t1 in zip(res[0][2:5], res[1][2:5]):
+        assert torch.equal(t0, t1)                              # identical bits on every rank => identical optimiser steps
