@@ -175,7 +175,15 @@ typedef struct {
   int32_t flags;      /* SNB_WHITE_BKGD | SNB_SIGMA_RELU */
   float half_diag;    /* diag / 2, the reference's host-rounded float32 (renderer.py:92) */
   float aabb_half[3]; /* (l, w, h) / diag (renderer.py:97-100) */
+  int32_t mode;       /* SNB_RENDER_BOX: the renderer.py stack above.  SNB_RENDER_SHELL: the utils.py stack every refine loop
+                         calls (utils.render_rays_v2 utils.py:435-502, render_rays :380-432, render_rays_specified :504-551):
+                         z_steps then holds the SHARED sample vector z (S) built by the caller as utils.sample_from_rays does
+                         (utils.py:154-167), jitter is unused (may be NULL), compositing is utils.volume_rendering2 (shared z) */
+  float obj_diag;     /* shell mode: xyz /= obj_diag (utils.py:472) */
+  int32_t shapenet_swap; /* shell mode: (x,y,z) -> (-y,x,z) of xyz and viewdir (utils.py:491-495) */
 } snb_render_desc;
+#define SNB_RENDER_BOX 0
+#define SNB_RENDER_SHELL 1
 size_t snb_render_workspace_bytes(snb_handle h, const snb_render_desc* d);
 size_t snb_render_bwd_scratch_bytes(snb_handle h, const snb_render_desc* d);
 int snb_render_fwd(snb_handle h, const snb_render_desc* d, const float* px, const float* py, const float* K,

@@ -20,7 +20,7 @@ class SnbArch(ctypes.Structure):
 
 class SnbRenderDesc(ctypes.Structure):
     _fields_ = [("n_rays", c_i64), ("n_samples", c_i32), ("precision", c_i32), ("flags", c_i32), ("half_diag", c_flt),
-                ("aabb_half", c_flt * 3)]
+                ("aabb_half", c_flt * 3), ("mode", c_i32), ("obj_diag", c_flt), ("shapenet_swap", c_i32)]
 
 
 # name -> (restype, argtypes); mirrors include/supnerf_b200.h one to one

@@ -52,6 +52,7 @@ int check_desc(snb_handle h, const snb_render_desc* d, const char* who) {
   SNB_REQUIRE(h != nullptr && d != nullptr, "%s: null handle or descriptor", who);
   SNB_REQUIRE(d->n_rays >= 0 && d->n_samples >= 1, "%s: bad sizes", who);
   SNB_REQUIRE(d->precision == SNB_PREC_FP32 || d->precision == SNB_PREC_BF16, "%s: unknown precision %d", who, d->precision);
+  SNB_REQUIRE(d->mode == SNB_RENDER_BOX || d->mode == SNB_RENDER_SHELL, "%s: unknown mode %d", who, d->mode);
   return 0;
 }
 
@@ -76,19 +77,23 @@ extern "C" int snb_render_fwd(snb_handle h, const snb_render_desc* d, const floa
                               void* workspace, void* stream) {
   if (check_desc(h, d, "render_fwd")) return 2;
   if (d->n_rays == 0) return 0;
-  SNB_REQUIRE(px && py && K && c2w && z_steps && jitter && shape_latent && texture_latent && out_rgb && out_depth && out_acc &&
-              out_hit && workspace, "render_fwd: null pointer");
+  const bool shell = d->mode == SNB_RENDER_SHELL;
+  SNB_REQUIRE(px && py && K && c2w && z_steps && (jitter || shell) && shape_latent && texture_latent && out_rgb && out_depth &&
+              out_acc && (out_hit || shell) && workspace, "render_fwd: null pointer");
   SNB_REQUIRE(((uintptr_t)workspace & 255) == 0, "render_fwd: workspace must be 256-byte aligned");
   const FwdLayout L(h, *d);
   const int64_t N = d->n_rays, M = N * d->n_samples;
   void* ws = workspace;
   if (snb_get_rays_fwd(px, py, N, K, c2w, F(ws, L.rays_o), F(ws, L.viewdir), stream)) return 1;
-  if (snb_sample_box_fwd(F(ws, L.rays_o), F(ws, L.viewdir), z_steps, jitter, N, d->n_samples, d->half_diag, d->aabb_half,
-                         F(ws, L.xyz), F(ws, L.vrep), F(ws, L.z), out_hit, stream)) return 1;
+  if (shell) {   // utils.py stack: one shared z vector, no slab test
+    if (snb_sample_shell_fwd(F(ws, L.rays_o), F(ws, L.viewdir), z_steps, N, d->n_samples, d->obj_diag, d->shapenet_swap,
+                             F(ws, L.xyz), F(ws, L.vrep), stream)) return 1;
+  } else if (snb_sample_box_fwd(F(ws, L.rays_o), F(ws, L.viewdir), z_steps, jitter, N, d->n_samples, d->half_diag, d->aabb_half,
+                                F(ws, L.xyz), F(ws, L.vrep), F(ws, L.z), out_hit, stream)) return 1;
   if (snb_mlp_fwd(h, d->precision, F(ws, L.xyz), F(ws, L.vrep), M, 1, shape_latent, texture_latent, F(ws, L.sigma), F(ws, L.rgb),
                   static_cast<uint8_t*>(ws) + L.mlp, stream)) return 1;
-  return snb_composite_fwd(F(ws, L.sigma), F(ws, L.rgb), F(ws, L.z), 1, N, d->n_samples, d->flags, out_rgb, out_depth, out_acc,
-                           stream);
+  return snb_composite_fwd(F(ws, L.sigma), F(ws, L.rgb), shell ? z_steps : F(ws, L.z), shell ? N : 1, N, d->n_samples, d->flags,
+                           out_rgb, out_depth, out_acc, stream);
 }
 
 extern "C" int snb_render_bwd(snb_handle h, const snb_render_desc* d, const float* px, const float* py, const float* K,
@@ -101,8 +106,9 @@ extern "C" int snb_render_bwd(snb_handle h, const snb_render_desc* d, const floa
   cudaStream_t st = (cudaStream_t)stream;
   if (g_c2w) SNB_CHECK_CUDA(cudaMemsetAsync(g_c2w, 0, 12 * sizeof(float), st));
   if (d->n_rays == 0) return 0;
-  SNB_REQUIRE(px && py && K && c2w && z_steps && jitter && shape_latent && texture_latent && workspace && g_rgb && g_depth &&
-              g_acc && scratch, "render_bwd: null pointer");
+  const bool shell = d->mode == SNB_RENDER_SHELL;
+  SNB_REQUIRE(px && py && K && c2w && z_steps && (jitter || shell) && shape_latent && texture_latent && workspace && g_rgb &&
+              g_depth && g_acc && scratch, "render_bwd: null pointer");
   SNB_REQUIRE((((uintptr_t)workspace | (uintptr_t)scratch) & 255) == 0, "render_bwd: workspace/scratch must be 256-byte aligned");
   const FwdLayout L(h, *d);
   const BwdLayout G(h, *d);
@@ -110,14 +116,18 @@ extern "C" int snb_render_bwd(snb_handle h, const snb_render_desc* d, const floa
   const void* ws = workspace;
   void* sc = scratch;
   const bool pose = g_c2w != nullptr;
-  if (snb_composite_bwd(F(ws, L.sigma), F(ws, L.rgb), F(ws, L.z), 1, N, d->n_samples, d->flags, g_rgb, g_depth, g_acc,
-                        F(sc, G.g_sigma), F(sc, G.g_rgbs), pose ? F(sc, G.g_z) : nullptr, stream)) return 1;
+  // shell mode: z is built from detached python floats (utils.py:468-469), it carries no gradient
+  if (snb_composite_bwd(F(ws, L.sigma), F(ws, L.rgb), shell ? z_steps : F(ws, L.z), shell ? N : 1, N, d->n_samples, d->flags, g_rgb,
+                        g_depth, g_acc, F(sc, G.g_sigma), F(sc, G.g_rgbs), (pose && !shell) ? F(sc, G.g_z) : nullptr, stream)) return 1;
   if (snb_mlp_bwd(h, d->precision, F(ws, L.xyz), F(ws, L.vrep), M, 1, shape_latent, texture_latent, F(ws, L.sigma),
                   F(sc, G.g_sigma), F(sc, G.g_rgbs), static_cast<const uint8_t*>(ws) + L.mlp, static_cast<uint8_t*>(sc) + G.mlp,
                   pose ? F(sc, G.g_xyz) : nullptr, pose ? F(sc, G.g_vrep) : nullptr, g_shape_latent, g_texture_latent, g_weights,
                   stream)) return 1;
   if (!pose) return 0;
-  if (snb_sample_box_bwd(F(ws, L.rays_o), F(ws, L.viewdir), z_steps, jitter, N, d->n_samples, d->half_diag, d->aabb_half,
-                         F(sc, G.g_xyz), F(sc, G.g_vrep), F(sc, G.g_z), F(sc, G.g_rays_o), F(sc, G.g_viewdir), stream)) return 1;
+  if (shell) {
+    if (snb_sample_shell_bwd(z_steps, N, d->n_samples, d->obj_diag, d->shapenet_swap, F(sc, G.g_xyz), F(sc, G.g_vrep),
+                             F(sc, G.g_rays_o), F(sc, G.g_viewdir), stream)) return 1;
+  } else if (snb_sample_box_bwd(F(ws, L.rays_o), F(ws, L.viewdir), z_steps, jitter, N, d->n_samples, d->half_diag, d->aabb_half,
+                                F(sc, G.g_xyz), F(sc, G.g_vrep), F(sc, G.g_z), F(sc, G.g_rays_o), F(sc, G.g_viewdir), stream)) return 1;
   return snb_get_rays_bwd(px, py, N, K, c2w, F(sc, G.g_rays_o), F(sc, G.g_viewdir), g_c2w, stream);
 }

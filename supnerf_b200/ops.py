@@ -353,16 +353,21 @@ class _RenderBox(torch.autograd.Function):
     intermediate in one workspace tensor.  Differentiable to cam_pose, the latents and (fp32 back end) the weights."""
 
     @staticmethod
-    def forward(ctx, handle, precision, n_samples, flags, half_diag, aabb_half, px, py, K, c2w, z_steps, jitter, shape_latent,
+    def forward(ctx, handle, precision, n_samples, flags, geom, px, py, K, c2w, z_steps, jitter, shape_latent,
                 texture_latent, *weights):
         lib = _lib.load()
         require_cuda(px, py, K, c2w, z_steps, jitter, shape_latent, texture_latent)
-        px, py, K, c2w, z_steps, jitter = f32c(px), f32c(py), f32c(K), f32c(c2w), f32c(z_steps), f32c(jitter)
+        px, py, K, c2w, z_steps = f32c(px), f32c(py), f32c(K), f32c(c2w), f32c(z_steps)
+        jitter = f32c(jitter) if jitter is not None else z_steps   # shell mode: unused by the library
         shape_latent, texture_latent = f32c(shape_latent), f32c(texture_latent)
         n = px.numel()
         dev = px.device
-        desc = _lib.SnbRenderDesc(n, int(n_samples), int(precision), int(flags), float(half_diag),
-                                  (ctypes.c_float * 3)(*[float(v) for v in aabb_half]))
+        if geom[0] == "box":      # ("box", half_diag, aabb_half)
+            desc = _lib.SnbRenderDesc(n, int(n_samples), int(precision), int(flags), float(geom[1]),
+                                      (ctypes.c_float * 3)(*[float(v) for v in geom[2]]), 0, 1.0, 0)
+        else:                     # ("shell", obj_diag, shapenet_swap)
+            desc = _lib.SnbRenderDesc(n, int(n_samples), int(precision), int(flags), 1.0, (ctypes.c_float * 3)(1.0, 1.0, 1.0), 1,
+                                      float(geom[1]), int(bool(geom[2])))
         handle.set_weights(weights)
         if precision == PREC["bf16"]:
             handle.ensure_packed(weights)
@@ -392,10 +397,10 @@ class _RenderBox(torch.autograd.Function):
         g_dep = f32c(g_dep) if g_dep is not None else torch.zeros(n, device=dev)
         g_acc = f32c(g_acc) if g_acc is not None else torch.zeros(n, device=dev)
         need = ctx.needs_input_grad
-        g_c2w = torch.empty(3, 4, device=dev, dtype=torch.float32) if need[9] else None
+        g_c2w = torch.empty(3, 4, device=dev, dtype=torch.float32) if need[8] else None
         g_sl = torch.empty_like(shape_latent)
         g_tl = torch.empty_like(texture_latent)
-        need_w = any(need[14:])
+        need_w = any(need[13:])
         gws, gw_arr = None, None
         if need_w:
             gws = [torch.empty_like(w, dtype=torch.float32).contiguous() for w in weights]
@@ -407,15 +412,24 @@ class _RenderBox(torch.autograd.Function):
                                      ptr(shape_latent), ptr(texture_latent), ptr(ws), ptr(g_rgb), ptr(g_dep), ptr(g_acc),
                                      ptr(scratch), ptr(g_c2w), ptr(g_sl), ptr(g_tl), gw_arr, stream_ptr()), "snb_render_bwd")
         out_w = tuple(gws) if need_w else tuple(None for _ in weights)
-        return (None,) * 9 + (g_c2w, None, None, g_sl if need[12] else None, g_tl if need[13] else None) + out_w
+        return (None,) * 8 + (g_c2w, None, None, g_sl if need[11] else None, g_tl if need[12] else None) + out_w
 
 
 def render_box(handle, precision, n_samples, white_bkgd, half_diag, aabb_half, px, py, K, c2w, z_steps, jitter, shape_latent,
                texture_latent, weights):
     """-> rgb (N,3), depth (N,), acc (N,), hit (N,) bool for one object (latents (1,D))."""
     flags = (WHITE_BKGD if white_bkgd else 0) | SIGMA_RELU
-    return _RenderBox.apply(handle, PREC[precision] if isinstance(precision, str) else precision, n_samples, flags, half_diag,
-                            aabb_half, px, py, K, c2w, z_steps, jitter, shape_latent, texture_latent, *weights)
+    return _RenderBox.apply(handle, PREC[precision] if isinstance(precision, str) else precision, n_samples, flags,
+                            ("box", half_diag, aabb_half), px, py, K, c2w, z_steps, jitter, shape_latent, texture_latent, *weights)
+
+
+def render_shell(handle, precision, n_samples, obj_diag, shapenet_swap, px, py, K, c2w, z_vals, shape_latent, texture_latent, weights):
+    """The utils.py stack (utils.render_rays_v2, utils.py:435-502) for one object: shared sample vector z_vals (S),
+    xyz / obj_diag, optional shapenet axis swap, utils.volume_rendering2.  -> rgb (N,3), depth (N,), acc (N,)."""
+    rgb, dep, acc, _ = _RenderBox.apply(handle, PREC[precision] if isinstance(precision, str) else precision, n_samples, SIGMA_RELU,
+                                        ("shell", obj_diag, shapenet_swap), px, py, K, c2w, z_vals, None, shape_latent,
+                                        texture_latent, *weights)
+    return rgb, dep, acc
 
 
 def box_constants(obj_sz):

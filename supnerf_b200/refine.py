@@ -1,0 +1,141 @@
+"""Refine-iteration glue around the render hot path: the test-time optimisation loop of
+``optimizer_nuscenes.py:684-769`` (identical in optimizer_kitti.py / optimizer_waymo.py) for ONE object --
+
+    rot_vec, trans_vec -> cam2opt                         (:684-699; the axis-angle map is pytorch3d's, one step upstream of the path)
+    render_rays_v2(model, ..., cam2opt, ...)              (:716-726 -> utils.py:435-502)
+    loss_rgb + loss_occ_coef * loss_occ ; backward        (:729-737)
+    AdamW step on shapecode, texturecode, rot_vec, trans_vec   (:757-769, groups/lrs of :1762-1769)
+
+-- with every host synchronisation removed so that one iteration can be captured in a CUDA graph and replayed: the
+reference reads ``cam_pose[:, -1].tolist()`` on the host every iteration to build the shared sample vector
+(utils.py:468-469 -> sample_from_rays :154-167); here near/far are evaluated on the device with the same arithmetic
+(float64 norm, float32 ``torch.linspace`` formula), and the per-iteration jitter -- drawn on the CPU generator by the
+same ``torch.rand(n_samples)`` calls, in the same order -- is uploaded once as a table.  ``ms per refine iteration``
+then is kernel time (~100 small launches replayed from one graph) instead of ~2.4 ms of Python / launch latency.
+
+The render, loss and their backward are the package's fused kernels (ops.render_shell, losses.refine_loss); the pose map
+and AdamW are ordinary torch ops captured in the same graph (torch.optim.AdamW(capturable=True)).  CUDA only."""
+import numpy as np
+import torch
+
+from . import losses, models, ops
+from . import utils as U
+
+
+def axis_angle_to_matrix(v):
+    """Rodrigues' formula, R = I + sin(t)/t [v]x + (1-cos(t))/t^2 [v]x^2 -- what pytorch3d.transforms.axis_angle_to_matrix
+    evaluates (via quaternions); pytorch3d itself is not part of the reference tree (parity unpinned there)."""
+    t = torch.sqrt((v * v).sum() + 1e-20)
+    zero = torch.zeros((), device=v.device, dtype=v.dtype)
+    kx = torch.stack([torch.stack([zero, -v[2], v[1]]), torch.stack([v[2], zero, -v[0]]), torch.stack([-v[1], v[0], zero])])
+    return torch.eye(3, device=v.device, dtype=v.dtype) + torch.sin(t) / t * kx + (1 - torch.cos(t)) / (t * t) * (kx @ kx)
+
+
+def shell_samples_on_device(cam_pose, obj_diag, n_samples, jitter):
+    """utils.sample_from_rays' shared vector (utils.py:154-167 with near/far of :468-469) without leaving the device.
+    near/far: float64 like the reference's python floats; linspace: torch's float32 formula (step = (end-start)/(n-1);
+    first half start + i*step, second half end - (n-1-i)*step); jitter (S,) = the torch.rand(n_samples) draw."""
+    n = torch.linalg.vector_norm(cam_pose[:, -1].detach().double())
+    half = float(obj_diag) / 2          # obj_diag is np.float32 in the reference: exactly representable
+    near, far = n - half, n + half
+    dist = (far - near) / (2 * n_samples)
+    start, end = (near + dist).float(), (far - dist).float()
+    step = (end - start) / (n_samples - 1) if n_samples > 1 else torch.zeros_like(start)
+    i = torch.arange(n_samples, device=cam_pose.device, dtype=torch.float32)
+    lo = start + step * i
+    hi = end - step * (n_samples - 1 - i)
+    z = torch.where(i < n_samples // 2, lo, hi)
+    return z + jitter * ((far - near) / (2 * n_samples)).float()
+
+
+class ObjectRefiner:
+    """One object's refine loop.  ``step()`` runs one iteration eagerly; ``capture()`` records it into a CUDA graph and
+    ``run(n)`` replays it.  State (codes, pose parameters, AdamW moments) lives in this object's tensors."""
+
+    def __init__(self, model, device, img, mask_occ, K, roi, obj_diag, shapecode, texturecode, rot_vec, trans_vec, n_samples=64,
+                 im_sz=32, lr_shape=0.02, lr_texture=0.02, lr_pose=0.01, loss_occ_coef=0.1, shapenet_obj_cood=True,
+                 opt_cam_pose=False, max_iters=100):
+        if not isinstance(model, models._DecoderBase):
+            raise TypeError("ObjectRefiner needs a supnerf_b200 decoder")
+        self.model, self.device = model, torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("supnerf_b200 has no CPU path")
+        dev = self.device
+        self.n_samples, self.im_sz, self.coef = int(n_samples), int(im_sz), float(loss_occ_coef)
+        self.obj_diag, self.swap, self.opt_cam_pose = np.float32(obj_diag), bool(shapenet_obj_cood), bool(opt_cam_pose)
+        self.K = K.to(dev, torch.float32)
+        self.px, self.py = U._pixel_grid_on(dev, roi, [im_sz, im_sz])
+        img, mask_occ = U._resize_targets(img, mask_occ, im_sz)          # utils.py:448-453
+        self.rgb_tgt = img.reshape(-1, 3).to(dev).contiguous()
+        self.occ = mask_occ.reshape(-1, 1).to(dev).contiguous()
+        self.shapecode = shapecode.detach().to(dev).clone().requires_grad_()
+        self.texturecode = texturecode.detach().to(dev).clone().requires_grad_()
+        self.rot_vec = rot_vec.detach().to(dev).reshape(3).clone().requires_grad_()
+        self.trans_vec = trans_vec.detach().to(dev).reshape(3).clone().requires_grad_()
+        self.opt = torch.optim.AdamW([{"params": [self.shapecode], "lr": lr_shape}, {"params": [self.texturecode], "lr": lr_texture},
+                                      {"params": [self.rot_vec], "lr": lr_pose}, {"params": [self.trans_vec], "lr": lr_pose}],
+                                     capturable=True)
+        # the reference draws torch.rand(n_samples) on the CPU generator once per iteration (utils.py:164): same calls, same order
+        self.jitter = torch.stack([torch.rand(self.n_samples) for _ in range(max_iters)]).to(dev)
+        self.it = torch.zeros((), dtype=torch.long, device=dev)
+        self.loss = torch.zeros(3, device=dev)
+        self.graph = None
+
+    def cam2opt(self):
+        rot = axis_angle_to_matrix(self.rot_vec)
+        t = self.trans_vec.unsqueeze(-1)
+        if not self.opt_cam_pose:                     # optimizer_nuscenes.py:695-697
+            rot = rot.transpose(-2, -1)
+            t = -rot @ t
+        return torch.cat((rot, t), dim=-1)
+
+    def step(self):
+        """One iteration (no host synchronisation anywhere)."""
+        self.opt.zero_grad(set_to_none=False) if self.shapecode.grad is not None else None
+        cam = self.cam2opt()
+        jit = self.jitter.index_select(0, self.it.reshape(1)).reshape(-1)
+        z = shell_samples_on_device(cam, self.obj_diag, self.n_samples, jit)
+        prec = self.model.precision or models.get_default_precision()
+        rgb, dep, acc = ops.render_shell(self.model._handle(self.device), prec, self.n_samples, float(self.obj_diag), self.swap,
+                                         self.px, self.py, self.K, cam, z, self.shapecode, self.texturecode, self.model._weights())
+        loss, l_rgb, l_occ = losses.refine_loss(rgb, acc, self.rgb_tgt, self.occ, self.coef)
+        loss.backward()
+        self.opt.step()
+        self.loss.copy_(torch.stack([loss.detach(), l_rgb, l_occ]))
+        self.it += 1
+        return self.loss
+
+    def capture(self, warmup=3):
+        """Warm up on a side stream (allocator, weight packing, AdamW state), then capture one iteration."""
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            snapshot = [t.detach().clone() for t in (self.shapecode, self.texturecode, self.rot_vec, self.trans_vec)]
+            for _ in range(warmup):
+                self.step()
+            # undo the warm-up updates: parameters, AdamW moments and step counters, iteration counter
+            with torch.no_grad():
+                for t, v in zip((self.shapecode, self.texturecode, self.rot_vec, self.trans_vec), snapshot):
+                    t.copy_(v)
+                for st in self.opt.state.values():
+                    for v in st.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
+                self.it.zero_()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.step()
+        # the capture itself does not execute: state is still the pre-capture one
+        return self
+
+    def run(self, iters):
+        """Run `iters` iterations (graph replays if captured).  Returns the last [loss, loss_rgb, loss_occ] (device tensor)."""
+        if int(iters) > self.jitter.shape[0]:
+            raise ValueError("iters exceeds the pre-drawn jitter table (max_iters)")
+        for _ in range(int(iters)):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self.step()
+        return self.loss

@@ -213,6 +213,44 @@ def _shell_samples(rays_o, viewdir, near, far, n_samples, obj_diag, shapenet_obj
     return xyz, vd, z_dev
 
 
+FUSED_RENDER = True  # render_rays* go through ops.render_shell (one autograd node, two C-ABI calls); False = staged ops
+
+
+def _can_fuse_shell(model, device, shapecode, kitti2nusc):
+    from . import models
+    return (FUSED_RENDER and isinstance(model, models._DecoderBase) and shapecode.shape[0] == 1 and not kitti2nusc
+            and torch.device(device).type == "cuda")
+
+
+def _shell_fused(model, device, px, py, K, cam_pose, obj_diag, n_samples, shapecode, texturecode, shapenet_obj_cood, sym_aug,
+                 kitti2nusc):
+    """get_rays -> sample_from_rays -> /obj_diag -> swap -> model -> volume_rendering2 (utils.py:456-500) as one autograd
+    node (callers check _can_fuse_shell first).  RNG consumption is the staged path's: torch.rand(n_samples) on the CPU
+    generator, then random.uniform if sym_aug."""
+    from . import models
+    device = torch.device(device)
+    near, far = _shell_near_far(cam_pose, obj_diag)
+    dist = (far - near) / (2 * n_samples)
+    z_vals = torch.linspace(near + dist, far - dist, n_samples).type_as(cam_pose)
+    z_vals += (torch.rand(n_samples) * (far - near) / (2 * n_samples)).type_as(cam_pose)
+    flip = bool(sym_aug) and random.uniform(0, 1) > 0.5
+    z_dev = z_vals.to(device, non_blocking=True)
+    if flip:   # rare branch: staged ops on the samples already drawn
+        rays_o, viewdir = _rays(K, cam_pose, px, py)
+        xyz, vd = ops.sample_shell(rays_o.to(device), viewdir.to(device), z_dev, float(obj_diag), False)
+        xyz = xyz * xyz.new_tensor([1., -1., 1.])
+        vd = vd * vd.new_tensor([1., -1., 1.])
+        if shapenet_obj_cood:
+            xyz, vd = _swap(xyz), _swap(vd)
+        sigmas, rgbs = model(xyz, vd, shapecode, texturecode)
+        return volume_rendering2(sigmas, rgbs, z_dev)
+    prec = model.precision or models.get_default_precision()
+    return ops.render_shell(model._handle(device), prec, n_samples, float(obj_diag), bool(shapenet_obj_cood),
+                            px.to(device, torch.float32), py.to(device, torch.float32), K.to(device, non_blocking=True),
+                            cam_pose.to(device, non_blocking=True), z_dev, shapecode.to(device, non_blocking=True),
+                            texturecode.to(device, non_blocking=True), model._weights())
+
+
 def prepare_pixel_samples(img, mask_occ, cam_pose, obj_diag, K, roi, n_rays, n_samples, shapenet_obj_cood, sym_aug, im_sz=None):
     """utils.py:330-377."""
     near, far = _shell_near_far(cam_pose, obj_diag)
@@ -238,6 +276,15 @@ def prepare_pixel_samples(img, mask_occ, cam_pose, obj_diag, K, roi, n_rays, n_s
 def render_rays(model, device, img, mask_occ, cam_pose, obj_diag, K, roi, n_samples, shapecode, texturecode,
                 shapenet_obj_cood, sym_aug, kitti2nusc=False, n_rays=2500):
     """utils.py:380-432."""
+    if _can_fuse_shell(model, device, shapecode, kitti2nusc):
+        px, py = _pixel_grid_on(torch.device(device), roi, None)
+        n_rays = np.minimum(px.numel(), n_rays)
+        random_ray_ids = np.random.permutation(px.numel())[:n_rays]
+        rgb_tgt = img.reshape(-1, 3)[random_ray_ids].to(device)
+        occ_pixels = mask_occ.reshape(-1, 1)[random_ray_ids].to(device)
+        out = _shell_fused(model, device, px[random_ray_ids], py[random_ray_ids], K, cam_pose, obj_diag, n_samples, shapecode,
+                           texturecode, shapenet_obj_cood, sym_aug, kitti2nusc)
+        return out[0], out[1], out[2], rgb_tgt, occ_pixels
     rays_o, viewdir = get_rays(K, cam_pose, roi)
     n_rays = np.minimum(rays_o.shape[0], n_rays)
     random_ray_ids = np.random.permutation(rays_o.shape[0])[:n_rays]
@@ -256,6 +303,20 @@ def render_rays(model, device, img, mask_occ, cam_pose, obj_diag, K, roi, n_samp
 def render_rays_v2(model, device, img, mask_occ, cam_pose, obj_diag, K, roi, n_samples, shapecode, texturecode,
                    shapenet_obj_cood, sym_aug, kitti2nusc=False, im_sz=64, n_rays=None):
     """utils.py:435-502 — the render every refine iteration calls (optimizer_nuscenes.py:716-726)."""
+    if _can_fuse_shell(model, device, shapecode, kitti2nusc):
+        px, py = _pixel_grid_on(torch.device(device), roi, [im_sz, im_sz])
+        img, mask_occ = _resize_targets(img, mask_occ, im_sz)
+        rgb_tgt = img.reshape(-1, 3).to(device, non_blocking=True)
+        occ_pixels = mask_occ.reshape(-1, 1).to(device, non_blocking=True)
+        if n_rays is not None:
+            n_rays = np.minimum(px.numel(), n_rays)
+            random_ray_ids = np.random.permutation(px.numel())[:n_rays]
+            px, py = px[random_ray_ids], py[random_ray_ids]
+            rgb_tgt = rgb_tgt[random_ray_ids]
+            occ_pixels = occ_pixels[random_ray_ids]
+        out = _shell_fused(model, device, px, py, K, cam_pose, obj_diag, n_samples, shapecode, texturecode, shapenet_obj_cood,
+                           sym_aug, kitti2nusc)
+        return out[0], out[1], out[2], rgb_tgt, occ_pixels
     rays_o, viewdir = get_rays(K, cam_pose, roi, uv_steps=[im_sz, im_sz])
     img, mask_occ = _resize_targets(img, mask_occ, im_sz)
     rgb_tgt = img.reshape(-1, 3).to(device)
@@ -278,6 +339,14 @@ def render_rays_v2(model, device, img, mask_occ, cam_pose, obj_diag, K, roi, n_s
 def render_rays_specified(model, device, img, mask_occ, cam_pose, obj_diag, K, roi, x_vec, y_vec, n_samples, shapecode,
                           texturecode, shapenet_obj_cood, sym_aug, kitti2nusc=False):
     """utils.py:504-551."""
+    if _can_fuse_shell(model, device, shapecode, kitti2nusc):
+        px = torch.from_numpy(np.asarray(x_vec + roi[0].numpy())).t().reshape(-1)
+        py = torch.from_numpy(np.asarray(y_vec + roi[1].numpy())).t().reshape(-1)
+        rgb_tgt = img[y_vec, x_vec, :].to(device)
+        occ_pixels = mask_occ[y_vec, x_vec, :].to(device)
+        out = _shell_fused(model, device, px, py, K, cam_pose, obj_diag, n_samples, shapecode, texturecode, shapenet_obj_cood,
+                           sym_aug, kitti2nusc)
+        return out[0], out[1], out[2], rgb_tgt, occ_pixels
     rays_o, viewdir = get_rays_specified(K, cam_pose, x_vec + roi[0].numpy(), y_vec + roi[1].numpy())
     rgb_tgt = img[y_vec, x_vec, :].to(device)
     occ_pixels = mask_occ[y_vec, x_vec, :].to(device)

@@ -467,3 +467,105 @@ def test_refine_loss_kernel_vs_oracle(n):
     assert rel_err(half, 0.5 * l64[0]) < TOL
     with pytest.raises(S._lib.SnbError):
         S.losses.refine_loss(rgb, acc, tgt, occ)   # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("n_rays,sym", [(None, 0), (512, 1)])
+def test_fused_shell_render_equals_staged_ops(prec, n_rays, sym):
+    """utils.render_rays_v2 (the refine loops' render, utils.py:435) through the fused C-ABI entry points in shell mode vs
+    the staged ops: same bits forward (same kernels), gradients to 1e-5; with sym_aug the flip draw must be consumed alike."""
+    import random
+    S = snb()
+    obj = oracle.synthetic_object(35, im_sz=32)
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=35)
+    m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
+    m.precision = prec
+    if prec == "bf16":
+        m.requires_grad_(False)
+    shp0, tex0 = oracle.synthetic_latents(35, 1)
+    diag = np.linalg.norm(obj["wlh"]).astype(np.float32)
+    out = {}
+    for fused in (True, False):
+        S.utils.FUSED_RENDER = fused
+        try:
+            for trial in range(3 if sym else 1):   # several draws so that both flip outcomes occur
+                cam = obj["cam_pose"].to(DEV).requires_grad_()
+                shp, tex = shp0.to(DEV).requires_grad_(), tex0.to(DEV).requires_grad_()
+                m.zero_grad()
+                np.random.seed(5 + trial); torch.manual_seed(9 + trial); random.seed(11 + trial)
+                rgb, dep, acc, tgt, occ = S.utils.render_rays_v2(m, DEV, obj["img"], obj["mask_occ"], cam, diag, obj["K"].to(DEV), obj["roi"],
+                                                                 64, shp, tex, 1, sym, im_sz=32, n_rays=n_rays)
+                oracle.refine_losses(rgb, acc, tgt, occ)[0].backward()
+                out[(fused, trial)] = [rgb, dep, acc, tgt, occ, cam.grad, shp.grad, tex.grad]
+        finally:
+            S.utils.FUSED_RENDER = True
+    for (fused, trial), vals in out.items():
+        if not fused:
+            continue
+        ref = out[(False, trial)]
+        for a, b in zip(vals[:5], ref[:5]):
+            assert torch.equal(a, b)
+        for a, b in zip(vals[5:], ref[5:]):
+            assert rel_err(a, b) < 1e-5
+
+
+def test_object_refiner_matches_reference_api_loop_and_graph_replay():
+    """refine.ObjectRefiner (device-side shell bounds, capturable AdamW, optional CUDA graph) against the loop written with
+    the reference-shaped API (render_rays_v2 with host-side near/far + the inline losses + torch AdamW), 6 iterations."""
+    S = snb()
+    import tools.refine_bench as rb
+    obj = oracle.synthetic_object(51, im_sz=32)
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=51)
+    m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
+    m.requires_grad_(False)
+    shp0, tex0 = oracle.synthetic_latents(51, 1)
+    diag = np.linalg.norm(obj["wlh"]).astype(np.float32)
+    c2o = obj["cam_pose"]
+    R_obj = c2o[:, :3].t().contiguous()
+    t_obj = -(R_obj @ c2o[:, 3:]).reshape(3)
+    rv0 = rb.matrix_to_axis_angle(R_obj)
+    iters = 6
+    # reference-API loop
+    shp, tex = shp0.to(DEV).requires_grad_(), tex0.to(DEV).requires_grad_()
+    rv, tv = rv0.to(DEV).requires_grad_(), t_obj.to(DEV).requires_grad_()
+    opt = torch.optim.AdamW([{"params": shp, "lr": 0.02}, {"params": tex, "lr": 0.02}, {"params": rv, "lr": 0.01}, {"params": tv, "lr": 0.01}])
+    torch.manual_seed(77)
+    for _ in range(iters):
+        opt.zero_grad()
+        rot = S.refine.axis_angle_to_matrix(rv).t()
+        cam = torch.cat((rot, -rot @ tv.unsqueeze(-1)), -1)
+        rgb, dep, acc, tgt, occ = S.utils.render_rays_v2(m, DEV, obj["img"], obj["mask_occ"], cam, diag, obj["K"].to(DEV), obj["roi"], 64,
+                                                         shp, tex, 1, 0, im_sz=32, n_rays=None)
+        loss_ref = oracle.refine_losses(rgb, acc, tgt, occ)[0]
+        loss_ref.backward()
+        opt.step()
+    outs = []
+    for graphed in (False, True):
+        torch.manual_seed(77)   # the refiner pre-draws the same torch.rand(64) sequence
+        r = S.refine.ObjectRefiner(m, DEV, obj["img"], obj["mask_occ"], obj["K"], obj["roi"], diag, shp0, tex0, rv0, t_obj, n_samples=64,
+                                   im_sz=32, max_iters=iters)
+        if graphed:
+            r.capture()
+        last = r.run(iters)
+        torch.cuda.synchronize()
+        outs.append((r, last.clone()))
+        assert rel_err(last[0], loss_ref) < 1e-4
+        # Adam's g / sqrt(v) turns last-ulp differences of near-zero gradient components into O(lr) parameter differences:
+        # the codes are compared at 2e-2 of their scale, the loss trajectory and the (well-conditioned) pose tightly
+        assert rel_err(r.shapecode, shp) < 2e-2 and rel_err(r.texturecode, tex) < 2e-2
+        assert rel_err(r.rot_vec, rv) < 1e-3 and rel_err(r.trans_vec, tv) < 1e-3
+    assert rel_err(outs[1][0].shapecode, outs[0][0].shapecode) < 2e-2 and rel_err(outs[1][1], outs[0][1]) < 1e-4
+
+
+def test_device_side_shell_samples_match_host_built_vector():
+    """refine.shell_samples_on_device vs the reference's host arithmetic (utils.py:154-167, :468-469)."""
+    S = snb()
+    for seed in range(5):
+        obj = oracle.synthetic_object(60 + seed, im_sz=8)
+        diag = np.linalg.norm(obj["wlh"]).astype(np.float32)
+        jit = torch.rand(64, generator=torch.Generator().manual_seed(seed))
+        near, far = oracle.shell_bounds(obj["cam_pose"], float(diag))
+        dist = (far - near) / (2 * 64)
+        z_ref = torch.linspace(near + dist, far - dist, 64) + jit * (far - near) / (2 * 64)
+        z = S.refine.shell_samples_on_device(obj["cam_pose"].to(DEV), diag, 64, jit.to(DEV))
+        assert rel_err(z, z_ref) < 2e-7
