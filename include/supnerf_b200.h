@@ -30,7 +30,9 @@ extern "C" {
 
 /* MLP arithmetic */
 #define SNB_PREC_FP32 0 /* SIMT FFMA, fp32 everywhere: the 1e-5 parity mode */
-#define SNB_PREC_BF16 1 /* tcgen05 bf16 x bf16 -> fp32 TMEM accumulators: the 2e-2 throughput mode */
+#define SNB_PREC_BF16 1 /* tcgen05 bf16 x bf16 -> fp32 TMEM accumulators: the 2e-2 throughput mode (weights frozen) */
+#define SNB_PREC_BF16_TRAIN 2 /* the same arithmetic; the forward/backward additionally keep every layer's operand tiles in the
+                                 workspace / scratch so that snb_mlp_bwd can produce all weight gradients on the tensor core */
 
 typedef struct snb_handle_s* snb_handle;
 

@@ -40,11 +40,13 @@ int tc_timing_read(int which, float* ms, int max_n);
 size_t tc_workspace_bytes(const snb_handle_s* h, int64_t M, int64_t B);
 size_t tc_bwd_scratch_bytes(const snb_handle_s* h, int64_t M, int64_t B);
 int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
-               const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, void* ws, cudaStream_t st);
+               const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, void* ws, cudaStream_t st, bool train);
 int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                 const float* shape_latent, const float* texture_latent, const float* sigma, const float* g_sigma,
                 const float* g_rgb, const void* ws, void* scratch, float* g_xyz, float* g_viewdir, float* g_shape_latent,
-                float* g_texture_latent, float* const* g_weights, cudaStream_t st);
+                float* g_texture_latent, float* const* g_weights, cudaStream_t st, bool train);
+size_t tc_train_workspace_extra(const snb_handle_s* h, int64_t M);
+size_t tc_train_scratch_extra(const snb_handle_s* h, int64_t M);
 
 }  // namespace snb
 
@@ -151,7 +153,8 @@ extern "C" int snb_pack_weights(snb_handle h, void* packed, void* stream) {
 static int check_mlp_args(snb_handle h, int32_t precision, int64_t M, int64_t B) {
   SNB_REQUIRE(h != nullptr, "mlp: null handle");
   SNB_REQUIRE(h->weights_set, "mlp: weights not set");
-  SNB_REQUIRE(precision == SNB_PREC_FP32 || precision == SNB_PREC_BF16, "mlp: unknown precision %d", precision);
+  SNB_REQUIRE(precision == SNB_PREC_FP32 || precision == SNB_PREC_BF16 || precision == SNB_PREC_BF16_TRAIN,
+              "mlp: unknown precision %d", precision);
   SNB_REQUIRE(M >= 0 && B >= 1 && M % B == 0, "mlp: n_rows (%lld) must be a multiple of n_objs (%lld)", (long long)M, (long long)B);
   SNB_REQUIRE(sm_count() > 0, "mlp: no CUDA device (there is no CPU fallback)");
   return 0;
@@ -160,12 +163,14 @@ static int check_mlp_args(snb_handle h, int32_t precision, int64_t M, int64_t B)
 extern "C" size_t snb_mlp_workspace_bytes(snb_handle h, int64_t M, int64_t B, int32_t precision) {
   if (!h) return 0;
   if (precision == SNB_PREC_BF16) return tc_workspace_bytes(h, M, B);
+  if (precision == SNB_PREC_BF16_TRAIN) return tc_workspace_bytes(h, M, B) + tc_train_workspace_extra(h, M);
   return f32_workspace_floats(h, M, B) * sizeof(float);
 }
 
 extern "C" size_t snb_mlp_bwd_scratch_bytes(snb_handle h, int64_t M, int64_t B, int32_t precision) {
   if (!h) return 0;
   if (precision == SNB_PREC_BF16) return tc_bwd_scratch_bytes(h, M, B);
+  if (precision == SNB_PREC_BF16_TRAIN) return tc_bwd_scratch_bytes(h, M, B) + tc_train_scratch_extra(h, M);
   return f32_bwd_scratch_floats(h, M, B) * sizeof(float);
 }
 
@@ -175,8 +180,9 @@ extern "C" int snb_mlp_fwd(snb_handle h, int32_t precision, const float* xyz, co
   if (check_mlp_args(h, precision, M, B)) return 2;
   if (M == 0) return 0;
   SNB_REQUIRE(xyz && viewdir && shape_latent && texture_latent && sigma && rgb && workspace, "mlp_fwd: null pointer");
-  if (precision == SNB_PREC_BF16)
-    return tc_forward(h, xyz, viewdir, M, B, shape_latent, texture_latent, sigma, rgb, workspace, (cudaStream_t)stream);
+  if (precision != SNB_PREC_FP32)
+    return tc_forward(h, xyz, viewdir, M, B, shape_latent, texture_latent, sigma, rgb, workspace, (cudaStream_t)stream,
+                      precision == SNB_PREC_BF16_TRAIN);
   return f32_forward(h, xyz, viewdir, M, B, shape_latent, texture_latent, sigma, rgb, (float*)workspace, (cudaStream_t)stream);
 }
 
@@ -189,9 +195,10 @@ extern "C" int snb_mlp_bwd(snb_handle h, int32_t precision, const float* xyz, co
   if (M == 0) return 0;
   SNB_REQUIRE(xyz && viewdir && shape_latent && texture_latent && sigma && g_sigma && g_rgb && workspace && scratch,
               "mlp_bwd: null pointer");
-  if (precision == SNB_PREC_BF16)
+  if (precision != SNB_PREC_FP32)
     return tc_backward(h, xyz, viewdir, M, B, shape_latent, texture_latent, sigma, g_sigma, g_rgb, workspace, scratch, g_xyz,
-                       g_viewdir, g_shape_latent, g_texture_latent, g_weights, (cudaStream_t)stream);
+                       g_viewdir, g_shape_latent, g_texture_latent, g_weights, (cudaStream_t)stream,
+                       precision == SNB_PREC_BF16_TRAIN);
   return f32_backward(h, xyz, viewdir, M, B, shape_latent, texture_latent, sigma, g_sigma, g_rgb, (const float*)workspace,
                       (float*)scratch, g_xyz, g_viewdir, g_shape_latent, g_texture_latent, g_weights, (cudaStream_t)stream);
 }

@@ -50,6 +50,8 @@ int latent_forward_fused(const snb_handle_s* h, int64_t B, const float* shape_la
 // they are first folded through W_layer^T into fold_tmp (same size as dz).
 int latent_backward_fused(const snb_handle_s* h, int64_t B, const float* zlat, const float* dz, float* g_shape_latent,
                           float* g_texture_latent, cudaStream_t st, float* fold_tmp = nullptr);
+// dz[slot][b][i] = sum_o W_layer[o][i] s_lat[slot][b][o]  (the W^T fold of the two-tile backward's column sums)
+int latent_fold(const snb_handle_s* h, int64_t B, const float* s_lat, float* dz, cudaStream_t st);
 // dz holds d loss / d zlat (post-ReLU outputs) and is overwritten by the pre-activation gradient.
 int latent_backward(const snb_handle_s* h, int64_t B, const float* shape_latent, const float* texture_latent,
                     const float* zlat, float* dz, float* g_shape_latent, float* g_texture_latent, float* const* g_weights,

@@ -166,6 +166,15 @@ int latent_forward_fused(const snb_handle_s* h, int64_t B, const float* shape_la
   return 0;
 }
 
+int latent_fold(const snb_handle_s* h, int64_t B, const float* s_lat, float* dz, cudaStream_t st) {
+  LatentLayers L;
+  if (fill_layers(h, L)) return 2;
+  dim3 gridf(L.n_total, (unsigned)B, (unsigned)((L.W + 31) / 32));
+  latent_fold_kernel<<<gridf, 1024, 0, st>>>(L, B, s_lat, dz);
+  SNB_LAUNCH_CHECK();
+  return 0;
+}
+
 int latent_backward_fused(const snb_handle_s* h, int64_t B, const float* zlat, const float* dz, float* g_shape_latent,
                           float* g_texture_latent, cudaStream_t st, float* fold_tmp) {
   LatentLayers L;

@@ -731,10 +731,15 @@ bool tc2_supported(const snb_handle_s* h);
 size_t tc2_packed_bytes(const snb_handle_s* h);
 int tc2_pack_weights(const snb_handle_s* h, void* packed, cudaStream_t st);
 int tc2_launch_fwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
-                   const uint8_t* eimg, uint32_t* masks, float* sigma, float* rgb, float* dbg, cudaStream_t st);
+                   const uint8_t* eimg, uint32_t* masks, float* sigma, float* rgb, float* dbg, uint8_t* save, cudaStream_t st);
 int tc2_launch_bwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                    const uint32_t* masks, const float* sigma, const float* g_sigma, const float* g_rgb, float* g_xyz,
-                   float* g_viewdir, float* g_zlat, cudaStream_t st);
+                   float* g_viewdir, float* g_zlat, uint8_t* save, cudaStream_t st);
+size_t tc2_fwd_save_bytes(const snb_handle_s* h, int64_t M);
+size_t tc2_bwd_save_bytes(const snb_handle_s* h, int64_t M);
+int tc2_launch_wgrad(const snb_handle_s* h, int64_t M, int64_t B, const uint8_t* fsave, const uint8_t* bsave, const float* sigma,
+                     const float* g_sigma, const float* g_rgb, const float* s_lat, const float* zlat, float* const* gw,
+                     cudaStream_t st);
 
 static size_t v1_packed_bytes(const snb_handle_s* h) { return ((size_t)build_plan(h).total_bytes + 1024 + 1023) & ~size_t(1023); }
 static bool use_v2(const snb_handle_s* h) {
@@ -778,7 +783,14 @@ size_t tc_workspace_bytes(const snb_handle_s* h, int64_t M, int64_t B) {
   const int slots = h->arch.shape_blocks + h->arch.texture_blocks + 3;
   return ws_masks_off(h, B) + (size_t)tiles_of(M) * slots * 8 * 128 * 4 + 256;
 }
-size_t tc_bwd_scratch_bytes(const snb_handle_s* h, int64_t, int64_t B) { return 2 * ws_zlat_bytes(h, B) + 256; }   // column sums + their W^T fold
+size_t tc_bwd_scratch_bytes(const snb_handle_s* h, int64_t, int64_t B) { return ((2 * ws_zlat_bytes(h, B) + 255) & ~size_t(255)) + 256; }   // column sums + their W^T fold
+// training mode (SNB_PREC_BF16_TRAIN): the operand tiles kept for the weight-gradient kernels live behind the normal
+// workspace (forward) / scratch (backward: + a d xyz / d viewdir dummy, since training runs the full backward program)
+size_t tc_train_workspace_extra(const snb_handle_s* h, int64_t M) { return tc2_supported(h) ? tc2_fwd_save_bytes(h, M) + 1024 : 0; }
+size_t tc_train_scratch_extra(const snb_handle_s* h, int64_t M) {
+  return tc2_supported(h) ? tc2_bwd_save_bytes(h, M) + (size_t)M * 24 + 1024 : 0;
+}
+static inline uint8_t* align1k(uint8_t* p) { return (uint8_t*)(((uintptr_t)p + 1023) & ~uintptr_t(1023)); }
 
 static int tc_common_checks(const snb_handle_s* h, int64_t M, int64_t B, const char* who) {
   const char* why = "";
@@ -832,8 +844,12 @@ static float* g_tc_debug_acts = nullptr;  // test hook (snb_tc_set_debug): per-s
 void tc_set_debug(float* acts) { g_tc_debug_acts = acts; }
 
 int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
-               const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, void* ws, cudaStream_t st) {
+               const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, void* ws, cudaStream_t st,
+               bool train) {
   if (tc_common_checks(h, M, B, "mlp_fwd(bf16)")) return 2;
+  SNB_REQUIRE(!train || use_v2(h), "mlp_fwd(bf16, training): weight gradients need the two-tile tcgen05 kernels (W = 256, "
+                                    "shape_blocks + texture_blocks <= 4); use precision='fp32' for this architecture");
+  uint8_t* fsave = train ? align1k((uint8_t*)ws + tc_workspace_bytes(h, M, B)) : nullptr;
   float* zlat = (float*)ws;
   float* ebias = (float*)((uint8_t*)ws + ws_zlat_bytes(h, B));
   uint32_t* masks = (uint32_t*)((uint8_t*)ws + ws_masks_off(h, B));
@@ -842,7 +858,7 @@ int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, in
   if (use_v2(h)) {
     ScopedKernelTimer tm2(st, g_timing_on);
     if (tc2_launch_fwd(h, (const uint8_t*)h->packed + v1_packed_bytes(h), xyz, viewdir, M, B, eimg, masks, sigma, rgb,
-                       g_tc_debug_acts, st)) return 1;
+                       g_tc_debug_acts, fsave, st)) return 1;
     tm2.stop(g_ev_fwd);
     SNB_LAUNCH_CHECK();
     return 0;
@@ -863,24 +879,42 @@ int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, in
 int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                 const float* shape_latent, const float* texture_latent, const float* sigma, const float* g_sigma,
                 const float* g_rgb, const void* ws, void* scratch, float* g_xyz, float* g_viewdir, float* g_shape_latent,
-                float* g_texture_latent, float* const* g_weights, cudaStream_t st) {
+                float* g_texture_latent, float* const* g_weights, cudaStream_t st, bool train) {
   if (tc_common_checks(h, M, B, "mlp_bwd(bf16)")) return 2;
-  SNB_REQUIRE(g_weights == nullptr,
-              "mlp_bwd(bf16): weight gradients are not produced by the bf16 back end; freeze the weights "
-              "(requires_grad_(False)) or use precision='fp32'");
+  SNB_REQUIRE(g_weights == nullptr || (train && use_v2(h)),
+              "mlp_bwd(bf16): weight gradients need the forward to have run in training mode (SNB_PREC_BF16_TRAIN: the python "
+              "modules select it when a weight requires grad) on an architecture the two-tile kernels cover; otherwise freeze "
+              "the weights (requires_grad_(False)) or use precision='fp32'");
   SNB_REQUIRE((g_xyz == nullptr) == (g_viewdir == nullptr), "mlp_bwd(bf16): request both g_xyz and g_viewdir or neither");
   const float* zlat = (const float*)ws;
   uint32_t* masks = (uint32_t*)((uint8_t*)ws + ws_masks_off(h, B));
   float* g_zlat = (float*)scratch;
   SNB_CHECK_CUDA(cudaMemsetAsync(g_zlat, 0, ws_zlat_bytes(h, B), st));
   if (use_v2(h)) {
+    float* fold_tmp = (float*)((uint8_t*)scratch + ws_zlat_bytes(h, B));
+    uint8_t* bsave = nullptr;
+    const bool want_w = train && g_weights != nullptr;
+    if (want_w) {   // training: keep every step's d pre-activation tile, run the full program (d xyz into a dummy if unwanted)
+      bsave = align1k((uint8_t*)scratch + tc_bwd_scratch_bytes(h, M, B));
+      float* dummy = (float*)(bsave + tc2_bwd_save_bytes(h, M));
+      if (g_xyz == nullptr) { g_xyz = dummy; g_viewdir = dummy + 3 * M; }
+      for (size_t i = 0; i < h->layers.size(); ++i) {   // every weight gradient is accumulated (atomics / +=): zero first
+        SNB_CHECK_CUDA(cudaMemsetAsync(g_weights[2 * i], 0, sizeof(float) * h->layers[i].out * h->layers[i].in, st));
+        SNB_CHECK_CUDA(cudaMemsetAsync(g_weights[2 * i + 1], 0, sizeof(float) * h->layers[i].out, st));
+      }
+    }
     ScopedKernelTimer tm2(st, g_timing_on);
     if (tc2_launch_bwd(h, (const uint8_t*)h->packed + v1_packed_bytes(h), xyz, viewdir, M, B, masks, sigma, g_sigma, g_rgb, g_xyz,
-                       g_viewdir, g_zlat, st)) return 1;
+                       g_viewdir, g_zlat, bsave, st)) return 1;
     tm2.stop(g_ev_bwd);
     SNB_LAUNCH_CHECK();
-    return latent_backward_fused(h, B, zlat, g_zlat, g_shape_latent, g_texture_latent, st,
-                                 (float*)((uint8_t*)scratch + ws_zlat_bytes(h, B)));
+    if (!want_w) return latent_backward_fused(h, B, zlat, g_zlat, g_shape_latent, g_texture_latent, st, fold_tmp);
+    const uint8_t* fsave = align1k((uint8_t*)ws + tc_workspace_bytes(h, M, B));
+    if (tc2_launch_wgrad(h, M, B, fsave, bsave, sigma, g_sigma, g_rgb, g_zlat, zlat, g_weights, st)) return 1;
+    // latent layers (per object, fp32): fold the column sums through W_layer^T into fold_tmp (= d loss / d z), then the
+    // generic backward gives d latent AND the latent layers' weight / bias gradients
+    if (latent_fold(h, B, g_zlat, fold_tmp, st)) return 1;
+    return latent_backward(h, B, shape_latent, texture_latent, zlat, fold_tmp, g_shape_latent, g_texture_latent, g_weights, st);
   }
   TcPlan pl = build_plan(h);
   Params p;

@@ -31,7 +31,7 @@ constexpr int kCluster = 2;               // CTAs per cluster: every weight stag
 constexpr uint16_t kClusterMask = (uint16_t)((1u << kCluster) - 1u);
 constexpr int kRing = 5;
 constexpr uint32_t kStageBytes = 16384;   // [256 n][32 k] bf16
-constexpr int kMaxSteps = 12;
+constexpr int kMaxSteps = 13;
 constexpr int kMaxLat = 4;                // shape_blocks + texture_blocks <= 4 (every shipped config: 3 + 1)
 
 constexpr uint32_t SM_RING = 8 * kChunkBytes;                    // A chunks [slot][4]
@@ -47,7 +47,7 @@ constexpr uint32_t SM_TOTAL = SM_BARS + 256;
 constexpr uint32_t SM_ALLOC = SM_TOTAL + 1024;                   // + alignment slack
 static_assert(SM_ALLOC <= 232448, "shared memory budget");
 
-enum Epi : int { F_RELU = 0, F_SIGMA = 1, F_PEV = 2, F_RGB = 3, B_MASK = 4, B_VD = 5, B_EV = 6, B_XYZ = 7 };
+enum Epi : int { F_RELU = 0, F_SIGMA = 1, F_PEV = 2, F_RGB = 3, B_MASK = 4, B_VD = 5, B_EV = 6, B_XYZ = 7, F_NONE = 8 };
 constexpr int BAR_WFULL = 0, BAR_WEMPTY = kRing, BAR_READY = 2 * kRing, BAR_ACC = 2 * kRing + 2;
 
 struct Step {
@@ -55,11 +55,14 @@ struct Step {
   uint16_t n_stages, n_out;  // K / 32, N
   int8_t epi, mask_slot, latent_slot, bias_row, dbg_idx, accumulate, produce_a, colsum;
   int8_t bias_stage;         // 0 none; 1 static image right after the step's weight stages; 2 per-object image of latent_slot (fwd only)
-  uint8_t pad_[3];
+  int8_t save_chunks;        // training mode: number of 16 KB A-operand chunks of this step kept for the weight-gradient kernels (0 = none)
+  uint8_t pad_[2];
+  uint32_t save_off;         // ... and their byte offset inside the tile's save block
 };
 
 struct Program {
   int n_steps, n_mask_slots;
+  uint32_t save_tile_bytes;  // size of one tile's save block (training mode)
   Step s[kMaxSteps];
 };
 
@@ -74,6 +77,7 @@ struct Params {
   const float* sigma_in; const float* g_sigma; const float* g_rgb;
   float* g_xyz; float* g_viewdir; float* g_zlat;   // g_zlat [(Bs+Bt)][B][256], accumulated with atomics
   int r0_mask_slot, n_latent;
+  uint8_t* save;      // training mode (weight gradients wanted): [tile][Program::save_tile_bytes] copies of every step's A operand
   long long* trace;   // timing experiments only: CTA 0 writes clock64 stamps [pair][step][slot][4] = READY seen, MMAs issued, ACC seen, published
   int exp_flags;   // timing experiments only (env SNB_TC_EXP): 1 = producer skips the weight copies, 4 = every stage copies the same image
   Program prog;
@@ -181,6 +185,13 @@ __device__ __forceinline__ void bulk_g2s_multicast_elect(uint32_t dst, const voi
       "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%4], %5;\n"
       "}" ::"r"(dst), "l"(src), "r"(part_bytes), "r"(total_bytes), "r"(bar), "h"(cta_mask) : "memory");
 }
+// smem -> global bulk copy of an operand tile (training mode), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n cp.async.bulk.commit_group;"
+               ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_elect(uint32_t bar) {
   asm volatile(
       "{\n"
@@ -265,7 +276,9 @@ __device__ __forceinline__ void mma_loop(const Params& p, const Smem& sm, int64_
   const uint64_t ones_desc = umma_desc_sw32(sm.base_u32 + SM_TAB + TAB_LAT);
   const bool trace = p.trace != nullptr && blockIdx.x == 0;
   int64_t tr = 0;
-  for (int64_t pair0 = (int64_t)blockIdx.x - cluster_ctarank(); pair0 < n_pairs; pair0 += gridDim.x) {
+  const int64_t crank_m = cluster_ctarank(), n_tiles_m = (p.M + kTileM - 1) / kTileM;
+  const uint32_t lane_m = threadIdx.x & 31u;
+  for (int64_t pair0 = (int64_t)blockIdx.x - crank_m; pair0 < n_pairs; pair0 += gridDim.x) {
     for (int si = 0; si < p.prog.n_steps; ++si) {
       const Step& st = p.prog.s[si];
       const uint32_t idesc = umma_idesc(128, st.n_out);
@@ -279,6 +292,13 @@ __device__ __forceinline__ void mma_loop(const Params& p, const Smem& sm, int64_
         const uint32_t d_tmem = tmem_base + slot * 256u;
         uint64_t a_desc = umma_desc(sm.chunk_u32(slot, 0));
         uint32_t acc = (uint32_t)st.accumulate;
+        bool saving = false;
+        if (p.save != nullptr && st.save_chunks > 0) {   // training mode: keep this step's A operand for the weight-gradient kernels
+          const int64_t tile = 2 * (pair0 + crank_m) + slot;
+          saving = (pair0 + crank_m) < n_pairs && tile < n_tiles_m;
+          if (saving && lane_m == 0)
+            bulk_s2g(p.save + (size_t)tile * p.prog.save_tile_bytes + st.save_off, sm.chunk_u32(slot, 0), (uint32_t)st.save_chunks * kChunkBytes);
+        }
         for (int j = 0; j < n_stages; ++j) {
           mbar_wait(sm.bar(BAR_WFULL + stage), ph);
           tc_fence_after();
@@ -293,11 +313,16 @@ __device__ __forceinline__ void mma_loop(const Params& p, const Smem& sm, int64_
           umma_bias_elect(d_tmem, ones_desc, umma_desc_sw32(sm.stage_u32(stage)), idesc, sm.bar(BAR_WEMPTY + stage));
           if (++stage == (uint32_t)kRing) { stage = 0; ph ^= 1u; }
         }
+        if (saving) {   // the epilogue overwrites the chunks after BAR_ACC: the bulk store must have read them by then
+          if (lane_m == 0) bulk_wait_read_all();
+          __syncwarp();
+        }
         umma_commit_elect(sm.bar(BAR_ACC + slot));
         if (trace) p.trace[tr + 1] = clock64();
       }
     }
   }
+  if (p.save != nullptr && lane_m == 0) bulk_wait_all();
 }
 
 __device__ __forceinline__ void kernel_prologue(Smem& sm, uint32_t tid, uint32_t warp, uint32_t& tmem_base) {
@@ -361,12 +386,12 @@ __device__ __forceinline__ uint32_t fwd_half(const Params& p, const Smem& sm, co
     if (EPI == F_SIGMA) {
       pk[2 * i4] = pack_bf16(v[0], v[1]);
       pk[2 * i4 + 1] = pack_bf16(v[2], v[3]);
-    } else if (EPI == F_RELU) {
+    } else {   // F_RELU; F_RGB only keeps it in training mode (rgb.2's input for the weight-gradient kernels)
       pk[2 * i4] = pack_bf16_relu(v[0], v[1]);
       pk[2 * i4 + 1] = pack_bf16_relu(v[2], v[3]);
     }
   }
-  if (EPI != F_RGB) store_row16(sm.chunk(e.slot, c), e.row, e.hh * 4u + (uint32_t)h * 2u, pk);
+  if (EPI != F_RGB || p.save != nullptr) store_row16(sm.chunk(e.slot, c), e.row, e.hh * 4u + (uint32_t)h * 2u, pk);
   return ((mm[0] & 0xffu) << 8) | (mm[1] & 0xffu);
 }
 
@@ -464,7 +489,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_const
         if (st.epi == F_RELU) fwd_epilogue<F_RELU, DBG>(p, sm, st, e, mask_tile, tile_ok, sig_acc, rgb_acc);
         else if (st.epi == F_SIGMA) fwd_epilogue<F_SIGMA, DBG>(p, sm, st, e, mask_tile, tile_ok, sig_acc, rgb_acc);
         else if (st.epi == F_PEV) write_pe_row<4>(sm.chunk(slot, 0), e.row, e.hh, dir);   // accumulator untouched: the next step adds to it
-        else fwd_epilogue<F_RGB, DBG>(p, sm, st, e, mask_tile, tile_ok, sig_acc, rgb_acc);
+        else if (st.epi == F_RGB) fwd_epilogue<F_RGB, DBG>(p, sm, st, e, mask_tile, tile_ok, sig_acc, rgb_acc);
+        // F_NONE (training mode's last step): no MMAs, no epilogue -- the MMA warp only copies rgb.2's input out of the A chunks
         if (!last) publish(sm, slot, lane);
         else if (has_next) {   // rgb.0's MMAs are complete and its accumulator is drained: hand the NEXT tile's PE(xyz) to the MMA warp
           write_pe_row<10>(sm.chunk(slot, 0), e.row, e.hh, xn);   // before the tile-end bookkeeping below
@@ -808,7 +834,7 @@ bool tc2_supported(const snb_handle_s* h) {
 }
 
 struct Tc2Plan {
-  tc2::Program fwd, bwd_full, bwd_noxyz;
+  tc2::Program fwd, fwd_train, bwd_full, bwd_noxyz;
   std::vector<tc2::PackJob> jobs;
   uint32_t total_bytes = 0;
   int r0_slot = 0;
@@ -887,6 +913,20 @@ static Tc2Plan build_plan2(const snb_handle_s* h) {
     add_stages(pl, ly[h->iR0].w, W, false, 128, 128, W, 8, &s.w_off);
     add_bias_stage(pl, s, ly[h->iR0].b, 128, 128);
     push(f, s);
+    // save layout (training mode): every step's A operand = that layer's input, K/64 chunks, in program order
+    uint32_t off = 0;
+    for (int i = 0; i < f.n_steps; ++i) {
+      f.s[i].save_chunks = (int8_t)((f.s[i].n_stages + 1) / 2);
+      f.s[i].save_off = off;
+      off += (uint32_t)f.s[i].save_chunks * kChunkBytes;
+    }
+    pl.fwd_train = f;
+    tc2::Step sv = mk(F_NONE, 128, 0, -1, -1, -1, -1);   // rgb.2's input: ReLU(rgb.0) left in chunks 0,1 by the F_RGB epilogue
+    sv.produce_a = 0; sv.w_off = 0; sv.save_chunks = 2; sv.save_off = off;
+    off += 2 * kChunkBytes;
+    push(pl.fwd_train, sv);
+    pl.fwd_train.save_tile_bytes = off;
+    f.save_tile_bytes = 0;
   }
   {  // ---------------- backward (B operand = W^T: n = input unit, k = output unit)
     for (int full = 0; full < 2; ++full) {
@@ -929,6 +969,16 @@ static Tc2Plan build_plan2(const snb_handle_s* h) {
         add_stages(pl, ly[h->iX].w, dx, true, dx, 64, W, 8, &s.w_off);
         push(b, s);
       }
+      // save layout (training mode uses the full program): every step's A operand = d pre-activation of the layer it goes
+      // through; the B_VD step shares encoding_viewdir's with B_EV
+      uint32_t off = 0;
+      for (int i = 0; i < b.n_steps; ++i) {
+        b.s[i].save_chunks = b.s[i].epi == B_VD ? 0 : (int8_t)((b.s[i].n_stages + 1) / 2);
+        if (!full && b.s[i].n_stages == 0) b.s[i].save_chunks = 0;
+        b.s[i].save_off = off;
+        off += (uint32_t)b.s[i].save_chunks * kChunkBytes;
+      }
+      b.save_tile_bytes = off;
     }
   }
   return pl;
@@ -1005,12 +1055,13 @@ static cudaError_t tc2_launch(K kernel, int grid, cudaStream_t st, const tc2::Pa
 }
 
 int tc2_launch_fwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
-                   const uint8_t* eimg, uint32_t* masks, float* sigma, float* rgb, float* dbg, cudaStream_t st) {
+                   const uint8_t* eimg, uint32_t* masks, float* sigma, float* rgb, float* dbg, uint8_t* save, cudaStream_t st) {
   Tc2Plan pl = build_plan2(h);
   tc2::Params p;
   fill_common2(p, h, packed2, xyz, viewdir, M, B, eimg, masks);
   p.sigma = sigma; p.rgb = rgb; p.dbg = dbg;
-  p.prog = pl.fwd;
+  p.save = save;
+  p.prog = save ? pl.fwd_train : pl.fwd;
   if (dbg) {
     SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
     SNB_CHECK_CUDA(tc2_launch(tc2_fwd_kernel<true>, tc2_grid(tc2_fwd_kernel<true>, M), st, p));
@@ -1023,15 +1074,324 @@ int tc2_launch_fwd(const snb_handle_s* h, const void* packed2, const float* xyz,
 
 int tc2_launch_bwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                    const uint32_t* masks, const float* sigma, const float* g_sigma, const float* g_rgb, float* g_xyz,
-                   float* g_viewdir, float* g_zlat, cudaStream_t st) {
+                   float* g_viewdir, float* g_zlat, uint8_t* save, cudaStream_t st) {
   Tc2Plan pl = build_plan2(h);
   tc2::Params p;
   fill_common2(p, h, packed2, xyz, viewdir, M, B, nullptr, const_cast<uint32_t*>(masks));
   p.sigma_in = sigma; p.g_sigma = g_sigma; p.g_rgb = g_rgb; p.g_xyz = g_xyz; p.g_viewdir = g_viewdir; p.g_zlat = g_zlat;
   p.r0_mask_slot = pl.r0_slot;
+  p.save = save;
+  SNB_REQUIRE(save == nullptr || g_xyz != nullptr, "tc2 backward: training mode runs the full program (g_xyz scratch required)");
   p.prog = g_xyz ? pl.bwd_full : pl.bwd_noxyz;
   SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
   SNB_CHECK_CUDA(tc2_launch(tc2_bwd_kernel, tc2_grid(tc2_bwd_kernel, M), st, p));
+  return 0;
+}
+
+// =====================================================================================================================
+// Weight gradients (training mode, SNB_PREC_BF16_TRAIN): dW_l = sum_samples dY_l^T X_l on the tensor core.
+// The forward / backward kernels above left every layer's input X_l and pre-activation gradient dY_l in HBM as the very
+// shared-memory operand images they used (128-sample tiles, 16 KB chunks of [128 samples][64 features] bf16, 128-byte
+// swizzle).  Read with samples as the K dimension those bytes are exactly tcgen05's canonical MN-MAJOR 128B-swizzled layout
+// (64 contiguous features per 128-byte row, 8-sample atoms of 1024 B), so no transposition is needed: per 16 samples one
+// MMA  D[128 out][N in] += dY^T[128 out][16] . X^T[N in][16]  with both operands MN-major.  D (two 128-row halves x 256
+// columns fp32) fills TMEM; one CTA owns (layer, tile range), accumulates over its tiles and adds its partial dW to global
+// memory with atomics.  HBM-bound: 2 x (dy_chunks + x_chunks) x 8 KB per 64 samples.  Bias gradients = column sums of dY,
+// taken by the epilogue warps from the same shared-memory pieces while the MMAs run.
+// =====================================================================================================================
+namespace tc2 {
+
+constexpr int kWThreads = 192;            // warp 0 producer, warp 1 MMA issuer (+ TMEM alloc), warps 2..5 colsum + epilogue
+constexpr int kWStages = 3;
+constexpr uint32_t kWPiece = 8192;        // half a chunk: [64 samples][64 features]
+constexpr uint32_t kWStageBytes = 8 * kWPiece;
+constexpr uint32_t SMW_BARS = kWStages * kWStageBytes;
+constexpr uint32_t SMW_ALLOC = SMW_BARS + 256 + 1024;
+constexpr int kMaxWJobs = 16;
+
+struct WJob {
+  uint32_t dy_off, x_off;        // byte offsets inside the backward / forward tile save blocks
+  int32_t dy_chunks, x_chunks;   // 64-feature chunks of dY (2 or 4) and of X (1 or 4)
+  int32_t n_out, n_in;           // valid rows / columns of dW
+  float* gw; int32_t ld, col0;   // dW (out, ld) row-major, this job's columns start at col0
+  float* gb;                     // bias gradient (n_out) or NULL
+};
+struct WParams {
+  const uint8_t* fsave; const uint8_t* bsave;
+  uint32_t f_tile_bytes, b_tile_bytes;
+  int64_t n_tiles;
+  int32_t n_jobs, splits;
+  WJob jobs[kMaxWJobs];
+};
+
+// MN-major, 128-byte-swizzled operand: 64 features per 128-byte row, consecutive samples 128 B apart, 8-sample atoms 1024 B
+// apart (SBO), next 64-feature group one piece further (LBO).
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(kWPiece >> 4) << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kWThreads, 1) tc2_wgrad_kernel(const __grid_constant__ WParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
+  uint8_t* base = smem_raw + pad;
+  const uint32_t base_u32 = raw + pad;
+  auto bar = [&](int i) { return base_u32 + SMW_BARS + 8u * (uint32_t)i; };   // full[0..2], empty[3..5], done[6]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base + SMW_BARS + 128);
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const WJob& jb = p.jobs[blockIdx.x / p.splits];
+  const int split = blockIdx.x % p.splits;
+  if (tid == 0) {
+    for (int i = 0; i < kWStages; ++i) { mbar_init(bar(i), 1); mbar_init(bar(kWStages + i), 1 + 4); }
+    mbar_init(bar(2 * kWStages), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_pieces = jb.dy_chunks + jb.x_chunks;
+  const int64_t my_tiles = p.n_tiles > split ? (p.n_tiles - split + p.splits - 1) / p.splits : 0;
+  const int64_t n_iters = my_tiles * 2;   // half tiles
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- producer: one 64-sample half tile per stage
+    uint32_t stage = 0, ph = 0;
+    for (int64_t it = 0; it < n_iters; ++it) {
+      const int64_t tile = split + (it >> 1) * p.splits;
+      const uint32_t ht = (uint32_t)(it & 1);
+      mbar_wait(bar(kWStages + stage), ph ^ 1u);
+      if (lane == 0) {
+        mbar_expect_tx(bar(stage), (uint32_t)n_pieces * kWPiece);
+        const uint8_t* dy = p.bsave + (size_t)tile * p.b_tile_bytes + jb.dy_off + ht * kWPiece;
+        const uint8_t* xx = p.fsave + (size_t)tile * p.f_tile_bytes + jb.x_off + ht * kWPiece;
+        const uint32_t dst = base_u32 + stage * kWStageBytes;
+        for (int c = 0; c < jb.dy_chunks; ++c) bulk_g2s(dst + (uint32_t)c * kWPiece, dy + (size_t)c * kChunkBytes, kWPiece, bar(stage));
+        for (int c = 0; c < jb.x_chunks; ++c)
+          bulk_g2s(dst + (uint32_t)(jb.dy_chunks + c) * kWPiece, xx + (size_t)c * kChunkBytes, kWPiece, bar(stage));
+      }
+      __syncwarp();
+      if (++stage == (uint32_t)kWStages) { stage = 0; ph ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    const uint32_t n_cols = (uint32_t)jb.x_chunks * 64u;
+    const uint32_t idesc = umma_idesc(128, n_cols) | (1u << 15) | (1u << 16);   // A and B MN-major
+    const int n_halves = jb.dy_chunks / 2;
+    uint32_t stage = 0, ph = 0;
+    for (int64_t it = 0; it < n_iters; ++it) {
+      mbar_wait(bar(stage), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sb = base_u32 + stage * kWStageBytes;
+        for (int ks = 0; ks < 4; ++ks) {          // 16 samples per MMA: two 8-sample atoms
+          const uint64_t b_desc = umma_desc_mn(sb + (uint32_t)jb.dy_chunks * kWPiece + (uint32_t)ks * 2048u);
+          for (int hf = 0; hf < n_halves; ++hf) {
+            const uint64_t a_desc = umma_desc_mn(sb + (uint32_t)(2 * hf) * kWPiece + (uint32_t)ks * 2048u);
+            umma_bf16(tmem_base + (uint32_t)hf * 256u, a_desc, b_desc, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(bar(kWStages + stage));
+      }
+      __syncwarp();
+      if (++stage == (uint32_t)kWStages) { stage = 0; ph ^= 1u; }
+    }
+    if (lane == 0) umma_commit(bar(2 * kWStages));
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------- bias column sums during the loop, then the epilogue
+    const uint32_t w4 = warp - 2;                 // 0..3: dY piece this warp sums
+    float acc[2][8];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[a][i] = 0.f;
+    const uint32_t rsub = ((lane >> 3) & 3u) + 4u * ((lane >> 2) & 1u);
+    const bool do_sum = jb.gb != nullptr && (int)w4 < jb.dy_chunks;
+    uint32_t stage = 0, ph = 0;
+    for (int64_t it = 0; it < n_iters; ++it) {
+      mbar_wait(bar(stage), ph);
+      if (do_sum) {
+        const uint8_t* piece = base + stage * kWStageBytes + w4 * kWPiece;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const uint32_t unit = (uint32_t)a * 4u + (lane & 3u);
+#pragma unroll 4
+          for (uint32_t g = 0; g < 8; ++g) {
+            const uint4 q = *reinterpret_cast<const uint4*>(piece + swz(g * 8u + rsub, unit));
+            acc[a][0] += __uint_as_float(q.x << 16); acc[a][1] += __uint_as_float(q.x & 0xffff0000u);
+            acc[a][2] += __uint_as_float(q.y << 16); acc[a][3] += __uint_as_float(q.y & 0xffff0000u);
+            acc[a][4] += __uint_as_float(q.z << 16); acc[a][5] += __uint_as_float(q.z & 0xffff0000u);
+            acc[a][6] += __uint_as_float(q.w << 16); acc[a][7] += __uint_as_float(q.w & 0xffff0000u);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kWStages + stage));
+      if (++stage == (uint32_t)kWStages) { stage = 0; ph ^= 1u; }
+    }
+    if (do_sum) {
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+#pragma unroll
+        for (int o = 4; o >= 1; o >>= 1) {
+          const bool upper = (lane & (uint32_t)(4 * o)) != 0;
+#pragma unroll
+          for (int i = 0; i < o; ++i) {
+            const float keep = upper ? acc[a][i + o] : acc[a][i];
+            const float send = upper ? acc[a][i] : acc[a][i + o];
+            acc[a][i] = keep + __shfl_xor_sync(0xffffffffu, send, 4 * o);
+          }
+        }
+        const uint32_t idx = ((lane >> 4) & 1u) * 4u + ((lane >> 3) & 1u) * 2u + ((lane >> 2) & 1u);
+        const int col = (int)(w4 * 64u + ((uint32_t)a * 4u + (lane & 3u)) * 8u + idx);
+        if (col < jb.n_out && n_iters > 0) atomicAdd(jb.gb + col, acc[a][0]);
+      }
+    }
+    // epilogue: this warp owns TMEM lanes 32 (warp % 4) ..: rows of dW
+    mbar_wait(bar(2 * kWStages), 0u);
+    tc_fence_after();
+    if (n_iters > 0) {
+      const uint32_t q4 = warp & 3u;
+      const int n_halves = jb.dy_chunks / 2, n_cols = jb.x_chunks * 64;
+      for (int hf = 0; hf < n_halves; ++hf) {
+        const int row = hf * 128 + (int)(q4 * 32u + lane);
+        for (int c0 = 0; c0 < n_cols; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + (uint32_t)hf * 256u + (uint32_t)c0 + ((q4 * 32u) << 16), r);
+          if (row < jb.n_out) {
+            float* dst = jb.gw + (size_t)row * jb.ld + jb.col0 + c0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c0 + i < jb.n_in) atomicAdd(dst + i, __uint_as_float(r[i]));
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// dW_layer[o][i] += sum_obj s[slot][obj][o] * z[slot][obj][i]: the per-object latent vector z is part of the consuming
+// layer's input (x + z), but the tensor-core path only saw x (z was folded into the bias).  grid (slots, W), block W.
+struct OuterJobs { int n; float* gw[kMaxLat]; };
+__global__ void __launch_bounds__(256) wgrad_latent_outer_kernel(const __grid_constant__ OuterJobs J, int64_t B, int W,
+                                                                const float* __restrict__ s, const float* __restrict__ z) {
+  const int slot = blockIdx.x, o = blockIdx.y, i = threadIdx.x;
+  if (i >= W) return;
+  float acc = 0.f;
+  for (int64_t b = 0; b < B; ++b) acc = fmaf(s[((size_t)slot * B + b) * W + o], z[((size_t)slot * B + b) * W + i], acc);
+  J.gw[slot][(size_t)o * W + i] += acc;
+}
+
+// sigma head and rgb.2 on CUDA cores from the saved operand images: y = encoding_shape output (4 chunks), h = ReLU(rgb.0) (2 chunks)
+//   d w_sigma[i] = sum_s gsp[s] y[s][i],  d b_sigma = sum_s gsp[s];  d W2[k][j] = sum_s g_rgb[s][k] h[s][j],  d b2[k] = sum_s g_rgb[s][k]
+__global__ void __launch_bounds__(256) wgrad_heads_kernel(const uint8_t* __restrict__ fsave, uint32_t f_tile_bytes, uint32_t y_off,
+                                                         uint32_t h_off, int64_t n_tiles, int64_t M, const float* __restrict__ sigma,
+                                                         const float* __restrict__ g_sigma, const float* __restrict__ g_rgb,
+                                                         float* __restrict__ gw_sig, float* __restrict__ gb_sig,
+                                                         float* __restrict__ gw2, float* __restrict__ gb2) {
+  __shared__ float gs[128], g3[128][3];
+  const int i = threadIdx.x;   // column of y (256); threads < 128 also own column i of h
+  const uint32_t cy = (uint32_t)i >> 6, uy = ((uint32_t)i & 63u) >> 3, ey = (uint32_t)i & 7u;
+  float a_sig = 0.f, a_b = 0.f, a2[3] = {0.f, 0.f, 0.f}, a_b2 = 0.f;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    __syncthreads();
+    if (i < 128) {
+      const int64_t r = tile * 128 + i;
+      const bool ok = r < M;
+      gs[i] = ok ? __ldg(g_sigma + r) * (-expm1f(-__ldg(sigma + r))) : 0.f;
+      g3[i][0] = ok ? __ldg(g_rgb + 3 * r) : 0.f; g3[i][1] = ok ? __ldg(g_rgb + 3 * r + 1) : 0.f; g3[i][2] = ok ? __ldg(g_rgb + 3 * r + 2) : 0.f;
+    }
+    __syncthreads();
+    const uint8_t* ty = fsave + (size_t)tile * f_tile_bytes + y_off + (size_t)cy * kChunkBytes;
+    const uint8_t* th = fsave + (size_t)tile * f_tile_bytes + h_off + (size_t)cy * kChunkBytes;
+    for (uint32_t s = 0; s < 128; ++s) {
+      const float yv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(ty + swz(s, uy) + ey * 2u));
+      a_sig = fmaf(gs[s], yv, a_sig);
+      if (i < 128) {
+        const float hv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(th + swz(s, uy) + ey * 2u));
+        a2[0] = fmaf(g3[s][0], hv, a2[0]); a2[1] = fmaf(g3[s][1], hv, a2[1]); a2[2] = fmaf(g3[s][2], hv, a2[2]);
+      }
+      if (i == 0) a_b += gs[s];
+      if (i >= 1 && i <= 3) a_b2 += g3[s][i - 1];
+    }
+  }
+  atomicAdd(gw_sig + i, a_sig);
+  if (i < 128) { atomicAdd(gw2 + i, a2[0]); atomicAdd(gw2 + 128 + i, a2[1]); atomicAdd(gw2 + 256 + i, a2[2]); }
+  if (i == 0) atomicAdd(gb_sig, a_b);
+  if (i >= 1 && i <= 3) atomicAdd(gb2 + (i - 1), a_b2);
+}
+
+}  // namespace tc2
+
+size_t tc2_fwd_save_bytes(const snb_handle_s* h, int64_t M) {
+  return (size_t)((M + kTileM - 1) / kTileM) * build_plan2(h).fwd_train.save_tile_bytes;
+}
+size_t tc2_bwd_save_bytes(const snb_handle_s* h, int64_t M) {
+  return (size_t)((M + kTileM - 1) / kTileM) * build_plan2(h).bwd_full.save_tile_bytes;
+}
+
+// All weight / bias gradients of the decoder layers that run on the tensor core, the two heads, and the z (x) s outer products
+// of the latent-consuming layers.  g_weights: canonical order (2 per layer), already zeroed.  s_lat: the per-object column sums
+// [(Bs+Bt)][B][256] the backward kernel produced; zlat: the forward's per-object latent activations.
+int tc2_launch_wgrad(const snb_handle_s* h, int64_t M, int64_t B, const uint8_t* fsave, const uint8_t* bsave, const float* sigma,
+                     const float* g_sigma, const float* g_rgb, const float* s_lat, const float* zlat, float* const* gw,
+                     cudaStream_t st) {
+  Tc2Plan pl = build_plan2(h);
+  const tc2::Program& F = pl.fwd_train;
+  const tc2::Program& Bp = pl.bwd_full;
+  const int Bs = h->arch.shape_blocks, Bt = h->arch.texture_blocks, W = 256, dv = h->d_dir(), dx = h->d_xyz();
+  // forward step indices: 0 X | 1..Bs S_j | Bs+1 ES | Bs+2 EVy | Bs+3 EVdir | Bs+4.. T_j | Bs+Bt+4 R0 | Bs+Bt+5 rgb.2 input
+  // backward (full) step indices: 0 R0 | 1..Bt T_j (j = Bt..1) | Bt+1 VD | Bt+2 EV | Bt+3 ES | Bt+4.. S_j (j = Bs..1) | Bs+Bt+4 XYZ
+  auto fX = [&](int step) { return F.s[step].save_off; };
+  auto bY = [&](int step) { return Bp.s[step].save_off; };
+  tc2::WParams p{};
+  p.fsave = fsave; p.bsave = bsave; p.f_tile_bytes = F.save_tile_bytes; p.b_tile_bytes = Bp.save_tile_bytes;
+  p.n_tiles = (M + kTileM - 1) / kTileM;
+  int nj = 0;
+  auto add = [&](int layer, int col0, int ld, uint32_t dy_off, int dy_chunks, int n_out, uint32_t x_off, int x_chunks, int n_in, bool bias) {
+    tc2::WJob& j = p.jobs[nj++];
+    j.dy_off = dy_off; j.dy_chunks = dy_chunks; j.n_out = n_out; j.x_off = x_off; j.x_chunks = x_chunks; j.n_in = n_in;
+    j.gw = gw[2 * layer]; j.ld = ld; j.col0 = col0; j.gb = bias ? gw[2 * layer + 1] : nullptr;
+  };
+  add(h->iX, 0, dx, bY(Bs + Bt + 4), 4, W, fX(0), 1, dx, true);
+  for (int j = 1; j <= Bs; ++j) add(h->iS(j), 0, W, bY(Bt + 4 + (Bs - j)), 4, W, fX(j), 4, W, true);
+  add(h->iES, 0, W, bY(Bt + 3), 4, W, fX(Bs + 1), 4, W, true);
+  add(h->iEV, 0, W + dv, bY(Bt + 2), 4, W, fX(Bs + 2), 4, W, true);
+  add(h->iEV, W, W + dv, bY(Bt + 2), 4, W, fX(Bs + 3), 1, dv, false);
+  for (int j = 1; j <= Bt; ++j) add(h->iT(j), 0, W, bY(1 + (Bt - j)), 4, W, fX(Bs + 3 + j), 4, W, true);
+  add(h->iR0, 0, W, bY(0), 2, W / 2, fX(Bs + Bt + 4), 4, W, true);
+  SNB_REQUIRE(nj <= tc2::kMaxWJobs, "wgrad: too many jobs");
+  p.n_jobs = nj;
+  const int sms = sm_count();
+  int splits = sms / nj;
+  if (splits < 1) splits = 1;
+  if ((int64_t)splits > p.n_tiles) splits = (int)p.n_tiles;
+  p.splits = splits;
+  SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2::tc2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2::SMW_ALLOC));
+  tc2::tc2_wgrad_kernel<<<nj * splits, tc2::kWThreads, tc2::SMW_ALLOC, st>>>(p);
+  SNB_LAUNCH_CHECK();
+  // z (x) s outer products of the latent-consuming layers
+  tc2::OuterJobs oj{};
+  oj.n = Bs + Bt;
+  for (int j = 1; j <= Bs + Bt; ++j) oj.gw[j - 1] = gw[2 * (j <= Bs ? h->iS(j) : h->iT(j - Bs))];
+  tc2::wgrad_latent_outer_kernel<<<dim3((unsigned)(Bs + Bt), (unsigned)W), 256, 0, st>>>(oj, B, W, s_lat, zlat);
+  SNB_LAUNCH_CHECK();
+  // heads
+  const int64_t nt = p.n_tiles;
+  const int grid = (int)(nt < 2 * sms ? nt : 2 * sms);
+  tc2::wgrad_heads_kernel<<<grid, 256, 0, st>>>(fsave, F.save_tile_bytes, fX(Bs + 2), fX(Bs + Bt + 5), nt, M, sigma, g_sigma, g_rgb,
+                                               gw[2 * h->iSG], gw[2 * h->iSG + 1], gw[2 * h->iR2], gw[2 * h->iR2 + 1]);
+  SNB_LAUNCH_CHECK();
   return 0;
 }
 

@@ -51,7 +51,8 @@ struct BwdLayout {
 int check_desc(snb_handle h, const snb_render_desc* d, const char* who) {
   SNB_REQUIRE(h != nullptr && d != nullptr, "%s: null handle or descriptor", who);
   SNB_REQUIRE(d->n_rays >= 0 && d->n_samples >= 1, "%s: bad sizes", who);
-  SNB_REQUIRE(d->precision == SNB_PREC_FP32 || d->precision == SNB_PREC_BF16, "%s: unknown precision %d", who, d->precision);
+  SNB_REQUIRE(d->precision == SNB_PREC_FP32 || d->precision == SNB_PREC_BF16 || d->precision == SNB_PREC_BF16_TRAIN,
+              "%s: unknown precision %d", who, d->precision);
   SNB_REQUIRE(d->mode == SNB_RENDER_BOX || d->mode == SNB_RENDER_SHELL, "%s: unknown mode %d", who, d->mode);
   return 0;
 }

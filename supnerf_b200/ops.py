@@ -12,6 +12,7 @@ from ._lib import check, f32c, ptr, require_cuda, stream_ptr
 
 WHITE_BKGD, SIGMA_RELU = 1, 2
 PREC = {"fp32": 0, "bf16": 1}
+PREC_BF16_TRAIN = 2  # selected automatically in bf16 mode when a weight requires grad (SNB_PREC_BF16_TRAIN)
 TIMING_HOOK = None  # bench.py: callable(which, (start_event, end_event)) around the decoder C-ABI calls
 
 
@@ -296,6 +297,8 @@ class _Decoder(torch.autograd.Function):
         handle.set_weights(weights)
         if precision == PREC["bf16"]:
             handle.ensure_packed(weights)
+            if any(ctx.needs_input_grad[7:]):
+                precision = PREC_BF16_TRAIN   # keep the operand tiles: the backward produces the weight gradients on the tensor core
         ws = torch.empty(lib.snb_mlp_workspace_bytes(handle.h, m, n_objs, precision), dtype=torch.uint8, device=dev)
         sigma = torch.empty(m, device=dev, dtype=torch.float32)
         rgb = torch.empty(m, 3, device=dev, dtype=torch.float32)
@@ -371,6 +374,8 @@ class _RenderBox(torch.autograd.Function):
         handle.set_weights(weights)
         if precision == PREC["bf16"]:
             handle.ensure_packed(weights)
+            if any(ctx.needs_input_grad[13:]):
+                desc.precision = PREC_BF16_TRAIN
         ws = torch.empty(lib.snb_render_workspace_bytes(handle.h, ctypes.byref(desc)), dtype=torch.uint8, device=dev)
         o_rgb = torch.empty(n, 3, device=dev, dtype=torch.float32)
         o_dep = torch.empty(n, device=dev, dtype=torch.float32)
