@@ -740,6 +740,8 @@ size_t tc2_bwd_save_bytes(const snb_handle_s* h, int64_t M);
 int tc2_launch_wgrad(const snb_handle_s* h, int64_t M, int64_t B, const uint8_t* fsave, const uint8_t* bsave, const float* sigma,
                      const float* g_sigma, const float* g_rgb, const float* s_lat, const float* zlat, float* const* gw,
                      cudaStream_t st);
+int tc2_launch_latent_wgrad(const snb_handle_s* h, int64_t B, const float* zlat, const float* dz, const float* shape_latent,
+                            const float* texture_latent, float* const* gw, cudaStream_t st);
 
 static size_t v1_packed_bytes(const snb_handle_s* h) { return ((size_t)build_plan(h).total_bytes + 1024 + 1023) & ~size_t(1023); }
 static bool use_v2(const snb_handle_s* h) {
@@ -911,10 +913,9 @@ int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, i
     if (!want_w) return latent_backward_fused(h, B, zlat, g_zlat, g_shape_latent, g_texture_latent, st, fold_tmp);
     const uint8_t* fsave = align1k((uint8_t*)ws + tc_workspace_bytes(h, M, B));
     if (tc2_launch_wgrad(h, M, B, fsave, bsave, sigma, g_sigma, g_rgb, g_zlat, zlat, g_weights, st)) return 1;
-    // latent layers (per object, fp32): fold the column sums through W_layer^T into fold_tmp (= d loss / d z), then the
-    // generic backward gives d latent AND the latent layers' weight / bias gradients
-    if (latent_fold(h, B, g_zlat, fold_tmp, st)) return 1;
-    return latent_backward(h, B, shape_latent, texture_latent, zlat, fold_tmp, g_shape_latent, g_texture_latent, g_weights, st);
+    // latent layers (per object): fold the column sums through W_layer^T (= d loss / d z), d latent, then their weight gradients
+    if (latent_backward_fused(h, B, zlat, g_zlat, g_shape_latent, g_texture_latent, st, fold_tmp)) return 1;
+    return tc2_launch_latent_wgrad(h, B, zlat, fold_tmp, shape_latent, texture_latent, g_weights, st);
   }
   TcPlan pl = build_plan(h);
   Params p;

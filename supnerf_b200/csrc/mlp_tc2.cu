@@ -1294,41 +1294,97 @@ __global__ void __launch_bounds__(256) wgrad_latent_outer_kernel(const __grid_co
 
 // sigma head and rgb.2 on CUDA cores from the saved operand images: y = encoding_shape output (4 chunks), h = ReLU(rgb.0) (2 chunks)
 //   d w_sigma[i] = sum_s gsp[s] y[s][i],  d b_sigma = sum_s gsp[s];  d W2[k][j] = sum_s g_rgb[s][k] h[s][j],  d b2[k] = sum_s g_rgb[s][k]
+// Thread t owns one 16-byte unit (8 columns) u = t % 32 and the 16 rows of row group t / 32 of every tile: a warp reads one whole
+// 512-byte sample row per step (16-byte loads, independent across the 16 rows), partial sums stay in registers across tiles.
 __global__ void __launch_bounds__(256) wgrad_heads_kernel(const uint8_t* __restrict__ fsave, uint32_t f_tile_bytes, uint32_t y_off,
                                                          uint32_t h_off, int64_t n_tiles, int64_t M, const float* __restrict__ sigma,
                                                          const float* __restrict__ g_sigma, const float* __restrict__ g_rgb,
                                                          float* __restrict__ gw_sig, float* __restrict__ gb_sig,
                                                          float* __restrict__ gw2, float* __restrict__ gb2) {
-  __shared__ float gs[128], g3[128][3];
-  const int i = threadIdx.x;   // column of y (256); threads < 128 also own column i of h
-  const uint32_t cy = (uint32_t)i >> 6, uy = ((uint32_t)i & 63u) >> 3, ey = (uint32_t)i & 7u;
-  float a_sig = 0.f, a_b = 0.f, a2[3] = {0.f, 0.f, 0.f}, a_b2 = 0.f;
+  __shared__ float gs[128], g3[3][128];
+  __shared__ float red[8][4][256];   // [row group][sigma | rgb k][column]
+  const uint32_t t = threadIdx.x, u = t & 31u, rg = t >> 5;
+  const uint32_t chunk = u >> 3, unit = u & 7u;
+  float a_sig[8], a2[3][8], a_b = 0.f, a_b2[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a_sig[i] = 0.f; a2[0][i] = 0.f; a2[1][i] = 0.f; a2[2][i] = 0.f; }
+  auto fma8 = [](float (&acc)[8], float w, const uint4& q) {
+    acc[0] = fmaf(w, __uint_as_float(q.x << 16), acc[0]); acc[1] = fmaf(w, __uint_as_float(q.x & 0xffff0000u), acc[1]);
+    acc[2] = fmaf(w, __uint_as_float(q.y << 16), acc[2]); acc[3] = fmaf(w, __uint_as_float(q.y & 0xffff0000u), acc[3]);
+    acc[4] = fmaf(w, __uint_as_float(q.z << 16), acc[4]); acc[5] = fmaf(w, __uint_as_float(q.z & 0xffff0000u), acc[5]);
+    acc[6] = fmaf(w, __uint_as_float(q.w << 16), acc[6]); acc[7] = fmaf(w, __uint_as_float(q.w & 0xffff0000u), acc[7]);
+  };
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     __syncthreads();
-    if (i < 128) {
-      const int64_t r = tile * 128 + i;
+    if (t < 128) {
+      const int64_t r = tile * 128 + t;
       const bool ok = r < M;
-      gs[i] = ok ? __ldg(g_sigma + r) * (-expm1f(-__ldg(sigma + r))) : 0.f;
-      g3[i][0] = ok ? __ldg(g_rgb + 3 * r) : 0.f; g3[i][1] = ok ? __ldg(g_rgb + 3 * r + 1) : 0.f; g3[i][2] = ok ? __ldg(g_rgb + 3 * r + 2) : 0.f;
+      gs[t] = ok ? __ldg(g_sigma + r) * (-expm1f(-__ldg(sigma + r))) : 0.f;
+      g3[0][t] = ok ? __ldg(g_rgb + 3 * r) : 0.f; g3[1][t] = ok ? __ldg(g_rgb + 3 * r + 1) : 0.f; g3[2][t] = ok ? __ldg(g_rgb + 3 * r + 2) : 0.f;
     }
     __syncthreads();
-    const uint8_t* ty = fsave + (size_t)tile * f_tile_bytes + y_off + (size_t)cy * kChunkBytes;
-    const uint8_t* th = fsave + (size_t)tile * f_tile_bytes + h_off + (size_t)cy * kChunkBytes;
-    for (uint32_t s = 0; s < 128; ++s) {
-      const float yv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(ty + swz(s, uy) + ey * 2u));
-      a_sig = fmaf(gs[s], yv, a_sig);
-      if (i < 128) {
-        const float hv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(th + swz(s, uy) + ey * 2u));
-        a2[0] = fmaf(g3[s][0], hv, a2[0]); a2[1] = fmaf(g3[s][1], hv, a2[1]); a2[2] = fmaf(g3[s][2], hv, a2[2]);
+    const uint8_t* ty = fsave + (size_t)tile * f_tile_bytes + y_off + (size_t)chunk * kChunkBytes;
+    const uint8_t* th = fsave + (size_t)tile * f_tile_bytes + h_off + (size_t)chunk * kChunkBytes;
+#pragma unroll 4
+    for (uint32_t k = 0; k < 16; ++k) {
+      const uint32_t srow = rg * 16u + k;
+      const uint4 qy = __ldg(reinterpret_cast<const uint4*>(ty + swz(srow, unit)));
+      fma8(a_sig, gs[srow], qy);
+      if (chunk < 2) {
+        const uint4 qh = __ldg(reinterpret_cast<const uint4*>(th + swz(srow, unit)));
+        fma8(a2[0], g3[0][srow], qh); fma8(a2[1], g3[1][srow], qh); fma8(a2[2], g3[2][srow], qh);
       }
-      if (i == 0) a_b += gs[s];
-      if (i >= 1 && i <= 3) a_b2 += g3[s][i - 1];
+      if (u == 0) { a_b += gs[srow]; a_b2[0] += g3[0][srow]; a_b2[1] += g3[1][srow]; a_b2[2] += g3[2][srow]; }
     }
   }
-  atomicAdd(gw_sig + i, a_sig);
-  if (i < 128) { atomicAdd(gw2 + i, a2[0]); atomicAdd(gw2 + 128 + i, a2[1]); atomicAdd(gw2 + 256 + i, a2[2]); }
-  if (i == 0) atomicAdd(gb_sig, a_b);
-  if (i >= 1 && i <= 3) atomicAdd(gb2 + (i - 1), a_b2);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t col = chunk * 64u + unit * 8u + (uint32_t)i;
+    red[rg][0][col] = a_sig[i];
+    if (chunk < 2) { red[rg][1][col] = a2[0][i]; red[rg][2][col] = a2[1][i]; red[rg][3][col] = a2[2][i]; }
+  }
+  __syncthreads();
+  {
+    float v = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) v += red[g][0][t];
+    atomicAdd(gw_sig + t, v);
+    if (t < 128) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float w = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) w += red[g][1 + k][t];
+        atomicAdd(gw2 + k * 128 + t, w);
+      }
+    }
+  }
+  if (u == 0) {   // one lane per row group
+    atomicAdd(gb_sig, a_b);
+    atomicAdd(gb2, a_b2[0]); atomicAdd(gb2 + 1, a_b2[1]); atomicAdd(gb2 + 2, a_b2[2]);
+  }
+}
+
+// latent layers (per object): d pre = dz * [z > 0];  d W_lat[o][k] += sum_b dpre[b][o] latent[b][k];  d b_lat[o] += sum_b dpre[b][o].
+// grid (slots, W), block D.  (The fp32 back end's generic sgemm takes ~70 us per layer for these 8-row GEMMs.)
+struct LatWJobs { int n, n_shape; float* gw[kMaxLat]; float* gb[kMaxLat]; };
+__global__ void __launch_bounds__(1024) wgrad_latent_layers_kernel(const __grid_constant__ LatWJobs J, int64_t B, int W, int D,
+                                                                  const float* __restrict__ zlat, const float* __restrict__ dz,
+                                                                  const float* __restrict__ shape_latent,
+                                                                  const float* __restrict__ texture_latent) {
+  const int slot = blockIdx.x, o = blockIdx.y, k = threadIdx.x;
+  if (k >= D) return;
+  const float* lat = slot < J.n_shape ? shape_latent : texture_latent;
+  float acc = 0.f, accb = 0.f;
+  for (int64_t b = 0; b < B; ++b) {
+    const size_t zi = ((size_t)slot * B + b) * W + o;
+    const float dp = zlat[zi] > 0.f ? dz[zi] : 0.f;
+    acc = fmaf(dp, lat[b * D + k], acc);
+    accb += dp;
+  }
+  J.gw[slot][(size_t)o * D + k] += acc;
+  if (k == 0) J.gb[slot][o] += accb;
 }
 
 }  // namespace tc2
@@ -1388,9 +1444,26 @@ int tc2_launch_wgrad(const snb_handle_s* h, int64_t M, int64_t B, const uint8_t*
   SNB_LAUNCH_CHECK();
   // heads
   const int64_t nt = p.n_tiles;
-  const int grid = (int)(nt < 2 * sms ? nt : 2 * sms);
+  const int grid = (int)(nt < 4 * sms ? nt : 4 * sms);
   tc2::wgrad_heads_kernel<<<grid, 256, 0, st>>>(fsave, F.save_tile_bytes, fX(Bs + 2), fX(Bs + Bt + 5), nt, M, sigma, g_sigma, g_rgb,
                                                gw[2 * h->iSG], gw[2 * h->iSG + 1], gw[2 * h->iR2], gw[2 * h->iR2 + 1]);
+  SNB_LAUNCH_CHECK();
+  return 0;
+}
+
+// weight / bias gradients of the per-object latent layers from dz = d loss / d z (the folded column sums)
+int tc2_launch_latent_wgrad(const snb_handle_s* h, int64_t B, const float* zlat, const float* dz, const float* shape_latent,
+                            const float* texture_latent, float* const* gw, cudaStream_t st) {
+  const int Bs = h->arch.shape_blocks, Bt = h->arch.texture_blocks, W = h->arch.W, D = h->arch.latent_dim;
+  SNB_REQUIRE(D <= 1024, "latent wgrad: latent_dim > 1024");
+  tc2::LatWJobs J{};
+  J.n = Bs + Bt; J.n_shape = Bs;
+  for (int j = 1; j <= Bs + Bt; ++j) {
+    const int li = j <= Bs ? h->iSL(j) : h->iTL(j - Bs);
+    J.gw[j - 1] = gw[2 * li]; J.gb[j - 1] = gw[2 * li + 1];
+  }
+  tc2::wgrad_latent_layers_kernel<<<dim3((unsigned)(Bs + Bt), (unsigned)W), (unsigned)((D + 31) / 32 * 32), 0, st>>>(
+      J, B, W, D, zlat, dz, shape_latent, texture_latent);
   SNB_LAUNCH_CHECK();
   return 0;
 }

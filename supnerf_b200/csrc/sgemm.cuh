@@ -27,8 +27,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
   __shared__ __align__(16) float As[BK][BM];
   __shared__ __align__(16) float Bs[BK][BN];
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
-  const int64_t i0 = (int64_t)blockIdx.y * BM;
-  const int j0 = blockIdx.x * BN;
+  const int64_t i0 = (int64_t)blockIdx.x * BM;   // M tiles on grid.x (up to 2^31-1: M reaches 10^7 rows), N tiles on grid.y
+  const int j0 = blockIdx.y * BN;
   int64_t kbeg = 0, kend = g.K;
   if (g.k_split > 0) {
     kbeg = (int64_t)blockIdx.z * g.k_split;
@@ -132,7 +132,7 @@ inline int launch_sgemm(const GemmArgs& g, bool a_kc, bool b_kc, cudaStream_t st
   if (g.M == 0 || g.N == 0) return 0;
   int64_t splits = 1;
   if (g.k_split > 0) splits = ceil_div(g.K, g.k_split);
-  dim3 grid((unsigned)ceil_div(g.N, 128), (unsigned)ceil_div(g.M, 128), (unsigned)splits);
+  dim3 grid((unsigned)ceil_div(g.M, 128), (unsigned)ceil_div(g.N, 128), (unsigned)splits);
   if (a_kc && b_kc) sgemm_kernel<true, true><<<grid, 256, 0, st>>>(g);
   else if (a_kc && !b_kc) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(g);
   else if (!a_kc && !b_kc) sgemm_kernel<false, false><<<grid, 256, 0, st>>>(g);

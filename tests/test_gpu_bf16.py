@@ -177,3 +177,30 @@ def test_tc_render_c1_full_size_end_to_end():
                 g_shape=rel_err(s_g.grad, s_o.grad), g_texture=rel_err(t_g.grad, t_o.grad))
     print(errs)
     assert all(e < TOL for e in errs.values()), errs
+
+
+def test_tc_training_mode_through_fused_render():
+    """NeRFRenderer.render_rays with trainable weights in bf16 mode (fused render, training precision selected automatically):
+    weight gradients against the fp32 back end of the same library on the same inputs."""
+    S = snb()
+    obj = oracle.synthetic_object(37, im_sz=32)
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=37)
+    shp0, tex0 = oracle.synthetic_latents(37, 1)
+    jit = torch.rand(1024, 64, generator=torch.Generator().manual_seed(37))
+    R = S.renderer.NeRFRenderer(n_samples=64)
+    grads = {}
+    for prec in ("fp32", "bf16"):
+        m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
+        m.precision = prec
+        cam = obj["cam_pose"].to(DEV).requires_grad_()
+        shp, tex = shp0.to(DEV).requires_grad_(), tex0.to(DEV).requires_grad_()
+        with forced_rand_like(jit):
+            rgb, dep, acc, tgt, occ = R.render_rays(m, DEV, obj["img"], obj["mask_occ"], cam, obj["wlh"], obj["K"].to(DEV), obj["roi"],
+                                                    shp, tex, im_sz=32)
+        oracle.refine_losses(rgb, acc, tgt, occ)[0].backward()
+        grads[prec] = {k: p_.grad.clone() for k, p_ in m.named_parameters() if p_.grad is not None}
+        grads[prec].update(cam=cam.grad, shp=shp.grad, tex=tex.grad)
+    assert set(grads["bf16"]) == set(grads["fp32"]) and len(grads["bf16"]) >= 28 + 3
+    errs = {k: rel_err(grads["bf16"][k], grads["fp32"][k]) for k in grads["fp32"]}
+    print(errs)
+    assert all(e < TOL for e in errs.values()), {k: e for k, e in errs.items() if e >= TOL}
