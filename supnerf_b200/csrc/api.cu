@@ -40,11 +40,12 @@ int tc_timing_read(int which, float* ms, int max_n);
 size_t tc_workspace_bytes(const snb_handle_s* h, int64_t M, int64_t B);
 size_t tc_bwd_scratch_bytes(const snb_handle_s* h, int64_t M, int64_t B);
 int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
-               const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, void* ws, cudaStream_t st, bool train);
+               const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, void* ws, cudaStream_t st, bool train,
+               const int64_t* m_dev);
 int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                 const float* shape_latent, const float* texture_latent, const float* sigma, const float* g_sigma,
                 const float* g_rgb, const void* ws, void* scratch, float* g_xyz, float* g_viewdir, float* g_shape_latent,
-                float* g_texture_latent, float* const* g_weights, cudaStream_t st, bool train);
+                float* g_texture_latent, float* const* g_weights, cudaStream_t st, bool train, const int64_t* m_dev);
 size_t tc_train_workspace_extra(const snb_handle_s* h, int64_t M);
 size_t tc_train_scratch_extra(const snb_handle_s* h, int64_t M);
 
@@ -182,7 +183,7 @@ extern "C" int snb_mlp_fwd(snb_handle h, int32_t precision, const float* xyz, co
   SNB_REQUIRE(xyz && viewdir && shape_latent && texture_latent && sigma && rgb && workspace, "mlp_fwd: null pointer");
   if (precision != SNB_PREC_FP32)
     return tc_forward(h, xyz, viewdir, M, B, shape_latent, texture_latent, sigma, rgb, workspace, (cudaStream_t)stream,
-                      precision == SNB_PREC_BF16_TRAIN);
+                      precision == SNB_PREC_BF16_TRAIN, nullptr);
   return f32_forward(h, xyz, viewdir, M, B, shape_latent, texture_latent, sigma, rgb, (float*)workspace, (cudaStream_t)stream);
 }
 
@@ -198,7 +199,7 @@ extern "C" int snb_mlp_bwd(snb_handle h, int32_t precision, const float* xyz, co
   if (precision != SNB_PREC_FP32)
     return tc_backward(h, xyz, viewdir, M, B, shape_latent, texture_latent, sigma, g_sigma, g_rgb, workspace, scratch, g_xyz,
                        g_viewdir, g_shape_latent, g_texture_latent, g_weights, (cudaStream_t)stream,
-                       precision == SNB_PREC_BF16_TRAIN);
+                       precision == SNB_PREC_BF16_TRAIN, nullptr);
   return f32_backward(h, xyz, viewdir, M, B, shape_latent, texture_latent, sigma, g_sigma, g_rgb, (const float*)workspace,
                       (float*)scratch, g_xyz, g_viewdir, g_shape_latent, g_texture_latent, g_weights, (cudaStream_t)stream);
 }

@@ -1,0 +1,29 @@
+// Miss-ray compaction helpers (compact.cu) and the internal tensor-core decoder entry points the fused render calls directly.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "handle.h"
+
+namespace snb {
+
+int compact_plan(const uint8_t* hit, int64_t n_rays, int S, int32_t* order, int32_t* pos, int64_t* counts, cudaStream_t st);
+int compact_gather(const float* xyz, const float* vrep, const int32_t* order, const int64_t* counts, int64_t n_rays, int S,
+                   float* xyz_c, float* vrep_c, cudaStream_t st);
+int compact_expand(const float* sigma_c, const float* rgb_c, const uint8_t* hit, const int32_t* pos, const int64_t* counts,
+                   int64_t n_rays, int S, float* sigma, float* rgb, cudaStream_t st);
+int compact_reduce(const float* g_sigma, const float* g_rgb, const int32_t* order, const int64_t* counts, int64_t n_rays, int S,
+                   float* g_sigma_c, float* g_rgb_c, cudaStream_t st);
+int compact_scatter(const float* g_xyz_c, const float* g_vrep_c, const uint8_t* hit, const int32_t* pos, const int64_t* counts,
+                    int64_t n_rays, int S, float* g_xyz, float* g_vrep, cudaStream_t st);
+
+// mlp_tc.cu: m_dev (optional) = device-side number of rows actually present (a multiple of 128, <= M)
+bool tc_two_tile_active(const snb_handle_s* h);
+int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
+               const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, void* ws, cudaStream_t st, bool train,
+               const int64_t* m_dev);
+int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
+                const float* shape_latent, const float* texture_latent, const float* sigma, const float* g_sigma,
+                const float* g_rgb, const void* ws, void* scratch, float* g_xyz, float* g_viewdir, float* g_shape_latent,
+                float* g_texture_latent, float* const* g_weights, cudaStream_t st, bool train, const int64_t* m_dev);
+
+}  // namespace snb

@@ -728,18 +728,20 @@ static TcPlan build_plan(const snb_handle_s* h) {
 
 // second-generation kernels (mlp_tc2.cu): two tiles in flight per CTA
 bool tc2_supported(const snb_handle_s* h);
+bool tc_two_tile_active(const snb_handle_s* h);
 size_t tc2_packed_bytes(const snb_handle_s* h);
 int tc2_pack_weights(const snb_handle_s* h, void* packed, cudaStream_t st);
 int tc2_launch_fwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
-                   const uint8_t* eimg, uint32_t* masks, float* sigma, float* rgb, float* dbg, uint8_t* save, cudaStream_t st);
+                   const uint8_t* eimg, uint32_t* masks, float* sigma, float* rgb, float* dbg, uint8_t* save, cudaStream_t st,
+                   const int64_t* m_dev);
 int tc2_launch_bwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                    const uint32_t* masks, const float* sigma, const float* g_sigma, const float* g_rgb, float* g_xyz,
-                   float* g_viewdir, float* g_zlat, uint8_t* save, cudaStream_t st);
+                   float* g_viewdir, float* g_zlat, uint8_t* save, cudaStream_t st, const int64_t* m_dev);
 size_t tc2_fwd_save_bytes(const snb_handle_s* h, int64_t M);
 size_t tc2_bwd_save_bytes(const snb_handle_s* h, int64_t M);
 int tc2_launch_wgrad(const snb_handle_s* h, int64_t M, int64_t B, const uint8_t* fsave, const uint8_t* bsave, const float* sigma,
                      const float* g_sigma, const float* g_rgb, const float* s_lat, const float* zlat, float* const* gw,
-                     cudaStream_t st);
+                     cudaStream_t st, const int64_t* m_dev);
 int tc2_launch_latent_wgrad(const snb_handle_s* h, int64_t B, const float* zlat, const float* dz, const float* shape_latent,
                             const float* texture_latent, float* const* gw, cudaStream_t st);
 
@@ -748,6 +750,8 @@ static bool use_v2(const snb_handle_s* h) {
   static const bool force_v1 = [] { const char* e = getenv("SNB_TC_V1"); return e && atoi(e) != 0; }();
   return !force_v1 && tc2_supported(h);
 }
+
+bool tc_two_tile_active(const snb_handle_s* h) { const char* why; return tc_supported(h, &why) && use_v2(h); }
 
 size_t tc_packed_bytes(const snb_handle_s* h) {
   const char* why;
@@ -847,8 +851,9 @@ void tc_set_debug(float* acts) { g_tc_debug_acts = acts; }
 
 int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, void* ws, cudaStream_t st,
-               bool train) {
+               bool train, const int64_t* m_dev) {
   if (tc_common_checks(h, M, B, "mlp_fwd(bf16)")) return 2;
+  SNB_REQUIRE(m_dev == nullptr || (use_v2(h) && B == 1), "mlp_fwd(bf16): a device-side row count needs the two-tile kernels and one object");
   SNB_REQUIRE(!train || use_v2(h), "mlp_fwd(bf16, training): weight gradients need the two-tile tcgen05 kernels (W = 256, "
                                     "shape_blocks + texture_blocks <= 4); use precision='fp32' for this architecture");
   uint8_t* fsave = train ? align1k((uint8_t*)ws + tc_workspace_bytes(h, M, B)) : nullptr;
@@ -860,7 +865,7 @@ int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, in
   if (use_v2(h)) {
     ScopedKernelTimer tm2(st, g_timing_on);
     if (tc2_launch_fwd(h, (const uint8_t*)h->packed + v1_packed_bytes(h), xyz, viewdir, M, B, eimg, masks, sigma, rgb,
-                       g_tc_debug_acts, fsave, st)) return 1;
+                       g_tc_debug_acts, fsave, st, m_dev)) return 1;
     tm2.stop(g_ev_fwd);
     SNB_LAUNCH_CHECK();
     return 0;
@@ -881,8 +886,9 @@ int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, in
 int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                 const float* shape_latent, const float* texture_latent, const float* sigma, const float* g_sigma,
                 const float* g_rgb, const void* ws, void* scratch, float* g_xyz, float* g_viewdir, float* g_shape_latent,
-                float* g_texture_latent, float* const* g_weights, cudaStream_t st, bool train) {
+                float* g_texture_latent, float* const* g_weights, cudaStream_t st, bool train, const int64_t* m_dev) {
   if (tc_common_checks(h, M, B, "mlp_bwd(bf16)")) return 2;
+  SNB_REQUIRE(m_dev == nullptr || (use_v2(h) && B == 1), "mlp_bwd(bf16): a device-side row count needs the two-tile kernels and one object");
   SNB_REQUIRE(g_weights == nullptr || (train && use_v2(h)),
               "mlp_bwd(bf16): weight gradients need the forward to have run in training mode (SNB_PREC_BF16_TRAIN: the python "
               "modules select it when a weight requires grad) on an architecture the two-tile kernels cover; otherwise freeze "
@@ -907,12 +913,12 @@ int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, i
     }
     ScopedKernelTimer tm2(st, g_timing_on);
     if (tc2_launch_bwd(h, (const uint8_t*)h->packed + v1_packed_bytes(h), xyz, viewdir, M, B, masks, sigma, g_sigma, g_rgb, g_xyz,
-                       g_viewdir, g_zlat, bsave, st)) return 1;
+                       g_viewdir, g_zlat, bsave, st, m_dev)) return 1;
     tm2.stop(g_ev_bwd);
     SNB_LAUNCH_CHECK();
     if (!want_w) return latent_backward_fused(h, B, zlat, g_zlat, g_shape_latent, g_texture_latent, st, fold_tmp);
     const uint8_t* fsave = align1k((uint8_t*)ws + tc_workspace_bytes(h, M, B));
-    if (tc2_launch_wgrad(h, M, B, fsave, bsave, sigma, g_sigma, g_rgb, g_zlat, zlat, g_weights, st)) return 1;
+    if (tc2_launch_wgrad(h, M, B, fsave, bsave, sigma, g_sigma, g_rgb, g_zlat, zlat, g_weights, st, m_dev)) return 1;
     // latent layers (per object): fold the column sums through W_layer^T (= d loss / d z), d latent, then their weight gradients
     if (latent_backward_fused(h, B, zlat, g_zlat, g_shape_latent, g_texture_latent, st, fold_tmp)) return 1;
     return tc2_launch_latent_wgrad(h, B, zlat, fold_tmp, shape_latent, texture_latent, g_weights, st);

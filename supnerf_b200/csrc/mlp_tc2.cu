@@ -77,6 +77,8 @@ struct Params {
   const float* sigma_in; const float* g_sigma; const float* g_rgb;
   float* g_xyz; float* g_viewdir; float* g_zlat;   // g_zlat [(Bs+Bt)][B][256], accumulated with atomics
   int r0_mask_slot, n_latent;
+  const int64_t* m_dev;   // optional: the number of rows actually present (<= M), read on the device -- the fused render compacts
+                          // the samples of rays that miss the box on the GPU and never learns the count on the host
   uint8_t* save;      // training mode (weight gradients wanted): [tile][Program::save_tile_bytes] copies of every step's A operand
   long long* trace;   // timing experiments only: CTA 0 writes clock64 stamps [pair][step][slot][4] = READY seen, MMAs issued, ACC seen, published
   int exp_flags;   // timing experiments only (env SNB_TC_EXP): 1 = producer skips the weight copies, 4 = every stage copies the same image
@@ -237,9 +239,11 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
       "}" ::"r"(bar) : "memory");
 }
 
+__device__ __forceinline__ int64_t rows_present(const Params& p) { return p.m_dev ? __ldg(p.m_dev) : p.M; }
+
 __device__ __forceinline__ void producer_loop(const Params& p, const Smem& sm, int64_t n_pairs) {
   uint32_t stage = 0, ph = 0;
-  const int64_t n_tiles = (p.M + kTileM - 1) / kTileM;
+  const int64_t n_tiles = (rows_present(p) + kTileM - 1) / kTileM;
   const uint32_t crank = cluster_ctarank();
   // every CTA of a cluster runs the same number of iterations (a CTA past the last pair still streams its share of the weights)
   for (int64_t pair0 = (int64_t)blockIdx.x - crank; pair0 < n_pairs; pair0 += gridDim.x) {
@@ -276,7 +280,7 @@ __device__ __forceinline__ void mma_loop(const Params& p, const Smem& sm, int64_
   const uint64_t ones_desc = umma_desc_sw32(sm.base_u32 + SM_TAB + TAB_LAT);
   const bool trace = p.trace != nullptr && blockIdx.x == 0;
   int64_t tr = 0;
-  const int64_t crank_m = cluster_ctarank(), n_tiles_m = (p.M + kTileM - 1) / kTileM;
+  const int64_t crank_m = cluster_ctarank(), n_tiles_m = (rows_present(p) + kTileM - 1) / kTileM;
   const uint32_t lane_m = threadIdx.x & 31u;
   for (int64_t pair0 = (int64_t)blockIdx.x - crank_m; pair0 < n_pairs; pair0 += gridDim.x) {
     for (int si = 0; si < p.prog.n_steps; ++si) {
@@ -437,7 +441,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_const
   }
   uint32_t tmem_base;
   kernel_prologue(sm, tid, warp, tmem_base);
-  const int64_t n_tiles = (p.M + kTileM - 1) / kTileM;
+  const int64_t M_eff = rows_present(p);
+  const int64_t n_tiles = (M_eff + kTileM - 1) / kTileM;
   const int64_t n_pairs = (n_tiles + 1) / 2;
 
   if (warp == 16) {
@@ -459,7 +464,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_const
     float x[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 1.f};
     auto load_coords = [&](int64_t pr, float (&xo)[3], float (&dro)[3]) {   // clamped: tiles past the end redo row M-1, never stored
       int64_t r = (2 * pr + slot) * kTileM + e.row;
-      if (pr >= n_pairs || r >= p.M) r = p.M - 1;
+      if (pr >= n_pairs || r >= M_eff) r = M_eff - 1;
       xo[0] = __ldg(p.xyz + 3 * r); xo[1] = __ldg(p.xyz + 3 * r + 1); xo[2] = __ldg(p.xyz + 3 * r + 2);
       dro[0] = __ldg(p.viewdir + 3 * r); dro[1] = __ldg(p.viewdir + 3 * r + 1); dro[2] = __ldg(p.viewdir + 3 * r + 2);
     };
@@ -474,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_const
       const bool tile_ok = pair < n_pairs && tile < n_tiles;
       const bool has_next = pair0 + (int64_t)gridDim.x < n_pairs;   // cluster-uniform
       e.grow = tile * kTileM + e.row;
-      e.valid = tile_ok && e.grow < p.M;
+      e.valid = tile_ok && e.grow < M_eff;
       uint32_t* mask_tile = p.masks + (size_t)(tile_ok ? tile : 0) * nslots * 8 * 128;
       float sig_acc = 0.f, rgb_acc[3] = {0.f, 0.f, 0.f};
       float xn[3] = {0.f, 0.f, 0.f}, dn[3] = {0.f, 0.f, 1.f};
@@ -615,7 +620,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_const
   }
   uint32_t tmem_base;
   kernel_prologue(sm, tid, warp, tmem_base);
-  const int64_t n_tiles = (p.M + kTileM - 1) / kTileM;
+  const int64_t M_eff = rows_present(p);
+  const int64_t n_tiles = (M_eff + kTileM - 1) / kTileM;
   const int64_t n_pairs = (n_tiles + 1) / 2;
 
   if (warp == 16) {
@@ -640,8 +646,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_const
       const int64_t t = 2 * pr + slot;
       const bool ok = pr < n_pairs && t < n_tiles;
       const int64_t r = t * kTileM + e.row;
-      const bool valid = ok && r < p.M;
-      const int64_t cr = valid ? r : p.M - 1;
+      const bool valid = ok && r < M_eff;
+      const int64_t cr = valid ? r : M_eff - 1;
       const float gsg = valid ? __ldg(p.g_sigma + r) : 0.f;
       gsp_o = gsg * (-expm1f(-__ldg(p.sigma_in + cr)));   // d softplus = 1 - exp(-softplus)
 #pragma unroll
@@ -685,8 +691,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_const
       const bool tile_ok = pair < n_pairs && tile < n_tiles;
       const bool has_next = pair0 + (int64_t)gridDim.x < n_pairs;   // cluster-uniform
       e.grow = tile * kTileM + e.row;
-      e.valid = tile_ok && e.grow < p.M;
-      const int64_t crow = e.valid ? e.grow : p.M - 1;
+      e.valid = tile_ok && e.grow < M_eff;
+      const int64_t crow = e.valid ? e.grow : M_eff - 1;
       const int64_t obj = tile_ok ? (tile * kTileM) / p.rows_per_obj : 0;
       const uint32_t* mask_tile = p.masks + (size_t)(tile_ok ? tile : 0) * nslots * 8 * 128;
       float gsp_n = 0.f, g3n[3] = {0.f, 0.f, 0.f}, gx[3] = {0.f, 0.f, 0.f};
@@ -1055,12 +1061,14 @@ static cudaError_t tc2_launch(K kernel, int grid, cudaStream_t st, const tc2::Pa
 }
 
 int tc2_launch_fwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
-                   const uint8_t* eimg, uint32_t* masks, float* sigma, float* rgb, float* dbg, uint8_t* save, cudaStream_t st) {
+                   const uint8_t* eimg, uint32_t* masks, float* sigma, float* rgb, float* dbg, uint8_t* save, cudaStream_t st,
+                   const int64_t* m_dev) {
   Tc2Plan pl = build_plan2(h);
   tc2::Params p;
   fill_common2(p, h, packed2, xyz, viewdir, M, B, eimg, masks);
   p.sigma = sigma; p.rgb = rgb; p.dbg = dbg;
   p.save = save;
+  p.m_dev = m_dev;
   p.prog = save ? pl.fwd_train : pl.fwd;
   if (dbg) {
     SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
@@ -1074,13 +1082,14 @@ int tc2_launch_fwd(const snb_handle_s* h, const void* packed2, const float* xyz,
 
 int tc2_launch_bwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                    const uint32_t* masks, const float* sigma, const float* g_sigma, const float* g_rgb, float* g_xyz,
-                   float* g_viewdir, float* g_zlat, uint8_t* save, cudaStream_t st) {
+                   float* g_viewdir, float* g_zlat, uint8_t* save, cudaStream_t st, const int64_t* m_dev) {
   Tc2Plan pl = build_plan2(h);
   tc2::Params p;
   fill_common2(p, h, packed2, xyz, viewdir, M, B, nullptr, const_cast<uint32_t*>(masks));
   p.sigma_in = sigma; p.g_sigma = g_sigma; p.g_rgb = g_rgb; p.g_xyz = g_xyz; p.g_viewdir = g_viewdir; p.g_zlat = g_zlat;
   p.r0_mask_slot = pl.r0_slot;
   p.save = save;
+  p.m_dev = m_dev;
   SNB_REQUIRE(save == nullptr || g_xyz != nullptr, "tc2 backward: training mode runs the full program (g_xyz scratch required)");
   p.prog = g_xyz ? pl.bwd_full : pl.bwd_noxyz;
   SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
@@ -1120,6 +1129,7 @@ struct WParams {
   const uint8_t* fsave; const uint8_t* bsave;
   uint32_t f_tile_bytes, b_tile_bytes;
   int64_t n_tiles;
+  const int64_t* m_dev;   // optional device-side row count (see Params::m_dev)
   int32_t n_jobs, splits;
   WJob jobs[kMaxWJobs];
 };
@@ -1157,7 +1167,8 @@ __global__ void __launch_bounds__(kWThreads, 1) tc2_wgrad_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n_pieces = jb.dy_chunks + jb.x_chunks;
-  const int64_t my_tiles = p.n_tiles > split ? (p.n_tiles - split + p.splits - 1) / p.splits : 0;
+  const int64_t n_tiles = p.m_dev ? (__ldg(p.m_dev) + kTileM - 1) / kTileM : p.n_tiles;
+  const int64_t my_tiles = n_tiles > split ? (n_tiles - split + p.splits - 1) / p.splits : 0;
   const int64_t n_iters = my_tiles * 2;   // half tiles
 
   if (warp == 0) {
@@ -1297,11 +1308,13 @@ __global__ void __launch_bounds__(256) wgrad_latent_outer_kernel(const __grid_co
 // Thread t owns one 16-byte unit (8 columns) u = t % 32 and the 16 rows of row group t / 32 of every tile: a warp reads one whole
 // 512-byte sample row per step (16-byte loads, independent across the 16 rows), partial sums stay in registers across tiles.
 __global__ void __launch_bounds__(256) wgrad_heads_kernel(const uint8_t* __restrict__ fsave, uint32_t f_tile_bytes, uint32_t y_off,
-                                                         uint32_t h_off, int64_t n_tiles, int64_t M, const float* __restrict__ sigma,
+                                                         uint32_t h_off, int64_t n_tiles, int64_t M, const int64_t* __restrict__ m_dev,
+                                                         const float* __restrict__ sigma,
                                                          const float* __restrict__ g_sigma, const float* __restrict__ g_rgb,
                                                          float* __restrict__ gw_sig, float* __restrict__ gb_sig,
                                                          float* __restrict__ gw2, float* __restrict__ gb2) {
   __shared__ float gs[128], g3[3][128];
+  if (m_dev) { M = __ldg(m_dev); n_tiles = (M + kTileM - 1) / kTileM; }
   __shared__ float red[8][4][256];   // [row group][sigma | rgb k][column]
   const uint32_t t = threadIdx.x, u = t & 31u, rg = t >> 5;
   const uint32_t chunk = u >> 3, unit = u & 7u;
@@ -1401,7 +1414,7 @@ size_t tc2_bwd_save_bytes(const snb_handle_s* h, int64_t M) {
 // [(Bs+Bt)][B][256] the backward kernel produced; zlat: the forward's per-object latent activations.
 int tc2_launch_wgrad(const snb_handle_s* h, int64_t M, int64_t B, const uint8_t* fsave, const uint8_t* bsave, const float* sigma,
                      const float* g_sigma, const float* g_rgb, const float* s_lat, const float* zlat, float* const* gw,
-                     cudaStream_t st) {
+                     cudaStream_t st, const int64_t* m_dev) {
   Tc2Plan pl = build_plan2(h);
   const tc2::Program& F = pl.fwd_train;
   const tc2::Program& Bp = pl.bwd_full;
@@ -1413,6 +1426,7 @@ int tc2_launch_wgrad(const snb_handle_s* h, int64_t M, int64_t B, const uint8_t*
   tc2::WParams p{};
   p.fsave = fsave; p.bsave = bsave; p.f_tile_bytes = F.save_tile_bytes; p.b_tile_bytes = Bp.save_tile_bytes;
   p.n_tiles = (M + kTileM - 1) / kTileM;
+  p.m_dev = m_dev;
   int nj = 0;
   auto add = [&](int layer, int col0, int ld, uint32_t dy_off, int dy_chunks, int n_out, uint32_t x_off, int x_chunks, int n_in, bool bias) {
     tc2::WJob& j = p.jobs[nj++];
@@ -1445,7 +1459,7 @@ int tc2_launch_wgrad(const snb_handle_s* h, int64_t M, int64_t B, const uint8_t*
   // heads
   const int64_t nt = p.n_tiles;
   const int grid = (int)(nt < 4 * sms ? nt : 4 * sms);
-  tc2::wgrad_heads_kernel<<<grid, 256, 0, st>>>(fsave, F.save_tile_bytes, fX(Bs + 2), fX(Bs + Bt + 5), nt, M, sigma, g_sigma, g_rgb,
+  tc2::wgrad_heads_kernel<<<grid, 256, 0, st>>>(fsave, F.save_tile_bytes, fX(Bs + 2), fX(Bs + Bt + 5), nt, M, m_dev, sigma, g_sigma, g_rgb,
                                                gw[2 * h->iSG], gw[2 * h->iSG + 1], gw[2 * h->iR2], gw[2 * h->iR2 + 1]);
   SNB_LAUNCH_CHECK();
   return 0;

@@ -5,6 +5,8 @@
 // iteration costs two host calls per object instead of ~50 autograd-node launches.
 #include "common.cuh"
 #include "handle.h"
+#include "compact.h"
+#include <stdlib.h>
 
 using namespace snb;
 
@@ -12,12 +14,31 @@ namespace {
 
 inline size_t al(size_t bytes) { return (bytes + 255) & ~size_t(255); }
 
+// Miss-ray compaction (compact.cu) applies to the box render on the two-tile tensor-core decoder; SNB_NO_COMPACT=1 disables it.
+bool use_compaction(snb_handle h, const snb_render_desc& d) {
+  static const bool off = [] { const char* e = getenv("SNB_NO_COMPACT"); return e && atoi(e) != 0; }();
+  return !off && d.mode == SNB_RENDER_BOX && d.precision != SNB_PREC_FP32 && tc_two_tile_active(h) &&
+         ((int64_t)d.n_rays * d.n_samples) % 128 == 0 && d.n_rays > 0;
+}
+
 // forward workspace (kept for the backward): rays_o, viewdir (N,3) | xyz, vrep (M,3) | z_vals (M) | sigma (M) | rgb (M,3) | mlp ws
+// | compaction: hit (N) u8, order, pos (N) i32, counts (4) i64, xyz_c, vrep_c (M+128,3), sigma_c (M+128), rgb_c (M+128,3)
 struct FwdLayout {
   size_t rays_o, viewdir, xyz, vrep, z, sigma, rgb, mlp, total;
+  size_t hit, order, pos, counts, xyz_c, vrep_c, sigma_c, rgb_c;
   FwdLayout(snb_handle h, const snb_render_desc& d) {
     const size_t N = (size_t)d.n_rays, M = N * (size_t)d.n_samples;
     size_t o = 0;
+    hit = o; o += al(N);
+    order = o; o += al(N * 4);
+    pos = o; o += al(N * 4);
+    counts = o; o += al(64);
+    if (use_compaction(h, d)) {
+      xyz_c = o; o += al((M + 128) * 12);
+      vrep_c = o; o += al((M + 128) * 12);
+      sigma_c = o; o += al((M + 128) * 4);
+      rgb_c = o; o += al((M + 128) * 12);
+    } else { xyz_c = vrep_c = sigma_c = rgb_c = 0; }
     rays_o = o; o += al(N * 12);
     viewdir = o; o += al(N * 12);
     xyz = o; o += al(M * 12);
@@ -33,9 +54,16 @@ struct FwdLayout {
 // backward scratch: g_sigma (M) | g_rgbs (M,3) | g_z (M) | g_xyz, g_vrep (M,3) | g_rays_o, g_viewdir (N,3) | mlp scratch
 struct BwdLayout {
   size_t g_sigma, g_rgbs, g_z, g_xyz, g_vrep, g_rays_o, g_viewdir, mlp, total;
+  size_t g_sigma_c, g_rgb_c, g_xyz_c, g_vrep_c;
   BwdLayout(snb_handle h, const snb_render_desc& d) {
     const size_t N = (size_t)d.n_rays, M = N * (size_t)d.n_samples;
     size_t o = 0;
+    if (use_compaction(h, d)) {
+      g_sigma_c = o; o += al((M + 128) * 4);
+      g_rgb_c = o; o += al((M + 128) * 12);
+      g_xyz_c = o; o += al((M + 128) * 12);
+      g_vrep_c = o; o += al((M + 128) * 12);
+    } else { g_sigma_c = g_rgb_c = g_xyz_c = g_vrep_c = 0; }
     g_sigma = o; o += al(M * 4);
     g_rgbs = o; o += al(M * 12);
     g_z = o; o += al(M * 4);
@@ -86,13 +114,29 @@ extern "C" int snb_render_fwd(snb_handle h, const snb_render_desc* d, const floa
   const int64_t N = d->n_rays, M = N * d->n_samples;
   void* ws = workspace;
   if (snb_get_rays_fwd(px, py, N, K, c2w, F(ws, L.rays_o), F(ws, L.viewdir), stream)) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* wsb = static_cast<uint8_t*>(ws);
   if (shell) {   // utils.py stack: one shared z vector, no slab test
     if (snb_sample_shell_fwd(F(ws, L.rays_o), F(ws, L.viewdir), z_steps, N, d->n_samples, d->obj_diag, d->shapenet_swap,
                              F(ws, L.xyz), F(ws, L.vrep), stream)) return 1;
-  } else if (snb_sample_box_fwd(F(ws, L.rays_o), F(ws, L.viewdir), z_steps, jitter, N, d->n_samples, d->half_diag, d->aabb_half,
-                                F(ws, L.xyz), F(ws, L.vrep), F(ws, L.z), out_hit, stream)) return 1;
-  if (snb_mlp_fwd(h, d->precision, F(ws, L.xyz), F(ws, L.vrep), M, 1, shape_latent, texture_latent, F(ws, L.sigma), F(ws, L.rgb),
-                  static_cast<uint8_t*>(ws) + L.mlp, stream)) return 1;
+  } else {
+    if (snb_sample_box_fwd(F(ws, L.rays_o), F(ws, L.viewdir), z_steps, jitter, N, d->n_samples, d->half_diag, d->aabb_half,
+                           F(ws, L.xyz), F(ws, L.vrep), F(ws, L.z), wsb + L.hit, stream)) return 1;
+    SNB_CHECK_CUDA(cudaMemcpyAsync(out_hit, wsb + L.hit, (size_t)N, cudaMemcpyDeviceToDevice, st));
+  }
+  if (use_compaction(h, *d)) {
+    // decoder on the compacted rows only: S rows per hit ray + ONE row per miss ray (their S samples are one point)
+    int32_t* order = reinterpret_cast<int32_t*>(wsb + L.order);
+    int32_t* pos = reinterpret_cast<int32_t*>(wsb + L.pos);
+    int64_t* counts = reinterpret_cast<int64_t*>(wsb + L.counts);
+    if (compact_plan(wsb + L.hit, N, d->n_samples, order, pos, counts, st)) return 1;
+    if (compact_gather(F(ws, L.xyz), F(ws, L.vrep), order, counts, N, d->n_samples, F(ws, L.xyz_c), F(ws, L.vrep_c), st)) return 1;
+    if (tc_forward(h, F(ws, L.xyz_c), F(ws, L.vrep_c), M, 1, shape_latent, texture_latent, F(ws, L.sigma_c), F(ws, L.rgb_c),
+                   wsb + L.mlp, st, d->precision == SNB_PREC_BF16_TRAIN, counts + 3)) return 1;
+    if (compact_expand(F(ws, L.sigma_c), F(ws, L.rgb_c), wsb + L.hit, pos, counts, N, d->n_samples, F(ws, L.sigma), F(ws, L.rgb), st))
+      return 1;
+  } else if (snb_mlp_fwd(h, d->precision, F(ws, L.xyz), F(ws, L.vrep), M, 1, shape_latent, texture_latent, F(ws, L.sigma),
+                         F(ws, L.rgb), wsb + L.mlp, stream)) return 1;
   return snb_composite_fwd(F(ws, L.sigma), F(ws, L.rgb), shell ? z_steps : F(ws, L.z), shell ? N : 1, N, d->n_samples, d->flags,
                            out_rgb, out_depth, out_acc, stream);
 }
@@ -120,7 +164,19 @@ extern "C" int snb_render_bwd(snb_handle h, const snb_render_desc* d, const floa
   // shell mode: z is built from detached python floats (utils.py:468-469), it carries no gradient
   if (snb_composite_bwd(F(ws, L.sigma), F(ws, L.rgb), shell ? z_steps : F(ws, L.z), shell ? N : 1, N, d->n_samples, d->flags, g_rgb,
                         g_depth, g_acc, F(sc, G.g_sigma), F(sc, G.g_rgbs), (pose && !shell) ? F(sc, G.g_z) : nullptr, stream)) return 1;
-  if (snb_mlp_bwd(h, d->precision, F(ws, L.xyz), F(ws, L.vrep), M, 1, shape_latent, texture_latent, F(ws, L.sigma),
+  if (use_compaction(h, *d)) {
+    const uint8_t* wsb = static_cast<const uint8_t*>(ws);
+    const int32_t* order = reinterpret_cast<const int32_t*>(wsb + L.order);
+    const int32_t* pos = reinterpret_cast<const int32_t*>(wsb + L.pos);
+    const int64_t* counts = reinterpret_cast<const int64_t*>(wsb + L.counts);
+    if (compact_reduce(F(sc, G.g_sigma), F(sc, G.g_rgbs), order, counts, N, d->n_samples, F(sc, G.g_sigma_c), F(sc, G.g_rgb_c), st)) return 1;
+    if (tc_backward(h, F(ws, L.xyz_c), F(ws, L.vrep_c), M, 1, shape_latent, texture_latent, F(ws, L.sigma_c), F(sc, G.g_sigma_c),
+                    F(sc, G.g_rgb_c), wsb + L.mlp, static_cast<uint8_t*>(sc) + G.mlp, pose ? F(sc, G.g_xyz_c) : nullptr,
+                    pose ? F(sc, G.g_vrep_c) : nullptr, g_shape_latent, g_texture_latent, g_weights, st,
+                    d->precision == SNB_PREC_BF16_TRAIN, counts + 3)) return 1;
+    if (pose && compact_scatter(F(sc, G.g_xyz_c), F(sc, G.g_vrep_c), wsb + L.hit, pos, counts, N, d->n_samples, F(sc, G.g_xyz),
+                                F(sc, G.g_vrep), st)) return 1;
+  } else if (snb_mlp_bwd(h, d->precision, F(ws, L.xyz), F(ws, L.vrep), M, 1, shape_latent, texture_latent, F(ws, L.sigma),
                   F(sc, G.g_sigma), F(sc, G.g_rgbs), static_cast<const uint8_t*>(ws) + L.mlp, static_cast<uint8_t*>(sc) + G.mlp,
                   pose ? F(sc, G.g_xyz) : nullptr, pose ? F(sc, G.g_vrep) : nullptr, g_shape_latent, g_texture_latent, g_weights,
                   stream)) return 1;
