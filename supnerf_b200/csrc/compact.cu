@@ -22,44 +22,30 @@ namespace snb {
 __global__ void __launch_bounds__(1024) compact_plan_kernel(const uint8_t* __restrict__ hit, int64_t n_rays, int S,
                                                            int32_t* __restrict__ order, int32_t* __restrict__ pos,
                                                            int64_t* __restrict__ counts) {
+  // every thread owns one contiguous chunk of rays: count its hits, block-scan the counts, then rank its rays (stable)
   __shared__ int warp_tot[32];
-  __shared__ int carry_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // pass 1: number of hits (to place the miss rays behind them)
-  int local = 0;
-  for (int64_t i = tid; i < n_rays; i += 1024) local += hit[i] ? 1 : 0;
+  const int64_t per = (n_rays + 1023) / 1024;
+  const int64_t i0 = (int64_t)tid * per, i1 = (i0 + per < n_rays) ? i0 + per : n_rays;
+  int cnt = 0;
+  for (int64_t i = i0; i < i1; ++i) cnt += hit[i] ? 1 : 0;
+  int incl = cnt;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-  if (lane == 0) warp_tot[warp] = local;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
   __syncthreads();
-  int n_hit = 0;
-  for (int w = 0; w < 32; ++w) n_hit += warp_tot[w];
-  __syncthreads();
-  if (tid == 0) carry_s = 0;
-  __syncthreads();
-  // pass 2: stable ranks, 1024 rays per round
-  for (int64_t base = 0; base < n_rays; base += 1024) {
-    const int64_t i = base + tid;
-    const int h = (i < n_rays && hit[i]) ? 1 : 0;
-    int incl = h;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    int before = carry_s;
-    for (int w = 0; w < warp; ++w) before += warp_tot[w];
-    const int hits_before = before + incl - h;          // hit rays with a smaller index
-    if (i < n_rays) {
-      const int p = h ? hits_before : (int)(i - hits_before);   // rank inside its class
-      pos[i] = p;
-      order[h ? p : n_hit + p] = (int32_t)i;
-    }
-    __syncthreads();
-    if (tid == 1023) carry_s = before + incl;
-    __syncthreads();
+  int before = 0, n_hit = 0;
+  for (int w = 0; w < 32; ++w) { const int t = warp_tot[w]; if (w < warp) before += t; n_hit += t; }
+  int hits_before = before + incl - cnt;      // hit rays with a smaller index than this thread's chunk
+  for (int64_t i = i0; i < i1; ++i) {
+    const int h = hit[i] ? 1 : 0;
+    const int p = h ? hits_before : (int)(i - hits_before);   // rank inside its class
+    pos[i] = p;
+    order[h ? p : n_hit + p] = (int32_t)i;
+    hits_before += h;
   }
   if (tid == 0) {
     const int64_t n_miss = n_rays - n_hit;

@@ -16,6 +16,12 @@ int compact_reduce(const float* g_sigma, const float* g_rgb, const int32_t* orde
 int compact_scatter(const float* g_xyz_c, const float* g_vrep_c, const uint8_t* hit, const int32_t* pos, const int64_t* counts,
                     int64_t n_rays, int S, float* g_xyz, float* g_vrep, cudaStream_t st);
 
+// sampler.cu: box-sampler backward reading the decoder's input gradients in compact row order (no scatter to dense)
+int sample_box_bwd_compact(const float* rays_o, const float* viewdir, const float* z_steps, const float* jitter, int64_t n_rays,
+                           int32_t n_samples, float half_diag, const float* h, const float* g_xyz_c, const float* g_vrep_c,
+                           const float* g_z_vals, const int32_t* pos, const int64_t* counts, float* g_rays_o, float* g_viewdir,
+                           cudaStream_t st);
+
 // mlp_tc.cu: m_dev (optional) = device-side number of rows actually present (a multiple of 128, <= M)
 bool tc_two_tile_active(const snb_handle_s* h);
 int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,

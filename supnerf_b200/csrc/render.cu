@@ -174,8 +174,11 @@ extern "C" int snb_render_bwd(snb_handle h, const snb_render_desc* d, const floa
                     F(sc, G.g_rgb_c), wsb + L.mlp, static_cast<uint8_t*>(sc) + G.mlp, pose ? F(sc, G.g_xyz_c) : nullptr,
                     pose ? F(sc, G.g_vrep_c) : nullptr, g_shape_latent, g_texture_latent, g_weights, st,
                     d->precision == SNB_PREC_BF16_TRAIN, counts + 3)) return 1;
-    if (pose && compact_scatter(F(sc, G.g_xyz_c), F(sc, G.g_vrep_c), wsb + L.hit, pos, counts, N, d->n_samples, F(sc, G.g_xyz),
-                                F(sc, G.g_vrep), st)) return 1;
+    if (!pose) return 0;
+    if (sample_box_bwd_compact(F(ws, L.rays_o), F(ws, L.viewdir), z_steps, jitter, N, d->n_samples, d->half_diag, d->aabb_half,
+                               F(sc, G.g_xyz_c), F(sc, G.g_vrep_c), F(sc, G.g_z), pos, counts, F(sc, G.g_rays_o), F(sc, G.g_viewdir), st))
+      return 1;
+    return snb_get_rays_bwd(px, py, N, K, c2w, F(sc, G.g_rays_o), F(sc, G.g_viewdir), g_c2w, stream);
   } else if (snb_mlp_bwd(h, d->precision, F(ws, L.xyz), F(ws, L.vrep), M, 1, shape_latent, texture_latent, F(ws, L.sigma),
                   F(sc, G.g_sigma), F(sc, G.g_rgbs), static_cast<const uint8_t*>(ws) + L.mlp, static_cast<uint8_t*>(sc) + G.mlp,
                   pose ? F(sc, G.g_xyz) : nullptr, pose ? F(sc, G.g_vrep) : nullptr, g_shape_latent, g_texture_latent, g_weights,

@@ -239,7 +239,8 @@ __global__ void __launch_bounds__(256) sample_box_bwd_kernel(
     const float* __restrict__ rays_o, const float* __restrict__ viewdir, const float* __restrict__ z_steps,
     const float* __restrict__ jitter, int64_t n_rays, int S, float half_diag, float hx, float hy, float hz,
     const float* __restrict__ g_xyz, const float* __restrict__ g_vrep, const float* __restrict__ g_zv,
-    float* __restrict__ g_rays_o, float* __restrict__ g_viewdir) {
+    float* __restrict__ g_rays_o, float* __restrict__ g_viewdir,
+    const int32_t* __restrict__ cpos, const int64_t* __restrict__ ccounts) {   // non-NULL: g_xyz / g_vrep are in compact.cu's row order
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -261,11 +262,14 @@ __global__ void __launch_bounds__(256) sample_box_bwd_kernel(
       const float zs = __fadd_rn(__ldg(z_steps + k), __fmul_rn(__ldg(jitter + idx), fstep));
       const float zc = __fadd_rn(__fmul_rn(near, __fsub_rn(1.f, zs)), __fmul_rn(far, zs));
       float gx[3] = {0.f, 0.f, 0.f};
-      if (g_xyz) { gx[0] = __ldg(g_xyz + 3 * idx); gx[1] = __ldg(g_xyz + 3 * idx + 1); gx[2] = __ldg(g_xyz + 3 * idx + 2); }
+      // compacted gradients: S rows per hit ray; a miss ray's single row stands for all its samples and is credited to the last one
+      int64_t gidx = idx;
+      if (cpos != nullptr) gidx = sl.hit ? (int64_t)cpos[ray] * S + k : (k == S - 1 ? ccounts[0] * S + cpos[ray] : -1);
+      if (g_xyz && gidx >= 0) { gx[0] = __ldg(g_xyz + 3 * gidx); gx[1] = __ldg(g_xyz + 3 * gidx + 1); gx[2] = __ldg(g_xyz + 3 * gidx + 2); }
       float gz = gx[0] * d[0] + gx[1] * d[1] + gx[2] * d[2];
 #pragma unroll
       for (int a = 0; a < 3; ++a) { gon[a] += gx[a]; gd[a] += zc * gx[a]; }
-      if (g_vrep) { gd[0] += __ldg(g_vrep + 3 * idx); gd[1] += __ldg(g_vrep + 3 * idx + 1); gd[2] += __ldg(g_vrep + 3 * idx + 2); }
+      if (g_vrep && gidx >= 0) { gd[0] += __ldg(g_vrep + 3 * gidx); gd[1] += __ldg(g_vrep + 3 * gidx + 1); gd[2] += __ldg(g_vrep + 3 * gidx + 2); }
       if (g_zv) {
         const float gv = __ldg(g_zv + idx);
         const float sgn = (zc > 0.f) ? 1.f : ((zc < 0.f) ? -1.f : 0.f);
@@ -441,10 +445,27 @@ extern "C" int snb_sample_box_bwd(const float* rays_o, const float* viewdir, con
   SNB_REQUIRE(grid > 0, "sample_box_bwd: no CUDA device");
   sample_box_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rays_o, viewdir, z_steps, jitter, n_rays, n_samples,
                                                                 half_diag, h[0], h[1], h[2], g_xyz, g_viewdir_rep, g_z_vals,
-                                                                g_rays_o, g_viewdir);
+                                                                g_rays_o, g_viewdir, nullptr, nullptr);
   SNB_LAUNCH_CHECK();
   return 0;
 }
+
+// internal (fused render with miss-ray compaction): g_xyz / g_viewdir_rep hold the decoder's input gradients in compact.cu's row
+// order (pos / counts from compact_plan); g_z_vals stays dense.  Replaces a scatter to dense + snb_sample_box_bwd.
+namespace snb {
+int sample_box_bwd_compact(const float* rays_o, const float* viewdir, const float* z_steps, const float* jitter, int64_t n_rays,
+                           int32_t n_samples, float half_diag, const float* h, const float* g_xyz_c, const float* g_vrep_c,
+                           const float* g_z_vals, const int32_t* pos, const int64_t* counts, float* g_rays_o, float* g_viewdir,
+                           cudaStream_t st) {
+  if (n_rays == 0) return 0;
+  int grid = ray_grid(n_rays, 8);
+  SNB_REQUIRE(grid > 0, "sample_box_bwd: no CUDA device");
+  sample_box_bwd_kernel<<<grid, 256, 0, st>>>(rays_o, viewdir, z_steps, jitter, n_rays, n_samples, half_diag, h[0], h[1], h[2],
+                                              g_xyz_c, g_vrep_c, g_z_vals, g_rays_o, g_viewdir, pos, counts);
+  SNB_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace snb
 
 extern "C" int snb_sample_shell_fwd(const float* rays_o, const float* viewdir, const float* z, int64_t n_rays,
                                     int32_t n_samples, float obj_diag, int32_t shapenet_swap,

@@ -44,8 +44,12 @@ class _DecoderBase(nn.Module):
         raise NotImplementedError
 
     def _weights(self):
+        layers = self.__dict__.get("_layer_cache")
+        if layers is None:   # the Linear modules are fixed after construction; their Parameters are read fresh every call
+            layers = self._decoder_layers()
+            self.__dict__["_layer_cache"] = layers
         out = []
-        for lin in self._decoder_layers():
+        for lin in layers:
             out += [lin.weight, lin.bias]
         return out
 
@@ -74,6 +78,8 @@ class _DecoderBase(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
+            if k == "_layer_cache":
+                continue
             setattr(new, k, {} if k == "_handles" else copy.deepcopy(v, memo))
         return new
 

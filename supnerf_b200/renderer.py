@@ -11,6 +11,20 @@ from . import models, ops
 from . import utils as U
 from .utils import get_rays, get_rays_specified, ray_box_intersection, ray_box_intersection_tensor  # noqa: F401
 
+_Z_STEPS = {}
+
+
+def _z_steps_on(device, n_samples):
+    """torch.linspace(0, 1 - 1/S, S) (renderer.py:36-38) on `device`, cached: a pure function of (S, device)."""
+    key = (str(device), int(n_samples))
+    z = _Z_STEPS.get(key)
+    if z is None:
+        step = 1.0 / n_samples
+        z = torch.linspace(0, 1 - step, n_samples, device=device)
+        _Z_STEPS[key] = z
+    return z
+
+
 FUSED_RENDER = True  # render_rays / render_rays_specified go through ops.render_box (one autograd node); False = staged ops
 
 
@@ -65,8 +79,7 @@ class NeRFRenderer(torch.nn.Module):
         device = torch.device(device)
         diag, half = ops.box_constants(obj_sz)
         n = px.numel()
-        step = 1.0 / self.n_samples
-        z_steps = torch.linspace(0, 1 - step, self.n_samples, device=device)
+        z_steps = _z_steps_on(device, self.n_samples)
         if jitter is None:
             jitter = torch.rand_like(torch.empty(n, self.n_samples, device=device))  # renderer.py:39-40
         prec = model.precision or models.get_default_precision()

@@ -164,7 +164,10 @@ def ray_box_intersection(ray_o, ray_d, aabb_min=None, aabb_max=None):
 
 
 def _resize_targets(img, mask_occ, im_sz):
-    """utils.py:448-453 (identical torchvision calls: they define rgb_tgt / occ_pixels)."""
+    """utils.py:448-453 (identical torchvision calls: they define rgb_tgt / occ_pixels).  When the crop already has the target
+    size torchvision's resize returns its input unchanged, so only the mask's int32 round trip remains."""
+    if img.shape[0] == im_sz and img.shape[1] == im_sz and mask_occ.shape[0] == im_sz and mask_occ.shape[1] == im_sz:
+        return img.unsqueeze(0), mask_occ.unsqueeze(0).type(torch.int32).type(torch.float32)
     img = img.unsqueeze(0).permute((0, 3, 1, 2))
     img = Resize((im_sz, im_sz))(img)
     img = img.permute((0, 2, 3, 1))
