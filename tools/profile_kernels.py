@@ -70,7 +70,9 @@ def composite_pass():
 
 
 decoder_pass()
-f, b = decoder_pass()
+for _ in range(3):
+    f, b = decoder_pass()
+    print(f"  pass: fwd {f:.3f} ms  bwd {b:.3f} ms")
 fl = 2 * 449664 * a.rays * S / 1e12
 print(f"decoder rays={a.rays} S={S}: fwd {f:.3f} ms ({fl / f * 1e3:.0f} TF/s)  bwd {b:.3f} ms ({fl / b * 1e3:.0f} TF/s)  [C-ABI call incl. latent kernels]")
 composite_pass()
