@@ -160,31 +160,54 @@ def run_ours(args):
         hobjs.append(dict(K=o["K"].pin_memory(), cam=o["cam_pose"].pin_memory(), wlh=o["wlh"], roi=o["roi"], img=o["img"].pin_memory(),
                           mask=o["mask_occ"].pin_memory(), shp=o["shapecode"].pin_memory(), tex=o["texturecode"].pin_memory()))
 
+    # Objects are independent: they alternate over `--streams` CUDA streams so that one object's small kernels
+    # (sampler, compaction, compositing, loss) fill the issue slots the other object's persistent decoder kernel leaves idle.
+    # Every step forks from / joins back into the timing stream on the device (no host synchronisation).
+    main_stream = torch.cuda.current_stream(dev)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, args.streams))] if args.streams > 1 else [main_stream]
+
+    def fork():
+        if len(streams) > 1:
+            for st_ in streams:
+                st_.wait_stream(main_stream)
+
+    def join():
+        if len(streams) > 1:
+            for st_ in streams:
+                main_stream.wait_stream(st_)
+
     def step_resident():
         """One pass over the batch through the public API (NeRFRenderer.render_rays -> fused C-ABI render) with every input
         already resident in HBM; the loss and its backward to pose + latents close the step."""
-        for d in dobjs:
-            d["cam"].grad = d["shp"].grad = d["tex"].grad = None
-            rgb, dep, acc, tgt, occ = R.render_rays(model, dev, d["img"], d["mask"], d["cam"], d["wlh"], d["K"], d["roi"], d["shp"], d["tex"],
-                                                    im_sz=IM_SZ)
-            loss = snb.losses.refine_loss(rgb, acc, tgt, occ, 0.1)[0]
-            loss.backward()
+        fork()
+        for i, d in enumerate(dobjs):
+            with torch.cuda.stream(streams[i % len(streams)]):
+                d["cam"].grad = d["shp"].grad = d["tex"].grad = None
+                rgb, dep, acc, tgt, occ = R.render_rays(model, dev, d["img"], d["mask"], d["cam"], d["wlh"], d["K"], d["roi"], d["shp"],
+                                                        d["tex"], im_sz=IM_SZ)
+                loss = snb.losses.refine_loss(rgb, acc, tgt, occ, 0.1)[0]
+                loss.backward()
+        join()
         return loss
 
     # pinned result buffers: per object the loss (1) + d cam_pose (12) + d shapecode (256) + d texturecode (256)
     res_host = torch.empty(N_OBJ, 1 + 12 + 512, dtype=torch.float32).pin_memory()
 
     def step_e2e():
+        fork()
         for i, h in enumerate(hobjs):
-            cam = h["cam"].to(dev, non_blocking=True).requires_grad_()
-            shp = h["shp"].to(dev, non_blocking=True).requires_grad_()
-            tex = h["tex"].to(dev, non_blocking=True).requires_grad_()
-            K = h["K"].to(dev, non_blocking=True)
-            rgb, dep, acc, tgt, occ = R.render_rays(model, dev, h["img"], h["mask"], cam, h["wlh"], K, h["roi"], shp, tex, im_sz=IM_SZ)
-            loss = snb.losses.refine_loss(rgb, acc, tgt, occ, 0.1)[0]
-            loss.backward()
-            # D2H read of the step's result: the loss and the gradients the refine loop consumes, into pinned memory
-            res_host[i].copy_(torch.cat([loss.detach().reshape(1), cam.grad.reshape(-1), shp.grad.reshape(-1), tex.grad.reshape(-1)]), non_blocking=True)
+            with torch.cuda.stream(streams[i % len(streams)]):
+                cam = h["cam"].to(dev, non_blocking=True).requires_grad_()
+                shp = h["shp"].to(dev, non_blocking=True).requires_grad_()
+                tex = h["tex"].to(dev, non_blocking=True).requires_grad_()
+                K = h["K"].to(dev, non_blocking=True)
+                rgb, dep, acc, tgt, occ = R.render_rays(model, dev, h["img"], h["mask"], cam, h["wlh"], K, h["roi"], shp, tex, im_sz=IM_SZ)
+                loss = snb.losses.refine_loss(rgb, acc, tgt, occ, 0.1)[0]
+                loss.backward()
+                # D2H read of the step's result: the loss and the gradients the refine loop consumes, into pinned memory
+                res_host[i].copy_(torch.cat([loss.detach().reshape(1), cam.grad.reshape(-1), shp.grad.reshape(-1), tex.grad.reshape(-1)]),
+                                  non_blocking=True)
+        join()
         torch.cuda.synchronize()   # every object's result is on the host when the step ends
         return float(res_host[:, 0].sum().item())
 
@@ -296,7 +319,7 @@ def run_ours(args):
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: AutoRF-mix (3/1/256) render fwd+bwd, 16 objects x 128x128 rays x 64 samples per GPU per step",
                        "objects_per_gpu": N_OBJ, "rays_per_object": n_rays, "samples_per_ray": N_SAMPLES, "weights": "frozen (refine mode)",
-                       "grads": "cam_pose, shapecode, texturecode", "parallelism": "object-parallel x%d, no collective" % world,
+                       "grads": "cam_pose, shapecode, texturecode", "parallelism": "object-parallel x%d, no collective" % world, "cuda_streams_per_gpu": len(streams),
                        "l2": "inputs larger than L2: per object ~45 MB of samples / decoder outputs / gradients and ~12 MB of ReLU masks stream through HBM, 16 objects per step",
                        "hit_fraction": round(hit_fraction, 4),
                        "precision": args.precision},
@@ -361,6 +384,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--streams", type=int, default=2, help="CUDA streams the independent objects alternate over (1 = one stream)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

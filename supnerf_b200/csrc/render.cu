@@ -13,12 +13,14 @@ using namespace snb;
 namespace {
 
 inline size_t al(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+// rows handed to the decoder as the host-side maximum: with compaction the real count is on the device and always a multiple
+// of the 128-row tile, so any ray / sample count works; without it the bf16 decoder needs N * S to be a multiple of 128 itself
+inline int64_t decoder_rows(snb_handle h, const snb_render_desc& d);
 
 // Miss-ray compaction (compact.cu) applies to the box render on the two-tile tensor-core decoder; SNB_NO_COMPACT=1 disables it.
 bool use_compaction(snb_handle h, const snb_render_desc& d) {
   static const bool off = [] { const char* e = getenv("SNB_NO_COMPACT"); return e && atoi(e) != 0; }();
-  return !off && d.mode == SNB_RENDER_BOX && d.precision != SNB_PREC_FP32 && tc_two_tile_active(h) &&
-         ((int64_t)d.n_rays * d.n_samples) % 128 == 0 && d.n_rays > 0;
+  return !off && d.mode == SNB_RENDER_BOX && d.precision != SNB_PREC_FP32 && tc_two_tile_active(h) && d.n_rays > 0;
 }
 
 // forward workspace (kept for the backward): rays_o, viewdir (N,3) | xyz, vrep (M,3) | z_vals (M) | sigma (M) | rgb (M,3) | mlp ws
@@ -46,7 +48,7 @@ struct FwdLayout {
     z = o; o += al(M * 4);
     sigma = o; o += al(M * 4);
     rgb = o; o += al(M * 12);
-    mlp = o; o += al(snb_mlp_workspace_bytes(h, (int64_t)M, 1, d.precision));
+    mlp = o; o += al(snb_mlp_workspace_bytes(h, decoder_rows(h, d), 1, d.precision));
     total = o;
   }
 };
@@ -71,10 +73,15 @@ struct BwdLayout {
     g_vrep = o; o += al(M * 12);
     g_rays_o = o; o += al(N * 12);
     g_viewdir = o; o += al(N * 12);
-    mlp = o; o += al(snb_mlp_bwd_scratch_bytes(h, (int64_t)M, 1, d.precision));
+    mlp = o; o += al(snb_mlp_bwd_scratch_bytes(h, decoder_rows(h, d), 1, d.precision));
     total = o;
   }
 };
+
+inline int64_t decoder_rows(snb_handle h, const snb_render_desc& d) {
+  const int64_t M = (int64_t)d.n_rays * d.n_samples;
+  return use_compaction(h, d) ? (M + 127) / 128 * 128 : M;
+}
 
 int check_desc(snb_handle h, const snb_render_desc* d, const char* who) {
   SNB_REQUIRE(h != nullptr && d != nullptr, "%s: null handle or descriptor", who);
@@ -131,7 +138,7 @@ extern "C" int snb_render_fwd(snb_handle h, const snb_render_desc* d, const floa
     int64_t* counts = reinterpret_cast<int64_t*>(wsb + L.counts);
     if (compact_plan(wsb + L.hit, N, d->n_samples, order, pos, counts, st)) return 1;
     if (compact_gather(F(ws, L.xyz), F(ws, L.vrep), order, counts, N, d->n_samples, F(ws, L.xyz_c), F(ws, L.vrep_c), st)) return 1;
-    if (tc_forward(h, F(ws, L.xyz_c), F(ws, L.vrep_c), M, 1, shape_latent, texture_latent, F(ws, L.sigma_c), F(ws, L.rgb_c),
+    if (tc_forward(h, F(ws, L.xyz_c), F(ws, L.vrep_c), decoder_rows(h, *d), 1, shape_latent, texture_latent, F(ws, L.sigma_c), F(ws, L.rgb_c),
                    wsb + L.mlp, st, d->precision == SNB_PREC_BF16_TRAIN, counts + 3)) return 1;
     if (compact_expand(F(ws, L.sigma_c), F(ws, L.rgb_c), wsb + L.hit, pos, counts, N, d->n_samples, F(ws, L.sigma), F(ws, L.rgb), st))
       return 1;
@@ -170,7 +177,7 @@ extern "C" int snb_render_bwd(snb_handle h, const snb_render_desc* d, const floa
     const int32_t* pos = reinterpret_cast<const int32_t*>(wsb + L.pos);
     const int64_t* counts = reinterpret_cast<const int64_t*>(wsb + L.counts);
     if (compact_reduce(F(sc, G.g_sigma), F(sc, G.g_rgbs), order, counts, N, d->n_samples, F(sc, G.g_sigma_c), F(sc, G.g_rgb_c), st)) return 1;
-    if (tc_backward(h, F(ws, L.xyz_c), F(ws, L.vrep_c), M, 1, shape_latent, texture_latent, F(ws, L.sigma_c), F(sc, G.g_sigma_c),
+    if (tc_backward(h, F(ws, L.xyz_c), F(ws, L.vrep_c), decoder_rows(h, *d), 1, shape_latent, texture_latent, F(ws, L.sigma_c), F(sc, G.g_sigma_c),
                     F(sc, G.g_rgb_c), wsb + L.mlp, static_cast<uint8_t*>(sc) + G.mlp, pose ? F(sc, G.g_xyz_c) : nullptr,
                     pose ? F(sc, G.g_vrep_c) : nullptr, g_shape_latent, g_texture_latent, g_weights, st,
                     d->precision == SNB_PREC_BF16_TRAIN, counts + 3)) return 1;

@@ -204,3 +204,32 @@ def test_tc_training_mode_through_fused_render():
     errs = {k: rel_err(grads["bf16"][k], grads["fp32"][k]) for k in grads["fp32"]}
     print(errs)
     assert all(e < TOL for e in errs.values()), {k: e for k, e in errs.items() if e >= TOL}
+
+
+def test_tc_fused_render_any_ray_count():
+    """With miss-ray compaction the decoder's row count is padded to the 128-row tile on the device, so the fused bf16 box render
+    accepts ray counts whose N * S is not a multiple of 128 (n_rays = 333 random rays x 50 samples); checked against the fp32
+    back end on the same rays."""
+    S = snb()
+    obj = oracle.synthetic_object(43, im_sz=32)
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=43)
+    shp0, tex0 = oracle.synthetic_latents(43, 1)
+    jit = torch.rand(333, 50, generator=torch.Generator().manual_seed(43))
+    R = S.renderer.NeRFRenderer(n_samples=50)
+    res = {}
+    for prec in ("fp32", "bf16"):
+        m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
+        m.precision = prec
+        m.requires_grad_(False)
+        cam = obj["cam_pose"].to(DEV).requires_grad_()
+        shp, tex = shp0.to(DEV).requires_grad_(), tex0.to(DEV).requires_grad_()
+        np.random.seed(3)
+        with forced_rand_like(jit):
+            rgb, dep, acc, tgt, occ = R.render_rays(m, DEV, obj["img"], obj["mask_occ"], cam, obj["wlh"], obj["K"].to(DEV), obj["roi"],
+                                                    shp, tex, im_sz=32, n_rays=333)
+        assert rgb.shape == (333, 3)
+        oracle.refine_losses(rgb, acc, tgt, occ)[0].backward()
+        res[prec] = [rgb, dep, acc, cam.grad, shp.grad, tex.grad]
+    errs = [rel_err(a, b) for a, b in zip(res["bf16"], res["fp32"])]
+    print(errs)
+    assert all(e < TOL for e in errs), errs
