@@ -487,6 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_const
         const Step& st = p.prog.s[si];
         const bool last = si + 1 == p.prog.n_steps;
         if (last && has_next) load_coords(pair + gridDim.x, xn, dn);   // the global latency hides behind rgb.0's MMAs
+        // (computing PE(xn) here as well was measured SLOWER: 16 more live registers spill in the rgb-head epilogue)
         mbar_wait(sm.bar(BAR_ACC + slot), acc_cnt & 1u);
         acc_cnt++;
         tc_fence_after();

@@ -145,10 +145,11 @@ __device__ __forceinline__ void trig_ladder(const float x[3], float s[DEG][3], f
   }
 }
 
-// Write PE(x) (model_codenerf.py:4-10 column order) as one bf16 row of the AUX chunk; this thread stores the 4 units of
-// its column half `hh` (columns 32*hh .. 32*hh+31); columns >= 3+6*DEG are zero.
+// PE(x) (model_codenerf.py:4-10 column order) as one bf16 row of 64 columns; this thread owns the 4 units of its column half
+// `hh` (columns 32*hh .. 32*hh+31); columns >= 3+6*DEG are zero.  pe_half computes them (16 packed words), store_pe_half writes
+// them into a 128B-swizzled chunk -- split so that the arithmetic can run before the chunk is free.
 template <int DEG>
-__device__ __forceinline__ void write_pe_row(uint8_t* aux, uint32_t row, uint32_t hh, const float x[3]) {
+__device__ __forceinline__ void pe_half(const float x[3], uint32_t hh, uint32_t (&pk)[16]) {
   float s[DEG][3], c[DEG][3];
   trig_ladder<DEG>(x, s, c);
   float v[64];
@@ -164,16 +165,18 @@ __device__ __forceinline__ void write_pe_row(uint8_t* aux, uint32_t row, uint32_
       v[3 + 3 * DEG + 3 * f + a] = c[f][a];
     }
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    if ((uint32_t)(u >> 2) == hh) {
-      uint4 q;
-      q.x = pack_bf16(v[8 * u + 0], v[8 * u + 1]);
-      q.y = pack_bf16(v[8 * u + 2], v[8 * u + 3]);
-      q.z = pack_bf16(v[8 * u + 4], v[8 * u + 5]);
-      q.w = pack_bf16(v[8 * u + 6], v[8 * u + 7]);
-      *reinterpret_cast<uint4*>(aux + swz(row, u)) = q;
-    }
-  }
+  for (int i = 0; i < 16; ++i) pk[i] = hh ? pack_bf16(v[32 + 2 * i], v[33 + 2 * i]) : pack_bf16(v[2 * i], v[2 * i + 1]);
+}
+__device__ __forceinline__ void store_pe_half(uint8_t* aux, uint32_t row, uint32_t hh, const uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    *reinterpret_cast<uint4*>(aux + swz(row, hh * 4u + (uint32_t)u)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+}
+template <int DEG>
+__device__ __forceinline__ void write_pe_row(uint8_t* aux, uint32_t row, uint32_t hh, const float x[3]) {
+  uint32_t pk[16];
+  pe_half<DEG>(x, hh, pk);
+  store_pe_half(aux, row, hh, pk);
 }
 
 // One 32-byte row of a bias stage: both 16-byte units hold {hi, mid, lo, 0, 0, 0, 0, 0}, the bf16 split of bias / 2, so the
