@@ -300,7 +300,8 @@ def run_ours(args):
     if dom:
         roofline = {"bound": "tensor", "kernel": "tc2_%s_kernel" % dom if args.precision == "bf16" else "sgemm_kernel (fp32 SIMT)",
                     "achieved": round(roof[dom]["tflops"], 2), "peak": peak, "unit": "TFLOP/s",
-                    "frac": round(roof[dom]["tflops"] / peak, 4) if peak else None, "traffic": traffic if args.precision == "bf16" else None,
+                    "frac": round(roof[dom]["tflops"] / peak, 4) if peak else None,
+                    "frac_vs_burst_peak": round(roof[dom]["tflops"] / pk["tf_burst"], 4) if args.precision == "bf16" else None, "traffic": traffic if args.precision == "bf16" else None,
                     "peak_source": pk["source"] + ", sustained bf16", "flop_per_launch": flop_per_launch,
                     "rows_executed_per_launch": rows, "rows_reference_semantics": rows_full, "hit_fraction": round(hit_fraction, 4),
                     "accounting": "achieved = 2 x 449664 MAC x rows the decoder EXECUTED (S per hit ray + 1 per miss ray, 128-row padded) / kernel time; "
@@ -311,6 +312,49 @@ def run_ours(args):
                     "timed": "CUDA events on the launch stream around the kernel alone, inside the timed region" if kern.get("fwd") else
                              "CUDA events around the decoder C-ABI call"}
 
+    # secondary roofline, HBM-bound: the compositing kernels on one step's worth of rays (16 x 16384 rays x 64 samples: 335 MB in,
+    # larger than L2), forward and backward, CUDA events around the C-ABI calls on the launch stream
+    comp = None
+    if rank == 0:
+        try:
+            nr = N_OBJ * n_rays
+            g = torch.Generator().manual_seed(0)
+            sg = (torch.rand(nr, N_SAMPLES, generator=g) * 4 - 1).to(dev)
+            cg = torch.rand(nr, N_SAMPLES, 3, generator=g).to(dev)
+            zg = (torch.rand(nr, N_SAMPLES, generator=g).sort(-1).values + 0.5).to(dev)
+            o3, o1, o2 = torch.empty(nr, 3, device=dev), torch.empty(nr, device=dev), torch.empty(nr, device=dev)
+            go3, go1, go2 = torch.rand(nr, 3, device=dev), torch.rand(nr, device=dev), torch.rand(nr, device=dev)
+            gsg, gcg, gzg = torch.empty_like(sg), torch.empty_like(cg), torch.empty_like(zg)
+            P, stp = _lib.ptr, _lib.stream_ptr()
+
+            def cf():
+                _lib.check(lib.snb_composite_fwd(P(sg), P(cg), P(zg), 1, nr, N_SAMPLES, 3, P(o3), P(o1), P(o2), stp), "composite_fwd")
+
+            def cb():
+                _lib.check(lib.snb_composite_bwd(P(sg), P(cg), P(zg), 1, nr, N_SAMPLES, 3, P(go3), P(go1), P(go2), P(gsg), P(gcg), P(gzg), stp),
+                           "composite_bwd")
+            res = {}
+            for name, fn, nbytes in (("fwd", cf, nr * (20 * N_SAMPLES + 20)), ("bwd", cb, nr * (40 * N_SAMPLES + 20))):
+                for _ in range(3):
+                    fn()
+                ts = []
+                for _ in range(7):
+                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a0.record(); fn(); a1.record()
+                    torch.cuda.synchronize()
+                    ts.append(a0.elapsed_time(a1))
+                t = float(np.median(ts))
+                res[name] = {"ms": round(t, 4), "gbs": round(nbytes / t / 1e6, 1), "frac": round(nbytes / t / 1e6 / peaks()["hbm"], 4),
+                             "algorithmic_bytes": int(nbytes)}
+            tot_b = res["fwd"]["algorithmic_bytes"] + res["bwd"]["algorithmic_bytes"]
+            tot_t = res["fwd"]["ms"] + res["bwd"]["ms"]
+            comp = {"bound": "hbm", "kernel": "composite_fwd4_kernel + composite_bwd4_kernel", "achieved": round(tot_b / tot_t / 1e6, 1),
+                    "peak": peaks()["hbm"], "unit": "GB/s", "frac": round(tot_b / tot_t / 1e6 / peaks()["hbm"], 4), "fwd": res["fwd"], "bwd": res["bwd"],
+                    "rays": nr, "samples_per_ray": N_SAMPLES, "bytes_per_ray": "fwd 20 S + 20, bwd 40 S + 20 (SURVEY 8d)",
+                    "timed": "CUDA events around the C-ABI call, median of 7, inputs 335 MB (> L2)"}
+            del sg, cg, zg, gsg, gcg, gzg
+        except Exception as exc:   # never lose the headline line over the secondary measurement
+            comp = {"error": str(exc)}
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -328,7 +372,7 @@ def run_ours(args):
                        "precision": args.precision},
             "e2e": {"value": round(e2e_value, 1), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
-            "gpu_launches": int(launches), "clocks": dict(clk.summary(), e2e_region=clk2.summary()), "roofline": roofline, "cpu_baseline": cpu}
+            "roofline_compositing": comp, "gpu_launches": int(launches), "clocks": dict(clk.summary(), e2e_region=clk2.summary()), "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
 
 
