@@ -373,7 +373,7 @@ def run_ours(args):
             "e2e": {"value": round(e2e_value, 1), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
             "roofline_compositing": comp, "gpu_launches": int(launches), "clocks": dict(clk.summary(), e2e_region=clk2.summary()), "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line))
+    print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
 # ----------------------------------------------------------------------------------------------------- CPU arms
@@ -421,10 +421,18 @@ def run_reference(args):
             "config": {"workload": "configs[1] (AutoRF-mix 3/1/256 render fwd+bwd), bounded sample: " + cpu["sample"]},
             "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": round(wall, 1)}
-    print(json.dumps(line))
+    print(json.dumps(line), file=JSON_OUT, flush=True)
+
+
+JSON_OUT = sys.stdout
 
 
 def main():
+    # stdout carries exactly ONE JSON line: anything a library prints there (e.g. NCCL's version banner under NCCL_DEBUG=VERSION)
+    # is diverted to stderr by pointing fd 1 at fd 2 and keeping a private handle on the real stdout for the result
+    global JSON_OUT
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

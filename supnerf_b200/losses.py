@@ -14,6 +14,9 @@ from . import _lib
 from ._lib import check, f32c, ptr, require_cuda, stream_ptr
 
 
+_SCRATCH_BYTES = None
+
+
 class _RefineLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rgb, acc, tgt, occ, coef, den):
@@ -24,7 +27,10 @@ class _RefineLoss(torch.autograd.Function):
         n = acc.numel()
         dev = rgb.device
         out = torch.empty(3, device=dev, dtype=torch.float32)
-        scratch = torch.empty(lib.snb_refine_loss_scratch_bytes(), dtype=torch.uint8, device=dev)
+        global _SCRATCH_BYTES
+        if _SCRATCH_BYTES is None:
+            _SCRATCH_BYTES = lib.snb_refine_loss_scratch_bytes()
+        scratch = torch.empty(_SCRATCH_BYTES, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             check(lib.snb_refine_loss_fwd(ptr(rgb), ptr(acc), ptr(tgt), ptr(occ), n, float(coef), ptr(den), ptr(out), ptr(scratch),
                                           stream_ptr()), "snb_refine_loss_fwd")

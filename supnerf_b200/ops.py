@@ -355,6 +355,23 @@ def decoder(handle, precision, xyz, viewdir, shape_latent, texture_latent, weigh
 # ---------------------------------------------------------------------------------------------------
 # fused box render of one object — renderer.py:125-165 (get_rays -> prepare_sampled_rays -> model -> volume_render)
 # ---------------------------------------------------------------------------------------------------
+_RENDER_SIZES = {}
+_ZEROS = {}
+
+
+def _zeros_like_cached(dev, n):
+    """Read-only zeros (n,) on `dev`, for upstream gradients autograd did not supply (never written by the kernels)."""
+    key = (str(dev), int(n))
+    z = _ZEROS.get(key)
+    if z is None:
+        if len(_ZEROS) > 64:
+            _ZEROS.clear()
+        z = torch.zeros(n, device=dev, dtype=torch.float32)
+        torch.cuda.current_stream(dev).synchronize()   # one-time: other streams may read it from now on
+        _ZEROS[key] = z
+    return z
+
+
 class _RenderBox(torch.autograd.Function):
     """One autograd node for the whole per-object render: two C-ABI calls (snb_render_fwd / snb_render_bwd), every
     intermediate in one workspace tensor.  Differentiable to cam_pose, the latents and (fp32 back end) the weights."""
@@ -380,7 +397,14 @@ class _RenderBox(torch.autograd.Function):
             handle.ensure_packed(weights)
             if any(ctx.needs_input_grad[13:]):
                 desc.precision = PREC_BF16_TRAIN
-        ws = torch.empty(lib.snb_render_workspace_bytes(handle.h, ctypes.byref(desc)), dtype=torch.uint8, device=dev)
+        key = (id(handle), n, int(n_samples), int(desc.precision), int(desc.mode))
+        sizes = _RENDER_SIZES.get(key)
+        if sizes is None:   # pure functions of (architecture, N, S, precision, mode)
+            if len(_RENDER_SIZES) > 512:
+                _RENDER_SIZES.clear()
+            sizes = (lib.snb_render_workspace_bytes(handle.h, ctypes.byref(desc)), lib.snb_render_bwd_scratch_bytes(handle.h, ctypes.byref(desc)))
+            _RENDER_SIZES[key] = sizes
+        ws = torch.empty(sizes[0], dtype=torch.uint8, device=dev)
         o_rgb = torch.empty(n, 3, device=dev, dtype=torch.float32)
         o_dep = torch.empty(n, device=dev, dtype=torch.float32)
         o_acc = torch.empty(n, device=dev, dtype=torch.float32)
@@ -390,8 +414,8 @@ class _RenderBox(torch.autograd.Function):
                                      ptr(shape_latent), ptr(texture_latent), ptr(o_rgb), ptr(o_dep), ptr(o_acc), ptr(hit), ptr(ws),
                                      stream_ptr()), "snb_render_fwd")
         ctx.save_for_backward(px, py, K, c2w, z_steps, jitter, shape_latent, texture_latent, ws, *weights)
-        ctx.meta = (handle, desc)
-        hitb = hit.bool()
+        ctx.meta = (handle, desc, sizes[1])
+        hitb = hit.view(torch.bool)   # 0 / 1 bytes: a zero-copy view
         ctx.mark_non_differentiable(hitb)
         return o_rgb, o_dep, o_acc, hitb
 
@@ -399,12 +423,12 @@ class _RenderBox(torch.autograd.Function):
     def backward(ctx, g_rgb, g_dep, g_acc, _g_hit):
         lib = _lib.load()
         px, py, K, c2w, z_steps, jitter, shape_latent, texture_latent, ws, *weights = ctx.saved_tensors
-        handle, desc = ctx.meta
+        handle, desc, scratch_bytes = ctx.meta
         n = px.numel()
         dev = px.device
         g_rgb = f32c(g_rgb) if g_rgb is not None else torch.zeros(n, 3, device=dev)
-        g_dep = f32c(g_dep) if g_dep is not None else torch.zeros(n, device=dev)
-        g_acc = f32c(g_acc) if g_acc is not None else torch.zeros(n, device=dev)
+        g_dep = f32c(g_dep) if g_dep is not None else _zeros_like_cached(dev, n)   # an unused output (e.g. depth): shared zeros
+        g_acc = f32c(g_acc) if g_acc is not None else _zeros_like_cached(dev, n)
         need = ctx.needs_input_grad
         g_c2w = torch.empty(3, 4, device=dev, dtype=torch.float32) if need[8] else None
         g_sl = torch.empty_like(shape_latent)
@@ -415,7 +439,7 @@ class _RenderBox(torch.autograd.Function):
             gws = [torch.empty_like(w, dtype=torch.float32).contiguous() for w in weights]
             gw_arr = (ctypes.c_void_p * len(gws))(*[g.data_ptr() for g in gws])
         handle.set_weights(weights)
-        scratch = torch.empty(lib.snb_render_bwd_scratch_bytes(handle.h, ctypes.byref(desc)), dtype=torch.uint8, device=dev)
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             check(lib.snb_render_bwd(handle.h, ctypes.byref(desc), ptr(px), ptr(py), ptr(K), ptr(c2w), ptr(z_steps), ptr(jitter),
                                      ptr(shape_latent), ptr(texture_latent), ptr(ws), ptr(g_rgb), ptr(g_dep), ptr(g_acc),
