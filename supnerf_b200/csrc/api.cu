@@ -193,7 +193,17 @@ extern "C" int snb_mlp_bwd(snb_handle h, int32_t precision, const float* xyz, co
                            float* g_viewdir, float* g_shape_latent, float* g_texture_latent, float* const* g_weights,
                            void* stream) {
   if (check_mlp_args(h, precision, M, B)) return 2;
-  if (M == 0) return 0;
+  if (M == 0) {   // no samples: every gradient is zero
+    cudaStream_t st0 = (cudaStream_t)stream;
+    if (g_shape_latent) SNB_CHECK_CUDA(cudaMemsetAsync(g_shape_latent, 0, sizeof(float) * B * h->arch.latent_dim, st0));
+    if (g_texture_latent) SNB_CHECK_CUDA(cudaMemsetAsync(g_texture_latent, 0, sizeof(float) * B * h->arch.latent_dim, st0));
+    if (g_weights)
+      for (size_t i = 0; i < h->layers.size(); ++i) {
+        SNB_CHECK_CUDA(cudaMemsetAsync(g_weights[2 * i], 0, sizeof(float) * h->layers[i].out * h->layers[i].in, st0));
+        SNB_CHECK_CUDA(cudaMemsetAsync(g_weights[2 * i + 1], 0, sizeof(float) * h->layers[i].out, st0));
+      }
+    return 0;
+  }
   SNB_REQUIRE(xyz && viewdir && shape_latent && texture_latent && sigma && g_sigma && g_rgb && workspace && scratch,
               "mlp_bwd: null pointer");
   if (precision != SNB_PREC_FP32)

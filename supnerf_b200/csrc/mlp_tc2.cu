@@ -318,7 +318,7 @@ __device__ __forceinline__ void mma_loop(const Params& p, const Smem& sm, int64_
           if (++stage == (uint32_t)kRing) { stage = 0; ph ^= 1u; }
         }
         if (saving) {   // the epilogue overwrites the chunks after BAR_ACC: the bulk store must have read them by then
-          if (lane_m == 0) bulk_wait_read_all();
+          if (lane_m == 0 && !(p.exp_flags & 8)) bulk_wait_read_all();   // exp flag 8 (timing experiment only, WRONG results): no wait
           __syncwarp();
         }
         umma_commit_elect(sm.bar(BAR_ACC + slot));

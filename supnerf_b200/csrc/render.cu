@@ -157,7 +157,16 @@ extern "C" int snb_render_bwd(snb_handle h, const snb_render_desc* d, const floa
   SNB_REQUIRE(g_shape_latent && g_texture_latent, "render_bwd: latent gradient outputs are required");
   cudaStream_t st = (cudaStream_t)stream;
   if (g_c2w) SNB_CHECK_CUDA(cudaMemsetAsync(g_c2w, 0, 12 * sizeof(float), st));
-  if (d->n_rays == 0) return 0;
+  if (d->n_rays == 0) {   // nothing rendered: every gradient is zero
+    SNB_CHECK_CUDA(cudaMemsetAsync(g_shape_latent, 0, sizeof(float) * h->arch.latent_dim, st));
+    SNB_CHECK_CUDA(cudaMemsetAsync(g_texture_latent, 0, sizeof(float) * h->arch.latent_dim, st));
+    if (g_weights)
+      for (size_t i = 0; i < h->layers.size(); ++i) {
+        SNB_CHECK_CUDA(cudaMemsetAsync(g_weights[2 * i], 0, sizeof(float) * h->layers[i].out * h->layers[i].in, st));
+        SNB_CHECK_CUDA(cudaMemsetAsync(g_weights[2 * i + 1], 0, sizeof(float) * h->layers[i].out, st));
+      }
+    return 0;
+  }
   const bool shell = d->mode == SNB_RENDER_SHELL;
   SNB_REQUIRE(px && py && K && c2w && z_steps && (jitter || shell) && shape_latent && texture_latent && workspace && g_rgb &&
               g_depth && g_acc && scratch, "render_bwd: null pointer");

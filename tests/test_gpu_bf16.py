@@ -233,3 +233,78 @@ def test_tc_fused_render_any_ray_count():
     errs = [rel_err(a, b) for a, b in zip(res["bf16"], res["fp32"])]
     print(errs)
     assert all(e < TOL for e in errs), errs
+
+
+@pytest.mark.parametrize("im,S_,label", [(128, 64, "C2 object"), (512, 128, "C4 object")])
+def test_full_size_properties_bf16(im, S_, label):
+    """BASELINE configs at FULL size on one GPU (C2: 128x128 rays x 64 samples; C4: 512x512 rays x 128 samples = 33.5 M samples):
+    size-independent properties -- hit mask bit-exact with the oracle's slab test, miss rays render the reference's closed form
+    (acc = 1, depth = diag/2), transmittance in [0, 1], and renders + pose/latent gradients of a strided ray subsample equal
+    to the fp32 oracle within the bf16 budget (the gradients of the loss restricted to the subsample)."""
+    S = snb()
+    obj = oracle.synthetic_object(71, im_sz=im)
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=71)
+    m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
+    m.precision = "bf16"
+    m.requires_grad_(False)
+    shp0, tex0 = oracle.synthetic_latents(71, 1)
+    n = im * im
+    torch.manual_seed(71)
+    torch.cuda.manual_seed(71)
+    jit_dev = torch.rand(n, S_, device=DEV)          # drawn on the device (33.5 M values for C4); the oracle gets the same rows
+    R = S.renderer.NeRFRenderer(n_samples=S_)
+    cam = obj["cam_pose"].to(DEV).requires_grad_()
+    shp, tex = shp0.to(DEV).requires_grad_(), tex0.to(DEV).requires_grad_()
+    with forced_rand_like(jit_dev):
+        rgb, dep, acc, tgt, occ = R.render_rays(m, DEV, obj["img"], obj["mask_occ"], cam, obj["wlh"], obj["K"].to(DEV), obj["roi"], shp, tex,
+                                                im_sz=im)
+    ids = torch.arange(0, n, max(n // 256, 1))
+    sel = torch.zeros(n, 1, device=DEV)
+    sel[ids.to(DEV)] = 1.0
+    oracle.refine_losses(rgb, acc, tgt, occ * sel)[0].backward()      # loss over the subsample only
+    # oracle on the subsample
+    cam_o = obj["cam_pose"].clone().requires_grad_()
+    s_o, t_o = shp0.clone().requires_grad_(), tex0.clone().requires_grad_()
+    o_rgb, o_dep, o_acc, o_hit = oracle.render_rays_box(sd, obj["K"], cam_o, obj["wlh"], obj["roi"], im, S_, s_o, t_o, jit_dev[ids.to(DEV)].cpu(),
+                                                        ray_ids=ids)
+    tg, oc = obj["img"].reshape(-1, 3)[ids], obj["mask_occ"].reshape(-1, 1)[ids]
+    oracle.refine_losses(o_rgb, o_acc, tg, oc)[0].backward()
+    errs = dict(rgb=rel_err(rgb[ids.to(DEV)], o_rgb), depth=rel_err(dep[ids.to(DEV)], o_dep), acc=rel_err(acc[ids.to(DEV)], o_acc),
+                g_pose=rel_err(cam.grad, cam_o.grad), g_shape=rel_err(shp.grad, s_o.grad), g_texture=rel_err(tex.grad, t_o.grad))
+    print(label, errs)
+    assert all(e < TOL for e in errs.values()), errs
+    # hit mask of ALL rays, bit-exact (slab test on the CPU oracle)
+    ro, vd = oracle.get_rays(obj["K"], obj["cam_pose"], obj["roi"], uv_steps=[im, im])
+    diag, half = oracle.box_constants(obj["wlh"])
+    hb = torch.from_numpy(half)
+    _, _, hit = oracle.ray_box_intersection(ro / (diag / 2), vd, -hb.expand_as(ro), hb.expand_as(ro))
+    rays_o, viewdir = S.utils.get_rays(obj["K"].to(DEV), obj["cam_pose"].to(DEV), obj["roi"], uv_steps=[im, im])
+    with forced_rand_like(jit_dev):
+        hit_gpu = R.prepare_sampled_rays(rays_o, viewdir, obj["wlh"])[3]
+    assert torch.equal(hit_gpu.cpu(), hit)
+    miss = ~hit
+    assert 0 < int(miss.sum()) < n
+    assert torch.all(acc.detach().cpu()[miss] == 1.0)
+    assert torch.allclose(dep.detach().cpu()[miss], torch.full((int(miss.sum()),), float(diag) / 2), rtol=1e-5)
+    a = acc.detach()
+    assert bool(((a >= 0) & (a <= 1.0 + 1e-6)).all()) and bool(torch.isfinite(rgb).all())
+
+
+def test_fused_render_empty_ray_set():
+    """n_rays = 0 (an empty random subset): every entry point returns empty tensors and zero gradients without launching."""
+    S = snb()
+    obj = oracle.synthetic_object(5, im_sz=16)
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=5)
+    for prec in ("fp32", "bf16"):
+        m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
+        m.precision = prec
+        m.requires_grad_(False)
+        shp0, tex0 = oracle.synthetic_latents(5, 1)
+        cam = obj["cam_pose"].to(DEV).requires_grad_()
+        shp, tex = shp0.to(DEV).requires_grad_(), tex0.to(DEV).requires_grad_()
+        R = S.renderer.NeRFRenderer(n_samples=64)
+        rgb, dep, acc, tgt, occ = R.render_rays(m, DEV, obj["img"], obj["mask_occ"], cam, obj["wlh"], obj["K"].to(DEV), obj["roi"], shp, tex,
+                                                im_sz=16, n_rays=0)
+        assert rgb.shape == (0, 3) and dep.shape == (0,) and acc.shape == (0,) and tgt.shape == (0, 3)
+        (rgb.sum() + acc.sum()).backward()
+        assert float(cam.grad.abs().sum()) == 0.0 and float(shp.grad.abs().sum()) == 0.0
