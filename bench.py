@@ -360,7 +360,8 @@ def run_ours(args):
         torch.distributed.destroy_process_group()
     if rank != 0:
         return
-    cpu = cpu_baseline(steps=3, warmup=1)
+    # the CPU arm is timed on rank 0 at N = 1 only (at N > 1 the other ranks' processes share the host cores)
+    cpu = cpu_baseline(steps=3, warmup=1) if world == 1 else None
     line = {"metric": METRIC, "value": round(value, 1), "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
