@@ -348,8 +348,17 @@ class _Decoder(torch.autograd.Function):
 
 def decoder(handle, precision, xyz, viewdir, shape_latent, texture_latent, weights):
     n_objs = shape_latent.shape[0]
-    return _Decoder.apply(handle, PREC[precision] if isinstance(precision, str) else precision, n_objs, xyz, viewdir,
-                          shape_latent, texture_latent, *weights)
+    prec = PREC[precision] if isinstance(precision, str) else precision
+    m = xyz.shape[0]
+    if prec == PREC["bf16"] and n_objs == 1 and m % 128 != 0 and m > 0:
+        # the tensor-core decoder works on 128-row tiles: pad a single object's rows with copies of its last row (outputs
+        # sliced off again, so the copies get zero upstream gradient).  Batched latents must bring tile-aligned row counts.
+        pad = 128 - m % 128
+        xyz_p = torch.cat([xyz, xyz[-1:].expand(pad, 3)])
+        vd_p = torch.cat([viewdir, viewdir[-1:].expand(pad, 3)])
+        sigma, rgb = _Decoder.apply(handle, prec, n_objs, xyz_p, vd_p, shape_latent, texture_latent, *weights)
+        return sigma[:m], rgb[:m]
+    return _Decoder.apply(handle, prec, n_objs, xyz, viewdir, shape_latent, texture_latent, *weights)
 
 
 # ---------------------------------------------------------------------------------------------------

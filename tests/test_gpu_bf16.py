@@ -100,8 +100,15 @@ def test_tc_weight_grads_fail_loudly_where_unsupported():
         sig, rgbs = m(xyz.to(DEV), vd.to(DEV), shp.to(DEV), tex.to(DEV))
         (sig.sum() + rgbs.sum()).backward()
     m.requires_grad_(False)
-    with pytest.raises(RuntimeError):  # 100 rows per object: not a multiple of the 128-row tile
-        m(xyz[:, :10].to(DEV)[:10], vd[:, :10].to(DEV)[:10], shp.to(DEV), tex.to(DEV))
+    # 100 rows of ONE object: padded to the 128-row tile internally
+    xs, vs = xyz[:, :10].to(DEV), vd[:, :10].to(DEV)          # 8 rays x 10 samples = 80 rows
+    sig, rgbs = m(xs, vs, shp.to(DEV), tex.to(DEV))
+    assert sig.shape == (8, 10, 1) and rgbs.shape == (8, 10, 3) and bool(torch.isfinite(sig).all())
+    sig_o, rgb_o = oracle.codenerf_decoder(sd, xs.cpu(), vs.cpu(), shp, tex)
+    assert rel_err(sig, sig_o) < TOL and rel_err(rgbs, rgb_o) < TOL
+    with pytest.raises(RuntimeError):  # batched latents: 50 rows per object cannot be tile-aligned
+        s2, t2 = oracle.synthetic_latents(2, 2)
+        m(xs, vs, s2.to(DEV), t2.to(DEV))   # 40 rows per object
 
 
 @pytest.mark.parametrize("blocks,B,n,S_", [((3, 1), 2, 64, 16), ((2, 1), 1, 256, 8)])
@@ -308,3 +315,27 @@ def test_fused_render_empty_ray_set():
         assert rgb.shape == (0, 3) and dep.shape == (0,) and acc.shape == (0,) and tgt.shape == (0, 3)
         (rgb.sum() + acc.sum()).backward()
         assert float(cam.grad.abs().sum()) == 0.0 and float(shp.grad.abs().sum()) == 0.0
+
+
+def test_render_full_img_bf16_ragged_rows():
+    """NeRFRenderer.render_full_img (renderer.py:238-294: row-chunked decode, chunk = roi side) in bf16 mode on a crop whose
+    chunk rows x samples is not a multiple of the 128-row tile (37 x 50): padded internally; image equals the fp32 back end."""
+    S = snb()
+    obj = oracle.synthetic_object(47, im_sz=8)
+    r = obj["roi"].clone()
+    roi = torch.tensor([int(r[0]), int(r[1]), int(r[0]) + 37, int(r[1]) + 37], dtype=r.dtype)
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=47)
+    shp, tex = oracle.synthetic_latents(47, 1)
+    imgs = {}
+    for prec in ("fp32", "bf16"):
+        m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
+        m.precision = prec
+        m.requires_grad_(False)
+        R = S.renderer.NeRFRenderer(n_samples=50)
+        torch.manual_seed(1); torch.cuda.manual_seed(1)
+        with torch.no_grad():
+            img, dep = R.render_full_img(m, DEV, obj["cam_pose"].to(DEV), obj["wlh"], obj["K"].to(DEV), roi, shp.to(DEV), tex.to(DEV),
+                                         out_depth=True)
+        assert img.shape == (37, 37, 3) and dep.shape == (37, 37)
+        imgs[prec] = (img, dep)
+    assert rel_err(imgs["bf16"][0], imgs["fp32"][0]) < TOL and rel_err(imgs["bf16"][1], imgs["fp32"][1]) < TOL
