@@ -22,30 +22,58 @@ namespace snb {
 __global__ void __launch_bounds__(1024) compact_plan_kernel(const uint8_t* __restrict__ hit, int64_t n_rays, int S,
                                                            int32_t* __restrict__ order, int32_t* __restrict__ pos,
                                                            int64_t* __restrict__ counts) {
-  // every thread owns one contiguous chunk of rays: count its hits, block-scan the counts, then rank its rays (stable)
+  // One block.  Pre-pass: total number of hits (so the miss rays can be placed behind them).  Then super-chunks of 16 384 rays:
+  // warp w owns 512 consecutive rays as 16 coalesced 32-byte rows held in registers (16 independent loads = one memory
+  // latency), ballots give the in-row ranks, a 32-entry shared-memory scan the warp offsets, a running carry the rest.
   __shared__ int warp_tot[32];
+  __shared__ int total_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t per = (n_rays + 1023) / 1024;
-  const int64_t i0 = (int64_t)tid * per, i1 = (i0 + per < n_rays) ? i0 + per : n_rays;
-  int cnt = 0;
-  for (int64_t i = i0; i < i1; ++i) cnt += hit[i] ? 1 : 0;
-  int incl = cnt;
+  const unsigned lt = (1u << lane) - 1u;
+  int local = 0;
+  for (int64_t i0 = 0; i0 < n_rays; i0 += 8 * 1024) {
+    int h[8];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
+    for (int k = 0; k < 8; ++k) { const int64_t i = i0 + (int64_t)k * 1024 + tid; h[k] = (i < n_rays && hit[i]) ? 1 : 0; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) local += h[k];
   }
-  if (lane == 31) warp_tot[warp] = incl;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if (lane == 0) warp_tot[warp] = local;
   __syncthreads();
-  int before = 0, n_hit = 0;
-  for (int w = 0; w < 32; ++w) { const int t = warp_tot[w]; if (w < warp) before += t; n_hit += t; }
-  int hits_before = before + incl - cnt;      // hit rays with a smaller index than this thread's chunk
-  for (int64_t i = i0; i < i1; ++i) {
-    const int h = hit[i] ? 1 : 0;
-    const int p = h ? hits_before : (int)(i - hits_before);   // rank inside its class
-    pos[i] = p;
-    order[h ? p : n_hit + p] = (int32_t)i;
-    hits_before += h;
+  if (tid == 0) { int t = 0; for (int w = 0; w < 32; ++w) t += warp_tot[w]; total_s = t; }
+  __syncthreads();
+  const int n_hit = total_s;
+  int carry = 0;   // hits in earlier super-chunks (identical in every thread)
+  for (int64_t sc = 0; sc < n_rays; sc += 16384) {
+    const int64_t wbase = sc + (int64_t)warp * 512;
+    unsigned m[16];
+    int wcnt = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int64_t i = wbase + k * 32 + lane;
+      m[k] = __ballot_sync(0xffffffffu, i < n_rays && hit[i]);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) wcnt += __popc(m[k]);
+    __syncthreads();                       // warp_tot is free again
+    if (lane == 0) warp_tot[warp] = wcnt;
+    __syncthreads();
+    int before = carry, chunk_tot = 0;
+    for (int w = 0; w < 32; ++w) { const int t = warp_tot[w]; if (w < warp) before += t; chunk_tot += t; }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int64_t i = wbase + k * 32 + lane;
+      const int h = (m[k] >> lane) & 1u;
+      const int hits_before = before + __popc(m[k] & lt);      // hit rays with a smaller index
+      if (i < n_rays) {
+        const int p = h ? hits_before : (int)(i - hits_before);   // rank inside its class
+        pos[i] = p;
+        order[h ? p : n_hit + p] = (int32_t)i;
+      }
+      before += __popc(m[k]);
+    }
+    carry += chunk_tot;
   }
   if (tid == 0) {
     const int64_t n_miss = n_rays - n_hit;
