@@ -364,7 +364,6 @@ def decoder(handle, precision, xyz, viewdir, shape_latent, texture_latent, weigh
 # ---------------------------------------------------------------------------------------------------
 # fused box render of one object — renderer.py:125-165 (get_rays -> prepare_sampled_rays -> model -> volume_render)
 # ---------------------------------------------------------------------------------------------------
-_RENDER_SIZES = {}
 _ZEROS = {}
 
 
@@ -406,13 +405,14 @@ class _RenderBox(torch.autograd.Function):
             handle.ensure_packed(weights)
             if any(ctx.needs_input_grad[13:]):
                 desc.precision = PREC_BF16_TRAIN
-        key = (id(handle), n, int(n_samples), int(desc.precision), int(desc.mode))
-        sizes = _RENDER_SIZES.get(key)
-        if sizes is None:   # pure functions of (architecture, N, S, precision, mode)
-            if len(_RENDER_SIZES) > 512:
-                _RENDER_SIZES.clear()
+        key = (n, int(n_samples), int(desc.precision), int(desc.mode))
+        cache = handle.__dict__.setdefault("_render_sizes", {})   # per handle: pure functions of (architecture, N, S, precision, mode)
+        sizes = cache.get(key)
+        if sizes is None:
+            if len(cache) > 512:
+                cache.clear()
             sizes = (lib.snb_render_workspace_bytes(handle.h, ctypes.byref(desc)), lib.snb_render_bwd_scratch_bytes(handle.h, ctypes.byref(desc)))
-            _RENDER_SIZES[key] = sizes
+            cache[key] = sizes
         ws = torch.empty(sizes[0], dtype=torch.uint8, device=dev)
         o_rgb = torch.empty(n, 3, device=dev, dtype=torch.float32)
         o_dep = torch.empty(n, device=dev, dtype=torch.float32)
