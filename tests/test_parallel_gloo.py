@@ -45,10 +45,12 @@ def _free_port():
 
 
 def _full_reference():
+    """float64 throughout: the test is about the sharding logic, not fp32 summation order (the pose gradient is ill-conditioned)."""
     obj = oracle.synthetic_object(5, im_sz=IM)
-    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=5)
-    shp, tex = oracle.synthetic_latents(5, 1)
-    jit = torch.rand(IM * IM, S, generator=torch.Generator().manual_seed(5))
+    obj = {k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in obj.items()}
+    sd = {k: v.double() for k, v in oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=5).items()}
+    shp, tex = [t.double() for t in oracle.synthetic_latents(5, 1)]
+    jit = torch.rand(IM * IM, S, generator=torch.Generator().manual_seed(5)).double()
     return obj, sd, shp, tex, jit
 
 
@@ -79,16 +81,34 @@ def _worker(rank, world, port, q):
 
 def test_ray_sharded_allreduce_matches_single_process():
     world = 2
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+
+    def run_world():
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        try:
+            out = sorted([q.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
+            for p in procs:
+                p.join(timeout=60)
+                if p.exitcode != 0:
+                    raise RuntimeError("worker exit code %r" % p.exitcode)
+            return out
+        finally:
+            for p in procs:
+                if p.is_alive():
+                    p.kill()
+
+    res, last = None, None
+    for _attempt in range(3):   # the rendezvous port is picked by bind-and-release: retry if another process grabbed it meanwhile
+        try:
+            res = run_world()
+            break
+        except Exception as exc:   # noqa: BLE001  (numeric checks below are NOT retried)
+            last = exc
+    assert res is not None, last
     # single-process truth
     obj, sd, shp0, tex0, jit = _full_reference()
     cam = obj["cam_pose"].clone().requires_grad_()
@@ -100,9 +120,9 @@ def test_ray_sharded_allreduce_matches_single_process():
     def rel(x, y):
         return ((x - y).abs().max() / y.abs().max()).item()
     for rank, l, g_cam, g_shp, g_tex, full_rgb in res:
-        assert abs(l - loss.item()) <= 1e-5 * abs(loss.item())
-        assert rel(g_cam, cam.grad) < 1e-4 and rel(g_shp, shp.grad) < 1e-4 and rel(g_tex, tex.grad) < 1e-4
-        assert rel(full_rgb, rgb.detach()) < 1e-6
+        assert abs(l - loss.item()) <= 1e-6 * abs(loss.item())          # the flat all-reduce buffer is fp32
+        assert rel(g_cam, cam.grad) < 1e-5 and rel(g_shp, shp.grad) < 1e-5 and rel(g_tex, tex.grad) < 1e-5
+        assert rel(full_rgb, rgb.detach()) < 1e-9
     # every rank ends with identical bits (so identical optimiser steps)
     for t0, t1 in zip(res[0][2:5], res[1][2:5]):
         assert torch.equal(t0, t1)
