@@ -213,6 +213,15 @@ int snb_refine_loss_fwd(const float* rgb, const float* acc, const float* tgt, co
 int snb_refine_loss_bwd(const float* rgb, const float* acc, const float* tgt, const float* occ, int64_t n_rays,
                         float occ_coef, const void* scratch, const float* g_loss, float* g_rgb, float* g_acc, void* stream);
 
+/* ---- multi-object scene compositor, merge step ------------------------------------------------
+ * Replaces scripts/demo.py:560-567: z_sort = sort(z_vals).values; z_args = searchsorted(z_sort, z_vals);
+ * sigmas_sort / rgbs_sort = zeros.scatter_(1, z_args, .) -- ties collide, the last element in index order wins, the other
+ * slots of the tie group stay zero.  z, sigma (R, K), rgb (R, K, 3) with K = objects x samples <= 1024; z_args (R, K) int64
+ * may be NULL.  Follow with snb_composite_fwd(sigma_sort, rgb_sort, z_sort, 1, R, K, SNB_WHITE_BKGD | SNB_SIGMA_RELU)
+ * (= volume_rendering3(..., white_bkgd=True), demo.py:569). */
+int snb_merge_sort_samples(const float* z, const float* sigma, const float* rgb, int64_t n_rays, int32_t n_per_ray,
+                           float* z_sort, float* sigma_sort, float* rgb_sort, int64_t* z_args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -417,3 +417,19 @@ def refine_losses(rgb_rays, acc_rays, rgb_tgt, occ_pixels, loss_occ_coef=0.1):
     loss_rgb = torch.sum((rgb_rays - rgb_tgt) ** 2 * torch.abs(occ_pixels)) / den
     loss_occ = torch.sum(torch.exp(-occ_pixels * (0.5 - acc_rays.unsqueeze(-1))) * torch.abs(occ_pixels)) / den
     return loss_rgb + loss_occ_coef * loss_occ, loss_rgb, loss_occ
+
+
+# --------------------------------------------------------------------------------------------------
+# next row: multi-object scene compositor, merge step
+# --------------------------------------------------------------------------------------------------
+def merge_objects(z_vals: Tensor, sigmas: Tensor, rgbs: Tensor):
+    """scripts/demo.py:560-567: sort every ray's Nb*S depths, ``searchsorted`` the originals into them and scatter sigma / rgb
+    to those slots.  Ties collide on one slot; the sequential CPU ``scatter_`` keeps the LAST element in index order and
+    leaves the other slots of the tie group zero (pinned by tests/golden/scene_merge.npz, produced by executing those very
+    source lines).  z_vals, sigmas (R,K); rgbs (R,K,3) -> z_sort, sigmas_sort, rgbs_sort, z_args."""
+    z_sort = torch.sort(z_vals, 1).values
+    z_args = torch.searchsorted(z_sort, z_vals.contiguous())
+    rgbs_sort = torch.zeros_like(rgbs).scatter_(1, z_args[:, :, None].repeat(1, 1, 3), rgbs)
+    sigmas_sort = torch.zeros_like(sigmas).scatter_(1, z_args, sigmas)
+    return z_sort, sigmas_sort, rgbs_sort, z_args
+

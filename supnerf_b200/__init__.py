@@ -8,7 +8,7 @@ Everything computes in hand-written CUDA kernels reached through the C ABI of li
 (include/supnerf_b200.h); there is no CPU or eager-PyTorch fallback."""
 from . import _lib, ops  # noqa: F401
 from .models import AutoRF, AutoRFMix, CodeNeRF, SUPNeRF, get_default_precision, set_default_precision  # noqa: F401
-from . import losses, parallel, refine, renderer, synthetic, utils  # noqa: F401,E402
+from . import losses, parallel, refine, renderer, scene, synthetic, utils  # noqa: F401,E402
 
-__all__ = ["renderer", "utils", "ops", "parallel", "synthetic", "losses", "refine", "CodeNeRF", "AutoRFMix", "SUPNeRF", "AutoRF", "set_default_precision",
+__all__ = ["renderer", "utils", "ops", "parallel", "synthetic", "losses", "refine", "scene", "CodeNeRF", "AutoRFMix", "SUPNeRF", "AutoRF", "set_default_precision",
            "get_default_precision"]

@@ -612,3 +612,27 @@ def test_device_side_shell_samples_match_host_built_vector():
         z_ref = torch.linspace(near + dist, far - dist, 64) + jit * (far - near) / (2 * 64)
         z = S.refine.shell_samples_on_device(obj["cam_pose"].to(DEV), diag, 64, jit.to(DEV))
         assert rel_err(z, z_ref) < 2e-7
+
+
+def test_scene_merge_kernel_golden_and_random():
+    """scene.merge_objects / render_merged (csrc/scene.cu) against the reference's own lines (fixture) and the oracle on a
+    larger random case with many ties: the searchsorted indices and the scattered values bit-exact, the render to 1e-5."""
+    S = snb()
+    g = load_golden("scene_merge")
+    zs, ss, cs, args = S.scene.merge_objects(T(g["z_vals"], device=DEV), T(g["sigmas"], device=DEV), T(g["rgbs"], device=DEV), return_args=True)
+    assert np.array_equal(args.cpu().numpy(), g["z_args"]) and np.array_equal(zs.cpu().numpy(), g["z_sort"])
+    assert np.array_equal(ss.cpu().numpy(), g["sigmas_sort"]) and np.array_equal(cs.cpu().numpy(), g["rgbs_sort"])
+    rgb, dep, acc = S.scene.render_merged(T(g["z_vals"], device=DEV), T(g["sigmas"], device=DEV), T(g["rgbs"], device=DEV))
+    assert rel_err(rgb, g["rgb"]) < TOL and rel_err(dep, g["depth"]) < TOL and rel_err(acc, g["acc"]) < TOL
+    gen = torch.Generator().manual_seed(3)
+    R_, Nb, S_ = 3000, 8, 64                                   # K = 512 samples per ray
+    z = (torch.rand(R_, Nb, S_, generator=gen) * 20).round() / 4      # quantised depths: many ties
+    z[torch.rand(R_, Nb, 1, generator=gen).expand(-1, -1, S_) < 0.4] = -1.0
+    z = z.reshape(R_, Nb * S_)
+    sig, col = torch.rand(R_, Nb * S_, generator=gen), torch.rand(R_, Nb * S_, 3, generator=gen)
+    o = oracle.merge_objects(z, sig, col)
+    k = S.scene.merge_objects(z.to(DEV), sig.to(DEV), col.to(DEV), return_args=True)
+    for a, b in zip(k, o):
+        assert torch.equal(a.cpu(), b)
+    with pytest.raises(S._lib.SnbError):
+        S.scene.merge_objects(z, sig, col)     # CPU tensors: no fallback

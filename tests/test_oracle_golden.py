@@ -167,3 +167,14 @@ def test_autorf_decoder():
     assert rel_err(tex.grad, g["g_texturecode"]) < 1e-5 and rel_err(vd.grad, g["g_viewdir"]) < 1e-5
     for k, v in sd.items():
         assert rel_err(v.grad, g["gw_" + k]) < 1e-5, k
+
+
+def test_scene_merge_oracle_matches_reference_lines():
+    """oracle.merge_objects + oracle.composite against the fixture produced by executing demo.py:560-569 itself."""
+    g = load_golden("scene_merge")
+    z_sort, s_sort, c_sort, args = oracle.merge_objects(T(g["z_vals"]), T(g["sigmas"]), T(g["rgbs"]))
+    assert np.array_equal(args.numpy(), g["z_args"]) and np.array_equal(z_sort.numpy(), g["z_sort"])
+    assert np.array_equal(s_sort.numpy(), g["sigmas_sort"]) and np.array_equal(c_sort.numpy(), g["rgbs_sort"])
+    rgb, dep, acc = oracle.composite(s_sort, c_sort, z_sort, white_bkgd=True)
+    assert rel_err(rgb, g["rgb"]) < 1e-6 and rel_err(dep, g["depth"]) < 1e-6 and rel_err(acc, g["acc"]) < 1e-6
+

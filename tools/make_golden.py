@@ -271,6 +271,33 @@ def golden_autorf():
          **{"gw_" + k: p.grad for k, p in model.named_parameters() if p.grad is not None and not k.startswith("img_encoder")})
 
 
+def golden_scene_merge():
+    """The merge step of the demo's scene compositor: the reference has no function for it, so the fixture EXECUTES the
+    reference's own source lines (scripts/demo.py:560-569, read from the read-only tree, dedented) on synthetic samples of
+    3 objects x 16 samples per ray, including rays that miss an object (z = -1, colour 1, sigma 0: demo.py:541, 555-556)."""
+    import textwrap
+    src = open("/root/reference/scripts/demo.py").read().splitlines()
+    block = textwrap.dedent("\n".join(src[559:569]))        # lines 560-569 (1-based)
+    assert block.lstrip().startswith("# sort by z values") and "z_args = torch.searchsorted(z_sort, z_vals)" in block and \
+        block.rstrip().endswith("volume_rendering3(sigmas_sort, rgbs_sort, z_sort, white_bkgd=True)"), block
+    g = torch.Generator().manual_seed(12)
+    Nr, Nb, n_samples = 64, 3, 16
+    z = torch.rand(Nr * Nb, n_samples, generator=g).sort(-1).values * 6 + 4 + torch.rand(Nr * Nb, 1, generator=g) * 3
+    sig = torch.rand(Nr * Nb, n_samples, generator=g) * 3 - 0.5
+    rgb = torch.rand(Nr * Nb, n_samples, 3, generator=g)
+    empty = torch.rand(Nr * Nb, 1, generator=g) < 0.3                     # this object is missed by this ray
+    z = torch.where(empty, torch.full_like(z, -1.0), z)
+    z[5, 3] = z[5, 7]                                                      # a genuine tie between two samples
+    sig = torch.where(empty, torch.zeros_like(sig), sig)
+    rgb = torch.where(empty.unsqueeze(-1), torch.ones_like(rgb), rgb)
+    env = dict(z_vals=z.clone(), sigmas=sig.clone(), rgbs=rgb.clone(), Nb=Nb, n_samples=n_samples, torch=torch,
+               volume_rendering3=ref_renderer.volume_rendering3)
+    exec(block, env)
+    save("scene_merge", n_objects=np.int64(Nb), n_samples=np.int64(n_samples), z_vals=z.view(-1, Nb * n_samples),
+         sigmas=sig.view(-1, Nb * n_samples), rgbs=rgb.view(-1, Nb * n_samples, 3), z_sort=env["z_sort"], z_args=env["z_args"],
+         sigmas_sort=env["sigmas_sort"], rgbs_sort=env["rgbs_sort"], rgb=env["rgb"], depth=env["depth"], acc=env["weights"])
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     golden_stages()
@@ -278,3 +305,4 @@ if __name__ == "__main__":
     golden_render_shell()
     golden_decoder_batch()
     golden_autorf()
+    golden_scene_merge()
