@@ -71,6 +71,24 @@ def allreduce_grads(params, loss=None, group=None):
     return buf[off] if loss is not None else None
 
 
+def allreduce_weight_grads(model, group=None, average=True):
+    """Data-parallel training: the batch is split by objects over the ranks, every rank back-propagates
+    its own objects, then ONE all_reduce(sum) over the flat buffer of all weight gradients (decoder: 0.7-1.1 M floats) and a
+    scale by 1/G -- what DistributedDataParallel's single bucket would do.  Per-instance latent codes stay rank-local (each
+    object lives on exactly one rank).  Parameters without a gradient are skipped consistently on every rank (they must be the
+    same set everywhere)."""
+    params = [p for p in model.parameters() if p.grad is not None]
+    if not params:
+        return 0
+    allreduce_grads(params, None, group)
+    if average and dist.is_available() and dist.is_initialized():
+        g = dist.get_world_size(group)
+        if g > 1:
+            for p in params:
+                p.grad.div_(g)
+    return sum(p.numel() for p in params)
+
+
 def render_rays_sharded(renderer, model, device, img, mask_occ, cam_pose, obj_sz, K, roi, shapecode, texturecode, im_sz=64,
                         rank=None, world=None):
     """Ray-sharded NeRFRenderer.render_rays (renderer.py:117-167 semantics, `n_rays=None`): renders only this rank's

@@ -126,3 +126,52 @@ def test_ray_sharded_allreduce_matches_single_process():
     # every rank ends with identical bits (so identical optimiser steps)
     for t0, t1 in zip(res[0][2:5], res[1][2:5]):
         assert torch.equal(t0, t1)
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+        x = torch.arange(4 * 7, dtype=torch.float32).reshape(4, 7) / 10.0
+        mine = parallel.object_shard(4, rank, world)            # objects r, r+G, ...
+        model(x[mine]).pow(2).sum().backward()
+        n = parallel.allreduce_weight_grads(model)
+        q.put((rank, n, [p.grad.clone() for p in model.parameters()]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_weight_gradient_allreduce():
+    """C5 host logic: objects split over 2 ranks, one flat all-reduce of the weight gradients, averaged."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    res, last = None, None
+    for _attempt in range(3):
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_dp_worker, args=(r, world, port, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        try:
+            res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
+            for p in procs:
+                p.join(timeout=60)
+            break
+        except Exception as exc:   # noqa: BLE001
+            last = exc
+        finally:
+            for p in procs:
+                if p.is_alive():
+                    p.kill()
+    assert res is not None, last
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    x = torch.arange(4 * 7, dtype=torch.float32).reshape(4, 7) / 10.0
+    model(x).pow(2).sum().backward()
+    for rank, n, grads in res:
+        assert n == sum(p.numel() for p in model.parameters())
+        for g, p in zip(grads, model.parameters()):
+            assert torch.allclose(g, p.grad / world, rtol=1e-5, atol=1e-7)
+
