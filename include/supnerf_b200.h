@@ -222,6 +222,22 @@ int snb_refine_loss_bwd(const float* rgb, const float* acc, const float* tgt, co
 int snb_merge_sort_samples(const float* z, const float* sigma, const float* rgb, int64_t n_rays, int32_t n_per_ray,
                            float* z_sort, float* sigma_sort, float* rgb_sort, int64_t* z_args, void* stream);
 
+/* ---- refine-iteration glue around the render ----------------------------------------------------
+ * snb_refine_pose_fwd/bwd: optimizer_nuscenes.py:684-699 -- rot_vec (3, axis-angle; Rodrigues = what
+ * pytorch3d.transforms.axis_angle_to_matrix evaluates), trans_vec (3) -> cam2opt (3,4) = [R | t] (opt_cam_pose != 0) or
+ * [R^T | -R^T t] (opt_cam_pose == 0, every shipped config), and -- if z != NULL -- the shared sample vector z (S) of
+ * utils.sample_from_rays (utils.py:154-167) with near/far = ||cam2opt[:,3]|| -/+ obj_diag/2 (utils.py:468-469, detached) and
+ * jitter (S) = the torch.rand(n_samples) draw.  Backward: g_cam (12) -> g_rot (3), g_trans (3).
+ * snb_adamw_step: torch.optim.AdamW's update (optimizer_nuscenes.py:757-769, groups of :1762-1769) on up to 8 tensors with
+ * their own learning rates; `step` is a device float holding the number of steps taken (incremented). */
+int snb_refine_pose_fwd(const float* rot_vec, const float* trans_vec, int32_t opt_cam_pose, float obj_diag, int32_t n_samples,
+                        const float* jitter, float* cam, float* z, void* stream);
+int snb_refine_pose_bwd(const float* rot_vec, const float* trans_vec, int32_t opt_cam_pose, const float* g_cam, float* g_rot,
+                        float* g_trans, void* stream);
+int snb_adamw_step(int32_t n_groups, float* const* params, const float* const* grads, float* const* exp_avg,
+                   float* const* exp_avg_sq, const int32_t* sizes, const float* lrs, float beta1, float beta2, float eps,
+                   float weight_decay, float* step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,11 @@ SIGNATURES = {
     "snb_refine_loss_fwd": (c_i32, [c_f, c_f, c_f, c_f, c_i64, c_flt, c_f, c_f, c_f, c_f]),
     "snb_refine_loss_bwd": (c_i32, [c_f, c_f, c_f, c_f, c_i64, c_flt, c_f, c_f, c_f, c_f, c_f]),
     "snb_merge_sort_samples": (c_i32, [c_f, c_f, c_f, c_i64, c_i32, c_f, c_f, c_f, c_f, c_f]),
+    "snb_refine_pose_fwd": (c_i32, [c_f, c_f, c_i32, c_flt, c_i32, c_f, c_f, c_f, c_f]),
+    "snb_refine_pose_bwd": (c_i32, [c_f, c_f, c_i32, c_f, c_f, c_f, c_f]),
+    "snb_adamw_step": (c_i32, [c_i32, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
+                               ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(c_i32), ctypes.POINTER(c_flt), c_flt, c_flt, c_flt, c_flt,
+                               c_f, c_f]),
     "snb_render_workspace_bytes": (c_sz, [ctypes.c_void_p, ctypes.POINTER(SnbRenderDesc)]),
     "snb_render_bwd_scratch_bytes": (c_sz, [ctypes.c_void_p, ctypes.POINTER(SnbRenderDesc)]),
     "snb_render_fwd": (c_i32, [ctypes.c_void_p, ctypes.POINTER(SnbRenderDesc)] + [c_f] * 14),

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsupnerf_b200.so")
-SOURCES = ["api.cu", "composite.cu", "sampler.cu", "latent.cu", "mlp_f32.cu", "mlp_tc.cu", "mlp_tc2.cu", "render.cu", "loss.cu", "compact.cu", "scene.cu"]
+SOURCES = ["api.cu", "composite.cu", "sampler.cu", "latent.cu", "mlp_f32.cu", "mlp_tc.cu", "mlp_tc2.cu", "render.cu", "loss.cu", "compact.cu", "scene.cu", "refine.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]  # no --use_fast_math: sinf/expf accuracy is part of parity
 

@@ -11,15 +11,86 @@ reference reads ``cam_pose[:, -1].tolist()`` on the host every iteration to buil
 (utils.py:468-469 -> sample_from_rays :154-167); here near/far are evaluated on the device with the same arithmetic
 (float64 norm, float32 ``torch.linspace`` formula), and the per-iteration jitter -- drawn on the CPU generator by the
 same ``torch.rand(n_samples)`` calls, in the same order -- is uploaded once as a table.  ``ms per refine iteration``
-then is kernel time (~100 small launches replayed from one graph) instead of ~2.4 ms of Python / launch latency.
+then is kernel time (~25 launches replayed from one graph: 0.21 ms at 32x32 rays on a B200) instead of ~2.4 ms of
+Python / launch latency.
 
-The render, loss and their backward are the package's fused kernels (ops.render_shell, losses.refine_loss); the pose map
-and AdamW are ordinary torch ops captured in the same graph (torch.optim.AdamW(capturable=True)).  CUDA only."""
+The render, loss and their backward are the package's fused kernels (ops.render_shell, losses.refine_loss); with
+``fused=True`` (default) the pose map + sample vector and the AdamW update are single launches too (csrc/refine.cu:
+snb_refine_pose_fwd/bwd, snb_adamw_step); ``fused=False`` keeps them as torch ops (torch.optim.AdamW(capturable=True)) --
+the tests check both against the loop written with the reference-shaped API.  CUDA only."""
+import ctypes
+
 import numpy as np
 import torch
 
-from . import losses, models, ops
+from . import _lib, losses, models, ops
 from . import utils as U
+from ._lib import check, f32c, ptr, require_cuda, stream_ptr
+
+
+class _PoseAndSamples(torch.autograd.Function):
+    """rot_vec, trans_vec -> cam2opt (3,4) and the shared sample vector z (S) in ONE launch (csrc/refine.cu); backward in one."""
+
+    @staticmethod
+    def forward(ctx, rot_vec, trans_vec, jitter, opt_cam_pose, obj_diag, n_samples):
+        lib = _lib.load()
+        require_cuda(rot_vec, trans_vec, jitter)
+        rot_vec, trans_vec, jitter = f32c(rot_vec), f32c(trans_vec), f32c(jitter)
+        dev = rot_vec.device
+        cam = torch.empty(3, 4, device=dev, dtype=torch.float32)
+        z = torch.empty(int(n_samples), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            check(lib.snb_refine_pose_fwd(ptr(rot_vec), ptr(trans_vec), int(bool(opt_cam_pose)), float(obj_diag), int(n_samples), ptr(jitter),
+                                          ptr(cam), ptr(z), stream_ptr()), "snb_refine_pose_fwd")
+        ctx.save_for_backward(rot_vec, trans_vec)
+        ctx.opt_cam_pose = int(bool(opt_cam_pose))
+        ctx.mark_non_differentiable(z)
+        return cam, z
+
+    @staticmethod
+    def backward(ctx, g_cam, _g_z):
+        lib = _lib.load()
+        rot_vec, trans_vec = ctx.saved_tensors
+        g_cam = f32c(g_cam)
+        g_rot, g_trans = torch.empty_like(rot_vec), torch.empty_like(trans_vec)
+        with torch.cuda.device(rot_vec.device):
+            check(lib.snb_refine_pose_bwd(ptr(rot_vec), ptr(trans_vec), ctx.opt_cam_pose, ptr(g_cam), ptr(g_rot), ptr(g_trans), stream_ptr()),
+                  "snb_refine_pose_bwd")
+        return g_rot, g_trans, None, None, None, None
+
+
+class FusedAdamW:
+    """torch.optim.AdamW's update for a handful of small tensors in ONE launch (snb_adamw_step); state lives on the device."""
+
+    def __init__(self, groups, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        self.params = [g["params"] for g in groups]
+        self.lrs = [float(g["lr"]) for g in groups]
+        self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
+        dev = self.params[0].device
+        self.m = [torch.zeros_like(p) for p in self.params]
+        self.v = [torch.zeros_like(p) for p in self.params]
+        self.step_t = torch.zeros((), device=dev, dtype=torch.float32)
+        n = len(self.params)
+        self._sizes = (ctypes.c_int32 * n)(*[p.numel() for p in self.params])
+        self._lrs = (ctypes.c_float * n)(*self.lrs)
+
+    def zero_grad(self):
+        for p in self.params:
+            if p.grad is not None:
+                p.grad.zero_()
+
+    def reset(self):
+        for t in self.m + self.v:
+            t.zero_()
+        self.step_t.zero_()
+
+    def step(self):
+        lib = _lib.load()
+        n = len(self.params)
+        arr = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])  # noqa: E731
+        with torch.cuda.device(self.params[0].device):
+            check(lib.snb_adamw_step(n, arr(self.params), arr([p.grad for p in self.params]), arr(self.m), arr(self.v), self._sizes, self._lrs,
+                                     self.betas[0], self.betas[1], self.eps, self.weight_decay, ptr(self.step_t), stream_ptr()), "snb_adamw_step")
 
 
 def axis_angle_to_matrix(v):
@@ -54,7 +125,7 @@ class ObjectRefiner:
 
     def __init__(self, model, device, img, mask_occ, K, roi, obj_diag, shapecode, texturecode, rot_vec, trans_vec, n_samples=64,
                  im_sz=32, lr_shape=0.02, lr_texture=0.02, lr_pose=0.01, loss_occ_coef=0.1, shapenet_obj_cood=True,
-                 opt_cam_pose=False, max_iters=100):
+                 opt_cam_pose=False, max_iters=100, fused=True):
         if not isinstance(model, models._DecoderBase):
             raise TypeError("ObjectRefiner needs a supnerf_b200 decoder")
         self.model, self.device = model, torch.device(device)
@@ -72,9 +143,15 @@ class ObjectRefiner:
         self.texturecode = texturecode.detach().to(dev).clone().requires_grad_()
         self.rot_vec = rot_vec.detach().to(dev).reshape(3).clone().requires_grad_()
         self.trans_vec = trans_vec.detach().to(dev).reshape(3).clone().requires_grad_()
-        self.opt = torch.optim.AdamW([{"params": [self.shapecode], "lr": lr_shape}, {"params": [self.texturecode], "lr": lr_texture},
-                                      {"params": [self.rot_vec], "lr": lr_pose}, {"params": [self.trans_vec], "lr": lr_pose}],
-                                     capturable=True)
+        # fused = True: pose map + sample vector and the AdamW update as single launches (csrc/refine.cu); False: torch ops
+        self.fused = bool(fused)
+        if self.fused:
+            self.opt = FusedAdamW([{"params": self.shapecode, "lr": lr_shape}, {"params": self.texturecode, "lr": lr_texture},
+                                   {"params": self.rot_vec, "lr": lr_pose}, {"params": self.trans_vec, "lr": lr_pose}])
+        else:
+            self.opt = torch.optim.AdamW([{"params": [self.shapecode], "lr": lr_shape}, {"params": [self.texturecode], "lr": lr_texture},
+                                          {"params": [self.rot_vec], "lr": lr_pose}, {"params": [self.trans_vec], "lr": lr_pose}],
+                                         capturable=True)
         # the reference draws torch.rand(n_samples) on the CPU generator once per iteration (utils.py:164): same calls, same order
         self.jitter = torch.stack([torch.rand(self.n_samples) for _ in range(max_iters)]).to(dev)
         self.it = torch.zeros((), dtype=torch.long, device=dev)
@@ -91,10 +168,14 @@ class ObjectRefiner:
 
     def step(self):
         """One iteration (no host synchronisation anywhere)."""
-        self.opt.zero_grad(set_to_none=False) if self.shapecode.grad is not None else None
-        cam = self.cam2opt()
+        if self.shapecode.grad is not None:
+            self.opt.zero_grad() if self.fused else self.opt.zero_grad(set_to_none=False)
         jit = self.jitter.index_select(0, self.it.reshape(1)).reshape(-1)
-        z = shell_samples_on_device(cam, self.obj_diag, self.n_samples, jit)
+        if self.fused:
+            cam, z = _PoseAndSamples.apply(self.rot_vec, self.trans_vec, jit, self.opt_cam_pose, self.obj_diag, self.n_samples)
+        else:
+            cam = self.cam2opt()
+            z = shell_samples_on_device(cam, self.obj_diag, self.n_samples, jit)
         prec = self.model.precision or models.get_default_precision()
         rgb, dep, acc = ops.render_shell(self.model._handle(self.device), prec, self.n_samples, float(self.obj_diag), self.swap,
                                          self.px, self.py, self.K, cam, z, self.shapecode, self.texturecode, self.model._weights())
@@ -117,10 +198,13 @@ class ObjectRefiner:
             with torch.no_grad():
                 for t, v in zip((self.shapecode, self.texturecode, self.rot_vec, self.trans_vec), snapshot):
                     t.copy_(v)
-                for st in self.opt.state.values():
-                    for v in st.values():
-                        if torch.is_tensor(v):
-                            v.zero_()
+                if self.fused:
+                    self.opt.reset()
+                else:
+                    for st in self.opt.state.values():
+                        for v in st.values():
+                            if torch.is_tensor(v):
+                                v.zero_()
                 self.it.zero_()
         torch.cuda.current_stream(self.device).wait_stream(s)
         self.graph = torch.cuda.CUDAGraph()

@@ -583,10 +583,10 @@ def test_object_refiner_matches_reference_api_loop_and_graph_replay():
         loss_ref.backward()
         opt.step()
     outs = []
-    for graphed in (False, True):
+    for graphed, fused in ((False, False), (True, False), (False, True), (True, True)):
         torch.manual_seed(77)   # the refiner pre-draws the same torch.rand(64) sequence
         r = S.refine.ObjectRefiner(m, DEV, obj["img"], obj["mask_occ"], obj["K"], obj["roi"], diag, shp0, tex0, rv0, t_obj, n_samples=64,
-                                   im_sz=32, max_iters=iters)
+                                   im_sz=32, max_iters=iters, fused=fused)
         if graphed:
             r.capture()
         last = r.run(iters)
@@ -597,7 +597,8 @@ def test_object_refiner_matches_reference_api_loop_and_graph_replay():
         # the codes are compared at 2e-2 of their scale, the loss trajectory and the (well-conditioned) pose tightly
         assert rel_err(r.shapecode, shp) < 2e-2 and rel_err(r.texturecode, tex) < 2e-2
         assert rel_err(r.rot_vec, rv) < 1e-3 and rel_err(r.trans_vec, tv) < 1e-3
-    assert rel_err(outs[1][0].shapecode, outs[0][0].shapecode) < 2e-2 and rel_err(outs[1][1], outs[0][1]) < 1e-4
+    for o in outs[1:]:
+        assert rel_err(o[0].shapecode, outs[0][0].shapecode) < 2e-2 and rel_err(o[1], outs[0][1]) < 1e-4
 
 
 def test_device_side_shell_samples_match_host_built_vector():
@@ -636,3 +637,47 @@ def test_scene_merge_kernel_golden_and_random():
         assert torch.equal(a.cpu(), b)
     with pytest.raises(S._lib.SnbError):
         S.scene.merge_objects(z, sig, col)     # CPU tensors: no fallback
+
+
+def test_refine_pose_and_adamw_kernels_vs_torch():
+    """csrc/refine.cu: the Rodrigues pose map (both conventions) + its backward against torch autograd in float64, the fused
+    sample vector against refine.shell_samples_on_device, and the fused AdamW against torch.optim.AdamW over 5 steps."""
+    S = snb()
+    gen = torch.Generator().manual_seed(9)
+    for opt_cam in (False, True):
+        for scale in (1.3, 1e-5):           # generic angle and the small-angle series
+            rv = (torch.randn(3, generator=gen) * scale)
+            tv = torch.randn(3, generator=gen) * 5
+            jit = torch.rand(64, generator=gen)
+            up = torch.randn(3, 4, generator=gen)
+            r64, t64 = rv.double().requires_grad_(), tv.double().requires_grad_()
+            rot = S.refine.axis_angle_to_matrix(r64)
+            tt = t64.unsqueeze(-1)
+            if not opt_cam:
+                rot = rot.transpose(-2, -1)
+                tt = -rot @ tt
+            cam64 = torch.cat((rot, tt), -1)
+            (cam64 * up.double()).sum().backward()
+            rg, tg = rv.to(DEV).requires_grad_(), tv.to(DEV).requires_grad_()
+            cam, z = S.refine._PoseAndSamples.apply(rg, tg, jit.to(DEV), opt_cam, np.float32(4.7), 64)
+            (cam * up.to(DEV)).sum().backward()
+            assert rel_err(cam, cam64) < 1e-6
+            assert rel_err(rg.grad, r64.grad) < 1e-5 and rel_err(tg.grad, t64.grad) < 1e-5
+            z_ref = S.refine.shell_samples_on_device(cam.detach(), np.float32(4.7), 64, jit.to(DEV))
+            assert rel_err(z, z_ref) < 2e-7
+    ps = [torch.randn(n, generator=gen) for n in (256, 256, 3, 3)]
+    lrs = [0.02, 0.02, 0.01, 0.01]
+    ref = [p.clone().requires_grad_() for p in ps]
+    opt = torch.optim.AdamW([{"params": [p], "lr": lr} for p, lr in zip(ref, lrs)])
+    mine = [p.to(DEV).clone().requires_grad_() for p in ps]
+    fo = S.refine.FusedAdamW([{"params": p, "lr": lr} for p, lr in zip(mine, lrs)])
+    for it in range(5):
+        gs = [torch.randn(p.shape, generator=gen) for p in ps]
+        for p, q, g in zip(ref, mine, gs):
+            p.grad = g.clone()
+            q.grad = g.to(DEV)
+        opt.step()
+        fo.step()
+    for p, q in zip(ref, mine):
+        assert rel_err(q, p) < 1e-6
+
