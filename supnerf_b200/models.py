@@ -72,6 +72,30 @@ class _DecoderBase(nn.Module):
                                  shape_latent, texture_latent, self._weights())
         return sigma.reshape(*lead, 1), rgb.reshape(*lead, 3)
 
+    # ---- checkpoints: the reference saves the WHOLE module (optimizer_nuscenes.py:1795-1796 loads saved['model_params'] with the
+    # default strict=True); AutoRFMix / SUPNeRF checkpoints also carry the image encoder / pose head, which are not on this path.
+    # Those entries are kept verbatim (and re-emitted by state_dict()) so that a reference checkpoint loads and round-trips.
+    _OFFPATH_PREFIXES = ("img_encoder.", "pose_layer_", "regress_layer_", "out_delta_layer", "out_wlh_layer", "pose_encoder",
+                         "encoder.", "wlh_layer")
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        own = set(super().state_dict().keys())
+        mine, off = {}, {}
+        for k, v in state_dict.items():
+            if k in own or not k.startswith(self._OFFPATH_PREFIXES):
+                mine[k] = v          # unknown keys outside the known off-path families still raise under strict=True
+            else:
+                off[k] = v.detach().clone() if torch.is_tensor(v) else v
+        self.__dict__["_offpath_state"] = off
+        return super().load_state_dict(mine, strict=strict, assign=assign)
+
+    def state_dict(self, *args, **kwargs):
+        sd = super().state_dict(*args, **kwargs)
+        prefix = kwargs.get("prefix", args[1] if len(args) > 1 else "")
+        for k, v in self.__dict__.get("_offpath_state", {}).items():
+            sd[prefix + k] = v
+        return sd
+
     def __deepcopy__(self, memo):  # handles are per-instance C objects
         import copy
         cls = self.__class__

@@ -101,3 +101,30 @@ def test_state_dict_keys_match_reference_weight_abi():
         assert list(m.state_dict().keys()) == list(sd.keys())
         assert all(m.state_dict()[k].shape == sd[k].shape for k in sd)
         m.load_state_dict(sd)
+
+
+def test_reference_checkpoints_load_strict_and_round_trip():
+    """The checkpoint ABI: a reference state_dict -- including the image-encoder / pose-head entries of AutoRFMix and
+    SUPNeRF that are not on this path -- loads with the default strict=True (optimizer_nuscenes.py:1795-1796) and state_dict()
+    gives every entry back unchanged.  Keys / shapes come from tests/golden/state_dict_keys.json (tools/make_golden.py)."""
+    import json
+    import torch
+    import supnerf_b200 as snb
+    keys = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_keys.json")))
+    cases = {"CodeNeRF": (snb.CodeNeRF, ()), "AutoRFMix_3_1_256": (snb.AutoRFMix, (3, 1, 256)), "AutoRF": (snb.AutoRF, ()),
+             "SUPNeRF_3_1_3_3_256": (snb.SUPNeRF, (3, 1, 3, 3, 256))}
+    g = torch.Generator().manual_seed(0)
+    for name, (cls, args) in cases.items():
+        sd = {}
+        for k, (shape, dtype) in keys[name].items():
+            dt = getattr(torch, dtype)
+            sd[k] = torch.randn(shape, generator=g).to(dt) if dt.is_floating_point else torch.zeros(shape, dtype=dt)
+        m = cls(*args)
+        res = m.load_state_dict(sd)
+        assert not res.missing_keys and not res.unexpected_keys
+        out = m.state_dict()
+        assert set(out) == set(sd) and all(torch.equal(out[k], sd[k]) for k in sd), name
+        for k, p_ in m.named_parameters():
+            assert torch.equal(p_.detach(), sd[k])
+    with pytest.raises(RuntimeError):
+        snb.CodeNeRF().load_state_dict({"bogus.weight": torch.zeros(1)})

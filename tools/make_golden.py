@@ -298,6 +298,19 @@ def golden_scene_merge():
          sigmas_sort=env["sigmas_sort"], rgbs_sort=env["rgbs_sort"], rgb=env["rgb"], depth=env["depth"], acc=env["weights"])
 
 
+def golden_state_dict_keys():
+    """state_dict key -> shape of the reference modules (the checkpoint ABI): lets the CPU tests check that the
+    drop-in modules load a reference checkpoint with the default strict=True without importing the reference."""
+    import json
+    out = {}
+    for name, mod in (("CodeNeRF", model_codenerf.CodeNeRF()), ("AutoRFMix_3_1_256", model_autorf.AutoRFMix(3, 1, 256)),
+                      ("AutoRF", model_autorf.AutoRF()), ("SUPNeRF_3_1_3_3_256", model_supnerf.SUPNeRF(3, 1, 3, 3, 256))):
+        out[name] = {k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in mod.state_dict().items()}
+    path = os.path.join(OUT, "state_dict_keys.json")
+    json.dump(out, open(path, "w"))
+    print("wrote", path, {k: len(v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     golden_stages()
@@ -306,3 +319,4 @@ if __name__ == "__main__":
     golden_decoder_batch()
     golden_autorf()
     golden_scene_merge()
+    golden_state_dict_keys()
