@@ -31,6 +31,13 @@ constexpr int kCluster = 2;               // CTAs per cluster: every weight stag
 constexpr uint16_t kClusterMask = (uint16_t)((1u << kCluster) - 1u);
 constexpr int kRing = 5;
 constexpr uint32_t kStageBytes = 16384;   // [256 n][32 k] bf16
+// cta_group::2 variant (CG2): one M = 256 MMA spans the CTA pair, each CTA holds ITS half of every weight stage ([128 n][32 k],
+// 8 KB), so the ring is twice as deep in the same shared memory and the tensor core reads 4 KB (A) + 4 KB (B) per instruction
+// per SM instead of 4 + 8: the epilogue's operand stores get half of the shared-memory bandwidth instead of a quarter.
+constexpr int kRing2 = 10;
+constexpr uint32_t kStageBytes2 = 8192;
+constexpr int kRingMax = 10;              // barrier layout (both variants)
+static_assert(kRing * kStageBytes == kRing2 * kStageBytes2, "same ring footprint");
 constexpr int kMaxSteps = 13;
 constexpr int kMaxLat = 4;                // shape_blocks + texture_blocks <= 4 (every shipped config: 3 + 1)
 
@@ -48,7 +55,8 @@ constexpr uint32_t SM_ALLOC = SM_TOTAL + 1024;                   // + alignment 
 static_assert(SM_ALLOC <= 232448, "shared memory budget");
 
 enum Epi : int { F_RELU = 0, F_SIGMA = 1, F_PEV = 2, F_RGB = 3, B_MASK = 4, B_VD = 5, B_EV = 6, B_XYZ = 7, F_NONE = 8 };
-constexpr int BAR_WFULL = 0, BAR_WEMPTY = kRing, BAR_READY = 2 * kRing, BAR_ACC = 2 * kRing + 2;
+constexpr int BAR_WFULL = 0, BAR_WEMPTY = kRingMax, BAR_READY = 2 * kRingMax, BAR_ACC = 2 * kRingMax + 2;   // 24 barriers = 192 B
+constexpr uint32_t kTmemSlotOff = 240;    // inside the 256-byte barrier block
 
 struct Step {
   uint32_t w_off;            // byte offset of the step's first weight stage in the packed buffer
@@ -81,6 +89,7 @@ struct Params {
                           // the samples of rays that miss the box on the GPU and never learns the count on the host
   uint8_t* save;      // training mode (weight gradients wanted): [tile][Program::save_tile_bytes] copies of every step's A operand
   long long* trace;   // timing experiments only: CTA 0 writes clock64 stamps [pair][step][slot][4] = READY seen, MMAs issued, ACC seen, published
+  int stagger;     // slot 1 runs this many steps behind slot 0 (0 .. n_steps - 1), see for_each_item
   int exp_flags;   // timing experiments only (env SNB_TC_EXP): 1 = producer skips the weight copies, 4 = every stage copies the same image
   Program prog;
 };
@@ -112,6 +121,7 @@ struct Smem {
   __device__ uint8_t* chunk(uint32_t slot, int c) const { return base + (slot * 4u + (uint32_t)c) * kChunkBytes; }
   __device__ uint32_t chunk_u32(uint32_t slot, int c) const { return base_u32 + (slot * 4u + (uint32_t)c) * kChunkBytes; }
   __device__ uint32_t stage_u32(uint32_t s) const { return base_u32 + SM_RING + s * kStageBytes; }
+  __device__ uint32_t stage2_u32(uint32_t s) const { return base_u32 + SM_RING + s * kStageBytes2; }
   __device__ float* tab(uint32_t off) const { return reinterpret_cast<float*>(base + SM_TAB + off); }
   __device__ uint32_t bar(int i) const { return base_u32 + SM_BARS + 8u * i; }
 };
@@ -145,12 +155,38 @@ __device__ __forceinline__ void store_row16(uint8_t* chunk, uint32_t row, uint32
 
 __device__ __forceinline__ void group_bar(uint32_t slot) { asm volatile("bar.sync %0, 256;" ::"r"(slot + 1) : "memory"); }
 
+// ---- cluster-scope barrier helpers (CG2: the leader CTA's MMA warp waits for arrivals from BOTH CTAs of the pair)
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+
 // this thread's smem writes (generic proxy) and TMEM reads are done: make them visible to the tensor core and tell the MMA warp
-__device__ __forceinline__ void publish(const Smem& sm, uint32_t slot, uint32_t lane) {
+// (CG2: the MMA warp of the pair's leader CTA, through its cluster-mapped READY barrier `ready_leader`)
+template <bool CG2>
+__device__ __forceinline__ void publish(const Smem& sm, uint32_t slot, uint32_t lane, uint32_t ready_leader) {
   tc_fence_before();
   fence_async_smem();
   __syncwarp();
-  if (lane == 0) mbar_arrive(sm.bar(BAR_READY + slot));
+  if (lane == 0) {
+    if (CG2) mbar_arrive_cluster(ready_leader);
+    else mbar_arrive(sm.bar(BAR_READY + slot));
+  }
 }
 
 // ------------------------------------------------------------------------------------------ producer / MMA roles
@@ -241,102 +277,222 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
 
 __device__ __forceinline__ int64_t rows_present(const Params& p) { return p.m_dev ? __ldg(p.m_dev) : p.M; }
 
+// ---- cta_group::2 forms: issued by the leader CTA only; A = [128 rows][K] in EACH CTA (same smem offset), B = each CTA's half of
+// the N rows, D = 128 lanes x N columns in each CTA's TMEM; commits multicast to the same barrier offset in both CTAs.
+__device__ __forceinline__ void umma2_stage_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate,
+                                                  uint32_t empty_bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e, p, t;\n"
+      ".reg .b64 a1, b1;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.eq.b32 t, 0, 0;\n"
+      "add.s64 a1, %1, 2;\n"
+      "add.s64 b1, %2, 2;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %3, t;\n"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%5], %6;\n"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(empty_bar), "h"(kClusterMask) : "memory");
+}
+__device__ __forceinline__ void umma2_bias_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t empty_bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e, t;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "setp.eq.b32 t, 0, 0;\n"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, t;\n"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%4], %5;\n"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(empty_bar), "h"(kClusterMask) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+      "}" ::"r"(bar), "h"(kClusterMask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_elect(uint32_t cluster_addr) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e mbarrier.arrive.shared::cluster.b64 _, [%0];\n"
+      "}" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// Tile owned by (cluster-uniform pair index pair0, CTA rank, slot).  CG1: every CTA owns a pair of consecutive tiles.  CG2: a slot
+// is one 256-row super tile of the cluster and the CTA's rank picks its 128-row half (so that both halves share the B operand,
+// including the per-object bias stage: the host only selects CG2 when objects own multiples of 256 rows).
+template <bool CG2>
+__device__ __forceinline__ int64_t tile_index(int64_t pair0, uint32_t crank, uint32_t slot) {
+  return CG2 ? 2 * pair0 + 2 * (int64_t)slot + crank : 2 * (pair0 + crank) + slot;
+}
+
+
+// Order in which the producer, the relay and the MMA warp walk the (slot, step) items of this CTA's tiles.  Slot 1 runs
+// `p.stagger` steps BEHIND slot 0: one slot's short steps (encoding_xyz, the PE(viewdir) columns, rgb.0) and its tile boundary
+// (heads, next tile's PE) then fall next to the other slot's 256 x 256 layers, whose MMAs keep the tensor pipe busy meanwhile
+// (with both slots in lock step the pipe idled ~6 000 cycles per tile pair at the boundary, profiles/r1_trace_cg2.md).
+// The epilogue groups only follow their own slot's barriers, so they need no change.  body(slot, step, pair0, iteration).
+template <typename F>
+__device__ __forceinline__ void for_each_item(const Params& p, int64_t first_pair0, int64_t n_pairs, F&& body) {
+  const int n = p.prog.n_steps, d = p.stagger;
+  if (first_pair0 >= n_pairs) return;
+  const int64_t n_iter = (n_pairs - first_pair0 + (int64_t)gridDim.x - 1) / (int64_t)gridDim.x;
+  const int64_t n_items = n_iter * n;
+  int si_s[2] = {0, 0};
+  int64_t p0_s[2] = {first_pair0, first_pair0}, it_s[2] = {0, 0};
+  for (int64_t g = 0; g < n_items + d; ++g) {
+#pragma unroll
+    for (uint32_t slot = 0; slot < 2; ++slot) {
+      if (slot == 0 ? (g >= n_items) : (g < d)) continue;
+      body(slot, si_s[slot], p0_s[slot], it_s[slot]);
+      if (++si_s[slot] == n) { si_s[slot] = 0; p0_s[slot] += gridDim.x; ++it_s[slot]; }
+    }
+  }
+}
+
+template <bool CG2>
 __device__ __forceinline__ void producer_loop(const Params& p, const Smem& sm, int64_t n_pairs) {
+  constexpr uint32_t RING = CG2 ? kRing2 : kRing;
   uint32_t stage = 0, ph = 0;
   const int64_t n_tiles = (rows_present(p) + kTileM - 1) / kTileM;
   const uint32_t crank = cluster_ctarank();
   // every CTA of a cluster runs the same number of iterations (a CTA past the last pair still streams its share of the weights)
-  for (int64_t pair0 = (int64_t)blockIdx.x - crank; pair0 < n_pairs; pair0 += gridDim.x) {
-    const int64_t pair = pair0 + crank;
-    for (int si = 0; si < p.prog.n_steps; ++si) {
-      const Step& st = p.prog.s[si];
-      const uint32_t bytes = (uint32_t)st.n_out * 64u, part = bytes / kCluster;
-      for (int slot = 0; slot < 2; ++slot) {
-        const uint8_t* src = p.packed + st.w_off + crank * part;
-        for (int j = 0; j < st.n_stages; ++j) {
-          mbar_wait(sm.bar(BAR_WEMPTY + stage), ph ^ 1u);   // released by the MMA warps of ALL CTAs of the cluster
-          bulk_g2s_multicast_elect(sm.stage_u32(stage) + crank * part, src, part, bytes, sm.bar(BAR_WFULL + stage), kClusterMask);
-          src += bytes;
-          if (++stage == (uint32_t)kRing) { stage = 0; ph ^= 1u; }
-        }
-        if (st.bias_stage) {   // CTA-local (not multicast): static image after the weight stages, or this tile's object's image
-          const uint8_t* bsrc = p.packed + st.w_off + (uint32_t)st.n_stages * bytes;
-          if (st.bias_stage == 2) {
-            const int64_t tile = 2 * pair + slot;
-            const int64_t obj = (pair < n_pairs && tile < n_tiles) ? (tile * kTileM) / p.rows_per_obj : 0;
-            bsrc = p.eimg + ((size_t)st.latent_slot * p.B + obj) * (256u * kBiasStageRowBytes);
-          }
-          mbar_wait(sm.bar(BAR_WEMPTY + stage), ph ^ 1u);
-          bulk_g2s_elect(sm.stage_u32(stage), bsrc, (uint32_t)st.n_out * kBiasStageRowBytes, sm.bar(BAR_WFULL + stage));
-          if (++stage == (uint32_t)kRing) { stage = 0; ph ^= 1u; }
-        }
-      }
+  for_each_item(p, (int64_t)blockIdx.x - crank, n_pairs, [&](uint32_t slot, int si, int64_t pair0, int64_t) {
+    const Step& st = p.prog.s[si];
+    const uint32_t bytes = (uint32_t)st.n_out * 64u, part = bytes / kCluster;
+    const uint8_t* src = p.packed + st.w_off + crank * part;
+    for (int j = 0; j < st.n_stages; ++j) {
+      mbar_wait(sm.bar(BAR_WEMPTY + stage), ph ^ 1u);   // released by the MMA warps of ALL CTAs of the cluster
+      if (CG2) bulk_g2s_elect(sm.stage2_u32(stage), src, part, sm.bar(BAR_WFULL + stage));   // this CTA's half of the N rows
+      else bulk_g2s_multicast_elect(sm.stage_u32(stage) + crank * part, src, part, bytes, sm.bar(BAR_WFULL + stage), kClusterMask);
+      src += bytes;
+      if (++stage == RING) { stage = 0; ph ^= 1u; }
     }
-  }
+    if (st.bias_stage) {   // CTA-local (not multicast): static image after the weight stages, or this tile's object's image
+      const uint8_t* bsrc = p.packed + st.w_off + (uint32_t)st.n_stages * bytes;
+      if (st.bias_stage == 2) {
+        const int64_t tile = tile_index<CG2>(pair0, CG2 ? 0u : crank, slot);   // CG2: the super tile's object
+        const int64_t obj = tile < n_tiles ? (tile * kTileM) / p.rows_per_obj : 0;
+        bsrc = p.eimg + ((size_t)st.latent_slot * p.B + obj) * (256u * kBiasStageRowBytes);
+      }
+      mbar_wait(sm.bar(BAR_WEMPTY + stage), ph ^ 1u);
+      if (CG2) {
+        const uint32_t half = (uint32_t)st.n_out / 2u * kBiasStageRowBytes;
+        bulk_g2s_elect(sm.stage2_u32(stage), bsrc + crank * half, half, sm.bar(BAR_WFULL + stage));
+      } else {
+        bulk_g2s_elect(sm.stage_u32(stage), bsrc, (uint32_t)st.n_out * kBiasStageRowBytes, sm.bar(BAR_WFULL + stage));
+      }
+      if (++stage == RING) { stage = 0; ph ^= 1u; }
+    }
+  });
 }
 
+// CG2, non-leader CTA: its half of every weight stage lands in ITS shared memory on ITS full barrier; this warp forwards each
+// completion to the leader's full barrier (count 2: the leader's own expect_tx arrival + this one), in ring order.
+__device__ __forceinline__ void relay_loop(const Params& p, const Smem& sm, int64_t n_pairs) {
+  uint32_t stage = 0, ph = 0;
+  const uint32_t full0_leader = mapa_u32(sm.bar(BAR_WFULL), 0u);
+  for_each_item(p, (int64_t)blockIdx.x - 1, n_pairs, [&](uint32_t, int si, int64_t, int64_t) {
+    const Step& st = p.prog.s[si];
+    const int n = (int)st.n_stages + (st.bias_stage ? 1 : 0);
+    for (int k = 0; k < n; ++k) {
+      mbar_wait(sm.bar(BAR_WFULL + stage), ph);
+      mbar_arrive_cluster_elect(full0_leader + 8u * stage);
+      if (++stage == (uint32_t)kRing2) { stage = 0; ph ^= 1u; }
+    }
+  });
+}
+
+template <bool CG2>
 __device__ __forceinline__ void mma_loop(const Params& p, const Smem& sm, int64_t n_pairs, uint32_t tmem_base) {
+  constexpr uint32_t RING = CG2 ? kRing2 : kRing;
   uint32_t stage = 0, ph = 0, ready_ph = 0;
   const uint64_t ones_desc = umma_desc_sw32(sm.base_u32 + SM_TAB + TAB_LAT);
   const bool trace = p.trace != nullptr && blockIdx.x == 0;
-  int64_t tr = 0;
-  const int64_t crank_m = cluster_ctarank(), n_tiles_m = (rows_present(p) + kTileM - 1) / kTileM;
+  const uint32_t crank_m = cluster_ctarank();
+  const int64_t n_tiles_m = (rows_present(p) + kTileM - 1) / kTileM;
   const uint32_t lane_m = threadIdx.x & 31u;
-  for (int64_t pair0 = (int64_t)blockIdx.x - crank_m; pair0 < n_pairs; pair0 += gridDim.x) {
-    for (int si = 0; si < p.prog.n_steps; ++si) {
-      const Step& st = p.prog.s[si];
-      const uint32_t idesc = umma_idesc(128, st.n_out);
-      const int n_stages = st.n_stages;
-#pragma unroll
-      for (uint32_t slot = 0; slot < 2; ++slot, tr += 4) {
-        mbar_wait(sm.bar(BAR_READY + slot), (ready_ph >> slot) & 1u);   // A operand written, accumulator drained
-        ready_ph ^= 1u << slot;
-        tc_fence_after();
-        if (trace) p.trace[tr] = clock64();
-        const uint32_t d_tmem = tmem_base + slot * 256u;
-        uint64_t a_desc = umma_desc(sm.chunk_u32(slot, 0));
-        uint32_t acc = (uint32_t)st.accumulate;
-        bool saving = false;
-        if (p.save != nullptr && st.save_chunks > 0) {   // training mode: keep this step's A operand for the weight-gradient kernels
-          const int64_t tile = 2 * (pair0 + crank_m) + slot;
-          saving = (pair0 + crank_m) < n_pairs && tile < n_tiles_m;
-          if (saving && lane_m == 0)
-            bulk_s2g(p.save + (size_t)tile * p.prog.save_tile_bytes + st.save_off, sm.chunk_u32(slot, 0), (uint32_t)st.save_chunks * kChunkBytes);
-        }
-        for (int j = 0; j < n_stages; ++j) {
-          mbar_wait(sm.bar(BAR_WFULL + stage), ph);
-          tc_fence_after();
-          umma_stage_elect(d_tmem, a_desc, umma_desc_sw64(sm.stage_u32(stage)), idesc, acc, sm.bar(BAR_WEMPTY + stage));
-          acc = 1u;
-          a_desc += (j & 1) ? (uint64_t)((kChunkBytes - 64u) >> 4) : (uint64_t)(64u >> 4);   // next 32-k half of the chunk / next chunk
-          if (++stage == (uint32_t)kRing) { stage = 0; ph ^= 1u; }
-        }
-        if (st.bias_stage) {
-          mbar_wait(sm.bar(BAR_WFULL + stage), ph);
-          tc_fence_after();
-          umma_bias_elect(d_tmem, ones_desc, umma_desc_sw32(sm.stage_u32(stage)), idesc, sm.bar(BAR_WEMPTY + stage));
-          if (++stage == (uint32_t)kRing) { stage = 0; ph ^= 1u; }
-        }
-        if (saving) {   // the epilogue overwrites the chunks after BAR_ACC: the bulk store must have read them by then
-          if (lane_m == 0 && !(p.exp_flags & 8)) bulk_wait_read_all();   // exp flag 8 (timing experiment only, WRONG results): no wait
-          __syncwarp();
-        }
-        umma_commit_elect(sm.bar(BAR_ACC + slot));
-        if (trace) p.trace[tr + 1] = clock64();
-      }
+  for_each_item(p, (int64_t)blockIdx.x - crank_m, n_pairs, [&](uint32_t slot, int si, int64_t pair0, int64_t it) {
+    const Step& st = p.prog.s[si];
+    const uint32_t idesc = umma_idesc(CG2 ? 256 : 128, st.n_out);
+    const int n_stages = st.n_stages;
+    const int64_t tr = ((it * p.prog.n_steps + si) * 2 + slot) * 4;
+    // A operand written, accumulator drained (CG2: by the epilogue groups of both CTAs)
+    mbar_wait(sm.bar(BAR_READY + slot), (ready_ph >> slot) & 1u);
+    ready_ph ^= 1u << slot;
+    tc_fence_after();
+    if (trace) p.trace[tr] = clock64();
+    const uint32_t d_tmem = tmem_base + slot * 256u;
+    uint64_t a_desc = umma_desc(sm.chunk_u32(slot, 0));
+    uint32_t acc = (uint32_t)st.accumulate;
+    bool saving = false;
+    if (!CG2 && p.save != nullptr && st.save_chunks > 0) {   // training mode: keep this step's A operand for the weight-gradient kernels
+      const int64_t tile = tile_index<false>(pair0, crank_m, slot);
+      saving = tile < n_tiles_m;
+      if (saving && lane_m == 0)
+        bulk_s2g(p.save + (size_t)tile * p.prog.save_tile_bytes + st.save_off, sm.chunk_u32(slot, 0), (uint32_t)st.save_chunks * kChunkBytes);
     }
-  }
-  if (p.save != nullptr && lane_m == 0) bulk_wait_all();
+    for (int j = 0; j < n_stages; ++j) {
+      mbar_wait(sm.bar(BAR_WFULL + stage), ph);
+      tc_fence_after();
+      if (CG2) umma2_stage_elect(d_tmem, a_desc, umma_desc_sw64(sm.stage2_u32(stage)), idesc, acc, sm.bar(BAR_WEMPTY + stage));
+      else umma_stage_elect(d_tmem, a_desc, umma_desc_sw64(sm.stage_u32(stage)), idesc, acc, sm.bar(BAR_WEMPTY + stage));
+      acc = 1u;
+      a_desc += (j & 1) ? (uint64_t)((kChunkBytes - 64u) >> 4) : (uint64_t)(64u >> 4);   // next 32-k half of the chunk / next chunk
+      if (++stage == RING) { stage = 0; ph ^= 1u; }
+    }
+    if (st.bias_stage) {
+      mbar_wait(sm.bar(BAR_WFULL + stage), ph);
+      tc_fence_after();
+      if (CG2) umma2_bias_elect(d_tmem, ones_desc, umma_desc_sw32(sm.stage2_u32(stage)), idesc, sm.bar(BAR_WEMPTY + stage));
+      else umma_bias_elect(d_tmem, ones_desc, umma_desc_sw32(sm.stage_u32(stage)), idesc, sm.bar(BAR_WEMPTY + stage));
+      if (++stage == RING) { stage = 0; ph ^= 1u; }
+    }
+    if (saving) {   // the epilogue overwrites the chunks after BAR_ACC: the bulk store must have read them by then
+      if (lane_m == 0 && !(p.exp_flags & 8)) bulk_wait_read_all();   // exp flag 8 (timing experiment only, WRONG results): no wait
+      __syncwarp();
+    }
+    if (CG2) umma2_commit_elect(sm.bar(BAR_ACC + slot));
+    else umma_commit_elect(sm.bar(BAR_ACC + slot));
+    if (trace) p.trace[tr + 1] = clock64();
+  });
+  if (!CG2 && p.save != nullptr && lane_m == 0) bulk_wait_all();
 }
 
+template <bool CG2>
 __device__ __forceinline__ void kernel_prologue(Smem& sm, uint32_t tid, uint32_t warp, uint32_t& tmem_base) {
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.base + SM_BARS + 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.base + SM_BARS + kTmemSlotOff);
   if (tid == 0) {
-    for (int i = 0; i < kRing; ++i) { mbar_init(sm.bar(BAR_WFULL + i), 1); mbar_init(sm.bar(BAR_WEMPTY + i), kCluster); }
-    for (int i = 0; i < 2; ++i) { mbar_init(sm.bar(BAR_READY + i), 8); mbar_init(sm.bar(BAR_ACC + i), 1); }
+    if (CG2) {
+      // full: the CTA's own expect_tx arrival (+ on the leader: the peer's relayed completion); empty / acc: ONE commit of the
+      // leader's MMA warp, multicast to both CTAs; ready (leader only): 8 epilogue warps of each CTA
+      const uint32_t full_count = cluster_ctarank() == 0 ? 2u : 1u;
+      for (int i = 0; i < kRing2; ++i) { mbar_init(sm.bar(BAR_WFULL + i), full_count); mbar_init(sm.bar(BAR_WEMPTY + i), 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(sm.bar(BAR_READY + i), 16); mbar_init(sm.bar(BAR_ACC + i), 1); }
+    } else {
+      for (int i = 0; i < kRing; ++i) { mbar_init(sm.bar(BAR_WFULL + i), 1); mbar_init(sm.bar(BAR_WEMPTY + i), kCluster); }
+      for (int i = 0; i < 2; ++i) { mbar_init(sm.bar(BAR_READY + i), 8); mbar_init(sm.bar(BAR_ACC + i), 1); }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 16) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (CG2) {
+    __syncthreads();
+    cluster_sync_all();   // both CTAs of the pair are resident before the paired TMEM allocation
+    if (warp == 16) tmem_alloc2(smem_u32(tmem_slot), 512);
+  } else {
+    if (warp == 16) tmem_alloc(smem_u32(tmem_slot), 512);
+  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // every CTA's barriers are initialised before a peer multicasts data / arrivals into them
@@ -424,7 +580,7 @@ __device__ __forceinline__ void fwd_epilogue(const Params& p, const Smem& sm, co
 }
 
 // ------------------------------------------------------------------------------------------ forward kernel
-template <bool DBG>
+template <bool DBG, bool CG2>
 __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   Smem sm;
@@ -440,15 +596,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_const
     for (int i = tid; i < 384; i += kThreads) w2_s[i] = __ldg(p.w2 + i);
   }
   uint32_t tmem_base;
-  kernel_prologue(sm, tid, warp, tmem_base);
+  kernel_prologue<CG2>(sm, tid, warp, tmem_base);
   const int64_t M_eff = rows_present(p);
   const int64_t n_tiles = (M_eff + kTileM - 1) / kTileM;
   const int64_t n_pairs = (n_tiles + 1) / 2;
 
   if (warp == 16) {
-    producer_loop(p, sm, n_pairs);
+    producer_loop<CG2>(p, sm, n_pairs);
   } else if (warp == 17) {
-    mma_loop(p, sm, n_pairs, tmem_base);
+    if (CG2 && cluster_ctarank() != 0) relay_loop(p, sm, n_pairs);
+    else mma_loop<CG2>(p, sm, n_pairs, tmem_base);
   } else {
     const uint32_t slot = warp >> 3, gw = warp & 7u, gtid = tid & 255u;
     EpiCtx e;
@@ -462,21 +619,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_const
     const uint32_t crank = cluster_ctarank();
     const int64_t pair_first = (int64_t)blockIdx.x - crank;
     float x[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 1.f};
-    auto load_coords = [&](int64_t pr, float (&xo)[3], float (&dro)[3]) {   // clamped: tiles past the end redo row M-1, never stored
-      int64_t r = (2 * pr + slot) * kTileM + e.row;
-      if (pr >= n_pairs || r >= M_eff) r = M_eff - 1;
+    const uint32_t ready_leader = CG2 ? mapa_u32(sm.bar(BAR_READY + slot), 0u) : 0u;
+    auto load_coords = [&](int64_t p0, float (&xo)[3], float (&dro)[3]) {   // clamped: tiles past the end redo row M-1, never stored
+      int64_t r = tile_index<CG2>(p0, crank, slot) * kTileM + e.row;
+      if (r >= M_eff) r = M_eff - 1;
       xo[0] = __ldg(p.xyz + 3 * r); xo[1] = __ldg(p.xyz + 3 * r + 1); xo[2] = __ldg(p.xyz + 3 * r + 2);
       dro[0] = __ldg(p.viewdir + 3 * r); dro[1] = __ldg(p.viewdir + 3 * r + 1); dro[2] = __ldg(p.viewdir + 3 * r + 2);
     };
     if (pair_first < n_pairs) {   // first tile of this CTA: PE(xyz) -> chunk 0
-      load_coords(pair_first + crank, x, dir);
+      load_coords(pair_first, x, dir);
       write_pe_row<10>(sm.chunk(slot, 0), e.row, e.hh, x);
-      publish(sm, slot, lane);
+      publish<CG2>(sm, slot, lane, ready_leader);
     }
     for (int64_t pair0 = pair_first; pair0 < n_pairs; pair0 += gridDim.x) {
-      const int64_t pair = pair0 + crank;
-      const int64_t tile = 2 * pair + slot;
-      const bool tile_ok = pair < n_pairs && tile < n_tiles;
+      const int64_t tile = tile_index<CG2>(pair0, crank, slot);
+      const bool tile_ok = tile < n_tiles;
       const bool has_next = pair0 + (int64_t)gridDim.x < n_pairs;   // cluster-uniform
       e.grow = tile * kTileM + e.row;
       e.valid = tile_ok && e.grow < M_eff;
@@ -486,23 +643,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_const
       for (int si = 0; si < p.prog.n_steps; ++si) {
         const Step& st = p.prog.s[si];
         const bool last = si + 1 == p.prog.n_steps;
-        if (last && has_next) load_coords(pair + gridDim.x, xn, dn);   // the global latency hides behind rgb.0's MMAs
+        if (last && has_next) load_coords(pair0 + gridDim.x, xn, dn);   // the global latency hides behind rgb.0's MMAs
         // (computing PE(xn) here as well was measured SLOWER: 16 more live registers spill in the rgb-head epilogue)
         mbar_wait(sm.bar(BAR_ACC + slot), acc_cnt & 1u);
         acc_cnt++;
         tc_fence_after();
-        if (p.trace && blockIdx.x == 0 && gtid == 0) p.trace[(((pair / gridDim.x) * p.prog.n_steps + si) * 2 + slot) * 4 + 2] = clock64();
+        if (p.trace && blockIdx.x == 0 && gtid == 0) p.trace[(((pair0 / gridDim.x) * p.prog.n_steps + si) * 2 + slot) * 4 + 2] = clock64();
         if (st.epi == F_RELU) fwd_epilogue<F_RELU, DBG>(p, sm, st, e, mask_tile, tile_ok, sig_acc, rgb_acc);
         else if (st.epi == F_SIGMA) fwd_epilogue<F_SIGMA, DBG>(p, sm, st, e, mask_tile, tile_ok, sig_acc, rgb_acc);
         else if (st.epi == F_PEV) write_pe_row<4>(sm.chunk(slot, 0), e.row, e.hh, dir);   // accumulator untouched: the next step adds to it
         else if (st.epi == F_RGB) fwd_epilogue<F_RGB, DBG>(p, sm, st, e, mask_tile, tile_ok, sig_acc, rgb_acc);
         // F_NONE (training mode's last step): no MMAs, no epilogue -- the MMA warp only copies rgb.2's input out of the A chunks
-        if (!last) publish(sm, slot, lane);
+        if (!last) publish<CG2>(sm, slot, lane, ready_leader);
         else if (has_next) {   // rgb.0's MMAs are complete and its accumulator is drained: hand the NEXT tile's PE(xyz) to the MMA warp
           write_pe_row<10>(sm.chunk(slot, 0), e.row, e.hh, xn);   // before the tile-end bookkeeping below
-          publish(sm, slot, lane);
+          publish<CG2>(sm, slot, lane, ready_leader);
         } else tc_fence_before();
-        if (p.trace && blockIdx.x == 0 && gtid == 0) p.trace[(((pair / gridDim.x) * p.prog.n_steps + si) * 2 + slot) * 4 + 3] = clock64();
+        if (p.trace && blockIdx.x == 0 && gtid == 0) p.trace[(((pair0 / gridDim.x) * p.prog.n_steps + si) * 2 + slot) * 4 + 3] = clock64();
       }
       // tile end: combine the two column halves of the sigma / rgb heads
       if (e.hh == 1) *reinterpret_cast<float4*>(part + 4 * e.row) = make_float4(sig_acc, rgb_acc[0], rgb_acc[1], rgb_acc[2]);
@@ -523,7 +680,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_const
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // no CTA leaves while a peer can still multicast into its shared memory / barriers
-  if (warp == 16) tmem_dealloc(tmem_base, 512);
+  if (warp == 16) { if (CG2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
 // ------------------------------------------------------------------------------------------ backward epilogue
@@ -606,6 +763,7 @@ __device__ __forceinline__ void colsum_a_operand(const Smem& sm, uint32_t slot, 
 }
 
 // ------------------------------------------------------------------------------------------ backward kernel
+template <bool CG2>
 __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   Smem sm;
@@ -620,15 +778,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_const
     for (int i = tid; i < 384; i += kThreads) w2_s[i] = __ldg(p.w2 + i);
   }
   uint32_t tmem_base;
-  kernel_prologue(sm, tid, warp, tmem_base);
+  kernel_prologue<CG2>(sm, tid, warp, tmem_base);
   const int64_t M_eff = rows_present(p);
   const int64_t n_tiles = (M_eff + kTileM - 1) / kTileM;
   const int64_t n_pairs = (n_tiles + 1) / 2;
 
   if (warp == 16) {
-    producer_loop(p, sm, n_pairs);
+    producer_loop<CG2>(p, sm, n_pairs);
   } else if (warp == 17) {
-    mma_loop(p, sm, n_pairs, tmem_base);
+    if (CG2 && cluster_ctarank() != 0) relay_loop(p, sm, n_pairs);
+    else mma_loop<CG2>(p, sm, n_pairs, tmem_base);
   } else {
     const uint32_t slot = warp >> 3, gw = warp & 7u, gtid = tid & 255u;
     EpiCtx e;
@@ -643,9 +802,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_const
     const uint32_t crank = cluster_ctarank();
     const int64_t pair_first = (int64_t)blockIdx.x - crank;
     // upstream gradients of one tile row: d softplus-input of sigma, d rgb, and the rgb.0 ReLU mask words of this thread's columns
-    auto load_upstream = [&](int64_t pr, float& gsp_o, float (&g3o)[3], uint32_t (&mwo)[2]) {
-      const int64_t t = 2 * pr + slot;
-      const bool ok = pr < n_pairs && t < n_tiles;
+    const uint32_t ready_leader = CG2 ? mapa_u32(sm.bar(BAR_READY + slot), 0u) : 0u;
+    auto load_upstream = [&](int64_t p0, float& gsp_o, float (&g3o)[3], uint32_t (&mwo)[2]) {
+      const int64_t t = tile_index<CG2>(p0, crank, slot);
+      const bool ok = t < n_tiles;
       const int64_t r = t * kTileM + e.row;
       const bool valid = ok && r < M_eff;
       const int64_t cr = valid ? r : M_eff - 1;
@@ -682,14 +842,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_const
     float gsp = 0.f;
     if (pair_first < n_pairs) {   // first tile of this CTA
       float g3[3]; uint32_t mw2[2];
-      load_upstream(pair_first + crank, gsp, g3, mw2);
+      load_upstream(pair_first, gsp, g3, mw2);
       prologue(g3, mw2);
-      publish(sm, slot, lane);
+      publish<CG2>(sm, slot, lane, ready_leader);
     }
     for (int64_t pair0 = pair_first; pair0 < n_pairs; pair0 += gridDim.x) {
-      const int64_t pair = pair0 + crank;
-      const int64_t tile = 2 * pair + slot;
-      const bool tile_ok = pair < n_pairs && tile < n_tiles;
+      const int64_t tile = tile_index<CG2>(pair0, crank, slot);
+      const bool tile_ok = tile < n_tiles;
       const bool has_next = pair0 + (int64_t)gridDim.x < n_pairs;   // cluster-uniform
       e.grow = tile * kTileM + e.row;
       e.valid = tile_ok && e.grow < M_eff;
@@ -706,7 +865,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_const
           for (int c = 0; c < 4; ++c) mw[c] = mask_word(mask_tile, st.mask_slot, c * 2 + (int)e.hh, e.row);
         }
         const bool last = si + 1 == p.prog.n_steps;
-        if (last && has_next) load_upstream(pair + gridDim.x, gsp_n, g3n, mwn);   // global latency hides behind the last MMAs
+        if (last && has_next) load_upstream(pair0 + gridDim.x, gsp_n, g3n, mwn);   // global latency hides behind the last MMAs
         if (st.colsum) {   // column sums of this step's A operand (published by the whole group last step), while its MMAs run
           group_bar(slot);
           colsum_a_operand(sm, slot, gw, lane, colsum + st.latent_slot * 256);
@@ -715,7 +874,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_const
         acc_cnt++;
         tc_fence_after();
         if (st.colsum) group_bar(slot);   // every warp is done reading the chunks this step's epilogue overwrites
-        if (p.trace && blockIdx.x == 0 && gtid == 0) p.trace[(((pair / gridDim.x) * p.prog.n_steps + si) * 2 + slot) * 4 + 2] = clock64();
+        if (p.trace && blockIdx.x == 0 && gtid == 0) p.trace[(((pair0 / gridDim.x) * p.prog.n_steps + si) * 2 + slot) * 4 + 2] = clock64();
         if (st.epi == B_XYZ) {
           // acc = d PE(xyz) (64 columns): fold to d xyz.  g_x = g_0 + sum_f 2^f (g_sin,f cos_f - g_cos,f sin_f)
           uint32_t r[32];
@@ -765,12 +924,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_const
         } else if (st.produce_a) {
           bwd_epilogue<false, true>(sm, e, mw, gsp);
         }
-        if (!last) publish(sm, slot, lane);
+        if (!last) publish<CG2>(sm, slot, lane, ready_leader);
         else if (has_next) {   // the last MMAs are complete and their accumulator is drained: hand the NEXT tile's first operand over
           prologue(g3n, mwn);  // before the tile-end bookkeeping below
-          publish(sm, slot, lane);
+          publish<CG2>(sm, slot, lane, ready_leader);
         } else tc_fence_before();
-        if (p.trace && blockIdx.x == 0 && gtid == 0) p.trace[(((pair / gridDim.x) * p.prog.n_steps + si) * 2 + slot) * 4 + 3] = clock64();
+        if (p.trace && blockIdx.x == 0 && gtid == 0) p.trace[(((pair0 / gridDim.x) * p.prog.n_steps + si) * 2 + slot) * 4 + 3] = clock64();
       }
       // ---- tile end: d xyz, and flush the latent column sums when this slot's next tile belongs to another object
       const int64_t next = tile + 2 * (int64_t)gridDim.x;
@@ -797,7 +956,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_const
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // no CTA leaves while a peer can still multicast into its shared memory / barriers
-  if (warp == 16) tmem_dealloc(tmem_base, 512);
+  if (warp == 16) { if (CG2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
 // ------------------------------------------------------------------------------------------ weight packing
@@ -1020,6 +1179,7 @@ static void fill_common2(tc2::Params& p, const snb_handle_s* h, const void* pack
   p.w2 = h->layers[h->iR2].w; p.b2 = h->layers[h->iR2].b;
   p.n_latent = h->arch.shape_blocks + h->arch.texture_blocks;
   { const char* ev = getenv("SNB_TC_EXP"); p.exp_flags = ev ? atoi(ev) : 0; }
+  { static const int stg = [] { const char* e = getenv("SNB_TC_STAGGER"); return e ? atoi(e) : 0; }(); p.stagger = stg; }
   p.trace = g_trace;
 }
 
@@ -1027,7 +1187,7 @@ static void fill_common2(tc2::Params& p, const snb_handle_s* h, const void* pack
 // span GPCs, so a GPC with an odd SM count leaves one SM idle), at most one CTA per tile pair (rounded up to a full cluster).
 template <typename K>
 static int tc2_grid(K kernel, int64_t M) {
-  static int max_ctas = 0;   // same answer for both kernels of this file (same block size / shared memory)
+  static int max_ctas = 0;   // same answer for every kernel variant of this file (same block size / shared memory)
   if (max_ctas == 0) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(sm_count() / kCluster * kCluster), 1, 1);
@@ -1045,6 +1205,13 @@ static int tc2_grid(K kernel, int64_t M) {
   const int64_t pairs = ((M + kTileM - 1) / kTileM + 1) / 2;
   const int64_t want = (pairs + kCluster - 1) / kCluster * kCluster;
   return (int)(want < max_ctas ? want : max_ctas);
+}
+
+// cta_group::2 kernels: frozen weights only (no operand saves), and every 256-row super tile inside one object (the pair's two
+// tiles share the B operand, hence the per-object bias stage).  SNB_TC_CG2=0 selects the cta_group::1 kernels.
+static bool tc2_use_cg2(const tc2::Params& p) {
+  static const int env = [] { const char* e = getenv("SNB_TC_CG2"); return e ? atoi(e) : 1; }();
+  return env != 0 && p.save == nullptr && p.dbg == nullptr && (p.B == 1 || p.rows_per_obj % 256 == 0);
 }
 
 template <typename K>
@@ -1071,12 +1238,16 @@ int tc2_launch_fwd(const snb_handle_s* h, const void* packed2, const float* xyz,
   p.save = save;
   p.m_dev = m_dev;
   p.prog = save ? pl.fwd_train : pl.fwd;
+  p.stagger = std::max(0, std::min(p.stagger, p.prog.n_steps - 1));
   if (dbg) {
-    SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
-    SNB_CHECK_CUDA(tc2_launch(tc2_fwd_kernel<true>, tc2_grid(tc2_fwd_kernel<true>, M), st, p));
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
+    SNB_CHECK_CUDA(tc2_launch(tc2_fwd_kernel<true, false>, tc2_grid(tc2_fwd_kernel<true, false>, M), st, p));
+  } else if (tc2_use_cg2(p)) {
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
+    SNB_CHECK_CUDA(tc2_launch(tc2_fwd_kernel<false, true>, tc2_grid(tc2_fwd_kernel<false, true>, M), st, p));
   } else {
-    SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
-    SNB_CHECK_CUDA(tc2_launch(tc2_fwd_kernel<false>, tc2_grid(tc2_fwd_kernel<false>, M), st, p));
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
+    SNB_CHECK_CUDA(tc2_launch(tc2_fwd_kernel<false, false>, tc2_grid(tc2_fwd_kernel<false, false>, M), st, p));
   }
   return 0;
 }
@@ -1093,8 +1264,14 @@ int tc2_launch_bwd(const snb_handle_s* h, const void* packed2, const float* xyz,
   p.m_dev = m_dev;
   SNB_REQUIRE(save == nullptr || g_xyz != nullptr, "tc2 backward: training mode runs the full program (g_xyz scratch required)");
   p.prog = g_xyz ? pl.bwd_full : pl.bwd_noxyz;
-  SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
-  SNB_CHECK_CUDA(tc2_launch(tc2_bwd_kernel, tc2_grid(tc2_bwd_kernel, M), st, p));
+  p.stagger = std::max(0, std::min(p.stagger, p.prog.n_steps - 1));
+  if (tc2_use_cg2(p)) {
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
+    SNB_CHECK_CUDA(tc2_launch(tc2_bwd_kernel<true>, tc2_grid(tc2_bwd_kernel<true>, M), st, p));
+  } else {
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
+    SNB_CHECK_CUDA(tc2_launch(tc2_bwd_kernel<false>, tc2_grid(tc2_bwd_kernel<false>, M), st, p));
+  }
   return 0;
 }
 
