@@ -89,7 +89,6 @@ struct Params {
                           // the samples of rays that miss the box on the GPU and never learns the count on the host
   uint8_t* save;      // training mode (weight gradients wanted): [tile][Program::save_tile_bytes] copies of every step's A operand
   long long* trace;   // timing experiments only: CTA 0 writes clock64 stamps [pair][step][slot][4] = READY seen, MMAs issued, ACC seen, published
-  int stagger;     // slot 1 runs this many steps behind slot 0 (0 .. n_steps - 1), see for_each_item
   int exp_flags;   // timing experiments only (env SNB_TC_EXP): 1 = producer skips the weight copies, 4 = every stage copies the same image
   Program prog;
 };
@@ -164,18 +163,6 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta_rank) 
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
-
 // this thread's smem writes (generic proxy) and TMEM reads are done: make them visible to the tensor core and tell the MMA warp
 // (CG2: the MMA warp of the pair's leader CTA, through its cluster-mapped READY barrier `ready_leader`)
 template <bool CG2>
@@ -338,29 +325,10 @@ __device__ __forceinline__ int64_t tile_index(int64_t pair0, uint32_t crank, uin
 }
 
 
-// Order in which the producer, the relay and the MMA warp walk the (slot, step) items of this CTA's tiles.  Slot 1 runs
-// `p.stagger` steps BEHIND slot 0: one slot's short steps (encoding_xyz, the PE(viewdir) columns, rgb.0) and its tile boundary
-// (heads, next tile's PE) then fall next to the other slot's 256 x 256 layers, whose MMAs keep the tensor pipe busy meanwhile
-// (with both slots in lock step the pipe idled ~6 000 cycles per tile pair at the boundary, profiles/r1_trace_cg2.md).
-// The epilogue groups only follow their own slot's barriers, so they need no change.  body(slot, step, pair0, iteration).
-template <typename F>
-__device__ __forceinline__ void for_each_item(const Params& p, int64_t first_pair0, int64_t n_pairs, F&& body) {
-  const int n = p.prog.n_steps, d = p.stagger;
-  if (first_pair0 >= n_pairs) return;
-  const int64_t n_iter = (n_pairs - first_pair0 + (int64_t)gridDim.x - 1) / (int64_t)gridDim.x;
-  const int64_t n_items = n_iter * n;
-  int si_s[2] = {0, 0};
-  int64_t p0_s[2] = {first_pair0, first_pair0}, it_s[2] = {0, 0};
-  for (int64_t g = 0; g < n_items + d; ++g) {
-#pragma unroll
-    for (uint32_t slot = 0; slot < 2; ++slot) {
-      if (slot == 0 ? (g >= n_items) : (g < d)) continue;
-      body(slot, si_s[slot], p0_s[slot], it_s[slot]);
-      if (++si_s[slot] == n) { si_s[slot] = 0; p0_s[slot] += gridDim.x; ++it_s[slot]; }
-    }
-  }
-}
-
+// (A variant in which slot 1 ran a few steps BEHIND slot 0, so that one slot's short steps and tile boundary fall next to the other
+// slot's 256 x 256 layers, was measured: no gain -- the tensor pipe is in order, a short step's MMAs still queue behind the other
+// slot's long step and the long step's epilogue is then covered by only the short step's MMAs -- and its generic item iterator
+// cost the MMA warp its warp-uniform code: +9 % cycles per tile pair.  profiles/r1_trace_cg2.md.)
 template <bool CG2>
 __device__ __forceinline__ void producer_loop(const Params& p, const Smem& sm, int64_t n_pairs) {
   constexpr uint32_t RING = CG2 ? kRing2 : kRing;
@@ -368,34 +336,38 @@ __device__ __forceinline__ void producer_loop(const Params& p, const Smem& sm, i
   const int64_t n_tiles = (rows_present(p) + kTileM - 1) / kTileM;
   const uint32_t crank = cluster_ctarank();
   // every CTA of a cluster runs the same number of iterations (a CTA past the last pair still streams its share of the weights)
-  for_each_item(p, (int64_t)blockIdx.x - crank, n_pairs, [&](uint32_t slot, int si, int64_t pair0, int64_t) {
-    const Step& st = p.prog.s[si];
-    const uint32_t bytes = (uint32_t)st.n_out * 64u, part = bytes / kCluster;
-    const uint8_t* src = p.packed + st.w_off + crank * part;
-    for (int j = 0; j < st.n_stages; ++j) {
-      mbar_wait(sm.bar(BAR_WEMPTY + stage), ph ^ 1u);   // released by the MMA warps of ALL CTAs of the cluster
-      if (CG2) bulk_g2s_elect(sm.stage2_u32(stage), src, part, sm.bar(BAR_WFULL + stage));   // this CTA's half of the N rows
-      else bulk_g2s_multicast_elect(sm.stage_u32(stage) + crank * part, src, part, bytes, sm.bar(BAR_WFULL + stage), kClusterMask);
-      src += bytes;
-      if (++stage == RING) { stage = 0; ph ^= 1u; }
-    }
-    if (st.bias_stage) {   // CTA-local (not multicast): static image after the weight stages, or this tile's object's image
-      const uint8_t* bsrc = p.packed + st.w_off + (uint32_t)st.n_stages * bytes;
-      if (st.bias_stage == 2) {
-        const int64_t tile = tile_index<CG2>(pair0, CG2 ? 0u : crank, slot);   // CG2: the super tile's object
-        const int64_t obj = tile < n_tiles ? (tile * kTileM) / p.rows_per_obj : 0;
-        bsrc = p.eimg + ((size_t)st.latent_slot * p.B + obj) * (256u * kBiasStageRowBytes);
+  for (int64_t pair0 = (int64_t)blockIdx.x - crank; pair0 < n_pairs; pair0 += gridDim.x) {
+    for (int si = 0; si < p.prog.n_steps; ++si) {
+      const Step& st = p.prog.s[si];
+      const uint32_t bytes = (uint32_t)st.n_out * 64u, part = bytes / kCluster;
+      for (uint32_t slot = 0; slot < 2; ++slot) {
+        const uint8_t* src = p.packed + st.w_off + crank * part;
+        for (int j = 0; j < st.n_stages; ++j) {
+          mbar_wait(sm.bar(BAR_WEMPTY + stage), ph ^ 1u);   // released by the MMA warps of ALL CTAs of the cluster
+          if (CG2) bulk_g2s_elect(sm.stage2_u32(stage), src, part, sm.bar(BAR_WFULL + stage));   // this CTA's half of the N rows
+          else bulk_g2s_multicast_elect(sm.stage_u32(stage) + crank * part, src, part, bytes, sm.bar(BAR_WFULL + stage), kClusterMask);
+          src += bytes;
+          if (++stage == RING) { stage = 0; ph ^= 1u; }
+        }
+        if (st.bias_stage) {   // CTA-local (not multicast): static image after the weight stages, or this tile's object's image
+          const uint8_t* bsrc = p.packed + st.w_off + (uint32_t)st.n_stages * bytes;
+          if (st.bias_stage == 2) {
+            const int64_t tile = tile_index<CG2>(pair0, CG2 ? 0u : crank, slot);   // CG2: the super tile's object
+            const int64_t obj = tile < n_tiles ? (tile * kTileM) / p.rows_per_obj : 0;
+            bsrc = p.eimg + ((size_t)st.latent_slot * p.B + obj) * (256u * kBiasStageRowBytes);
+          }
+          mbar_wait(sm.bar(BAR_WEMPTY + stage), ph ^ 1u);
+          if (CG2) {
+            const uint32_t half = (uint32_t)st.n_out / 2u * kBiasStageRowBytes;
+            bulk_g2s_elect(sm.stage2_u32(stage), bsrc + crank * half, half, sm.bar(BAR_WFULL + stage));
+          } else {
+            bulk_g2s_elect(sm.stage_u32(stage), bsrc, (uint32_t)st.n_out * kBiasStageRowBytes, sm.bar(BAR_WFULL + stage));
+          }
+          if (++stage == RING) { stage = 0; ph ^= 1u; }
+        }
       }
-      mbar_wait(sm.bar(BAR_WEMPTY + stage), ph ^ 1u);
-      if (CG2) {
-        const uint32_t half = (uint32_t)st.n_out / 2u * kBiasStageRowBytes;
-        bulk_g2s_elect(sm.stage2_u32(stage), bsrc + crank * half, half, sm.bar(BAR_WFULL + stage));
-      } else {
-        bulk_g2s_elect(sm.stage_u32(stage), bsrc, (uint32_t)st.n_out * kBiasStageRowBytes, sm.bar(BAR_WFULL + stage));
-      }
-      if (++stage == RING) { stage = 0; ph ^= 1u; }
     }
-  });
+  }
 }
 
 // CG2, non-leader CTA: its half of every weight stage lands in ITS shared memory on ITS full barrier; this warp forwards each
@@ -403,15 +375,17 @@ __device__ __forceinline__ void producer_loop(const Params& p, const Smem& sm, i
 __device__ __forceinline__ void relay_loop(const Params& p, const Smem& sm, int64_t n_pairs) {
   uint32_t stage = 0, ph = 0;
   const uint32_t full0_leader = mapa_u32(sm.bar(BAR_WFULL), 0u);
-  for_each_item(p, (int64_t)blockIdx.x - 1, n_pairs, [&](uint32_t, int si, int64_t, int64_t) {
-    const Step& st = p.prog.s[si];
-    const int n = (int)st.n_stages + (st.bias_stage ? 1 : 0);
-    for (int k = 0; k < n; ++k) {
-      mbar_wait(sm.bar(BAR_WFULL + stage), ph);
-      mbar_arrive_cluster_elect(full0_leader + 8u * stage);
-      if (++stage == (uint32_t)kRing2) { stage = 0; ph ^= 1u; }
+  for (int64_t pair0 = (int64_t)blockIdx.x - 1; pair0 < n_pairs; pair0 += gridDim.x) {
+    for (int si = 0; si < p.prog.n_steps; ++si) {
+      const Step& st = p.prog.s[si];
+      const int n = (int)st.n_stages + (st.bias_stage ? 1 : 0);
+      for (int k = 0; k < 2 * n; ++k) {   // both slots
+        mbar_wait(sm.bar(BAR_WFULL + stage), ph);
+        mbar_arrive_cluster_elect(full0_leader + 8u * stage);
+        if (++stage == (uint32_t)kRing2) { stage = 0; ph ^= 1u; }
+      }
     }
-  });
+  }
 }
 
 template <bool CG2>
@@ -420,53 +394,57 @@ __device__ __forceinline__ void mma_loop(const Params& p, const Smem& sm, int64_
   uint32_t stage = 0, ph = 0, ready_ph = 0;
   const uint64_t ones_desc = umma_desc_sw32(sm.base_u32 + SM_TAB + TAB_LAT);
   const bool trace = p.trace != nullptr && blockIdx.x == 0;
+  int64_t tr = 0;
   const uint32_t crank_m = cluster_ctarank();
   const int64_t n_tiles_m = (rows_present(p) + kTileM - 1) / kTileM;
   const uint32_t lane_m = threadIdx.x & 31u;
-  for_each_item(p, (int64_t)blockIdx.x - crank_m, n_pairs, [&](uint32_t slot, int si, int64_t pair0, int64_t it) {
-    const Step& st = p.prog.s[si];
-    const uint32_t idesc = umma_idesc(CG2 ? 256 : 128, st.n_out);
-    const int n_stages = st.n_stages;
-    const int64_t tr = ((it * p.prog.n_steps + si) * 2 + slot) * 4;
-    // A operand written, accumulator drained (CG2: by the epilogue groups of both CTAs)
-    mbar_wait(sm.bar(BAR_READY + slot), (ready_ph >> slot) & 1u);
-    ready_ph ^= 1u << slot;
-    tc_fence_after();
-    if (trace) p.trace[tr] = clock64();
-    const uint32_t d_tmem = tmem_base + slot * 256u;
-    uint64_t a_desc = umma_desc(sm.chunk_u32(slot, 0));
-    uint32_t acc = (uint32_t)st.accumulate;
-    bool saving = false;
-    if (!CG2 && p.save != nullptr && st.save_chunks > 0) {   // training mode: keep this step's A operand for the weight-gradient kernels
-      const int64_t tile = tile_index<false>(pair0, crank_m, slot);
-      saving = tile < n_tiles_m;
-      if (saving && lane_m == 0)
-        bulk_s2g(p.save + (size_t)tile * p.prog.save_tile_bytes + st.save_off, sm.chunk_u32(slot, 0), (uint32_t)st.save_chunks * kChunkBytes);
+  for (int64_t pair0 = (int64_t)blockIdx.x - crank_m; pair0 < n_pairs; pair0 += gridDim.x) {
+    for (int si = 0; si < p.prog.n_steps; ++si) {
+      const Step& st = p.prog.s[si];
+      const uint32_t idesc = umma_idesc(CG2 ? 256 : 128, st.n_out);
+      const int n_stages = st.n_stages;
+#pragma unroll
+      for (uint32_t slot = 0; slot < 2; ++slot, tr += 4) {
+        mbar_wait(sm.bar(BAR_READY + slot), (ready_ph >> slot) & 1u);   // A operand written, accumulator drained (CG2: in both CTAs)
+        ready_ph ^= 1u << slot;
+        tc_fence_after();
+        if (trace) p.trace[tr] = clock64();
+        const uint32_t d_tmem = tmem_base + slot * 256u;
+        uint64_t a_desc = umma_desc(sm.chunk_u32(slot, 0));
+        uint32_t acc = (uint32_t)st.accumulate;
+        bool saving = false;
+        if (!CG2 && p.save != nullptr && st.save_chunks > 0) {   // training mode: keep this step's A operand for the weight-gradient kernels
+          const int64_t tile = tile_index<false>(pair0, crank_m, slot);
+          saving = tile < n_tiles_m;
+          if (saving && lane_m == 0)
+            bulk_s2g(p.save + (size_t)tile * p.prog.save_tile_bytes + st.save_off, sm.chunk_u32(slot, 0), (uint32_t)st.save_chunks * kChunkBytes);
+        }
+        for (int j = 0; j < n_stages; ++j) {
+          mbar_wait(sm.bar(BAR_WFULL + stage), ph);
+          tc_fence_after();
+          if (CG2) umma2_stage_elect(d_tmem, a_desc, umma_desc_sw64(sm.stage2_u32(stage)), idesc, acc, sm.bar(BAR_WEMPTY + stage));
+          else umma_stage_elect(d_tmem, a_desc, umma_desc_sw64(sm.stage_u32(stage)), idesc, acc, sm.bar(BAR_WEMPTY + stage));
+          acc = 1u;
+          a_desc += (j & 1) ? (uint64_t)((kChunkBytes - 64u) >> 4) : (uint64_t)(64u >> 4);   // next 32-k half of the chunk / next chunk
+          if (++stage == RING) { stage = 0; ph ^= 1u; }
+        }
+        if (st.bias_stage) {
+          mbar_wait(sm.bar(BAR_WFULL + stage), ph);
+          tc_fence_after();
+          if (CG2) umma2_bias_elect(d_tmem, ones_desc, umma_desc_sw32(sm.stage2_u32(stage)), idesc, sm.bar(BAR_WEMPTY + stage));
+          else umma_bias_elect(d_tmem, ones_desc, umma_desc_sw32(sm.stage_u32(stage)), idesc, sm.bar(BAR_WEMPTY + stage));
+          if (++stage == RING) { stage = 0; ph ^= 1u; }
+        }
+        if (saving) {   // the epilogue overwrites the chunks after BAR_ACC: the bulk store must have read them by then
+          if (lane_m == 0 && !(p.exp_flags & 8)) bulk_wait_read_all();   // exp flag 8 (timing experiment only, WRONG results): no wait
+          __syncwarp();
+        }
+        if (CG2) umma2_commit_elect(sm.bar(BAR_ACC + slot));
+        else umma_commit_elect(sm.bar(BAR_ACC + slot));
+        if (trace) p.trace[tr + 1] = clock64();
+      }
     }
-    for (int j = 0; j < n_stages; ++j) {
-      mbar_wait(sm.bar(BAR_WFULL + stage), ph);
-      tc_fence_after();
-      if (CG2) umma2_stage_elect(d_tmem, a_desc, umma_desc_sw64(sm.stage2_u32(stage)), idesc, acc, sm.bar(BAR_WEMPTY + stage));
-      else umma_stage_elect(d_tmem, a_desc, umma_desc_sw64(sm.stage_u32(stage)), idesc, acc, sm.bar(BAR_WEMPTY + stage));
-      acc = 1u;
-      a_desc += (j & 1) ? (uint64_t)((kChunkBytes - 64u) >> 4) : (uint64_t)(64u >> 4);   // next 32-k half of the chunk / next chunk
-      if (++stage == RING) { stage = 0; ph ^= 1u; }
-    }
-    if (st.bias_stage) {
-      mbar_wait(sm.bar(BAR_WFULL + stage), ph);
-      tc_fence_after();
-      if (CG2) umma2_bias_elect(d_tmem, ones_desc, umma_desc_sw32(sm.stage2_u32(stage)), idesc, sm.bar(BAR_WEMPTY + stage));
-      else umma_bias_elect(d_tmem, ones_desc, umma_desc_sw32(sm.stage_u32(stage)), idesc, sm.bar(BAR_WEMPTY + stage));
-      if (++stage == RING) { stage = 0; ph ^= 1u; }
-    }
-    if (saving) {   // the epilogue overwrites the chunks after BAR_ACC: the bulk store must have read them by then
-      if (lane_m == 0 && !(p.exp_flags & 8)) bulk_wait_read_all();   // exp flag 8 (timing experiment only, WRONG results): no wait
-      __syncwarp();
-    }
-    if (CG2) umma2_commit_elect(sm.bar(BAR_ACC + slot));
-    else umma_commit_elect(sm.bar(BAR_ACC + slot));
-    if (trace) p.trace[tr + 1] = clock64();
-  });
+  }
   if (!CG2 && p.save != nullptr && lane_m == 0) bulk_wait_all();
 }
 
@@ -1179,7 +1157,6 @@ static void fill_common2(tc2::Params& p, const snb_handle_s* h, const void* pack
   p.w2 = h->layers[h->iR2].w; p.b2 = h->layers[h->iR2].b;
   p.n_latent = h->arch.shape_blocks + h->arch.texture_blocks;
   { const char* ev = getenv("SNB_TC_EXP"); p.exp_flags = ev ? atoi(ev) : 0; }
-  { static const int stg = [] { const char* e = getenv("SNB_TC_STAGGER"); return e ? atoi(e) : 0; }(); p.stagger = stg; }
   p.trace = g_trace;
 }
 
@@ -1238,7 +1215,6 @@ int tc2_launch_fwd(const snb_handle_s* h, const void* packed2, const float* xyz,
   p.save = save;
   p.m_dev = m_dev;
   p.prog = save ? pl.fwd_train : pl.fwd;
-  p.stagger = std::max(0, std::min(p.stagger, p.prog.n_steps - 1));
   if (dbg) {
     SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
     SNB_CHECK_CUDA(tc2_launch(tc2_fwd_kernel<true, false>, tc2_grid(tc2_fwd_kernel<true, false>, M), st, p));
@@ -1264,7 +1240,6 @@ int tc2_launch_bwd(const snb_handle_s* h, const void* packed2, const float* xyz,
   p.m_dev = m_dev;
   SNB_REQUIRE(save == nullptr || g_xyz != nullptr, "tc2 backward: training mode runs the full program (g_xyz scratch required)");
   p.prog = g_xyz ? pl.bwd_full : pl.bwd_noxyz;
-  p.stagger = std::max(0, std::min(p.stagger, p.prog.n_steps - 1));
   if (tc2_use_cg2(p)) {
     SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
     SNB_CHECK_CUDA(tc2_launch(tc2_bwd_kernel<true>, tc2_grid(tc2_bwd_kernel<true>, M), st, p));
