@@ -238,18 +238,26 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step_resident()
     launches0 = lib.snb_launch_count()
-    lib.snb_kernel_timing_enable(1)   # CUDA events on the launch stream around the tcgen05 kernels alone
     with ClockSampler(local) as clk:
         ms_total = timed(step_resident, args.steps)
     launches = lib.snb_launch_count() - launches0
     torch.cuda.synchronize()
+    # Kernel-only pass for the roofline: the SAME step on ONE stream with CUDA events on the launch stream around the tcgen05
+    # kernels alone.  (With several streams an event pair also spans the time a decoder kernel queues behind another stream's
+    # decoder kernel -- the SMs hold one decoder CTA each -- so the multi-stream pass above is timed without them.)
     import ctypes
+    all_streams = list(streams)
+    streams[:] = [main_stream]
+    step_resident()
+    lib.snb_kernel_timing_enable(1)
+    ms_single = timed(step_resident, args.steps)
     kern = {}
     for which, name in ((0, "fwd"), (1, "bwd")):
         buf = (ctypes.c_float * 4096)()
         n = lib.snb_kernel_timing_read(which, buf, 4096)
         kern[name] = [buf[i] for i in range(n)]
     lib.snb_kernel_timing_enable(0)
+    streams[:] = all_streams
     for _ in range(2):
         step_e2e()
     with ClockSampler(local) as clk2:
@@ -309,7 +317,11 @@ def run_ours(args):
                     "avg_launch_ms": round(roof[dom]["ms"], 4),
                     "other": {k: {"ms": round(v["ms"], 4), "tflops": round(v["tflops"], 2)} for k, v in roof.items()},
                     "mlp_share_of_step": round(sum(v["total_ms"] for v in roof.values()) / ms_total, 4),
-                    "timed": "CUDA events on the launch stream around the kernel alone, inside the timed region" if kern.get("fwd") else
+                    "mlp_share_of_single_stream_step": round(sum(v["total_ms"] for v in roof.values()) / ms_single, 4),
+                    "single_stream_ms_per_step": round(ms_single / args.steps, 3),
+                    "timed": "CUDA events on the launch stream around the kernel alone, over a timed pass of the same step on ONE "
+                             "stream (K steps, right after the multi-stream pass `value` comes from: there an event pair would also "
+                             "span the kernel's wait behind another stream's decoder kernel)" if kern.get("fwd") else
                              "CUDA events around the decoder C-ABI call"}
 
     # secondary roofline, HBM-bound: the compositing kernels on one step's worth of rays (16 x 16384 rays x 64 samples: 335 MB in,
@@ -474,7 +486,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--streams", type=int, default=2, help="CUDA streams the independent objects alternate over (1 = one stream)")
+    ap.add_argument("--streams", type=int, default=3, help="CUDA streams the independent objects alternate over (1 = one stream)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -110,7 +110,27 @@ def ptr(t):
 
 
 def stream_ptr():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """cudaStream_t of torch's current stream on the current device (the raw accessor: torch.cuda.current_stream() builds a
+    Stream object per call, ~10x the cost, and every C-ABI call needs this)."""
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
+
+
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def on_device(dev):
+    """`with on_device(t.device):` == `with torch.cuda.device(t.device):`, but free when that device is already current."""
+    if dev.index is None or torch._C._cuda_getDevice() == dev.index:
+        return _NO_GUARD
+    return torch.cuda.device(dev)
 
 
 def require_cuda(*tensors):

@@ -1,5 +1,6 @@
 // Per-model handle shared by the MLP back ends.
 #pragma once
+#include <memory>
 #include <vector>
 #include "../../include/supnerf_b200.h"
 
@@ -15,6 +16,9 @@ struct snb_handle_s {
   bool weights_set = false;
   // bf16 back end
   const void* packed = nullptr;   // borrowed: caller-owned buffer filled by snb_pack_weights
+  // per-handle caches of pure functions of the architecture (built on first use; a handle is used by one host thread at a time)
+  mutable std::shared_ptr<void> tc2_programs;   // mlp_tc2.cu: the step programs of the two-tile kernels
+  mutable size_t v1_packed_bytes_cache = 0;     // mlp_tc.cu: size of the first-generation packed image
   // CodeNeRF-family layer indices
   int iX = 0, iES = 0, iSG = 0, iEV = 0, iR0 = 0, iR2 = 0;
   int iSL(int j) const { return 1 + 2 * (j - 1); }       // shape_latent_layer_j, j = 1..Bs

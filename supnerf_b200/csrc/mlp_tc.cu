@@ -745,7 +745,10 @@ int tc2_launch_wgrad(const snb_handle_s* h, int64_t M, int64_t B, const uint8_t*
 int tc2_launch_latent_wgrad(const snb_handle_s* h, int64_t B, const float* zlat, const float* dz, const float* shape_latent,
                             const float* texture_latent, float* const* gw, cudaStream_t st);
 
-static size_t v1_packed_bytes(const snb_handle_s* h) { return ((size_t)build_plan(h).total_bytes + 1024 + 1023) & ~size_t(1023); }
+static size_t v1_packed_bytes(const snb_handle_s* h) {
+  if (h->v1_packed_bytes_cache == 0) h->v1_packed_bytes_cache = ((size_t)build_plan(h).total_bytes + 1024 + 1023) & ~size_t(1023);
+  return h->v1_packed_bytes_cache;
+}
 static bool use_v2(const snb_handle_s* h) {
   static const bool force_v1 = [] { const char* e = getenv("SNB_TC_V1"); return e && atoi(e) != 0; }();
   return !force_v1 && tc2_supported(h);

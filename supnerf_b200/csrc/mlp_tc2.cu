@@ -1128,9 +1128,16 @@ static Tc2Plan build_plan2(const snb_handle_s* h) {
   return pl;
 }
 
+// The step programs depend on the architecture only (the pack jobs also carry the weight pointers: tc2_pack_weights rebuilds):
+// built once per handle, every launch reads them from the cache.
+static const Tc2Plan& cached_plan2(const snb_handle_s* h) {
+  if (!h->tc2_programs) h->tc2_programs = std::make_shared<Tc2Plan>(build_plan2(h));
+  return *static_cast<const Tc2Plan*>(h->tc2_programs.get());
+}
+
 size_t tc2_packed_bytes(const snb_handle_s* h) {
   if (!tc2_supported(h)) return 0;
-  return build_plan2(h).total_bytes + 1024;
+  return cached_plan2(h).total_bytes + 1024;
 }
 
 int tc2_pack_weights(const snb_handle_s* h, void* packed, cudaStream_t st) {
@@ -1156,7 +1163,7 @@ static void fill_common2(tc2::Params& p, const snb_handle_s* h, const void* pack
   p.wsig = h->layers[h->iSG].w; p.bsig = h->layers[h->iSG].b;
   p.w2 = h->layers[h->iR2].w; p.b2 = h->layers[h->iR2].b;
   p.n_latent = h->arch.shape_blocks + h->arch.texture_blocks;
-  { const char* ev = getenv("SNB_TC_EXP"); p.exp_flags = ev ? atoi(ev) : 0; }
+  { static const int exp_env = [] { const char* ev = getenv("SNB_TC_EXP"); return ev ? atoi(ev) : 0; }(); p.exp_flags = exp_env; }
   p.trace = g_trace;
 }
 
@@ -1191,6 +1198,21 @@ static bool tc2_use_cg2(const tc2::Params& p) {
   return env != 0 && p.save == nullptr && p.dbg == nullptr && (p.B == 1 || p.rows_per_obj % 256 == 0);
 }
 
+// opt-in shared-memory size of every kernel variant, once per device
+static int tc2_init_device() {
+  static bool done[64] = {};
+  int dev = 0;
+  SNB_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && done[dev]) return 0;
+  SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
+  SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
+  SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
+  SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
+  SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
+  if (dev >= 0 && dev < 64) done[dev] = true;
+  return 0;
+}
+
 template <typename K>
 static cudaError_t tc2_launch(K kernel, int grid, cudaStream_t st, const tc2::Params& p) {
   cudaLaunchConfig_t cfg{};
@@ -1208,21 +1230,19 @@ static cudaError_t tc2_launch(K kernel, int grid, cudaStream_t st, const tc2::Pa
 int tc2_launch_fwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                    const uint8_t* eimg, uint32_t* masks, float* sigma, float* rgb, float* dbg, uint8_t* save, cudaStream_t st,
                    const int64_t* m_dev) {
-  Tc2Plan pl = build_plan2(h);
+  const Tc2Plan& pl = cached_plan2(h);
   tc2::Params p;
   fill_common2(p, h, packed2, xyz, viewdir, M, B, eimg, masks);
   p.sigma = sigma; p.rgb = rgb; p.dbg = dbg;
   p.save = save;
   p.m_dev = m_dev;
   p.prog = save ? pl.fwd_train : pl.fwd;
+  if (tc2_init_device()) return 1;
   if (dbg) {
-    SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
     SNB_CHECK_CUDA(tc2_launch(tc2_fwd_kernel<true, false>, tc2_grid(tc2_fwd_kernel<true, false>, M), st, p));
   } else if (tc2_use_cg2(p)) {
-    SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
     SNB_CHECK_CUDA(tc2_launch(tc2_fwd_kernel<false, true>, tc2_grid(tc2_fwd_kernel<false, true>, M), st, p));
   } else {
-    SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
     SNB_CHECK_CUDA(tc2_launch(tc2_fwd_kernel<false, false>, tc2_grid(tc2_fwd_kernel<false, false>, M), st, p));
   }
   return 0;
@@ -1231,7 +1251,7 @@ int tc2_launch_fwd(const snb_handle_s* h, const void* packed2, const float* xyz,
 int tc2_launch_bwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                    const uint32_t* masks, const float* sigma, const float* g_sigma, const float* g_rgb, float* g_xyz,
                    float* g_viewdir, float* g_zlat, uint8_t* save, cudaStream_t st, const int64_t* m_dev) {
-  Tc2Plan pl = build_plan2(h);
+  const Tc2Plan& pl = cached_plan2(h);
   tc2::Params p;
   fill_common2(p, h, packed2, xyz, viewdir, M, B, nullptr, const_cast<uint32_t*>(masks));
   p.sigma_in = sigma; p.g_sigma = g_sigma; p.g_rgb = g_rgb; p.g_xyz = g_xyz; p.g_viewdir = g_viewdir; p.g_zlat = g_zlat;
@@ -1240,11 +1260,10 @@ int tc2_launch_bwd(const snb_handle_s* h, const void* packed2, const float* xyz,
   p.m_dev = m_dev;
   SNB_REQUIRE(save == nullptr || g_xyz != nullptr, "tc2 backward: training mode runs the full program (g_xyz scratch required)");
   p.prog = g_xyz ? pl.bwd_full : pl.bwd_noxyz;
+  if (tc2_init_device()) return 1;
   if (tc2_use_cg2(p)) {
-    SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
     SNB_CHECK_CUDA(tc2_launch(tc2_bwd_kernel<true>, tc2_grid(tc2_bwd_kernel<true>, M), st, p));
   } else {
-    SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
     SNB_CHECK_CUDA(tc2_launch(tc2_bwd_kernel<false>, tc2_grid(tc2_bwd_kernel<false>, M), st, p));
   }
   return 0;
@@ -1556,10 +1575,10 @@ __global__ void __launch_bounds__(1024) wgrad_latent_layers_kernel(const __grid_
 }  // namespace tc2
 
 size_t tc2_fwd_save_bytes(const snb_handle_s* h, int64_t M) {
-  return (size_t)((M + kTileM - 1) / kTileM) * build_plan2(h).fwd_train.save_tile_bytes;
+  return (size_t)((M + kTileM - 1) / kTileM) * cached_plan2(h).fwd_train.save_tile_bytes;
 }
 size_t tc2_bwd_save_bytes(const snb_handle_s* h, int64_t M) {
-  return (size_t)((M + kTileM - 1) / kTileM) * build_plan2(h).bwd_full.save_tile_bytes;
+  return (size_t)((M + kTileM - 1) / kTileM) * cached_plan2(h).bwd_full.save_tile_bytes;
 }
 
 // All weight / bias gradients of the decoder layers that run on the tensor core, the two heads, and the z (x) s outer products
@@ -1568,7 +1587,7 @@ size_t tc2_bwd_save_bytes(const snb_handle_s* h, int64_t M) {
 int tc2_launch_wgrad(const snb_handle_s* h, int64_t M, int64_t B, const uint8_t* fsave, const uint8_t* bsave, const float* sigma,
                      const float* g_sigma, const float* g_rgb, const float* s_lat, const float* zlat, float* const* gw,
                      cudaStream_t st, const int64_t* m_dev) {
-  Tc2Plan pl = build_plan2(h);
+  const Tc2Plan& pl = cached_plan2(h);
   const tc2::Program& F = pl.fwd_train;
   const tc2::Program& Bp = pl.bwd_full;
   const int Bs = h->arch.shape_blocks, Bt = h->arch.texture_blocks, W = 256, dv = h->d_dir(), dx = h->d_xyz();

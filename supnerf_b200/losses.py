@@ -11,7 +11,7 @@ The reference has no function for them: the same five lines are written inline i
 import torch
 
 from . import _lib
-from ._lib import check, f32c, ptr, require_cuda, stream_ptr
+from ._lib import check, f32c, on_device, ptr, require_cuda, stream_ptr
 
 
 _SCRATCH_BYTES = None
@@ -31,7 +31,7 @@ class _RefineLoss(torch.autograd.Function):
         if _SCRATCH_BYTES is None:
             _SCRATCH_BYTES = lib.snb_refine_loss_scratch_bytes()
         scratch = torch.empty(_SCRATCH_BYTES, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with on_device(dev):
             check(lib.snb_refine_loss_fwd(ptr(rgb), ptr(acc), ptr(tgt), ptr(occ), n, float(coef), ptr(den), ptr(out), ptr(scratch),
                                           stream_ptr()), "snb_refine_loss_fwd")
         ctx.save_for_backward(rgb, acc, tgt, occ, scratch)
@@ -48,7 +48,7 @@ class _RefineLoss(torch.autograd.Function):
         g_rgb = torch.empty_like(rgb)
         g_acc = torch.empty_like(acc)
         g_loss = f32c(g_loss)
-        with torch.cuda.device(rgb.device):
+        with on_device(rgb.device):
             check(lib.snb_refine_loss_bwd(ptr(rgb), ptr(acc), ptr(tgt), ptr(occ), n, ctx.coef, ptr(scratch), ptr(g_loss), ptr(g_rgb),
                                           ptr(g_acc), stream_ptr()), "snb_refine_loss_bwd")
         return g_rgb, g_acc, None, None, None, None

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import check, f32c, ptr, require_cuda, stream_ptr
+from ._lib import check, f32c, on_device, ptr, require_cuda, stream_ptr
 
 WHITE_BKGD, SIGMA_RELU = 1, 2
 PREC = {"fp32": 0, "bf16": 1}
@@ -29,7 +29,7 @@ class _Composite(torch.autograd.Function):
         o_rgb = torch.empty(n, 3, device=sigma.device, dtype=torch.float32)
         o_dep = torch.empty(n, device=sigma.device, dtype=torch.float32)
         o_acc = torch.empty(n, device=sigma.device, dtype=torch.float32)
-        with torch.cuda.device(sigma.device):
+        with on_device(sigma.device):
             check(lib.snb_composite_fwd(ptr(sigma), ptr(rgb), ptr(z), rays_per_zrow, n, s, flags, ptr(o_rgb), ptr(o_dep),
                                         ptr(o_acc), stream_ptr()), "snb_composite_fwd")
         ctx.save_for_backward(sigma, rgb, z)
@@ -49,7 +49,7 @@ class _Composite(torch.autograd.Function):
         g_rgbs = torch.empty_like(rgb)
         need_z = ctx.needs_input_grad[2]
         g_z = torch.empty_like(sigma) if need_z else None
-        with torch.cuda.device(sigma.device):
+        with on_device(sigma.device):
             check(lib.snb_composite_bwd(ptr(sigma), ptr(rgb), ptr(z), rays_per_zrow, n, s, flags, ptr(g_rgb), ptr(g_dep),
                                         ptr(g_acc), ptr(g_sigma), ptr(g_rgbs), ptr(g_z), stream_ptr()), "snb_composite_bwd")
         if need_z and z.shape[0] != n:  # shared rows: reduce the per-ray gradient onto the shared vector(s)
@@ -81,7 +81,7 @@ class _GetRays(torch.autograd.Function):
         n = px.numel()
         ro = torch.empty(n, 3, device=px.device, dtype=torch.float32)
         vd = torch.empty(n, 3, device=px.device, dtype=torch.float32)
-        with torch.cuda.device(px.device):
+        with on_device(px.device):
             check(lib.snb_get_rays_fwd(ptr(px), ptr(py), n, ptr(K), ptr(c2w), ptr(ro), ptr(vd), stream_ptr()), "snb_get_rays_fwd")
         ctx.save_for_backward(px, py, K, c2w)
         return ro, vd
@@ -94,7 +94,7 @@ class _GetRays(torch.autograd.Function):
         g_ro = f32c(g_ro) if g_ro is not None else torch.zeros(n, 3, device=px.device)
         g_vd = f32c(g_vd) if g_vd is not None else torch.zeros(n, 3, device=px.device)
         g_c2w = torch.zeros(3, 4, device=px.device, dtype=torch.float32)
-        with torch.cuda.device(px.device):
+        with on_device(px.device):
             check(lib.snb_get_rays_bwd(ptr(px), ptr(py), n, ptr(K), ptr(c2w), ptr(g_ro), ptr(g_vd), ptr(g_c2w), stream_ptr()),
                   "snb_get_rays_bwd")
         return None, None, None, g_c2w
@@ -116,7 +116,7 @@ class _RayBox(torch.autograd.Function):
         tn = torch.empty(n, device=ro.device, dtype=torch.float32)
         tf = torch.empty(n, device=ro.device, dtype=torch.float32)
         hit = torch.empty(n, device=ro.device, dtype=torch.uint8)
-        with torch.cuda.device(ro.device):
+        with on_device(ro.device):
             check(lib.snb_ray_box_fwd(ptr(ro), ptr(rd), ptr(amin), ptr(amax), n, ptr(tn), ptr(tf), ptr(hit), stream_ptr()),
                   "snb_ray_box_fwd")
         ctx.save_for_backward(ro, rd, amin, amax)
@@ -134,7 +134,7 @@ class _RayBox(torch.autograd.Function):
         g_o, g_d = torch.empty_like(ro), torch.empty_like(rd)
         g_min = torch.empty_like(ro) if amin is not None and ctx.needs_input_grad[2] else None
         g_max = torch.empty_like(ro) if amax is not None and ctx.needs_input_grad[3] else None
-        with torch.cuda.device(ro.device):
+        with on_device(ro.device):
             check(lib.snb_ray_box_bwd(ptr(ro), ptr(rd), ptr(amin), ptr(amax), n, ptr(g_tn), ptr(g_tf), ptr(g_o), ptr(g_d),
                                       ptr(g_min), ptr(g_max), stream_ptr()), "snb_ray_box_bwd")
         return g_o, g_d, g_min, g_max
@@ -158,7 +158,7 @@ class _SampleBox(torch.autograd.Function):
         zv = torch.empty(n, s, device=dev, dtype=torch.float32)
         hit = torch.empty(n, device=dev, dtype=torch.uint8)
         h3 = (ctypes.c_float * 3)(*[float(v) for v in aabb_half])
-        with torch.cuda.device(dev):
+        with on_device(dev):
             check(lib.snb_sample_box_fwd(ptr(rays_o), ptr(viewdir), ptr(z_steps), ptr(jitter), n, s, float(half_diag), h3,
                                          ptr(xyz), ptr(vrep), ptr(zv), ptr(hit), stream_ptr()), "snb_sample_box_fwd")
         ctx.save_for_backward(rays_o, viewdir, z_steps, jitter)
@@ -178,7 +178,7 @@ class _SampleBox(torch.autograd.Function):
         g_zv = f32c(g_zv) if g_zv is not None else None
         g_o, g_d = torch.empty_like(rays_o), torch.empty_like(viewdir)
         h3 = (ctypes.c_float * 3)(*half)
-        with torch.cuda.device(rays_o.device):
+        with on_device(rays_o.device):
             check(lib.snb_sample_box_bwd(ptr(rays_o), ptr(viewdir), ptr(z_steps), ptr(jitter), n, s, half_diag, h3, ptr(g_xyz),
                                          ptr(g_vrep), ptr(g_zv), ptr(g_o), ptr(g_d), stream_ptr()), "snb_sample_box_bwd")
         return g_o, g_d, None, None, None, None
@@ -197,7 +197,7 @@ class _SampleShell(torch.autograd.Function):
         n, s = rays_o.shape[0], z.numel()
         xyz = torch.empty(n, s, 3, device=rays_o.device, dtype=torch.float32)
         vrep = torch.empty(n, s, 3, device=rays_o.device, dtype=torch.float32)
-        with torch.cuda.device(rays_o.device):
+        with on_device(rays_o.device):
             check(lib.snb_sample_shell_fwd(ptr(rays_o), ptr(viewdir), ptr(z), n, s, float(obj_diag), int(swap), ptr(xyz),
                                            ptr(vrep), stream_ptr()), "snb_sample_shell_fwd")
         ctx.save_for_backward(z)
@@ -213,7 +213,7 @@ class _SampleShell(torch.autograd.Function):
         g_vrep = f32c(g_vrep) if g_vrep is not None else None
         g_o = torch.empty(n, 3, device=z.device, dtype=torch.float32)
         g_d = torch.empty(n, 3, device=z.device, dtype=torch.float32)
-        with torch.cuda.device(z.device):
+        with on_device(z.device):
             check(lib.snb_sample_shell_bwd(ptr(z), n, s, obj_diag, swap, ptr(g_xyz), ptr(g_vrep), ptr(g_o), ptr(g_d),
                                            stream_ptr()), "snb_sample_shell_bwd")
         return g_o, g_d, None, None, None
@@ -238,6 +238,7 @@ class DecoderHandle:
         self._packed = None
         self._packed_key = None
         self._keep = None
+        self._frozen = None
 
     def __del__(self):
         try:
@@ -246,17 +247,31 @@ class DecoderHandle:
         except Exception:
             pass
 
-    def set_weights(self, tensors):
+    def set_weights(self, tensors, saved=False):
+        """Point the handle at the fp32 weight storages.  saved=True (an autograd backward re-presenting the tensors its forward
+        saved): the forward already set exactly these storages unless another forward ran in between, so comparing the first
+        and last pointer is enough to skip the full key."""
         lib = _lib.load()
         assert len(tensors) == self.n_tensors, (len(tensors), self.n_tensors)
-        key = tuple(t.data_ptr() for t in tensors)
-        if key == getattr(self, "_set_key", None) and all(t.dtype == torch.float32 and t.is_contiguous() for t in tensors):
+        old = self.__dict__.get("_set_key")
+        if saved and old is not None and tensors[0].data_ptr() == old[0] and tensors[-1].data_ptr() == old[-1]:
+            return
+        key = tuple([t.data_ptr() for t in tensors])
+        if key == old and all([t.dtype == torch.float32 and t.is_contiguous() for t in tensors]):
             return   # same storage as last time: the handle already borrows these pointers
         self._set_key = key
         self._keep = [f32c(t.detach()) for t in tensors]
         require_cuda(*self._keep)
         arr = (ctypes.c_void_p * self.n_tensors)(*[t.data_ptr() for t in self._keep])
         check(lib.snb_set_weights(self.h, arr, self.n_tensors), "snb_set_weights")
+
+    def use_frozen(self, tensors, precision):
+        """Point the handle at a weight set that takes no part in autograd; `_frozen` identifies the set last used."""
+        self.set_weights(tensors)
+        if precision != PREC["fp32"]:
+            self.ensure_packed(tensors)
+        if self.__dict__.get("_frozen") is not tensors:
+            self._frozen = tensors
 
     def ensure_packed(self, tensors):
         """bf16 mode: (re)pack when a parameter was replaced or modified in place."""
@@ -268,7 +283,7 @@ class DecoderHandle:
         dev = self._keep[0].device
         if self._packed is None or self._packed.numel() < nbytes or self._packed.device != dev:
             self._packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with on_device(dev):
             check(lib.snb_pack_weights(self.h, ptr(self._packed), stream_ptr()), "snb_pack_weights")
         self._packed_key = key
 
@@ -306,7 +321,7 @@ class _Decoder(torch.autograd.Function):
         ws = torch.empty(lib.snb_mlp_workspace_bytes(handle.h, m, n_objs, precision), dtype=torch.uint8, device=dev)
         sigma = torch.empty(m, device=dev, dtype=torch.float32)
         rgb = torch.empty(m, 3, device=dev, dtype=torch.float32)
-        with torch.cuda.device(dev):
+        with on_device(dev):
             ev = _timing_start()
             check(lib.snb_mlp_fwd(handle.h, precision, ptr(xyz), ptr(viewdir), m, n_objs, ptr(shape_latent), ptr(texture_latent),
                                   ptr(sigma), ptr(rgb), ptr(ws), stream_ptr()), "snb_mlp_fwd")
@@ -334,9 +349,9 @@ class _Decoder(torch.autograd.Function):
         if need_w:
             gws = [torch.empty_like(w, dtype=torch.float32).contiguous() for w in weights]
             gw_arr = (ctypes.c_void_p * len(gws))(*[g.data_ptr() for g in gws])
-        handle.set_weights(weights)
+        handle.set_weights(weights, saved=True)
         scratch = torch.empty(lib.snb_mlp_bwd_scratch_bytes(handle.h, m, n_objs, precision), dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with on_device(dev):
             ev = _timing_start()
             check(lib.snb_mlp_bwd(handle.h, precision, ptr(xyz), ptr(viewdir), m, n_objs, ptr(shape_latent), ptr(texture_latent),
                                   ptr(sigma), ptr(g_sigma), ptr(g_rgb), ptr(ws), ptr(scratch), ptr(g_xyz), ptr(g_vd), ptr(g_sl),
@@ -400,11 +415,12 @@ class _RenderBox(torch.autograd.Function):
         else:                     # ("shell", obj_diag, shapenet_swap)
             desc = _lib.SnbRenderDesc(n, int(n_samples), int(precision), int(flags), 1.0, (ctypes.c_float * 3)(1.0, 1.0, 1.0), 1,
                                       float(geom[1]), int(bool(geom[2])))
-        handle.set_weights(weights)
-        if precision == PREC["bf16"]:
-            handle.ensure_packed(weights)
-            if any(ctx.needs_input_grad[13:]):
-                desc.precision = PREC_BF16_TRAIN
+        if weights:   # (frozen weights never enter the autograd node: _render_apply pointed the handle at them already)
+            handle.set_weights(weights)
+            if precision == PREC["bf16"]:
+                handle.ensure_packed(weights)
+                if any(ctx.needs_input_grad[13:]):
+                    desc.precision = PREC_BF16_TRAIN
         key = (n, int(n_samples), int(desc.precision), int(desc.mode))
         cache = handle.__dict__.setdefault("_render_sizes", {})   # per handle: pure functions of (architecture, N, S, precision, mode)
         sizes = cache.get(key)
@@ -418,12 +434,12 @@ class _RenderBox(torch.autograd.Function):
         o_dep = torch.empty(n, device=dev, dtype=torch.float32)
         o_acc = torch.empty(n, device=dev, dtype=torch.float32)
         hit = torch.empty(n, device=dev, dtype=torch.uint8)
-        with torch.cuda.device(dev):
+        with on_device(dev):
             check(lib.snb_render_fwd(handle.h, ctypes.byref(desc), ptr(px), ptr(py), ptr(K), ptr(c2w), ptr(z_steps), ptr(jitter),
                                      ptr(shape_latent), ptr(texture_latent), ptr(o_rgb), ptr(o_dep), ptr(o_acc), ptr(hit), ptr(ws),
                                      stream_ptr()), "snb_render_fwd")
         ctx.save_for_backward(px, py, K, c2w, z_steps, jitter, shape_latent, texture_latent, ws, *weights)
-        ctx.meta = (handle, desc, sizes[1])
+        ctx.meta = (handle, desc, sizes[1], handle._frozen if not weights else None)
         hitb = hit.view(torch.bool)   # 0 / 1 bytes: a zero-copy view
         ctx.mark_non_differentiable(hitb)
         return o_rgb, o_dep, o_acc, hitb
@@ -432,7 +448,7 @@ class _RenderBox(torch.autograd.Function):
     def backward(ctx, g_rgb, g_dep, g_acc, _g_hit):
         lib = _lib.load()
         px, py, K, c2w, z_steps, jitter, shape_latent, texture_latent, ws, *weights = ctx.saved_tensors
-        handle, desc, scratch_bytes = ctx.meta
+        handle, desc, scratch_bytes, frozen = ctx.meta
         n = px.numel()
         dev = px.device
         g_rgb = f32c(g_rgb) if g_rgb is not None else torch.zeros(n, 3, device=dev)
@@ -447,9 +463,12 @@ class _RenderBox(torch.autograd.Function):
         if need_w:
             gws = [torch.empty_like(w, dtype=torch.float32).contiguous() for w in weights]
             gw_arr = (ctypes.c_void_p * len(gws))(*[g.data_ptr() for g in gws])
-        handle.set_weights(weights)
+        if weights:
+            handle.set_weights(weights, saved=True)
+        elif frozen is not handle._frozen:   # another weight set was rendered in between: point the handle back at this node's
+            handle.use_frozen(frozen, desc.precision)
         scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with on_device(dev):
             check(lib.snb_render_bwd(handle.h, ctypes.byref(desc), ptr(px), ptr(py), ptr(K), ptr(c2w), ptr(z_steps), ptr(jitter),
                                      ptr(shape_latent), ptr(texture_latent), ptr(ws), ptr(g_rgb), ptr(g_dep), ptr(g_acc),
                                      ptr(scratch), ptr(g_c2w), ptr(g_sl), ptr(g_tl), gw_arr, stream_ptr()), "snb_render_bwd")
@@ -457,20 +476,32 @@ class _RenderBox(torch.autograd.Function):
         return (None,) * 8 + (g_c2w, None, None, g_sl if need[11] else None, g_tl if need[12] else None) + out_w
 
 
+def _render_apply(handle, prec, n_samples, flags, geom, px, py, K, c2w, z_steps, jitter, shape_latent, texture_latent, weights):
+    """Frozen weights (the refine loops: no weight requires grad) stay OUT of the autograd node: 2 x ~30 tensors less to wrap,
+    save and return gradients for per object.  The node remembers which weight set it rendered (DecoderHandle.use_frozen)."""
+    for w in weights:
+        if w.requires_grad:
+            break
+    else:
+        handle.use_frozen(weights, prec)
+        return _RenderBox.apply(handle, prec, n_samples, flags, geom, px, py, K, c2w, z_steps, jitter, shape_latent, texture_latent)
+    return _RenderBox.apply(handle, prec, n_samples, flags, geom, px, py, K, c2w, z_steps, jitter, shape_latent, texture_latent, *weights)
+
+
 def render_box(handle, precision, n_samples, white_bkgd, half_diag, aabb_half, px, py, K, c2w, z_steps, jitter, shape_latent,
                texture_latent, weights):
     """-> rgb (N,3), depth (N,), acc (N,), hit (N,) bool for one object (latents (1,D))."""
     flags = (WHITE_BKGD if white_bkgd else 0) | SIGMA_RELU
-    return _RenderBox.apply(handle, PREC[precision] if isinstance(precision, str) else precision, n_samples, flags,
-                            ("box", half_diag, aabb_half), px, py, K, c2w, z_steps, jitter, shape_latent, texture_latent, *weights)
+    return _render_apply(handle, PREC[precision] if isinstance(precision, str) else precision, n_samples, flags,
+                         ("box", half_diag, aabb_half), px, py, K, c2w, z_steps, jitter, shape_latent, texture_latent, weights)
 
 
 def render_shell(handle, precision, n_samples, obj_diag, shapenet_swap, px, py, K, c2w, z_vals, shape_latent, texture_latent, weights):
     """The utils.py stack (utils.render_rays_v2, utils.py:435-502) for one object: shared sample vector z_vals (S),
     xyz / obj_diag, optional shapenet axis swap, utils.volume_rendering2.  -> rgb (N,3), depth (N,), acc (N,)."""
-    rgb, dep, acc, _ = _RenderBox.apply(handle, PREC[precision] if isinstance(precision, str) else precision, n_samples, SIGMA_RELU,
-                                        ("shell", obj_diag, shapenet_swap), px, py, K, c2w, z_vals, None, shape_latent,
-                                        texture_latent, *weights)
+    rgb, dep, acc, _ = _render_apply(handle, PREC[precision] if isinstance(precision, str) else precision, n_samples, SIGMA_RELU,
+                                     ("shell", obj_diag, shapenet_swap), px, py, K, c2w, z_vals, None, shape_latent,
+                                     texture_latent, weights)
     return rgb, dep, acc
 
 

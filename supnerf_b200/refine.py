@@ -25,7 +25,7 @@ import torch
 
 from . import _lib, losses, models, ops
 from . import utils as U
-from ._lib import check, f32c, ptr, require_cuda, stream_ptr
+from ._lib import check, f32c, on_device, ptr, require_cuda, stream_ptr
 
 
 class _PoseAndSamples(torch.autograd.Function):
@@ -39,7 +39,7 @@ class _PoseAndSamples(torch.autograd.Function):
         dev = rot_vec.device
         cam = torch.empty(3, 4, device=dev, dtype=torch.float32)
         z = torch.empty(int(n_samples), device=dev, dtype=torch.float32)
-        with torch.cuda.device(dev):
+        with on_device(dev):
             check(lib.snb_refine_pose_fwd(ptr(rot_vec), ptr(trans_vec), int(bool(opt_cam_pose)), float(obj_diag), int(n_samples), ptr(jitter),
                                           ptr(cam), ptr(z), stream_ptr()), "snb_refine_pose_fwd")
         ctx.save_for_backward(rot_vec, trans_vec)
@@ -53,7 +53,7 @@ class _PoseAndSamples(torch.autograd.Function):
         rot_vec, trans_vec = ctx.saved_tensors
         g_cam = f32c(g_cam)
         g_rot, g_trans = torch.empty_like(rot_vec), torch.empty_like(trans_vec)
-        with torch.cuda.device(rot_vec.device):
+        with on_device(rot_vec.device):
             check(lib.snb_refine_pose_bwd(ptr(rot_vec), ptr(trans_vec), ctx.opt_cam_pose, ptr(g_cam), ptr(g_rot), ptr(g_trans), stream_ptr()),
                   "snb_refine_pose_bwd")
         return g_rot, g_trans, None, None, None, None
@@ -88,7 +88,7 @@ class FusedAdamW:
         lib = _lib.load()
         n = len(self.params)
         arr = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])  # noqa: E731
-        with torch.cuda.device(self.params[0].device):
+        with on_device(self.params[0].device):
             check(lib.snb_adamw_step(n, arr(self.params), arr([p.grad for p in self.params]), arr(self.m), arr(self.v), self._sizes, self._lrs,
                                      self.betas[0], self.betas[1], self.eps, self.weight_decay, ptr(self.step_t), stream_ptr()), "snb_adamw_step")
 

@@ -4,7 +4,7 @@ as one CUDA kernel plus the package's compositing kernel.  Forward only, like th
 import torch
 
 from . import _lib, ops
-from ._lib import check, f32c, ptr, require_cuda, stream_ptr
+from ._lib import check, f32c, on_device, ptr, require_cuda, stream_ptr
 
 
 def merge_objects(z_vals, sigmas, rgbs, return_args=False):
@@ -20,7 +20,7 @@ def merge_objects(z_vals, sigmas, rgbs, return_args=False):
         raise ValueError("merge_objects: expected z_vals (R,K), sigmas (R,K), rgbs (R,K,3)")
     z_sort, s_sort, c_sort = torch.empty_like(z), torch.empty_like(s), torch.empty_like(c)
     args = torch.empty(r, k, dtype=torch.int64, device=z.device) if return_args else None
-    with torch.cuda.device(z.device):
+    with on_device(z.device):
         check(lib.snb_merge_sort_samples(ptr(z), ptr(s), ptr(c), r, k, ptr(z_sort), ptr(s_sort), ptr(c_sort), ptr(args), stream_ptr()),
               "snb_merge_sort_samples")
     return (z_sort, s_sort, c_sort, args) if return_args else (z_sort, s_sort, c_sort)
