@@ -373,21 +373,25 @@ def run_ours(args):
     if rank == 0:
         try:
             import numpy as _np
-            o = make_objects(300, 1, 32)[0]
-            c2o = o["cam_pose"]
-            r_obj = c2o[:, :3].t().contiguous().double()
-            t_obj = -(r_obj.float() @ c2o[:, 3:]).reshape(3)
-            ang = torch.acos(((torch.trace(r_obj) - 1) / 2).clamp(-1, 1))
-            w = torch.stack([r_obj[2, 1] - r_obj[1, 2], r_obj[0, 2] - r_obj[2, 0], r_obj[1, 0] - r_obj[0, 1]])
-            rot_vec = (w / (2 * torch.sin(ang).clamp_min(1e-12)) * ang).float()
             sup = snb.SUPNeRF(3, 1, 3, 3, 256)
             sup.load_state_dict(sd)
             sup = sup.to(dev)
             sup.precision = args.precision
             sup.requires_grad_(False)
-            ref = snb.refine.ObjectRefiner(sup, dev, o["img"].to(dev), o["mask_occ"].to(dev), o["K"], o["roi"],
-                                           _np.linalg.norm(o["wlh"]).astype(_np.float32), o["shapecode"], o["texturecode"], rot_vec, t_obj,
-                                           n_samples=N_SAMPLES, im_sz=32, max_iters=60).capture()
+
+            def refiner_for(k, max_iters):
+                o = make_objects(300 + k, 1, 32)[0]
+                c2o = o["cam_pose"]
+                r_obj = c2o[:, :3].t().contiguous().double()
+                t_obj = -(r_obj.float() @ c2o[:, 3:]).reshape(3)
+                ang = torch.acos(((torch.trace(r_obj) - 1) / 2).clamp(-1, 1))
+                w = torch.stack([r_obj[2, 1] - r_obj[1, 2], r_obj[0, 2] - r_obj[2, 0], r_obj[1, 0] - r_obj[0, 1]])
+                rot_vec = (w / (2 * torch.sin(ang).clamp_min(1e-12)) * ang).float()
+                return snb.refine.ObjectRefiner(sup, dev, o["img"].to(dev), o["mask_occ"].to(dev), o["K"], o["roi"],
+                                                _np.linalg.norm(o["wlh"]).astype(_np.float32), o["shapecode"], o["texturecode"], rot_vec,
+                                                t_obj, n_samples=N_SAMPLES, im_sz=32, max_iters=max_iters).capture()
+
+            ref = refiner_for(0, 60)
             ref.run(5)
             torch.cuda.synchronize()
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -399,6 +403,17 @@ def run_ours(args):
                          "config": "configs[2] shape: one object, 32x32 rays x %d samples, AdamW on pose + shape/texture codes, "
                                    "supnerf_b200.refine.ObjectRefiner (one CUDA graph per iteration)" % N_SAMPLES,
                          "loss_after": round(float(last[0]), 5)}
+            # configs[2] gives every GPU 4 objects: refined side by side (refine.run_objects, one stream per object)
+            refs = [refiner_for(k, 60) for k in range(4)]
+            snb.refine.run_objects(refs, 5, 4)
+            torch.cuda.synchronize()
+            a0.record()
+            snb.refine.run_objects(refs, 50, 4)
+            a1.record()
+            torch.cuda.synchronize()
+            refine_it["four_objects_side_by_side"] = {
+                "ms_per_refine_iteration": round(a0.elapsed_time(a1) / (4 * 50), 4), "objects": 4, "iterations": 50, "cuda_streams": 4,
+                "note": "per object-iteration: elapsed / (4 objects x 50 iterations) (configs[2]: 4 objects per GPU), refine.run_objects"}
         except Exception as exc:
             refine_it = {"error": str(exc)}
     if world > 1:

@@ -223,3 +223,25 @@ class ObjectRefiner:
             else:
                 self.step()
         return self.loss
+
+
+def run_objects(refiners, iters, n_streams=4):
+    """Refine several INDEPENDENT objects side by side (object-parallel: own pose, codes, rays, loss and AdamW state):
+    iteration k of every object is issued round-robin over `n_streams` CUDA streams, so one object's small kernels (pose map,
+    sampler, compositing, loss, AdamW) run under another object's decoder kernel instead of leaving the GPU idle between two
+    decoder launches.  No host synchronisation; the caller's current stream waits for all of them at the end.
+    Returns the objects' last [loss, loss_rgb, loss_occ] tensors."""
+    if not refiners:
+        return []
+    dev = refiners[0].device
+    main = torch.cuda.current_stream(dev)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(int(n_streams), len(refiners))))]
+    for s in streams:
+        s.wait_stream(main)
+    for _ in range(int(iters)):
+        for i, r in enumerate(refiners):
+            with torch.cuda.stream(streams[i % len(streams)]):
+                r.run(1)
+    for s in streams:
+        main.wait_stream(s)
+    return [r.loss for r in refiners]

@@ -601,6 +601,39 @@ def test_object_refiner_matches_reference_api_loop_and_graph_replay():
         assert rel_err(o[0].shapecode, outs[0][0].shapecode) < 2e-2 and rel_err(o[1], outs[0][1]) < 1e-4
 
 
+def test_run_objects_side_by_side_equals_one_after_the_other():
+    """refine.run_objects (independent objects' graph replays issued round-robin over several CUDA streams) leaves every object
+    in the state its own sequential loop would: same kernels, same order per object, no shared mutable state."""
+    S = snb()
+    import tools.refine_bench as rb
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=52)
+    m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
+    m.requires_grad_(False)
+    iters = 5
+
+    def make(seed):
+        obj = oracle.synthetic_object(seed, im_sz=32)
+        shp0, tex0 = oracle.synthetic_latents(seed, 1)
+        c2o = obj["cam_pose"]
+        R_obj = c2o[:, :3].t().contiguous()
+        t_obj = -(R_obj @ c2o[:, 3:]).reshape(3)
+        torch.manual_seed(seed)
+        return S.refine.ObjectRefiner(m, DEV, obj["img"], obj["mask_occ"], obj["K"], obj["roi"], np.linalg.norm(obj["wlh"]).astype(np.float32),
+                                      shp0, tex0, rb.matrix_to_axis_angle(R_obj), t_obj, n_samples=64, im_sz=32, max_iters=iters).capture()
+
+    seq = [make(60 + k) for k in range(3)]
+    for r in seq:
+        r.run(iters)
+    par = [make(60 + k) for k in range(3)]
+    S.refine.run_objects(par, iters, n_streams=3)
+    torch.cuda.synchronize()
+    for a, b in zip(seq, par):
+        # (the decoder's latent-gradient column sums are accumulated with atomics: equal to rounding, not bit for bit)
+        assert rel_err(b.loss, a.loss) < 1e-4
+        assert rel_err(b.shapecode, a.shapecode) < 2e-2 and rel_err(b.texturecode, a.texturecode) < 2e-2
+        assert rel_err(b.rot_vec, a.rot_vec) < 1e-3 and rel_err(b.trans_vec, a.trans_vec) < 1e-3
+
+
 def test_device_side_shell_samples_match_host_built_vector():
     """refine.shell_samples_on_device vs the reference's host arithmetic (utils.py:154-167, :468-469)."""
     S = snb()

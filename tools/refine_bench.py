@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--im", type=int, default=32)
     ap.add_argument("--samples", type=int, default=64)
     ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--streams", type=int, default=1, help="with --graph: refine this rank's objects side by side over this many CUDA streams (refine.run_objects)")
     ap.add_argument("--graph", action="store_true", help="supnerf_b200.refine.ObjectRefiner: one CUDA graph per iteration, no host sync")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -108,7 +109,10 @@ def main():
         torch.distributed.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    last = [refine(o, a.iters) for o in objs]
+    if a.graph and a.streams > 1:
+        last = [l[0] for l in snb.refine.run_objects(refiners, a.iters, a.streams)]
+    else:
+        last = [refine(o, a.iters) for o in objs]
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -123,7 +127,7 @@ def main():
                           "n_gpus": world, "ms_total": round(ms, 2), "ms_per_refine_iteration": round(ms / max(n_local * a.iters, 1), 4),
                           "objects_per_gpu": n_local, "rays_per_s": round(a.objects * a.iters * a.im * a.im / (ms / 1e3), 1),
                           "loss_first_object": {"before": round(l0, 5), "after": round(float(last[0].detach()), 5)}, "precision": a.precision,
-                          "mode": "one CUDA graph per iteration (refine.ObjectRefiner)" if a.graph else "eager reference-API loop (render_rays_v2 + torch AdamW)"}))
+                          "mode": ("one CUDA graph per iteration (refine.ObjectRefiner)" + (", objects side by side over %d streams (refine.run_objects)" % a.streams if a.streams > 1 else "")) if a.graph else "eager reference-API loop (render_rays_v2 + torch AdamW)"}))
     if world > 1:
         torch.distributed.destroy_process_group()
 
