@@ -37,13 +37,16 @@ class _RefineLoss(torch.autograd.Function):
         ctx.save_for_backward(rgb, acc, tgt, occ, scratch)
         ctx.coef = float(coef)
         loss, parts = out[0], out[1:]
-        ctx.mark_non_differentiable(parts)
-        return loss, parts
+        ctx.mark_non_differentiable(parts, out)
+        ctx.set_materialize_grads(False)
+        return loss, parts, out
 
     @staticmethod
-    def backward(ctx, g_loss, _g_parts):
+    def backward(ctx, g_loss, _g_parts, _g_vec):
         lib = _lib.load()
         rgb, acc, tgt, occ, scratch = ctx.saved_tensors
+        if g_loss is None:
+            return None, None, None, None, None, None
         n = acc.numel()
         g_rgb = torch.empty_like(rgb)
         g_acc = torch.empty_like(acc)
@@ -61,5 +64,12 @@ def refine_loss(rgb_rays, acc_trans_rays, rgb_tgt, occ_pixels, loss_occ_coef=0.1
     n = acc_trans_rays.numel()
     if tuple(rgb_rays.shape) != (n, 3) or tuple(rgb_tgt.shape) != (n, 3) or occ_pixels.numel() != n:
         raise ValueError("refine_loss: expected rgb (N,3), acc (N,), tgt (N,3), occ (N,1)")
-    loss, parts = _RefineLoss.apply(rgb_rays, acc_trans_rays.reshape(-1), rgb_tgt, occ_pixels.reshape(-1), loss_occ_coef, den)
+    loss, parts, _ = _RefineLoss.apply(rgb_rays, acc_trans_rays.reshape(-1), rgb_tgt, occ_pixels.reshape(-1), loss_occ_coef, den)
     return loss, parts[0], parts[1]
+
+
+def refine_loss_vec(rgb_rays, acc_trans_rays, rgb_tgt, occ_pixels, loss_occ_coef=0.1, den=None):
+    """-> (loss, vec): `loss` as refine_loss; `vec` (3,) = [loss, loss_rgb, loss_occ] as the kernel wrote them (one tensor, no
+    stacking kernels: what a graph-captured loop keeps to read the losses after a replay)."""
+    loss, _, vec = _RefineLoss.apply(rgb_rays, acc_trans_rays.reshape(-1), rgb_tgt, occ_pixels.reshape(-1), loss_occ_coef, den)
+    return loss, vec

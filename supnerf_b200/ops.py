@@ -442,6 +442,7 @@ class _RenderBox(torch.autograd.Function):
         ctx.meta = (handle, desc, sizes[1], handle._frozen if not weights else None)
         hitb = hit.view(torch.bool)   # 0 / 1 bytes: a zero-copy view
         ctx.mark_non_differentiable(hitb)
+        ctx.set_materialize_grads(False)   # unused outputs (depth, the hit mask) arrive as None, not as freshly filled zeros
         return o_rgb, o_dep, o_acc, hitb
 
     @staticmethod
@@ -451,7 +452,7 @@ class _RenderBox(torch.autograd.Function):
         handle, desc, scratch_bytes, frozen = ctx.meta
         n = px.numel()
         dev = px.device
-        g_rgb = f32c(g_rgb) if g_rgb is not None else torch.zeros(n, 3, device=dev)
+        g_rgb = f32c(g_rgb) if g_rgb is not None else _zeros_like_cached(dev, 3 * n)
         g_dep = f32c(g_dep) if g_dep is not None else _zeros_like_cached(dev, n)   # an unused output (e.g. depth): shared zeros
         g_acc = f32c(g_acc) if g_acc is not None else _zeros_like_cached(dev, n)
         need = ctx.needs_input_grad

@@ -45,12 +45,15 @@ class _PoseAndSamples(torch.autograd.Function):
         ctx.save_for_backward(rot_vec, trans_vec)
         ctx.opt_cam_pose = int(bool(opt_cam_pose))
         ctx.mark_non_differentiable(z)
+        ctx.set_materialize_grads(False)
         return cam, z
 
     @staticmethod
     def backward(ctx, g_cam, _g_z):
         lib = _lib.load()
         rot_vec, trans_vec = ctx.saved_tensors
+        if g_cam is None:
+            return None, None, None, None, None, None
         g_cam = f32c(g_cam)
         g_rot, g_trans = torch.empty_like(rot_vec), torch.empty_like(trans_vec)
         with on_device(rot_vec.device):
@@ -74,10 +77,15 @@ class FusedAdamW:
         self._sizes = (ctypes.c_int32 * n)(*[p.numel() for p in self.params])
         self._lrs = (ctypes.c_float * n)(*self.lrs)
 
-    def zero_grad(self):
+    def zero_grad(self, set_to_none=True):
+        """set_to_none (default): the next backward ASSIGNS the gradients instead of accumulating into zero-filled ones: no fill
+        and no add kernel per parameter (inside a CUDA graph the assigned tensors keep their addresses across replays)."""
         for p in self.params:
             if p.grad is not None:
-                p.grad.zero_()
+                if set_to_none:
+                    p.grad = None
+                else:
+                    p.grad.zero_()
 
     def reset(self):
         for t in self.m + self.v:
@@ -179,10 +187,10 @@ class ObjectRefiner:
         prec = self.model.precision or models.get_default_precision()
         rgb, dep, acc = ops.render_shell(self.model._handle(self.device), prec, self.n_samples, float(self.obj_diag), self.swap,
                                          self.px, self.py, self.K, cam, z, self.shapecode, self.texturecode, self.model._weights())
-        loss, l_rgb, l_occ = losses.refine_loss(rgb, acc, self.rgb_tgt, self.occ, self.coef)
+        loss, vec = losses.refine_loss_vec(rgb, acc, self.rgb_tgt, self.occ, self.coef)
         loss.backward()
         self.opt.step()
-        self.loss.copy_(torch.stack([loss.detach(), l_rgb, l_occ]))
+        self.loss = vec   # [loss, loss_rgb, loss_occ] as the loss kernel wrote them (graph mode: a static tensor of the graph's pool)
         self.it += 1
         return self.loss
 
