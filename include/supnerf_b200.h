@@ -136,6 +136,10 @@ int snb_tc_set_debug(float* acts);
  * kernels writes clock64 stamps [pair][step][slot][4] = {operand-ready seen by the MMA warp, MMAs issued, accumulator-ready
  * seen by the epilogue, epilogue published}.  tools/trace_pipeline.py prints the timeline.  Pass NULL to switch it off. */
 int snb_tc_set_trace(long long* stamps);
+/* Test / tuning hook: which two-tile decoder kernels frozen-weight calls use.  1: the cta_group::2 kernels (one M = 256 MMA over
+ * the CTA pair, half of every weight stage per SM) wherever they apply (every object owns a multiple of 256 rows); 0: always the
+ * cta_group::1 kernels; -1 (initial state): the SNB_TC_CG2 environment variable, default 1.  Both give the same arithmetic. */
+int snb_tc_set_cg2(int32_t mode);
 /* Measurement hook (bench.py roofline): while enabled, every bf16 decoder call records a CUDA-event pair on its
  * launch stream around the tcgen05 kernel alone.  snb_kernel_timing_read (after a synchronize) copies up to max_n
  * durations in ms to HOST memory and returns how many; which = 0 forward, 1 backward.  Enabling clears old events. */

@@ -47,6 +47,7 @@ SIGNATURES = {
     "snb_packed_bytes": (c_sz, [ctypes.c_void_p]),
     "snb_tc_set_debug": (c_i32, [c_f]),
     "snb_tc_set_trace": (c_i32, [c_f]),
+    "snb_tc_set_cg2": (c_i32, [c_i32]),
     "snb_kernel_timing_enable": (c_i32, [c_i32]),
     "snb_kernel_timing_read": (c_i32, [c_i32, ctypes.POINTER(c_flt), c_i32]),
     "snb_pack_weights": (c_i32, [ctypes.c_void_p, c_f, c_f]),

@@ -35,6 +35,7 @@ size_t tc_packed_bytes(const snb_handle_s* h);
 int tc_pack_weights(snb_handle_s* h, void* packed, cudaStream_t st);
 void tc_set_debug(float* acts);
 void tc2_set_trace(long long* buf);
+void tc2_set_cg2(int mode);
 void tc_timing_enable(int on);
 int tc_timing_read(int which, float* ms, int max_n);
 size_t tc_workspace_bytes(const snb_handle_s* h, int64_t M, int64_t B);
@@ -140,6 +141,7 @@ extern "C" int snb_set_weights(snb_handle h, const float* const* tensors, int32_
 
 extern "C" int snb_tc_set_debug(float* acts) { tc_set_debug(acts); return 0; }
 extern "C" int snb_tc_set_trace(long long* stamps) { tc2_set_trace(stamps); return 0; }
+extern "C" int snb_tc_set_cg2(int32_t mode) { tc2_set_cg2(mode); return 0; }
 extern "C" int snb_kernel_timing_enable(int32_t on) { tc_timing_enable(on); return 0; }
 extern "C" int snb_kernel_timing_read(int32_t which, float* ms_host, int32_t max_n) { return tc_timing_read(which, ms_host, max_n); }
 

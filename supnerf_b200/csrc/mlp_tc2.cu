@@ -1193,9 +1193,12 @@ static int tc2_grid(K kernel, int64_t M) {
 
 // cta_group::2 kernels: frozen weights only (no operand saves), and every 256-row super tile inside one object (the pair's two
 // tiles share the B operand, hence the per-object bias stage).  SNB_TC_CG2=0 selects the cta_group::1 kernels.
+static int g_cg2_mode = -1;   // snb_tc_set_cg2
+void tc2_set_cg2(int mode) { g_cg2_mode = mode; }
 static bool tc2_use_cg2(const tc2::Params& p) {
   static const int env = [] { const char* e = getenv("SNB_TC_CG2"); return e ? atoi(e) : 1; }();
-  return env != 0 && p.save == nullptr && p.dbg == nullptr && (p.B == 1 || p.rows_per_obj % 256 == 0);
+  const int want = g_cg2_mode < 0 ? env : g_cg2_mode;
+  return want != 0 && p.save == nullptr && p.dbg == nullptr && (p.B == 1 || p.rows_per_obj % 256 == 0);
 }
 
 // opt-in shared-memory size of every kernel variant, once per device

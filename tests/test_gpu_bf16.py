@@ -339,3 +339,34 @@ def test_render_full_img_bf16_ragged_rows():
         assert img.shape == (37, 37, 3) and dep.shape == (37, 37)
         imgs[prec] = (img, dep)
     assert rel_err(imgs["bf16"][0], imgs["fp32"][0]) < TOL and rel_err(imgs["bf16"][1], imgs["fp32"][1]) < TOL
+
+
+@pytest.mark.parametrize("B,n,S_", [(1, 150, 64), (4, 64, 16), (1, 16, 8), (3, 96, 8)])
+def test_cta_group2_kernels_equal_cta_group1_kernels(B, n, S_):
+    """The cta_group::2 decoder kernels (one M = 256 MMA over the CTA pair, half weight stages per SM; the default wherever every
+    object owns a multiple of 256 rows) against the cta_group::1 kernels on the same inputs: same MMAs in the same K order, so
+    sigma / rgb and the per-sample gradients must agree to the last bits; the latent gradients are sums of atomics (order differs).
+    Covers an odd number of tile pairs (75), several objects per launch (256- and 768-row objects: super tiles never straddle
+    two objects) and a launch of a single tile (half of one CTA pair's super tile)."""
+    S = snb()
+    lib = S._lib.load()
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=11)
+    xyz, vd, shp, tex, up_s, up_c = _case(B, n, S_, 40 + B)
+    m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
+    m.precision = "bf16"
+    m.requires_grad_(False)
+    outs = []
+    try:
+        for mode in (0, 1):
+            lib.snb_tc_set_cg2(mode)
+            ins = [t.to(DEV).requires_grad_() for t in (xyz, vd, shp, tex)]
+            sig, rgbs = m(*ins)
+            ((sig * up_s.to(DEV)).sum() + (rgbs * up_c.to(DEV)).sum()).backward()
+            torch.cuda.synchronize()
+            outs.append((sig.detach(), rgbs.detach(), [t.grad for t in ins]))
+    finally:
+        lib.snb_tc_set_cg2(-1)
+    (s0, c0, g0), (s1, c1, g1) = outs
+    assert torch.equal(s0, s1) and torch.equal(c0, c1)
+    assert rel_err(g1[0], g0[0]) < 1e-6 and rel_err(g1[1], g0[1]) < 1e-6      # d xyz, d viewdir: per sample, no reduction
+    assert rel_err(g1[2], g0[2]) < 1e-5 and rel_err(g1[3], g0[3]) < 1e-5      # latent gradients: atomically accumulated sums
