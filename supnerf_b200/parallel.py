@@ -40,6 +40,24 @@ def ray_shard(n_rays, n_samples, rank, world):
     return start, end
 
 
+def ray_shard_indices(n_rays, n_samples, rank, world, device=None):
+    """Ray ids of `rank` in the INTERLEAVED layout: the rays are cut into tiles of 128 rays (128 x S sample rows = S whole
+    128-row decoder tiles for any S) and rank r owns tiles r, r+G, r+2G, ...
+    With miss-ray compaction a rank's decoder work is proportional to the rays of its shard that HIT the object box, and a
+    contiguous split of a row-major crop gives the ranks holding the middle rows about twice the hits of the outer ones
+    (512x512 rays on 4 GPUs: 12.1 ms per step against 7.8 ms for a balanced split); interleaved tiles sample the crop uniformly.
+    -> sorted int64 tensor of ray ids (the last tile may be partial)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    tile = TILE_ROWS   # 128 rays x S samples = S whole decoder tiles
+    n_tiles = -(-int(n_rays) // tile)
+    if rank >= n_tiles:
+        return torch.empty(0, dtype=torch.int64, device=device)
+    mine = torch.arange(rank, n_tiles, world, dtype=torch.int64, device=device)
+    ids = (mine[:, None] * tile + torch.arange(tile, dtype=torch.int64, device=device)[None, :]).reshape(-1)
+    return ids[ids < n_rays]
+
+
 def refine_loss_sharded(rgb_rays, acc_rays, rgb_tgt, occ_pixels, occ_all, loss_occ_coef=0.1):
     """This rank's PARTIAL of the refine loss (optimizer_nuscenes.py:729-736): local numerators over the GLOBAL
     denominator sum|occ_all| + 1e-9 (a function of the input mask only, so every rank evaluates it locally), so that the
@@ -90,10 +108,12 @@ def allreduce_weight_grads(model, group=None, average=True):
 
 
 def render_rays_sharded(renderer, model, device, img, mask_occ, cam_pose, obj_sz, K, roi, shapecode, texturecode, im_sz=64,
-                        rank=None, world=None):
-    """Ray-sharded NeRFRenderer.render_rays (renderer.py:117-167 semantics, `n_rays=None`): renders only this rank's
-    contiguous ray tile.  The (N,S) jitter is drawn in full on every rank (same generator state => same numbers as the
-    single-GPU call) and sliced, so the union of the shards is bit-identical to the unsharded render.
+                        rank=None, world=None, layout="contiguous"):
+    """Ray-sharded NeRFRenderer.render_rays (renderer.py:117-167 semantics, `n_rays=None`): renders only this rank's rays --
+    one contiguous ray tile (layout="contiguous", ray_shard) or every G-th 128-ray tile (layout="interleaved",
+    ray_shard_indices: balanced decoder work under miss-ray compaction).  The (N,S) jitter is drawn in full on every rank
+    (same generator state => same numbers as the single-GPU call) and sliced, so the union of the shards is bit-identical to
+    the unsharded render.
     -> rgb, depth, acc, rgb_tgt, occ_pixels of the shard, plus occ_all (N,1) for the global loss denominator."""
     if rank is None:
         rank = dist.get_rank() if dist.is_initialized() else 0
@@ -103,25 +123,41 @@ def render_rays_sharded(renderer, model, device, img, mask_occ, cam_pose, obj_sz
     px, py = U._pixel_grid_on(device, roi, [im_sz, im_sz])
     img, mask_occ = U._resize_targets(img, mask_occ, im_sz)
     n = px.numel()
-    a, b = ray_shard(n, renderer.n_samples, rank, world)
-    rgb_tgt = img.reshape(-1, 3)[a:b].to(device, non_blocking=True)
     occ_all = mask_occ.reshape(-1, 1).to(device, non_blocking=True)
-    jitter = torch.rand_like(torch.empty(n, renderer.n_samples, device=device))[a:b]
-    rgb, dep, acc = renderer._render_fused(model, device, px[a:b], py[a:b], K, cam_pose, obj_sz, shapecode, texturecode,
-                                           jitter=jitter.contiguous())
-    return rgb, dep, acc, rgb_tgt, occ_all[a:b], occ_all
+    jitter = torch.rand_like(torch.empty(n, renderer.n_samples, device=device))
+    if layout == "interleaved":
+        sel = ray_shard_indices(n, renderer.n_samples, rank, world, device=device)
+    elif layout == "contiguous":
+        a, b = ray_shard(n, renderer.n_samples, rank, world)
+        sel = slice(a, b)
+    else:
+        raise ValueError("layout must be 'contiguous' or 'interleaved'")
+    rgb_tgt = img.reshape(-1, 3).to(device, non_blocking=True)[sel]
+    rgb, dep, acc = renderer._render_fused(model, device, px[sel].contiguous(), py[sel].contiguous(), K, cam_pose, obj_sz, shapecode,
+                                           texturecode, jitter=jitter[sel].contiguous())
+    return rgb, dep, acc, rgb_tgt, occ_all[sel], occ_all
 
 
-def gather_rays(t, n_rays, n_samples, group=None):
+def gather_rays(t, n_rays, n_samples, group=None, layout="contiguous"):
     """Optional: assemble the full (N, ...) image from the per-rank shards (an all_gather of 20 B/ray; only when the caller
-    wants the whole render on every rank)."""
+    wants the whole render on every rank).  `layout` as in render_rays_sharded."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return t
     world = dist.get_world_size(group)
-    sizes = [ray_shard(n_rays, n_samples, r, world) for r in range(world)]
-    width = max(b - a for a, b in sizes)
+    if layout == "interleaved":
+        ids = [ray_shard_indices(n_rays, n_samples, r, world, device=t.device) for r in range(world)]
+        counts = [int(i.numel()) for i in ids]
+    else:
+        sizes = [ray_shard(n_rays, n_samples, r, world) for r in range(world)]
+        counts = [b - a for a, b in sizes]
+    width = max(counts)
     pad = torch.zeros((width,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
     pad[:t.shape[0]] = t
     outs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(outs, pad, group=group)
-    return torch.cat([o[:b - a] for o, (a, b) in zip(outs, sizes)], 0)
+    if layout == "interleaved":
+        full = torch.empty((n_rays,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        for o, i, c in zip(outs, ids, counts):
+            full[i] = o[:c]
+        return full
+    return torch.cat([o[:c] for o, c in zip(outs, counts)], 0)

@@ -34,7 +34,7 @@ def _setup(dev, prec):
     return snb, obj, m, shp, tex
 
 
-def _worker(rank, world, port, prec, q):
+def _worker(rank, world, port, prec, q, layout="contiguous"):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -48,24 +48,24 @@ def _worker(rank, world, port, prec, q):
         torch.manual_seed(7)
         torch.cuda.manual_seed(7)   # same device generator state on every rank => same full jitter
         rgb, dep, acc, tgt, occ, occ_all = snb.parallel.render_rays_sharded(R, m, dev, obj["img"], obj["mask_occ"], cam, obj["wlh"],
-                                                                           obj["K"], obj["roi"], shp, tex, im_sz=IM)
+                                                                           obj["K"], obj["roi"], shp, tex, im_sz=IM, layout=layout)
         part = snb.parallel.refine_loss_sharded(rgb, acc, tgt, occ, occ_all)
         part.backward()
         loss = snb.parallel.allreduce_grads([cam, shp, tex], part)
-        full = snb.parallel.gather_rays(rgb.detach(), IM * IM, S)
+        full = snb.parallel.gather_rays(rgb.detach(), IM * IM, S, layout=layout)
         q.put((rank, float(loss), cam.grad.cpu(), shp.grad.cpu(), tex.grad.cpu(), full.cpu()))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("prec,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
-def test_ray_sharded_two_gpus_matches_one(prec, tol):
+@pytest.mark.parametrize("prec,tol,layout", [("fp32", 1e-5, "contiguous"), ("bf16", 2e-2, "contiguous"), ("bf16", 2e-2, "interleaved")])
+def test_ray_sharded_two_gpus_matches_one(prec, tol, layout):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, prec, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, prec, q, layout)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])

@@ -30,6 +30,22 @@ def test_ray_shards_tile_aligned_and_cover():
         parallel.ray_shard(10, 64, 2, 2)
 
 
+def test_interleaved_ray_shards_partition_and_balance():
+    """parallel.ray_shard_indices: every ray in exactly one shard, whole 128-ray tiles (=> whole decoder tiles for any S), tile t
+    on rank t % G, shard sizes within one tile of each other."""
+    for n in (262144, 4096, 1000, 130, 6, 0):
+        for world in (1, 2, 3, 4, 8):
+            ids = [parallel.ray_shard_indices(n, 64, r, world) for r in range(world)]
+            assert sorted(torch.cat(ids).tolist()) == list(range(n))
+            for r, i in enumerate(ids):
+                assert torch.equal(i, i.sort().values)
+                assert torch.all((i // 128) % world == r)
+            sizes = [int(i.numel()) for i in ids]
+            assert max(sizes) - min(sizes) <= 128
+    with pytest.raises(ValueError):
+        parallel.ray_shard_indices(10, 64, 2, 2)
+
+
 def test_object_shards_partition():
     for n in (0, 1, 16, 32, 33):
         for world in (1, 2, 8):
@@ -74,6 +90,11 @@ def _worker(rank, world, port, q):
         part.backward()
         loss = parallel.allreduce_grads([cam, shp, tex], part)
         full_rgb = parallel.gather_rays(rgb.detach(), n, S)
+        # interleaved layout: scatter this rank's tiles of a known per-ray value, gather, expect the identity
+        mine = parallel.ray_shard_indices(n, S, rank, world)
+        marks = torch.stack([mine.double(), mine.double() * 2 + 1], -1)
+        back = parallel.gather_rays(marks, n, S, layout="interleaved")
+        assert torch.equal(back[:, 0], torch.arange(n).double()) and torch.equal(back[:, 1], torch.arange(n).double() * 2 + 1)
         q.put((rank, float(loss), cam.grad.clone(), shp.grad.clone(), tex.grad.clone(), full_rgb))
     finally:
         dist.destroy_process_group()

@@ -19,6 +19,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--im", type=int, default=512)
 ap.add_argument("--samples", type=int, default=128)
+ap.add_argument("--layout", default="interleaved", choices=["contiguous", "interleaved"],
+                help="ray shards: one contiguous tile per rank, or every G-th 128-ray tile (balanced under miss-ray compaction)")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -42,7 +44,7 @@ img, mask, K = obj["img"].to(dev), obj["mask_occ"].to(dev), obj["K"].to(dev)
 def step():
     cam.grad = shp.grad = tex.grad = None
     rgb, dep, acc, tgt, occ, occ_all = snb.parallel.render_rays_sharded(R, m, dev, img, mask, cam, obj["wlh"], K, obj["roi"], shp, tex,
-                                                                       im_sz=a.im, rank=rank, world=world)
+                                                                       im_sz=a.im, rank=rank, world=world, layout=a.layout)
     part = snb.parallel.refine_loss_sharded(rgb, acc, tgt, occ, occ_all)
     part.backward()
     return snb.parallel.allreduce_grads([cam, shp, tex], part)
@@ -66,7 +68,7 @@ if world > 1:
     ms = float(t.item())
 if rank == 0:
     n = a.im * a.im
-    print(json.dumps({"config": "C4: %dx%d rays x %d samples, ray-sharded x%d, one all-reduce of 525 floats per step" % (a.im, a.im, a.samples, world),
+    print(json.dumps({"config": "C4: %dx%d rays x %d samples, ray-sharded x%d (%s tiles), one all-reduce of 525 floats per step" % (a.im, a.im, a.samples, world, a.layout),
                       "n_gpus": world, "ms_per_step": round(ms / a.steps, 3), "rays_per_s": round(n * a.steps / (ms / 1e3), 1),
                       "scaling": "strong", "loss": float(loss)}))
 if world > 1:
