@@ -153,11 +153,23 @@ static F32Layout make_layout(const snb_handle_s* h, int64_t M, int64_t B, float*
   return L;
 }
 
+struct AutoRFLayout;
+static size_t autorf_workspace_floats(const snb_handle_s* h, int64_t M, int64_t B);
+static size_t autorf_bwd_scratch_floats(const snb_handle_s* h, int64_t M, int64_t B);
+static int autorf_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B, const float* shape_latent,
+                          const float* texture_latent, float* sigma, float* rgb, float* ws, cudaStream_t st);
+static int autorf_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B, const float* shape_latent,
+                           const float* texture_latent, const float* sigma, const float* g_sigma, const float* g_rgb, const float* ws,
+                           float* scratch, float* g_xyz, float* g_viewdir, float* g_shape_latent, float* g_texture_latent,
+                           float* const* gw, cudaStream_t st);
+
 size_t f32_workspace_floats(const snb_handle_s* h, int64_t M, int64_t B) {
+  if (h->arch.arch == SNB_ARCH_AUTORF) return autorf_workspace_floats(h, M, B);
   return (size_t)make_layout(h, M, B, nullptr).total + 16;
 }
 
 size_t f32_bwd_scratch_floats(const snb_handle_s* h, int64_t M, int64_t B) {
+  if (h->arch.arch == SNB_ARCH_AUTORF) return autorf_bwd_scratch_floats(h, M, B);
   const int W = h->arch.W;
   const int ldx = (h->d_xyz() + 3) & ~3, ldv = (h->d_dir() + 3) & ~3;
   return (size_t)(2 * al4(M * W) + al4(M * (W / 2)) + al4(M * ldx) + al4(M * ldv) + al4(M) +
@@ -229,6 +241,7 @@ static int zero(float* p, int64_t n, cudaStream_t st) {
 int f32_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                 const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, float* ws,
                 cudaStream_t st) {
+  if (h->arch.arch == SNB_ARCH_AUTORF) return autorf_forward(h, xyz, viewdir, M, B, shape_latent, texture_latent, sigma, rgb, ws, st);
   SNB_REQUIRE(h->arch.arch == SNB_ARCH_CODENERF, "f32_forward: arch %d not handled here", h->arch.arch);
   F32Layout L = make_layout(h, M, B, ws);
   const int W = L.W, D = h->arch.latent_dim;
@@ -262,6 +275,9 @@ int f32_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, 
                  const float* shape_latent, const float* texture_latent, const float* sigma, const float* g_sigma,
                  const float* g_rgb, const float* ws, float* scratch, float* g_xyz, float* g_viewdir,
                  float* g_shape_latent, float* g_texture_latent, float* const* gw, cudaStream_t st) {
+  if (h->arch.arch == SNB_ARCH_AUTORF)
+    return autorf_backward(h, xyz, viewdir, M, B, shape_latent, texture_latent, sigma, g_sigma, g_rgb, ws, scratch, g_xyz, g_viewdir,
+                           g_shape_latent, g_texture_latent, gw, st);
   SNB_REQUIRE(h->arch.arch == SNB_ARCH_CODENERF, "f32_backward: arch %d not handled here", h->arch.arch);
   F32Layout L = make_layout(h, M, B, const_cast<float*>(ws));
   const int W = L.W, D = h->arch.latent_dim, W2 = W / 2;
@@ -351,6 +367,236 @@ int f32_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, 
     TRY(bwd_weight(dZT(j), W, B, W, texture_latent, D, D, GW(h->iTL(j)), D, GB(h->iTL(j)), nullptr, 0, st));
     if (g_texture_latent) TRY(bwd_data(dZT(j), W, B, W, ly[h->iTL(j)].w, D, D, g_texture_latent, D, 1, st));
   }
+  return 0;
+}
+
+
+// =====================================================================================================================
+// AutoRF decoder (model_autorf.py:156-186), fp32.  W = latent_dim = D.  With P = relu(encoding_xyz(PE(x))):
+//   shape:    s_0 = shape_latent (per object);  s_{j+1} = relu(shape_layer_j((s_j + P) / 2)),  j = 0 .. Bs-2
+//             sigma = softplus(sigma.0((s_{Bs-1} + P) / 2))
+//   texture:  t_0 = texture_latent (per object); t_{j+1} = relu(texture_layer_j((t_j + P) / 2)), j = 0 .. Bt-3
+//             t'  = relu(texture_layer_{Bt-2}([ (t_{Bt-2} + s_{Bs-1} + P) / 3, PE(d) ]))
+//             rgb = sigmoid(rgb.0([ (t' + P) / 2, PE(d) ]))
+// Every Linear input (the mixed tensors) is kept for the weight gradients; the `cat` layers are two accumulating GEMMs.
+// Layers (handle order): 0 encoding_xyz | 1..Bs-1 shape_layer_j | iSG sigma.0 | iSG+1..iSG+Bt-2 texture_layer_j (plain) |
+// iSG+Bt-1 texture_layer_{Bt-2} (D x (D + dv)) | iR0 rgb.0 (3 x (D + dv)).
+// =====================================================================================================================
+// out[m][c] = scale * (t0 + t1 [+ t2]);  a term with bcast != 0 is per object: row m / rows_per_obj of a (B, D) tensor
+__global__ void mix_kernel(float* __restrict__ out, const float* __restrict__ t0, int b0, const float* __restrict__ t1, int b1,
+                           const float* __restrict__ t2, int b2, int D, int64_t M, int64_t rpo, float scale) {
+  const int64_t n = M * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / D;
+    const int c = (int)(i - m * D);
+    const int64_t o = m / rpo;
+    float v = t0[(b0 ? o : m) * D + c] + t1[(b1 ? o : m) * D + c];
+    if (t2 != nullptr) v += t2[(b2 ? o : m) * D + c];
+    out[i] = v * scale;   // (a + b) / 2 == (a + b) * 0.5f exactly; / 3 is rounded like the reference's division below
+  }
+}
+// out = (t0 + t1 + t2) / 3 with a true division (model_autorf.py:176)
+__global__ void mix3_div_kernel(float* __restrict__ out, const float* __restrict__ t0, int b0, const float* __restrict__ t1, int b1,
+                                const float* __restrict__ t2, int D, int64_t M, int64_t rpo) {
+  const int64_t n = M * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / D;
+    const int c = (int)(i - m * D);
+    const int64_t o = m / rpo;
+    out[i] = (t0[(b0 ? o : m) * D + c] + t1[(b1 ? o : m) * D + c] + t2[i]) / 3.f;
+  }
+}
+__global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, int64_t n, float scale, int accumulate) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = (accumulate ? y[i] : 0.f) + scale * x[i];
+}
+__global__ void sigmoid_kernel(float* __restrict__ x, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = 1.f / (1.f + expf(-x[i]));
+}
+__global__ void sigmoid_bwd_kernel(const float* __restrict__ y, const float* __restrict__ g, float* __restrict__ g_pre, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    g_pre[i] = g[i] * y[i] * (1.f - y[i]);
+}
+
+struct AutoRFLayout {
+  int D, Bs, Bt, dx, dv, ldx, ldv;
+  int64_t total;
+  float *X0, *V, *P, *Asig, *C, *Tv, *Cr, *RGB;
+  float* S[17];    // S[1..Bs-1]  (S[0] = the shape latent, per object)
+  float* As[17];   // As[0..Bs-2] = (s_j + P) / 2
+  float* T[17];    // T[1..Bt-2]  (T[0] = the texture latent)
+  float* At[17];   // At[0..Bt-3]
+};
+
+static AutoRFLayout autorf_layout(const snb_handle_s* h, int64_t M, float* ws) {
+  AutoRFLayout L;
+  L.D = h->arch.latent_dim; L.Bs = h->arch.shape_blocks; L.Bt = h->arch.texture_blocks;
+  L.dx = h->d_xyz(); L.dv = h->d_dir();
+  L.ldx = (L.dx + 3) & ~3; L.ldv = (L.dv + 3) & ~3;
+  Bump b{ws};
+  L.X0 = b.take(M * L.ldx);
+  L.V = b.take(M * L.ldv);
+  L.P = b.take(M * L.D);
+  for (int j = 1; j <= L.Bs - 1; ++j) L.S[j] = b.take(M * L.D);
+  for (int j = 0; j <= L.Bs - 2; ++j) L.As[j] = b.take(M * L.D);
+  L.Asig = b.take(M * L.D);
+  for (int j = 1; j <= L.Bt - 2; ++j) L.T[j] = b.take(M * L.D);
+  for (int j = 0; j <= L.Bt - 3; ++j) L.At[j] = b.take(M * L.D);
+  L.C = b.take(M * L.D);
+  L.Tv = b.take(M * L.D);
+  L.Cr = b.take(M * L.D);
+  L.RGB = b.take(M * 4);
+  L.total = b.used;
+  return L;
+}
+
+static size_t autorf_workspace_floats(const snb_handle_s* h, int64_t M, int64_t) { return (size_t)autorf_layout(h, M, nullptr).total + 16; }
+static size_t autorf_bwd_scratch_floats(const snb_handle_s* h, int64_t M, int64_t) {
+  const int D = h->arch.latent_dim, ldx = (h->d_xyz() + 3) & ~3, ldv = (h->d_dir() + 3) & ~3;
+  return (size_t)(4 * al4(M * D) + al4(M * ldx) + al4(M * ldv) + al4(M) + al4(M * 4) + 16);
+}
+
+static int mix2(float* out, const float* a, bool a_obj, const float* P, int D, int64_t M, int64_t rpo, cudaStream_t st) {
+  if (M == 0) return 0;
+  mix_kernel<<<ew_grid(M * D), 256, 0, st>>>(out, a, a_obj ? 1 : 0, P, 0, nullptr, 0, D, M, rpo, 0.5f);
+  SNB_LAUNCH_CHECK();
+  return 0;
+}
+static int axpy(float* y, const float* x, int64_t n, float scale, bool accumulate, cudaStream_t st) {
+  if (n == 0) return 0;
+  axpy_kernel<<<ew_grid(n), 256, 0, st>>>(y, x, n, scale, accumulate ? 1 : 0);
+  SNB_LAUNCH_CHECK();
+  return 0;
+}
+
+static int autorf_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B, const float* shape_latent,
+                          const float* texture_latent, float* sigma, float* rgb, float* ws, cudaStream_t st) {
+  AutoRFLayout L = autorf_layout(h, M, ws);
+  const int D = L.D, Bs = L.Bs, Bt = L.Bt, iSG = h->iSG, iTV = h->iSG + Bt - 1, iR0 = h->iR0;
+  const int64_t rpo = M / B;
+  const auto& ly = h->layers;
+  if (M == 0) return 0;
+  pe_fwd_kernel<<<ew_grid(M * 3), 256, 0, st>>>(xyz, M, h->arch.num_xyz_freq, L.X0, L.ldx);
+  SNB_LAUNCH_CHECK();
+  pe_fwd_kernel<<<ew_grid(M * 3), 256, 0, st>>>(viewdir, M, h->arch.num_dir_freq, L.V, L.ldv);
+  SNB_LAUNCH_CHECK();
+  TRY(fwd_linear(L.X0, L.ldx, M, L.dx, ly[0].w, L.dx, ly[0].b, D, L.P, D, 1, 0, nullptr, 0, st));
+  // shape branch
+  for (int j = 0; j <= Bs - 2; ++j) {
+    TRY(mix2(L.As[j], j == 0 ? shape_latent : L.S[j], j == 0, L.P, D, M, rpo, st));
+    TRY(fwd_linear(L.As[j], D, M, D, ly[1 + j].w, D, ly[1 + j].b, D, L.S[j + 1], D, 1, 0, nullptr, 0, st));
+  }
+  const float* s_last = Bs - 1 == 0 ? shape_latent : L.S[Bs - 1];
+  const bool s_last_obj = Bs - 1 == 0;
+  TRY(mix2(L.Asig, s_last, s_last_obj, L.P, D, M, rpo, st));
+  TRY(fwd_linear(L.Asig, D, M, D, ly[iSG].w, D, ly[iSG].b, 1, sigma, 1, 0, 0, nullptr, 0, st));
+  softplus_kernel<<<ew_grid(M), 256, 0, st>>>(sigma, M);
+  SNB_LAUNCH_CHECK();
+  // texture branch
+  for (int j = 0; j <= Bt - 3; ++j) {
+    TRY(mix2(L.At[j], j == 0 ? texture_latent : L.T[j], j == 0, L.P, D, M, rpo, st));
+    TRY(fwd_linear(L.At[j], D, M, D, ly[iSG + 1 + j].w, D, ly[iSG + 1 + j].b, D, L.T[j + 1], D, 1, 0, nullptr, 0, st));
+  }
+  const float* t_last = Bt - 2 == 0 ? texture_latent : L.T[Bt - 2];
+  mix3_div_kernel<<<ew_grid(M * D), 256, 0, st>>>(L.C, t_last, Bt - 2 == 0 ? 1 : 0, s_last, s_last_obj ? 1 : 0, L.P, D, M, rpo);
+  SNB_LAUNCH_CHECK();
+  TRY(fwd_linear(L.C, D, M, D, ly[iTV].w, D + L.dv, nullptr, D, L.Tv, D, 0, 0, nullptr, 0, st));
+  TRY(fwd_linear(L.V, L.ldv, M, L.dv, ly[iTV].w + D, D + L.dv, ly[iTV].b, D, L.Tv, D, 1, 1, nullptr, 0, st));
+  TRY(mix2(L.Cr, L.Tv, false, L.P, D, M, rpo, st));
+  TRY(fwd_linear(L.Cr, D, M, D, ly[iR0].w, D + L.dv, nullptr, 3, rgb, 3, 0, 0, nullptr, 0, st));
+  TRY(fwd_linear(L.V, L.ldv, M, L.dv, ly[iR0].w + D, D + L.dv, ly[iR0].b, 3, rgb, 3, 0, 1, nullptr, 0, st));
+  sigmoid_kernel<<<ew_grid(M * 3), 256, 0, st>>>(rgb, M * 3);
+  SNB_LAUNCH_CHECK();
+  SNB_CHECK_CUDA(cudaMemcpyAsync(L.RGB, rgb, (size_t)M * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));   // sigmoid' needs the output
+  return 0;
+}
+
+static int autorf_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B, const float* shape_latent,
+                           const float* texture_latent, const float* sigma, const float* g_sigma, const float* g_rgb, const float* ws,
+                           float* scratch, float* g_xyz, float* g_viewdir, float* g_shape_latent, float* g_texture_latent,
+                           float* const* gw, cudaStream_t st) {
+  AutoRFLayout L = autorf_layout(h, M, const_cast<float*>(ws));
+  const int D = L.D, Bs = L.Bs, Bt = L.Bt, iSG = h->iSG, iTV = h->iSG + Bt - 1, iR0 = h->iR0;
+  const auto& ly = h->layers;
+  auto GW = [&](int layer) -> float* { return gw ? gw[2 * layer] : nullptr; };
+  auto GB = [&](int layer) -> float* { return gw ? gw[2 * layer + 1] : nullptr; };
+  if (gw)
+    for (size_t i = 0; i < ly.size(); ++i) {
+      TRY(zero(gw[2 * i], (int64_t)ly[i].out * ly[i].in, st));
+      TRY(zero(gw[2 * i + 1], ly[i].out, st));
+    }
+  if (g_shape_latent) TRY(zero(g_shape_latent, B * D, st));
+  if (g_texture_latent) TRY(zero(g_texture_latent, B * D, st));
+  if (M == 0) return 0;
+  Bump sb{scratch};
+  float* cur = sb.take(M * D);    // gradient w.r.t. the output of the layer being unwound
+  float* tmp = sb.take(M * D);    // gradient w.r.t. a Linear's (mixed) input
+  float* gP = sb.take(M * D);     // accumulated gradient of P (it enters every mix)
+  float* gS = sb.take(M * D);     // gradient of s_{Bs-1} (sigma head + the 3-way mix)
+  float* dX0 = sb.take(M * L.ldx);
+  float* dV = sb.take(M * L.ldv);
+  float* gsp = sb.take(M);
+  float* dpre = sb.take(M * 4);
+  // rgb = sigmoid([Cr, V] Wr^T + br)
+  sigmoid_bwd_kernel<<<ew_grid(M * 3), 256, 0, st>>>(L.RGB, g_rgb, dpre, M * 3);
+  SNB_LAUNCH_CHECK();
+  TRY(bwd_weight(dpre, 3, M, 3, L.Cr, D, D, GW(iR0), D + L.dv, GB(iR0), nullptr, 0, st));
+  TRY(bwd_weight(dpre, 3, M, 3, L.V, L.ldv, L.dv, gw ? GW(iR0) + D : nullptr, D + L.dv, nullptr, nullptr, 0, st));
+  if (g_viewdir) TRY(bwd_data(dpre, 3, M, 3, ly[iR0].w + D, D + L.dv, L.dv, dV, L.ldv, 0, st));
+  TRY(bwd_data(dpre, 3, M, 3, ly[iR0].w, D + L.dv, D, tmp, D, 0, st));              // d Cr;  Cr = (Tv + P) / 2
+  TRY(axpy(gP, tmp, M * D, 0.5f, false, st));
+  TRY(axpy(cur, tmp, M * D, 0.5f, false, st));                                       // d Tv
+  // Tv = relu([C, V] Wv^T + bv)
+  TRY(mask_colsum(cur, L.Tv, D, D, M, B, nullptr, st));
+  TRY(bwd_weight(cur, D, M, D, L.C, D, D, GW(iTV), D + L.dv, GB(iTV), nullptr, 0, st));
+  TRY(bwd_weight(cur, D, M, D, L.V, L.ldv, L.dv, gw ? GW(iTV) + D : nullptr, D + L.dv, nullptr, nullptr, 0, st));
+  if (g_viewdir) TRY(bwd_data(cur, D, M, D, ly[iTV].w + D, D + L.dv, L.dv, dV, L.ldv, 1, st));
+  TRY(bwd_data(cur, D, M, D, ly[iTV].w, D + L.dv, D, tmp, D, 0, st));               // d C;  C = (t_{Bt-2} + s_{Bs-1} + P) / 3
+  const float third = 1.f / 3.f;
+  TRY(axpy(gP, tmp, M * D, third, true, st));
+  TRY(axpy(gS, tmp, M * D, third, false, st));
+  TRY(axpy(cur, tmp, M * D, third, false, st));                                      // d t_{Bt-2}
+  // texture chain: t_{j+1} = relu(texture_layer_j(At_j)),  At_j = (t_j + P) / 2
+  for (int j = Bt - 3; j >= 0; --j) {
+    TRY(mask_colsum(cur, L.T[j + 1], D, D, M, B, nullptr, st));
+    TRY(bwd_weight(cur, D, M, D, L.At[j], D, D, GW(iSG + 1 + j), D, GB(iSG + 1 + j), nullptr, 0, st));
+    TRY(bwd_data(cur, D, M, D, ly[iSG + 1 + j].w, D, D, tmp, D, 0, st));
+    TRY(axpy(gP, tmp, M * D, 0.5f, true, st));
+    TRY(axpy(cur, tmp, M * D, 0.5f, false, st));                                     // d t_j
+  }
+  if (g_texture_latent) TRY(mask_colsum(cur, nullptr, D, D, M, B, g_texture_latent, st));   // t_0 = the latent: per-object column sums
+  // sigma = softplus(sigma.0(Asig)),  Asig = (s_{Bs-1} + P) / 2
+  softplus_bwd_kernel<<<ew_grid(M), 256, 0, st>>>(sigma, g_sigma, gsp, M);
+  SNB_LAUNCH_CHECK();
+  TRY(bwd_weight(gsp, 1, M, 1, L.Asig, D, D, GW(iSG), D, GB(iSG), nullptr, 0, st));
+  TRY(bwd_data(gsp, 1, M, 1, ly[iSG].w, D, D, tmp, D, 0, st));
+  TRY(axpy(gP, tmp, M * D, 0.5f, true, st));
+  TRY(axpy(gS, tmp, M * D, 0.5f, true, st));
+  // shape chain
+  float* g = gS;
+  for (int j = Bs - 2; j >= 0; --j) {
+    TRY(mask_colsum(g, L.S[j + 1], D, D, M, B, nullptr, st));
+    TRY(bwd_weight(g, D, M, D, L.As[j], D, D, GW(1 + j), D, GB(1 + j), nullptr, 0, st));
+    TRY(bwd_data(g, D, M, D, ly[1 + j].w, D, D, tmp, D, 0, st));
+    TRY(axpy(gP, tmp, M * D, 0.5f, true, st));
+    TRY(axpy(cur, tmp, M * D, 0.5f, false, st));                                     // d s_j
+    g = cur;
+  }
+  if (g_shape_latent) TRY(mask_colsum(g, nullptr, D, D, M, B, g_shape_latent, st));
+  // P = relu(encoding_xyz(X0))
+  TRY(mask_colsum(gP, L.P, D, D, M, B, nullptr, st));
+  TRY(bwd_weight(gP, D, M, D, L.X0, L.ldx, L.dx, GW(0), L.dx, GB(0), nullptr, 0, st));
+  if (g_xyz) {
+    TRY(bwd_data(gP, D, M, D, ly[0].w, L.dx, L.dx, dX0, L.ldx, 0, st));
+    pe_bwd_kernel<<<ew_grid(M * 3), 256, 0, st>>>(dX0, L.ldx, xyz, M, h->arch.num_xyz_freq, g_xyz);
+    SNB_LAUNCH_CHECK();
+  }
+  if (g_viewdir) {
+    pe_bwd_kernel<<<ew_grid(M * 3), 256, 0, st>>>(dV, L.ldv, viewdir, M, h->arch.num_dir_freq, g_viewdir);
+    SNB_LAUNCH_CHECK();
+  }
+  (void)shape_latent; (void)texture_latent;
   return 0;
 }
 

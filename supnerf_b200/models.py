@@ -169,6 +169,7 @@ class AutoRF(_DecoderBase):
                  norm_layer_type='BatchNorm2d'):
         super().__init__()
         self._init_common(shape_blocks, texture_blocks, latent_dim, latent_dim, num_xyz_freq, num_dir_freq)
+        self.precision = "fp32"   # the AutoRF chain (W = 128, feature mixing after every layer) runs on the fp32 back end only
         d_xyz, d_viewdir = 3 + 6 * num_xyz_freq, 3 + 6 * num_dir_freq
         self.encoding_xyz = nn.Sequential(nn.Linear(d_xyz, latent_dim), nn.ReLU())
         for j in range(shape_blocks - 1):

@@ -298,6 +298,108 @@ def golden_scene_merge():
          sigmas_sort=env["sigmas_sort"], rgbs_sort=env["rgbs_sort"], rgb=env["rgb"], depth=env["depth"], acc=env["weights"])
 
 
+def golden_drivers():
+    """The remaining public drivers of SURVEY 8(b), each executed through the UNMODIFIED reference on one small object:
+    renderer.render_rays_v3 (full grid and a random ray subset), utils.render_rays / render_rays_specified /
+    prepare_pixel_samples / render_full_img, NeRFRenderer.render_rays_specified / prepare_pixel_samples / render_full_img.
+    Every torch.rand_like draw of the box stack is recorded (the CUDA path draws on the device generator: the tests feed the
+    recorded jitter back); the shell stack draws torch.rand(S) on the CPU generator on both sides (same seed, same numbers)."""
+    seed, S_box, S = 7, 64, 16
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=seed)
+    model = model_supnerf.SUPNeRF(shape_blocks=3, texture_blocks=1, pose_blocks=3, regress_blocks=3, latent_dim=256)
+    assert not model.load_state_dict(sd, strict=False).unexpected_keys
+    model.requires_grad_(False)
+    obj = oracle.synthetic_object(seed, im_sz=8)
+    shp0, tex0 = oracle.synthetic_latents(seed, 1)
+    diag = np.linalg.norm(obj["wlh"]).astype(np.float32)
+    # a small full-resolution crop (12 x 10 pixels) around the projected box centre, with its own image / coherent +-1 mask
+    r = [int(v) for v in obj["roi"]]
+    cx, cy = (r[0] + r[2]) // 2, (r[1] + r[3]) // 2
+    roi_s = torch.tensor([cx - 6, cy - 5, cx + 6, cy + 5], dtype=torch.int32)
+    g = torch.Generator().manual_seed(seed)
+    img_s = torch.rand(10, 12, 3, generator=g)
+    mask_s = torch.ones(10, 12, 1)
+    mask_s[:, 7:] = -1.0
+    mask_s[:2] = 0.0
+    x_vec = np.array([0, 3, 11, 5, 7, 2, 9], dtype=np.int64)
+    y_vec = np.array([0, 9, 4, 5, 1, 8, 3], dtype=np.int64)
+    out = dict(seed=seed, wlh=obj["wlh"], obj_diag=diag, K=obj["K"], cam_pose=obj["cam_pose"], roi=obj["roi"], img=obj["img"],
+               mask_occ=obj["mask_occ"], roi_s=roi_s, img_s=img_s, mask_s=mask_s, x_vec=x_vec, y_vec=y_vec, shapecode=shp0,
+               texturecode=tex0, weights_sha256=np.frombuffer(state_hash(sd).encode(), dtype=np.uint8))
+
+    draws = []
+    orig_rand_like = torch.rand_like
+
+    def recording_rand_like(t, *a, **k):
+        v = orig_rand_like(t, *a, **k)
+        draws.append(v.clone())
+        return v
+
+    def leaves():
+        return obj["cam_pose"].clone().requires_grad_(), shp0.clone().requires_grad_(), tex0.clone().requires_grad_()
+
+    torch.rand_like = recording_rand_like
+    try:
+        # ---- renderer.render_rays_v3 (renderer.py:382): full 8x8 grid, shapenet frame, adjust_scale, fwd + bwd
+        cam, shp, tex = leaves()
+        torch.manual_seed(70)
+        rgb, dep, acc, tgt, occ = ref_renderer.render_rays_v3(model, "cpu", obj["img"], obj["mask_occ"], cam, obj["wlh"], obj["K"], obj["roi"],
+                                                             S_box, shp, tex, 1, 0, im_sz=8, n_rays=None, adjust_scale=1.1)
+        loss = losses(rgb, acc, tgt, occ)
+        loss.backward()
+        out.update(v3_jitter=draws.pop(), v3_rgb=rgb, v3_depth=dep, v3_acc=acc, v3_tgt=tgt, v3_occ=occ, v3_loss=loss,
+                   v3_g_cam=cam.grad, v3_g_shp=shp.grad, v3_g_tex=tex.grad)
+        assert not draws
+        # ---- ... with a random ray subset (np.random.permutation under a fixed numpy seed)
+        cam, shp, tex = leaves()
+        np.random.seed(71)
+        torch.manual_seed(71)
+        rgb, dep, acc, tgt, occ = ref_renderer.render_rays_v3(model, "cpu", obj["img"], obj["mask_occ"], cam, obj["wlh"], obj["K"], obj["roi"],
+                                                             S_box, shp, tex, 0, 0, im_sz=8, n_rays=20)
+        out.update(v3s_jitter=draws.pop(), v3s_rgb=rgb, v3s_depth=dep, v3s_acc=acc, v3s_tgt=tgt, v3s_occ=occ)
+        # ---- NeRFRenderer drivers on the small full-resolution crop
+        R = ref_renderer.NeRFRenderer(n_samples=S)
+        cam, shp, tex = leaves()
+        torch.manual_seed(72)
+        rgb, dep, acc, tgt, occ = R.render_rays_specified(model, "cpu", img_s, mask_s, cam, obj["wlh"], obj["K"], roi_s, x_vec, y_vec, shp, tex)
+        loss = losses(rgb, acc, tgt, occ)
+        loss.backward()
+        out.update(rs_jitter=draws.pop(), rs_rgb=rgb, rs_depth=dep, rs_acc=acc, rs_tgt=tgt, rs_occ=occ, rs_g_cam=cam.grad,
+                   rs_g_shp=shp.grad, rs_g_tex=tex.grad)
+        np.random.seed(73)
+        torch.manual_seed(73)
+        xyz, vd, zv, tgt, occ = R.prepare_pixel_samples(img_s, mask_s, obj["cam_pose"], obj["wlh"], obj["K"], roi_s, 40)
+        out.update(rp_jitter=draws.pop(), rp_xyz=xyz, rp_viewdir=vd, rp_z_vals=zv, rp_tgt=tgt, rp_occ=occ)
+        torch.manual_seed(74)
+        with torch.no_grad():
+            im_full, dep_full = R.render_full_img(model, "cpu", obj["cam_pose"], obj["wlh"], obj["K"], roi_s, shp0, tex0, out_depth=True)
+        out.update(rf_jitter=draws.pop(), rf_img=im_full, rf_depth=dep_full)
+        assert not draws
+    finally:
+        torch.rand_like = orig_rand_like
+    # ---- utils drivers (shell stack: one torch.rand(S) on the CPU generator per call)
+    cam, shp, tex = leaves()
+    np.random.seed(75)
+    torch.manual_seed(75)
+    rgb, dep, acc, tgt, occ = ref_utils.render_rays(model, "cpu", img_s, mask_s, cam, diag, obj["K"], roi_s, S, shp, tex, 1, 0, n_rays=50)
+    loss = losses(rgb, acc, tgt, occ)
+    loss.backward()
+    out.update(ur_rgb=rgb, ur_depth=dep, ur_acc=acc, ur_tgt=tgt, ur_occ=occ, ur_g_cam=cam.grad, ur_g_shp=shp.grad, ur_g_tex=tex.grad)
+    cam, shp, tex = leaves()
+    torch.manual_seed(76)
+    rgb, dep, acc, tgt, occ = ref_utils.render_rays_specified(model, "cpu", img_s, mask_s, cam, diag, obj["K"], roi_s, x_vec, y_vec, S, shp, tex, 1, 0)
+    out.update(us_rgb=rgb, us_depth=dep, us_acc=acc, us_tgt=tgt, us_occ=occ)
+    np.random.seed(77)
+    torch.manual_seed(77)
+    xyz, vd, zv, tgt, occ = ref_utils.prepare_pixel_samples(img_s, mask_s, obj["cam_pose"], diag, obj["K"], roi_s, 40, S, 1, 0)
+    out.update(up_xyz=xyz, up_viewdir=vd, up_z_vals=zv, up_tgt=tgt, up_occ=occ)
+    torch.manual_seed(78)
+    with torch.no_grad():
+        im_full, dep_full = ref_utils.render_full_img(model, "cpu", obj["cam_pose"], obj["wlh"], obj["K"], roi_s, S, shp0, tex0, 1, out_depth=True)
+    out.update(uf_img=im_full, uf_depth=dep_full)
+    save("drivers", **out)
+
+
 def golden_state_dict_keys():
     """state_dict key -> shape of the reference modules (the checkpoint ABI): lets the CPU tests check that the
     drop-in modules load a reference checkpoint with the default strict=True without importing the reference."""
@@ -319,4 +421,5 @@ if __name__ == "__main__":
     golden_decoder_batch()
     golden_autorf()
     golden_scene_merge()
+    golden_drivers()
     golden_state_dict_keys()
