@@ -154,3 +154,26 @@ def test_autorf_decoder_block_counts_vs_oracle_all_grads(blocks, B, n, S_):
         assert rel_err(a.grad, b.grad) < 1e-4, name
     for k, p_ in m.named_parameters():
         assert rel_err(p_.grad, sdr[k].grad) < 1e-4, k
+
+
+def test_kitti2nusc_rotation_and_symmetric_augmentation(ctx):
+    """The frame fix-ups no shipped caller enables but the API carries: kitti2nusc=True through NeRFRenderer.render_rays
+    (renderer.py:153-163) and, together with the y-flip of sym_aug (python `random` seeded so that the flip is taken), through
+    utils.render_rays_v2 (utils.py:474-489)."""
+    import random
+    g, S, m = ctx
+    R = S.renderer.NeRFRenderer(n_samples=16)
+    cam, shp, tex = _leaves(g)
+    with forced_rand_like(T(g["k2n_jitter"])):
+        out = R.render_rays(m, DEV, T(g["img"]), T(g["mask_occ"]), cam, g["wlh"], T(g["K"]), T(g["roi"]), shp, tex, kitti2nusc=True, im_sz=8)
+    _check_render(out, g, "k2n")
+    oracle.refine_losses(out[0], out[2], out[3], out[4])[0].backward()
+    _check_grads(cam, shp, tex, g, "k2n")
+    cam, shp, tex = _leaves(g)
+    random.seed(2)
+    torch.manual_seed(80)
+    out = S.utils.render_rays_v2(m, DEV, T(g["img"]), T(g["mask_occ"]), cam, np.float32(g["obj_diag"]), T(g["K"]), T(g["roi"]), 16, shp, tex,
+                                 1, 1, kitti2nusc=True, im_sz=8, n_rays=None)
+    _check_render(out, g, "sym")
+    oracle.refine_losses(out[0], out[2], out[3], out[4])[0].backward()
+    _check_grads(cam, shp, tex, g, "sym")

@@ -374,9 +374,29 @@ def golden_drivers():
         with torch.no_grad():
             im_full, dep_full = R.render_full_img(model, "cpu", obj["cam_pose"], obj["wlh"], obj["K"], roi_s, shp0, tex0, out_depth=True)
         out.update(rf_jitter=draws.pop(), rf_img=im_full, rf_depth=dep_full)
+        # ---- the kitti2nusc frame rotation (renderer.py:153-163; no shipped caller enables it) through NeRFRenderer.render_rays
+        R64 = ref_renderer.NeRFRenderer(n_samples=S)
+        cam, shp, tex = leaves()
+        torch.manual_seed(79)
+        rgb, dep, acc, tgt, occ = R64.render_rays(model, "cpu", obj["img"], obj["mask_occ"], cam, obj["wlh"], obj["K"], obj["roi"], shp, tex,
+                                                  kitti2nusc=True, im_sz=8)
+        loss = losses(rgb, acc, tgt, occ)
+        loss.backward()
+        out.update(k2n_jitter=draws.pop(), k2n_rgb=rgb, k2n_depth=dep, k2n_acc=acc, k2n_tgt=tgt, k2n_occ=occ, k2n_g_cam=cam.grad,
+                   k2n_g_shp=shp.grad, k2n_g_tex=tex.grad)
         assert not draws
     finally:
         torch.rand_like = orig_rand_like
+    # ---- utils.render_rays_v2 with the symmetric augmentation taken (python `random`: seed 2 draws 0.956 > 0.5) and kitti2nusc
+    import random as _random
+    cam, shp, tex = leaves()
+    _random.seed(2)
+    torch.manual_seed(80)
+    rgb, dep, acc, tgt, occ = ref_utils.render_rays_v2(model, "cpu", obj["img"], obj["mask_occ"], cam, diag, obj["K"], obj["roi"], S, shp, tex,
+                                                       1, 1, kitti2nusc=True, im_sz=8, n_rays=None)
+    loss = losses(rgb, acc, tgt, occ)
+    loss.backward()
+    out.update(sym_rgb=rgb, sym_depth=dep, sym_acc=acc, sym_tgt=tgt, sym_occ=occ, sym_g_cam=cam.grad, sym_g_shp=shp.grad, sym_g_tex=tex.grad)
     # ---- utils drivers (shell stack: one torch.rand(S) on the CPU generator per call)
     cam, shp, tex = leaves()
     np.random.seed(75)
