@@ -664,10 +664,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_const
 // ------------------------------------------------------------------------------------------ backward epilogue
 // acc = gradient w.r.t. the layer's input; mask it by the producing layer's ReLU bits and hand it on as the next A operand.
 // EV: add the sigma-head gradient first, no mask.  16-column pieces, two register sets (see fwd_epilogue).
-template <bool EV, bool MASK>
-__device__ __forceinline__ void bwd_half(const Smem& sm, const EpiCtx& e, const uint32_t (&r)[16], int c, int h, uint32_t mw, float gsp) {
+template <bool EV, bool MASK, int H>
+__device__ __forceinline__ void bwd_half(const Smem& sm, const EpiCtx& e, const uint32_t (&r)[16], int c, const uint32_t (&msh)[8], float gsp) {
   const float* wsig_s = sm.tab(TAB_WSIG);
-  const int col0 = c * 64 + (int)e.hh * 32 + h * 16;
+  const int col0 = c * 64 + (int)e.hh * 32 + H * 16;
   uint32_t pk[8];
 #pragma unroll
   for (int i4 = 0; i4 < 4; ++i4) {
@@ -676,14 +676,15 @@ __device__ __forceinline__ void bwd_half(const Smem& sm, const EpiCtx& e, const 
       const float4 ws = *reinterpret_cast<const float4*>(wsig_s + col0 + 4 * i4);
       v[0] += gsp * ws.x; v[1] += gsp * ws.y; v[2] += gsp * ws.z; v[3] += gsp * ws.w;
     }
-    if (MASK) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) if (!mask_bit(mw, h * 16 + 4 * i4 + u)) v[u] = 0.f;
-    }
     pk[2 * i4] = pack_bf16(v[0], v[1]);
     pk[2 * i4 + 1] = pack_bf16(v[2], v[3]);
   }
-  store_row16(sm.chunk(e.slot, c), e.row, e.hh * 4u + (uint32_t)h * 2u, pk);
+  if (MASK) {   // ReLU mask on the packed pairs: one prmt + one and per pair (tc_ptx.cuh: mask_pair)
+    pk[0] &= mask_pair<H * 16 + 0>(msh); pk[1] &= mask_pair<H * 16 + 2>(msh); pk[2] &= mask_pair<H * 16 + 4>(msh);
+    pk[3] &= mask_pair<H * 16 + 6>(msh); pk[4] &= mask_pair<H * 16 + 8>(msh); pk[5] &= mask_pair<H * 16 + 10>(msh);
+    pk[6] &= mask_pair<H * 16 + 12>(msh); pk[7] &= mask_pair<H * 16 + 14>(msh);
+  }
+  store_row16(sm.chunk(e.slot, c), e.row, e.hh * 4u + (uint32_t)H * 2u, pk);
 }
 
 template <bool EV, bool MASK>
@@ -693,12 +694,14 @@ __device__ __forceinline__ void bwd_epilogue(const Smem& sm, const EpiCtx& e, co
   tmem_ld16_issue(t0, ra);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
+    uint32_t msh[8];
+    if (MASK) mask_shifts(mw[c], msh);
     tmem_ld_wait();
     tmem_ld16_issue(t0 + (uint32_t)c * 64u + 16u, rb);
-    bwd_half<EV, MASK>(sm, e, ra, c, 0, mw[c], gsp);
+    bwd_half<EV, MASK, 0>(sm, e, ra, c, msh, gsp);
     tmem_ld_wait();
     if (c + 1 < 4) tmem_ld16_issue(t0 + (uint32_t)(c + 1) * 64u, ra);
-    bwd_half<EV, MASK>(sm, e, rb, c, 1, mw[c], gsp);
+    bwd_half<EV, MASK, 1>(sm, e, rb, c, msh, gsp);
   }
 }
 

@@ -126,6 +126,24 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
 // element from the sign bit of the pre-activation (1 = active).
 __device__ __forceinline__ bool mask_bit(uint32_t mw, int i) { return (mw >> (31 - i)) & 1u; }
 
+// bf16x2 AND-mask of the element pair (e, e + 1), e even, of a ReLU mask word: 0xFFFF in the low half iff element e is active,
+// in the high half iff element e + 1 is.  The bit of element e sits at 31 - e = the MSB of byte 3 - (e >> 3) of (mw << (e & 7)):
+// ONE prmt in sign-replicate mode (selector nibble 8 | byte) expands both bits, against a bit test + select per element.
+// sh[t] = mw << t, t = 0 .. 7 (shared by the 16 pairs of a mask word).
+template <int E>
+__device__ __forceinline__ uint32_t mask_pair(const uint32_t (&sh)[8]) {
+  static_assert(E % 2 == 0 && E >= 0 && E < 32, "even element index inside a 32-column mask word");
+  constexpr uint32_t j = 3u - (uint32_t)(E >> 3);
+  constexpr uint32_t sel = (8u | j) | ((8u | j) << 4) | ((8u | (4u + j)) << 8) | ((8u | (4u + j)) << 12);
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(sh[E & 7]), "r"(sh[(E & 7) + 1]), "n"(sel));
+  return d;
+}
+__device__ __forceinline__ void mask_shifts(uint32_t mw, uint32_t (&sh)[8]) {
+#pragma unroll
+  for (int t = 0; t < 8; ++t) sh[t] = mw << t;
+}
+
 // byte offset of 16-byte unit `unit` (0..7) of row `row` inside a 128B-swizzled [rows][64] bf16 chunk
 __device__ __forceinline__ uint32_t swz(uint32_t row, uint32_t unit) { return row * 128u + ((unit ^ (row & 7u)) << 4); }
 
