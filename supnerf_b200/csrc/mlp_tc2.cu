@@ -34,14 +34,17 @@ constexpr uint32_t kStageBytes = 16384;   // [256 n][32 k] bf16
 // cta_group::2 variant (CG2): one M = 256 MMA spans the CTA pair, each CTA holds ITS half of every weight stage ([128 n][32 k],
 // 8 KB), so the ring is twice as deep in the same shared memory and the tensor core reads 4 KB (A) + 4 KB (B) per instruction
 // per SM instead of 4 + 8: the epilogue's operand stores get half of the shared-memory bandwidth instead of a quarter.
-constexpr int kRing2 = 10;
+constexpr int kRing2 = 8;                 // (10 stages measured no faster: 39 188 vs 39 164 cycles per forward tile pair)
 constexpr uint32_t kStageBytes2 = 8192;
 constexpr int kRingMax = 10;              // barrier layout (both variants)
-static_assert(kRing * kStageBytes == kRing2 * kStageBytes2, "same ring footprint");
+static_assert(kRing * kStageBytes >= kRing2 * kStageBytes2, "ring footprint");
 constexpr int kMaxSteps = 13;
 constexpr int kMaxLat = 4;                // shape_blocks + texture_blocks <= 4 (every shipped config: 3 + 1)
 
 constexpr uint32_t SM_RING = 8 * kChunkBytes;                    // A chunks [slot][4]
+constexpr uint32_t SM_PEV = SM_RING + kRing2 * kStageBytes2;      // CG2 forward: PE(viewdir) A tile per slot, [128][32] bf16, 64-byte swizzle
+constexpr uint32_t kPevBytes = 8192;
+static_assert(SM_PEV + 2 * kPevBytes <= SM_RING + kRing * kStageBytes, "the PE(viewdir) tiles live inside the ring footprint");
 constexpr uint32_t SM_TAB = SM_RING + kRing * kStageBytes;
 constexpr uint32_t TAB_BIAS = 0;                                 // (unused since the biases ride on the tensor core; kept for layout stability)
 constexpr uint32_t TAB_LAT = TAB_BIAS + 4 * 1024;                // fwd: [128][16] bf16 all-ones A tile (4 KB); bwd: [slot][kMaxLat][256] latent column sums
@@ -64,12 +67,15 @@ struct Step {
   int8_t epi, mask_slot, latent_slot, bias_row, dbg_idx, accumulate, produce_a, colsum;
   int8_t bias_stage;         // 0 none; 1 static image right after the step's weight stages; 2 per-object image of latent_slot (fwd only)
   int8_t save_chunks;        // training mode: number of 16 KB A-operand chunks of this step kept for the weight-gradient kernels (0 = none)
-  uint8_t pad_[2];
+  int8_t tail_pev;           // 1: the step's LAST weight stage multiplies the slot's PE(viewdir) tile instead of the next chunk half
+  uint8_t pad_[1];
   uint32_t save_off;         // ... and their byte offset inside the tile's save block
 };
 
 struct Program {
   int n_steps, n_mask_slots;
+  int pev;                   // 1: encoding_viewdir is ONE step (y columns + PE(viewdir) columns); the epilogue groups keep PE(viewdir) of
+                             // their tile in the slot's PEV tile (written with the tile's PE(xyz))
   uint32_t save_tile_bytes;  // size of one tile's save block (training mode)
   Step s[kMaxSteps];
 };
@@ -121,6 +127,8 @@ struct Smem {
   __device__ uint32_t chunk_u32(uint32_t slot, int c) const { return base_u32 + (slot * 4u + (uint32_t)c) * kChunkBytes; }
   __device__ uint32_t stage_u32(uint32_t s) const { return base_u32 + SM_RING + s * kStageBytes; }
   __device__ uint32_t stage2_u32(uint32_t s) const { return base_u32 + SM_RING + s * kStageBytes2; }
+  __device__ uint8_t* pev(uint32_t slot) const { return base + SM_PEV + slot * kPevBytes; }
+  __device__ uint32_t pev_u32(uint32_t slot) const { return base_u32 + SM_PEV + slot * kPevBytes; }
   __device__ float* tab(uint32_t off) const { return reinterpret_cast<float*>(base + SM_TAB + off); }
   __device__ uint32_t bar(int i) const { return base_u32 + SM_BARS + 8u * i; }
 };
@@ -422,8 +430,10 @@ __device__ __forceinline__ void mma_loop(const Params& p, const Smem& sm, int64_
         for (int j = 0; j < n_stages; ++j) {
           mbar_wait(sm.bar(BAR_WFULL + stage), ph);
           tc_fence_after();
-          if (CG2) umma2_stage_elect(d_tmem, a_desc, umma_desc_sw64(sm.stage2_u32(stage)), idesc, acc, sm.bar(BAR_WEMPTY + stage));
-          else umma_stage_elect(d_tmem, a_desc, umma_desc_sw64(sm.stage_u32(stage)), idesc, acc, sm.bar(BAR_WEMPTY + stage));
+          if (CG2) {
+            const uint64_t a_use = (st.tail_pev && j == n_stages - 1) ? umma_desc_sw64(sm.pev_u32(slot)) : a_desc;
+            umma2_stage_elect(d_tmem, a_use, umma_desc_sw64(sm.stage2_u32(stage)), idesc, acc, sm.bar(BAR_WEMPTY + stage));
+          } else umma_stage_elect(d_tmem, a_desc, umma_desc_sw64(sm.stage_u32(stage)), idesc, acc, sm.bar(BAR_WEMPTY + stage));
           acc = 1u;
           a_desc += (j & 1) ? (uint64_t)((kChunkBytes - 64u) >> 4) : (uint64_t)(64u >> 4);   // next 32-k half of the chunk / next chunk
           if (++stage == RING) { stage = 0; ph ^= 1u; }
@@ -557,6 +567,34 @@ __device__ __forceinline__ void fwd_epilogue(const Params& p, const Smem& sm, co
   }
 }
 
+// PE(viewdir) (deg 4: 27 columns, zero-padded to 32) of this thread's row into the slot's PEV tile: [128 rows][32 k] bf16, K-major,
+// 64-byte swizzle (rows 64 B apart, 16-byte unit u of row r at (u ^ ((r >> 1) & 3))), the layout umma_desc_sw64 describes.
+// The hh == 0 thread of a row writes columns 0-15, the hh == 1 thread columns 16-31.
+__device__ __forceinline__ void write_pev_row(uint8_t* pev, uint32_t row, uint32_t hh, const float d[3]) {
+  float s[4][3], c[4][3];
+  trig_ladder<4>(d, s, c);
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) v[a] = d[a];
+#pragma unroll
+  for (int f = 0; f < 4; ++f)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      v[3 + 3 * f + a] = s[f][a];
+      v[15 + 3 * f + a] = c[f][a];
+    }
+  uint32_t pk[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) pk[i] = hh ? pack_bf16(v[16 + 2 * i], v[17 + 2 * i]) : pack_bf16(v[2 * i], v[2 * i + 1]);
+#pragma unroll
+  for (uint32_t u = 0; u < 2; ++u) {
+    const uint32_t unit = 2u * hh + u;
+    *reinterpret_cast<uint4*>(pev + row * 64u + ((unit ^ ((row >> 1) & 3u)) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ forward kernel
 template <bool DBG, bool CG2>
 __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_constant__ Params p) {
@@ -608,6 +646,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_const
       load_coords(pair_first, x, dir);
       write_pe_row<10>(sm.chunk(slot, 0), e.row, e.hh, x);
       publish<CG2>(sm, slot, lane, ready_leader);
+      if (CG2 && p.prog.pev) write_pev_row(sm.pev(slot), e.row, e.hh, dir);   // needed at encoding_viewdir only: ordered by the next publish
     }
     for (int64_t pair0 = pair_first; pair0 < n_pairs; pair0 += gridDim.x) {
       const int64_t tile = tile_index<CG2>(pair0, crank, slot);
@@ -636,6 +675,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_const
         else if (has_next) {   // rgb.0's MMAs are complete and its accumulator is drained: hand the NEXT tile's PE(xyz) to the MMA warp
           write_pe_row<10>(sm.chunk(slot, 0), e.row, e.hh, xn);   // before the tile-end bookkeeping below
           publish<CG2>(sm, slot, lane, ready_leader);
+          // PE(viewdir) of the next tile, OFF the boundary's critical chain: it is only read by the next tile's encoding_viewdir MMAs,
+          // which the MMA warp issues after this warp's next publish (fence + arrive); this tile's MMAs are all complete
+          if (CG2 && p.prog.pev) write_pev_row(sm.pev(slot), e.row, e.hh, dn);
         } else tc_fence_before();
         if (p.trace && blockIdx.x == 0 && gtid == 0) p.trace[(((pair0 / gridDim.x) * p.prog.n_steps + si) * 2 + slot) * 4 + 3] = clock64();
       }
@@ -981,7 +1023,7 @@ bool tc2_supported(const snb_handle_s* h) {
 }
 
 struct Tc2Plan {
-  tc2::Program fwd, fwd_train, bwd_full, bwd_noxyz;
+  tc2::Program fwd, fwd_train, fwd_merged, bwd_full, bwd_noxyz;
   std::vector<tc2::PackJob> jobs;
   uint32_t total_bytes = 0;
   int r0_slot = 0;
@@ -1128,6 +1170,25 @@ static Tc2Plan build_plan2(const snb_handle_s* h) {
       b.save_tile_bytes = off;
     }
   }
+  {  // ---------------- forward, cta_group::2 kernels: encoding_viewdir as ONE step.  The y columns (8 stages) are followed by ONE 32-k
+     // stage of the PE(viewdir) columns, multiplied with the slot's PEV tile: one commit -> epilogue round trip less per tile
+     // (~2 000 idle tensor-pipe cycles per tile pair, profiles/r1_trace_cg2.md).  Its stages are a second copy at the image's end.
+    const tc2::Program& f = pl.fwd;
+    tc2::Program& g = pl.fwd_merged;
+    g = tc2::Program{};
+    g.n_mask_slots = f.n_mask_slots; g.pev = 1; g.save_tile_bytes = 0;
+    for (int i = 0; i < f.n_steps; ++i) {
+      if (i == Bs + 3) continue;                 // the separate PE(viewdir) step
+      if (i != Bs + 2) { push(g, f.s[i]); continue; }
+      tc2::Step s = mk(F_RELU, 256, 9, slot_vv, -1, 2, Bs + 2);
+      s.tail_pev = 1;
+      uint32_t unused;
+      add_stages(pl, ly[h->iEV].w, W + dv, false, 256, 256, W, 8, &s.w_off);
+      add_stages(pl, ly[h->iEV].w + W, W + dv, false, 256, 256, dv, 1, &unused);   // directly behind the y stages
+      add_bias_stage(pl, s, ly[h->iEV].b, 256, 256);
+      push(g, s);
+    }
+  }
   return pl;
 }
 
@@ -1242,11 +1303,12 @@ int tc2_launch_fwd(const snb_handle_s* h, const void* packed2, const float* xyz,
   p.sigma = sigma; p.rgb = rgb; p.dbg = dbg;
   p.save = save;
   p.m_dev = m_dev;
-  p.prog = save ? pl.fwd_train : pl.fwd;
+  const bool cg2 = tc2_use_cg2(p);
+  p.prog = save ? pl.fwd_train : ((cg2 && !dbg) ? pl.fwd_merged : pl.fwd);
   if (tc2_init_device()) return 1;
   if (dbg) {
     SNB_CHECK_CUDA(tc2_launch(tc2_fwd_kernel<true, false>, tc2_grid(tc2_fwd_kernel<true, false>, M), st, p));
-  } else if (tc2_use_cg2(p)) {
+  } else if (cg2) {
     SNB_CHECK_CUDA(tc2_launch(tc2_fwd_kernel<false, true>, tc2_grid(tc2_fwd_kernel<false, true>, M), st, p));
   } else {
     SNB_CHECK_CUDA(tc2_launch(tc2_fwd_kernel<false, false>, tc2_grid(tc2_fwd_kernel<false, false>, M), st, p));

@@ -17,7 +17,9 @@ xyz = ((torch.rand(N, S, 3, generator=g) - 0.5) * 1.6).to(dev).requires_grad_()
 vd = torch.nn.functional.normalize(torch.randn(N, 1, 3, generator=g), dim=-1).repeat(1, S, 1).to(dev).requires_grad_()
 shp, tex = [t.to(dev).requires_grad_() for t in oracle.synthetic_latents(0, 1)]
 lib = snb._lib.load()
-n_pairs, n_steps = 28, 9
+# forward under the (default) cta_group::2 kernels: encoding_viewdir is one step -> 8 steps; otherwise 9.  Override: argv[2].
+n_pairs = 28
+n_steps = int(sys.argv[2]) if len(sys.argv) > 2 else (8 if which == "fwd" and os.environ.get("SNB_TC_CG2", "1") != "0" else 9)
 buf = torch.zeros(n_pairs * n_steps * 2 * 4 + 64, dtype=torch.int64, device=dev)
 sig, rgb = m(xyz, vd, shp, tex)   # warm-up
 torch.cuda.synchronize()
