@@ -178,3 +178,57 @@ def test_scene_merge_oracle_matches_reference_lines():
     rgb, dep, acc = oracle.composite(s_sort, c_sort, z_sort, white_bkgd=True)
     assert rel_err(rgb, g["rgb"]) < 1e-6 and rel_err(dep, g["depth"]) < 1e-6 and rel_err(acc, g["acc"]) < 1e-6
 
+
+
+def test_oracle_stages_against_driver_fixture():
+    """The oracle's stage functions composed the way the remaining drivers compose them, against tests/golden/drivers.npz (the
+    reference's own outputs): NeRFRenderer.render_rays_specified (get_rays_specified on a non-square full-resolution crop -> box
+    sampler -> decoder -> compositing, gradients to pose and codes), NeRFRenderer.prepare_pixel_samples (numpy permutation),
+    NeRFRenderer.render_full_img, utils.render_rays_specified / render_full_img (shell stack) and renderer.render_rays_v3."""
+    g = load_golden("drivers")
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=int(g["seed"]))
+    _check_weights(g, sd)
+    K, roi_s, wlh, diag = T(g["K"]), [int(v) for v in g["roi_s"]], g["wlh"], float(g["obj_diag"])
+    xs, ys = g["x_vec"] + roi_s[0], g["y_vec"] + roi_s[1]
+    # NeRFRenderer.render_rays_specified (renderer.py:169-201) + the refine losses, backward
+    cam = T(g["cam_pose"]).requires_grad_()
+    shp, tex = T(g["shapecode"]).requires_grad_(), T(g["texturecode"]).requires_grad_()
+    ro, vd = oracle.get_rays_specified(K, cam, xs, ys)
+    xyz, vdr, zv, _ = oracle.prepare_sampled_rays(ro, vd, wlh, 16, T(g["rs_jitter"]))
+    sig, rgbs = oracle.codenerf_decoder(sd, xyz, vdr, shp, tex)
+    rgb, dep, acc = oracle.composite(sig.squeeze(-1), rgbs, zv, True)
+    assert rel_err(rgb, g["rs_rgb"]) < TOL and rel_err(dep, g["rs_depth"]) < TOL and rel_err(acc, g["rs_acc"]) < TOL
+    oracle.refine_losses(rgb, acc, T(g["rs_tgt"]), T(g["rs_occ"]))[0].backward()
+    assert rel_err(shp.grad, g["rs_g_shp"]) < 1e-5 and rel_err(tex.grad, g["rs_g_tex"]) < 1e-5 and rel_err(cam.grad, g["rs_g_cam"]) < 1e-4
+    with torch.no_grad():
+        cam0, shp0, tex0 = T(g["cam_pose"]), T(g["shapecode"]), T(g["texturecode"])
+        # NeRFRenderer.prepare_pixel_samples (renderer.py:203-236): the same numpy permutation under the same seed
+        ro, vd = oracle.get_rays(K, cam0, roi_s)
+        np.random.seed(73)
+        ids = np.random.permutation(ro.shape[0])[:40]
+        xyz, vdr, zv, _ = oracle.prepare_sampled_rays(ro[ids], vd[ids], wlh, 16, T(g["rp_jitter"]))
+        assert rel_err(xyz, g["rp_xyz"]) < TOL and rel_err(vdr, g["rp_viewdir"]) < TOL and rel_err(zv, g["rp_z_vals"]) < TOL
+        assert torch.equal(T(g["img_s"]).reshape(-1, 3)[ids], T(g["rp_tgt"])) and torch.equal(T(g["mask_s"]).reshape(-1, 1)[ids], T(g["rp_occ"]))
+        # NeRFRenderer.render_full_img (renderer.py:238-294): every pixel of the crop, row-major
+        xyz, vdr, zv, _ = oracle.prepare_sampled_rays(ro, vd, wlh, 16, T(g["rf_jitter"]))
+        sig, rgbs = oracle.codenerf_decoder(sd, xyz, vdr, shp0, tex0)
+        rgb, dep, _ = oracle.composite(sig.squeeze(-1), rgbs, zv, True)
+        assert rel_err(rgb.reshape(10, 12, 3), g["rf_img"]) < TOL and rel_err(dep.reshape(10, 12), g["rf_depth"]) < TOL
+        # utils.render_rays_specified (utils.py:504-551) and utils.render_full_img (:554-616): the shell stack, torch.rand(S) per call
+        near, far = oracle.shell_bounds(cam0, diag)
+        for seed, rays, key, shape in ((76, oracle.get_rays_specified(K, cam0, xs, ys), "us", None), (78, (ro, vd), "uf", (10, 12))):
+            torch.manual_seed(seed)
+            jit = torch.rand(16)
+            x, v, z = oracle.sample_from_rays_shell(rays[0], rays[1], near, far, 16, jit)
+            sig, rgbs = oracle.codenerf_decoder(sd, oracle.shapenet_swap(x / diag), oracle.shapenet_swap(v), shp0, tex0)
+            rgb, dep, acc = oracle.composite(sig.squeeze(-1), rgbs, z.unsqueeze(0).expand(x.shape[0], -1), False)
+            if shape is None:
+                assert rel_err(rgb, g["us_rgb"]) < TOL and rel_err(dep, g["us_depth"]) < TOL and rel_err(acc, g["us_acc"]) < TOL
+            else:
+                assert rel_err(rgb.reshape(*shape, 3), g["uf_img"]) < TOL and rel_err(dep.reshape(shape), g["uf_depth"]) < TOL
+        # renderer.render_rays_v3 (renderer.py:382-473): slab test on detached rays, 64 strata, adjust_scale, shapenet frame, black background
+        ro, vd = oracle.get_rays(K, cam0, g["roi"], uv_steps=[8, 8])
+        xyz, vdr, zv, _ = oracle.prepare_sampled_rays(ro, vd, wlh, 64, T(g["v3_jitter"]))
+        sig, rgbs = oracle.codenerf_decoder(sd, oracle.shapenet_swap(xyz * 1.1), oracle.shapenet_swap(vdr), shp0, tex0)
+        rgb, dep, acc = oracle.composite(sig.squeeze(-1), rgbs, zv, False)
+        assert rel_err(rgb, g["v3_rgb"]) < TOL and rel_err(dep, g["v3_depth"]) < TOL and rel_err(acc, g["v3_acc"]) < TOL
