@@ -11,8 +11,16 @@
 // Warp roles (576 threads): warps 0-7 epilogue group of slot 0, warps 8-15 of slot 1 (warp w owns TMEM lanes
 // 32*(w%4).. and the column half (w/4)%2 of every 64-column chunk), warp 16 weight producer (+ TMEM alloc), warp 17
 // MMA issuer.  Weights: pre-tiled bf16 images, [N rows][32 k] per stage (64-byte swizzle, K-major), streamed L2 ->
-// smem by cp.async.bulk through a 5-stage mbarrier ring.  No AUX operand buffer: PE(xyz) is written into the slot's
-// chunk 0, and encoding_viewdir runs as two accumulating steps (y part, then PE(viewdir) written into chunk 0).
+// smem by cp.async.bulk through an mbarrier ring.  PE(xyz) is written into the slot's chunk 0.
+//
+// Two variants of both kernels (template parameter CG2):
+//  * cta_group::1 (training mode with operand saves, or objects that do not own a multiple of 256 rows): M = 128 MMAs per CTA,
+//    5 stages of 16 KB, every stage fetched from L2 once per 2-CTA cluster (half per CTA, multicast); encoding_viewdir runs as
+//    two accumulating steps (y part, then PE(viewdir) written into chunk 0).
+//  * cta_group::2 (frozen weights: the default): ONE M = 256 MMA spans the CTA pair; each CTA holds its 128-row A operand and its
+//    half of every stage (8 stages of 8 KB); the leader CTA's MMA warp issues for both SMs and collects both CTAs' epilogue
+//    arrivals, the peer's MMA warp relays its stage completions; in the forward encoding_viewdir is one step whose last stage
+//    multiplies a per-slot PE(viewdir) tile.  Same arithmetic, bit-identical sigma / rgb (tests/test_gpu_bf16.py).
 #include "common.cuh"
 #include "handle.h"
 #include "tc_ptx.cuh"
