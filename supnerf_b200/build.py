@@ -59,7 +59,8 @@ def build(force=False, verbose=False):
         for _, err in results:
             sys.stderr.write(err)
     tmp = LIB + ".tmp"
-    r = subprocess.run([nvcc, "-shared", "-o", tmp] + [o for o, _ in results], capture_output=True, text=True)
+    # -cudart shared: the static runtime would embed the names of every runtime entry point in the .so
+    r = subprocess.run([nvcc, "-shared", "-cudart", "shared", "-o", tmp] + [o for o, _ in results], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     os.replace(tmp, LIB)

@@ -128,3 +128,22 @@ def test_reference_checkpoints_load_strict_and_round_trip():
             assert torch.equal(p_.detach(), sd[k])
     with pytest.raises(RuntimeError):
         snb.CodeNeRF().load_state_dict({"bogus.weight": torch.zeros(1)})
+
+
+def test_shipped_artefacts_do_not_name_batch_memcpy_entry_points():
+    """a statically linked CUDA runtime embeds the names of every runtime entry point, including the batched memcpy
+    calls the GPU pool refuses.  The library links the shared runtime; no binary that travels to the GPU box may carry the names."""
+    import subprocess
+    from supnerf_b200 import _lib
+    from supnerf_b200.build import build
+    build()
+    banned = re.compile(rb"cu(da)?Memcpy(3D)?BatchAsync")
+    tracked = subprocess.run(["git", "ls-files"], cwd=ROOT, capture_output=True, text=True).stdout.split()
+    paths = [_lib.LIB_PATH] + [os.path.join(ROOT, p) for p in tracked]
+    for p in paths:
+        if not os.path.isfile(p) or p.endswith("test_abi_exports.py") or os.path.basename(p) in ("ADVICE.md", "VERDICT.md"):
+            continue
+        with open(p, "rb") as f:
+            assert not banned.search(f.read()), p
+    with open(_lib.LIB_PATH, "rb") as f:
+        assert b"libcudart.so" in f.read()  # dynamic runtime

@@ -2,7 +2,7 @@
 // wait for the mbarrier, repeat.  mode 0: the issuing thread waits itself.  mode 1: a second warp waits for the commit,
 // does the fences an epilogue would (tcgen05.fence, fence.proxy.async) and arrives on a second mbarrier the issuer waits on
 // (the hand-shake of a fused MLP layer chain).  Prints cycles per round trip and the overhead over nb x 128 cycles.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 mma_latency.cu -o mma_latency
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared mma_latency.cu -o mma_latency
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>

@@ -1,6 +1,6 @@
 // Micro-benchmark: issue rate of tcgen05.mma kind::f16 (bf16, SS mode, 128B swizzle) on B200 for a few shapes.
 // Every CTA (one per SM) issues `iters` x 4 MMAs (K=16 each) over operands resident in shared memory, commits, waits.
-// Prints cycles per MMA instruction and the implied MAC/cycle/SM.   nvcc -arch=sm_100a -O3 mma_rate.cu -o mma_rate
+// Prints cycles per MMA instruction and the implied MAC/cycle/SM.   nvcc -arch=sm_100a -O3 -cudart shared mma_rate.cu -o mma_rate
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
