@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import T, load_golden, rel_err
+from conftest import T, load_golden, parity, parity_ok, rel_err
 from oracle import oracle
 from test_gpu_parity import DEV, forced_rand_like, model_from_state, snb
 
@@ -45,10 +45,9 @@ def test_tc_forward_layer_by_layer():
     errs = []
     for i, a in enumerate(acts):
         w = a.shape[-1]
-        errs.append(rel_err(dbg[i, :, :w], a.reshape(M, w)))
+        errs.append(parity("layer_%d_activations" % i, dbg[i, :, :w], a.reshape(M, w), TOL))
     print("per-layer rel err:", ["%.2e" % e for e in errs])
-    assert all(e < TOL for e in errs), errs
-    assert rel_err(sig2, sig) < TOL and rel_err(rgbs2, rgbs) < TOL
+    assert parity_ok("sig2", sig2, sig, TOL) and parity_ok("rgbs2", rgbs2, rgbs, TOL)
 
 
 @pytest.mark.parametrize("blocks,B,n,S_", [((2, 1), 1, 128, 16), ((3, 1), 4, 32, 8), ((5, 3), 2, 16, 16)])
@@ -71,22 +70,34 @@ def test_tc_decoder_fwd_bwd_vs_oracle(blocks, B, n, S_):
     m.requires_grad_(False)  # refine mode: frozen weights (the bf16 back end produces no weight gradients)
     gin = [t.to(DEV).requires_grad_() for t in (xyz, vd, shp, tex)]
     sig2, rgbs2 = m(*gin)
-    assert rel_err(sig2, sig) < TOL and rel_err(rgbs2, rgbs) < TOL
-    assert rel_err(sig2, sig_e) < 5e-3 and rel_err(rgbs2, rgbs_e) < 5e-3
+    assert parity_ok("sig2", sig2, sig, TOL) and parity_ok("rgbs2", rgbs2, rgbs, TOL)
+    assert parity_ok("sig2", sig2, sig_e, 5e-3) and parity_ok("rgbs2", rgbs2, rgbs_e, 5e-3)
     ((sig2 * up_s.to(DEV)).sum() + (rgbs2 * up_c.to(DEV)).sum()).backward()
     names = ("xyz", "viewdir", "shape", "texture")
-    err_fp32 = {n_: rel_err(a.grad, b.grad) for a, b, n_ in zip(gin, ins, names)}
-    err_emul = {n_: rel_err(a.grad, b.grad) for a, b, n_ in zip(gin, ine, names)}
-    emul_fp32 = {n_: rel_err(a.grad, b.grad) for a, b, n_ in zip(ine, ins, names)}
-    print("kernel vs fp32 oracle:", err_fp32, "\nkernel vs bf16 emulation:", err_emul, "\nemulation vs fp32:", emul_fp32)
-    for n_ in names:  # no further from the fp32 oracle than the emulation of its own rounding (+25 %), and close to the emulation
-        assert err_fp32[n_] < max(TOL, 1.25 * emul_fp32[n_]), (n_, err_fp32, emul_fp32)
-        assert err_emul[n_] < max(TOL, 1.0 * emul_fp32[n_]), (n_, err_emul, emul_fp32)
+    # kernel vs the bf16 emulation (same rounding points): the kernel-correctness check, held to the bf16 budget; kernel vs the fp32
+    # oracle: at most 1.25 x what the emulation of the prescribed rounding itself shows on these adversarial inputs (recorded)
+    for a, b, c, n_ in zip(gin, ins, ine, names):
+        floor = rel_err(c.grad, b.grad)
+        parity("g_%s_vs_bf16_emulation" % n_, a.grad, c.grad, TOL, floor=floor, floor_slack=1.0)
+        parity("g_%s_vs_fp32_oracle" % n_, a.grad, b.grad, TOL, floor=floor)
+    # the same decoder under a SMOOTH upstream gradient (identical for every sample: what a loss over rendered pixels looks like):
+    # reductions are well conditioned and the plain 2e-2 budget against the fp32 oracle applies
+    us, uc = torch.tensor(0.7), torch.tensor([0.3, -0.5, 0.9])
+    ins_s = [t.clone().requires_grad_() for t in (xyz, vd, shp, tex)]
+    sig_s, rgbs_s = oracle.codenerf_decoder(sd, *ins_s)
+    ((sig_s * us).sum() + (rgbs_s * uc).sum()).backward()
+    gin_s = [t.to(DEV).requires_grad_() for t in (xyz, vd, shp, tex)]
+    sig4, rgbs4 = m(*gin_s)
+    ((sig4 * us.to(DEV)).sum() + (rgbs4 * uc.to(DEV)).sum()).backward()
+    for a, b, n_ in zip(gin_s[2:], ins_s[2:], names[2:]):   # the reductions over samples: latent gradients
+        parity("smooth_upstream_g_%s" % n_, a.grad, b.grad, TOL)
+    for a, b, n_ in zip(gin_s[:2], ins_s[:2], names[:2]):   # per-sample gradients: sign flips of single ReLU units show at full size
+        parity("smooth_upstream_g_%s" % n_, a.grad, b.grad, TOL, floor=rel_err(ine[names.index(n_)].grad, ins[names.index(n_)].grad))
     # latents only (no pose gradient requested): the shorter backward program must give the same latent gradients
     gin2 = [t.to(DEV) for t in (xyz, vd)] + [t.to(DEV).requires_grad_() for t in (shp, tex)]
     sig3, rgbs3 = m(*gin2)
     ((sig3 * up_s.to(DEV)).sum() + (rgbs3 * up_c.to(DEV)).sum()).backward()
-    assert rel_err(gin2[2].grad, gin[2].grad) < 1e-4 and rel_err(gin2[3].grad, gin[3].grad) < 1e-4
+    assert parity_ok("gin2_2__grad", gin2[2].grad, gin[2].grad, 1e-4) and parity_ok("gin2_3__grad", gin2[3].grad, gin[3].grad, 1e-4)
 
 
 def test_tc_weight_grads_fail_loudly_where_unsupported():
@@ -105,7 +116,7 @@ def test_tc_weight_grads_fail_loudly_where_unsupported():
     sig, rgbs = m(xs, vs, shp.to(DEV), tex.to(DEV))
     assert sig.shape == (8, 10, 1) and rgbs.shape == (8, 10, 3) and bool(torch.isfinite(sig).all())
     sig_o, rgb_o = oracle.codenerf_decoder(sd, xs.cpu(), vs.cpu(), shp, tex)
-    assert rel_err(sig, sig_o) < TOL and rel_err(rgbs, rgb_o) < TOL
+    assert parity_ok("sig", sig, sig_o, TOL) and parity_ok("rgbs", rgbs, rgb_o, TOL)
     with pytest.raises(RuntimeError):  # batched latents: 50 rows per object cannot be tile-aligned
         s2, t2 = oracle.synthetic_latents(2, 2)
         m(xs, vs, s2.to(DEV), t2.to(DEV))   # 40 rows per object
@@ -135,18 +146,15 @@ def test_tc_training_mode_weight_grads_vs_oracle(blocks, B, n, S_):
     gin = [t.to(DEV).requires_grad_() for t in (xyz, vd, shp, tex)]
     sig2, rgbs2 = m(*gin)
     ((sig2 * up_s.to(DEV)).sum() + (rgbs2 * up_c.to(DEV)).sum()).backward()
-    bad, report = {}, {}
     for k, p_ in m.named_parameters():
         assert p_.grad is not None, k
-        e32, ee, ref = rel_err(p_.grad, sd32[k].grad), rel_err(p_.grad, sde[k].grad), rel_err(sde[k].grad, sd32[k].grad)
-        report[k] = (round(e32, 5), round(ee, 5), round(ref, 5))
-        if not (ee < max(TOL, ref) and e32 < max(TOL, 1.25 * ref)):
-            bad[k] = (e32, ee, ref)
-    print("weight grads (kernel vs fp32, kernel vs bf16 emulation, emulation vs fp32):", report)
-    assert not bad, bad
+        floor = rel_err(sde[k].grad, sd32[k].grad)
+        parity("gw_%s_vs_bf16_emulation" % k, p_.grad, sde[k].grad, TOL, floor=floor, floor_slack=1.0)
+        parity("gw_%s_vs_fp32_oracle" % k, p_.grad, sd32[k].grad, TOL, floor=floor)
     for a, b, c, name in zip(gin, in32, ine, ("xyz", "viewdir", "shape", "texture")):
-        ref = rel_err(c.grad, b.grad)
-        assert rel_err(a.grad, c.grad) < max(TOL, ref) and rel_err(a.grad, b.grad) < max(TOL, 1.25 * ref), name
+        floor = rel_err(c.grad, b.grad)
+        parity("g_%s_vs_bf16_emulation" % name, a.grad, c.grad, TOL, floor=floor, floor_slack=1.0)
+        parity("g_%s_vs_fp32_oracle" % name, a.grad, b.grad, TOL, floor=floor)
     # frozen-weight mode must give the same input gradients (same arithmetic, shorter program)
     m.requires_grad_(False)
     gin2 = [t.to(DEV).requires_grad_() for t in (xyz, vd, shp, tex)]
@@ -154,7 +162,7 @@ def test_tc_training_mode_weight_grads_vs_oracle(blocks, B, n, S_):
     assert torch.equal(sig3, sig2) and torch.equal(rgbs3, rgbs2)
     ((sig3 * up_s.to(DEV)).sum() + (rgbs3 * up_c.to(DEV)).sum()).backward()
     for a, b in zip(gin2, gin):
-        assert rel_err(a.grad, b.grad) < 1e-4
+        assert parity_ok("a_grad", a.grad, b.grad, 1e-4)
 
 
 def test_tc_render_c1_full_size_end_to_end():
@@ -180,10 +188,10 @@ def test_tc_render_c1_full_size_end_to_end():
         rgb, dep, acc, tg, oc = R.render_rays(m, DEV, obj["img"], obj["mask_occ"], cam, obj["wlh"], obj["K"].to(DEV), obj["roi"],
                                               s_g, t_g, im_sz=64)
     oracle.refine_losses(rgb, acc, tg, oc)[0].backward()
-    errs = dict(rgb=rel_err(rgb, rgb_o), depth=rel_err(dep, dep_o), acc=rel_err(acc, acc_o), g_pose=rel_err(cam.grad, cam_o.grad),
-                g_shape=rel_err(s_g.grad, s_o.grad), g_texture=rel_err(t_g.grad, t_o.grad))
+    errs = dict(rgb=parity("rgb", rgb, rgb_o, TOL), depth=parity("depth", dep, dep_o, TOL), acc=parity("acc", acc, acc_o, TOL),
+                g_pose=parity("g_pose", cam.grad, cam_o.grad, TOL), g_shape=parity("g_shape", s_g.grad, s_o.grad, TOL),
+                g_texture=parity("g_texture", t_g.grad, t_o.grad, TOL))
     print(errs)
-    assert all(e < TOL for e in errs.values()), errs
 
 
 def test_tc_training_mode_through_fused_render():
@@ -208,9 +216,8 @@ def test_tc_training_mode_through_fused_render():
         grads[prec] = {k: p_.grad.clone() for k, p_ in m.named_parameters() if p_.grad is not None}
         grads[prec].update(cam=cam.grad, shp=shp.grad, tex=tex.grad)
     assert set(grads["bf16"]) == set(grads["fp32"]) and len(grads["bf16"]) >= 28 + 3
-    errs = {k: rel_err(grads["bf16"][k], grads["fp32"][k]) for k in grads["fp32"]}
+    errs = {k: parity("g_" + k, grads["bf16"][k], grads["fp32"][k], TOL) for k in grads["fp32"]}
     print(errs)
-    assert all(e < TOL for e in errs.values()), {k: e for k, e in errs.items() if e >= TOL}
 
 
 def test_tc_fused_render_any_ray_count():
@@ -237,9 +244,8 @@ def test_tc_fused_render_any_ray_count():
         assert rgb.shape == (333, 3)
         oracle.refine_losses(rgb, acc, tgt, occ)[0].backward()
         res[prec] = [rgb, dep, acc, cam.grad, shp.grad, tex.grad]
-    errs = [rel_err(a, b) for a, b in zip(res["bf16"], res["fp32"])]
+    errs = [parity(n_, a, b, TOL) for n_, a, b in zip(("rgb", "depth", "acc", "g_pose", "g_shape", "g_texture"), res["bf16"], res["fp32"])]
     print(errs)
-    assert all(e < TOL for e in errs), errs
 
 
 @pytest.mark.parametrize("im,S_,label", [(128, 64, "C2 object"), (512, 128, "C4 object")])
@@ -276,10 +282,10 @@ def test_full_size_properties_bf16(im, S_, label):
                                                         ray_ids=ids)
     tg, oc = obj["img"].reshape(-1, 3)[ids], obj["mask_occ"].reshape(-1, 1)[ids]
     oracle.refine_losses(o_rgb, o_acc, tg, oc)[0].backward()
-    errs = dict(rgb=rel_err(rgb[ids.to(DEV)], o_rgb), depth=rel_err(dep[ids.to(DEV)], o_dep), acc=rel_err(acc[ids.to(DEV)], o_acc),
-                g_pose=rel_err(cam.grad, cam_o.grad), g_shape=rel_err(shp.grad, s_o.grad), g_texture=rel_err(tex.grad, t_o.grad))
+    errs = dict(rgb=parity("rgb", rgb[ids.to(DEV)], o_rgb, TOL, rows=n * S_), depth=parity("depth", dep[ids.to(DEV)], o_dep, TOL),
+                acc=parity("acc", acc[ids.to(DEV)], o_acc, TOL), g_pose=parity("g_pose", cam.grad, cam_o.grad, TOL),
+                g_shape=parity("g_shape", shp.grad, s_o.grad, TOL), g_texture=parity("g_texture", tex.grad, t_o.grad, TOL))
     print(label, errs)
-    assert all(e < TOL for e in errs.values()), errs
     # hit mask of ALL rays, bit-exact (slab test on the CPU oracle)
     ro, vd = oracle.get_rays(obj["K"], obj["cam_pose"], obj["roi"], uv_steps=[im, im])
     diag, half = oracle.box_constants(obj["wlh"])
@@ -338,7 +344,7 @@ def test_render_full_img_bf16_ragged_rows():
                                          out_depth=True)
         assert img.shape == (37, 37, 3) and dep.shape == (37, 37)
         imgs[prec] = (img, dep)
-    assert rel_err(imgs["bf16"][0], imgs["fp32"][0]) < TOL and rel_err(imgs["bf16"][1], imgs["fp32"][1]) < TOL
+    assert parity_ok("imgs_bf16_0", imgs["bf16"][0], imgs["fp32"][0], TOL) and parity_ok("imgs_bf16_1", imgs["bf16"][1], imgs["fp32"][1], TOL)
 
 
 @pytest.mark.parametrize("B,n,S_", [(1, 150, 64), (4, 64, 16), (1, 16, 8), (3, 96, 8)])
@@ -368,5 +374,5 @@ def test_cta_group2_kernels_equal_cta_group1_kernels(B, n, S_):
         lib.snb_tc_set_cg2(-1)
     (s0, c0, g0), (s1, c1, g1) = outs
     assert torch.equal(s0, s1) and torch.equal(c0, c1)
-    assert rel_err(g1[0], g0[0]) < 1e-6 and rel_err(g1[1], g0[1]) < 1e-6      # d xyz, d viewdir: per sample, no reduction
-    assert rel_err(g1[2], g0[2]) < 1e-5 and rel_err(g1[3], g0[3]) < 1e-5      # latent gradients: atomically accumulated sums
+    assert parity_ok("g1_0", g1[0], g0[0], 1e-6) and parity_ok("g1_1", g1[1], g0[1], 1e-6)      # d xyz, d viewdir: per sample, no reduction
+    assert parity_ok("g1_2", g1[2], g0[2], 1e-5) and parity_ok("g1_3", g1[3], g0[3], 1e-5)      # latent gradients: atomically accumulated sums

@@ -1,25 +1,27 @@
 """Every remaining public driver of SURVEY 8(b) (row a9) through the drop-in package on the GPU, against outputs of the UNMODIFIED
 reference (tests/golden/drivers.npz, made by tools/make_golden.py:golden_drivers): renderer.render_rays_v3, utils.render_rays /
 render_rays_specified / prepare_pixel_samples / render_full_img, NeRFRenderer.render_rays_specified / prepare_pixel_samples /
-render_full_img.  fp32 back end; tolerance: per-tensor max|a-b|/max|b| <= 1e-5 for renders and samples (north star), looser
-and stated below for the gradients that are ill-conditioned sums (pose)."""
+render_full_img.  fp32 back end; tolerance: per-tensor max|a-b|/max|b| <= 1e-5 for renders, samples AND gradients (north star).
+The pose / latent gradients are sums with heavy cancellation where the reference's own fp32 value is up to 5e-3 away from the
+exact one: for those the fixture tests/golden/drivers_truth64.npz holds the same reference drivers run in float64, and
+conftest.parity passes a gradient that is within 1e-5 of the fp32 reference OR no further from the fp64 truth than 1.5 x the
+fp32 reference itself.  Every measured error lands in profiles/parity_r2.json."""
 import numpy as np
 import pytest
 import torch
 
-from conftest import T, load_golden, rel_err
+from conftest import T, load_golden, parity, parity_ok, rel_err
 from oracle import oracle
 from test_gpu_parity import DEV, forced_rand_like, model_from_state, snb
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
-TOL_LATENT_GRAD = 1e-4   # sums over all samples of one object, fp32 in both implementations
-TOL_POSE_GRAD = 5e-3     # heavy cancellation: the reference's own fp32 value is only good to ~1e-3
 
 
 @pytest.fixture(scope="module")
 def ctx():
     g = load_golden("drivers")
+    g.update(load_golden("drivers_truth64"))
     S = snb()
     sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=int(g["seed"]))
     m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
@@ -35,13 +37,14 @@ def _leaves(g):
 
 def _check_render(got, g, pre):
     rgb, dep, acc, tgt, occ = got
-    assert rel_err(tgt, g[pre + "_tgt"]) < 1e-6 and torch.equal(occ.cpu(), T(g[pre + "_occ"]))
-    assert rel_err(rgb, g[pre + "_rgb"]) < TOL and rel_err(dep, g[pre + "_depth"]) < TOL and rel_err(acc, g[pre + "_acc"]) < TOL
+    assert parity_ok("tgt", tgt, g[pre + "_tgt"], 1e-6) and torch.equal(occ.cpu(), T(g[pre + "_occ"]))
+    for name, t in (("rgb", rgb), ("depth", dep), ("acc", acc)):
+        parity(pre + "_" + name, t, g[pre + "_" + name], TOL)
 
 
 def _check_grads(cam, shp, tex, g, pre):
-    assert rel_err(shp.grad, g[pre + "_g_shp"]) < TOL_LATENT_GRAD and rel_err(tex.grad, g[pre + "_g_tex"]) < TOL_LATENT_GRAD
-    assert rel_err(cam.grad, g[pre + "_g_cam"]) < TOL_POSE_GRAD
+    for name, t in (("g_cam", cam), ("g_shp", shp), ("g_tex", tex)):
+        parity(pre + "_" + name, t.grad, g[pre + "_" + name], TOL, truth=g[pre + "_" + name + "64"])
 
 
 def test_render_rays_v3_full_grid_and_random_subset(ctx):
@@ -52,7 +55,7 @@ def test_render_rays_v3_full_grid_and_random_subset(ctx):
                                         im_sz=8, n_rays=None, adjust_scale=1.1)
     _check_render(out, g, "v3")
     loss = oracle.refine_losses(out[0], out[2], out[3], out[4])[0]
-    assert rel_err(loss, g["v3_loss"]) < TOL
+    parity("v3_loss", loss, g["v3_loss"], TOL)
     loss.backward()
     _check_grads(cam, shp, tex, g, "v3")
     cam, shp, tex = _leaves(g)
@@ -76,13 +79,13 @@ def test_renderer_class_drivers_on_a_full_resolution_crop(ctx):
     np.random.seed(73)
     with forced_rand_like(T(g["rp_jitter"])):
         xyz, vd, zv, tgt, occ = R.prepare_pixel_samples(img, mask, T(g["cam_pose"], device=DEV), g["wlh"], T(g["K"]), roi, 40)
-    assert rel_err(xyz, g["rp_xyz"]) < TOL and rel_err(vd, g["rp_viewdir"]) < TOL and rel_err(zv, g["rp_z_vals"]) < TOL
-    assert rel_err(tgt, g["rp_tgt"]) < 1e-6 and torch.equal(occ.cpu(), T(g["rp_occ"]))
+    assert parity_ok("xyz", xyz, g["rp_xyz"], TOL) and parity_ok("vd", vd, g["rp_viewdir"], TOL) and parity_ok("zv", zv, g["rp_z_vals"], TOL)
+    assert parity_ok("tgt", tgt, g["rp_tgt"], 1e-6) and torch.equal(occ.cpu(), T(g["rp_occ"]))
     with torch.no_grad(), forced_rand_like(T(g["rf_jitter"])):
         im, dep = R.render_full_img(m, DEV, T(g["cam_pose"], device=DEV), g["wlh"], T(g["K"]), roi, T(g["shapecode"], device=DEV),
                                     T(g["texturecode"], device=DEV), out_depth=True)
     assert tuple(im.shape) == (10, 12, 3) and tuple(dep.shape) == (10, 12)
-    assert rel_err(im, g["rf_img"]) < TOL and rel_err(dep, g["rf_depth"]) < TOL
+    assert parity_ok("im", im, g["rf_img"], TOL) and parity_ok("dep", dep, g["rf_depth"], TOL)
 
 
 def test_utils_drivers_on_a_full_resolution_crop(ctx):
@@ -102,13 +105,13 @@ def test_utils_drivers_on_a_full_resolution_crop(ctx):
     np.random.seed(77)
     torch.manual_seed(77)
     xyz, vd, zv, tgt, occ = S.utils.prepare_pixel_samples(img, mask, T(g["cam_pose"], device=DEV), diag, T(g["K"]), roi, 40, 16, 1, 0)
-    assert rel_err(xyz, g["up_xyz"]) < TOL and rel_err(vd, g["up_viewdir"]) < TOL and rel_err(zv, g["up_z_vals"]) < TOL
-    assert rel_err(tgt, g["up_tgt"]) < 1e-6 and torch.equal(occ.cpu(), T(g["up_occ"]))
+    assert parity_ok("xyz", xyz, g["up_xyz"], TOL) and parity_ok("vd", vd, g["up_viewdir"], TOL) and parity_ok("zv", zv, g["up_z_vals"], TOL)
+    assert parity_ok("tgt", tgt, g["up_tgt"], 1e-6) and torch.equal(occ.cpu(), T(g["up_occ"]))
     torch.manual_seed(78)
     with torch.no_grad():
         im, dep = S.utils.render_full_img(m, DEV, T(g["cam_pose"], device=DEV), g["wlh"], T(g["K"]), roi, 16, T(g["shapecode"], device=DEV),
                                           T(g["texturecode"], device=DEV), 1, out_depth=True)
-    assert rel_err(im, g["uf_img"]) < TOL and rel_err(dep, g["uf_depth"]) < TOL
+    assert parity_ok("im", im, g["uf_img"], TOL) and parity_ok("dep", dep, g["uf_depth"], TOL)
 
 
 def test_autorf_decoder_fp32_back_end_golden():
@@ -120,13 +123,19 @@ def test_autorf_decoder_fp32_back_end_golden():
     m.precision = "fp32"
     ins = [T(g[k], device=DEV).requires_grad_() for k in ("xyz", "viewdir", "shapecode", "texturecode")]
     sig, rgbs = m(*ins)
-    assert rel_err(sig, g["sigmas"]) < TOL and rel_err(rgbs, g["rgbs"]) < TOL
+    parity("sigmas", sig, g["sigmas"], TOL)
+    parity("rgbs", rgbs, g["rgbs"], TOL)
     ((sig * T(g["up_sigma"], device=DEV)).sum() + (rgbs * T(g["up_rgb"], device=DEV)).sum()).backward()
-    for t, k in zip(ins, ("g_xyz", "g_viewdir", "g_shapecode", "g_texturecode")):
-        assert rel_err(t.grad, g[k]) < TOL, k
+    # fp64 truth of the same computation: the oracle (pinned to this fixture by tests/test_oracle_golden.py) in float64
+    sd64 = {k: v.double().requires_grad_() for k, v in sd.items()}
+    in64 = [T(g[k]).double().requires_grad_() for k in ("xyz", "viewdir", "shapecode", "texturecode")]
+    s64, c64 = oracle.autorf_decoder(sd64, *in64)
+    ((s64 * T(g["up_sigma"]).double()).sum() + (c64 * T(g["up_rgb"]).double()).sum()).backward()
+    for t, t64, k in zip(ins, in64, ("g_xyz", "g_viewdir", "g_shapecode", "g_texturecode")):
+        parity(k, t.grad, g[k], TOL, truth=t64.grad)
     for k, p_ in m.named_parameters():
         if "gw_" + k in g:
-            assert rel_err(p_.grad, g["gw_" + k]) < 1e-4, k   # sums over every sample, fp32 in a different order
+            parity("gw_" + k, p_.grad, g["gw_" + k], TOL, truth=sd64[k].grad)   # sums over every sample
 
 
 @pytest.mark.parametrize("blocks,B,n,S_", [((1, 2), 1, 40, 8), ((2, 3), 2, 24, 8), ((5, 5), 3, 16, 4)])
@@ -148,12 +157,17 @@ def test_autorf_decoder_block_counts_vs_oracle_all_grads(blocks, B, n, S_):
     m = model_from_state(S.AutoRF, sd, shape_blocks=blocks[0], texture_blocks=blocks[1])
     gin = [t.to(DEV).requires_grad_() for t in (xyz, vd, shp, tex)]
     sig2, rgbs2 = m(*gin)
-    assert rel_err(sig2, sig) < TOL and rel_err(rgbs2, rgbs) < TOL
+    parity("sigmas", sig2, sig, TOL)
+    parity("rgbs", rgbs2, rgbs, TOL)
     ((sig2 * up_s.to(DEV)).sum() + (rgbs2 * up_c.to(DEV)).sum()).backward()
-    for a, b, name in zip(gin, ins, ("xyz", "viewdir", "shape", "texture")):
-        assert rel_err(a.grad, b.grad) < 1e-4, name
+    sd64 = {k: v.double().requires_grad_() for k, v in sd.items()}
+    in64 = [t.double().requires_grad_() for t in (xyz, vd, shp, tex)]
+    s64, c64 = oracle.autorf_decoder(sd64, *in64, shape_blocks=blocks[0], texture_blocks=blocks[1])
+    ((s64 * up_s.double()).sum() + (c64 * up_c.double()).sum()).backward()
+    for a, b, c, name in zip(gin, ins, in64, ("xyz", "viewdir", "shape", "texture")):
+        parity("g_" + name, a.grad, b.grad, TOL, truth=c.grad)
     for k, p_ in m.named_parameters():
-        assert rel_err(p_.grad, sdr[k].grad) < 1e-4, k
+        parity("gw_" + k, p_.grad, sdr[k].grad, TOL, truth=sd64[k].grad)
 
 
 def test_kitti2nusc_rotation_and_symmetric_augmentation(ctx):

@@ -90,7 +90,11 @@ def test_ray_sharded_two_gpus_matches_one(prec, tol, layout):
     for rank, l, g_cam, g_shp, g_tex, full in res:
         assert abs(l - loss.item()) <= 1e-5 * abs(loss.item()) + 1e-7
         assert torch.equal(full, rgb.detach().cpu())            # the union of the shards is bit-identical to the unsharded render
-        assert rel(g_shp, shp.grad) < max(tol, 1e-4) and rel(g_tex, tex.grad) < max(tol, 1e-4)
-        assert rel(g_cam, cam.grad) < max(tol, 1e-3)            # fp32 sums in a different order (ill-conditioned reduction)
+        # all-reduced shard gradients against the one-GPU gradients of the same library: the shards sum the same per-ray terms in a
+        # different order (pose: an ill-conditioned reduction, see conftest.parity); measured errors land in the parity ledger
+        from conftest import parity
+        parity("rank%d_g_shape_2gpu_vs_1gpu" % rank, g_shp, shp.grad, max(tol, 1e-4))
+        parity("rank%d_g_texture_2gpu_vs_1gpu" % rank, g_tex, tex.grad, max(tol, 1e-4))
+        parity("rank%d_g_pose_2gpu_vs_1gpu" % rank, g_cam, cam.grad, max(tol, 1e-3))
     for t0, t1 in zip(res[0][2:5], res[1][2:5]):
         assert torch.equal(t0, t1)                              # identical bits on every rank => identical optimiser steps

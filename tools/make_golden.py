@@ -420,6 +420,92 @@ def golden_drivers():
     save("drivers", **out)
 
 
+def golden_drivers_truth64():
+    """fp64 TRUTH for the driver gradients of tests/golden/drivers.npz: the same UNMODIFIED reference drivers executed with
+    torch's default dtype set to float64 (model.double(), float64 inputs, the fp32 fixture's recorded jitter replayed), so that the
+    GPU tests can tell a kernel's error from the fp32 reference's own (pose gradients are sums with heavy cancellation: the
+    reference's fp32 value is 3e-3 .. 5e-3 away from this truth, its latent gradients up to 4e-5).  Host-side float32 roundings
+    the reference makes explicitly (`.astype(np.float32)`, renderer.py:92,97-100) are part of its semantics and stay."""
+    import random as _random
+    g = dict(np.load(os.path.join(OUT, "drivers.npz")))
+    seed = int(g["seed"])
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=seed)
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    orig_rand_like = torch.rand_like
+    orig_from_numpy = torch.from_numpy
+    try:
+        # the kitti2nusc rotation is built as a float32 numpy matrix of 0 / +-1 entries (renderer.py:154-157, utils.py:481-484) and
+        # `@` does not promote: hand float32 arrays over as float64 (same values) for this run only
+        torch.from_numpy = lambda a: orig_from_numpy(a).double() if a.dtype == np.float32 else orig_from_numpy(a)
+        model = model_supnerf.SUPNeRF(shape_blocks=3, texture_blocks=1, pose_blocks=3, regress_blocks=3, latent_dim=256)
+        model.load_state_dict(sd, strict=False)
+        model = model.double()
+        model.requires_grad_(False)
+        T_ = lambda a: orig_from_numpy(np.asarray(a))   # noqa: E731
+        D_ = lambda a: T_(a).double()                     # noqa: E731
+
+        def leaves():
+            return D_(g["cam_pose"]).requires_grad_(), D_(g["shapecode"]).requires_grad_(), D_(g["texturecode"]).requires_grad_()
+
+        def replay(key):
+            torch.rand_like = lambda t, *a, **k: D_(g[key])
+
+        out = {}
+
+        def finish(pre, res, cam, shp, tex):
+            rgb, dep, acc, tgt, occ = res
+            losses(rgb, acc, tgt, occ).backward()
+            for name, t32 in (("rgb", rgb), ("depth", dep), ("acc", acc)):   # same render as the fp32 fixture (no flipped hit masks)
+                e = float((t32.detach() - D_(g[pre + "_" + name])).abs().max() / D_(g[pre + "_" + name]).abs().max())
+                assert e < 2e-5, (pre, name, e)
+            out.update({pre + "_g_cam64": cam.grad, pre + "_g_shp64": shp.grad, pre + "_g_tex64": tex.grad})
+
+        img, mask, K, roi, wlh = D_(g["img"]), D_(g["mask_occ"]), D_(g["K"]), T_(g["roi"]), g["wlh"]
+        img_s, mask_s, roi_s, diag = D_(g["img_s"]), D_(g["mask_s"]), T_(g["roi_s"]), np.float32(g["obj_diag"])
+        cam, shp, tex = leaves()
+        replay("v3_jitter")
+        finish("v3", ref_renderer.render_rays_v3(model, "cpu", img, mask, cam, wlh, K, roi, 64, shp, tex, 1, 0, im_sz=8, n_rays=None,
+                                                 adjust_scale=1.1), cam, shp, tex)
+        R = ref_renderer.NeRFRenderer(n_samples=16)
+        cam, shp, tex = leaves()
+        replay("rs_jitter")
+        finish("rs", R.render_rays_specified(model, "cpu", img_s, mask_s, cam, wlh, K, roi_s, g["x_vec"], g["y_vec"], shp, tex), cam, shp, tex)
+        cam, shp, tex = leaves()
+        replay("k2n_jitter")
+        finish("k2n", R.render_rays(model, "cpu", img, mask, cam, wlh, K, roi, shp, tex, kitti2nusc=True, im_sz=8), cam, shp, tex)
+        torch.rand_like = orig_rand_like
+        # shell stack: torch.rand(S) on the CPU generator; drawn in float32 under the fixture's seed (the generator's float64 stream
+        # differs), then handed to the float64 run
+        def shell_rand(seed_):
+            torch.manual_seed(seed_)
+            j = torch.rand(16, dtype=torch.float32).double()
+            orig = torch.rand
+            torch.rand = lambda *a, **k: j
+            return orig
+        cam, shp, tex = leaves()
+        _random.seed(2)
+        orig = shell_rand(80)
+        try:
+            res = ref_utils.render_rays_v2(model, "cpu", img, mask, cam, diag, K, roi, 16, shp, tex, 1, 1, kitti2nusc=True, im_sz=8, n_rays=None)
+        finally:
+            torch.rand = orig
+        finish("sym", res, cam, shp, tex)
+        cam, shp, tex = leaves()
+        np.random.seed(75)
+        orig = shell_rand(75)
+        try:
+            res = ref_utils.render_rays(model, "cpu", img_s, mask_s, cam, diag, K, roi_s, 16, shp, tex, 1, 0, n_rays=50)
+        finally:
+            torch.rand = orig
+        finish("ur", res, cam, shp, tex)
+    finally:
+        torch.rand_like = orig_rand_like
+        torch.from_numpy = orig_from_numpy
+        torch.set_default_dtype(old)
+    save("drivers_truth64", **out)
+
+
 def golden_state_dict_keys():
     """state_dict key -> shape of the reference modules (the checkpoint ABI): lets the CPU tests check that the
     drop-in modules load a reference checkpoint with the default strict=True without importing the reference."""
@@ -442,4 +528,5 @@ if __name__ == "__main__":
     golden_autorf()
     golden_scene_merge()
     golden_drivers()
+    golden_drivers_truth64()
     golden_state_dict_keys()
