@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 N_OBJ, IM_SZ, N_SAMPLES = 16, 128, 64
 MAC_PER_SAMPLE = 449664  # decoder Bs=3, Bt=1, W=256
 METRIC = "rays/s fwd+bwd, CodeNeRF-MLP render"
+WORKLOAD = "configs[1]: AutoRF-mix (3/1/256) render fwd+bwd, 16 objects x 128x128 rays x 64 samples per GPU per step"
 
 
 def peaks():
@@ -416,6 +417,16 @@ def run_ours(args):
                 "note": "per object-iteration: elapsed / (4 objects x 50 iterations) (configs[2]: 4 objects per GPU), refine.run_objects"}
         except Exception as exc:
             refine_it = {"error": str(exc)}
+    # the collective-bearing modes of the north star (configs[3], configs[4]): run at every N (N = 1 anchors the strong-scaling curve)
+    modes = {}
+    if not args.skip_modes:
+        for key, fn in (("ray_sharded_c4", run_c4), ("dp_train_c5", run_c5)):
+            try:
+                modes[key] = fn(snb, dev, rank, world, args.steps, args.warmup, args.precision)
+            except Exception as exc:   # never lose the headline line over a secondary mode
+                import traceback
+                traceback.print_exc()
+                modes[key] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -423,10 +434,11 @@ def run_ours(args):
         return
     # the CPU arm is timed on rank 0 at N = 1 only (at N > 1 the other ranks' processes share the host cores)
     cpu = cpu_baseline(steps=3, warmup=1) if world == 1 else None
+    eager = gpu_eager_baseline(dev) if world == 1 else None
     line = {"metric": METRIC, "value": round(value, 1), "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: AutoRF-mix (3/1/256) render fwd+bwd, 16 objects x 128x128 rays x 64 samples per GPU per step",
+            "config": {"workload": WORKLOAD,
                        "objects_per_gpu": N_OBJ, "rays_per_object": n_rays, "samples_per_ray": N_SAMPLES, "weights": "frozen (refine mode)",
                        "grads": "cam_pose, shapecode, texturecode", "parallelism": "object-parallel x%d, no collective; every rank renders the same 16-object set" % world, "cuda_streams_per_gpu": len(streams),
                        "l2": "inputs larger than L2: per object ~45 MB of samples / decoder outputs / gradients and ~12 MB of ReLU masks stream through HBM, 16 objects per step",
@@ -434,11 +446,202 @@ def run_ours(args):
                        "precision": args.precision},
             "e2e": {"value": round(e2e_value, 1), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
-            "roofline_compositing": comp, "refine_iteration": refine_it, "gpu_launches": int(launches), "clocks": dict(clk.summary(), e2e_region=clk2.summary()), "roofline": roofline, "cpu_baseline": cpu}
+            "roofline_compositing": comp, "refine_iteration": refine_it, "gpu_launches": int(launches), "clocks": dict(clk.summary(), e2e_region=clk2.summary()), "roofline": roofline, "cpu_baseline": cpu, "gpu_eager_baseline": eager}
+    line.update(modes)
+    if modes:
+        line["multi_gpu_parity"] = "pass" if all(m.get("multi_gpu_parity", "pass") == "pass" and "error" not in m for m in modes.values()) else "FAIL"
     print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
-# ----------------------------------------------------------------------------------------------------- CPU arms
+# ----------------------------------------------------------------------------------------------------- collective-bearing modes
+def _maxr(x, dev, world, op="max"):
+    """max (or min) over ranks of a python float / list of floats."""
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor(x if isinstance(x, (list, tuple)) else [x], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.MIN)
+    out = [float(v) for v in t.tolist()]
+    return out if isinstance(x, (list, tuple)) else out[0]
+
+
+def run_c4(snb, dev, rank, world, steps, warmup, precision):
+    """configs[3]: ONE 512x512 object, 128 samples per ray, ray-sharded over the launched ranks (interleaved 128-ray tiles), weights /
+    pose / codes replicated, ONE NCCL all-reduce of [d cam_pose | d shapecode | d texturecode | loss] (525 floats) per step.  STRONG
+    scaling: total work fixed.  Self-checks what tests/test_gpu_multi.py asserts, on this very run, before timing."""
+    import torch.distributed as dist
+    from supnerf_b200 import parallel, synthetic
+    IM, S = 512, 128
+    obj = synthetic.synthetic_object(4, im_sz=IM)
+    sd = synthetic.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=4)
+    m = snb.SUPNeRF(3, 1, 3, 3, 256)
+    m.load_state_dict(sd)
+    m = m.to(dev)
+    m.precision = precision
+    m.requires_grad_(False)
+    R = snb.renderer.NeRFRenderer(n_samples=S)
+    shp0, tex0 = synthetic.synthetic_latents(4, 1)
+    img, mask, K = obj["img"].to(dev), obj["mask_occ"].to(dev), obj["K"].to(dev)
+
+    def leaves():
+        return obj["cam_pose"].to(dev).requires_grad_(), shp0.to(dev).requires_grad_(), tex0.to(dev).requires_grad_()
+
+    shard = parallel.RayShard(R, m, dev, img, mask, obj["wlh"], K, obj["roi"], IM, rank=rank, world=world, layout="interleaved")
+    whole = parallel.RayShard(R, m, dev, img, mask, obj["wlh"], K, obj["roi"], IM, rank=0, world=1, layout="interleaved", group=None)
+    # ---- parity, on this run: the sharded step against the SAME step on one rank (every rank renders the whole object once)
+    cam, shp, tex = leaves()
+    loss_s, rgb_s, _, _ = shard.step(cam, shp, tex, seed=1234)
+    g_sharded = torch.cat([cam.grad.reshape(-1), shp.grad.reshape(-1), tex.grad.reshape(-1)]).clone()
+    cam1, shp1, tex1 = leaves()
+    # one-rank reference: no collective (world 1 => allreduce_grads reduces over nothing)
+    from supnerf_b200 import losses, ops
+    jit = ops.jitter_fill(1234, IM * IM, S, dev)
+    rgb_1, dep_1, acc_1 = R._render_fused(m, dev, whole.px, whole.py, K, cam1, obj["wlh"], shp1, tex1, jitter=jit)
+    part = losses.refine_loss(rgb_1, acc_1, whole.rgb_tgt, whole.occ, 0.1, den=whole.den)[0]
+    part.backward()
+    g_one = torch.cat([cam1.grad.reshape(-1), shp1.grad.reshape(-1), tex1.grad.reshape(-1)])
+    full = parallel.gather_rays(rgb_s.detach(), IM * IM, S, layout="interleaved") if world > 1 else rgb_s.detach()
+
+    def rel(a, b):
+        return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+    checks = {"loss_rel_err_vs_1rank": abs(float(loss_s) - float(part)) / abs(float(part)),
+              "gathered_image_bit_identical": bool(torch.equal(full, rgb_1.detach())),
+              "g_pose_rel_err_vs_1rank": rel(g_sharded[:12], g_one[:12]), "g_shape_rel_err_vs_1rank": rel(g_sharded[12:268], g_one[12:268]),
+              "g_texture_rel_err_vs_1rank": rel(g_sharded[268:], g_one[268:])}
+    if world > 1:
+        gs = [torch.empty_like(g_sharded) for _ in range(world)]
+        dist.all_gather(gs, g_sharded)
+        checks["gradients_bit_identical_across_ranks"] = bool(all(torch.equal(gs[0], g) for g in gs[1:]))
+    else:
+        checks["gradients_bit_identical_across_ranks"] = True
+    tol_g = 2e-2 if precision == "bf16" else 1e-3
+    ok = (checks["loss_rel_err_vs_1rank"] <= 1e-5 and checks["gathered_image_bit_identical"] and checks["gradients_bit_identical_across_ranks"]
+          and checks["g_shape_rel_err_vs_1rank"] <= tol_g and checks["g_texture_rel_err_vs_1rank"] <= tol_g and checks["g_pose_rel_err_vs_1rank"] <= tol_g)
+    ok = bool(_maxr(0.0 if ok else 1.0, dev, world) == 0.0)
+    del rgb_1, dep_1, acc_1, jit, full
+
+    # ---- timing: K steps, phases marked with CUDA events on the launch stream
+    cam, shp, tex = leaves()
+    names = ("jitter", "forward", "backward", "allreduce")
+
+    def timed(sh, k, record):
+        evs = []
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(k):
+            row = [torch.cuda.Event(enable_timing=True)]
+            row[0].record()
+
+            def mark(name, row=row):
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                row.append(e)
+            loss = sh.step(cam, shp, tex, seed=1000 + i, events=mark if record else None)[0]
+            evs.append(row)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t1.record()
+        torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1) / k
+        phases = None
+        if record:
+            phases = [float(np.mean([r[j].elapsed_time(r[j + 1]) for r in evs])) for j in range(len(names))]
+        return ms, phases, float(loss)
+
+    for _ in range(max(warmup, 3)):
+        shard.step(cam, shp, tex, seed=1)
+    ms_plain, _, loss = timed(shard, steps, False)          # the number: no per-phase events inside
+    ms, phases, _ = timed(shard, steps, True)
+    ms_max = _maxr(ms_plain, dev, world)
+    ph_max = _maxr(phases, dev, world)
+    ph_min = _maxr(phases, dev, world, "min")
+    # one-GPU time of the same step IN THIS RUN (rank 0 alone renders the whole object; the other ranks wait)
+    ms_one = None
+    if world > 1:
+        if rank == 0:
+            for _ in range(2):
+                whole.step(cam, shp, tex, seed=1)
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for i in range(steps):
+                whole.step(cam, shp, tex, seed=1000 + i)
+            a1.record()
+            torch.cuda.synchronize()
+            ms_one = a0.elapsed_time(a1) / steps
+        ms_one = _maxr(ms_one if ms_one is not None else 0.0, dev, world)
+    n = IM * IM
+    out = {"config": "configs[3]: one 512x512 object x 128 samples, ray-sharded x%d (interleaved 128-ray tiles), one all-reduce of 525 floats per step" % world,
+           "scaling": "strong", "n_gpus": world, "ms_per_step": round(ms_max, 3), "rays_per_s": round(n / (ms_max / 1e3), 1),
+           "precision": precision, "loss": loss,
+           "one_gpu_ms_per_step_same_run": round(ms_one, 3) if ms_one else None,
+           "efficiency_vs_one_gpu_same_run": round(ms_one / (world * ms_max), 4) if ms_one else None,
+           "phases_ms_max_over_ranks": dict(zip(names, [round(v, 4) for v in ph_max])),
+           "phases_ms_min_over_ranks": dict(zip(names, [round(v, 4) for v in ph_min])),
+           "allreduce_us": round(1e3 * ph_max[3], 1),
+           "phase_note": "CUDA events on the launch stream in a second timed pass of the same K steps; `allreduce` = torch.cat of the three "
+                         "gradients + loss, ncclAllReduce(525 floats), views back; it also absorbs the wait for the slowest rank's backward",
+           "multi_gpu_parity": "pass" if ok else "FAIL", "parity_checks": checks}
+    return out
+
+
+def run_c5(snb, dev, rank, world, steps, warmup, precision):
+    raise NotImplementedError("configs[4] mode not wired yet")
+
+
+# ----------------------------------------------------------------------------------------------------- reference arms
+def load_reference():
+    """The UNMODIFIED reference staged under baseline/_ref/ by baseline/install_ref.py (its renderer.py / utils.py / model_*.py,
+    byte for byte; matplotlib, which utils.py imports for an off-path colour map, is stubbed).  None if it was not staged."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "renderer.py")):
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "baseline"))
+            import install_ref
+            if not install_ref.install(verbose=False):
+                return None
+        except Exception:
+            return None
+    import importlib
+    import types
+    sys.modules.setdefault("matplotlib", types.ModuleType("matplotlib"))
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    import warnings
+    warnings.filterwarnings("ignore")
+    mods = {name: importlib.import_module(name) for name in ("renderer", "model_autorf")}
+    mods["manifest"] = json.load(open(os.path.join(ref_dir, "MANIFEST.json")))["sha256"] if os.path.exists(os.path.join(ref_dir, "MANIFEST.json")) else None
+    return mods
+
+
+def reference_model(ref, device):
+    """The reference's own AutoRFMix(3, 1, 256) module with the bench's weights (same state_dict keys: decoder entries only)."""
+    from supnerf_b200 import synthetic
+    sd = synthetic.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=0)
+    m = ref["model_autorf"].AutoRFMix(shape_blocks=3, texture_blocks=1, latent_dim=256)
+    res = m.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    m = m.to(device)
+    m.requires_grad_(False)   # refine mode, as in the measured arm
+    return m
+
+
+def reference_step(ref, R, model, objs, device):
+    """One pass over `objs` through the reference's NeRFRenderer.render_rays (renderer.py:117-167) + the refine losses
+    (optimizer_nuscenes.py:729-736) + backward to pose and codes: the reference's stock code path, device = cpu or cuda."""
+    total = 0.0
+    for o in objs:
+        cam = o["cam_pose"].to(device).requires_grad_()
+        shp, tex = o["shapecode"].to(device).requires_grad_(), o["texturecode"].to(device).requires_grad_()
+        rgb, dep, acc, tgt, occ = R.render_rays(model, device, o["img"], o["mask_occ"], cam, o["wlh"], o["K"], o["roi"], shp, tex, im_sz=IM_SZ)
+        loss = refine_loss(rgb, acc, tgt, occ)
+        loss.backward()
+        total += float(loss.detach())
+    return total
+
+
 def cpu_render_step(oracle, sd, obj, jitter):
     cam = obj["cam_pose"].clone().requires_grad_()
     shp, tex = obj["shapecode"].clone().requires_grad_(), obj["texturecode"].clone().requires_grad_()
@@ -449,11 +652,37 @@ def cpu_render_step(oracle, sd, obj, jitter):
     return loss
 
 
-def cpu_baseline(steps, warmup, im_sz=64):
-    """The reference's algorithm (CPU oracle port) on the host cores: one object, im_sz^2 rays x 64 samples per step."""
-    from oracle import oracle
+CPU_SAMPLE_OBJECTS = 1   # objects of the 16-object set one CPU step renders (1 object = 16 384 rays x 64 samples = 1 M decoder rows)
+
+
+def cpu_baseline(steps, warmup):
+    """The reference's CPU path on the host cores, all threads: `kind: reference` = the unmodified reference (baseline/_ref) through
+    its own NeRFRenderer.render_rays on the first CPU_SAMPLE_OBJECTS objects of the SAME 16-object set at the same 128x128 rays x 64
+    samples; `kind: port` (only if the reference was not staged) = the oracle port on one 64x64-ray object."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    ref = load_reference()
+    if ref is not None:
+        model = reference_model(ref, "cpu")
+        R = ref["renderer"].NeRFRenderer(n_samples=N_SAMPLES)
+        objs = make_objects(100, N_OBJ, IM_SZ)[:CPU_SAMPLE_OBJECTS]
+        torch.manual_seed(0)
+        for _ in range(warmup):
+            reference_step(ref, R, model, objs, "cpu")
+        ts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            reference_step(ref, R, model, objs, "cpu")
+            ts.append(time.perf_counter() - t0)
+        sec = float(np.median(ts))
+        rays = len(objs) * IM_SZ * IM_SZ
+        return {"value": round(rays / sec, 1), "unit": "rays/s", "cores": cores, "kind": "reference", "rays_per_step": rays, "s_per_step": round(sec, 3),
+                "sample": "unmodified reference (baseline/_ref: renderer.NeRFRenderer.render_rays + model_autorf.AutoRFMix(3,1,256)), torch CPU fp32, "
+                          "%d of the 16 objects of configs[1] per step (%dx%d rays x %d samples each), fwd+bwd to pose+codes, weights frozen, "
+                          "%d steps (median %.2f s/step)" % (len(objs), IM_SZ, IM_SZ, N_SAMPLES, steps, sec),
+                "reference_sha256": ref["manifest"]}
+    from oracle import oracle
+    im_sz = 64
     sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=0)
     obj = make_objects(100, 1, im_sz)[0]
     jitter = torch.rand(im_sz * im_sz, N_SAMPLES, generator=torch.Generator().manual_seed(0))
@@ -465,9 +694,40 @@ def cpu_baseline(steps, warmup, im_sz=64):
         cpu_render_step(oracle, sd, obj, jitter)
         ts.append(time.perf_counter() - t0)
     sec = float(np.median(ts))
-    return {"value": round(im_sz * im_sz / sec, 1), "unit": "rays/s", "cores": cores, "kind": "port",
-            "sample": "1 object, %dx%d rays x %d samples, fwd+bwd to pose+latents, weights frozen, %d steps (median %.2f s/step)"
+    return {"value": round(im_sz * im_sz / sec, 1), "unit": "rays/s", "cores": cores, "kind": "port", "rays_per_step": im_sz * im_sz, "s_per_step": round(sec, 3),
+            "sample": "oracle port (reference not staged): 1 object, %dx%d rays x %d samples, fwd+bwd to pose+latents, weights frozen, %d steps (median %.2f s/step)"
                       % (im_sz, im_sz, N_SAMPLES, steps, sec)}
+
+
+def gpu_eager_baseline(dev, steps=3, warmup=2):
+    """The reference's own eager PyTorch path on the SAME B200 (SURVEY 8d / BASELINE.md section 4: "the real same-box bar"): the
+    unmodified reference with device='cuda', fp32, TF32 off (torch default), weights frozen, the full 16-object step of configs[1]."""
+    ref = load_reference()
+    if ref is None:
+        return {"unavailable": "reference not staged under baseline/_ref"}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    model = reference_model(ref, dev)
+    R = ref["renderer"].NeRFRenderer(n_samples=N_SAMPLES)
+    objs = make_objects(100, N_OBJ, IM_SZ)
+    for _ in range(warmup):
+        reference_step(ref, R, model, objs, dev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        reference_step(ref, R, model, objs, dev)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    peak_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    del model
+    torch.cuda.empty_cache()
+    return {"value": round(N_OBJ * IM_SZ * IM_SZ / (ms / 1e3), 1), "unit": "rays/s", "ms_per_step": round(ms, 3), "steps": steps, "warmup": warmup,
+            "kind": "reference", "device": torch.cuda.get_device_name(dev), "dtype": "f32 (allow_tf32 = False)",
+            "what": "unmodified reference (baseline/_ref) NeRFRenderer.render_rays + refine losses + backward, device='cuda', eager PyTorch, "
+                    "the same 16 objects x 128x128 rays x 64 samples per step, inputs as the reference takes them (host img / mask, .to(device) inside)",
+            "peak_memory_gib": round(peak_gb, 2)}
 
 
 def run_reference(args):
@@ -478,9 +738,11 @@ def run_reference(args):
     cpu = cpu_baseline(steps=steps, warmup=warmup)
     wall = time.perf_counter() - t0
     line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "rays/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
-            "steps": steps, "warmup": warmup, "ms_per_step": round(1e3 * 64 * 64 / cpu["value"], 3), "higher_is_better": True,
+            "steps": steps, "warmup": warmup, "ms_per_step": round(1e3 * cpu["s_per_step"], 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1] (AutoRF-mix 3/1/256 render fwd+bwd), bounded sample: " + cpu["sample"]},
+            "config": {"workload": WORKLOAD, "objects_per_gpu": N_OBJ, "rays_per_object": IM_SZ * IM_SZ, "samples_per_ray": N_SAMPLES,
+                       "weights": "frozen (refine mode)", "grads": "cam_pose, shapecode, texturecode",
+                       "bounded_sample": cpu["sample"]},
             "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": round(wall, 1)}
     print(json.dumps(line), file=JSON_OUT, flush=True)
@@ -501,6 +763,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--skip-modes", action="store_true", help="skip the configs[3] / configs[4] collective-bearing modes")
     ap.add_argument("--streams", type=int, default=3, help="CUDA streams the independent objects alternate over (1 = one stream)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -111,6 +111,12 @@ int snb_sample_shell_bwd(const float* z, int64_t n_rays, int32_t n_samples, floa
                          const float* g_xyz, const float* g_viewdir_rep,
                          float* g_rays_o, float* g_viewdir, void* stream);
 
+/* Counter-based stratified jitter for the ray-sharded mode (no reference counterpart: the reference draws the (N, S) jitter
+ * with one torch.rand_like, renderer.py:39-40, which a rank rendering a shard of the rays cannot slice without drawing all of
+ * it).  out[r][k] = Philox4x32-10(counter = (ray id, k / 4), key = seed)[k % 4] * 2^-24 in [0, 1): a pure function of
+ * (seed, ray id, k), so the union of the shards equals the one-GPU fill bit for bit.  ray_ids NULL = rays 0 .. n_rays-1. */
+int snb_jitter_fill(uint64_t seed, const int64_t* ray_ids, int64_t n_rays, int32_t n_samples, float* out, void* stream);
+
 /* ---- K2 / K2b: positional encoding + latent-conditioned decoder MLP -----------------------------
  * Replaces CodeNeRF.forward (model_codenerf.py:39-63) ≡ AutoRFMix.forward (model_autorf.py:226-250)
  * ≡ SUPNeRF.forward (model_supnerf.py:241-269), and AutoRF.forward (model_autorf.py:156-186).

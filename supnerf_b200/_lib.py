@@ -39,6 +39,7 @@ SIGNATURES = {
     "snb_sample_box_bwd": (c_i32, [c_f, c_f, c_f, c_f, c_i64, c_i32, c_flt, ctypes.POINTER(c_flt), c_f, c_f, c_f, c_f, c_f, c_f]),
     "snb_sample_shell_fwd": (c_i32, [c_f, c_f, c_f, c_i64, c_i32, c_flt, c_i32, c_f, c_f, c_f]),
     "snb_sample_shell_bwd": (c_i32, [c_f, c_i64, c_i32, c_flt, c_i32, c_f, c_f, c_f, c_f, c_f]),
+    "snb_jitter_fill": (c_i32, [ctypes.c_uint64, c_f, c_i64, c_i32, c_f, c_f]),
     "snb_create": (c_i32, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(SnbArch)]),
     "snb_destroy": (c_i32, [ctypes.c_void_p]),
     "snb_num_weight_tensors": (c_i32, [ctypes.c_void_p]),

@@ -9,7 +9,7 @@
 namespace snb {
 
 static thread_local char g_err[512] = "";
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -55,7 +55,7 @@ size_t tc_train_scratch_extra(const snb_handle_s* h, int64_t M);
 using namespace snb;
 
 extern "C" int snb_abi_version(void) { return SNB_ABI_VERSION; }
-extern "C" uint64_t snb_launch_count(void) { return g_launches; }
+extern "C" uint64_t snb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" const char* snb_last_error(void) { return g_err; }
 
 extern "C" int snb_device_info(int* sms, int* major, int* minor) {

@@ -1,6 +1,7 @@
 // Shared helpers for the supnerf_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -25,10 +26,10 @@ void set_error(const char* fmt, ...);
     }                                  \
   } while (0)
 
-extern unsigned long long g_launches;  // kernels launched by this library (all threads), for bench.py's gpu_launches
+extern std::atomic<unsigned long long> g_launches;  // kernels launched by this library (all host threads), for bench.py's gpu_launches
 #define SNB_LAUNCH_CHECK()            \
   do {                                \
-    ++snb::g_launches;                \
+    snb::g_launches.fetch_add(1, std::memory_order_relaxed); \
     SNB_CHECK_CUDA(cudaGetLastError()); \
   } while (0)
 

@@ -490,3 +490,56 @@ extern "C" int snb_sample_shell_bwd(const float* z, int64_t n_rays, int32_t n_sa
   SNB_LAUNCH_CHECK();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Counter-based stratified jitter: u[r][k] = Philox4x32-10(counter = (ray id, k / 4), key = seed)[k % 4] in [0, 1).
+// The reference draws the (N, S) jitter with ONE torch.rand_like on the device generator (renderer.py:39-40), whose stream
+// cannot be sliced: a rank that renders a shard of the rays would have to draw all N x S numbers (33.5 M at config C4) to
+// stay consistent with the other ranks.  A counter-based draw is a pure function of (seed, ray id, sample index): every rank
+// fills ONLY its rows and the union over the ranks equals the one-GPU draw bit for bit.  (Not the reference's random stream:
+// the tests that pin results to the reference feed the recorded jitter instead.)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace snb {
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+__global__ void __launch_bounds__(256) jitter_fill_kernel(uint64_t seed, const int64_t* __restrict__ ray_ids, int64_t n_rays, int n_samples,
+                                                        float* __restrict__ out) {
+  const int quads = (n_samples + 3) / 4;
+  const int64_t total = n_rays * quads;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / quads;
+    const int q = (int)(i - r * quads);
+    const uint64_t id = ray_ids ? (uint64_t)ray_ids[r] : (uint64_t)r;
+    const uint4 x = philox4x32_10(make_uint4((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)q, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float u[4] = {(float)(x.x >> 8) * 5.9604644775390625e-8f, (float)(x.y >> 8) * 5.9604644775390625e-8f,
+                        (float)(x.z >> 8) * 5.9604644775390625e-8f, (float)(x.w >> 8) * 5.9604644775390625e-8f};
+    float* dst = out + r * n_samples + 4 * q;
+    if ((n_samples & 3) == 0) *reinterpret_cast<float4*>(dst) = make_float4(u[0], u[1], u[2], u[3]);
+    else
+      for (int j = 0; j < 4 && 4 * q + j < n_samples; ++j) dst[j] = u[j];
+  }
+}
+}  // namespace snb
+
+extern "C" int snb_jitter_fill(uint64_t seed, const int64_t* ray_ids, int64_t n_rays, int32_t n_samples, float* out, void* stream) {
+  if (n_rays == 0) return 0;
+  SNB_REQUIRE(n_rays > 0 && n_samples >= 1 && out, "jitter_fill: bad arguments");
+  SNB_REQUIRE((n_samples & 3) != 0 || ((uintptr_t)out & 15) == 0, "jitter_fill: out must be 16-byte aligned");
+  const int64_t total = n_rays * ((n_samples + 3) / 4);
+  const int sms = sm_count();
+  SNB_REQUIRE(sms > 0, "jitter_fill: no CUDA device");
+  int64_t grid = (total + 255) / 256;
+  if (grid > (int64_t)sms * 16) grid = (int64_t)sms * 16;
+  jitter_fill_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(seed, ray_ids, n_rays, n_samples, out);
+  SNB_LAUNCH_CHECK();
+  return 0;
+}

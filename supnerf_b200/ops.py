@@ -184,6 +184,24 @@ class _SampleBox(torch.autograd.Function):
         return g_o, g_d, None, None, None, None
 
 
+def jitter_fill(seed, n_rays, n_samples, device, ray_ids=None):
+    """(n_rays, S) stratified jitter in [0, 1) as a pure function of (seed, ray id, sample index) (snb_jitter_fill: Philox4x32-10):
+    a rank of the ray-sharded mode fills only ITS rows (`ray_ids`: int64 ids of its rays) and the union over the ranks equals the
+    one-GPU fill bit for bit.  Not the reference's torch.rand_like stream."""
+    lib = _lib.load()
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("supnerf_b200 has no CPU path")
+    if ray_ids is not None:
+        require_cuda(ray_ids)
+        ray_ids = ray_ids.to(torch.int64).contiguous()
+        n_rays = ray_ids.numel()
+    out = torch.empty(int(n_rays), int(n_samples), device=device, dtype=torch.float32)
+    with on_device(device):
+        check(lib.snb_jitter_fill(int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(ray_ids), int(n_rays), int(n_samples), ptr(out), stream_ptr()), "snb_jitter_fill")
+    return out
+
+
 def sample_box(rays_o, viewdir, z_steps, jitter, half_diag, aabb_half):
     return _SampleBox.apply(rays_o, viewdir, z_steps, jitter, half_diag, aabb_half)
 

@@ -67,24 +67,24 @@ def refine_loss_sharded(rgb_rays, acc_rays, rgb_tgt, occ_pixels, occ_all, loss_o
     return losses.refine_loss(rgb_rays, acc_rays, rgb_tgt, occ_pixels, loss_occ_coef, den=den)[0]
 
 
-def allreduce_grads(params, loss=None, group=None):
+def allreduce_grads(params, loss=None, group=None, scale=None):
     """Sum the gradients of `params` (cam_pose, shapecode, texturecode, ...) and, if given, the partial loss over all ranks
-    with ONE all_reduce of one flat fp32 buffer (2.1 KB for 12 + 256 + 256 + 1 floats).  Writes the sums back into
-    ``p.grad`` and returns the global loss (a 0-dim tensor) or None."""
+    with ONE all_reduce of one flat fp32 buffer (2.1 KB for 12 + 256 + 256 + 1 floats): one gather kernel (torch.cat) in, the
+    collective, and the parameters' ``.grad`` become VIEWS of the reduced buffer (no copy back).  Returns the global loss
+    (a 0-dim tensor) or None."""
     flat = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params]
     if loss is not None:
         flat.append(loss.detach().reshape(1).float())
     buf = torch.cat(flat)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    if scale is not None:
+        buf.mul_(scale)          # one kernel over the flat buffer (data-parallel averaging)
     off = 0
     for p in params:
         n = p.numel()
-        g = buf[off:off + n].reshape(p.shape).to(p.dtype)
-        if p.grad is None:
-            p.grad = g.clone()
-        else:
-            p.grad.copy_(g)
+        g = buf[off:off + n].view(p.shape)
+        p.grad = g if g.dtype == p.dtype else g.to(p.dtype)
         off += n
     return buf[off] if loss is not None else None
 
@@ -98,22 +98,20 @@ def allreduce_weight_grads(model, group=None, average=True):
     params = [p for p in model.parameters() if p.grad is not None]
     if not params:
         return 0
-    allreduce_grads(params, None, group)
-    if average and dist.is_available() and dist.is_initialized():
-        g = dist.get_world_size(group)
-        if g > 1:
-            for p in params:
-                p.grad.div_(g)
+    g = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    allreduce_grads(params, None, group, scale=(1.0 / g) if (average and g > 1) else None)
     return sum(p.numel() for p in params)
 
 
 def render_rays_sharded(renderer, model, device, img, mask_occ, cam_pose, obj_sz, K, roi, shapecode, texturecode, im_sz=64,
-                        rank=None, world=None, layout="contiguous"):
+                        rank=None, world=None, layout="contiguous", jitter="torch", seed=None):
     """Ray-sharded NeRFRenderer.render_rays (renderer.py:117-167 semantics, `n_rays=None`): renders only this rank's rays --
     one contiguous ray tile (layout="contiguous", ray_shard) or every G-th 128-ray tile (layout="interleaved",
     ray_shard_indices: balanced decoder work under miss-ray compaction).  The (N,S) jitter is drawn in full on every rank
     (same generator state => same numbers as the single-GPU call) and sliced, so the union of the shards is bit-identical to
-    the unsharded render.
+    the unsharded render.  jitter="counter": only the shard's rows are filled, with the counter-based draw of ops.jitter_fill
+    (a pure function of (seed, ray id, sample): the union of the shards equals the world=1 call with the same seed bit for bit;
+    `seed` defaults to one draw from torch's CPU generator, identical on every rank when the ranks seed it identically).
     -> rgb, depth, acc, rgb_tgt, occ_pixels of the shard, plus occ_all (N,1) for the global loss denominator."""
     if rank is None:
         rank = dist.get_rank() if dist.is_initialized() else 0
@@ -124,7 +122,6 @@ def render_rays_sharded(renderer, model, device, img, mask_occ, cam_pose, obj_sz
     img, mask_occ = U._resize_targets(img, mask_occ, im_sz)
     n = px.numel()
     occ_all = mask_occ.reshape(-1, 1).to(device, non_blocking=True)
-    jitter = torch.rand_like(torch.empty(n, renderer.n_samples, device=device))
     if layout == "interleaved":
         sel = ray_shard_indices(n, renderer.n_samples, rank, world, device=device)
     elif layout == "contiguous":
@@ -132,10 +129,69 @@ def render_rays_sharded(renderer, model, device, img, mask_occ, cam_pose, obj_sz
         sel = slice(a, b)
     else:
         raise ValueError("layout must be 'contiguous' or 'interleaved'")
+    if jitter == "torch":
+        jit = torch.rand_like(torch.empty(n, renderer.n_samples, device=device))[sel].contiguous()
+    elif jitter == "counter":
+        from . import ops
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        ids = sel if torch.is_tensor(sel) else torch.arange(sel.start, sel.stop, dtype=torch.int64, device=device)
+        jit = ops.jitter_fill(seed, ids.numel(), renderer.n_samples, device, ray_ids=ids)
+    else:
+        raise ValueError("jitter must be 'torch' or 'counter'")
     rgb_tgt = img.reshape(-1, 3).to(device, non_blocking=True)[sel]
     rgb, dep, acc = renderer._render_fused(model, device, px[sel].contiguous(), py[sel].contiguous(), K, cam_pose, obj_sz, shapecode,
-                                           texturecode, jitter=jitter[sel].contiguous())
+                                           texturecode, jitter=jit)
     return rgb, dep, acc, rgb_tgt, occ_all[sel], occ_all
+
+
+class RayShard:
+    """One rank's share of a ray-sharded object, prepared ONCE (config C4's refine-style loop re-renders the same crop every
+    step): the shard's pixel coordinates, targets and mask, the global loss denominator and the flat gradient buffer are built
+    here, so a step is   jitter rows (counter-based) -> fused render of the shard -> partial loss over the global denominator ->
+    backward -> ONE all_reduce(sum) of [d cam_pose | d shapecode | d texturecode | loss]   with no per-step index arithmetic."""
+
+    def __init__(self, renderer, model, device, img, mask_occ, obj_sz, K, roi, im_sz, rank=None, world=None, layout="interleaved",
+                 group=None):
+        self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
+        self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        self.renderer, self.model, self.device, self.group = renderer, model, torch.device(device), group
+        self.obj_sz, self.K, self.layout = obj_sz, K.to(self.device), layout
+        dev = self.device
+        px, py = U._pixel_grid_on(dev, roi, [im_sz, im_sz])
+        img, mask_occ = U._resize_targets(img, mask_occ, im_sz)
+        self.n_rays, S = px.numel(), renderer.n_samples
+        if layout == "interleaved":
+            self.ids = ray_shard_indices(self.n_rays, S, self.rank, self.world, device=dev)
+        elif layout == "contiguous":
+            a, b = ray_shard(self.n_rays, S, self.rank, self.world)
+            self.ids = torch.arange(a, b, dtype=torch.int64, device=dev)
+        else:
+            raise ValueError("layout must be 'contiguous' or 'interleaved'")
+        occ_all = mask_occ.reshape(-1, 1).to(dev)
+        self.den = torch.sum(torch.abs(occ_all)) + 1e-9          # global denominator: a function of the input mask only
+        self.px, self.py = px[self.ids].contiguous(), py[self.ids].contiguous()
+        self.rgb_tgt = img.reshape(-1, 3).to(dev)[self.ids].contiguous()
+        self.occ = occ_all[self.ids].contiguous()
+        self.flat = None
+
+    def step(self, cam_pose, shapecode, texturecode, seed, loss_occ_coef=0.1, events=None):
+        """-> (global loss, rgb, depth, acc of the shard); afterwards cam_pose.grad / shapecode.grad / texturecode.grad hold the
+        all-reduced gradients (views of one flat buffer).  `events`: optional callable(name) the bench uses to mark phases."""
+        from . import losses, ops
+        mark = events if events is not None else (lambda name: None)
+        jit = ops.jitter_fill(seed, self.ids.numel(), self.renderer.n_samples, self.device, ray_ids=self.ids)
+        mark("jitter")
+        rgb, dep, acc = self.renderer._render_fused(self.model, self.device, self.px, self.py, self.K, cam_pose, self.obj_sz, shapecode,
+                                                    texturecode, jitter=jit)
+        part = losses.refine_loss(rgb, acc, self.rgb_tgt, self.occ, loss_occ_coef, den=self.den)[0]
+        mark("forward")
+        cam_pose.grad = shapecode.grad = texturecode.grad = None
+        part.backward()
+        mark("backward")
+        loss = allreduce_grads([cam_pose, shapecode, texturecode], part, self.group)
+        mark("allreduce")
+        return loss, rgb, dep, acc
 
 
 def gather_rays(t, n_rays, n_samples, group=None, layout="contiguous"):

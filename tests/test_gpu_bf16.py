@@ -91,8 +91,15 @@ def test_tc_decoder_fwd_bwd_vs_oracle(blocks, B, n, S_):
     ((sig4 * us.to(DEV)).sum() + (rgbs4 * uc.to(DEV)).sum()).backward()
     for a, b, n_ in zip(gin_s[2:], ins_s[2:], names[2:]):   # the reductions over samples: latent gradients
         parity("smooth_upstream_g_%s" % n_, a.grad, b.grad, TOL)
-    for a, b, n_ in zip(gin_s[:2], ins_s[:2], names[:2]):   # per-sample gradients: sign flips of single ReLU units show at full size
-        parity("smooth_upstream_g_%s" % n_, a.grad, b.grad, TOL, floor=rel_err(ine[names.index(n_)].grad, ins[names.index(n_)].grad))
+    ine_s = [t.clone().requires_grad_() for t in (xyz, vd, shp, tex)]
+    sig_es, rgbs_es = oracle.codenerf_decoder_bf16(sd, *ine_s)
+    ((sig_es * us).sum() + (rgbs_es * uc).sum()).backward()
+    for a, b, c, n_ in zip(gin_s[:2], ins_s[:2], ine_s[:2], names[:2]):
+        # PER-SAMPLE gradients (no reduction): a single ReLU unit whose sign flips under bf16 rounding changes one sample's
+        # gradient at full size (the 2^9 PE frequency multiplies it), so max|a-b|/max|b| sits at 10-20 % for ANY bf16 MLP
+        # (the emulation's own figure is recorded); the quantities the path returns are their sums over samples (pose gradient),
+        # held to 2e-2 in the render tests below
+        parity("smooth_upstream_g_%s" % n_, a.grad, b.grad, TOL, floor=rel_err(c.grad, b.grad), floor_slack=1.5)
     # latents only (no pose gradient requested): the shorter backward program must give the same latent gradients
     gin2 = [t.to(DEV) for t in (xyz, vd)] + [t.to(DEV).requires_grad_() for t in (shp, tex)]
     sig3, rgbs3 = m(*gin2)
