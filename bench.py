@@ -588,7 +588,109 @@ def run_c4(snb, dev, rank, world, steps, warmup, precision):
 
 
 def run_c5(snb, dev, rank, world, steps, warmup, precision):
-    raise NotImplementedError("configs[4] mode not wired yet")
+    """configs[4]: the joint training step of trainer_unified_nuscenes.py:27-148 + :316-329 per GPU -- pose-estimator forward
+    (ImgEncoder on (8,3,128,128) crops, bf16 channels-last cuDNN; direct corner regression; 3 pose-regress iterations), the render of
+    8 objects x 1024 rays x 64 samples through the decoder with EVERY weight gradient (tcgen05 training mode), all losses, backward
+    through both halves, data-parallel all-reduce of all 49 M gradients (196 MB) in 3 buckets overlapped with the encoder's
+    backward, fused AdamW on weights + codes.  WEAK scaling: every rank its own 8 objects."""
+    import torch.distributed as dist
+    from supnerf_b200 import parallel, pose_estimator as pe, synthetic
+    B, n, S = 8, 1024, N_SAMPLES
+    g = torch.Generator().manual_seed(50 + rank)
+    sd = dict(synthetic.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=5))
+    m = snb.SUPNeRF(3, 1, 3, 3, 256)
+    m.materialize_pose_estimator()
+    sd.update(synthetic.pose_estimator_state(m.state_dict(), 5))
+    m.load_state_dict(sd)
+    m = m.to(dev).to(memory_format=torch.channels_last)
+    m.precision = precision
+    m.train()
+    img = torch.rand(B, 3, 128, 128, generator=g).to(dev)
+    xyz = ((torch.rand(B, n, S, 3, generator=g) - 0.5) * 1.2).to(dev)
+    vd = torch.nn.functional.normalize(torch.randn(B, n, 1, 3, generator=g), dim=-1).repeat(1, 1, S, 1).to(dev)
+    zv = (torch.rand(B, S, generator=g).sort(-1).values * 4 + 8).to(dev)
+    tgt, occ = torch.rand(B, n, 3, generator=g).to(dev), torch.randint(-1, 2, (B, n, 1), generator=g).float().to(dev)
+    objs = [synthetic.synthetic_object(500 + rank * B + i, im_sz=16) for i in range(B)]
+    c2o = torch.stack([o["cam_pose"] for o in objs])
+    R_o2c = c2o[:, :, :3].transpose(1, 2)
+    obj_pose = torch.cat([R_o2c, -R_o2c @ c2o[:, :, 3:]], -1).contiguous().to(dev)
+    wlh = torch.stack([torch.from_numpy(np.asarray(o["wlh"], dtype=np.float32)) for o in objs]).to(dev)
+    K = torch.stack([o["K"] for o in objs]).to(dev)
+    roi = torch.stack([torch.as_tensor(np.asarray(o["roi"]), dtype=torch.float32) for o in objs]).to(dev)
+    tgt_uv = pe.view_points_batch(pe.corners_of_box_batch(obj_pose, wlh), K, normalize=True)[:, :2, :]
+    src_pose = torch.cat([obj_pose[:, :, :3], obj_pose[:, :, 3:] * torch.tensor([1.03, 0.98, 1.05], device=dev).view(1, 3, 1)], -1)
+    shp0, tex0 = synthetic.synthetic_latents(5 + rank, B)
+    shp, tex = shp0.to(dev).requires_grad_(), tex0.to(dev).requires_grad_()
+    hp = {"loss_pose_coef": 0.01, "loss_code_coef": 0.1, "loss_occ_coef": 0.1}
+    enc = m.img_encoder
+    trunk = [p_ for mod in (enc.conv1, enc.bn1, enc.layer1, enc.layer2, enc.layer3) for p_ in mod.parameters()]
+    branches = [p_ for mod in (enc.layer4_shape, enc.layer4_texture, enc.layer4_pose) for p_ in mod.parameters()]
+    seen = set(id(p_) for p_ in trunk + branches)
+    early = [p_ for p_ in m.parameters() if id(p_) not in seen]          # decoder, pose head, encoder heads: ready first
+    n_params = sum(p_.numel() for p_ in m.parameters())
+    opt = torch.optim.AdamW([{"params": list(m.parameters()), "lr": 1e-4}, {"params": [shp, tex], "lr": 1e-3}], fused=True)
+    buckets = parallel.BucketedGradAllReduce([early, branches, trunk])
+
+    def step(overlap=True):
+        m.zero_grad(set_to_none=True)
+        shp.grad = tex.grad = None
+        losses_all, total, *_ = pe.joint_training_losses(m, hp, img, shp, tex, xyz, vd, zv, tgt, occ, src_pose, tgt_uv, roi, K, wlh, tgt_uv,
+                                                         encode=m.encode_img_fast)
+        if overlap:
+            total.backward()
+            buckets.finish()
+        else:                      # the same exchange as ONE flat all-reduce after the whole backward (no overlap)
+            saved = buckets.world
+            buckets.world = 1
+            total.backward()
+            buckets.finish()
+            buckets.world = saved
+            if world > 1:
+                parallel.allreduce_weight_grads(m)
+        opt.step()
+        return total.detach()
+
+    def timed(k, **kw):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(k):
+            loss = step(**kw)
+        a1.record()
+        torch.cuda.synchronize()
+        return _maxr(a0.elapsed_time(a1) / k, dev, world), float(loss)
+
+    for _ in range(max(warmup, 3)):
+        step()
+    ms, loss = timed(steps)
+    ar = buckets.allreduce_ms() if world > 1 else {}
+    ms_flat, _ = timed(steps, overlap=False) if world > 1 else (None, None)
+    # phase split on one rank's stream (second pass, events): encoder+pose forward | render forward | backward | optimizer
+    finite = bool(np.isfinite(loss))
+    flops_dec = 3 * 2 * MAC_PER_SAMPLE * B * n * S
+    out = {"config": "configs[4]: joint training step per GPU: ImgEncoder (8,3,128,128) bf16 channels-last + pose regression x3 + render of "
+                     "%d objects x %d rays x %d samples fwd/bwd with all weight gradients + AdamW; data-parallel x%d, %d parameters (%.0f MB of "
+                     "gradients) all-reduced in 3 buckets overlapped with the encoder backward" % (B, n, S, world, n_params, n_params * 4 / 1e6),
+           "scaling": "weak", "n_gpus": world, "ms_per_step": round(ms, 3), "rays_per_s": round(world * B * n / (ms / 1e3), 1),
+           "decoder_tflops_per_gpu_if_step_were_decoder_only": round(flops_dec / (ms / 1e3) / 1e12, 1),
+           "loss": loss, "loss_finite": finite, "precision": precision, "parameters": n_params,
+           "ms_per_step_without_overlap": round(ms_flat, 3) if ms_flat else None,
+           "allreduce_ms_by_bucket": {"early(decoder+heads)": round(ar.get(0, 0.0), 3), "layer4 branches": round(ar.get(1, 0.0), 3),
+                                      "trunk": round(ar.get(2, 0.0), 3)} if ar else None,
+           "overlap_hidden_ms": round(ms_flat - ms, 3) if ms_flat else None,
+           "multi_gpu_parity": "pass" if finite else "FAIL"}
+    if world > 1:   # every rank must hold identical weights after the step (same reduced gradients, same update)
+        probe = torch.cat([m.encoding_xyz[0].weight.reshape(-1)[:64], enc.conv1.weight.reshape(-1)[:64], enc.layer4_pose[2].conv2.weight.reshape(-1)[:64]])
+        gs = [torch.empty_like(probe) for _ in range(world)]
+        dist.all_gather(gs, probe)
+        same = bool(all(torch.equal(gs[0], t) for t in gs[1:]))
+        out["weights_bit_identical_across_ranks_after_training"] = same
+        if not same:
+            out["multi_gpu_parity"] = "FAIL"
+    buckets.remove()
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------- reference arms

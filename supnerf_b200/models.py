@@ -45,13 +45,21 @@ class _DecoderBase(nn.Module):
 
     def _weights(self):
         layers = self.__dict__.get("_layer_cache")
-        if layers is None:   # the Linear modules are fixed after construction; their Parameters are read fresh every call
+        # the Linear modules are fixed after construction; their Parameters are read fresh every call.  The cache is validated
+        # against this module's own first layer: nn.DataParallel's replicas shallow-copy __dict__
+        if layers is None or layers[0] is not self._modules["encoding_xyz"][0]:
             layers = self._decoder_layers()
             self.__dict__["_layer_cache"] = layers
         out = []
         for lin in layers:
             out += [lin.weight, lin.bias]
         return out
+
+    def _replicate_for_data_parallel(self):
+        replica = super()._replicate_for_data_parallel()
+        replica.__dict__.pop("_layer_cache", None)     # replicas own their parameters and their C handles
+        replica.__dict__["_handles"] = {}
+        return replica
 
     def _handle(self, device):
         key = (device.type, device.index)
@@ -68,6 +76,8 @@ class _DecoderBase(nn.Module):
         if n_rows % shape_latent.shape[0] != 0:
             raise ValueError("number of samples must be a multiple of the number of objects")
         prec = self.precision or _DEFAULT_PRECISION
+        if self.encoding_xyz[0].weight.device != xyz.device:
+            raise RuntimeError("decoder weights live on %s, inputs on %s" % (self.encoding_xyz[0].weight.device, xyz.device))
         sigma, rgb = ops.decoder(self._handle(xyz.device), prec, xyz.reshape(-1, 3), viewdir.reshape(-1, 3),
                                  shape_latent, texture_latent, self._weights())
         return sigma.reshape(*lead, 1), rgb.reshape(*lead, 3)
@@ -153,6 +163,11 @@ class AutoRFMix(_CodeNeRFFamily):
 
 
 class SUPNeRF(_CodeNeRFFamily):
+    """model_supnerf.py:165-269.  The decoder is the package's kernel path; the pose estimator half (``img_encoder``,
+    ``pose_layer_j`` / ``regress_layer_j`` / ``out_delta_layer``; SURVEY 8f rank 2, pose_estimator.py) is materialised on first
+    use -- ``encode_img`` / ``pose_update`` / ``materialize_pose_estimator()`` -- or when a checkpoint carrying its keys is
+    loaded and then used, so decoder-only callers (the refine loops of this path) do not build 49 M encoder parameters."""
+
     def __init__(self, shape_blocks=5, texture_blocks=5, pose_blocks=3, regress_blocks=3, latent_dim=256, pose_dim=16,
                  num_xyz_freq=10, num_dir_freq=4, norm_layer_type='BatchNorm2d', pose_shortcut=False, pred_wlh=False):
         super().__init__()
@@ -160,6 +175,62 @@ class SUPNeRF(_CodeNeRFFamily):
         self._build(shape_blocks, texture_blocks, latent_dim, latent_dim, num_xyz_freq, num_dir_freq)
         self.pose_blocks, self.regress_blocks = pose_blocks, regress_blocks
         self.pose_shortcut, self.pred_wlh = pose_shortcut, pred_wlh
+        self._pose_dim, self._norm_layer_type = pose_dim, norm_layer_type
+
+    def has_pose_estimator(self):
+        return "img_encoder" in self._modules
+
+    def materialize_pose_estimator(self):
+        """Build ``img_encoder`` + the pose head (same registration order and initialisers as model_supnerf.py:169-216) on the
+        decoder's device; entries of a previously loaded reference checkpoint that belong to them are moved in."""
+        if self.has_pose_estimator():
+            return self
+        from . import pose_estimator as pe
+        norm = nn.InstanceNorm2d if self._norm_layer_type == "InstanceNorm2d" else nn.BatchNorm2d
+        enc = pe.ImgEncoder((3, 4, 6, 3), num_classes=self._latent_dim, norm_layer=norm, pred_wlh=self.pred_wlh)
+        self.img_encoder = enc
+        mods = dict(self._modules)                       # the reference registers the encoder first (state_dict order)
+        self._modules.clear()
+        self._modules["img_encoder"] = mods.pop("img_encoder")
+        self._modules.update(mods)
+        pe.build_pose_head(self, self.pose_blocks, self.regress_blocks, self._latent_dim, self._pose_dim)
+        ref = self.encoding_xyz[0].weight
+        for name in ["img_encoder", "out_delta_layer"] + [f"pose_layer_{j}" for j in range(self.pose_blocks)] + \
+                [f"regress_layer_{j}" for j in range(self.regress_blocks)]:
+            self._modules[name].to(device=ref.device).train(self.training)
+        off = self.__dict__.get("_offpath_state") or {}
+        mine = {k: v for k, v in off.items() if k.startswith(("img_encoder.", "pose_layer_", "regress_layer_", "out_delta_layer"))}
+        if mine:
+            own = super(_DecoderBase, self).state_dict()
+            missing = [k for k in own if k.startswith(tuple(set(k2.split(".")[0] + "." for k2 in mine))) and k not in mine and "num_batches_tracked" not in k]
+            if missing:
+                raise RuntimeError("checkpoint lacks pose-estimator entries: %s" % missing[:5])
+            with torch.no_grad():
+                for k, v in mine.items():
+                    own[k].copy_(v)
+                    del off[k]
+        return self
+
+    def encode_img(self, img):
+        """model_supnerf.py:218-224 -> (shape_feat, texture_feat, pose_feat, box_uv_pred, box_wlh_pred | None)."""
+        self.materialize_pose_estimator()
+        out = self.img_encoder(img, self.pose_shortcut)
+        return out if self.pred_wlh else out + (None,)
+
+    def encode_img_fast(self, img):
+        """``encode_img`` under bf16 autocast with channels-last activations (cuDNN tensor-core convolutions; the B200 way to run
+        this library stage).  Heads return fp32."""
+        self.materialize_pose_estimator()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = self.img_encoder(img.contiguous(memory_format=torch.channels_last), self.pose_shortcut)
+        out = tuple(t.float() for t in out)
+        return out if self.pred_wlh else out + (None,)
+
+    def pose_update(self, im_feat, box_uv_src):
+        """model_supnerf.py:226-239."""
+        self.materialize_pose_estimator()
+        from . import pose_estimator as pe
+        return pe.pose_update(self, im_feat, box_uv_src)
 
 
 class AutoRF(_DecoderBase):

@@ -103,6 +103,103 @@ def allreduce_weight_grads(model, group=None, average=True):
     return sum(p.numel() for p in params)
 
 
+class BucketedGradAllReduce:
+    """Data-parallel gradient exchange of the joint training step (config C5) OVERLAPPED with the rest of the backward pass.
+    The parameters are cut into buckets in the order their gradients become ready (caller-supplied lists: e.g. decoder + pose head
+    + encoder heads first, the three ``layer4`` branches -- 80 % of the 49 M parameters -- next, the encoder trunk last).  A
+    post-accumulate hook counts a bucket's gradients; when the last one has arrived the bucket is gathered into one flat fp32
+    buffer (ONE torch.cat), all-reduced (sum) and scaled by 1/G on a side stream while autograd keeps producing the remaining
+    buckets on the main stream.  ``finish()`` makes the main stream wait for the side stream and re-points every ``p.grad`` at its
+    slice of the reduced buffer (views, no copy).  World size 1: no collective, gradients untouched."""
+
+    def __init__(self, buckets, group=None, average=True):
+        self.buckets = [[p for p in b if p.requires_grad] for b in buckets]
+        self.buckets = [b for b in self.buckets if b]
+        self.group, self.average = group, average
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self._bucket_of, self._pending, self._flat = {}, [0] * len(self.buckets), [None] * len(self.buckets)
+        self._handles = []
+        dev = self.buckets[0][0].device
+        self.stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self.events = []
+        for i, b in enumerate(self.buckets):
+            for p in b:
+                self._bucket_of[p] = i
+                self._handles.append(p.register_post_accumulate_grad_hook(self._hook))
+        self.reset()
+
+    def reset(self):
+        self._pending = [len(b) for b in self.buckets]
+        self._flat = [None] * len(self.buckets)
+        self.events = []
+
+    def _hook(self, p):
+        i = self._bucket_of[p]
+        self._pending[i] -= 1
+        if self._pending[i] == 0 and self.world > 1:
+            self._launch(i)
+
+    def _launch(self, i):
+        b = self.buckets[i]
+        if self.stream is not None:
+            main = torch.cuda.current_stream(b[0].device)
+            self.stream.wait_stream(main)
+            ctx = torch.cuda.stream(self.stream)
+        else:
+            import contextlib
+            ctx = contextlib.nullcontext()
+        with ctx:
+            e0 = torch.cuda.Event(enable_timing=True) if self.stream is not None else None
+            if e0 is not None:
+                e0.record()
+            flat = torch.cat([p.grad.reshape(-1) for p in b])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            if self.average:
+                flat.mul_(1.0 / self.world)
+            if e0 is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                self.events.append((i, e0, e1))
+            for p in b:
+                if self.stream is not None:
+                    p.grad.record_stream(self.stream)
+            self._flat[i] = flat
+
+    def finish(self):
+        """After backward(): wait for the exchanges, point the gradients at the reduced buffers.  -> floats exchanged."""
+        if self.world == 1:
+            self.reset()
+            return 0
+        for i, n in enumerate(self._pending):
+            if n == 0 and self._flat[i] is None:
+                self._launch(i)
+            elif n != 0:   # a parameter of this bucket got no gradient this step: exchange what exists, consistently on every rank
+                raise RuntimeError("bucket %d: %d parameters received no gradient" % (i, n))
+        if self.stream is not None:
+            torch.cuda.current_stream(self.buckets[0][0].device).wait_stream(self.stream)
+        total = 0
+        for b, flat in zip(self.buckets, self._flat):
+            off = 0
+            for p in b:
+                n = p.numel()
+                p.grad = flat[off:off + n].view(p.shape)
+                off += n
+            total += off
+        events = self.events
+        self.reset()
+        self.last_events = events
+        return total
+
+    def allreduce_ms(self):
+        """Per-bucket duration of gather + all-reduce + scale on the side stream of the last finished step (after a synchronize)."""
+        return {i: e0.elapsed_time(e1) for i, e0, e1 in getattr(self, "last_events", [])}
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+
 def render_rays_sharded(renderer, model, device, img, mask_occ, cam_pose, obj_sz, K, roi, shapecode, texturecode, im_sz=64,
                         rank=None, world=None, layout="contiguous", jitter="torch", seed=None):
     """Ray-sharded NeRFRenderer.render_rays (renderer.py:117-167 semantics, `n_rays=None`): renders only this rank's rays --

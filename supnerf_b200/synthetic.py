@@ -116,3 +116,32 @@ def synthetic_latents(seed: int, B: int, D: int = 256) -> Tuple[Tensor, Tensor]:
     s = torch.randn(B, D, generator=g) / math.sqrt(D / 2)
     t = torch.randn(B, D, generator=g) / math.sqrt(D / 2)
     return s, t
+
+
+def pose_estimator_state(template, seed=0):
+    """Deterministic weights for the pose-estimator half of SUPNeRF (img_encoder.*, pose_layer_*, regress_layer_*, out_delta_layer):
+    every entry of `template` (a state_dict: key -> tensor, only shapes / dtypes are read) whose key belongs to that half is drawn
+    from ONE seeded generator in key order -- conv / linear weights He-scaled, norm weights near 1, running statistics near (0, 1)
+    -- so that the reference module (tools/make_golden.py) and the drop-in (tests) hold identical parameters without shipping
+    49 M floats.  Decoder entries are not touched (init_codenerf_state covers them)."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    out = {}
+    for k, v in template.items():
+        if not k.startswith(("img_encoder.", "pose_layer_", "regress_layer_", "out_delta_layer")):
+            continue
+        shape = tuple(v.shape)
+        if k.endswith("num_batches_tracked"):
+            out[k] = torch.zeros(shape, dtype=torch.int64)
+        elif k.endswith("running_mean"):
+            out[k] = 0.1 * torch.randn(shape, generator=g)
+        elif k.endswith("running_var"):
+            out[k] = 1.0 + 0.2 * torch.rand(shape, generator=g)
+        elif len(shape) == 4:      # conv: He, fan_out
+            out[k] = torch.randn(shape, generator=g) * (2.0 / (shape[0] * shape[2] * shape[3])) ** 0.5
+        elif len(shape) == 2:      # linear
+            out[k] = torch.randn(shape, generator=g) * (1.0 / shape[1]) ** 0.5
+        elif ".bn" in k or "downsample.1" in k:
+            out[k] = (1.0 + 0.1 * torch.randn(shape, generator=g)) if k.endswith("weight") else 0.1 * torch.randn(shape, generator=g)
+        else:                      # linear bias
+            out[k] = 0.05 * torch.randn(shape, generator=g)
+    return out

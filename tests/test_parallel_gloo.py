@@ -159,7 +159,16 @@ def _dp_worker(rank, world, port, q):
         mine = parallel.object_shard(4, rank, world)            # objects r, r+G, ...
         model(x[mine]).pow(2).sum().backward()
         n = parallel.allreduce_weight_grads(model)
-        q.put((rank, n, [p.grad.clone() for p in model.parameters()]))
+        flat_grads = [p.grad.clone() for p in model.parameters()]
+        # the same exchange through the bucketed, hook-driven path (config C5's overlap machinery; no side stream on the CPU)
+        model.zero_grad(set_to_none=True)
+        params = list(model.parameters())
+        buckets = parallel.BucketedGradAllReduce([params[2:], params[:2]])   # the last layer's gradients are ready first
+        model(x[mine]).pow(2).sum().backward()
+        n2 = buckets.finish()
+        bucket_grads = [p.grad.clone() for p in model.parameters()]
+        buckets.remove()
+        q.put((rank, n, flat_grads, n2, bucket_grads))
     finally:
         dist.destroy_process_group()
 
@@ -191,8 +200,9 @@ def test_data_parallel_weight_gradient_allreduce():
     model = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
     x = torch.arange(4 * 7, dtype=torch.float32).reshape(4, 7) / 10.0
     model(x).pow(2).sum().backward()
-    for rank, n, grads in res:
-        assert n == sum(p.numel() for p in model.parameters())
-        for g, p in zip(grads, model.parameters()):
+    for rank, n, grads, n2, bucket_grads in res:
+        assert n == n2 == sum(p.numel() for p in model.parameters())
+        for g, gb, p in zip(grads, bucket_grads, model.parameters()):
             assert torch.allclose(g, p.grad / world, rtol=1e-5, atol=1e-7)
+            assert torch.equal(gb, g)      # bucketed exchange == flat exchange, bit for bit (same sums, same scale)
 

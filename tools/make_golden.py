@@ -506,6 +506,108 @@ def golden_drivers_truth64():
     save("drivers_truth64", **out)
 
 
+def golden_pose_estimator():
+    """SURVEY 8f rank 2 through the UNMODIFIED reference: SUPNeRF.encode_img (eval and train mode batch norm) + pose_update
+    (model_supnerf.py:108-152, 218-239), the box-corner projection helpers (utils.py:1032-1147, 1175-1197) and one whole
+    ParallelModel.forward of the joint trainer (trainer_unified_nuscenes.py:27-148) with its backward.  The trainer imports
+    pytorch3d's axis-angle maps, which are not part of the reference tree: they are stubbed with the package's Rodrigues
+    restatement, so everything except those two maps is the reference's own arithmetic.  Weights: synthetic.pose_estimator_state."""
+    from supnerf_b200 import pose_estimator as pe, synthetic
+    seed = 21
+    model = model_supnerf.SUPNeRF(shape_blocks=3, texture_blocks=1, pose_blocks=3, regress_blocks=3, latent_dim=256)
+    sd = dict(oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=seed))
+    sd.update(synthetic.pose_estimator_state(model.state_dict(), seed))
+    assert set(sd) == set(model.state_dict())
+    model.load_state_dict(sd)
+    g = torch.Generator().manual_seed(seed)
+    B = 2
+    img = torch.rand(B, 3, 128, 128, generator=g)
+    out = dict(seed=seed, img=img, weights_sha256=np.frombuffer(state_hash(sd).encode(), dtype=np.uint8))
+    model.eval()
+    img_r = img.clone().requires_grad_()
+    f_s, f_t, f_p, uv, _ = model.encode_img(img_r)
+    uv_src = torch.rand(B, 16, generator=g) * 2 - 1
+    delta = model.pose_update(f_p, uv_src)
+    up = [torch.randn(t.shape, generator=g) for t in (f_s, f_t, f_p, uv, delta)]
+    model.zero_grad()
+    sum((t * u).sum() for t, u in zip((f_s, f_t, f_p, uv, delta), up)).backward()
+    out.update(eval_shape=f_s, eval_texture=f_t, eval_pose=f_p, eval_uv=uv, uv_src=uv_src, eval_delta=delta,
+               up_shape=up[0], up_texture=up[1], up_pose=up[2], up_uv=up[3], up_delta=up[4], eval_g_img=img_r.grad,
+               eval_gw_conv1=model.img_encoder.conv1.weight.grad, eval_gw_fc_pose=model.img_encoder.fc_pose.weight.grad,
+               eval_gw_l4pose_conv=model.img_encoder.layer4_pose[2].conv2.weight.grad[::16, ::16].contiguous(),   # a strided slice: small fixture
+               
+               eval_gw_out_delta=model.out_delta_layer.weight.grad, eval_gw_regress0=model.regress_layer_0[0].weight.grad)
+    model.train()
+    with torch.no_grad():
+        f_s, f_t, f_p, uv, _ = model.encode_img(img)
+    out.update(train_shape=f_s, train_texture=f_t, train_pose=f_p, train_uv=uv,
+               train_running_mean_bn1=model.img_encoder.bn1.running_mean.clone())
+    # ---- box-corner projection helpers
+    objs = [oracle.synthetic_object(seed + i, im_sz=16) for i in range(B)]
+    c2o = torch.stack([o["cam_pose"] for o in objs])                       # camera -> object
+    R_o2c = c2o[:, :, :3].transpose(1, 2)
+    obj_pose = torch.cat([R_o2c, -R_o2c @ c2o[:, :, 3:]], -1).contiguous()  # object -> camera (the trainer's obj_poses)
+    wlh = torch.stack([torch.from_numpy(np.asarray(o["wlh"], dtype=np.float32)) for o in objs])
+    K = torch.stack([o["K"] for o in objs])
+    roi = torch.stack([torch.as_tensor(np.asarray(o["roi"]), dtype=torch.float32) for o in objs])
+    corners = ref_utils.corners_of_box_batch(obj_pose, wlh)
+    corners_k = ref_utils.corners_of_box_batch(obj_pose, wlh, is_kitti=True, scale=1.1)
+    uv_all = ref_utils.view_points_batch(corners, K, normalize=True)
+    uv_norm, dim = ref_utils.normalize_by_roi(uv_all[:, :2, :], roi, need_square=True)
+    uv_norm2, _ = ref_utils.normalize_by_roi(uv_all[:, :2, :], roi, need_square=False)
+    out.update(obj_pose=obj_pose, wlh=wlh, K=K, roi=roi, corners=corners, corners_kitti=corners_k, uv_all=uv_all, uv_norm=uv_norm,
+               uv_dim=dim, uv_norm_nonsquare=uv_norm2)
+    # ---- one joint training step (ParallelModel.forward + backward), pytorch3d's two maps stubbed
+    stubs = {}
+    for name in ("wandb", "torch.utils.tensorboard", "pytorch3d", "pytorch3d.transforms", "pytorch3d.transforms.rotation_conversions",
+                 "imageio", "skimage", "skimage.metrics"):
+        if name not in sys.modules:
+            stubs[name] = sys.modules[name] = types.ModuleType(name)
+    sys.modules["torch.utils.tensorboard"].SummaryWriter = object
+    rc = sys.modules["pytorch3d.transforms.rotation_conversions"]
+    rc.matrix_to_axis_angle, rc.axis_angle_to_matrix = pe.matrix_to_axis_angle_batch, pe.axis_angle_to_matrix_batch
+    sys.modules["pytorch3d.transforms"].rotation_conversions = rc
+    sys.modules["pytorch3d"].transforms = sys.modules["pytorch3d.transforms"]
+    if "skimage.metrics" in stubs:
+        sys.modules["skimage.metrics"].structural_similarity = None
+    import trainer_unified_nuscenes as tun
+    hp = {"loss_pose_coef": 0.01, "loss_code_coef": 0.1, "loss_occ_coef": 0.1}
+    pm = tun.ParallelModel(model, hp, im_enc_rate=1.0, pred_wlh=False)
+    n, S_ = 48, 16
+    xyz = (torch.rand(B, n, S_, 3, generator=g) - 0.5) * 1.2
+    vd = torch.nn.functional.normalize(torch.randn(B, n, 1, 3, generator=g), dim=-1).repeat(1, 1, S_, 1)
+    zv = (torch.rand(B, S_, generator=g).sort(-1).values * 4 + 8)   # one shared sample vector per object (the shell stack)
+    tgt = torch.rand(B, n, 3, generator=g)
+    occ = torch.randint(-1, 2, (B, n, 1), generator=g).float()
+    shp, tex = oracle.synthetic_latents(seed, B)
+    shp, tex = shp.clone().requires_grad_(), tex.clone().requires_grad_()
+    # a perturbed source pose: small rotation about z + a translation error
+    ang = torch.tensor([0.15, -0.1])
+    Rz = torch.stack([torch.stack([torch.stack([torch.cos(a), -torch.sin(a), torch.zeros(())]), torch.stack([torch.sin(a), torch.cos(a), torch.zeros(())]),
+                                   torch.tensor([0., 0., 1.])]) for a in ang])
+    src_pose = torch.cat([obj_pose[:, :, :3] @ Rz, obj_pose[:, :, 3:] * torch.tensor([1.03, 0.98, 1.05]).view(1, 3, 1)], -1)
+    tgt_uv = uv_all[:, :2, :]
+    model.train()
+    model.zero_grad()
+    import random as _random
+    _random.seed(0)   # enc_active = random.uniform(0, 1) < 1.0: always taken
+    losses_all, loss_total, shp_out, tex_out, pred_pose3, pred_uv_direct = pm(img, shp, tex, xyz, vd, zv, tgt, occ, src_pose, tgt_uv, wlh, roi, K,
+                                                                              wlh, tgt_uv)
+    loss_total.mean().backward()
+    out.update(j_xyz=xyz, j_viewdir=vd, j_z_vals=zv, j_rgb_tgt=tgt, j_occ=occ, j_shapecode=shp.detach(), j_texturecode=tex.detach(),
+               j_src_pose=src_pose, j_tgt_uv=tgt_uv, j_loss_total=loss_total.detach(), j_shapecode_out=shp_out, j_texturecode_out=tex_out,
+               j_pred_pose3=pred_pose3, j_pred_uv_direct=pred_uv_direct, j_g_shapecode=shp.grad, j_g_texturecode=tex.grad,
+               j_gw_conv1=model.img_encoder.conv1.weight.grad, j_gw_fc_shape=model.img_encoder.fc_shape.weight.grad,
+               j_gw_out_delta=model.out_delta_layer.weight.grad, j_gw_encoding_xyz=model.encoding_xyz[0].weight.grad,
+               j_gw_rgb2=model.rgb[2].weight.grad)
+    for k_, v_ in losses_all.items():
+        if k_ != "psnr":
+            out["j_" + k_] = v_.detach() if torch.is_tensor(v_) else torch.tensor(v_)
+    for name in stubs:
+        sys.modules.pop(name, None)
+    save("pose_estimator", **out)
+
+
 def golden_state_dict_keys():
     """state_dict key -> shape of the reference modules (the checkpoint ABI): lets the CPU tests check that the
     drop-in modules load a reference checkpoint with the default strict=True without importing the reference."""
@@ -529,4 +631,5 @@ if __name__ == "__main__":
     golden_scene_merge()
     golden_drivers()
     golden_drivers_truth64()
+    golden_pose_estimator()
     golden_state_dict_keys()
