@@ -139,7 +139,9 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints a banner)
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a short collective timeout: a mismatched collective must fail in minutes, not hold the GPUs for the default 10
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=150))
     lib = _lib.load()
 
     sd = synthetic.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=0)

@@ -67,7 +67,7 @@ def refine_loss_sharded(rgb_rays, acc_rays, rgb_tgt, occ_pixels, occ_all, loss_o
     return losses.refine_loss(rgb_rays, acc_rays, rgb_tgt, occ_pixels, loss_occ_coef, den=den)[0]
 
 
-def allreduce_grads(params, loss=None, group=None, scale=None):
+def allreduce_grads(params, loss=None, group=None, scale=None, collective=True):
     """Sum the gradients of `params` (cam_pose, shapecode, texturecode, ...) and, if given, the partial loss over all ranks
     with ONE all_reduce of one flat fp32 buffer (2.1 KB for 12 + 256 + 256 + 1 floats): one gather kernel (torch.cat) in, the
     collective, and the parameters' ``.grad`` become VIEWS of the reduced buffer (no copy back).  Returns the global loss
@@ -76,7 +76,7 @@ def allreduce_grads(params, loss=None, group=None, scale=None):
     if loss is not None:
         flat.append(loss.detach().reshape(1).float())
     buf = torch.cat(flat)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    if collective and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     if scale is not None:
         buf.mul_(scale)          # one kernel over the flat buffer (data-parallel averaging)
@@ -286,7 +286,8 @@ class RayShard:
         cam_pose.grad = shapecode.grad = texturecode.grad = None
         part.backward()
         mark("backward")
-        loss = allreduce_grads([cam_pose, shapecode, texturecode], part, self.group)
+        # a RayShard built with world=1 (the one-GPU anchor of a multi-rank run) must not enter a collective the other ranks skip
+        loss = allreduce_grads([cam_pose, shapecode, texturecode], part, self.group, collective=self.world > 1)
         mark("allreduce")
         return loss, rgb, dep, acc
 

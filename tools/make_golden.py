@@ -603,6 +603,31 @@ def golden_pose_estimator():
     for k_, v_ in losses_all.items():
         if k_ != "psnr":
             out["j_" + k_] = v_.detach() if torch.is_tensor(v_) else torch.tensor(v_)
+    # ---- the same joint step in float64 (default dtype float64, model.double(), float32 numpy constants handed over as float64):
+    # the TRUTH for its gradients (sums over all samples with cancellation: see conftest.parity)
+    old_dt = torch.get_default_dtype()
+    orig_from_numpy = torch.from_numpy
+    torch.set_default_dtype(torch.float64)
+    torch.from_numpy = lambda a: orig_from_numpy(a).double() if a.dtype == np.float32 else orig_from_numpy(a)
+    try:
+        model64 = model_supnerf.SUPNeRF(shape_blocks=3, texture_blocks=1, pose_blocks=3, regress_blocks=3, latent_dim=256)
+        model64.load_state_dict(sd)
+        model64 = model64.double()
+        model64.train()
+        pm64 = tun.ParallelModel(model64, hp, im_enc_rate=1.0, pred_wlh=False)
+        shp64, tex64 = shp.detach().double().requires_grad_(), tex.detach().double().requires_grad_()
+        D_ = lambda t: t.detach().double()   # noqa: E731
+        _random.seed(0)
+        _, total64, *_ = pm64(D_(img), shp64, tex64, D_(xyz), D_(vd), D_(zv), D_(tgt), D_(occ), D_(src_pose), D_(tgt_uv), D_(wlh), D_(roi), D_(K),
+                              D_(wlh), D_(tgt_uv))
+        total64.mean().backward()
+        e64 = model64.img_encoder
+        out.update(j64_loss_total=total64.detach(), j64_g_shapecode=shp64.grad, j64_g_texturecode=tex64.grad,
+                   j64_gw_conv1=e64.conv1.weight.grad, j64_gw_fc_shape=e64.fc_shape.weight.grad, j64_gw_out_delta=model64.out_delta_layer.weight.grad,
+                   j64_gw_encoding_xyz=model64.encoding_xyz[0].weight.grad, j64_gw_rgb2=model64.rgb[2].weight.grad)
+    finally:
+        torch.from_numpy = orig_from_numpy
+        torch.set_default_dtype(old_dt)
     for name in stubs:
         sys.modules.pop(name, None)
     save("pose_estimator", **out)
