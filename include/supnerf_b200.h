@@ -208,6 +208,43 @@ int snb_render_bwd(snb_handle h, const snb_render_desc* d, const float* px, cons
                    const float* g_acc, void* scratch, float* g_c2w, float* g_shape_latent, float* g_texture_latent,
                    float* const* g_weights, void* stream);
 
+/* ---- batched fused box render: ONE launch set for n_objs objects -----------------------------------------------------
+ * The loops that call NeRFRenderer.render_rays once per object (optimizer_nuscenes.py:716-726 over the objects of a scene;
+ * configs[1]: 16 objects per step) become two C calls for the whole batch.  Same arithmetic per object as snb_render_fwd / bwd
+ * in SNB_RENDER_BOX mode with miss-ray compaction; frozen weights, bf16 decoder.  Every object brings rays_per_obj rays.
+ *   px, py (B,N) pixel coordinates; K (B,3,3); c2w (B,3,4); box (B,4) = {diag/2, l/diag, w/diag, h/diag} per object
+ *   (renderer.py:92-100, rounded to float32 on the host as the reference does); z_steps (S); jitter (B,N,S);
+ *   shape_latent / texture_latent (B,D).  Outputs rgb (B,N,3), depth (B,N), acc (B,N), hit (B,N; may be NULL).
+ *   workspace: snb_render_batch_workspace_bytes, 256-byte aligned, kept until the backward; scratch likewise.
+ *   Backward: g_rgb (B,N,3), g_depth / g_acc (B,N; NULL = zero) -> g_c2w (B,3,4; NULL = not wanted), g_shape_latent,
+ *   g_texture_latent (B,D). */
+typedef struct snb_batch_desc {
+  int32_t n_objs;
+  int32_t n_samples;
+  int64_t rays_per_obj;
+  int32_t flags;        /* SNB_WHITE_BKGD | SNB_SIGMA_RELU */
+  int32_t reserved;
+} snb_batch_desc;
+size_t snb_render_batch_workspace_bytes(snb_handle h, const snb_batch_desc* d);
+size_t snb_render_batch_scratch_bytes(snb_handle h, const snb_batch_desc* d);
+int snb_render_batch_fwd(snb_handle h, const snb_batch_desc* d, const float* px, const float* py, const float* K,
+                         const float* c2w, const float* box, const float* z_steps, const float* jitter,
+                         const float* shape_latent, const float* texture_latent, float* out_rgb, float* out_depth,
+                         float* out_acc, uint8_t* out_hit, void* workspace, void* stream);
+int snb_render_batch_bwd(snb_handle h, const snb_batch_desc* d, const float* px, const float* py, const float* K,
+                         const float* c2w, const float* box, const float* z_steps, const float* jitter,
+                         const float* shape_latent, const float* texture_latent, const void* workspace,
+                         const float* g_rgb, const float* g_depth, const float* g_acc, void* scratch, float* g_c2w,
+                         float* g_shape_latent, float* g_texture_latent, void* stream);
+/* The refine losses (below) of n_objs objects in one launch per direction: rgb, tgt (B,N,3); acc, occ (B,N);
+ * out3 (B,3) = {loss, loss_rgb, loss_occ} per object, each over its own denominator; g_loss (B) or NULL (= ones). */
+size_t snb_refine_loss_batch_scratch_bytes(int32_t n_objs);
+int snb_refine_loss_batch_fwd(const float* rgb, const float* acc, const float* tgt, const float* occ, int32_t n_objs,
+                              int64_t rays_per_obj, float occ_coef, float* out3, void* scratch, void* stream);
+int snb_refine_loss_batch_bwd(const float* rgb, const float* acc, const float* tgt, const float* occ, int32_t n_objs,
+                              int64_t rays_per_obj, float occ_coef, const void* scratch, const float* g_loss, float* g_rgb,
+                              float* g_acc, void* stream);
+
 /* ---- refine-iteration loss (the caller just above the render) -------------------------------
  * Replaces the inline loss of optimizer_nuscenes.py:729-736 (= optimizer_kitti.py / optimizer_waymo.py, and the render
  * losses of trainer_unified_nuscenes.py:316-332):

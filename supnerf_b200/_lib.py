@@ -23,6 +23,10 @@ class SnbRenderDesc(ctypes.Structure):
                 ("aabb_half", c_flt * 3), ("mode", c_i32), ("obj_diag", c_flt), ("shapenet_swap", c_i32)]
 
 
+class SnbBatchDesc(ctypes.Structure):
+    _fields_ = [("n_objs", c_i32), ("n_samples", c_i32), ("rays_per_obj", c_i64), ("flags", c_i32), ("reserved", c_i32)]
+
+
 # name -> (restype, argtypes); mirrors include/supnerf_b200.h one to one
 SIGNATURES = {
     "snb_abi_version": (c_i32, []),
@@ -70,6 +74,13 @@ SIGNATURES = {
     "snb_render_bwd_scratch_bytes": (c_sz, [ctypes.c_void_p, ctypes.POINTER(SnbRenderDesc)]),
     "snb_render_fwd": (c_i32, [ctypes.c_void_p, ctypes.POINTER(SnbRenderDesc)] + [c_f] * 14),
     "snb_render_bwd": (c_i32, [ctypes.c_void_p, ctypes.POINTER(SnbRenderDesc)] + [c_f] * 16 + [ctypes.POINTER(ctypes.c_void_p), c_f]),
+    "snb_render_batch_workspace_bytes": (c_sz, [ctypes.c_void_p, ctypes.POINTER(SnbBatchDesc)]),
+    "snb_render_batch_scratch_bytes": (c_sz, [ctypes.c_void_p, ctypes.POINTER(SnbBatchDesc)]),
+    "snb_render_batch_fwd": (c_i32, [ctypes.c_void_p, ctypes.POINTER(SnbBatchDesc)] + [c_f] * 15),
+    "snb_render_batch_bwd": (c_i32, [ctypes.c_void_p, ctypes.POINTER(SnbBatchDesc)] + [c_f] * 18),
+    "snb_refine_loss_batch_scratch_bytes": (c_sz, [c_i32]),
+    "snb_refine_loss_batch_fwd": (c_i32, [c_f, c_f, c_f, c_f, c_i32, c_i64, c_flt, c_f, c_f, c_f]),
+    "snb_refine_loss_batch_bwd": (c_i32, [c_f, c_f, c_f, c_f, c_i32, c_i64, c_flt, c_f, c_f, c_f, c_f, c_f]),
 }
 
 _lib = None

@@ -22,14 +22,17 @@ int sample_box_bwd_compact(const float* rays_o, const float* viewdir, const floa
                            const float* g_z_vals, const int32_t* pos, const int64_t* counts, float* g_rays_o, float* g_viewdir,
                            cudaStream_t st);
 
-// mlp_tc.cu: m_dev (optional) = device-side number of rows actually present (a multiple of 128, <= M)
+// mlp_tc.cu: m_dev (optional) = device-side number of rows actually present (a multiple of 128, <= M);
+// tile_start (optional, B + 1 device ints, ascending, even): object b owns the 128-row tiles [tile_start[b], tile_start[b+1]) -- the
+// batched render's objects own different numbers of rows (render_batch.cu)
 bool tc_two_tile_active(const snb_handle_s* h);
 int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, void* ws, cudaStream_t st, bool train,
-               const int64_t* m_dev);
+               const int64_t* m_dev, const int32_t* tile_start = nullptr);
 int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                 const float* shape_latent, const float* texture_latent, const float* sigma, const float* g_sigma,
                 const float* g_rgb, const void* ws, void* scratch, float* g_xyz, float* g_viewdir, float* g_shape_latent,
-                float* g_texture_latent, float* const* g_weights, cudaStream_t st, bool train, const int64_t* m_dev);
+                float* g_texture_latent, float* const* g_weights, cudaStream_t st, bool train, const int64_t* m_dev,
+                const int32_t* tile_start = nullptr);
 
 }  // namespace snb

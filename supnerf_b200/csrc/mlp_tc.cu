@@ -733,10 +733,10 @@ size_t tc2_packed_bytes(const snb_handle_s* h);
 int tc2_pack_weights(const snb_handle_s* h, void* packed, cudaStream_t st);
 int tc2_launch_fwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                    const uint8_t* eimg, uint32_t* masks, float* sigma, float* rgb, float* dbg, uint8_t* save, cudaStream_t st,
-                   const int64_t* m_dev);
+                   const int64_t* m_dev, const int32_t* tile_start);
 int tc2_launch_bwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                    const uint32_t* masks, const float* sigma, const float* g_sigma, const float* g_rgb, float* g_xyz,
-                   float* g_viewdir, float* g_zlat, uint8_t* save, cudaStream_t st, const int64_t* m_dev);
+                   float* g_viewdir, float* g_zlat, uint8_t* save, cudaStream_t st, const int64_t* m_dev, const int32_t* tile_start);
 size_t tc2_fwd_save_bytes(const snb_handle_s* h, int64_t M);
 size_t tc2_bwd_save_bytes(const snb_handle_s* h, int64_t M);
 int tc2_launch_wgrad(const snb_handle_s* h, int64_t M, int64_t B, const uint8_t* fsave, const uint8_t* bsave, const float* sigma,
@@ -801,11 +801,11 @@ size_t tc_train_scratch_extra(const snb_handle_s* h, int64_t M) {
 }
 static inline uint8_t* align1k(uint8_t* p) { return (uint8_t*)(((uintptr_t)p + 1023) & ~uintptr_t(1023)); }
 
-static int tc_common_checks(const snb_handle_s* h, int64_t M, int64_t B, const char* who) {
+static int tc_common_checks(const snb_handle_s* h, int64_t M, int64_t B, const char* who, bool ragged = false) {
   const char* why = "";
   SNB_REQUIRE(tc_supported(h, &why), "%s: %s", who, why);
   SNB_REQUIRE(h->packed != nullptr, "%s: weights not packed (call snb_pack_weights)", who);
-  SNB_REQUIRE((M / B) % kTileM == 0, "%s: bf16 mode needs samples-per-object (%lld) to be a multiple of %d; use fp32 mode",
+  SNB_REQUIRE(ragged || (M / B) % kTileM == 0, "%s: bf16 mode needs samples-per-object (%lld) to be a multiple of %d; use fp32 mode",
               who, (long long)(M / B), kTileM);
   return 0;
 }
@@ -854,9 +854,11 @@ void tc_set_debug(float* acts) { g_tc_debug_acts = acts; }
 
 int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, void* ws, cudaStream_t st,
-               bool train, const int64_t* m_dev) {
-  if (tc_common_checks(h, M, B, "mlp_fwd(bf16)")) return 2;
-  SNB_REQUIRE(m_dev == nullptr || (use_v2(h) && B == 1), "mlp_fwd(bf16): a device-side row count needs the two-tile kernels and one object");
+               bool train, const int64_t* m_dev, const int32_t* tile_start) {
+  if (tc_common_checks(h, M, B, "mlp_fwd(bf16)", tile_start != nullptr)) return 2;
+  SNB_REQUIRE(m_dev == nullptr || (use_v2(h) && (B == 1 || tile_start != nullptr)),
+              "mlp_fwd(bf16): a device-side row count needs the two-tile kernels and one object (or per-object tile offsets)");
+  SNB_REQUIRE(tile_start == nullptr || (use_v2(h) && m_dev != nullptr && !train), "mlp_fwd(bf16): per-object tile offsets need the two-tile kernels, frozen weights and a device-side row count");
   SNB_REQUIRE(!train || use_v2(h), "mlp_fwd(bf16, training): weight gradients need the two-tile tcgen05 kernels (W = 256, "
                                     "shape_blocks + texture_blocks <= 4); use precision='fp32' for this architecture");
   uint8_t* fsave = train ? align1k((uint8_t*)ws + tc_workspace_bytes(h, M, B)) : nullptr;
@@ -868,7 +870,7 @@ int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, in
   if (use_v2(h)) {
     ScopedKernelTimer tm2(st, g_timing_on);
     if (tc2_launch_fwd(h, (const uint8_t*)h->packed + v1_packed_bytes(h), xyz, viewdir, M, B, eimg, masks, sigma, rgb,
-                       g_tc_debug_acts, fsave, st, m_dev)) return 1;
+                       g_tc_debug_acts, fsave, st, m_dev, tile_start)) return 1;
     tm2.stop(g_ev_fwd);
     SNB_LAUNCH_CHECK();
     return 0;
@@ -889,9 +891,12 @@ int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, in
 int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                 const float* shape_latent, const float* texture_latent, const float* sigma, const float* g_sigma,
                 const float* g_rgb, const void* ws, void* scratch, float* g_xyz, float* g_viewdir, float* g_shape_latent,
-                float* g_texture_latent, float* const* g_weights, cudaStream_t st, bool train, const int64_t* m_dev) {
-  if (tc_common_checks(h, M, B, "mlp_bwd(bf16)")) return 2;
-  SNB_REQUIRE(m_dev == nullptr || (use_v2(h) && B == 1), "mlp_bwd(bf16): a device-side row count needs the two-tile kernels and one object");
+                float* g_texture_latent, float* const* g_weights, cudaStream_t st, bool train, const int64_t* m_dev,
+                const int32_t* tile_start) {
+  if (tc_common_checks(h, M, B, "mlp_bwd(bf16)", tile_start != nullptr)) return 2;
+  SNB_REQUIRE(m_dev == nullptr || (use_v2(h) && (B == 1 || tile_start != nullptr)),
+              "mlp_bwd(bf16): a device-side row count needs the two-tile kernels and one object (or per-object tile offsets)");
+  SNB_REQUIRE(tile_start == nullptr || (use_v2(h) && m_dev != nullptr && !train), "mlp_bwd(bf16): per-object tile offsets need the two-tile kernels, frozen weights and a device-side row count");
   SNB_REQUIRE(g_weights == nullptr || (train && use_v2(h)),
               "mlp_bwd(bf16): weight gradients need the forward to have run in training mode (SNB_PREC_BF16_TRAIN: the python "
               "modules select it when a weight requires grad) on an architecture the two-tile kernels cover; otherwise freeze "
@@ -916,7 +921,7 @@ int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, i
     }
     ScopedKernelTimer tm2(st, g_timing_on);
     if (tc2_launch_bwd(h, (const uint8_t*)h->packed + v1_packed_bytes(h), xyz, viewdir, M, B, masks, sigma, g_sigma, g_rgb, g_xyz,
-                       g_viewdir, g_zlat, bsave, st, m_dev)) return 1;
+                       g_viewdir, g_zlat, bsave, st, m_dev, tile_start)) return 1;
     tm2.stop(g_ev_bwd);
     SNB_LAUNCH_CHECK();
     if (!want_w) return latent_backward_fused(h, B, zlat, g_zlat, g_shape_latent, g_texture_latent, st, fold_tmp);

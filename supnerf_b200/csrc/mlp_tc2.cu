@@ -101,6 +101,7 @@ struct Params {
   int r0_mask_slot, n_latent;
   const int64_t* m_dev;   // optional: the number of rows actually present (<= M), read on the device -- the fused render compacts
                           // the samples of rays that miss the box on the GPU and never learns the count on the host
+  const int32_t* tile_start;   // optional (batched render): B + 1 ascending even tile offsets, object b owns tiles [tile_start[b], tile_start[b+1])
   uint8_t* save;      // training mode (weight gradients wanted): [tile][Program::save_tile_bytes] copies of every step's A operand
   long long* trace;   // timing experiments only: CTA 0 writes clock64 stamps [pair][step][slot][4] = READY seen, MMAs issued, ACC seen, published
   int exp_flags;   // timing experiments only (env SNB_TC_EXP): 1 = producer skips the weight copies, 4 = every stage copies the same image
@@ -280,6 +281,17 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
 
 __device__ __forceinline__ int64_t rows_present(const Params& p) { return p.m_dev ? __ldg(p.m_dev) : p.M; }
 
+// object that owns a tile: uniform rows per object, or (batched render) a search in the ascending tile offsets (B + 1 ints in L1)
+__device__ __forceinline__ int64_t obj_of_tile(const Params& p, int64_t tile) {
+  if (p.tile_start == nullptr) return (tile * kTileM) / p.rows_per_obj;
+  int lo = 0, hi = (int)p.B;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if ((int64_t)__ldg(p.tile_start + mid) <= tile) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
 // ---- cta_group::2 forms: issued by the leader CTA only; A = [128 rows][K] in EACH CTA (same smem offset), B = each CTA's half of
 // the N rows, D = 128 lanes x N columns in each CTA's TMEM; commits multicast to the same barrier offset in both CTAs.
 __device__ __forceinline__ void umma2_stage_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate,
@@ -369,7 +381,7 @@ __device__ __forceinline__ void producer_loop(const Params& p, const Smem& sm, i
           const uint8_t* bsrc = p.packed + st.w_off + (uint32_t)st.n_stages * bytes;
           if (st.bias_stage == 2) {
             const int64_t tile = tile_index<CG2>(pair0, CG2 ? 0u : crank, slot);   // CG2: the super tile's object
-            const int64_t obj = tile < n_tiles ? (tile * kTileM) / p.rows_per_obj : 0;
+            const int64_t obj = tile < n_tiles ? obj_of_tile(p, tile) : 0;
             bsrc = p.eimg + ((size_t)st.latent_slot * p.B + obj) * (256u * kBiasStageRowBytes);
           }
           mbar_wait(sm.bar(BAR_WEMPTY + stage), ph ^ 1u);
@@ -884,7 +896,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_const
       e.grow = tile * kTileM + e.row;
       e.valid = tile_ok && e.grow < M_eff;
       const int64_t crow = e.valid ? e.grow : M_eff - 1;
-      const int64_t obj = tile_ok ? (tile * kTileM) / p.rows_per_obj : 0;
+      const int64_t obj = tile_ok ? obj_of_tile(p, tile) : 0;
       const uint32_t* mask_tile = p.masks + (size_t)(tile_ok ? tile : 0) * nslots * 8 * 128;
       float gsp_n = 0.f, g3n[3] = {0.f, 0.f, 0.f}, gx[3] = {0.f, 0.f, 0.f};
       uint32_t mwn[2] = {0u, 0u};
@@ -964,7 +976,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_const
       }
       // ---- tile end: d xyz, and flush the latent column sums when this slot's next tile belongs to another object
       const int64_t next = tile + 2 * (int64_t)gridDim.x;
-      const bool flush = tile_ok && (next >= n_tiles || (next * kTileM) / p.rows_per_obj != obj);
+      const bool flush = tile_ok && (next >= n_tiles || obj_of_tile(p, next) != obj);
       if (p.g_xyz != nullptr && e.hh == 1) *reinterpret_cast<float4*>(part + 4 * e.row) = make_float4(gx[0], gx[1], gx[2], 0.f);
       group_bar(slot);
       if (p.g_xyz != nullptr && e.hh == 0 && e.valid) {
@@ -1270,7 +1282,7 @@ void tc2_set_cg2(int mode) { g_cg2_mode = mode; }
 static bool tc2_use_cg2(const tc2::Params& p) {
   static const int env = [] { const char* e = getenv("SNB_TC_CG2"); return e ? atoi(e) : 1; }();
   const int want = g_cg2_mode < 0 ? env : g_cg2_mode;
-  return want != 0 && p.save == nullptr && p.dbg == nullptr && (p.B == 1 || p.rows_per_obj % 256 == 0);
+  return want != 0 && p.save == nullptr && p.dbg == nullptr && (p.B == 1 || p.tile_start != nullptr || p.rows_per_obj % 256 == 0);
 }
 
 // opt-in shared-memory size of every kernel variant, once per device
@@ -1304,13 +1316,14 @@ static cudaError_t tc2_launch(K kernel, int grid, cudaStream_t st, const tc2::Pa
 
 int tc2_launch_fwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                    const uint8_t* eimg, uint32_t* masks, float* sigma, float* rgb, float* dbg, uint8_t* save, cudaStream_t st,
-                   const int64_t* m_dev) {
+                   const int64_t* m_dev, const int32_t* tile_start) {
   const Tc2Plan& pl = cached_plan2(h);
   tc2::Params p;
   fill_common2(p, h, packed2, xyz, viewdir, M, B, eimg, masks);
   p.sigma = sigma; p.rgb = rgb; p.dbg = dbg;
   p.save = save;
   p.m_dev = m_dev;
+  p.tile_start = tile_start;
   const bool cg2 = tc2_use_cg2(p);
   p.prog = save ? pl.fwd_train : ((cg2 && !dbg) ? pl.fwd_merged : pl.fwd);
   if (tc2_init_device()) return 1;
@@ -1326,7 +1339,7 @@ int tc2_launch_fwd(const snb_handle_s* h, const void* packed2, const float* xyz,
 
 int tc2_launch_bwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                    const uint32_t* masks, const float* sigma, const float* g_sigma, const float* g_rgb, float* g_xyz,
-                   float* g_viewdir, float* g_zlat, uint8_t* save, cudaStream_t st, const int64_t* m_dev) {
+                   float* g_viewdir, float* g_zlat, uint8_t* save, cudaStream_t st, const int64_t* m_dev, const int32_t* tile_start) {
   const Tc2Plan& pl = cached_plan2(h);
   tc2::Params p;
   fill_common2(p, h, packed2, xyz, viewdir, M, B, nullptr, const_cast<uint32_t*>(masks));
@@ -1334,6 +1347,7 @@ int tc2_launch_bwd(const snb_handle_s* h, const void* packed2, const float* xyz,
   p.r0_mask_slot = pl.r0_slot;
   p.save = save;
   p.m_dev = m_dev;
+  p.tile_start = tile_start;
   SNB_REQUIRE(save == nullptr || g_xyz != nullptr, "tc2 backward: training mode runs the full program (g_xyz scratch required)");
   p.prog = g_xyz ? pl.bwd_full : pl.bwd_noxyz;
   if (tc2_init_device()) return 1;

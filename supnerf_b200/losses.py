@@ -73,3 +73,51 @@ def refine_loss_vec(rgb_rays, acc_trans_rays, rgb_tgt, occ_pixels, loss_occ_coef
     stacking kernels: what a graph-captured loop keeps to read the losses after a replay)."""
     loss, _, vec = _RefineLoss.apply(rgb_rays, acc_trans_rays.reshape(-1), rgb_tgt, occ_pixels.reshape(-1), loss_occ_coef, den)
     return loss, vec
+
+
+class _RefineLossBatch(torch.autograd.Function):
+    """The refine losses of B objects (each over its own denominator) in one launch per direction (snb_refine_loss_batch_*)."""
+
+    @staticmethod
+    def forward(ctx, rgb, acc, tgt, occ, coef):
+        lib = _lib.load()
+        require_cuda(rgb, acc, tgt, occ)
+        rgb, acc, tgt, occ = f32c(rgb), f32c(acc), f32c(tgt), f32c(occ)
+        b, n = acc.shape
+        dev = rgb.device
+        out = torch.empty(b, 3, device=dev, dtype=torch.float32)
+        scratch = torch.empty(lib.snb_refine_loss_batch_scratch_bytes(b), dtype=torch.uint8, device=dev)
+        with on_device(dev):
+            check(lib.snb_refine_loss_batch_fwd(ptr(rgb), ptr(acc), ptr(tgt), ptr(occ), b, n, float(coef), ptr(out), ptr(scratch), stream_ptr()),
+                  "snb_refine_loss_batch_fwd")
+        ctx.save_for_backward(rgb, acc, tgt, occ, scratch)
+        ctx.coef = float(coef)
+        loss = out[:, 0]
+        ctx.mark_non_differentiable(out)
+        ctx.set_materialize_grads(False)
+        return loss, out
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_out):
+        lib = _lib.load()
+        rgb, acc, tgt, occ, scratch = ctx.saved_tensors
+        if g_loss is None:
+            return None, None, None, None, None
+        b, n = acc.shape
+        g_rgb, g_acc = torch.empty_like(rgb), torch.empty_like(acc)
+        g_loss = f32c(g_loss)
+        if not g_loss.is_contiguous() or g_loss.stride() != (1,):
+            g_loss = g_loss.contiguous()
+        with on_device(rgb.device):
+            check(lib.snb_refine_loss_batch_bwd(ptr(rgb), ptr(acc), ptr(tgt), ptr(occ), b, n, ctx.coef, ptr(scratch), ptr(g_loss), ptr(g_rgb),
+                                                ptr(g_acc), stream_ptr()), "snb_refine_loss_batch_bwd")
+        return g_rgb, g_acc, None, None, None
+
+
+def refine_loss_batch(rgb_rays, acc_trans_rays, rgb_tgt, occ_pixels, loss_occ_coef=0.1):
+    """The refine losses (optimizer_nuscenes.py:729-736) of B objects at once: rgb_rays, rgb_tgt (B,N,3); acc_trans_rays (B,N);
+    occ_pixels (B,N,1) or (B,N).  -> (loss (B,), parts (B,3) = [loss, loss_rgb, loss_occ] per object); ``loss`` is differentiable."""
+    b, n = acc_trans_rays.shape
+    if tuple(rgb_rays.shape) != (b, n, 3) or tuple(rgb_tgt.shape) != (b, n, 3) or occ_pixels.numel() != b * n:
+        raise ValueError("refine_loss_batch: expected rgb (B,N,3), acc (B,N), tgt (B,N,3), occ (B,N,1)")
+    return _RefineLossBatch.apply(rgb_rays, acc_trans_rays, rgb_tgt, occ_pixels.reshape(b, n), loss_occ_coef)

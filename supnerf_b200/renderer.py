@@ -89,6 +89,44 @@ class NeRFRenderer(torch.nn.Module):
                                              texturecode.to(device, non_blocking=True), model._weights())
         return rgb, dep, acc
 
+    def render_rays_batch(self, model, device, imgs, masks_occ, cam_poses, obj_szs, Ks, rois, shapecodes, texturecodes, im_sz=64,
+                          jitter=None):
+        """``render_rays`` (renderer.py:117-167, ``n_rays=None``) of B objects in ONE launch set (csrc/render_batch.cu) -- what the
+        reference does with a Python loop over the objects of a scene (optimizer_nuscenes.py:716-726; configs[1]: 16 objects per step).
+        imgs (B,h,w,3) / masks_occ (B,h,w,1) stacked tensors or lists of per-object crops; cam_poses (B,3,4); obj_szs B x (w,l,h);
+        Ks (B,3,3) or one (3,3); rois B x (4,); shapecodes / texturecodes (B,D).  Every object is resampled to im_sz x im_sz rays.
+        -> rgb (B,N,3), depth (B,N), acc (B,N), rgb_tgt (B,N,3), occ_pixels (B,N,1).  One torch.rand_like of (B,N,S) where the
+        per-object calls draw B x (N,S).  Frozen weights, bf16 decoder (no CPU or per-object fallback)."""
+        device = torch.device(device)
+        if not isinstance(model, models._DecoderBase) or device.type != "cuda":
+            raise RuntimeError("render_rays_batch needs a supnerf_b200 decoder on a CUDA device")
+        b = len(rois)
+        boxes, pxs, pys, tgts, occs = [], [], [], [], []
+        for i in range(b):
+            diag, half = ops.box_constants(obj_szs[i])
+            boxes.append([float(diag / 2), float(half[0]), float(half[1]), float(half[2])])
+            px, py = U._pixel_grid_on(device, rois[i], [im_sz, im_sz])
+            pxs.append(px)
+            pys.append(py)
+            img, mask = U._resize_targets(imgs[i], masks_occ[i], im_sz)
+            tgts.append(img.reshape(-1, 3))
+            occs.append(mask.reshape(-1, 1))
+        box = torch.tensor(boxes, dtype=torch.float32).to(device, non_blocking=True)
+        px, py = torch.stack(pxs), torch.stack(pys)
+        rgb_tgt = torch.stack(tgts).to(device, non_blocking=True)
+        occ_pixels = torch.stack(occs).to(device, non_blocking=True)
+        n = px.shape[1]
+        Ks = torch.as_tensor(Ks) if not torch.is_tensor(Ks) else Ks
+        if Ks.dim() == 2:
+            Ks = Ks.unsqueeze(0).expand(b, 3, 3)
+        if jitter is None:
+            jitter = torch.rand_like(torch.empty(b, n, self.n_samples, device=device))
+        rgb, dep, acc, _hit = ops.render_box_batch(model._handle(device), self.n_samples, self.white_bkgd, px, py,
+                                                   Ks.to(device, non_blocking=True), cam_poses.to(device, non_blocking=True), box,
+                                                   _z_steps_on(device, self.n_samples), jitter, shapecodes.to(device, non_blocking=True),
+                                                   texturecodes.to(device, non_blocking=True), model._weights())
+        return rgb, dep, acc, rgb_tgt, occ_pixels
+
     @staticmethod
     def _can_fuse(model, device, kitti2nusc, shapecode):
         return (FUSED_RENDER and not kitti2nusc and isinstance(model, models._DecoderBase) and shapecode.shape[0] == 1
