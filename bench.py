@@ -165,12 +165,13 @@ def run_ours(args):
                           shp=o["shapecode"].to(dev).requires_grad_(), tex=o["texturecode"].to(dev).requires_grad_()))
         hobjs.append(dict(K=o["K"].pin_memory(), cam=o["cam_pose"].pin_memory(), wlh=o["wlh"], roi=o["roi"], img=o["img"].pin_memory(),
                           mask=o["mask_occ"].pin_memory(), shp=o["shapecode"].pin_memory(), tex=o["texturecode"].pin_memory()))
+    batched = args.batched and args.precision == "bf16"
 
-    # Objects are independent: they alternate over `--streams` CUDA streams so that one object's small kernels
-    # (sampler, compaction, compositing, loss) fill the issue slots the other object's persistent decoder kernel leaves idle.
-    # Every step forks from / joins back into the timing stream on the device (no host synchronisation).
+    # Objects are independent.  Default: ALL 16 objects of the step go through ONE launch set (NeRFRenderer.render_batch ->
+    # snb_render_batch_fwd / bwd, csrc/render_batch.cu; the batched refine losses).  --per-object keeps round 1's path: one fused
+    # render per object, the objects alternating over `--streams` CUDA streams.
     main_stream = torch.cuda.current_stream(dev)
-    streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, args.streams))] if args.streams > 1 else [main_stream]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, args.streams))] if (args.streams > 1 and not batched) else [main_stream]
 
     def fork():
         if len(streams) > 1:
@@ -182,9 +183,31 @@ def run_ours(args):
             for st_ in streams:
                 main_stream.wait_stream(st_)
 
+    wlhs, rois = [o["wlh"] for o in objs], [o["roi"] for o in objs]
+    if batched:
+        batch = R.make_batch(dev, torch.stack([o["img"] for o in objs]), torch.stack([o["mask_occ"] for o in objs]), wlhs,
+                             torch.stack([o["K"] for o in objs]), rois, IM_SZ)
+        cams = torch.stack([o["cam_pose"] for o in objs]).to(dev).requires_grad_()
+        shps = torch.cat([o["shapecode"] for o in objs]).to(dev).requires_grad_()
+        texs = torch.cat([o["texturecode"] for o in objs]).to(dev).requires_grad_()
+        ones_b = torch.ones(N_OBJ, device=dev)
+        # pinned host copies for `e2e`: one buffer per input kind for the whole batch
+        h_img = torch.stack([o["img"] for o in objs]).pin_memory()
+        h_mask = torch.stack([o["mask_occ"] for o in objs]).pin_memory()
+        h_cam = torch.stack([o["cam_pose"] for o in objs]).pin_memory()
+        h_K = torch.stack([o["K"] for o in objs]).pin_memory()
+        h_shp = torch.cat([o["shapecode"] for o in objs]).pin_memory()
+        h_tex = torch.cat([o["texturecode"] for o in objs]).pin_memory()
+
     def step_resident():
-        """One pass over the batch through the public API (NeRFRenderer.render_rays -> fused C-ABI render) with every input
-        already resident in HBM; the loss and its backward to pose + latents close the step."""
+        """One pass over the batch through the public API with every input already resident in HBM; the losses and their backward
+        to the poses + latents close the step."""
+        if batched:
+            cams.grad = shps.grad = texs.grad = None
+            rgb, dep, acc = R.render_batch(model, batch, cams, shps, texs)
+            loss, parts = snb.losses.refine_loss_batch(rgb, acc, batch.rgb_tgt, batch.occ_pixels, 0.1)
+            loss.backward(gradient=ones_b)     # every object's own loss, upstream gradient 1 each
+            return parts
         fork()
         for i, d in enumerate(dobjs):
             with torch.cuda.stream(streams[i % len(streams)]):
@@ -200,6 +223,17 @@ def run_ours(args):
     res_host = torch.empty(N_OBJ, 1 + 12 + 512, dtype=torch.float32).pin_memory()
 
     def step_e2e():
+        if batched:
+            # H2D of the step's inputs from pinned memory (crops, masks, poses, intrinsics, codes), the drop-in call, D2H of the result
+            cam = h_cam.to(dev, non_blocking=True).requires_grad_()
+            shp = h_shp.to(dev, non_blocking=True).requires_grad_()
+            tex = h_tex.to(dev, non_blocking=True).requires_grad_()
+            rgb, dep, acc, tgt, occ = R.render_rays_batch(model, dev, h_img, h_mask, cam, wlhs, h_K, rois, shp, tex, im_sz=IM_SZ)
+            loss, parts = snb.losses.refine_loss_batch(rgb, acc, tgt, occ, 0.1)
+            loss.backward(gradient=ones_b)
+            res_host.copy_(torch.cat([parts[:, :1], cam.grad.reshape(N_OBJ, 12), shp.grad, tex.grad], 1), non_blocking=True)
+            torch.cuda.synchronize()
+            return float(res_host[:, 0].sum().item())
         fork()
         for i, h in enumerate(hobjs):
             with torch.cuda.stream(streams[i % len(streams)]):
@@ -285,18 +319,20 @@ def run_ours(args):
             hit = R.prepare_sampled_rays(ro, vd, d["wlh"])[3]
             nh = int(hit.sum().item())
             compacted = args.precision == "bf16" and os.environ.get("SNB_NO_COMPACT", "0") in ("", "0")
-            rows_exec.append(-(-(nh * N_SAMPLES + (n_rays - nh)) // 128) * 128 if compacted else rows_full)
+            pad = 256 if batched else 128
+            rows_exec.append(-(-(nh * N_SAMPLES + (n_rays - nh)) // pad) * pad if compacted else rows_full)
             d["hit_fraction"] = nh / n_rays
     hit_fraction = float(np.mean([d["hit_fraction"] for d in dobjs]))
-    rows = float(np.mean(rows_exec))
+    rows = float(np.sum(rows_exec)) if batched else float(np.mean(rows_exec))   # one launch renders all objects in the batched path
     flop_per_launch = 2.0 * MAC_PER_SAMPLE * rows
     roof = {}
     for which in ("fwd", "bwd"):
         ts = kern.get(which) or []
-        if ts:   # launches cycle through the objects in order: pair every duration with its object's executed rows
-            tf = [2.0 * MAC_PER_SAMPLE * rows_exec[i % N_OBJ] / (t / 1e3) / 1e12 for i, t in enumerate(ts)]
+        if ts:   # per-object path: launches cycle through the objects in order (pair every duration with its object's executed rows)
+            per_launch = [rows] * len(ts) if batched else [rows_exec[i % N_OBJ] for i in range(len(ts))]
+            tf = [2.0 * MAC_PER_SAMPLE * r_ / (t / 1e3) / 1e12 for r_, t in zip(per_launch, ts)]
             avg = float(np.mean(ts))
-            roof[which] = dict(ms=avg, tflops=float(np.sum([2.0 * MAC_PER_SAMPLE * rows_exec[i % N_OBJ] for i in range(len(ts))]) / (np.sum(ts) / 1e3) / 1e12),
+            roof[which] = dict(ms=avg, tflops=float(np.sum([2.0 * MAC_PER_SAMPLE * r_ for r_ in per_launch]) / (np.sum(ts) / 1e3) / 1e12),
                                n=len(ts), total_ms=float(np.sum(ts)), tflops_min=float(min(tf)), tflops_max=float(max(tf)))
     dom = max(roof, key=lambda k: roof[k]["total_ms"]) if roof else None
     peak = pk["tf_sustained"] if args.precision == "bf16" else None
@@ -443,7 +479,8 @@ def run_ours(args):
             "config": {"workload": WORKLOAD,
                        "objects_per_gpu": N_OBJ, "rays_per_object": n_rays, "samples_per_ray": N_SAMPLES, "weights": "frozen (refine mode)",
                        "grads": "cam_pose, shapecode, texturecode", "parallelism": "object-parallel x%d, no collective; every rank renders the same 16-object set" % world, "cuda_streams_per_gpu": len(streams),
-                       "l2": "inputs larger than L2: per object ~45 MB of samples / decoder outputs / gradients and ~12 MB of ReLU masks stream through HBM, 16 objects per step",
+                       "launch_sets": "one batched launch set for the 16 objects (snb_render_batch_fwd/bwd)" if batched else "one fused render per object",
+                       "l2": "working set larger than L2 (126 MB): a step executes ~7 M decoder rows; per row 28 B of sample coordinates + z, 16 B of decoder outputs, as much again of gradients, and 224 B of ReLU mask bits (7 mask slots x 32 B) written by the forward and read by the backward: ~2 GB through HBM per step",
                        "hit_fraction": round(hit_fraction, 4),
                        "precision": args.precision},
             "e2e": {"value": round(e2e_value, 1), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -867,6 +904,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--per-object", dest="batched", action="store_false",
+                    help="round 1's path: one fused render per object over --streams CUDA streams (default: all objects in one launch set)")
     ap.add_argument("--skip-modes", action="store_true", help="skip the configs[3] / configs[4] collective-bearing modes")
     ap.add_argument("--streams", type=int, default=3, help="CUDA streams the independent objects alternate over (1 = one stream)")
     args = ap.parse_args()

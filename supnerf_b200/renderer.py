@@ -25,6 +25,15 @@ def _z_steps_on(device, n_samples):
     return z
 
 
+class RayBatch:
+    """Device-resident constants of a batch of object crops (NeRFRenderer.make_batch): px, py (B,N) pixel coordinates, K (B,3,3),
+    box (B,4) = {diag/2, l/diag, w/diag, h/diag}, rgb_tgt (B,N,3), occ_pixels (B,N,1)."""
+    __slots__ = ("px", "py", "K", "box", "rgb_tgt", "occ_pixels")
+
+    def __init__(self, px, py, K, box, rgb_tgt, occ_pixels):
+        self.px, self.py, self.K, self.box, self.rgb_tgt, self.occ_pixels = px, py, K, box, rgb_tgt, occ_pixels
+
+
 FUSED_RENDER = True  # render_rays / render_rays_specified go through ops.render_box (one autograd node); False = staged ops
 
 
@@ -89,43 +98,66 @@ class NeRFRenderer(torch.nn.Module):
                                              texturecode.to(device, non_blocking=True), model._weights())
         return rgb, dep, acc
 
-    def render_rays_batch(self, model, device, imgs, masks_occ, cam_poses, obj_szs, Ks, rois, shapecodes, texturecodes, im_sz=64,
-                          jitter=None):
-        """``render_rays`` (renderer.py:117-167, ``n_rays=None``) of B objects in ONE launch set (csrc/render_batch.cu) -- what the
-        reference does with a Python loop over the objects of a scene (optimizer_nuscenes.py:716-726; configs[1]: 16 objects per step).
-        imgs (B,h,w,3) / masks_occ (B,h,w,1) stacked tensors or lists of per-object crops; cam_poses (B,3,4); obj_szs B x (w,l,h);
-        Ks (B,3,3) or one (3,3); rois B x (4,); shapecodes / texturecodes (B,D).  Every object is resampled to im_sz x im_sz rays.
-        -> rgb (B,N,3), depth (B,N), acc (B,N), rgb_tgt (B,N,3), occ_pixels (B,N,1).  One torch.rand_like of (B,N,S) where the
-        per-object calls draw B x (N,S).  Frozen weights, bf16 decoder (no CPU or per-object fallback)."""
+    def make_batch(self, device, imgs, masks_occ, obj_szs, Ks, rois, im_sz=64):
+        """The per-batch constants of ``render_rays_batch``: pixel grids, targets, occupancy masks and box constants of B object
+        crops, on the device (a refine-style loop re-renders the same crops every iteration: build once, render many times).
+        imgs (B,h,w,3) / masks_occ (B,h,w,1) stacked tensors or lists of per-object crops, resampled to im_sz x im_sz like
+        renderer.py:127-133 (stacked tensors that already have that size take one copy for the whole batch)."""
         device = torch.device(device)
-        if not isinstance(model, models._DecoderBase) or device.type != "cuda":
-            raise RuntimeError("render_rays_batch needs a supnerf_b200 decoder on a CUDA device")
+        if device.type != "cuda":
+            raise RuntimeError("supnerf_b200 has no CPU path")
         b = len(rois)
-        boxes, pxs, pys, tgts, occs = [], [], [], [], []
+        boxes, pxs, pys = [], [], []
         for i in range(b):
             diag, half = ops.box_constants(obj_szs[i])
             boxes.append([float(diag / 2), float(half[0]), float(half[1]), float(half[2])])
             px, py = U._pixel_grid_on(device, rois[i], [im_sz, im_sz])
             pxs.append(px)
             pys.append(py)
-            img, mask = U._resize_targets(imgs[i], masks_occ[i], im_sz)
-            tgts.append(img.reshape(-1, 3))
-            occs.append(mask.reshape(-1, 1))
-        box = torch.tensor(boxes, dtype=torch.float32).to(device, non_blocking=True)
-        px, py = torch.stack(pxs), torch.stack(pys)
-        rgb_tgt = torch.stack(tgts).to(device, non_blocking=True)
-        occ_pixels = torch.stack(occs).to(device, non_blocking=True)
-        n = px.shape[1]
+        if torch.is_tensor(imgs) and torch.is_tensor(masks_occ) and imgs.dim() == 4 and tuple(imgs.shape[1:3]) == (im_sz, im_sz) \
+                and tuple(masks_occ.shape[1:3]) == (im_sz, im_sz):
+            # torchvision's Resize to the size the crop already has returns its input: only the mask's int32 round trip remains
+            rgb_tgt = imgs.to(device, non_blocking=True).reshape(b, -1, 3)
+            occ_pixels = masks_occ.to(device, non_blocking=True).reshape(b, -1, 1).type(torch.int32).type(torch.float32)
+        else:
+            tgts, occs = [], []
+            for i in range(b):
+                img, mask = U._resize_targets(imgs[i], masks_occ[i], im_sz)
+                tgts.append(img.reshape(-1, 3))
+                occs.append(mask.reshape(-1, 1))
+            rgb_tgt = torch.stack(tgts).to(device, non_blocking=True)
+            occ_pixels = torch.stack(occs).to(device, non_blocking=True)
         Ks = torch.as_tensor(Ks) if not torch.is_tensor(Ks) else Ks
         if Ks.dim() == 2:
             Ks = Ks.unsqueeze(0).expand(b, 3, 3)
+        return RayBatch(torch.stack(pxs), torch.stack(pys), Ks.to(device, torch.float32, non_blocking=True).contiguous(),
+                        torch.tensor(boxes, dtype=torch.float32).to(device, non_blocking=True), rgb_tgt, occ_pixels)
+
+    def render_batch(self, model, batch, cam_poses, shapecodes, texturecodes, jitter=None):
+        """B objects of a prepared ``RayBatch`` in ONE launch set (csrc/render_batch.cu).  cam_poses (B,3,4); shapecodes /
+        texturecodes (B,D).  -> rgb (B,N,3), depth (B,N), acc (B,N).  One torch.rand_like of (B,N,S) per call."""
+        if not isinstance(model, models._DecoderBase):
+            raise RuntimeError("render_batch needs a supnerf_b200 decoder")
+        device = batch.px.device
+        b, n = batch.px.shape
         if jitter is None:
             jitter = torch.rand_like(torch.empty(b, n, self.n_samples, device=device))
-        rgb, dep, acc, _hit = ops.render_box_batch(model._handle(device), self.n_samples, self.white_bkgd, px, py,
-                                                   Ks.to(device, non_blocking=True), cam_poses.to(device, non_blocking=True), box,
-                                                   _z_steps_on(device, self.n_samples), jitter, shapecodes.to(device, non_blocking=True),
+        rgb, dep, acc, _hit = ops.render_box_batch(model._handle(device), self.n_samples, self.white_bkgd, batch.px, batch.py, batch.K,
+                                                   cam_poses.to(device, non_blocking=True), batch.box, _z_steps_on(device, self.n_samples),
+                                                   jitter, shapecodes.to(device, non_blocking=True),
                                                    texturecodes.to(device, non_blocking=True), model._weights())
-        return rgb, dep, acc, rgb_tgt, occ_pixels
+        return rgb, dep, acc
+
+    def render_rays_batch(self, model, device, imgs, masks_occ, cam_poses, obj_szs, Ks, rois, shapecodes, texturecodes, im_sz=64,
+                          jitter=None):
+        """``render_rays`` (renderer.py:117-167, ``n_rays=None``) of B objects in ONE launch set -- what the reference does with a
+        Python loop over the objects of a scene (optimizer_nuscenes.py:716-726; configs[1]: 16 objects per step).
+        cam_poses (B,3,4); obj_szs B x (w,l,h); Ks (B,3,3) or one (3,3); rois B x (4,); shapecodes / texturecodes (B,D).
+        -> rgb (B,N,3), depth (B,N), acc (B,N), rgb_tgt (B,N,3), occ_pixels (B,N,1).  Frozen weights, bf16 decoder (no CPU or
+        per-object fallback)."""
+        batch = self.make_batch(device, imgs, masks_occ, obj_szs, Ks, rois, im_sz)
+        rgb, dep, acc = self.render_batch(model, batch, cam_poses, shapecodes, texturecodes, jitter)
+        return rgb, dep, acc, batch.rgb_tgt, batch.occ_pixels
 
     @staticmethod
     def _can_fuse(model, device, kitti2nusc, shapecode):
