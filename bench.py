@@ -511,6 +511,7 @@ def run_c4(snb, dev, rank, world, steps, warmup, precision):
     import torch.distributed as dist
     from supnerf_b200 import parallel, synthetic
     IM, S = 512, 128
+    LAYOUT = "strided"   # ray i on rank i % G: balanced hit counts (128-ray tiles left the ranks 15 % apart, profiles/r2_c4_layouts.md)
     obj = synthetic.synthetic_object(4, im_sz=IM)
     sd = synthetic.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=4)
     m = snb.SUPNeRF(3, 1, 3, 3, 256)
@@ -525,8 +526,8 @@ def run_c4(snb, dev, rank, world, steps, warmup, precision):
     def leaves():
         return obj["cam_pose"].to(dev).requires_grad_(), shp0.to(dev).requires_grad_(), tex0.to(dev).requires_grad_()
 
-    shard = parallel.RayShard(R, m, dev, img, mask, obj["wlh"], K, obj["roi"], IM, rank=rank, world=world, layout="interleaved")
-    whole = parallel.RayShard(R, m, dev, img, mask, obj["wlh"], K, obj["roi"], IM, rank=0, world=1, layout="interleaved", group=None)
+    shard = parallel.RayShard(R, m, dev, img, mask, obj["wlh"], K, obj["roi"], IM, rank=rank, world=world, layout=LAYOUT)
+    whole = parallel.RayShard(R, m, dev, img, mask, obj["wlh"], K, obj["roi"], IM, rank=0, world=1, layout=LAYOUT, group=None)
     # ---- parity, on this run: the sharded step against the SAME step on one rank (every rank renders the whole object once)
     cam, shp, tex = leaves()
     loss_s, rgb_s, _, _ = shard.step(cam, shp, tex, seed=1234)
@@ -539,7 +540,7 @@ def run_c4(snb, dev, rank, world, steps, warmup, precision):
     part = losses.refine_loss(rgb_1, acc_1, whole.rgb_tgt, whole.occ, 0.1, den=whole.den)[0]
     part.backward()
     g_one = torch.cat([cam1.grad.reshape(-1), shp1.grad.reshape(-1), tex1.grad.reshape(-1)])
-    full = parallel.gather_rays(rgb_s.detach(), IM * IM, S, layout="interleaved") if world > 1 else rgb_s.detach()
+    full = parallel.gather_rays(rgb_s.detach(), IM * IM, S, layout=LAYOUT) if world > 1 else rgb_s.detach()
 
     def rel(a, b):
         return float((a.double() - b.double()).abs().max() / b.double().abs().max())
@@ -612,7 +613,7 @@ def run_c4(snb, dev, rank, world, steps, warmup, precision):
             ms_one = a0.elapsed_time(a1) / steps
         ms_one = _maxr(ms_one if ms_one is not None else 0.0, dev, world)
     n = IM * IM
-    out = {"config": "configs[3]: one 512x512 object x 128 samples, ray-sharded x%d (interleaved 128-ray tiles), one all-reduce of 525 floats per step" % world,
+    out = {"config": "configs[3]: one 512x512 object x 128 samples, ray-sharded x%d (ray i on rank i %% G), one all-reduce of 525 floats per step" % world,
            "scaling": "strong", "n_gpus": world, "ms_per_step": round(ms_max, 3), "rays_per_s": round(n / (ms_max / 1e3), 1),
            "precision": precision, "loss": loss,
            "one_gpu_ms_per_step_same_run": round(ms_one, 3) if ms_one else None,

@@ -40,16 +40,19 @@ def ray_shard(n_rays, n_samples, rank, world):
     return start, end
 
 
-def ray_shard_indices(n_rays, n_samples, rank, world, device=None):
+def ray_shard_indices(n_rays, n_samples, rank, world, device=None, tile=TILE_ROWS):
     """Ray ids of `rank` in the INTERLEAVED layout: the rays are cut into tiles of 128 rays (128 x S sample rows = S whole
     128-row decoder tiles for any S) and rank r owns tiles r, r+G, r+2G, ...
     With miss-ray compaction a rank's decoder work is proportional to the rays of its shard that HIT the object box, and a
     contiguous split of a row-major crop gives the ranks holding the middle rows about twice the hits of the outer ones
     (512x512 rays on 4 GPUs: 12.1 ms per step against 7.8 ms for a balanced split); interleaved tiles sample the crop uniformly.
+    `tile` = rays per tile (default 128; 1 = ray i on rank i % G, "strided": neighbouring pixels go to different ranks, so the hit
+    counts -- hence the decoder rows after compaction -- agree to a few rays; miss-ray compaction makes tile alignment of the
+    shards irrelevant, the decoder pads each shard's rows itself).
     -> sorted int64 tensor of ray ids (the last tile may be partial)."""
     if not (0 <= rank < world):
         raise ValueError("rank out of range")
-    tile = TILE_ROWS   # 128 rays x S samples = S whole decoder tiles
+    tile = max(1, int(tile))
     n_tiles = -(-int(n_rays) // tile)
     if rank >= n_tiles:
         return torch.empty(0, dtype=torch.int64, device=device)
@@ -72,7 +75,7 @@ def allreduce_grads(params, loss=None, group=None, scale=None, collective=True):
     with ONE all_reduce of one flat fp32 buffer (2.1 KB for 12 + 256 + 256 + 1 floats): one gather kernel (torch.cat) in, the
     collective, and the parameters' ``.grad`` become VIEWS of the reduced buffer (no copy back).  Returns the global loss
     (a 0-dim tensor) or None."""
-    flat = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params]
+    flat = [_flat_view(p.grad if p.grad is not None else torch.zeros_like(p)).float() for p in params]
     if loss is not None:
         flat.append(loss.detach().reshape(1).float())
     buf = torch.cat(flat)
@@ -83,7 +86,7 @@ def allreduce_grads(params, loss=None, group=None, scale=None, collective=True):
     off = 0
     for p in params:
         n = p.numel()
-        g = buf[off:off + n].view(p.shape)
+        g = _unflat_view(buf[off:off + n], p)
         p.grad = g if g.dtype == p.dtype else g.to(p.dtype)
         off += n
     return buf[off] if loss is not None else None
@@ -101,6 +104,26 @@ def allreduce_weight_grads(model, group=None, average=True):
     g = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     allreduce_grads(params, None, group, scale=(1.0 / g) if (average and g > 1) else None)
     return sum(p.numel() for p in params)
+
+
+def _flat_view(g):
+    """1-D view of a dense gradient in MEMORY order (no copy): contiguous tensors as they are, channels-last 4-D tensors through
+    their NHWC permutation -- the same on every rank, so the element order of a flat bucket matches across ranks."""
+    if g.is_contiguous():
+        return g.reshape(-1)
+    if g.dim() == 4 and g.is_contiguous(memory_format=torch.channels_last):
+        return g.permute(0, 2, 3, 1).reshape(-1)
+    return g.contiguous().reshape(-1)
+
+
+def _unflat_view(flat, like):
+    """The inverse of _flat_view: a view of `flat` with the shape AND strides of `like` (fused optimisers require them equal)."""
+    if like.is_contiguous():
+        return flat.view(like.shape)
+    if like.dim() == 4 and like.is_contiguous(memory_format=torch.channels_last):
+        n, c, h, w = like.shape
+        return flat.view(n, h, w, c).permute(0, 3, 1, 2)
+    return flat.view(like.shape)
 
 
 class BucketedGradAllReduce:
@@ -152,7 +175,7 @@ class BucketedGradAllReduce:
             e0 = torch.cuda.Event(enable_timing=True) if self.stream is not None else None
             if e0 is not None:
                 e0.record()
-            flat = torch.cat([p.grad.reshape(-1) for p in b])
+            flat = torch.cat([_flat_view(p.grad) for p in b])
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
             if self.average:
                 flat.mul_(1.0 / self.world)
@@ -182,7 +205,7 @@ class BucketedGradAllReduce:
             off = 0
             for p in b:
                 n = p.numel()
-                p.grad = flat[off:off + n].view(p.shape)
+                p.grad = _unflat_view(flat[off:off + n], p)
                 off += n
             total += off
         events = self.events
@@ -219,8 +242,8 @@ def render_rays_sharded(renderer, model, device, img, mask_occ, cam_pose, obj_sz
     img, mask_occ = U._resize_targets(img, mask_occ, im_sz)
     n = px.numel()
     occ_all = mask_occ.reshape(-1, 1).to(device, non_blocking=True)
-    if layout == "interleaved":
-        sel = ray_shard_indices(n, renderer.n_samples, rank, world, device=device)
+    if layout in ("interleaved", "strided"):
+        sel = ray_shard_indices(n, renderer.n_samples, rank, world, device=device, tile=TILE_ROWS if layout == "interleaved" else 1)
     elif layout == "contiguous":
         a, b = ray_shard(n, renderer.n_samples, rank, world)
         sel = slice(a, b)
@@ -260,11 +283,13 @@ class RayShard:
         self.n_rays, S = px.numel(), renderer.n_samples
         if layout == "interleaved":
             self.ids = ray_shard_indices(self.n_rays, S, self.rank, self.world, device=dev)
+        elif layout == "strided":
+            self.ids = ray_shard_indices(self.n_rays, S, self.rank, self.world, device=dev, tile=1)
         elif layout == "contiguous":
             a, b = ray_shard(self.n_rays, S, self.rank, self.world)
             self.ids = torch.arange(a, b, dtype=torch.int64, device=dev)
         else:
-            raise ValueError("layout must be 'contiguous' or 'interleaved'")
+            raise ValueError("layout must be 'contiguous', 'interleaved' or 'strided'")
         occ_all = mask_occ.reshape(-1, 1).to(dev)
         self.den = torch.sum(torch.abs(occ_all)) + 1e-9          # global denominator: a function of the input mask only
         self.px, self.py = px[self.ids].contiguous(), py[self.ids].contiguous()
@@ -298,8 +323,8 @@ def gather_rays(t, n_rays, n_samples, group=None, layout="contiguous"):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return t
     world = dist.get_world_size(group)
-    if layout == "interleaved":
-        ids = [ray_shard_indices(n_rays, n_samples, r, world, device=t.device) for r in range(world)]
+    if layout in ("interleaved", "strided"):
+        ids = [ray_shard_indices(n_rays, n_samples, r, world, device=t.device, tile=TILE_ROWS if layout == "interleaved" else 1) for r in range(world)]
         counts = [int(i.numel()) for i in ids]
     else:
         sizes = [ray_shard(n_rays, n_samples, r, world) for r in range(world)]
@@ -309,7 +334,7 @@ def gather_rays(t, n_rays, n_samples, group=None, layout="contiguous"):
     pad[:t.shape[0]] = t
     outs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(outs, pad, group=group)
-    if layout == "interleaved":
+    if layout in ("interleaved", "strided"):
         full = torch.empty((n_rays,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         for o, i, c in zip(outs, ids, counts):
             full[i] = o[:c]

@@ -58,7 +58,7 @@ def _worker(rank, world, port, prec, q, layout="contiguous"):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("prec,tol,layout", [("fp32", 1e-5, "contiguous"), ("bf16", 2e-2, "contiguous"), ("bf16", 2e-2, "interleaved")])
+@pytest.mark.parametrize("prec,tol,layout", [("fp32", 1e-5, "contiguous"), ("bf16", 2e-2, "contiguous"), ("bf16", 2e-2, "interleaved"), ("bf16", 2e-2, "strided")])
 def test_ray_sharded_two_gpus_matches_one(prec, tol, layout):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

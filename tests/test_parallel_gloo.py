@@ -44,6 +44,12 @@ def test_interleaved_ray_shards_partition_and_balance():
             assert max(sizes) - min(sizes) <= 128
     with pytest.raises(ValueError):
         parallel.ray_shard_indices(10, 64, 2, 2)
+    # tile = 1 ("strided" layout): ray i on rank i % G
+    for n in (1000, 7, 0):
+        for world in (1, 2, 8):
+            ids = [parallel.ray_shard_indices(n, 64, r, world, tile=1) for r in range(world)]
+            assert sorted(torch.cat(ids).tolist()) == list(range(n))
+            assert all(torch.all(i % world == r) for r, i in enumerate(ids))
 
 
 def test_object_shards_partition():
