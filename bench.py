@@ -286,14 +286,15 @@ def run_ours(args):
     all_streams = list(streams)
     streams[:] = [main_stream]
     step_resident()
-    lib.snb_kernel_timing_enable(1)
+    hnd = model._handle(dev).h
+    lib.snb_kernel_timing_enable(hnd, 1)
     ms_single = timed(step_resident, args.steps)
     kern = {}
     for which, name in ((0, "fwd"), (1, "bwd")):
         buf = (ctypes.c_float * 4096)()
-        n = lib.snb_kernel_timing_read(which, buf, 4096)
+        n = lib.snb_kernel_timing_read(hnd, which, buf, 4096)
         kern[name] = [buf[i] for i in range(n)]
-    lib.snb_kernel_timing_enable(0)
+    lib.snb_kernel_timing_enable(hnd, 0)
     streams[:] = all_streams
     for _ in range(2):
         step_e2e()

@@ -135,22 +135,23 @@ int snb_set_weights(snb_handle h, const float* const* tensors, int32_t n_tensors
 /* bf16 mode only: re-tile the fp32 weights into the bf16 shared-memory images the tcgen05 kernels
  * stream with bulk copies.  packed must hold snb_packed_bytes(h).  Call again after weights change. */
 size_t snb_packed_bytes(snb_handle h);
-/* Test hook: when non-NULL, the next bf16 forwards also dump every step's post-epilogue fp32 activations to
+/* The four hooks below are PER HANDLE (no process-global state): they affect only calls made through `h`.
+ * Test hook: when non-NULL, the next bf16 forwards also dump every step's post-epilogue fp32 activations to
  * acts [n_steps][n_rows][256] (n_steps = shape_blocks + texture_blocks + 4).  Pass NULL to switch it off. */
-int snb_tc_set_debug(float* acts);
+int snb_tc_set_debug(snb_handle h, float* acts);
 /* Tuning hook: when non-NULL (device memory, >= 8 B x 4 x 2 x steps x tile pairs of CTA 0), CTA 0 of the next bf16 decoder
  * kernels writes clock64 stamps [pair][step][slot][4] = {operand-ready seen by the MMA warp, MMAs issued, accumulator-ready
  * seen by the epilogue, epilogue published}.  tools/trace_pipeline.py prints the timeline.  Pass NULL to switch it off. */
-int snb_tc_set_trace(long long* stamps);
+int snb_tc_set_trace(snb_handle h, long long* stamps);
 /* Test / tuning hook: which two-tile decoder kernels frozen-weight calls use.  1: the cta_group::2 kernels (one M = 256 MMA over
  * the CTA pair, half of every weight stage per SM) wherever they apply (every object owns a multiple of 256 rows); 0: always the
  * cta_group::1 kernels; -1 (initial state): the SNB_TC_CG2 environment variable, default 1.  Both give the same arithmetic. */
-int snb_tc_set_cg2(int32_t mode);
+int snb_tc_set_cg2(snb_handle h, int32_t mode);
 /* Measurement hook (bench.py roofline): while enabled, every bf16 decoder call records a CUDA-event pair on its
  * launch stream around the tcgen05 kernel alone.  snb_kernel_timing_read (after a synchronize) copies up to max_n
  * durations in ms to HOST memory and returns how many; which = 0 forward, 1 backward.  Enabling clears old events. */
-int snb_kernel_timing_enable(int32_t on);
-int snb_kernel_timing_read(int32_t which, float* ms_host, int32_t max_n);
+int snb_kernel_timing_enable(snb_handle h, int32_t on);
+int snb_kernel_timing_read(snb_handle h, int32_t which, float* ms_host, int32_t max_n);
 int snb_pack_weights(snb_handle h, void* packed, void* stream);
 /* Scratch the forward needs (and the backward re-reads): activations in fp32 mode, ReLU masks +
  * per-sample sigma/rgb in bf16 mode.  n_rows = N*S samples. */

@@ -50,11 +50,11 @@ SIGNATURES = {
     "snb_layer_shape": (c_i32, [ctypes.c_void_p, c_i32, ctypes.POINTER(c_i32), ctypes.POINTER(c_i32)]),
     "snb_set_weights": (c_i32, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), c_i32]),
     "snb_packed_bytes": (c_sz, [ctypes.c_void_p]),
-    "snb_tc_set_debug": (c_i32, [c_f]),
-    "snb_tc_set_trace": (c_i32, [c_f]),
-    "snb_tc_set_cg2": (c_i32, [c_i32]),
-    "snb_kernel_timing_enable": (c_i32, [c_i32]),
-    "snb_kernel_timing_read": (c_i32, [c_i32, ctypes.POINTER(c_flt), c_i32]),
+    "snb_tc_set_debug": (c_i32, [ctypes.c_void_p, c_f]),
+    "snb_tc_set_trace": (c_i32, [ctypes.c_void_p, c_f]),
+    "snb_tc_set_cg2": (c_i32, [ctypes.c_void_p, c_i32]),
+    "snb_kernel_timing_enable": (c_i32, [ctypes.c_void_p, c_i32]),
+    "snb_kernel_timing_read": (c_i32, [ctypes.c_void_p, c_i32, ctypes.POINTER(c_flt), c_i32]),
     "snb_pack_weights": (c_i32, [ctypes.c_void_p, c_f, c_f]),
     "snb_mlp_workspace_bytes": (c_sz, [ctypes.c_void_p, c_i64, c_i64, c_i32]),
     "snb_mlp_bwd_scratch_bytes": (c_sz, [ctypes.c_void_p, c_i64, c_i64, c_i32]),

@@ -33,11 +33,8 @@ int sm_count() {
 // bf16 / tcgen05 back end (mlp_tc.cu)
 size_t tc_packed_bytes(const snb_handle_s* h);
 int tc_pack_weights(snb_handle_s* h, void* packed, cudaStream_t st);
-void tc_set_debug(float* acts);
-void tc2_set_trace(long long* buf);
-void tc2_set_cg2(int mode);
-void tc_timing_enable(int on);
-int tc_timing_read(int which, float* ms, int max_n);
+void tc_timing_enable(snb_handle_s* h, int on);
+int tc_timing_read(snb_handle_s* h, int which, float* ms, int max_n);
 size_t tc_workspace_bytes(const snb_handle_s* h, int64_t M, int64_t B);
 size_t tc_bwd_scratch_bytes(const snb_handle_s* h, int64_t M, int64_t B);
 int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
@@ -140,11 +137,14 @@ extern "C" int snb_set_weights(snb_handle h, const float* const* tensors, int32_
   return 0;
 }
 
-extern "C" int snb_tc_set_debug(float* acts) { tc_set_debug(acts); return 0; }
-extern "C" int snb_tc_set_trace(long long* stamps) { tc2_set_trace(stamps); return 0; }
-extern "C" int snb_tc_set_cg2(int32_t mode) { tc2_set_cg2(mode); return 0; }
-extern "C" int snb_kernel_timing_enable(int32_t on) { tc_timing_enable(on); return 0; }
-extern "C" int snb_kernel_timing_read(int32_t which, float* ms_host, int32_t max_n) { return tc_timing_read(which, ms_host, max_n); }
+extern "C" int snb_tc_set_debug(snb_handle h, float* acts) { SNB_REQUIRE(h, "snb_tc_set_debug: null handle"); h->dbg_acts = acts; return 0; }
+extern "C" int snb_tc_set_trace(snb_handle h, long long* stamps) { SNB_REQUIRE(h, "snb_tc_set_trace: null handle"); h->trace = stamps; return 0; }
+extern "C" int snb_tc_set_cg2(snb_handle h, int32_t mode) { SNB_REQUIRE(h, "snb_tc_set_cg2: null handle"); h->cg2_mode = mode; return 0; }
+extern "C" int snb_kernel_timing_enable(snb_handle h, int32_t on) { SNB_REQUIRE(h, "snb_kernel_timing_enable: null handle"); tc_timing_enable(h, on); return 0; }
+extern "C" int snb_kernel_timing_read(snb_handle h, int32_t which, float* ms_host, int32_t max_n) {
+  if (!h) return 0;
+  return tc_timing_read(h, which, ms_host, max_n);
+}
 
 extern "C" size_t snb_packed_bytes(snb_handle h) { return h ? tc_packed_bytes(h) : 0; }
 

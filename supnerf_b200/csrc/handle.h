@@ -1,6 +1,7 @@
 // Per-model handle shared by the MLP back ends.
 #pragma once
 #include <memory>
+#include <utility>
 #include <vector>
 #include "../../include/supnerf_b200.h"
 
@@ -19,6 +20,12 @@ struct snb_handle_s {
   // per-handle caches of pure functions of the architecture (built on first use; a handle is used by one host thread at a time)
   mutable std::shared_ptr<void> tc2_programs;   // mlp_tc2.cu: the step programs of the two-tile kernels
   mutable size_t v1_packed_bytes_cache = 0;     // mlp_tc.cu: size of the first-generation packed image
+  // test / tuning / measurement hooks, per handle (a handle is used by one host thread at a time; nothing here is process-global)
+  float* dbg_acts = nullptr;                    // snb_tc_set_debug
+  long long* trace = nullptr;                   // snb_tc_set_trace
+  int cg2_mode = -1;                            // snb_tc_set_cg2 (-1: the SNB_TC_CG2 environment variable, default 1)
+  bool timing_on = false;                       // snb_kernel_timing_enable
+  std::vector<std::pair<void*, void*>> ev_fwd, ev_bwd;   // cudaEvent_t pairs around the tcgen05 kernels
   // CodeNeRF-family layer indices
   int iX = 0, iES = 0, iSG = 0, iEV = 0, iR0 = 0, iR2 = 0;
   int iSL(int j) const { return 1 + 2 * (j - 1); }       // shape_latent_layer_j, j = 1..Bs

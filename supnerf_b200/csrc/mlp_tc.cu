@@ -76,7 +76,6 @@ struct Params {
   const float* sigma_in; const float* g_sigma; const float* g_rgb;
   float* g_xyz; float* g_viewdir; float* g_zlat;   // g_zlat [(Bs+Bt)][B][256], accumulated with atomics
   int r0_mask_slot, n_latent, ev_step;
-  int exp_flags;   // timing experiments only (env SNB_TC_EXP): 1 = producer skips the weight copies, 2 = epilogues skip their math
   Program prog;
 };
 
@@ -113,12 +112,8 @@ __device__ __forceinline__ void producer_loop(const Params& p, const Smem& sm, i
           const uint32_t stage = it % kStages, ph = (it / kStages) & 1u;
           if (lane == 0) {
             mbar_wait(sm.bar(BAR_WEMPTY + stage), ph ^ 1u);
-            if ((p.exp_flags & 1) && it >= (uint32_t)kStages) {
-              mbar_arrive(sm.bar(BAR_WFULL + stage));
-            } else {
-              mbar_expect_tx(sm.bar(BAR_WFULL + stage), bytes);
-              bulk_g2s(sm.stage_u32(stage), p.packed + off0 + (size_t)kc * bytes, bytes, sm.bar(BAR_WFULL + stage));
-            }
+            mbar_expect_tx(sm.bar(BAR_WFULL + stage), bytes);
+            bulk_g2s(sm.stage_u32(stage), p.packed + off0 + (size_t)kc * bytes, bytes, sm.bar(BAR_WFULL + stage));
           }
           __syncwarp();
         }
@@ -353,9 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_fwd_kernel(const __grid_consta
           write_pe_row<10>(sm.chunk(4), e.row, e.hh, xn);
           publish_chunk(sm, 4, lane);
         }
-        if (p.exp_flags & 2) {
-          if (st.produce_a) for (int c = 0; c < 4; ++c) publish_chunk(sm, c, lane);
-        } else if (p.dbg != nullptr) fwd_epilogue_dispatch<true>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc);
+        if (p.dbg != nullptr) fwd_epilogue_dispatch<true>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc);
         else fwd_epilogue_dispatch<false>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc);
         tc_fence_before();
       }
@@ -818,7 +811,6 @@ static void fill_common(Params& p, const snb_handle_s* h, const float* xyz, cons
   p.wsig = h->layers[h->iSG].w; p.bsig = h->layers[h->iSG].b;
   p.n_latent = h->arch.shape_blocks + h->arch.texture_blocks;
   p.ev_step = h->arch.shape_blocks + 2;  // forward step index of encoding_viewdir
-  { const char* ev = getenv("SNB_TC_EXP"); p.exp_flags = ev ? atoi(ev) : 0; }
   p.w2 = h->layers[h->iR2].w; p.b2 = h->layers[h->iR2].b;
 }
 
@@ -829,16 +821,21 @@ static int tc_grid(int64_t M) {
 }
 
 // optional kernel-only timing (bench.py roofline): CUDA events recorded on the launch stream around the tcgen05 kernels
-static bool g_timing_on = false;
-static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_ev_fwd, g_ev_bwd;
-void tc_timing_enable(int on) {
-  g_timing_on = on != 0;
-  for (auto* v : {&g_ev_fwd, &g_ev_bwd}) { for (auto& e : *v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } v->clear(); }
+void tc_timing_enable(snb_handle_s* h, int on) {
+  h->timing_on = on != 0;
+  for (auto* v : {&h->ev_fwd, &h->ev_bwd}) {
+    for (auto& e : *v) { cudaEventDestroy((cudaEvent_t)e.first); cudaEventDestroy((cudaEvent_t)e.second); }
+    v->clear();
+  }
 }
-int tc_timing_read(int which, float* ms, int max_n) {   // call after a stream/device synchronize
-  auto& v = which == 0 ? g_ev_fwd : g_ev_bwd;
+int tc_timing_read(snb_handle_s* h, int which, float* ms, int max_n) {   // call after a stream/device synchronize
+  auto& v = which == 0 ? h->ev_fwd : h->ev_bwd;
   int n = 0;
-  for (auto& e : v) { if (n >= max_n) break; float t = 0.f; if (cudaEventElapsedTime(&t, e.first, e.second) == cudaSuccess) ms[n++] = t; }
+  for (auto& e : v) {
+    if (n >= max_n) break;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, (cudaEvent_t)e.first, (cudaEvent_t)e.second) == cudaSuccess) ms[n++] = t;
+  }
   return n;
 }
 struct ScopedKernelTimer {
@@ -846,11 +843,9 @@ struct ScopedKernelTimer {
   ScopedKernelTimer(cudaStream_t s, bool enable) : st(s), on(enable) {
     if (on) { cudaEventCreate(&ev.first); cudaEventCreate(&ev.second); cudaEventRecord(ev.first, st); }
   }
-  void stop(std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& into) { if (on) { cudaEventRecord(ev.second, st); into.push_back(ev); } }
+  void stop(std::vector<std::pair<void*, void*>>& into) { if (on) { cudaEventRecord(ev.second, st); into.push_back({(void*)ev.first, (void*)ev.second}); } }
 };
 
-static float* g_tc_debug_acts = nullptr;  // test hook (snb_tc_set_debug): per-step post-epilogue fp32 activations
-void tc_set_debug(float* acts) { g_tc_debug_acts = acts; }
 
 int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, void* ws, cudaStream_t st,
@@ -868,22 +863,22 @@ int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, in
   uint8_t* eimg = (uint8_t*)ws + ws_eimg_off(h, B);
   if (latent_forward_fused(h, B, shape_latent, texture_latent, zlat, ebias, st, use_v2(h) ? eimg : nullptr)) return 1;
   if (use_v2(h)) {
-    ScopedKernelTimer tm2(st, g_timing_on);
+    ScopedKernelTimer tm2(st, h->timing_on);
     if (tc2_launch_fwd(h, (const uint8_t*)h->packed + v1_packed_bytes(h), xyz, viewdir, M, B, eimg, masks, sigma, rgb,
-                       g_tc_debug_acts, fsave, st, m_dev, tile_start)) return 1;
-    tm2.stop(g_ev_fwd);
+                       h->dbg_acts, fsave, st, m_dev, tile_start)) return 1;
+    tm2.stop(const_cast<snb_handle_s*>(h)->ev_fwd);
     SNB_LAUNCH_CHECK();
     return 0;
   }
   TcPlan pl = build_plan(h);
   Params p;
   fill_common(p, h, xyz, viewdir, M, B, ebias, masks);
-  p.sigma = sigma; p.rgb = rgb; p.dbg = g_tc_debug_acts;
+  p.sigma = sigma; p.rgb = rgb; p.dbg = h->dbg_acts;
   p.prog = pl.fwd;
   SNB_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
-  ScopedKernelTimer tm(st, g_timing_on);
+  ScopedKernelTimer tm(st, h->timing_on);
   tc_fwd_kernel<<<tc_grid(M), kThreads, SM_ALLOC, st>>>(p);
-  tm.stop(g_ev_fwd);
+  tm.stop(const_cast<snb_handle_s*>(h)->ev_fwd);
   SNB_LAUNCH_CHECK();
   return 0;
 }
@@ -919,10 +914,10 @@ int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, i
         SNB_CHECK_CUDA(cudaMemsetAsync(g_weights[2 * i + 1], 0, sizeof(float) * h->layers[i].out, st));
       }
     }
-    ScopedKernelTimer tm2(st, g_timing_on);
+    ScopedKernelTimer tm2(st, h->timing_on);
     if (tc2_launch_bwd(h, (const uint8_t*)h->packed + v1_packed_bytes(h), xyz, viewdir, M, B, masks, sigma, g_sigma, g_rgb, g_xyz,
                        g_viewdir, g_zlat, bsave, st, m_dev, tile_start)) return 1;
-    tm2.stop(g_ev_bwd);
+    tm2.stop(const_cast<snb_handle_s*>(h)->ev_bwd);
     SNB_LAUNCH_CHECK();
     if (!want_w) return latent_backward_fused(h, B, zlat, g_zlat, g_shape_latent, g_texture_latent, st, fold_tmp);
     const uint8_t* fsave = align1k((uint8_t*)ws + tc_workspace_bytes(h, M, B));
@@ -938,9 +933,9 @@ int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, i
   p.r0_mask_slot = pl.r0_slot;
   p.prog = g_xyz ? pl.bwd_full : pl.bwd_noxyz;
   SNB_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
-  ScopedKernelTimer tm(st, g_timing_on);
+  ScopedKernelTimer tm(st, h->timing_on);
   tc_bwd_kernel<<<tc_grid(M), kThreads, SM_ALLOC, st>>>(p);
-  tm.stop(g_ev_bwd);
+  tm.stop(const_cast<snb_handle_s*>(h)->ev_bwd);
   SNB_LAUNCH_CHECK();
   return latent_backward_fused(h, B, zlat, g_zlat, g_shape_latent, g_texture_latent, st);
 }

@@ -54,7 +54,7 @@ constexpr uint32_t SM_PEV = SM_RING + kRing2 * kStageBytes2;      // CG2 forward
 constexpr uint32_t kPevBytes = 8192;
 static_assert(SM_PEV + 2 * kPevBytes <= SM_RING + kRing * kStageBytes, "the PE(viewdir) tiles live inside the ring footprint");
 constexpr uint32_t SM_TAB = SM_RING + kRing * kStageBytes;
-constexpr uint32_t TAB_BIAS = 0;                                 // (unused since the biases ride on the tensor core; kept for layout stability)
+constexpr uint32_t TAB_BIAS = 0;                                 // tile-end scratch: [slot][128][4] floats (the column halves' partial heads / d xyz)
 constexpr uint32_t TAB_LAT = TAB_BIAS + 4 * 1024;                // fwd: [128][16] bf16 all-ones A tile (4 KB); bwd: [slot][kMaxLat][256] latent column sums
 constexpr uint32_t kBiasStageRowBytes = 32;                       // bias stage: [N rows][16 k] bf16, 32-byte swizzle
 constexpr uint32_t TAB_WSIG = TAB_LAT + 2 * kMaxLat * 1024;      // [256]
@@ -104,7 +104,6 @@ struct Params {
   const int32_t* tile_start;   // optional (batched render): B + 1 ascending even tile offsets, object b owns tiles [tile_start[b], tile_start[b+1])
   uint8_t* save;      // training mode (weight gradients wanted): [tile][Program::save_tile_bytes] copies of every step's A operand
   long long* trace;   // timing experiments only: CTA 0 writes clock64 stamps [pair][step][slot][4] = READY seen, MMAs issued, ACC seen, published
-  int exp_flags;   // timing experiments only (env SNB_TC_EXP): 1 = producer skips the weight copies, 4 = every stage copies the same image
   Program prog;
 };
 
@@ -466,7 +465,7 @@ __device__ __forceinline__ void mma_loop(const Params& p, const Smem& sm, int64_
           if (++stage == RING) { stage = 0; ph ^= 1u; }
         }
         if (saving) {   // the epilogue overwrites the chunks after BAR_ACC: the bulk store must have read them by then
-          if (lane_m == 0 && !(p.exp_flags & 8)) bulk_wait_read_all();   // exp flag 8 (timing experiment only, WRONG results): no wait
+          if (lane_m == 0) bulk_wait_read_all();
           __syncwarp();
         }
         if (CG2) umma2_commit_elect(sm.bar(BAR_ACC + slot));
@@ -1236,8 +1235,6 @@ int tc2_pack_weights(const snb_handle_s* h, void* packed, cudaStream_t st) {
   return 0;
 }
 
-static long long* g_trace = nullptr;   // test / tuning hook (snb_tc_set_trace)
-void tc2_set_trace(long long* buf) { g_trace = buf; }
 
 static void fill_common2(tc2::Params& p, const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M,
                          int64_t B, const uint8_t* eimg, uint32_t* masks) {
@@ -1247,15 +1244,19 @@ static void fill_common2(tc2::Params& p, const snb_handle_s* h, const void* pack
   p.wsig = h->layers[h->iSG].w; p.bsig = h->layers[h->iSG].b;
   p.w2 = h->layers[h->iR2].w; p.b2 = h->layers[h->iR2].b;
   p.n_latent = h->arch.shape_blocks + h->arch.texture_blocks;
-  { static const int exp_env = [] { const char* ev = getenv("SNB_TC_EXP"); return ev ? atoi(ev) : 0; }(); p.exp_flags = exp_env; }
-  p.trace = g_trace;
+  p.trace = h->trace;
 }
 
 // Grid = a whole number of clusters, at most as many as can be co-resident (persistent kernel, 1 CTA per SM; clusters cannot
 // span GPCs, so a GPC with an odd SM count leaves one SM idle), at most one CTA per tile pair (rounded up to a full cluster).
 template <typename K>
 static int tc2_grid(K kernel, int64_t M) {
-  static int max_ctas = 0;   // same answer for every kernel variant of this file (same block size / shared memory)
+  // co-resident CTAs per device: the same answer for every kernel variant of this file (same block size / shared memory); cached
+  // per device, written at most once per (thread, device) -- host threads driving different GPUs never share an entry
+  static thread_local int cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); dev = 0; }
+  int& max_ctas = cached[dev];
   if (max_ctas == 0) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(sm_count() / kCluster * kCluster), 1, 1);
@@ -1277,26 +1278,24 @@ static int tc2_grid(K kernel, int64_t M) {
 
 // cta_group::2 kernels: frozen weights only (no operand saves), and every 256-row super tile inside one object (the pair's two
 // tiles share the B operand, hence the per-object bias stage).  SNB_TC_CG2=0 selects the cta_group::1 kernels.
-static int g_cg2_mode = -1;   // snb_tc_set_cg2
-void tc2_set_cg2(int mode) { g_cg2_mode = mode; }
-static bool tc2_use_cg2(const tc2::Params& p) {
+static bool tc2_use_cg2(const snb_handle_s* h, const tc2::Params& p) {
   static const int env = [] { const char* e = getenv("SNB_TC_CG2"); return e ? atoi(e) : 1; }();
-  const int want = g_cg2_mode < 0 ? env : g_cg2_mode;
+  const int want = h->cg2_mode < 0 ? env : h->cg2_mode;
   return want != 0 && p.save == nullptr && p.dbg == nullptr && (p.B == 1 || p.tile_start != nullptr || p.rows_per_obj % 256 == 0);
 }
 
 // opt-in shared-memory size of every kernel variant, once per device
 static int tc2_init_device() {
-  static bool done[64] = {};
+  static std::atomic<bool> done[64];   // setting the attribute twice is harmless: the flag only saves the calls
   int dev = 0;
   SNB_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && done[dev]) return 0;
+  if (dev >= 0 && dev < 64 && done[dev].load(std::memory_order_acquire)) return 0;
   SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
   SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
   SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
   SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
   SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
-  if (dev >= 0 && dev < 64) done[dev] = true;
+  if (dev >= 0 && dev < 64) done[dev].store(true, std::memory_order_release);
   return 0;
 }
 
@@ -1324,7 +1323,7 @@ int tc2_launch_fwd(const snb_handle_s* h, const void* packed2, const float* xyz,
   p.save = save;
   p.m_dev = m_dev;
   p.tile_start = tile_start;
-  const bool cg2 = tc2_use_cg2(p);
+  const bool cg2 = tc2_use_cg2(h, p);
   p.prog = save ? pl.fwd_train : ((cg2 && !dbg) ? pl.fwd_merged : pl.fwd);
   if (tc2_init_device()) return 1;
   if (dbg) {
@@ -1351,7 +1350,7 @@ int tc2_launch_bwd(const snb_handle_s* h, const void* packed2, const float* xyz,
   SNB_REQUIRE(save == nullptr || g_xyz != nullptr, "tc2 backward: training mode runs the full program (g_xyz scratch required)");
   p.prog = g_xyz ? pl.bwd_full : pl.bwd_noxyz;
   if (tc2_init_device()) return 1;
-  if (tc2_use_cg2(p)) {
+  if (tc2_use_cg2(h, p)) {
     SNB_CHECK_CUDA(tc2_launch(tc2_bwd_kernel<true>, tc2_grid(tc2_bwd_kernel<true>, M), st, p));
   } else {
     SNB_CHECK_CUDA(tc2_launch(tc2_bwd_kernel<false>, tc2_grid(tc2_bwd_kernel<false>, M), st, p));

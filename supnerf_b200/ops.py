@@ -13,7 +13,6 @@ from ._lib import check, f32c, on_device, ptr, require_cuda, stream_ptr
 WHITE_BKGD, SIGMA_RELU = 1, 2
 PREC = {"fp32": 0, "bf16": 1}
 PREC_BF16_TRAIN = 2  # selected automatically in bf16 mode when a weight requires grad (SNB_PREC_BF16_TRAIN)
-TIMING_HOOK = None  # bench.py: callable(which, (start_event, end_event)) around the decoder C-ABI calls
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -306,22 +305,6 @@ class DecoderHandle:
         self._packed_key = key
 
 
-def _timing_start():
-    if TIMING_HOOK is None:
-        return None
-    e = torch.cuda.Event(enable_timing=True)
-    e.record()
-    return e
-
-
-def _timing_end(which, e0):
-    if e0 is None or TIMING_HOOK is None:
-        return
-    e1 = torch.cuda.Event(enable_timing=True)
-    e1.record()
-    TIMING_HOOK(which, (e0, e1))
-
-
 class _Decoder(torch.autograd.Function):
     @staticmethod
     def forward(ctx, handle, precision, n_objs, xyz, viewdir, shape_latent, texture_latent, *weights):
@@ -340,10 +323,8 @@ class _Decoder(torch.autograd.Function):
         sigma = torch.empty(m, device=dev, dtype=torch.float32)
         rgb = torch.empty(m, 3, device=dev, dtype=torch.float32)
         with on_device(dev):
-            ev = _timing_start()
             check(lib.snb_mlp_fwd(handle.h, precision, ptr(xyz), ptr(viewdir), m, n_objs, ptr(shape_latent), ptr(texture_latent),
                                   ptr(sigma), ptr(rgb), ptr(ws), stream_ptr()), "snb_mlp_fwd")
-            _timing_end("fwd", ev)
         ctx.save_for_backward(xyz, viewdir, shape_latent, texture_latent, sigma, ws, *weights)
         ctx.meta = (handle, precision, n_objs)
         return sigma, rgb
@@ -370,11 +351,9 @@ class _Decoder(torch.autograd.Function):
         handle.set_weights(weights, saved=True)
         scratch = torch.empty(lib.snb_mlp_bwd_scratch_bytes(handle.h, m, n_objs, precision), dtype=torch.uint8, device=dev)
         with on_device(dev):
-            ev = _timing_start()
             check(lib.snb_mlp_bwd(handle.h, precision, ptr(xyz), ptr(viewdir), m, n_objs, ptr(shape_latent), ptr(texture_latent),
                                   ptr(sigma), ptr(g_sigma), ptr(g_rgb), ptr(ws), ptr(scratch), ptr(g_xyz), ptr(g_vd), ptr(g_sl),
                                   ptr(g_tl), gw_arr, stream_ptr()), "snb_mlp_bwd")
-            _timing_end("bwd", ev)
         out_w = tuple(gws) if need_w else tuple(None for _ in weights)
         return (None, None, None, g_xyz, g_vd, g_sl if need[5] else None, g_tl if need[6] else None) + out_w
 

@@ -26,12 +26,13 @@ def run(n):
 run(3)
 import ctypes
 lib = snb._lib.load()
-lib.snb_kernel_timing_enable(1)
+hnd = m._handle(torch.device(dev)).h
+lib.snb_kernel_timing_enable(hnd, 1)
 f, b = run(10)
 buf = (ctypes.c_float * 64)()
-kf = [buf[i] for i in range(lib.snb_kernel_timing_read(0, buf, 64))]
-kb = [buf[i] for i in range(lib.snb_kernel_timing_read(1, buf, 64))]
-lib.snb_kernel_timing_enable(0)
+kf = [buf[i] for i in range(lib.snb_kernel_timing_read(hnd, 0, buf, 64))]
+kb = [buf[i] for i in range(lib.snb_kernel_timing_read(hnd, 1, buf, 64))]
+lib.snb_kernel_timing_enable(hnd, 0)
 fl = 2 * 449664 * N * S / 1e12
 if kf: print(f"   kernel only: fwd {min(kf):.3f} ms ({2*449664*N*S/1e12/min(kf)*1e3:.0f} TF/s)  bwd {min(kb):.3f} ms ({2*449664*N*S/1e12/min(kb)*1e3:.0f} TF/s)")
 print(f"SNB_TC_EXP={os.environ.get('SNB_TC_EXP','0')} fwd {f:.3f} ms ({fl/f*1e3:.0f} TF/s)  bwd {b:.3f} ms ({fl/b*1e3:.0f} TF/s)")

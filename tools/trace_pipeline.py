@@ -24,16 +24,16 @@ buf = torch.zeros(n_pairs * n_steps * 2 * 4 + 64, dtype=torch.int64, device=dev)
 sig, rgb = m(xyz, vd, shp, tex)   # warm-up
 torch.cuda.synchronize()
 if which == "fwd":
-    lib.snb_tc_set_trace(ctypes.c_void_p(buf.data_ptr()))
+    lib.snb_tc_set_trace(m._handle(torch.device(dev)).h, ctypes.c_void_p(buf.data_ptr()))
     sig, rgb = m(xyz, vd, shp, tex)
     torch.cuda.synchronize()
-    lib.snb_tc_set_trace(None)
+    lib.snb_tc_set_trace(m._handle(torch.device(dev)).h, None)
 else:
     gs, gr = torch.ones_like(sig), torch.ones_like(rgb)
-    lib.snb_tc_set_trace(ctypes.c_void_p(buf.data_ptr()))
+    lib.snb_tc_set_trace(m._handle(torch.device(dev)).h, ctypes.c_void_p(buf.data_ptr()))
     torch.autograd.grad([sig, rgb], [xyz, vd, shp, tex], [gs, gr])
     torch.cuda.synchronize()
-    lib.snb_tc_set_trace(None)
+    lib.snb_tc_set_trace(m._handle(torch.device(dev)).h, None)
 t = buf[: n_pairs * n_steps * 8].cpu().reshape(n_pairs, n_steps, 2, 4)
 pair = 10
 t0 = int(t[pair][t[pair] > 0].min())
