@@ -527,7 +527,9 @@ def run_c4(snb, dev, rank, world, steps, warmup, precision):
     def leaves():
         return obj["cam_pose"].to(dev).requires_grad_(), shp0.to(dev).requires_grad_(), tex0.to(dev).requires_grad_()
 
-    shard = parallel.RayShard(R, m, dev, img, mask, obj["wlh"], K, obj["roi"], IM, rank=rank, world=world, layout=LAYOUT)
+    # the gradient all-reduce goes through the C ABI (snb_allreduce_grads) on this process' own NCCL communicator
+    comm = parallel.NcclComm(dev) if world > 1 else None
+    shard = parallel.RayShard(R, m, dev, img, mask, obj["wlh"], K, obj["roi"], IM, rank=rank, world=world, layout=LAYOUT, comm=comm)
     whole = parallel.RayShard(R, m, dev, img, mask, obj["wlh"], K, obj["roi"], IM, rank=0, world=1, layout=LAYOUT, group=None)
     # ---- parity, on this run: the sharded step against the SAME step on one rank (every rank renders the whole object once)
     cam, shp, tex = leaves()
@@ -623,8 +625,11 @@ def run_c4(snb, dev, rank, world, steps, warmup, precision):
            "phases_ms_min_over_ranks": dict(zip(names, [round(v, 4) for v in ph_min])),
            "allreduce_us": round(1e3 * ph_max[3], 1),
            "phase_note": "CUDA events on the launch stream in a second timed pass of the same K steps; `allreduce` = torch.cat of the three "
-                         "gradients + loss, ncclAllReduce(525 floats), views back; it also absorbs the wait for the slowest rank's backward",
+                         "gradients + loss, snb_allreduce_grads (ncclAllReduce of 525 floats through the C ABI), views back; it also absorbs "
+                         "the wait for the slowest rank's backward",
            "multi_gpu_parity": "pass" if ok else "FAIL", "parity_checks": checks}
+    if comm is not None:
+        comm.destroy()
     return out
 
 

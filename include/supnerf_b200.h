@@ -246,6 +246,14 @@ int snb_refine_loss_batch_bwd(const float* rgb, const float* acc, const float* t
                               int64_t rays_per_obj, float occ_coef, const void* scratch, const float* g_loss, float* g_rgb,
                               float* g_acc, void* stream);
 
+/* ---- gradient all-reduce of the sharded modes --------------------------------------------------------
+ * No reference counterpart (the reference only has nn.DataParallel, trainer_nerf_nuscenes.py:94-95).  ONE in-place
+ * ncclAllReduce(sum, fp32) of `flat` (n floats, device memory) over the caller's communicator (an ncclComm_t, passed as void*)
+ * on the caller's stream: the ray-sharded mode reduces [d cam_pose (12) | d shapecode (D) | d texturecode (D) | loss] (2.1 KB),
+ * the data-parallel mode its flat weight-gradient buffer.  NCCL is resolved at run time from the libnccl.so.2 the process
+ * already uses (torch.distributed's); the library does not link it. */
+int snb_allreduce_grads(snb_handle h, void* nccl_comm, float* flat, size_t n, void* stream);
+
 /* ---- refine-iteration loss (the caller just above the render) -------------------------------
  * Replaces the inline loss of optimizer_nuscenes.py:729-736 (= optimizer_kitti.py / optimizer_waymo.py, and the render
  * losses of trainer_unified_nuscenes.py:316-332):

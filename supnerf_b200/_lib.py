@@ -74,6 +74,7 @@ SIGNATURES = {
     "snb_render_bwd_scratch_bytes": (c_sz, [ctypes.c_void_p, ctypes.POINTER(SnbRenderDesc)]),
     "snb_render_fwd": (c_i32, [ctypes.c_void_p, ctypes.POINTER(SnbRenderDesc)] + [c_f] * 14),
     "snb_render_bwd": (c_i32, [ctypes.c_void_p, ctypes.POINTER(SnbRenderDesc)] + [c_f] * 16 + [ctypes.POINTER(ctypes.c_void_p), c_f]),
+    "snb_allreduce_grads": (c_i32, [ctypes.c_void_p, ctypes.c_void_p, c_f, c_sz, c_f]),
     "snb_render_batch_workspace_bytes": (c_sz, [ctypes.c_void_p, ctypes.POINTER(SnbBatchDesc)]),
     "snb_render_batch_scratch_bytes": (c_sz, [ctypes.c_void_p, ctypes.POINTER(SnbBatchDesc)]),
     "snb_render_batch_fwd": (c_i32, [ctypes.c_void_p, ctypes.POINTER(SnbBatchDesc)] + [c_f] * 15),

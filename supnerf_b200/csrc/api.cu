@@ -216,3 +216,40 @@ extern "C" int snb_mlp_bwd(snb_handle h, int32_t precision, const float* xyz, co
   return f32_backward(h, xyz, viewdir, M, B, shape_latent, texture_latent, sigma, g_sigma, g_rgb, (const float*)workspace,
                       (float*)scratch, g_xyz, g_viewdir, g_shape_latent, g_texture_latent, g_weights, (cudaStream_t)stream);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Gradient all-reduce of the sharded modes: ONE ncclAllReduce(sum, fp32) over the caller's flat buffer
+// -- [d cam_pose (12) | d shapecode (D) | d texturecode (D) | loss] in the ray-sharded mode (2.1 KB), the flat weight-gradient
+// buffer in the data-parallel mode -- on the caller's communicator and stream.  NCCL is not linked: the entry point is looked
+// up in the libnccl the process already uses (torch's), so the library has no NCCL dependency of its own.
+// ---------------------------------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+
+namespace {
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int /*ncclDataType_t*/, int /*ncclRedOp_t*/, void* /*ncclComm_t*/, cudaStream_t);
+nccl_allreduce_fn find_nccl_allreduce() {
+  static std::atomic<nccl_allreduce_fn> cached{nullptr};
+  nccl_allreduce_fn f = cached.load(std::memory_order_acquire);
+  if (f) return f;
+  void* sym = dlsym(RTLD_DEFAULT, "ncclAllReduce");
+  if (!sym) {
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // the instance torch.distributed already loaded
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW);
+    if (lib) sym = dlsym(lib, "ncclAllReduce");
+  }
+  f = reinterpret_cast<nccl_allreduce_fn>(sym);
+  if (f) cached.store(f, std::memory_order_release);
+  return f;
+}
+}  // namespace
+
+extern "C" int snb_allreduce_grads(snb_handle h, void* nccl_comm, float* flat, size_t n, void* stream) {
+  (void)h;   // the handle names the model the gradients belong to; the reduction itself is stateless
+  SNB_REQUIRE(nccl_comm != nullptr && (flat != nullptr || n == 0), "snb_allreduce_grads: null communicator or buffer");
+  if (n == 0) return 0;
+  nccl_allreduce_fn f = find_nccl_allreduce();
+  SNB_REQUIRE(f != nullptr, "snb_allreduce_grads: ncclAllReduce not found (libnccl.so.2 is not loaded in this process)");
+  const int rc = f(flat, flat, n, /*ncclFloat32*/ 7, /*ncclSum*/ 0, nccl_comm, (cudaStream_t)stream);
+  SNB_REQUIRE(rc == 0, "snb_allreduce_grads: ncclAllReduce failed with ncclResult_t %d", rc);
+  return 0;
+}

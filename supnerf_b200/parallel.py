@@ -70,7 +70,7 @@ def refine_loss_sharded(rgb_rays, acc_rays, rgb_tgt, occ_pixels, occ_all, loss_o
     return losses.refine_loss(rgb_rays, acc_rays, rgb_tgt, occ_pixels, loss_occ_coef, den=den)[0]
 
 
-def allreduce_grads(params, loss=None, group=None, scale=None, collective=True):
+def allreduce_grads(params, loss=None, group=None, scale=None, collective=True, comm=None):
     """Sum the gradients of `params` (cam_pose, shapecode, texturecode, ...) and, if given, the partial loss over all ranks
     with ONE all_reduce of one flat fp32 buffer (2.1 KB for 12 + 256 + 256 + 1 floats): one gather kernel (torch.cat) in, the
     collective, and the parameters' ``.grad`` become VIEWS of the reduced buffer (no copy back).  Returns the global loss
@@ -79,7 +79,9 @@ def allreduce_grads(params, loss=None, group=None, scale=None, collective=True):
     if loss is not None:
         flat.append(loss.detach().reshape(1).float())
     buf = torch.cat(flat)
-    if collective and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    if collective and comm is not None and comm.world > 1:
+        comm.allreduce_(buf)        # the C-ABI collective (snb_allreduce_grads) on this process' own NCCL communicator
+    elif collective and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     if scale is not None:
         buf.mul_(scale)          # one kernel over the flat buffer (data-parallel averaging)
@@ -104,6 +106,65 @@ def allreduce_weight_grads(model, group=None, average=True):
     g = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     allreduce_grads(params, None, group, scale=(1.0 / g) if (average and g > 1) else None)
     return sum(p.numel() for p in params)
+
+
+class NcclComm:
+    """An NCCL communicator of this process' own (ncclCommInitRank over the ranks of `group`, the unique id broadcast through
+    torch.distributed), for the C-ABI all-reduce ``snb_allreduce_grads(handle, ncclComm_t, flat, n, stream)``: the collective then is
+    ONE call into libsupnerf_b200.so on the caller's stream, with no torch.distributed bookkeeping on the step's critical path.
+    Uses the libnccl.so.2 torch already loaded."""
+
+    def __init__(self, device, group=None):
+        import ctypes
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("NcclComm needs an initialised torch.distributed process group (for the rendezvous)")
+        self.device = torch.device(device)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        try:
+            self._nccl = ctypes.CDLL("libnccl.so.2")
+        except OSError:
+            import glob
+            import os
+            cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so.2"))
+            if not cands:
+                raise
+            self._nccl = ctypes.CDLL(cands[0])
+
+        class UniqueId(ctypes.Structure):
+            _fields_ = [("internal", ctypes.c_byte * 128)]
+        uid = UniqueId()
+        if self.rank == 0:
+            rc = self._nccl.ncclGetUniqueId(ctypes.byref(uid))
+            if rc != 0:
+                raise RuntimeError("ncclGetUniqueId failed: %d" % rc)
+        buf = torch.frombuffer(bytearray(bytes(uid.internal)), dtype=torch.uint8).clone().to(self.device)
+        dist.broadcast(buf, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = bytes(buf.cpu().numpy().tobytes())
+        ctypes.memmove(ctypes.byref(uid), raw, 128)
+        self.comm = ctypes.c_void_p()
+        self._nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, UniqueId, ctypes.c_int]
+        with torch.cuda.device(self.device):
+            rc = self._nccl.ncclCommInitRank(ctypes.byref(self.comm), self.world, uid, self.rank)
+        if rc != 0:
+            raise RuntimeError("ncclCommInitRank failed: %d" % rc)
+
+    def allreduce_(self, flat, handle=None):
+        """In-place sum of the flat fp32 CUDA tensor over the ranks, on the current stream (snb_allreduce_grads)."""
+        from . import _lib
+        from ._lib import check, on_device, ptr, stream_ptr
+        if flat.dtype != torch.float32 or not flat.is_cuda or not flat.is_contiguous():
+            raise ValueError("NcclComm.allreduce_: a contiguous fp32 CUDA tensor is required")
+        lib = _lib.load()
+        with on_device(flat.device):
+            check(lib.snb_allreduce_grads(handle, self.comm, ptr(flat), flat.numel(), stream_ptr()), "snb_allreduce_grads")
+        return flat
+
+    def destroy(self):
+        import ctypes
+        if getattr(self, "comm", None):
+            self._nccl.ncclCommDestroy.argtypes = [ctypes.c_void_p]
+            self._nccl.ncclCommDestroy(self.comm)
+            self.comm = None
 
 
 def _flat_view(g):
@@ -272,10 +333,11 @@ class RayShard:
     backward -> ONE all_reduce(sum) of [d cam_pose | d shapecode | d texturecode | loss]   with no per-step index arithmetic."""
 
     def __init__(self, renderer, model, device, img, mask_occ, obj_sz, K, roi, im_sz, rank=None, world=None, layout="interleaved",
-                 group=None):
+                 group=None, comm=None):
         self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
         self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         self.renderer, self.model, self.device, self.group = renderer, model, torch.device(device), group
+        self.comm = comm      # optional NcclComm: the gradient all-reduce then goes through the C ABI (snb_allreduce_grads)
         self.obj_sz, self.K, self.layout = obj_sz, K.to(self.device), layout
         dev = self.device
         px, py = U._pixel_grid_on(dev, roi, [im_sz, im_sz])
@@ -312,7 +374,7 @@ class RayShard:
         part.backward()
         mark("backward")
         # a RayShard built with world=1 (the one-GPU anchor of a multi-rank run) must not enter a collective the other ranks skip
-        loss = allreduce_grads([cam_pose, shapecode, texturecode], part, self.group, collective=self.world > 1)
+        loss = allreduce_grads([cam_pose, shapecode, texturecode], part, self.group, collective=self.world > 1, comm=self.comm)
         mark("allreduce")
         return loss, rgb, dep, acc
 

@@ -51,7 +51,12 @@ def _worker(rank, world, port, prec, q, layout="contiguous"):
                                                                            obj["K"], obj["roi"], shp, tex, im_sz=IM, layout=layout)
         part = snb.parallel.refine_loss_sharded(rgb, acc, tgt, occ, occ_all)
         part.backward()
-        loss = snb.parallel.allreduce_grads([cam, shp, tex], part)
+        # the strided case sends the collective through the C ABI (snb_allreduce_grads on the process' own NCCL communicator)
+        comm = snb.parallel.NcclComm(dev) if layout == "strided" else None
+        loss = snb.parallel.allreduce_grads([cam, shp, tex], part, comm=comm)
+        torch.cuda.synchronize()
+        if comm is not None:
+            comm.destroy()
         full = snb.parallel.gather_rays(rgb.detach(), IM * IM, S, layout=layout)
         q.put((rank, float(loss), cam.grad.cpu(), shp.grad.cpu(), tex.grad.cpu(), full.cpu()))
     finally:
