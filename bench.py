@@ -675,13 +675,44 @@ def run_c5(snb, dev, rank, world, steps, warmup, precision):
     early = [p_ for p_ in m.parameters() if id(p_) not in seen]          # decoder, pose head, encoder heads: ready first
     n_params = sum(p_.numel() for p_ in m.parameters())
     opt = torch.optim.AdamW([{"params": list(m.parameters()), "lr": 1e-4}, {"params": [shp, tex], "lr": 1e-3}], fused=True)
+    # The library stages of the step (the cuDNN encoder, ~330 launches forward + backward; the three pose-regress iterations, ~600
+    # small torch kernels) are launch-bound when issued eagerly (the eager step takes 21.6 ms on one B200, of which 2.5 ms is the
+    # render): both are captured as CUDA graphs (forward and backward) with torch.cuda.make_graphed_callables; the render half is
+    # the package's own kernels.  If a capture fails the stage stays eager (reported).
+    graphed = {"encoder": False, "pose_regress": False}
+    K_inv = torch.linalg.inv(K)
+    img_cl = img.contiguous(memory_format=torch.channels_last)
+    encode, regress3 = m.encode_img_fast, None
+    if os.environ.get("SNB_C5_EAGER", "0") in ("", "0"):
+        try:
+            with torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False):
+                enc_g = torch.cuda.make_graphed_callables(enc, (img_cl,), num_warmup_iters=3)
+
+            def encode(_img):
+                with torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False):
+                    out = enc_g(img_cl)
+                return tuple(t.float() for t in out) + (None,)
+            graphed["encoder"] = True
+        except Exception as exc:   # noqa: BLE001
+            graphed["encoder_error"] = "%s: %s" % (type(exc).__name__, str(exc)[:200])
+        try:
+            r3 = pe.PoseRegress3(m)
+            sample = (torch.randn(B, 256, device=dev, requires_grad=True), src_pose, tgt_uv, wlh, roi, K, K_inv)
+            r3_g = torch.cuda.make_graphed_callables(r3, sample, num_warmup_iters=3)
+
+            def regress3(posecode, src, tuv, wl, ro, K_):
+                return r3_g(posecode, src, tuv, wl, ro, K_, K_inv)
+            graphed["pose_regress"] = True
+        except Exception as exc:   # noqa: BLE001
+            graphed["pose_regress_error"] = "%s: %s" % (type(exc).__name__, str(exc)[:200])
+            regress3 = None
     buckets = parallel.BucketedGradAllReduce([early, branches, trunk])
 
     def step(overlap=True):
         m.zero_grad(set_to_none=True)
         shp.grad = tex.grad = None
         losses_all, total, *_ = pe.joint_training_losses(m, hp, img, shp, tex, xyz, vd, zv, tgt, occ, src_pose, tgt_uv, roi, K, wlh, tgt_uv,
-                                                         encode=m.encode_img_fast)
+                                                         encode=encode, regress3=regress3)
         if overlap:
             total.backward()
             buckets.finish()
@@ -721,7 +752,7 @@ def run_c5(snb, dev, rank, world, steps, warmup, precision):
                      "gradients) all-reduced in 3 buckets overlapped with the encoder backward" % (B, n, S, world, n_params, n_params * 4 / 1e6),
            "scaling": "weak", "n_gpus": world, "ms_per_step": round(ms, 3), "rays_per_s": round(world * B * n / (ms / 1e3), 1),
            "decoder_tflops_per_gpu_if_step_were_decoder_only": round(flops_dec / (ms / 1e3) / 1e12, 1),
-           "loss": loss, "loss_finite": finite, "precision": precision, "parameters": n_params,
+           "loss": loss, "loss_finite": finite, "precision": precision, "parameters": n_params, "cuda_graphed_library_stages": graphed,
            "ms_per_step_without_overlap": round(ms_flat, 3) if ms_flat else None,
            "allreduce_ms_by_bucket": {"early(decoder+heads)": round(ar.get(0, 0.0), 3), "layer4 branches": round(ar.get(1, 0.0), 3),
                                       "trunk": round(ar.get(2, 0.0), 3)} if ar else None,

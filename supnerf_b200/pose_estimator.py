@@ -210,7 +210,7 @@ def matrix_to_axis_angle_batch(R):
     return w / (2 * torch.sin(t).clamp_min(1e-12)).unsqueeze(-1) * t.unsqueeze(-1)
 
 
-def pose_regress(model, im_feat_batch, src_pose_batch, tgt_uv_batch, wlh_batch, roi_batch, K_batch):
+def pose_regress(model, im_feat_batch, src_pose_batch, tgt_uv_batch, wlh_batch, roi_batch, K_batch, K_inv=None):
     """trainer_unified_nuscenes.py:150-195 -> (loss (B, 8), pred_pose_batch (B, 3, 4))."""
     src_uv = view_points_batch(corners_of_box_batch(src_pose_batch.detach(), wlh_batch), K_batch, normalize=True)
     src_uv_norm, dim_batch = normalize_by_roi(src_uv[:, :2, :], roi_batch, need_square=True)
@@ -226,21 +226,45 @@ def pose_regress(model, im_feat_batch, src_pose_batch, tgt_uv_batch, wlh_batch, 
     pred_v = src_pose_uv[:, 1] / src_pose_uv[:, 2] + delta[:, 4:5]
     pred_Z = src_pose_batch[:, 2, 3:] * delta[:, 5:]
     pred_T = torch.cat([pred_u * pred_Z, pred_v * pred_Z, pred_Z], dim=1).unsqueeze(-1)
-    pred_T = torch.matmul(torch.linalg.inv(K_batch), pred_T)
+    pred_T = torch.matmul(torch.linalg.inv(K_batch) if K_inv is None else K_inv, pred_T)
     pred_pose = torch.cat([pred_R, pred_T], dim=2)
     pred_uv = view_points_batch(corners_of_box_batch(pred_pose, wlh_batch), K_batch, normalize=True)
     loss = torch.sqrt(torch.sum((pred_uv[:, :2, :] - tgt_uv_batch) ** 2, dim=-2))
     return loss, pred_pose
 
 
+class PoseRegress3(nn.Module):
+    """The three pose-regress iterations of the joint step (trainer_unified_nuscenes.py:93-118) as ONE module over the model's
+    pose head, so that they can be captured in a CUDA graph (torch.cuda.make_graphed_callables): ~100 small kernels per iteration
+    that are launch-bound when issued eagerly.  K_inv is passed in (torch.linalg.inv synchronises, which a capture forbids)."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.pose_blocks, self.regress_blocks = model.pose_blocks, model.regress_blocks
+        for name in [f"pose_layer_{j}" for j in range(model.pose_blocks)] + [f"regress_layer_{j}" for j in range(model.regress_blocks)] + ["out_delta_layer"]:
+            setattr(self, name, getattr(model, name))
+
+    def pose_update(self, im_feat, box_uv_src):
+        return pose_update(self, im_feat, box_uv_src)
+
+    def forward(self, posecode, src_pose, tgt_uv, wlh, roi, K, K_inv):
+        pose, losses = src_pose, []
+        for _ in range(3):
+            loss_i, pose = pose_regress(self, posecode, pose, tgt_uv, wlh, roi, K, K_inv)
+            losses.append(loss_i.mean())
+        return losses[0], losses[1], losses[2], pose
+
+
 def joint_training_losses(model, hpams, img_in_batch, shapecode_batch, texturecode_batch, xyz_batch, viewdir_batch, z_vals_batch,
                           rgb_tgt_batch, occ_pixels_batch, src_pose_batch, tgt_uv_batch, roi_batch, K_batch, wlh_batch_aug,
-                          tgt_uv_batch_aug, enc_active=True, im_enc_rate=1.0, encode=None):
+                          tgt_uv_batch_aug, enc_active=True, im_enc_rate=1.0, encode=None, regress3=None):
     """ParallelModel.forward (trainer_unified_nuscenes.py:27-148) without the ``pred_wlh`` branch: common image encoding, direct
     corner regression, code consistency, three pose-regress iterations, then the NeRF sub-network (the package's decoder +
     ``volume_rendering_batch`` kernels) and the rgb / occupancy losses.  ``enc_active`` replaces the reference's
     ``random.uniform(0, 1) < im_enc_rate`` draw (the caller draws it).  ``encode``: the image-encoding callable
-    (default ``model.encode_img``; the bench passes the bf16 channels-last one).
+    (default ``model.encode_img``; the bench passes the bf16 channels-last one).  ``regress3``: optional callable
+    (posecode, src_pose, tgt_uv, wlh, roi, K) -> (loss1, loss2, loss3, pose3) standing for the three pose-regress iterations
+    (the bench passes a CUDA-graphed PoseRegress3).
     -> (losses_all, loss_total, shapecode_batch, texturecode_batch, pred_pose_batch3, pred_uv_batch_direct)"""
     from . import utils as U
     losses_all = {}
@@ -260,11 +284,15 @@ def joint_training_losses(model, hpams, img_in_batch, shapecode_batch, textureco
             loss_total = loss_total + hpams["loss_code_coef"] * losses_all["loss_code"]
         shapecode_batch = (shapecode_batch + shapecode) / 2
         texturecode_batch = (texturecode_batch + texturecode) / 2
-    pose = src_pose_batch
-    iters = []
-    for _ in range(3):
-        loss_i, pose = pose_regress(model, posecode, pose, tgt_uv_batch_aug, wlh_batch_aug, roi_batch, K_batch)
-        iters.append(loss_i.mean())
+    if regress3 is not None:
+        l1, l2, l3, pose = regress3(posecode, src_pose_batch, tgt_uv_batch_aug, wlh_batch_aug, roi_batch, K_batch)
+        iters = [l1, l2, l3]
+    else:
+        pose = src_pose_batch
+        iters = []
+        for _ in range(3):
+            loss_i, pose = pose_regress(model, posecode, pose, tgt_uv_batch_aug, wlh_batch_aug, roi_batch, K_batch)
+            iters.append(loss_i.mean())
     for i, l in enumerate(iters):
         losses_all["loss_pose_iter%d" % (i + 1)] = l
     if enc_active:
