@@ -100,10 +100,18 @@ int snb_sample_box_fwd(const float* rays_o, const float* viewdir, const float* z
 int snb_sample_box_bwd(const float* rays_o, const float* viewdir, const float* z_steps, const float* jitter,
                        int64_t n_rays, int32_t n_samples, float half_diag, const float* aabb_half_host3,
                        const float* g_xyz, const float* g_viewdir_rep, const float* g_z_vals,
-                       float* g_rays_o, float* g_viewdir, void* stream);
+                       float* g_rays_o, float* g_viewdir, int32_t detach_bounds, void* stream);
 /* snb_sample_shell: utils.sample_from_rays (utils.py:154-167) + `xyz /= obj_diag` (utils.py:472) +
  * the shapenet axis swap (utils.py:491-495).  z (S) is the shared sample vector (built on the host
  * exactly as the reference does).  inv_scale = 1 for a plain sample_from_rays. */
+/* The per-ray stratified sampler on its own (renderer.py:27-41 = utils.sample_from_rays_v2, utils.py:170-184): rays (N, row_floats)
+ * with near / far in the last two columns, z_steps (S), jitter (N,S) -> z (N,S) = near (1 - zs) + far zs, zs = z_steps + jitter / S.
+ * Backward: g_z (N,S) -> g_near (N), g_far (N).  snb_sample_box_bwd's detach_bounds != 0: near / far carry no gradient (the slab
+ * test ran on detached rays: renderer.render_rays_v3, renderer.py:425-432). */
+int snb_stratified_z_fwd(const float* rays, int32_t row_floats, const float* z_steps, const float* jitter, int64_t n_rays,
+                         int32_t n_samples, float* z, void* stream);
+int snb_stratified_z_bwd(const float* z_steps, const float* jitter, int64_t n_rays, int32_t n_samples, const float* g_z,
+                         float* g_near, float* g_far, void* stream);
 int snb_sample_shell_fwd(const float* rays_o, const float* viewdir, const float* z, int64_t n_rays,
                          int32_t n_samples, float obj_diag, int32_t shapenet_swap,
                          float* xyz, float* viewdir_rep, void* stream);

@@ -40,7 +40,9 @@ SIGNATURES = {
     "snb_ray_box_fwd": (c_i32, [c_f, c_f, c_f, c_f, c_i64, c_f, c_f, c_f, c_f]),
     "snb_ray_box_bwd": (c_i32, [c_f, c_f, c_f, c_f, c_i64, c_f, c_f, c_f, c_f, c_f, c_f, c_f]),
     "snb_sample_box_fwd": (c_i32, [c_f, c_f, c_f, c_f, c_i64, c_i32, c_flt, ctypes.POINTER(c_flt), c_f, c_f, c_f, c_f, c_f]),
-    "snb_sample_box_bwd": (c_i32, [c_f, c_f, c_f, c_f, c_i64, c_i32, c_flt, ctypes.POINTER(c_flt), c_f, c_f, c_f, c_f, c_f, c_f]),
+    "snb_sample_box_bwd": (c_i32, [c_f, c_f, c_f, c_f, c_i64, c_i32, c_flt, ctypes.POINTER(c_flt), c_f, c_f, c_f, c_f, c_f, c_i32, c_f]),
+    "snb_stratified_z_fwd": (c_i32, [c_f, c_i32, c_f, c_f, c_i64, c_i32, c_f, c_f]),
+    "snb_stratified_z_bwd": (c_i32, [c_f, c_f, c_i64, c_i32, c_f, c_f, c_f, c_f]),
     "snb_sample_shell_fwd": (c_i32, [c_f, c_f, c_f, c_i64, c_i32, c_flt, c_i32, c_f, c_f, c_f]),
     "snb_sample_shell_bwd": (c_i32, [c_f, c_i64, c_i32, c_flt, c_i32, c_f, c_f, c_f, c_f, c_f]),
     "snb_jitter_fill": (c_i32, [ctypes.c_uint64, c_f, c_i64, c_i32, c_f, c_f]),

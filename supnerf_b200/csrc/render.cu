@@ -204,6 +204,6 @@ extern "C" int snb_render_bwd(snb_handle h, const snb_render_desc* d, const floa
     if (snb_sample_shell_bwd(z_steps, N, d->n_samples, d->obj_diag, d->shapenet_swap, F(sc, G.g_xyz), F(sc, G.g_vrep),
                              F(sc, G.g_rays_o), F(sc, G.g_viewdir), stream)) return 1;
   } else if (snb_sample_box_bwd(F(ws, L.rays_o), F(ws, L.viewdir), z_steps, jitter, N, d->n_samples, d->half_diag, d->aabb_half,
-                                F(sc, G.g_xyz), F(sc, G.g_vrep), F(sc, G.g_z), F(sc, G.g_rays_o), F(sc, G.g_viewdir), stream)) return 1;
+                                F(sc, G.g_xyz), F(sc, G.g_vrep), F(sc, G.g_z), F(sc, G.g_rays_o), F(sc, G.g_viewdir), 0, stream)) return 1;
   return snb_get_rays_bwd(px, py, N, K, c2w, F(sc, G.g_rays_o), F(sc, G.g_viewdir), g_c2w, stream);
 }

@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(256) sample_box_bwd_kernel(
     const float* __restrict__ jitter, int64_t n_rays, int S, float half_diag, float hx, float hy, float hz,
     const float* __restrict__ g_xyz, const float* __restrict__ g_vrep, const float* __restrict__ g_zv,
     float* __restrict__ g_rays_o, float* __restrict__ g_viewdir,
-    const int32_t* __restrict__ cpos, const int64_t* __restrict__ ccounts) {   // non-NULL: g_xyz / g_vrep are in compact.cu's row order
+    const int32_t* __restrict__ cpos, const int64_t* __restrict__ ccounts,   // non-NULL: g_xyz / g_vrep are in compact.cu's row order
+    int detach_bounds) {   // renderer.render_rays_v3: the slab test ran on detached copies of the rays (renderer.py:425-432)
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(256) sample_box_bwd_kernel(
 #pragma unroll
         for (int a = 0; a < 3; ++a) gd[a] += gzabs * half_diag * d[a] / dn;
       }
-      if (sl.hit) {
+      if (sl.hit && !detach_bounds) {
         const float lo[3] = {-half[0], -half[1], -half[2]};
         float go2[3], gd2[3], glo[3], ghi[3];
         slab_backward(sl, o, lo, half, gnear, gfar, go2, gd2, glo, ghi);
@@ -364,14 +365,14 @@ extern "C" int snb_sample_box_fwd(const float* rays_o, const float* viewdir, con
 extern "C" int snb_sample_box_bwd(const float* rays_o, const float* viewdir, const float* z_steps, const float* jitter,
                                   int64_t n_rays, int32_t n_samples, float half_diag, const float* h,
                                   const float* g_xyz, const float* g_viewdir_rep, const float* g_z_vals,
-                                  float* g_rays_o, float* g_viewdir, void* stream) {
+                                  float* g_rays_o, float* g_viewdir, int32_t detach_bounds, void* stream) {
   SNB_REQUIRE(n_samples >= 1 && h != nullptr, "sample_box_bwd: bad arguments");
   if (n_rays == 0) return 0;
   int grid = ray_grid(n_rays, 8);
   SNB_REQUIRE(grid > 0, "sample_box_bwd: no CUDA device");
   sample_box_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rays_o, viewdir, z_steps, jitter, n_rays, n_samples,
                                                                 half_diag, h[0], h[1], h[2], g_xyz, g_viewdir_rep, g_z_vals,
-                                                                g_rays_o, g_viewdir, nullptr, nullptr);
+                                                                g_rays_o, g_viewdir, nullptr, nullptr, detach_bounds != 0);
   SNB_LAUNCH_CHECK();
   return 0;
 }
@@ -387,7 +388,7 @@ int sample_box_bwd_compact(const float* rays_o, const float* viewdir, const floa
   int grid = ray_grid(n_rays, 8);
   SNB_REQUIRE(grid > 0, "sample_box_bwd: no CUDA device");
   sample_box_bwd_kernel<<<grid, 256, 0, st>>>(rays_o, viewdir, z_steps, jitter, n_rays, n_samples, half_diag, h[0], h[1], h[2],
-                                              g_xyz_c, g_vrep_c, g_z_vals, g_rays_o, g_viewdir, pos, counts);
+                                              g_xyz_c, g_vrep_c, g_z_vals, g_rays_o, g_viewdir, pos, counts, 0);
   SNB_LAUNCH_CHECK();
   return 0;
 }
@@ -413,6 +414,71 @@ extern "C" int snb_sample_shell_bwd(const float* z, int64_t n_rays, int32_t n_sa
   SNB_REQUIRE(grid > 0, "sample_shell_bwd: no CUDA device");
   sample_shell_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, n_rays, n_samples, obj_diag, shapenet_swap, g_xyz,
                                                                   g_viewdir_rep, g_rays_o, g_viewdir);
+  SNB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The per-ray stratified sampler on its own (renderer.py:27-41 = utils.sample_from_rays_v2, utils.py:170-184):
+//   z[r][k] = near_r (1 - zs) + far_r zs,   zs = z_steps[k] + jitter[r][k] * (1 / S)        (rays (N, 8): near, far in columns 6, 7)
+// Backward: g_near = sum_k g (1 - zs), g_far = sum_k g zs.  Inside prepare_sampled_rays the same arithmetic is fused into the box sampler.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace snb {
+__global__ void __launch_bounds__(256) stratified_z_fwd_kernel(const float* __restrict__ rays, int ld, const float* __restrict__ z_steps,
+                                                             const float* __restrict__ jitter, int64_t n_rays, int S, float* __restrict__ z) {
+  const float fstep = (float)(1.0 / (double)S);
+  const int64_t total = n_rays * S;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / S;
+    const int k = (int)(i - r * S);
+    const float near = __ldg(rays + r * ld + ld - 2), far = __ldg(rays + r * ld + ld - 1);
+    const float zs = __fadd_rn(__ldg(z_steps + k), __fmul_rn(__ldg(jitter + i), fstep));
+    z[i] = __fadd_rn(__fmul_rn(near, __fsub_rn(1.f, zs)), __fmul_rn(far, zs));
+  }
+}
+__global__ void __launch_bounds__(256) stratified_z_bwd_kernel(const float* __restrict__ z_steps, const float* __restrict__ jitter,
+                                                             int64_t n_rays, int S, const float* __restrict__ g_z,
+                                                             float* __restrict__ g_near, float* __restrict__ g_far) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float fstep = (float)(1.0 / (double)S);
+  for (int64_t r = warp; r < n_rays; r += nwarps) {
+    float a = 0.f, b = 0.f;
+    for (int k = lane; k < S; k += 32) {
+      const float zs = __fadd_rn(__ldg(z_steps + k), __fmul_rn(__ldg(jitter + r * S + k), fstep));
+      const float g = __ldg(g_z + r * S + k);
+      a += g * (1.f - zs);
+      b += g * zs;
+    }
+    a = warp_sum(a); b = warp_sum(b);
+    if (lane == 0) { g_near[r] = a; g_far[r] = b; }
+  }
+}
+}  // namespace snb
+
+extern "C" int snb_stratified_z_fwd(const float* rays, int32_t row_floats, const float* z_steps, const float* jitter, int64_t n_rays,
+                                    int32_t n_samples, float* z, void* stream) {
+  SNB_REQUIRE(n_rays >= 0 && n_samples >= 1 && row_floats >= 2, "stratified_z_fwd: bad arguments");
+  if (n_rays == 0) return 0;
+  SNB_REQUIRE(rays && z_steps && jitter && z, "stratified_z_fwd: null pointer");
+  const int sms = sm_count();
+  SNB_REQUIRE(sms > 0, "stratified_z_fwd: no CUDA device");
+  int64_t grid = (n_rays * n_samples + 255) / 256;
+  if (grid > (int64_t)sms * 16) grid = (int64_t)sms * 16;
+  stratified_z_fwd_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(rays, row_floats, z_steps, jitter, n_rays, n_samples, z);
+  SNB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int snb_stratified_z_bwd(const float* z_steps, const float* jitter, int64_t n_rays, int32_t n_samples, const float* g_z,
+                                    float* g_near, float* g_far, void* stream) {
+  SNB_REQUIRE(n_rays >= 0 && n_samples >= 1, "stratified_z_bwd: bad arguments");
+  if (n_rays == 0) return 0;
+  SNB_REQUIRE(z_steps && jitter && g_z && g_near && g_far, "stratified_z_bwd: null pointer");
+  int grid = ray_grid(n_rays, 8);
+  SNB_REQUIRE(grid > 0, "stratified_z_bwd: no CUDA device");
+  stratified_z_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z_steps, jitter, n_rays, n_samples, g_z, g_near, g_far);
   SNB_LAUNCH_CHECK();
   return 0;
 }

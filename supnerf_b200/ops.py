@@ -146,7 +146,7 @@ def ray_box(ro, rd, amin=None, amax=None):
 
 class _SampleBox(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, rays_o, viewdir, z_steps, jitter, half_diag, aabb_half):
+    def forward(ctx, rays_o, viewdir, z_steps, jitter, half_diag, aabb_half, detach_bounds=False):
         lib = _lib.load()
         require_cuda(rays_o, viewdir, z_steps, jitter)
         rays_o, viewdir, z_steps, jitter = f32c(rays_o), f32c(viewdir), f32c(z_steps), f32c(jitter)
@@ -161,7 +161,7 @@ class _SampleBox(torch.autograd.Function):
             check(lib.snb_sample_box_fwd(ptr(rays_o), ptr(viewdir), ptr(z_steps), ptr(jitter), n, s, float(half_diag), h3,
                                          ptr(xyz), ptr(vrep), ptr(zv), ptr(hit), stream_ptr()), "snb_sample_box_fwd")
         ctx.save_for_backward(rays_o, viewdir, z_steps, jitter)
-        ctx.meta = (float(half_diag), [float(v) for v in aabb_half])
+        ctx.meta = (float(half_diag), [float(v) for v in aabb_half], int(bool(detach_bounds)))
         hitb = hit.bool()
         ctx.mark_non_differentiable(hitb)
         return xyz, vrep, zv, hitb
@@ -170,7 +170,7 @@ class _SampleBox(torch.autograd.Function):
     def backward(ctx, g_xyz, g_vrep, g_zv, _g_hit):
         lib = _lib.load()
         rays_o, viewdir, z_steps, jitter = ctx.saved_tensors
-        half_diag, half = ctx.meta
+        half_diag, half, detach = ctx.meta
         n, s = jitter.shape
         g_xyz = f32c(g_xyz) if g_xyz is not None else None
         g_vrep = f32c(g_vrep) if g_vrep is not None else None

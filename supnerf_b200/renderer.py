@@ -246,26 +246,19 @@ class NeRFRenderer(torch.nn.Module):
         xyz, viewdir, z_vals, intersect = self.prepare_sampled_rays(rays_o.to(device), viewdir.to(device), obj_sz)
         if kitti2nusc:
             xyz, viewdir = U._kitti2nusc(xyz, viewdir, device)
-        generated_img, generated_depth, generated_acc_trans = [], [], []
-        sample_step = int(np.maximum(int(roi[2]) - int(roi[0]), int(roi[3]) - int(roi[1])))
-        for i in range(0, xyz.shape[0], sample_step):
-            sigmas, rgbs = model(xyz[i:i + sample_step].to(device), viewdir[i:i + sample_step].to(device), shapecode,
-                                 texturecode)
-            rgb_rays, depth_rays, acc_trans_rays = self.volume_render(sigmas.squeeze(), rgbs, z_vals[i:i + sample_step].to(device))
-            generated_img.append(rgb_rays)
-            if out_depth:
-                generated_depth.append(depth_rays)
-            if debug_occ:
-                generated_acc_trans.append(acc_trans_rays)
+        # one decoder launch + one compositing launch for the whole image (the reference's row-block loop, renderer.py:262-275,
+        # only bounds its activation memory: every sample is decoded and composited independently of its block)
+        sigmas, rgbs = model(xyz.to(device), viewdir.to(device), shapecode, texturecode)
+        rgb_rays, depth_rays, acc_trans_rays = self.volume_render(sigmas.squeeze(), rgbs, z_vals.to(device))
         h, w = int(roi[3]) - int(roi[1]), int(roi[2]) - int(roi[0])
-        generated_img = torch.cat(generated_img).reshape(h, w, 3)
+        generated_img = rgb_rays.reshape(h, w, 3)
         if debug_occ:
             import cv2
-            acc = torch.cat(generated_acc_trans).reshape(h, w)
+            acc = acc_trans_rays.reshape(h, w)
             cv2.imshow('est_occ', ((torch.ones_like(acc) - acc).cpu().numpy() * 255).astype(np.uint8))
             cv2.waitKey()
         if out_depth:
-            return generated_img, torch.cat(generated_depth).reshape(h, w)
+            return generated_img, depth_rays.reshape(h, w)
         return generated_img
 
     def render_virtual_imgs(self, model, device, obj_sz, K, shapecode, texturecode, radius=40., tilt=np.pi / 6,
@@ -310,17 +303,15 @@ def render_rays_v3(model, device, img, mask_occ, cam_pose, obj_wlh, K, roi, n_sa
     # float32 origins by the float32 half diagonal; the slab test then runs in float64 on the host.  The kernel
     # evaluates it in fp32 with the fp32-rounded box: identical hit masks except for rays within 1 ulp of an edge.
     half = np.asarray([obj_l / obj_diag, obj_w / obj_diag, obj_h / obj_diag]).astype(np.float32)
-    ro_d = rays_o.detach().to(device) / (obj_diag / 2)
-    vd_d = viewdir.detach().to(device)
-    amax = torch.from_numpy(half).to(device).reshape(1, 3).repeat(ro_d.shape[0], 1)
-    tn, tf, hit = ops.ray_box(ro_d, vd_d, -amax, amax)
-    minus1 = torch.full_like(tn, -1)
-    bounds = torch.stack([torch.where(hit, tn, minus1), torch.where(hit, tf, minus1)], -1)
-    rays = torch.concat([rays_o.to(device) / (obj_diag / 2), viewdir.to(device), bounds], -1)
-    z_coarse = renderer.sample_from_ray(rays)
-    xyz = rays[:, None, :3] + z_coarse[:, :, None] * rays[:, None, 3:6]
-    viewdir = viewdir.to(device).unsqueeze(-2).repeat(1, n_samples, 1)
-    z_vals = torch.norm((xyz - rays[:, None, :3]) * (obj_diag / 2), p=2, dim=-1)
+    # slab test on detached rays + 64-stratum sampler + xyz + z_vals (renderer.py:425-463) as ONE kernel: the box sampler with
+    # detached bounds (near / far carry no gradient, exactly as the reference's numpy round trip); same RNG draw (one rand_like (N, 64))
+    dev = torch.device(device)
+    n = rays_o.shape[0]
+    z_steps = _z_steps_on(dev, renderer.n_samples)
+    jitter = torch.rand_like(z_steps.unsqueeze(0).repeat(n, 1))
+    xyz, viewdir, z_vals, _hit = ops.sample_box(rays_o.to(dev), viewdir.to(dev), z_steps, jitter, obj_diag / 2, half, detach_bounds=True)
+    if n_samples != renderer.n_samples:   # the reference repeats viewdir n_samples times against 64 strata: shapes must agree there too
+        raise ValueError("render_rays_v3 samples with a default NeRFRenderer() (64 strata): n_samples must be 64")
     xyz = xyz * adjust_scale
     if sym_aug and random.uniform(0, 1) > 0.5:
         xyz = xyz * xyz.new_tensor([1., -1., 1.])

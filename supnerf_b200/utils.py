@@ -91,16 +91,16 @@ def sample_from_rays(ro, vd, near, far, N_samples, z_fixed=False):
 
 
 def sample_from_rays_v2(rays, n_samples):
-    """utils.py:170-184 (the per-ray stratified sampler; inside prepare_sampled_rays it is fused into the
-    box-sampler kernel, standalone it is three tiny elementwise ops on the rays' device)."""
-    device = rays.device
-    near, far = rays[:, -2:-1], rays[:, -1:]
+    """utils.py:170-184: rays (N, 8) = [o, d, near, far] -> z (N, S), the per-ray stratified sampler, one kernel
+    (snb_stratified_z_fwd; differentiable to near / far).  RNG: the reference's one torch.rand_like of (N, S) on the rays' device
+    (inside prepare_sampled_rays the same arithmetic is fused into the box-sampler kernel)."""
+    dev = _device_of(rays)
+    r = rays.to(dev)
     step = 1.0 / n_samples
-    B = rays.shape[0]
-    z_steps = torch.linspace(0, 1 - step, n_samples, device=device)
-    z_steps = z_steps.unsqueeze(0).repeat(B, 1)
-    z_steps += torch.rand_like(z_steps) * step
-    return near * (1 - z_steps) + far * z_steps
+    z_steps = torch.linspace(0, 1 - step, n_samples, device=dev)
+    jitter = torch.rand_like(z_steps.unsqueeze(0).repeat(r.shape[0], 1))
+    z = ops.stratified_z(r, z_steps, jitter)
+    return z if rays.is_cuda else z.to(rays.device)
 
 
 def _composite_any(sigmas, rgbs, z_vals, white_bkgd, relu):
@@ -225,6 +225,17 @@ def _can_fuse_shell(model, device, shapecode, kitti2nusc):
             and torch.device(device).type == "cuda")
 
 
+def _shell_z_on_device(cam_pose, obj_diag, n_samples, device):
+    """The shared sample vector of utils.sample_from_rays (utils.py:154-167 with near / far of :468-469) WITHOUT reading the pose
+    back to the host: the reference does `np.linalg.norm(cam_pose[:, -1].tolist())` every call, a device -> host synchronisation in
+    the middle of every refine iteration when the pose lives on the GPU.  Same arithmetic on the device (float64 norm, float32
+    linspace formula; refine.shell_samples_on_device, equal to the host-built vector to 2e-7); the torch.rand(n_samples) draw stays
+    on the CPU generator, as in the reference."""
+    from . import refine
+    jit = torch.rand(n_samples).to(device, non_blocking=True)
+    return refine.shell_samples_on_device(cam_pose.detach().to(device), obj_diag, n_samples, jit)
+
+
 def _shell_fused(model, device, px, py, K, cam_pose, obj_diag, n_samples, shapecode, texturecode, shapenet_obj_cood, sym_aug,
                  kitti2nusc):
     """get_rays -> sample_from_rays -> /obj_diag -> swap -> model -> volume_rendering2 (utils.py:456-500) as one autograd
@@ -232,12 +243,15 @@ def _shell_fused(model, device, px, py, K, cam_pose, obj_diag, n_samples, shapec
     generator, then random.uniform if sym_aug."""
     from . import models
     device = torch.device(device)
-    near, far = _shell_near_far(cam_pose, obj_diag)
-    dist = (far - near) / (2 * n_samples)
-    z_vals = torch.linspace(near + dist, far - dist, n_samples).type_as(cam_pose)
-    z_vals += (torch.rand(n_samples) * (far - near) / (2 * n_samples)).type_as(cam_pose)
+    if cam_pose.is_cuda:      # no device -> host read of the pose (see _shell_z_on_device)
+        z_dev = _shell_z_on_device(cam_pose, obj_diag, n_samples, device)
+    else:
+        near, far = _shell_near_far(cam_pose, obj_diag)
+        dist = (far - near) / (2 * n_samples)
+        z_vals = torch.linspace(near + dist, far - dist, n_samples).type_as(cam_pose)
+        z_vals += (torch.rand(n_samples) * (far - near) / (2 * n_samples)).type_as(cam_pose)
+        z_dev = z_vals.to(device, non_blocking=True)
     flip = bool(sym_aug) and random.uniform(0, 1) > 0.5
-    z_dev = z_vals.to(device, non_blocking=True)
     if flip:   # rare branch: staged ops on the samples already drawn
         rays_o, viewdir = _rays(K, cam_pose, px, py)
         xyz, vd = ops.sample_shell(rays_o.to(device), viewdir.to(device), z_dev, float(obj_diag), False)
@@ -368,25 +382,20 @@ def render_full_img(model, device, cam_pose, obj_sz, K, roi, n_samples, shapecod
     rays_o, viewdir = get_rays(K, cam_pose, roi)
     near, far = _shell_near_far(cam_pose, obj_diag)
     xyz, vd, z_vals = _shell_samples(rays_o, viewdir, near, far, n_samples, obj_diag, shapenet_obj_cood, 0, kitti2nusc, device)
-    generated_img, generated_depth, generated_acc_trans = [], [], []
-    sample_step = int(np.maximum(int(roi[2]) - int(roi[0]), int(roi[3]) - int(roi[1])))
-    for i in range(0, xyz.shape[0], sample_step):
-        sigmas, rgbs = model(xyz[i:i + sample_step], vd[i:i + sample_step], shapecode, texturecode)
-        rgb_rays, depth_rays, acc_trans_rays = volume_rendering2(sigmas, rgbs, z_vals)
-        generated_img.append(rgb_rays)
-        if out_depth:
-            generated_depth.append(depth_rays)
-        if debug_occ:
-            generated_acc_trans.append(acc_trans_rays)
+    # The reference walks the image in blocks of `sample_step` rays (utils.py:585-598) to bound its activation memory; every sample
+    # is decoded and composited independently of the block it sits in, so ONE decoder launch + ONE compositing launch over all rows
+    # give the same pixels (the kernels keep no per-layer activations).
+    sigmas, rgbs = model(xyz, vd, shapecode, texturecode)
+    rgb_rays, depth_rays, acc_trans_rays = volume_rendering2(sigmas, rgbs, z_vals)
     h, w = int(roi[3]) - int(roi[1]), int(roi[2]) - int(roi[0])
-    generated_img = torch.cat(generated_img).reshape(h, w, 3)
+    generated_img = rgb_rays.reshape(h, w, 3)
     if debug_occ:
         import cv2
-        acc = torch.cat(generated_acc_trans).reshape(h, w)
+        acc = acc_trans_rays.reshape(h, w)
         cv2.imshow('est_occ', ((torch.ones_like(acc) - acc).cpu().numpy() * 255).astype(np.uint8))
         cv2.waitKey()
     if out_depth:
-        return generated_img, torch.cat(generated_depth).reshape(h, w)
+        return generated_img, depth_rays.reshape(h, w)
     return generated_img
 
 
