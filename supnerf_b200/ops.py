@@ -179,8 +179,8 @@ class _SampleBox(torch.autograd.Function):
         h3 = (ctypes.c_float * 3)(*half)
         with on_device(rays_o.device):
             check(lib.snb_sample_box_bwd(ptr(rays_o), ptr(viewdir), ptr(z_steps), ptr(jitter), n, s, half_diag, h3, ptr(g_xyz),
-                                         ptr(g_vrep), ptr(g_zv), ptr(g_o), ptr(g_d), stream_ptr()), "snb_sample_box_bwd")
-        return g_o, g_d, None, None, None, None
+                                         ptr(g_vrep), ptr(g_zv), ptr(g_o), ptr(g_d), detach, stream_ptr()), "snb_sample_box_bwd")
+        return g_o, g_d, None, None, None, None, None
 
 
 def jitter_fill(seed, n_rays, n_samples, device, ray_ids=None):
@@ -201,8 +201,48 @@ def jitter_fill(seed, n_rays, n_samples, device, ray_ids=None):
     return out
 
 
-def sample_box(rays_o, viewdir, z_steps, jitter, half_diag, aabb_half):
-    return _SampleBox.apply(rays_o, viewdir, z_steps, jitter, half_diag, aabb_half)
+def sample_box(rays_o, viewdir, z_steps, jitter, half_diag, aabb_half, detach_bounds=False):
+    """renderer.py:91-115 in one kernel.  detach_bounds: the slab test's near / far carry no gradient (renderer.render_rays_v3 runs it
+    on detached host copies of the rays, renderer.py:425-432)."""
+    return _SampleBox.apply(rays_o, viewdir, z_steps, jitter, half_diag, aabb_half, detach_bounds)
+
+
+class _StratifiedZ(torch.autograd.Function):
+    """renderer.py:27-41 = utils.py:170-184 on its own: rays (N, C) with near / far in the last two columns -> z (N, S)."""
+
+    @staticmethod
+    def forward(ctx, rays, z_steps, jitter):
+        lib = _lib.load()
+        require_cuda(rays, z_steps, jitter)
+        rays, z_steps, jitter = f32c(rays), f32c(z_steps), f32c(jitter)
+        n, s = jitter.shape
+        z = torch.empty(n, s, device=rays.device, dtype=torch.float32)
+        with on_device(rays.device):
+            check(lib.snb_stratified_z_fwd(ptr(rays), int(rays.shape[1]), ptr(z_steps), ptr(jitter), n, s, ptr(z), stream_ptr()),
+                  "snb_stratified_z_fwd")
+        ctx.save_for_backward(z_steps, jitter)
+        ctx.cols = int(rays.shape[1])
+        return z
+
+    @staticmethod
+    def backward(ctx, g_z):
+        lib = _lib.load()
+        z_steps, jitter = ctx.saved_tensors
+        n, s = jitter.shape
+        g_z = f32c(g_z)
+        g_rays = torch.zeros(n, ctx.cols, device=jitter.device, dtype=torch.float32)
+        g_near = torch.empty(n, device=jitter.device, dtype=torch.float32)
+        g_far = torch.empty(n, device=jitter.device, dtype=torch.float32)
+        with on_device(jitter.device):
+            check(lib.snb_stratified_z_bwd(ptr(z_steps), ptr(jitter), n, s, ptr(g_z), ptr(g_near), ptr(g_far), stream_ptr()),
+                  "snb_stratified_z_bwd")
+        g_rays[:, -2] = g_near
+        g_rays[:, -1] = g_far
+        return g_rays, None, None
+
+
+def stratified_z(rays, z_steps, jitter):
+    return _StratifiedZ.apply(rays, z_steps, jitter)
 
 
 class _SampleShell(torch.autograd.Function):

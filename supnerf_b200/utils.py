@@ -225,6 +225,14 @@ def _can_fuse_shell(model, device, shapecode, kitti2nusc):
             and torch.device(device).type == "cuda")
 
 
+# The reference-shaped shell drivers build the shared sample vector on the HOST from `cam_pose[:, -1].tolist()` (utils.py:468-469,
+# :154-167), i.e. they read the pose back from the GPU every call.  False (default): do exactly that -- torch's CPU linspace is the
+# reference's arithmetic bit for bit.  True: build it on the device (refine.shell_samples_on_device: same formula, equal to 2e-7 -- the
+# CPU linspace's vectorised rounding is not reproducible elsewhere), no device -> host synchronisation.  refine.ObjectRefiner always
+# works on the device.
+SHELL_Z_ON_DEVICE = False
+
+
 def _shell_z_on_device(cam_pose, obj_diag, n_samples, device):
     """The shared sample vector of utils.sample_from_rays (utils.py:154-167 with near / far of :468-469) WITHOUT reading the pose
     back to the host: the reference does `np.linalg.norm(cam_pose[:, -1].tolist())` every call, a device -> host synchronisation in
@@ -243,7 +251,7 @@ def _shell_fused(model, device, px, py, K, cam_pose, obj_diag, n_samples, shapec
     generator, then random.uniform if sym_aug."""
     from . import models
     device = torch.device(device)
-    if cam_pose.is_cuda:      # no device -> host read of the pose (see _shell_z_on_device)
+    if SHELL_Z_ON_DEVICE and cam_pose.is_cuda:      # no device -> host read of the pose (see _shell_z_on_device)
         z_dev = _shell_z_on_device(cam_pose, obj_diag, n_samples, device)
     else:
         near, far = _shell_near_far(cam_pose, obj_diag)

@@ -35,7 +35,7 @@ def test_tc_forward_layer_by_layer():
     M = xyz.shape[0] * xyz.shape[1]
     dbg = torch.zeros(len(acts), M, 256, device=DEV)
     lib = S._lib.load()
-    hnd = m._handle(torch.device(DEV)).h
+    hnd = m._handle(dbg.device).h
     lib.snb_tc_set_debug(hnd, ctypes.c_void_p(dbg.data_ptr()))
     try:
         with torch.no_grad():
@@ -372,14 +372,14 @@ def test_cta_group2_kernels_equal_cta_group1_kernels(B, n, S_):
     outs = []
     try:
         for mode in (0, 1):
-            lib.snb_tc_set_cg2(m._handle(torch.device(DEV)).h, mode)
+            lib.snb_tc_set_cg2(m._handle(xyz.to(DEV).device).h, mode)
             ins = [t.to(DEV).requires_grad_() for t in (xyz, vd, shp, tex)]
             sig, rgbs = m(*ins)
             ((sig * up_s.to(DEV)).sum() + (rgbs * up_c.to(DEV)).sum()).backward()
             torch.cuda.synchronize()
             outs.append((sig.detach(), rgbs.detach(), [t.grad for t in ins]))
     finally:
-        lib.snb_tc_set_cg2(m._handle(torch.device(DEV)).h, -1)
+        lib.snb_tc_set_cg2(m._handle(xyz.to(DEV).device).h, -1)
     (s0, c0, g0), (s1, c1, g1) = outs
     assert torch.equal(s0, s1) and torch.equal(c0, c1)
     assert parity_ok("g1_0", g1[0], g0[0], 1e-6) and parity_ok("g1_1", g1[1], g0[1], 1e-6)      # d xyz, d viewdir: per sample, no reduction

@@ -784,3 +784,28 @@ def test_refine_pose_and_adamw_kernels_vs_torch():
     for p, q in zip(ref, mine):
         assert parity_ok("q", q, p, 1e-6)
 
+
+
+def test_shell_sample_vector_on_device_option():
+    """utils.SHELL_Z_ON_DEVICE: the reference-shaped shell drivers without the per-call device -> host read of the pose; renders equal
+    to the default (host-built vector) path to 1e-5, and no synchronisation is needed to issue the call."""
+    S = snb()
+    obj = oracle.synthetic_object(57, im_sz=16)
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=57)
+    m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
+    m.precision = "fp32"
+    m.requires_grad_(False)
+    shp, tex = oracle.synthetic_latents(57, 1)
+    diag = np.linalg.norm(obj["wlh"]).astype(np.float32)
+    outs = []
+    try:
+        for flag in (False, True):
+            S.utils.SHELL_Z_ON_DEVICE = flag
+            torch.manual_seed(3)
+            cam = obj["cam_pose"].to(DEV)
+            outs.append(S.utils.render_rays_v2(m, DEV, obj["img"], obj["mask_occ"], cam, diag, obj["K"].to(DEV), obj["roi"], 64, shp.to(DEV),
+                                               tex.to(DEV), 1, 0, im_sz=16, n_rays=None)[:3])
+    finally:
+        S.utils.SHELL_Z_ON_DEVICE = False
+    for a, b, n_ in zip(outs[1], outs[0], ("rgb", "depth", "acc")):
+        assert parity_ok(n_, a, b, 1e-5)
