@@ -367,7 +367,7 @@ def run_ours(args):
     # secondary roofline, HBM-bound: the compositing kernels on one step's worth of rays (16 x 16384 rays x 64 samples: 335 MB in,
     # larger than L2), forward and backward, CUDA events around the C-ABI calls on the launch stream
     comp = None
-    if rank == 0:
+    if rank == 0 and not args.no_extras:
         try:
             nr = N_OBJ * n_rays
             g = torch.Generator().manual_seed(0)
@@ -410,7 +410,7 @@ def run_ours(args):
     # the metric's second half, "ms per refine iteration" (config C3 shape: one object, 32x32 rays x 64 samples, pose + codes
     # optimised with AdamW): refine.ObjectRefiner, one CUDA graph per iteration, 50 iterations, CUDA events
     refine_it = None
-    if rank == 0:
+    if rank == 0 and not args.no_extras:
         try:
             import numpy as _np
             sup = snb.SUPNeRF(3, 1, 3, 3, 256)
@@ -472,8 +472,24 @@ def run_ours(args):
     if rank != 0:
         return
     # the CPU arm is timed on rank 0 at N = 1 only (at N > 1 the other ranks' processes share the host cores)
-    cpu = cpu_baseline(steps=3, warmup=1) if world == 1 else None
-    eager = gpu_eager_baseline(dev) if world == 1 else None
+    # secondary measurements in child processes (N = 1 only): (a) the same step WITHOUT miss-ray compaction (SNB_NO_COMPACT=1: every
+    # one of the N x S rows goes through the decoder, the reference's semantics row for row), (b) the fp32 (1e-5 parity) back end
+    extras = {}
+    if world == 1 and not args.no_extras:
+        for key, extra_args, env_add in (("dense_rows_no_compaction", ["--per-object", "--precision", "bf16"], {"SNB_NO_COMPACT": "1"}),
+                                         ("fp32_parity_mode", ["--per-object", "--precision", "fp32"], {})):
+            try:
+                env = dict(os.environ, **env_add)
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--skip-modes", "--no-extras", "--steps", "3", "--warmup", "3"] + extra_args,
+                                   capture_output=True, text=True, timeout=420, env=env)
+                sub = json.loads(r.stdout.strip().splitlines()[-1])
+                extras[key] = {"value": sub["value"], "unit": "rays/s", "ms_per_step": sub["ms_per_step"], "e2e": sub["e2e"]["value"],
+                               "precision": sub["config"]["precision"], "launch_sets": sub["config"].get("launch_sets"),
+                               "decoder_tflops": (sub.get("roofline") or {}).get("other"), "steps": sub["steps"]}
+            except Exception as exc:   # noqa: BLE001
+                extras[key] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+    cpu = cpu_baseline(steps=3, warmup=1) if (world == 1 and not args.no_extras) else None
+    eager = gpu_eager_baseline(dev) if (world == 1 and not args.no_extras) else None
     line = {"metric": METRIC, "value": round(value, 1), "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
@@ -487,6 +503,7 @@ def run_ours(args):
             "e2e": {"value": round(e2e_value, 1), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
             "roofline_compositing": comp, "refine_iteration": refine_it, "gpu_launches": int(launches), "clocks": dict(clk.summary(), e2e_region=clk2.summary()), "roofline": roofline, "cpu_baseline": cpu, "gpu_eager_baseline": eager}
+    line.update(extras)
     line.update(modes)
     if modes:
         line["multi_gpu_parity"] = "pass" if all(m.get("multi_gpu_parity", "pass") == "pass" and "error" not in m for m in modes.values()) else "FAIL"
@@ -953,6 +970,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--per-object", dest="batched", action="store_false",
                     help="round 1's path: one fused render per object over --streams CUDA streams (default: all objects in one launch set)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (dense rows, fp32 mode, CPU / eager-CUDA reference baselines)")
     ap.add_argument("--skip-modes", action="store_true", help="skip the configs[3] / configs[4] collective-bearing modes")
     ap.add_argument("--streams", type=int, default=3, help="CUDA streams the independent objects alternate over (1 = one stream)")
     args = ap.parse_args()

@@ -133,7 +133,7 @@ class ObjectRefiner:
 
     def __init__(self, model, device, img, mask_occ, K, roi, obj_diag, shapecode, texturecode, rot_vec, trans_vec, n_samples=64,
                  im_sz=32, lr_shape=0.02, lr_texture=0.02, lr_pose=0.01, loss_occ_coef=0.1, shapenet_obj_cood=True,
-                 opt_cam_pose=False, max_iters=100, fused=True):
+                 opt_cam_pose=False, max_iters=100, fused=True, lidar_xy=None):
         if not isinstance(model, models._DecoderBase):
             raise TypeError("ObjectRefiner needs a supnerf_b200 decoder")
         self.model, self.device = model, torch.device(device)
@@ -160,8 +160,29 @@ class ObjectRefiner:
             self.opt = torch.optim.AdamW([{"params": [self.shapecode], "lr": lr_shape}, {"params": [self.texturecode], "lr": lr_texture},
                                           {"params": [self.rot_vec], "lr": lr_pose}, {"params": [self.trans_vec], "lr": lr_pose}],
                                          capturable=True)
-        # the reference draws torch.rand(n_samples) on the CPU generator once per iteration (utils.py:164): same calls, same order
-        self.jitter = torch.stack([torch.rand(self.n_samples) for _ in range(max_iters)]).to(dev)
+        # Per-iteration evaluation the reference interleaves with the optimisation (optimizer_nuscenes.py:740-769): the PSNR loss over
+        # the object mask only (loss_rgb2) and a no-grad depth render of the pixels that carry a lidar return (render_rays_specified).
+        # lidar_xy = (x_vec, y_vec): integer pixel offsets inside the crop (np.where of the depth map, :759); None = not evaluated.
+        self.lidar = None
+        if lidar_xy is not None:
+            x_vec, y_vec = np.asarray(lidar_xy[0]), np.asarray(lidar_xy[1])
+            self.n_lidar = int(x_vec.shape[0])
+            if self.n_lidar > 0:
+                lx = torch.from_numpy(x_vec + int(roi[0])).reshape(-1).to(dev, torch.float32)
+                ly = torch.from_numpy(y_vec + int(roi[1])).reshape(-1).to(dev, torch.float32)
+                pad = (-self.n_lidar) % 2            # the bf16 decoder works on 128-row tiles: an even ray count at 64 samples
+                if pad:
+                    lx, ly = torch.cat([lx, lx[-1:]]), torch.cat([ly, ly[-1:]])
+                self.lidar = (lx.contiguous(), ly.contiguous())
+        self.occ_pos = self.occ.clamp_min(0.0)       # mask_rgb: occ_pixels with the negative (background) entries zeroed (:741-742)
+        self.loss_rgb2 = torch.zeros((), device=dev)
+        self.depth_pred = torch.zeros(0, device=dev)
+        # the reference draws torch.rand(n_samples) on the CPU generator once per render call (utils.py:164): per iteration one draw
+        # for the optimised render and, when the lidar pixels are evaluated, a second one for render_rays_specified -- same calls, same order
+        per_it = 2 if self.lidar is not None else 1
+        draws = torch.stack([torch.rand(self.n_samples) for _ in range(max_iters * per_it)]).to(dev)
+        self.jitter = draws[0::per_it].contiguous()
+        self.jitter_lidar = draws[1::per_it].contiguous() if self.lidar is not None else None
         self.it = torch.zeros((), dtype=torch.long, device=dev)
         self.loss = torch.zeros(3, device=dev)
         self.graph = None
@@ -189,6 +210,19 @@ class ObjectRefiner:
                                          self.px, self.py, self.K, cam, z, self.shapecode, self.texturecode, self.model._weights())
         loss, vec = losses.refine_loss_vec(rgb, acc, self.rgb_tgt, self.occ, self.coef)
         loss.backward()
+        with torch.no_grad():       # the per-iteration evaluation (optimizer_nuscenes.py:740-769), before the parameter update as there
+            self.loss_rgb2 = losses.refine_loss(rgb.detach(), acc.detach(), self.rgb_tgt, self.occ_pos, 0.0)[1]
+            if self.lidar is not None:
+                jit2 = self.jitter_lidar.index_select(0, self.it.reshape(1)).reshape(-1)
+                if self.fused:
+                    cam2, z2 = _PoseAndSamples.apply(self.rot_vec.detach(), self.trans_vec.detach(), jit2, self.opt_cam_pose, self.obj_diag, self.n_samples)
+                else:
+                    cam2 = cam.detach()
+                    z2 = shell_samples_on_device(cam2, self.obj_diag, self.n_samples, jit2)
+                _, dep2, _ = ops.render_shell(self.model._handle(self.device), prec, self.n_samples, float(self.obj_diag), self.swap,
+                                              self.lidar[0], self.lidar[1], self.K, cam2, z2, self.shapecode.detach(), self.texturecode.detach(),
+                                              self.model._weights())
+                self.depth_pred = dep2[:self.n_lidar]
         self.opt.step()
         self.loss = vec   # [loss, loss_rgb, loss_occ] as the loss kernel wrote them (graph mode: a static tensor of the graph's pool)
         self.it += 1
