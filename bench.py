@@ -427,9 +427,11 @@ def run_ours(args):
                 ang = torch.acos(((torch.trace(r_obj) - 1) / 2).clamp(-1, 1))
                 w = torch.stack([r_obj[2, 1] - r_obj[1, 2], r_obj[0, 2] - r_obj[2, 0], r_obj[1, 0] - r_obj[0, 1]])
                 rot_vec = (w / (2 * torch.sin(ang).clamp_min(1e-12)) * ang).float()
+                rs = _np.random.RandomState(300 + k)   # 64 "lidar" pixels of the crop: their no-grad depth render is part of every iteration
+                lidar = (rs.randint(0, o["img"].shape[1], 64), rs.randint(0, o["img"].shape[0], 64))
                 return snb.refine.ObjectRefiner(sup, dev, o["img"].to(dev), o["mask_occ"].to(dev), o["K"], o["roi"],
                                                 _np.linalg.norm(o["wlh"]).astype(_np.float32), o["shapecode"], o["texturecode"], rot_vec,
-                                                t_obj, n_samples=N_SAMPLES, im_sz=32, max_iters=max_iters).capture()
+                                                t_obj, n_samples=N_SAMPLES, im_sz=32, max_iters=max_iters, lidar_xy=lidar).capture()
 
             ref = refiner_for(0, 60)
             ref.run(5)
@@ -441,7 +443,8 @@ def run_ours(args):
             torch.cuda.synchronize()
             refine_it = {"ms_per_refine_iteration": round(a0.elapsed_time(a1) / 50, 4), "iterations": 50,
                          "config": "configs[2] shape: one object, 32x32 rays x %d samples, AdamW on pose + shape/texture codes, "
-                                   "supnerf_b200.refine.ObjectRefiner (one CUDA graph per iteration)" % N_SAMPLES,
+                                   "supnerf_b200.refine.ObjectRefiner (one CUDA graph per iteration), INCLUDING the per-iteration evaluation of "
+                                   "optimizer_nuscenes.py:740-769 (PSNR loss over the object mask + no-grad depth render of 64 lidar pixels)" % N_SAMPLES,
                          "loss_after": round(float(last[0]), 5)}
             # configs[2] gives every GPU 4 objects: refined side by side (refine.run_objects, one stream per object)
             refs = [refiner_for(k, 60) for k in range(4)]

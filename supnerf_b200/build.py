@@ -14,6 +14,7 @@ SOURCES = ["api.cu", "composite.cu", "sampler.cu", "latent.cu", "mlp_f32.cu", "m
            "compact.cu", "scene.cu", "refine.cu", "render_batch.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]  # no --use_fast_math: sinf/expf accuracy is part of parity
+NVCC_FLAGS += os.environ.get("SNB_EXTRA_NVCC_FLAGS", "").split()   # tuning builds only (e.g. -DSNB_EXP_... timing experiments)
 
 
 def _nvcc():

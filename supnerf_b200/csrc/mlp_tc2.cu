@@ -908,14 +908,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_bwd_kernel(const __grid_const
         }
         const bool last = si + 1 == p.prog.n_steps;
         if (last && has_next) load_upstream(pair0 + gridDim.x, gsp_n, g3n, mwn);   // global latency hides behind the last MMAs
+#ifndef SNB_EXP_NO_COLSUM   // (timing experiment builds only: upper bound of what the column-sum pass costs; wrong latent gradients)
         if (st.colsum) {   // column sums of this step's A operand (published by the whole group last step), while its MMAs run
           group_bar(slot);
           colsum_a_operand(sm, slot, gw, lane, colsum + st.latent_slot * 256);
         }
+#endif
         mbar_wait(sm.bar(BAR_ACC + slot), acc_cnt & 1u);
         acc_cnt++;
         tc_fence_after();
+#ifndef SNB_EXP_NO_COLSUM
         if (st.colsum) group_bar(slot);   // every warp is done reading the chunks this step's epilogue overwrites
+#endif
         if (p.trace && blockIdx.x == 0 && gtid == 0) p.trace[(((pair0 / gridDim.x) * p.prog.n_steps + si) * 2 + slot) * 4 + 2] = clock64();
         if (st.epi == B_XYZ) {
           // acc = d PE(xyz) (64 columns): fold to d xyz.  g_x = g_0 + sum_f 2^f (g_sin,f cos_f - g_cos,f sin_f)

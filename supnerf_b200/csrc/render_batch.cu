@@ -369,8 +369,12 @@ __global__ void __launch_bounds__(256) rb_composite_bwd_kernel(const float* __re
 }
 
 // --------------------------------------------------------------------------------------------------------------- rays backward
-// one warp per ray (lanes over its samples): d xyz / d viewdir / d z_vals of the ray's compact rows -> d (o, d, near, far) -> through the
-// slab test -> d (rays_o, viewdir) -> through get_rays -> this object's d cam_pose (12 fp64 block sums, one atomic each per block)
+// d xyz / d viewdir / d z_vals of a ray's compact rows -> d (o, d, near, far) -> through the slab test -> d (rays_o, viewdir) ->
+// through get_rays -> this object's d cam_pose (12 fp64 sums per thread, one block reduction + one atomic each per block).
+// Two phases per group of 32 rays of a warp: (1) the warp walks its 32 rays one after the other, lanes over the ray's samples, and
+// lane j keeps the nine sums of ray j; (2) every lane finishes ITS ray (slab backward, normalisation Jacobian, outer products) -- the
+// per-ray tail is ~400 instructions, which a warp-per-ray layout would issue for one active lane (measured: 672 warp instructions
+// per ray, 0.42 ms per 262 144 rays; this layout: ~60).
 __global__ void __launch_bounds__(256) rb_rays_bwd_kernel(const float* __restrict__ px, const float* __restrict__ py,
                                                          const float* __restrict__ K, const float* __restrict__ c2w,
                                                          const float* __restrict__ box, const float* __restrict__ rays8,
@@ -388,54 +392,88 @@ __global__ void __launch_bounds__(256) rb_rays_bwd_kernel(const float* __restric
   const float half[3] = {__ldg(box + 4 * b + 1), __ldg(box + 4 * b + 2), __ldg(box + 4 * b + 3)};
   const float cx = __ldg(Kb + 2), cy = __ldg(Kb + 5), fx = __ldg(Kb), fy = __ldg(Kb + 4);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const float fstep = (float)(1.0 / (double)S);
   double acc[12];
 #pragma unroll
   for (int i = 0; i < 12; ++i) acc[i] = 0.0;
-  for (int64_t ray = warp; ray < N; ray += nwarps) {
-    const int64_t gi = (int64_t)b * N + ray;
-    const float4 ra = __ldg(reinterpret_cast<const float4*>(rays8 + 8 * gi)), rb_ = __ldg(reinterpret_cast<const float4*>(rays8 + 8 * gi) + 1);
-    const float o[3] = {ra.x, ra.y, ra.z}, d[3] = {ra.w, rb_.x, rb_.y};
-    const bool h = hit[gi] != 0;
-    const float near = rb_.z, far = rb_.w;
-    const int p = pos_all[gi];
-    const float dn = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-    float gon[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f}, gzabs = 0.f, gnear = 0.f, gfar = 0.f;
-    for (int k = lane; k < S; k += 32) {
-      const float zs = __fadd_rn(__ldg(z_steps + k), __fmul_rn(__ldg(jitter + gi * S + k), fstep));
-      const float zc = __fadd_rn(__fmul_rn(near, __fsub_rn(1.f, zs)), __fmul_rn(far, zs));
-      // S rows per hit ray; a miss ray's single row stands for all its samples and is credited to the last one
-      const int64_t gidx = h ? c.row_start + (int64_t)p * S + k : (k == S - 1 ? c.row_start + c.n_hit * S + p : -1);
-      float gx[3] = {0.f, 0.f, 0.f};
-      if (gidx >= 0) { gx[0] = __ldg(g_xyz_c + 3 * gidx); gx[1] = __ldg(g_xyz_c + 3 * gidx + 1); gx[2] = __ldg(g_xyz_c + 3 * gidx + 2); }
-      float gz = gx[0] * d[0] + gx[1] * d[1] + gx[2] * d[2];
+  for (int64_t base = (int64_t)blockIdx.x * 256 + wib * 32; base < N; base += (int64_t)gridDim.x * 256) {
+    // ---- phase 1: the warp's 32 rays, one after the other; lane j keeps ray j's sums
+    float k_gon[3] = {0.f, 0.f, 0.f}, k_gd[3] = {0.f, 0.f, 0.f}, k_gzabs = 0.f, k_gnear = 0.f, k_gfar = 0.f;
+    const int n_here = (int)((N - base) < 32 ? (N - base) : 32);
+    for (int j = 0; j < n_here; ++j) {
+      const int64_t gi = (int64_t)b * N + base + j;
+      const float4 ra = __ldg(reinterpret_cast<const float4*>(rays8 + 8 * gi)), rb_ = __ldg(reinterpret_cast<const float4*>(rays8 + 8 * gi) + 1);
+      const float d[3] = {ra.w, rb_.x, rb_.y};
+      const bool h = hit[gi] != 0;
+      const float near = rb_.z, far = rb_.w;
+      const int p = pos_all[gi];
+      const float dn = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+      float gon[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f}, gzabs = 0.f, gnear = 0.f, gfar = 0.f;
+      if (h) {
+        for (int k = lane; k < S; k += 32) {
+          const float zs = __fadd_rn(__ldg(z_steps + k), __fmul_rn(__ldg(jitter + gi * S + k), fstep));
+          const float zc = __fadd_rn(__fmul_rn(near, __fsub_rn(1.f, zs)), __fmul_rn(far, zs));
+          const int64_t gidx = c.row_start + (int64_t)p * S + k;
+          const float gx[3] = {__ldg(g_xyz_c + 3 * gidx), __ldg(g_xyz_c + 3 * gidx + 1), __ldg(g_xyz_c + 3 * gidx + 2)};
+          float gz = gx[0] * d[0] + gx[1] * d[1] + gx[2] * d[2];
 #pragma unroll
-      for (int a = 0; a < 3; ++a) { gon[a] += gx[a]; gd[a] += zc * gx[a]; }
-      if (gidx >= 0) { gd[0] += __ldg(g_vrep_c + 3 * gidx); gd[1] += __ldg(g_vrep_c + 3 * gidx + 1); gd[2] += __ldg(g_vrep_c + 3 * gidx + 2); }
-      if (g_z_c != nullptr && gidx >= 0) {
-        const float gv = __ldg(g_z_c + gidx);
-        const float sgn = (zc > 0.f) ? 1.f : ((zc < 0.f) ? -1.f : 0.f);
-        gz += gv * sgn * dn * half_diag;
-        gzabs += gv * fabsf(zc);
+          for (int a = 0; a < 3; ++a) { gon[a] += gx[a]; gd[a] += zc * gx[a]; }
+          gd[0] += __ldg(g_vrep_c + 3 * gidx); gd[1] += __ldg(g_vrep_c + 3 * gidx + 1); gd[2] += __ldg(g_vrep_c + 3 * gidx + 2);
+          if (g_z_c != nullptr) {
+            const float gv = __ldg(g_z_c + gidx);
+            const float sgn = (zc > 0.f) ? 1.f : ((zc < 0.f) ? -1.f : 0.f);
+            gz += gv * sgn * dn * half_diag;
+            gzabs += gv * fabsf(zc);
+          }
+          gnear += gz * (1.f - zs);
+          gfar += gz * zs;
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { gon[a] = warp_sum(gon[a]); gd[a] = warp_sum(gd[a]); }
+        gzabs = warp_sum(gzabs); gnear = warp_sum(gnear); gfar = warp_sum(gfar);
+      } else if (lane == j) {
+        // a miss ray's single row stands for all its samples and is credited to the last one (k = S - 1)
+        const int k = S - 1;
+        const float zs = __fadd_rn(__ldg(z_steps + k), __fmul_rn(__ldg(jitter + gi * S + k), fstep));
+        const float zc = __fadd_rn(__fmul_rn(near, __fsub_rn(1.f, zs)), __fmul_rn(far, zs));
+        const int64_t gidx = c.row_start + c.n_hit * S + p;
+        const float gx[3] = {__ldg(g_xyz_c + 3 * gidx), __ldg(g_xyz_c + 3 * gidx + 1), __ldg(g_xyz_c + 3 * gidx + 2)};
+        float gz = gx[0] * d[0] + gx[1] * d[1] + gx[2] * d[2];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { gon[a] = gx[a]; gd[a] = zc * gx[a]; }
+        gd[0] += __ldg(g_vrep_c + 3 * gidx); gd[1] += __ldg(g_vrep_c + 3 * gidx + 1); gd[2] += __ldg(g_vrep_c + 3 * gidx + 2);
+        if (g_z_c != nullptr) {
+          const float gv = __ldg(g_z_c + gidx);
+          const float sgn = (zc > 0.f) ? 1.f : ((zc < 0.f) ? -1.f : 0.f);
+          gz += gv * sgn * dn * half_diag;
+          gzabs = gv * fabsf(zc);
+        }
+        gnear = gz * (1.f - zs);
+        gfar = gz * zs;
       }
-      gnear += gz * (1.f - zs);
-      gfar += gz * zs;
-    }
+      if (lane == j) {
 #pragma unroll
-    for (int a = 0; a < 3; ++a) { gon[a] = warp_sum(gon[a]); gd[a] = warp_sum(gd[a]); }
-    gzabs = warp_sum(gzabs); gnear = warp_sum(gnear); gfar = warp_sum(gfar);
-    if (lane == 0) {
+        for (int a = 0; a < 3; ++a) { k_gon[a] = gon[a]; k_gd[a] = gd[a]; }
+        k_gzabs = gzabs; k_gnear = gnear; k_gfar = gfar;
+      }
+    }
+    // ---- phase 2: every lane finishes its own ray
+    if (lane < n_here) {
+      const int64_t gi = (int64_t)b * N + base + lane;
+      const float4 ra = __ldg(reinterpret_cast<const float4*>(rays8 + 8 * gi)), rb_ = __ldg(reinterpret_cast<const float4*>(rays8 + 8 * gi) + 1);
+      const float o[3] = {ra.x, ra.y, ra.z}, d[3] = {ra.w, rb_.x, rb_.y};
+      const bool h = hit[gi] != 0;
+      const float dn = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+      float gon[3] = {k_gon[0], k_gon[1], k_gon[2]}, gd[3] = {k_gd[0], k_gd[1], k_gd[2]};
       if (dn > 0.f) {
 #pragma unroll
-        for (int a = 0; a < 3; ++a) gd[a] += gzabs * half_diag * d[a] / dn;
+        for (int a = 0; a < 3; ++a) gd[a] += k_gzabs * half_diag * d[a] / dn;
       }
       if (h) {
         const Slab sl = slab_test(o, d, half);
         const float lo[3] = {-half[0], -half[1], -half[2]};
         float go2[3], gd2[3], glo[3], ghi[3];
-        slab_backward(sl, o, lo, half, gnear, gfar, go2, gd2, glo, ghi);
+        slab_backward(sl, o, lo, half, k_gnear, k_gfar, go2, gd2, glo, ghi);
 #pragma unroll
         for (int a = 0; a < 3; ++a) { gon[a] += go2[a]; gd[a] += gd2[a]; }
       }
@@ -460,9 +498,12 @@ __global__ void __launch_bounds__(256) rb_rays_bwd_kernel(const float* __restric
     }
   }
   __shared__ double red[8][12];
-  if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < 12; ++i) red[wib][i] = acc[i];
+  for (int i = 0; i < 12; ++i) {
+    double v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[wib][i] = v;
   }
   __syncthreads();
   if (threadIdx.x < 12) {
@@ -733,7 +774,7 @@ extern "C" int snb_render_batch_bwd(snb_handle h, const snb_batch_desc* d, const
     return 1;
   if (!pose) return 0;
   SNB_CHECK_CUDA(cudaMemsetAsync(at<uint8_t>(sc, G.acc64), 0, G.mlp - G.acc64, st));   // fp64 sums + tickets
-  int gr = (int)ceil_div(N, 8);
+  int gr = (int)ceil_div(N, 256);
   if (gr > cap) gr = cap;
   if (gr < 1) gr = 1;
   rb::rb_rays_bwd_kernel<<<dim3((unsigned)gr, (unsigned)B), 256, 0, st>>>(px, py, K, c2w, box, at<float>(ws, L.rays8), at<uint8_t>(ws, L.hit),

@@ -26,7 +26,7 @@ def run(n):
 run(3)
 import ctypes
 lib = snb._lib.load()
-hnd = m._handle(torch.device(dev)).h
+hnd = m._handle(xyz.device).h
 lib.snb_kernel_timing_enable(hnd, 1)
 f, b = run(10)
 buf = (ctypes.c_float * 64)()
