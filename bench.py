@@ -766,12 +766,24 @@ def run_c5(snb, dev, rank, world, steps, warmup, precision):
     # all arrive together, so only the decoder / head bucket can overlap, and the per-parameter hook bookkeeping costs more host
     # time than the 1.2 ms exchange could hide
     ms, loss = timed(steps, overlap=False)
-    ms_bucketed, ar = None, {}
-    if world > 1:
+
+    def weights_identical():
+        torch.cuda.synchronize()
+        probe = torch.cat([m.encoding_xyz[0].weight.reshape(-1)[:64], enc.conv1.weight.reshape(-1)[:64], enc.layer4_pose[2].conv2.weight.reshape(-1)[:64],
+                           m.out_delta_layer.weight.reshape(-1)[:64]])
+        gs = [torch.empty_like(probe) for _ in range(world)]
+        dist.all_gather(gs, probe)
+        return bool(all(torch.equal(gs[0], t) for t in gs[1:]))
+    same_flat = weights_identical() if world > 1 else None
+    ms_bucketed, ar, same_bucketed = None, {}, None
+    if world > 1 and not (graphed["encoder"] or graphed["pose_regress"]):
+        # the hook-driven bucketed exchange needs gradients that arrive layer by layer: only meaningful with the EAGER library stages
+        # (SNB_C5_EAGER=1); with the encoder backward replayed as one CUDA graph all its gradients arrive together
         for _ in range(2):
             step(overlap=True)
         ms_bucketed, _ = timed(steps, overlap=True)
         ar = buckets.allreduce_ms()
+        same_bucketed = weights_identical()
     # phase split on one rank's stream (second pass, events): encoder+pose forward | render forward | backward | optimizer
     finite = bool(np.isfinite(loss))
     flops_dec = 3 * 2 * MAC_PER_SAMPLE * B * n * S
@@ -787,13 +799,11 @@ def run_c5(snb, dev, rank, world, steps, warmup, precision):
                                                "trunk": round(ar.get(2, 0.0), 3)} if ar else None,
            "overlap_gain_ms": round(ms - ms_bucketed, 3) if ms_bucketed else None,
            "multi_gpu_parity": "pass" if finite else "FAIL"}
-    if world > 1:   # every rank must hold identical weights after the step (same reduced gradients, same update)
-        probe = torch.cat([m.encoding_xyz[0].weight.reshape(-1)[:64], enc.conv1.weight.reshape(-1)[:64], enc.layer4_pose[2].conv2.weight.reshape(-1)[:64]])
-        gs = [torch.empty_like(probe) for _ in range(world)]
-        dist.all_gather(gs, probe)
-        same = bool(all(torch.equal(gs[0], t) for t in gs[1:]))
-        out["weights_bit_identical_across_ranks_after_training"] = same
-        if not same:
+    if world > 1:   # every rank must hold identical weights after training (same reduced gradients, same update)
+        out["weights_bit_identical_across_ranks_after_training"] = same_flat
+        if same_bucketed is not None:
+            out["weights_bit_identical_after_bucketed_steps"] = same_bucketed
+        if not same_flat or same_bucketed is False:
             out["multi_gpu_parity"] = "FAIL"
     buckets.remove()
     return out
