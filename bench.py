@@ -785,6 +785,26 @@ def run_c5(snb, dev, rank, world, steps, warmup, precision):
         ar = buckets.allreduce_ms()
         same_bucketed = weights_identical()
     # phase split on one rank's stream (second pass, events): encoder+pose forward | render forward | backward | optimizer
+    # the step's samples prepared on the device (utils.prepare_pixel_samples_batch) instead of by DataLoader workers
+    prep = None
+    if rank == 0:
+        try:
+            pobjs = [synthetic.synthetic_object(700 + i, im_sz=64) for i in range(B)]
+            pargs = (dev, [o["img"] for o in pobjs], [o["mask_occ"] for o in pobjs], [o["cam_pose"] for o in pobjs],
+                     [np.linalg.norm(o["wlh"]).astype(np.float32) for o in pobjs], [o["K"] for o in pobjs], [o["roi"] for o in pobjs], n, S, 1, 0)
+            for _ in range(2):
+                snb.utils.prepare_pixel_samples_batch(*pargs, im_sz=64)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                pxyz = snb.utils.prepare_pixel_samples_batch(*pargs, im_sz=64)[0]
+            torch.cuda.synchronize()
+            prep = {"ms_per_batch_host_plus_device": round((time.perf_counter() - t0) / 5 * 1e3, 3), "objects": B, "rays": n, "samples": S,
+                    "bytes_over_pcie_here": int(B * (S * 4 + 2 * n * 4 + n * 16 + 21 * 4)), "bytes_over_pcie_reference_loader": int(B * (2 * n * S * 12 + S * 4 + n * 16)),
+                    "what": "utils.prepare_pixel_samples (data_nuscenes.py:643-658) for the whole batch in one kernel on the device; bit-identical "
+                            "to per-object calls (tests/test_gpu_parity.py)", "shape": list(pxyz.shape)}
+        except Exception as exc:   # noqa: BLE001
+            prep = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
     finite = bool(np.isfinite(loss))
     flops_dec = 3 * 2 * MAC_PER_SAMPLE * B * n * S
     out = {"config": "configs[4]: joint training step per GPU: ImgEncoder (8,3,128,128) bf16 channels-last + pose regression x3 + render of "
@@ -793,6 +813,7 @@ def run_c5(snb, dev, rank, world, steps, warmup, precision):
            "scaling": "weak", "n_gpus": world, "ms_per_step": round(ms, 3), "rays_per_s": round(world * B * n / (ms / 1e3), 1),
            "decoder_tflops_per_gpu_if_step_were_decoder_only": round(flops_dec / (ms / 1e3) / 1e12, 1),
            "loss": loss, "loss_finite": finite, "precision": precision, "parameters": n_params, "cuda_graphed_library_stages": graphed,
+           "device_side_sample_prep": prep,
            "exchange": "one flat all-reduce (sum) of all %d gradients after the backward, scaled by 1/G" % n_params if world > 1 else "none (1 GPU)",
            "ms_per_step_bucketed_overlap": round(ms_bucketed, 3) if ms_bucketed else None,
            "bucketed_allreduce_ms_by_bucket": {"early(decoder+heads)": round(ar.get(0, 0.0), 3), "layer4 branches": round(ar.get(1, 0.0), 3),

@@ -245,6 +245,14 @@ int snb_render_batch_bwd(snb_handle h, const snb_batch_desc* d, const float* px,
                          const float* shape_latent, const float* texture_latent, const void* workspace,
                          const float* g_rgb, const float* g_depth, const float* g_acc, void* scratch, float* g_c2w,
                          float* g_shape_latent, float* g_texture_latent, void* stream);
+/* Dataset-side sample preparation on the device: utils.prepare_pixel_samples (utils.py:330-377), which the
+ * reference's DataLoader workers run per object on the CPU (data_nuscenes.py:615-658), for n_objs objects in one launch.
+ * px, py (B,n) pixel coordinates of the chosen rays; K (B,3,3); c2w (B,3,4); z (B,S) every object's shared sample vector
+ * (utils.sample_from_rays, built by the caller with the reference's torch calls); obj_diag (B); flip (B) int32 or NULL (sym_aug
+ * taken: y components negated); shapenet_swap: (x, y, z) -> (-y, x, z).  -> xyz, viewdir_rep (B,n,S,3), forward only. */
+int snb_prepare_samples_batch(const float* px, const float* py, const float* K, const float* c2w, const float* z,
+                              const float* obj_diag, const int32_t* flip, int32_t n_objs, int64_t rays_per_obj,
+                              int32_t n_samples, int32_t shapenet_swap, float* xyz, float* viewdir_rep, void* stream);
 /* The refine losses (below) of n_objs objects in one launch per direction: rgb, tgt (B,N,3); acc, occ (B,N);
  * out3 (B,3) = {loss, loss_rgb, loss_occ} per object, each over its own denominator; g_loss (B) or NULL (= ones). */
 size_t snb_refine_loss_batch_scratch_bytes(int32_t n_objs);

@@ -81,6 +81,7 @@ SIGNATURES = {
     "snb_render_batch_scratch_bytes": (c_sz, [ctypes.c_void_p, ctypes.POINTER(SnbBatchDesc)]),
     "snb_render_batch_fwd": (c_i32, [ctypes.c_void_p, ctypes.POINTER(SnbBatchDesc)] + [c_f] * 15),
     "snb_render_batch_bwd": (c_i32, [ctypes.c_void_p, ctypes.POINTER(SnbBatchDesc)] + [c_f] * 18),
+    "snb_prepare_samples_batch": (c_i32, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i32, c_i64, c_i32, c_i32, c_f, c_f, c_f]),
     "snb_refine_loss_batch_scratch_bytes": (c_sz, [c_i32]),
     "snb_refine_loss_batch_fwd": (c_i32, [c_f, c_f, c_f, c_f, c_i32, c_i64, c_flt, c_f, c_f, c_f]),
     "snb_refine_loss_batch_bwd": (c_i32, [c_f, c_f, c_f, c_f, c_i32, c_i64, c_flt, c_f, c_f, c_f, c_f, c_f]),

@@ -522,6 +522,54 @@ __global__ void __launch_bounds__(256) rb_rays_bwd_kernel(const float* __restric
   }
 }
 
+// --------------------------------------------------------------------------------------------------------------- dataset-side ray prep
+// the samples a training batch needs -- utils.prepare_pixel_samples (utils.py:330-377) as the reference's DataLoader
+// workers run it per object on the CPU (data_nuscenes.py:615-658), shipping (n_rays, S, 3) xyz + viewdir per object over PCIe --
+// for B objects in one launch on the device: pixel -> ray (utils.get_rays), shared sample vector z_b (S) of the object (built on the host
+// with the reference's torch calls, B x S floats), xyz = (o + d z) / obj_diag, optional y flip (sym_aug) and shapenet axis swap
+// (utils.py:471-495).  One warp per ray, lanes over samples.  Same arithmetic as get_rays_fwd_kernel + sample_shell_fwd_kernel.
+__global__ void __launch_bounds__(256) rb_shell_prep_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                                           const float* __restrict__ K, const float* __restrict__ c2w,
+                                                           const float* __restrict__ z, const float* __restrict__ obj_diag,
+                                                           const int32_t* __restrict__ flip, int64_t n, int S, int swap, int64_t total,
+                                                           float* __restrict__ xyz, float* __restrict__ vrep) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t i = warp; i < total; i += nwarps) {
+    const int64_t b = i / n;
+    const float* Kb = K + 9 * b;
+    const float* P = c2w + 12 * b;
+    const float cx = __ldg(Kb + 2), cy = __ldg(Kb + 5), fx = __ldg(Kb), fy = __ldg(Kb + 4);
+    const float p0 = __fdiv_rn(__fsub_rn(__ldg(px + i), cx), fx), p1 = __fdiv_rn(__fsub_rn(__ldg(py + i), cy), fy), p2 = 1.f;
+    float r[3], o[3], d[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      r[a] = __fadd_rn(__fadd_rn(__fmul_rn(p0, __ldg(P + 4 * a)), __fmul_rn(p1, __ldg(P + 4 * a + 1))), __fmul_rn(p2, __ldg(P + 4 * a + 2)));
+    const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(r[0], r[0]), __fmul_rn(r[1], r[1])), __fmul_rn(r[2], r[2])));
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { d[a] = __fdiv_rn(r[a], nrm); o[a] = __ldg(P + 4 * a + 3); }
+    const float diag = __ldg(obj_diag + b);
+    const float sy = (flip != nullptr && flip[b]) ? -1.f : 1.f;       // sym_aug: xyz[:, :, 1] *= -1, viewdir[:, :, 1] *= -1 (utils.py:474-477)
+    const float* zb = z + b * S;
+    for (int k = lane; k < S; k += 32) {
+      const float zk = __ldg(zb + k);
+      float x[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) x[a] = __fdiv_rn(__fadd_rn(o[a], __fmul_rn(d[a], zk)), diag);
+      const float xy = x[1] * sy, dy = d[1] * sy;
+      const int64_t idx = i * S + k;
+      if (swap) {   // x' = (-y, x, z) (utils.py:492-495)
+        xyz[3 * idx] = -xy; xyz[3 * idx + 1] = x[0]; xyz[3 * idx + 2] = x[2];
+        vrep[3 * idx] = -dy; vrep[3 * idx + 1] = d[0]; vrep[3 * idx + 2] = d[2];
+      } else {
+        xyz[3 * idx] = x[0]; xyz[3 * idx + 1] = xy; xyz[3 * idx + 2] = x[2];
+        vrep[3 * idx] = d[0]; vrep[3 * idx + 1] = dy; vrep[3 * idx + 2] = d[2];
+      }
+    }
+  }
+}
+
 // --------------------------------------------------------------------------------------------------------------- batched losses
 // optimizer_nuscenes.py:729-736 per object (see loss.cu): grid (chunks, B)
 struct LossAccB { double num_rgb, num_occ, den; unsigned int ticket, pad; double den_final; };
@@ -815,6 +863,23 @@ extern "C" int snb_refine_loss_batch_bwd(const float* rgb, const float* acc, con
   if (gx < 1) gx = 1;
   rb::rb_loss_bwd_kernel<<<dim3((unsigned)gx, (unsigned)n_objs), 256, 0, (cudaStream_t)stream>>>(rgb, acc, tgt, occ, rays_per_obj, occ_coef,
                                                                                                 (const rb::LossAccB*)scratch, g_loss, g_rgb, g_acc);
+  SNB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int snb_prepare_samples_batch(const float* px, const float* py, const float* K, const float* c2w, const float* z,
+                                         const float* obj_diag, const int32_t* flip, int32_t n_objs, int64_t rays_per_obj,
+                                         int32_t n_samples, int32_t shapenet_swap, float* xyz, float* viewdir_rep, void* stream) {
+  SNB_REQUIRE(n_objs >= 1 && rays_per_obj >= 0 && n_samples >= 1, "prepare_samples_batch: bad sizes");
+  if (rays_per_obj == 0) return 0;
+  SNB_REQUIRE(px && py && K && c2w && z && obj_diag && xyz && viewdir_rep, "prepare_samples_batch: null pointer");
+  const int sms = sm_count();
+  SNB_REQUIRE(sms > 0, "prepare_samples_batch: no CUDA device (there is no CPU fallback)");
+  const int64_t total = (int64_t)n_objs * rays_per_obj;
+  int64_t grid = ceil_div(total, 8);
+  if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
+  rb::rb_shell_prep_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(px, py, K, c2w, z, obj_diag, flip, rays_per_obj, n_samples,
+                                                                           shapenet_swap, total, xyz, viewdir_rep);
   SNB_LAUNCH_CHECK();
   return 0;
 }

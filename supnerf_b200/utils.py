@@ -298,6 +298,60 @@ def prepare_pixel_samples(img, mask_occ, cam_pose, obj_diag, K, roi, n_rays, n_s
     return xyz, viewdir_s, z_vals, rgb_tgt, occ_pixels
 
 
+def prepare_pixel_samples_batch(device, imgs, masks_occ, cam_poses, obj_diags, Ks, rois, n_rays, n_samples, shapenet_obj_cood, sym_aug,
+                                 im_sz=None):
+    """``prepare_pixel_samples`` (utils.py:330-377) for a whole training batch ON THE DEVICE: what the reference's
+    DataLoader workers compute per object on the CPU and ship over PCIe (data_nuscenes.py:643-658: (n_rays, S, 3) xyz + viewdir =
+    1.5 MB per object at 1024 x 64) becomes ONE kernel over the batch; only the crops' targets and B x S sample depths cross PCIe.
+    Per object, in batch order, the host consumes the RNGs exactly as the per-object call does (np.random.permutation, torch.rand(S)
+    on the CPU generator, random.uniform when sym_aug), so the result equals B per-object calls bit for bit.
+    imgs / masks_occ: lists of per-object crops (h,w,3) / (h,w,1); cam_poses B x (3,4); obj_diags B floats; Ks B x (3,3);
+    rois B x (4,).  Every object must yield the same number of rays (n_rays <= its pixel count).
+    -> xyz (B,n,S,3), viewdir (B,n,S,3), z_vals (B,S), rgb_tgt (B,n,3), occ_pixels (B,n,1) on `device`."""
+    from . import _lib
+    from ._lib import check, on_device, ptr, stream_ptr
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("supnerf_b200 has no CPU path")
+    b = len(rois)
+    pxs, pys, zs, tgts, occs, flips = [], [], [], [], [], []
+    for i in range(b):
+        cam = cam_poses[i]
+        near, far = _shell_near_far(cam, obj_diags[i])
+        img, mask = imgs[i], masks_occ[i]
+        if im_sz is None:
+            px, py = _pixel_grid(rois[i], None)
+        else:
+            px, py = _pixel_grid(rois[i], [im_sz, im_sz])
+            img, mask = _resize_targets(img, mask, im_sz)
+        n_i = int(np.minimum(px.numel(), n_rays))
+        ids = np.random.permutation(px.numel())[:n_i]
+        dist = (far - near) / (2 * n_samples)
+        z = torch.linspace(near + dist, far - dist, n_samples).type_as(cam)
+        z += (torch.rand(n_samples) * (far - near) / (2 * n_samples)).type_as(cam)
+        flips.append(1 if (bool(sym_aug) and random.uniform(0, 1) > 0.5) else 0)
+        pxs.append(px.reshape(-1)[ids])
+        pys.append(py.reshape(-1)[ids])
+        zs.append(z)
+        tgts.append(img.reshape(-1, 3)[ids])
+        occs.append(mask.reshape(-1, 1)[ids])
+    n = pxs[0].numel()
+    if any(p.numel() != n for p in pxs):
+        raise ValueError("prepare_pixel_samples_batch: every object must yield the same number of rays")
+    f32 = lambda ts: torch.stack([torch.as_tensor(t, dtype=torch.float32) for t in ts]).to(device, non_blocking=True).contiguous()  # noqa: E731
+    px_d, py_d, z_d, K_d, cam_d = f32(pxs), f32(pys), f32(zs), f32(list(Ks)), f32(list(cam_poses))
+    diag_d = torch.tensor([float(d) for d in obj_diags], dtype=torch.float32).to(device, non_blocking=True)
+    flip_d = torch.tensor(flips, dtype=torch.int32).to(device, non_blocking=True) if any(flips) else None
+    xyz = torch.empty(b, n, n_samples, 3, device=device, dtype=torch.float32)
+    vrep = torch.empty_like(xyz)
+    lib = _lib.load()
+    with on_device(device):
+        check(lib.snb_prepare_samples_batch(ptr(px_d), ptr(py_d), ptr(K_d), ptr(cam_d), ptr(z_d), ptr(diag_d), ptr(flip_d), b, n,
+                                            int(n_samples), int(bool(shapenet_obj_cood)), ptr(xyz), ptr(vrep), stream_ptr()),
+              "snb_prepare_samples_batch")
+    return xyz, vrep, z_d, f32(tgts), f32(occs)
+
+
 def render_rays(model, device, img, mask_occ, cam_pose, obj_diag, K, roi, n_samples, shapecode, texturecode,
                 shapenet_obj_cood, sym_aug, kitti2nusc=False, n_rays=2500):
     """utils.py:380-432."""

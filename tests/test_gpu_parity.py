@@ -826,3 +826,29 @@ def test_shell_sample_vector_on_device_option():
         S.utils.SHELL_Z_ON_DEVICE = False
     for a, b, n_ in zip(outs[1], outs[0], ("rgb", "depth", "acc")):
         assert parity_ok(n_, a, b, 1e-5)
+
+
+@pytest.mark.parametrize("sym_aug,im_sz", [(0, 24), (1, 16)])
+def test_prepare_pixel_samples_batch_equals_per_object_calls(sym_aug, im_sz):
+    """utils.prepare_pixel_samples_batch (ONE kernel for the batch, on the device) against B calls of
+    utils.prepare_pixel_samples (the reference's per-object DataLoader work, utils.py:330-377) under the same RNG state: bit-identical
+    samples, targets and masks, including the symmetric-augmentation flip and the shapenet swap."""
+    import random
+    S = snb()
+    B, n_rays, S_ = 4, 200, 16
+    objs = [oracle.synthetic_object(400 + i, im_sz=24) for i in range(B)]
+    diags = [np.linalg.norm(o["wlh"]).astype(np.float32) for o in objs]
+
+    def seed():
+        np.random.seed(13); torch.manual_seed(13); random.seed(13)
+    seed()
+    per = [S.utils.prepare_pixel_samples(o["img"].to(DEV), o["mask_occ"].to(DEV), o["cam_pose"].to(DEV), d, o["K"].to(DEV), o["roi"], n_rays, S_, 1,
+                                         sym_aug, im_sz=im_sz) for o, d in zip(objs, diags)]
+    seed()
+    xyz, vd, z, tgt, occ = S.utils.prepare_pixel_samples_batch(DEV, [o["img"] for o in objs], [o["mask_occ"] for o in objs],
+                                                               [o["cam_pose"] for o in objs], diags, [o["K"] for o in objs],
+                                                               [o["roi"] for o in objs], n_rays, S_, 1, sym_aug, im_sz=im_sz)
+    assert xyz.shape == (B, n_rays, S_, 3) and vd.shape == xyz.shape and z.shape == (B, S_) and tgt.shape == (B, n_rays, 3)
+    for i in range(B):
+        assert torch.equal(xyz[i], per[i][0]) and torch.equal(vd[i], per[i][1]) and torch.equal(z[i], per[i][2].to(z.device))
+        assert torch.equal(tgt[i], per[i][3].to(tgt.device)) and torch.equal(occ[i], per[i][4].to(occ.device))
