@@ -147,3 +147,19 @@ def test_shipped_artefacts_do_not_name_batch_memcpy_entry_points():
             assert not banned.search(f.read()), p
     with open(_lib.LIB_PATH, "rb") as f:
         assert b"libcudart.so" in f.read()  # dynamic runtime
+
+
+def test_result_file_formats_round_trip(tmp_path):
+    """The refine loops' result files (optimizer_nuscenes.py:1463-1476 codes+poses.pth, :1405-1409 cross_eval.pth): same keys."""
+    import torch
+    from supnerf_b200 import scene
+    p = str(tmp_path / "codes+poses.pth")
+    vals = dict(num_obj=2, optimized_shapecodes=torch.zeros(2, 3, 256), optimized_texturecodes=torch.zeros(2, 3, 256), optimized_poses=torch.zeros(2, 3, 3, 4),
+                psnr_eval={"a": [1.0]}, ssim_eval={}, depth_err_mean={}, lidar_pts_cnt={}, R_eval={}, T_eval={})
+    scene.save_opts_w_pose(p, **vals)
+    got = scene.load_result(p)
+    assert list(got.keys()) == ["num_obj", "optimized_shapecodes", "optimized_texturecodes", "optimized_poses", "psnr_eval", "ssim_eval",
+                                "depth_err_mean", "lidar_pts_cnt", "R_eval", "T_eval"]
+    q = str(tmp_path / "cross_eval.pth")
+    scene.save_cross_eval(q, {"i": [torch.ones(2, 2)]}, {}, {}, [0, 5, 10])
+    assert list(scene.load_result(q).keys()) == ["psnr_eval_mat_per_ins", "depth_eval_mat_per_ins", "cnt_lidar_pts_per_ins", "CODE_SAVE_ITERS_"]

@@ -852,3 +852,32 @@ def test_prepare_pixel_samples_batch_equals_per_object_calls(sym_aug, im_sz):
     for i in range(B):
         assert torch.equal(xyz[i], per[i][0]) and torch.equal(vd[i], per[i][1]) and torch.equal(z[i], per[i][2].to(z.device))
         assert torch.equal(tgt[i], per[i][3].to(tgt.device)) and torch.equal(occ[i], per[i][4].to(occ.device))
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_scene_compositor_against_the_reference_vis_scene(prec):
+    """scene.render_scene (ray bookkeeping around the merge, decoder over all objects' rows, merge-sort + white
+    compositing kernels) against the canvas the reference's own vis_scene (scripts/demo.py:425-579, executed unmodified by
+    tools/make_golden.py:golden_scene) painted for the same three objects, camera manipulation and jitter draws.  The canvas is
+    uint8: the reference evaluates the slab test in float64 on the host, the kernel in fp32, so single pixels may differ by one
+    grey level (fp32 mode) / a few (bf16 mode: 2e-2 x 255 = 5)."""
+    S = snb()
+    g = load_golden("scene")
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=int(g["seed"]))
+    m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
+    m.precision = prec
+    m.requires_grad_(False)
+    canvas = S.scene.render_scene(m, DEV, T(g["K"]), T(g["obj_poses"]), T(g["obj_wlh"]), T(g["shapecodes"]), T(g["texturecodes"]), int(g["H"]),
+                                  int(g["W"]), int(g["n_samples"]), manipulation=[float(v) for v in g["manipulation"]], rend_aabb=True,
+                                  adjust_scale=float(g["adjust_scale"]), shapenet_obj_cood=True, ray_batch_size=int(g["ray_batch_size"]),
+                                  jitter=T(g["jitter"]))
+    ref = g["canvas"]
+    assert canvas.shape == ref.shape and canvas.dtype == np.uint8
+    covered_ref, covered = (ref != 255).any(-1), (canvas != 255).any(-1)
+    assert np.array_equal(covered, covered_ref)                       # the same pixels are covered by an object
+    diff = np.abs(canvas.astype(np.int32) - ref.astype(np.int32))
+    tol = 1 if prec == "fp32" else 5
+    frac = float((diff <= tol).mean())
+    from conftest import parity
+    parity("canvas_uint8", canvas.astype(np.float32), ref.astype(np.float32), 1e-2 if prec == "fp32" else 2e-2)
+    assert frac >= 0.999, (frac, int(diff.max()))

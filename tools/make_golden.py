@@ -633,6 +633,58 @@ def golden_pose_estimator():
     save("pose_estimator", **out)
 
 
+def golden_scene():
+    """The whole scene compositor of the demo: the reference's `vis_scene` method (scripts/demo.py:425-579) is
+    EXECUTED as it stands (its source text is read from the read-only tree and exec-ed; `self` is a plain namespace carrying the
+    attributes it reads) on three synthetic cars in a 64 x 48 image, box-bounded rays, 16 samples, several ray batches.  Every
+    torch.rand_like draw is recorded (the reference draws on the CPU generator)."""
+    import textwrap
+    import tqdm
+    src = open("/root/reference/scripts/demo.py").read().splitlines()
+    start = next(i for i, l in enumerate(src) if l.startswith("    def vis_scene("))
+    end = next(i for i in range(start, len(src)) if src[i].strip() == "return canvas")
+    fn_src = textwrap.dedent("\n".join(src[start:end + 1]))
+    env = dict(torch=torch, np=np, tqdm=tqdm, corners_of_box_batch=ref_utils.corners_of_box_batch, view_points_batch=ref_utils.view_points_batch,
+               roi_process=ref_utils.roi_process, get_rays=ref_utils.get_rays, ray_box_intersection=ref_utils.ray_box_intersection,
+               sample_from_rays_v2=ref_utils.sample_from_rays_v2, volume_rendering3=ref_renderer.volume_rendering3)
+    exec(fn_src, env)
+    seed, Nb, H, W, S = 33, 3, 48, 64, 16
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=seed)
+    model = model_supnerf.SUPNeRF(shape_blocks=3, texture_blocks=1, pose_blocks=3, regress_blocks=3, latent_dim=256)
+    model.load_state_dict(sd, strict=False)
+    model.requires_grad_(False)
+    g = torch.Generator().manual_seed(seed)
+    base = torch.tensor([[0., -1., 0.], [0., 0., -1.], [1., 0., 0.]])
+    poses = []
+    for yaw, t in ((0.4, (-2.2, 0.3, 9.0)), (-1.1, (1.5, 0.2, 11.0)), (2.0, (0.2, 0.4, 14.0))):
+        Rz = torch.tensor([[np.cos(yaw), -np.sin(yaw), 0.], [np.sin(yaw), np.cos(yaw), 0.], [0., 0., 1.]], dtype=torch.float32)
+        poses.append(torch.cat([base @ Rz, torch.tensor(t).view(3, 1)], 1))
+    obj_poses = torch.stack(poses)
+    obj_wlh = torch.tensor([[1.9, 4.6, 1.7], [2.0, 4.9, 1.6], [1.8, 4.3, 1.8]])
+    K = torch.tensor([[60., 0., 32.], [0., 60., 24.], [0., 0., 1.]])
+    shp, tex = oracle.synthetic_latents(seed, Nb)
+    me = types.SimpleNamespace(obj_poses=obj_poses, obj_wlh=obj_wlh, hpams={"dataset": {"img_h": H, "img_w": W}, "n_samples": S, "shapenet_obj_cood": 1},
+                               rend_aabb=True, ray_batch_size=300, adjust_scale=1.1, model=model, device="cpu", shapecodes=shp, texturecodes=tex)
+    draws = []
+    orig = torch.rand_like
+
+    def rec(t, *a, **k):
+        v = orig(t, *a, **k)
+        draws.append(v.clone())
+        return v
+    torch.rand_like = rec
+    try:
+        torch.manual_seed(seed)
+        canvas = env["vis_scene"](me, {"cam_intrinsics": K}, [0.3, -0.1, 1.0])
+    finally:
+        torch.rand_like = orig
+    jitter = torch.cat(draws, 0).view(-1, Nb, S)
+    save("scene", seed=seed, H=H, W=W, n_samples=S, K=K, obj_poses=obj_poses, obj_wlh=obj_wlh, shapecodes=shp, texturecodes=tex,
+         manipulation=np.asarray([0.3, -0.1, 1.0], dtype=np.float32), adjust_scale=np.float32(1.1), ray_batch_size=np.int64(300), jitter=jitter,
+         canvas=canvas, weights_sha256=np.frombuffer(state_hash(sd).encode(), dtype=np.uint8))
+    print("scene: valid rays", jitter.shape[0], "non-white pixels", int((canvas != 255).any(-1).sum()))
+
+
 def golden_state_dict_keys():
     """state_dict key -> shape of the reference modules (the checkpoint ABI): lets the CPU tests check that the
     drop-in modules load a reference checkpoint with the default strict=True without importing the reference."""
@@ -657,4 +709,5 @@ if __name__ == "__main__":
     golden_drivers()
     golden_drivers_truth64()
     golden_pose_estimator()
+    golden_scene()
     golden_state_dict_keys()
