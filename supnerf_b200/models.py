@@ -61,6 +61,11 @@ class _DecoderBase(nn.Module):
         replica.__dict__["_handles"] = {}
         return replica
 
+    def invalidate_packed(self):
+        """bf16 mode: re-pack the weight images at the next call (after ``p.data`` edits autograd's version counter cannot see)."""
+        for h in self._handles.values():
+            h.invalidate_packed()
+
     def _handle(self, device):
         key = (device.type, device.index)
         if key not in self._handles:

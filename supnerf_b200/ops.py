@@ -330,10 +330,19 @@ class DecoderHandle:
         if self.__dict__.get("_frozen") is not tensors:
             self._frozen = tensors
 
+    def invalidate_packed(self):
+        """Force a re-pack of the bf16 weight images at the next call.  Needed after weight edits autograd's version counter does
+        not see (``p.data.copy_(...)``, ``p.data.mul_(...)``: EMA updates, manual checkpoint loading idioms); ordinary in-place
+        updates (optimisers, ``p.copy_`` under no_grad) bump the counter and are picked up automatically."""
+        self._packed_key = None
+
+    def packed_key(self, tensors):
+        return tuple((t.data_ptr(), t._version) for t in tensors)
+
     def ensure_packed(self, tensors):
         """bf16 mode: (re)pack when a parameter was replaced or modified in place."""
         lib = _lib.load()
-        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        key = self.packed_key(tensors)
         if key == self._packed_key and self._packed is not None:
             return
         nbytes = lib.snb_packed_bytes(self.h)
@@ -366,21 +375,28 @@ class _Decoder(torch.autograd.Function):
             check(lib.snb_mlp_fwd(handle.h, precision, ptr(xyz), ptr(viewdir), m, n_objs, ptr(shape_latent), ptr(texture_latent),
                                   ptr(sigma), ptr(rgb), ptr(ws), stream_ptr()), "snb_mlp_fwd")
         ctx.save_for_backward(xyz, viewdir, shape_latent, texture_latent, sigma, ws, *weights)
-        ctx.meta = (handle, precision, n_objs)
+        ctx.meta = (handle, precision, n_objs, handle._packed_key if precision != PREC["fp32"] else None)
         return sigma, rgb
 
     @staticmethod
     def backward(ctx, g_sigma, g_rgb):
         lib = _lib.load()
         xyz, viewdir, shape_latent, texture_latent, sigma, ws, *weights = ctx.saved_tensors
-        handle, precision, n_objs = ctx.meta
+        handle, precision, n_objs, packed_key = ctx.meta
+        if packed_key is not None and handle._packed_key != packed_key:
+            # the weights were re-packed between this graph's forward and its backward (forward, optimizer.step, forward,
+            # backward-of-the-first): the masks / activations of the old weights must not meet the W^T images of the new ones
+            raise RuntimeError("supnerf_b200: the decoder weights changed between this forward and its backward (bf16 mode keeps ONE "
+                               "packed image per handle); run the backward before updating the weights, or use precision='fp32'")
         m = xyz.numel() // 3
         dev = xyz.device
         g_sigma = f32c(g_sigma) if g_sigma is not None else torch.zeros(m, device=dev)
         g_rgb = f32c(g_rgb) if g_rgb is not None else torch.zeros(m, 3, device=dev)
         need = ctx.needs_input_grad
-        g_xyz = torch.empty_like(xyz) if need[3] else None
-        g_vd = torch.empty_like(viewdir) if need[4] else None
+        # the tensor-core backward folds d xyz and d viewdir in one program: when only one of them is wanted the other goes to scratch
+        want_pose = need[3] or need[4]
+        g_xyz = torch.empty_like(xyz) if want_pose else None
+        g_vd = torch.empty_like(viewdir) if want_pose else None
         g_sl = torch.empty_like(shape_latent)
         g_tl = torch.empty_like(texture_latent)
         need_w = any(need[7:])
@@ -395,7 +411,8 @@ class _Decoder(torch.autograd.Function):
                                   ptr(sigma), ptr(g_sigma), ptr(g_rgb), ptr(ws), ptr(scratch), ptr(g_xyz), ptr(g_vd), ptr(g_sl),
                                   ptr(g_tl), gw_arr, stream_ptr()), "snb_mlp_bwd")
         out_w = tuple(gws) if need_w else tuple(None for _ in weights)
-        return (None, None, None, g_xyz, g_vd, g_sl if need[5] else None, g_tl if need[6] else None) + out_w
+        return (None, None, None, g_xyz if need[3] else None, g_vd if need[4] else None, g_sl if need[5] else None,
+                g_tl if need[6] else None) + out_w
 
 
 def decoder(handle, precision, xyz, viewdir, shape_latent, texture_latent, weights):
@@ -423,6 +440,8 @@ def _zeros_like_cached(dev, n):
     """Read-only zeros (n,) on `dev`, for upstream gradients autograd did not supply (never written by the kernels)."""
     key = (str(dev), int(n))
     z = _ZEROS.get(key)
+    if z is None and torch.cuda.is_current_stream_capturing():
+        return torch.zeros(n, device=dev, dtype=torch.float32)   # inside a CUDA-graph capture: a graph-private buffer, no synchronisation, not cached
     if z is None:
         if len(_ZEROS) > 64:
             _ZEROS.clear()

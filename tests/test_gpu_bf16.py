@@ -449,3 +449,44 @@ def test_batched_render_equals_per_object_render(n_obj, im, S_):
     parity("obj0_g_pose_vs_oracle", cams.grad[0], cam_o.grad, TOL)
     parity("obj0_g_shape_vs_oracle", shps.grad[0], s_o.grad[0], TOL)
     parity("obj0_g_texture_vs_oracle", texs.grad[0], t_o.grad[0], TOL)
+
+
+def test_packed_weight_staleness_and_single_input_gradient():
+    """(a) weight edits through ``p.data`` do not bump autograd's version counter, so the packed bf16 images stay as they
+    were until ``model.invalidate_packed()``; (b) a backward whose forward's weights were re-packed in between fails loudly instead
+    of mixing old masks with new W^T images; (c) asking for d xyz WITHOUT d viewdir (or the reverse) works in bf16 mode."""
+    S = snb()
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=3)
+    m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
+    m.precision = "bf16"
+    m.requires_grad_(False)
+    xyz, vd, shp, tex, _, _ = _case(1, 32, 16, 3)
+    xyz, vd, shp, tex = xyz.to(DEV), vd.to(DEV), shp.to(DEV), tex.to(DEV)
+    with torch.no_grad():
+        s0, c0 = m(xyz, vd, shp, tex)
+        m.rgb[2].weight.data.mul_(2.0)          # the head is read from the live fp32 pointer: visible at once
+        m.shape_layer_2[0].weight.data.mul_(1.5)   # a tensor-core layer: the packed image is stale until invalidated
+        s1, c1 = m(xyz, vd, shp, tex)
+        assert torch.equal(s1, s0)
+        m.invalidate_packed()
+        s2, c2 = m(xyz, vd, shp, tex)
+        assert not torch.equal(s2, s0)
+    # (c) one input gradient only
+    x = xyz.clone().requires_grad_()
+    sig, rgbs = m(x, vd, shp, tex)
+    (sig.sum() + rgbs.sum()).backward()
+    gx = x.grad.clone()
+    x2, v2 = xyz.clone().requires_grad_(), vd.clone().requires_grad_()
+    sig, rgbs = m(x2, v2, shp, tex)
+    (sig.sum() + rgbs.sum()).backward()
+    assert torch.equal(gx, x2.grad)
+    # (b) re-pack between a forward and its backward
+    m2 = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
+    m2.precision = "bf16"
+    x3 = xyz.clone().requires_grad_()
+    sig, rgbs = m2(x3, vd, shp, tex)
+    with torch.no_grad():
+        m2.shape_layer_1[0].weight.mul_(1.01)      # an optimiser-style in-place update (bumps the version)
+    m2(xyz, vd, shp, tex)                           # second forward re-packs
+    with pytest.raises(RuntimeError):
+        (sig.sum() + rgbs.sum()).backward()
