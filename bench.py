@@ -340,7 +340,7 @@ def run_ours(args):
     roofline = None
     traffic = None
     try:   # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture (scaled by samples per launch)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
         k = tj["tc2_%s_kernel" % dom]
         traffic = int((k["dram_read_bytes"] + k["dram_write_bytes"]) * rows / tj["samples_per_captured_launch"])   # scaled to the executed rows
     except Exception:
