@@ -356,7 +356,7 @@ def run_ours(args):
                                   "value (rays/s) counts all rays, as the reference pushes all N x S rows through its MLP",
                     "avg_launch_ms": round(roof[dom]["ms"], 4),
                     "other": {k: {"ms": round(v["ms"], 4), "tflops": round(v["tflops"], 2)} for k, v in roof.items()},
-                    "mlp_share_of_step": round(sum(v["total_ms"] for v in roof.values()) / ms_total, 4),
+                    "mlp_share_of_step": round(sum(v["total_ms"] for v in roof.values()) / (ms_single if batched else ms_total), 4),
                     "mlp_share_of_single_stream_step": round(sum(v["total_ms"] for v in roof.values()) / ms_single, 4),
                     "single_stream_ms_per_step": round(ms_single / args.steps, 3),
                     "timed": "CUDA events on the launch stream around the kernel alone, over a timed pass of the same step on ONE "

@@ -465,7 +465,7 @@ def test_packed_weight_staleness_and_single_input_gradient():
     with torch.no_grad():
         s0, c0 = m(xyz, vd, shp, tex)
         m.rgb[2].weight.data.mul_(2.0)          # the head is read from the live fp32 pointer: visible at once
-        m.shape_layer_2[0].weight.data.mul_(1.5)   # a tensor-core layer: the packed image is stale until invalidated
+        m.encoding_shape.weight.data.mul_(1.5)     # a tensor-core layer: its packed image is stale until invalidated
         s1, c1 = m(xyz, vd, shp, tex)
         assert torch.equal(s1, s0)
         m.invalidate_packed()
