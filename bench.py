@@ -204,7 +204,7 @@ def run_ours(args):
         to the poses + latents close the step."""
         if batched:
             cams.grad = shps.grad = texs.grad = None
-            rgb, dep, acc = R.render_batch(model, batch, cams, shps, texs)
+            rgb, dep, acc = R.render_batch(model, batch, cams, shps, texs, fused_sampler=args.fused_sampler)
             loss, parts = snb.losses.refine_loss_batch(rgb, acc, batch.rgb_tgt, batch.occ_pixels, 0.1)
             loss.backward(gradient=ones_b)     # every object's own loss, upstream gradient 1 each
             return parts
@@ -1004,6 +1004,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--per-object", dest="batched", action="store_false",
                     help="round 1's path: one fused render per object over --streams CUDA streams (default: all objects in one launch set)")
+    ap.add_argument("--fused-sampler", action="store_true",
+                    help="north-star kernel K1: the decoder's forward computes its rows' samples from the rays (default: a sampler kernel writes them)")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (dense rows, fp32 mode, CPU / eager-CUDA reference baselines)")
     ap.add_argument("--skip-modes", action="store_true", help="skip the configs[3] / configs[4] collective-bearing modes")
     ap.add_argument("--streams", type=int, default=3, help="CUDA streams the independent objects alternate over (1 = one stream)")

@@ -231,9 +231,13 @@ typedef struct snb_batch_desc {
   int32_t n_objs;
   int32_t n_samples;
   int64_t rays_per_obj;
-  int32_t flags;        /* SNB_WHITE_BKGD | SNB_SIGMA_RELU */
+  int32_t flags;        /* SNB_WHITE_BKGD | SNB_SIGMA_RELU [| SNB_BATCH_FUSED_SAMPLER] */
   int32_t reserved;
 } snb_batch_desc;
+/* opt-in: the forward decoder computes every row's stratified sample itself from the ray (32 B) and its jitter (4 B) -- no sampler
+ * kernel and no per-row coordinates in HBM on the forward path; the backward re-materialises them in its scratch.  Bit-identical
+ * results; measured ~0.7 % slower per forward + backward step than the default. */
+#define SNB_BATCH_FUSED_SAMPLER 4
 size_t snb_render_batch_workspace_bytes(snb_handle h, const snb_batch_desc* d);
 size_t snb_render_batch_scratch_bytes(snb_handle h, const snb_batch_desc* d);
 int snb_render_batch_fwd(snb_handle h, const snb_batch_desc* d, const float* px, const float* py, const float* K,

@@ -2,6 +2,7 @@
 // handle and the precision dispatch of the decoder MLP.
 #include "common.cuh"
 #include "handle.h"
+#include "rb_rows.cuh"
 #include <stdarg.h>
 #include <string.h>
 #include <new>
@@ -39,7 +40,7 @@ size_t tc_workspace_bytes(const snb_handle_s* h, int64_t M, int64_t B);
 size_t tc_bwd_scratch_bytes(const snb_handle_s* h, int64_t M, int64_t B);
 int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, void* ws, cudaStream_t st, bool train,
-               const int64_t* m_dev, const int32_t* tile_start = nullptr);
+               const int64_t* m_dev, const int32_t* tile_start = nullptr, const rb::RowSrc* rs = nullptr);
 int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                 const float* shape_latent, const float* texture_latent, const float* sigma, const float* g_sigma,
                 const float* g_rgb, const void* ws, void* scratch, float* g_xyz, float* g_viewdir, float* g_shape_latent,

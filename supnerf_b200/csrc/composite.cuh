@@ -82,13 +82,13 @@ __device__ __forceinline__ Lane4 load_lane4(const float* __restrict__ sg, const 
   L.valid = k0 < S;
   if (L.valid) {
     const float4 s4 = __ldg(reinterpret_cast<const float4*>(sg + k0));
-    const float4 z4 = __ldg(reinterpret_cast<const float4*>(zr + k0));
+    const float4 z4 = zr ? __ldg(reinterpret_cast<const float4*>(zr + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);   // zr == NULL: the caller fills z
     const float4 a = __ldg(reinterpret_cast<const float4*>(cg + 3 * k0));
     const float4 b = __ldg(reinterpret_cast<const float4*>(cg + 3 * k0 + 4));
     const float4 c = __ldg(reinterpret_cast<const float4*>(cg + 3 * k0 + 8));
     L.s[0] = s4.x; L.s[1] = s4.y; L.s[2] = s4.z; L.s[3] = s4.w;
     L.z[0] = z4.x; L.z[1] = z4.y; L.z[2] = z4.z; L.z[3] = z4.w;
-    L.z[4] = (k0 + 4 < S) ? __ldg(zr + k0 + 4) : 0.f;
+    L.z[4] = (zr && k0 + 4 < S) ? __ldg(zr + k0 + 4) : 0.f;
     L.c[0][0] = a.x; L.c[0][1] = a.y; L.c[0][2] = a.z; L.c[1][0] = a.w;
     L.c[1][1] = b.x; L.c[1][2] = b.y; L.c[2][0] = b.z; L.c[2][1] = b.w;
     L.c[3][0] = c.y; L.c[3][1] = c.z; L.c[3][2] = c.w; L.c[2][2] = c.x;

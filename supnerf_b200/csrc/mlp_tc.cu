@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "handle.h"
 #include "tc_ptx.cuh"
+#include "rb_rows.cuh"
 #include <math.h>
 #include <algorithm>
 #include <stdlib.h>
@@ -726,7 +727,7 @@ size_t tc2_packed_bytes(const snb_handle_s* h);
 int tc2_pack_weights(const snb_handle_s* h, void* packed, cudaStream_t st);
 int tc2_launch_fwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                    const uint8_t* eimg, uint32_t* masks, float* sigma, float* rgb, float* dbg, uint8_t* save, cudaStream_t st,
-                   const int64_t* m_dev, const int32_t* tile_start);
+                   const int64_t* m_dev, const int32_t* tile_start, const rb::RowSrc* rs);
 int tc2_launch_bwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                    const uint32_t* masks, const float* sigma, const float* g_sigma, const float* g_rgb, float* g_xyz,
                    float* g_viewdir, float* g_zlat, uint8_t* save, cudaStream_t st, const int64_t* m_dev, const int32_t* tile_start);
@@ -849,8 +850,11 @@ struct ScopedKernelTimer {
 
 int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, void* ws, cudaStream_t st,
-               bool train, const int64_t* m_dev, const int32_t* tile_start) {
+               bool train, const int64_t* m_dev, const int32_t* tile_start, const rb::RowSrc* rs) {
   if (tc_common_checks(h, M, B, "mlp_fwd(bf16)", tile_start != nullptr)) return 2;
+  SNB_REQUIRE(rs == nullptr || (tile_start != nullptr && rs->rays8 && rs->box && rs->z_steps && rs->jitter && rs->order && rs->counts),
+              "mlp_fwd(bf16): a row source needs per-object tile offsets and all of its pointers");
+  SNB_REQUIRE(rs != nullptr || (xyz != nullptr && viewdir != nullptr), "mlp_fwd(bf16): null coordinates");
   SNB_REQUIRE(m_dev == nullptr || (use_v2(h) && (B == 1 || tile_start != nullptr)),
               "mlp_fwd(bf16): a device-side row count needs the two-tile kernels and one object (or per-object tile offsets)");
   SNB_REQUIRE(tile_start == nullptr || (use_v2(h) && m_dev != nullptr && !train), "mlp_fwd(bf16): per-object tile offsets need the two-tile kernels, frozen weights and a device-side row count");
@@ -865,7 +869,7 @@ int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, in
   if (use_v2(h)) {
     ScopedKernelTimer tm2(st, h->timing_on);
     if (tc2_launch_fwd(h, (const uint8_t*)h->packed + v1_packed_bytes(h), xyz, viewdir, M, B, eimg, masks, sigma, rgb,
-                       h->dbg_acts, fsave, st, m_dev, tile_start)) return 1;
+                       h->dbg_acts, fsave, st, m_dev, tile_start, rs)) return 1;
     tm2.stop(const_cast<snb_handle_s*>(h)->ev_fwd);
     SNB_LAUNCH_CHECK();
     return 0;

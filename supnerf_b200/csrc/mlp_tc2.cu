@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "handle.h"
 #include "tc_ptx.cuh"
+#include "rb_rows.cuh"
 #include <algorithm>
 #include <stdlib.h>
 #include <utility>
@@ -102,6 +103,8 @@ struct Params {
   const int64_t* m_dev;   // optional: the number of rows actually present (<= M), read on the device -- the fused render compacts
                           // the samples of rays that miss the box on the GPU and never learns the count on the host
   const int32_t* tile_start;   // optional (batched render): B + 1 ascending even tile offsets, object b owns tiles [tile_start[b], tile_start[b+1])
+  rb::RowSrc rs;               // forward, batched render (K1): rs.rays8 != NULL -> the epilogue warps compute their rows' sample
+                               // coordinates from the rays (32 B per ray + 4 B of jitter per row) instead of reading xyz / viewdir
   uint8_t* save;      // training mode (weight gradients wanted): [tile][Program::save_tile_bytes] copies of every step's A operand
   long long* trace;   // timing experiments only: CTA 0 writes clock64 stamps [pair][step][slot][4] = READY seen, MMAs issued, ACC seen, published
   Program prog;
@@ -615,7 +618,7 @@ __device__ __forceinline__ void write_pev_row(uint8_t* pev, uint32_t row, uint32
 }
 
 // ------------------------------------------------------------------------------------------ forward kernel
-template <bool DBG, bool CG2>
+template <bool DBG, bool CG2, bool K1 = false>
 __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   Smem sm;
@@ -655,14 +658,40 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_const
     const int64_t pair_first = (int64_t)blockIdx.x - crank;
     float x[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 1.f};
     const uint32_t ready_leader = CG2 ? mapa_u32(sm.bar(BAR_READY + slot), 0u) : 0u;
+    // K1 (batched render, opt-in: SNB_BATCH_FUSED_SAMPLER): a row's coordinates come from its ray.  Two dependent stages, issued one
+    // decoder step apart: (1) row -> (object, ray, sample) through tile_start / counts / order, kept as two ints; (2) rays8 + jitter
+    // -> the stratified sample (renderer.py:27-41, :111-114) in the reference's op order (rb::sample_point).  A tile's 128 rows are 2
+    // rays at S = 64, so the ray loads are warp-uniform.  Measured: bit-identical outputs, forward kernel +3 % (the epilogue warps are
+    // the critical resource at the tile boundary), see DESIGN.md row N1.
+    const float rs_fstep = K1 ? (float)(1.0 / (double)p.rs.S) : 0.f;
+    auto row_lookup = [&](int64_t p0, int32_t& gi32, int32_t& kb) {
+      int64_t r = tile_index<CG2>(p0, crank, slot) * kTileM + e.row;
+      if (r >= M_eff) r = M_eff - 1;
+      const int b = (int)obj_of_tile(p, r / kTileM);
+      const rb::ObjCounts c = p.rs.counts[b];
+      int64_t ray; int k;
+      rb::row_source(c, p.rs.order + (int64_t)b * p.rs.N, r - c.row_start, p.rs.S, &ray, &k);
+      gi32 = (int32_t)((int64_t)b * p.rs.N + ray);
+      kb = k | (b << 8);
+    };
+    auto coords_from_ray = [&](int32_t gi32, int32_t kb, float (&xo)[3], float (&dro)[3]) {
+      const int k = kb & 255, b = kb >> 8;
+      const int64_t gi = gi32;
+      const rb::SamplePt sp = rb::sample_point(p.rs.rays8 + 8 * gi, __ldg(p.rs.z_steps + k), __ldg(p.rs.jitter + gi * p.rs.S + k), rs_fstep,
+                                               __ldg(p.rs.box + 4 * b));
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { xo[a] = sp.x[a]; dro[a] = sp.d[a]; }
+    };
     auto load_coords = [&](int64_t p0, float (&xo)[3], float (&dro)[3]) {   // clamped: tiles past the end redo row M-1, never stored
       int64_t r = tile_index<CG2>(p0, crank, slot) * kTileM + e.row;
       if (r >= M_eff) r = M_eff - 1;
       xo[0] = __ldg(p.xyz + 3 * r); xo[1] = __ldg(p.xyz + 3 * r + 1); xo[2] = __ldg(p.xyz + 3 * r + 2);
       dro[0] = __ldg(p.viewdir + 3 * r); dro[1] = __ldg(p.viewdir + 3 * r + 1); dro[2] = __ldg(p.viewdir + 3 * r + 2);
     };
+    constexpr bool k1 = K1;   // compile-time: the default kernel carries none of the K1 code (it sits at the 96-register cap)
     if (pair_first < n_pairs) {   // first tile of this CTA: PE(xyz) -> chunk 0
-      load_coords(pair_first, x, dir);
+      if constexpr (k1) { int32_t g0, kb0; row_lookup(pair_first, g0, kb0); coords_from_ray(g0, kb0, x, dir); }
+      else load_coords(pair_first, x, dir);
       write_pe_row<10>(sm.chunk(slot, 0), e.row, e.hh, x);
       publish<CG2>(sm, slot, lane, ready_leader);
       if (CG2 && p.prog.pev) write_pev_row(sm.pev(slot), e.row, e.hh, dir);   // needed at encoding_viewdir only: ordered by the next publish
@@ -676,10 +705,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_fwd_kernel(const __grid_const
       uint32_t* mask_tile = p.masks + (size_t)(tile_ok ? tile : 0) * nslots * 8 * 128;
       float sig_acc = 0.f, rgb_acc[3] = {0.f, 0.f, 0.f};
       float xn[3] = {0.f, 0.f, 0.f}, dn[3] = {0.f, 0.f, 1.f};
+      int32_t nx_gi = 0, nx_kb = 0;
       for (int si = 0; si < p.prog.n_steps; ++si) {
         const Step& st = p.prog.s[si];
         const bool last = si + 1 == p.prog.n_steps;
-        if (last && has_next) load_coords(pair0 + gridDim.x, xn, dn);   // the global latency hides behind rgb.0's MMAs
+        if constexpr (k1) {
+          if (has_next && si + 2 == p.prog.n_steps) row_lookup(pair0 + gridDim.x, nx_gi, nx_kb);   // stage 1, one step ahead
+        }
+        if (last && has_next) {   // the global latency hides behind rgb.0's MMAs
+          if constexpr (k1) coords_from_ray(nx_gi, nx_kb, xn, dn);
+          else load_coords(pair0 + gridDim.x, xn, dn);
+        }
         // (computing PE(xn) here as well was measured SLOWER: 16 more live registers spill in the rgb-head epilogue)
         mbar_wait(sm.bar(BAR_ACC + slot), acc_cnt & 1u);
         acc_cnt++;
@@ -1296,6 +1332,7 @@ static int tc2_init_device() {
   if (dev >= 0 && dev < 64 && done[dev].load(std::memory_order_acquire)) return 0;
   SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
   SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
+  SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
   SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
   SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
   SNB_CHECK_CUDA(cudaFuncSetAttribute(tc2_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
@@ -1319,7 +1356,7 @@ static cudaError_t tc2_launch(K kernel, int grid, cudaStream_t st, const tc2::Pa
 
 int tc2_launch_fwd(const snb_handle_s* h, const void* packed2, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                    const uint8_t* eimg, uint32_t* masks, float* sigma, float* rgb, float* dbg, uint8_t* save, cudaStream_t st,
-                   const int64_t* m_dev, const int32_t* tile_start) {
+                   const int64_t* m_dev, const int32_t* tile_start, const rb::RowSrc* rs) {
   const Tc2Plan& pl = cached_plan2(h);
   tc2::Params p;
   fill_common2(p, h, packed2, xyz, viewdir, M, B, eimg, masks);
@@ -1327,11 +1364,15 @@ int tc2_launch_fwd(const snb_handle_s* h, const void* packed2, const float* xyz,
   p.save = save;
   p.m_dev = m_dev;
   p.tile_start = tile_start;
+  if (rs) p.rs = *rs;
   const bool cg2 = tc2_use_cg2(h, p);
+  SNB_REQUIRE(rs == nullptr || (cg2 && !dbg && !save), "tc2 forward: the fused sampler runs on the cta_group::2 kernels (frozen weights)");
   p.prog = save ? pl.fwd_train : ((cg2 && !dbg) ? pl.fwd_merged : pl.fwd);
   if (tc2_init_device()) return 1;
   if (dbg) {
     SNB_CHECK_CUDA(tc2_launch(tc2_fwd_kernel<true, false>, tc2_grid(tc2_fwd_kernel<true, false>, M), st, p));
+  } else if (cg2 && p.rs.rays8 != nullptr) {
+    SNB_CHECK_CUDA(tc2_launch(tc2_fwd_kernel<false, true, true>, tc2_grid(tc2_fwd_kernel<false, true, true>, M), st, p));
   } else if (cg2) {
     SNB_CHECK_CUDA(tc2_launch(tc2_fwd_kernel<false, true>, tc2_grid(tc2_fwd_kernel<false, true>, M), st, p));
   } else {

@@ -21,11 +21,11 @@
 #include "compact.h"
 #include "sampler.cuh"
 #include "composite.cuh"
+#include "rb_rows.cuh"
 
 namespace snb {
 namespace rb {
 
-struct ObjCounts { int64_t n_hit, n_miss, rows, row_start; };
 struct Meta { int64_t total_rows; unsigned int done, pad; };
 
 constexpr int kMaxObjs = 1024;
@@ -143,44 +143,6 @@ __global__ void __launch_bounds__(1024) rb_plan_kernel(const uint8_t* __restrict
   }
 }
 
-// object of a global compact row (row_start is ascending; every object owns at least one row)
-__device__ __forceinline__ int obj_of_row(const ObjCounts* __restrict__ counts, int B, int64_t row) {
-  int lo = 0, hi = B;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (counts[mid].row_start <= row) lo = mid; else hi = mid;
-  }
-  return lo;
-}
-
-// (ray, sample) a compact row stands for; pad rows (behind the object's last row, up to the 256-row boundary) replay its first row
-__device__ __forceinline__ void row_source(const ObjCounts& c, const int32_t* __restrict__ order, int64_t lr, int S, int64_t* ray, int* k) {
-  if (lr >= c.rows) lr = 0;
-  if (lr < c.n_hit * S) { *ray = order[lr / S]; *k = (int)(lr % S); }
-  else { *ray = order[c.n_hit + (lr - c.n_hit * S)]; *k = S - 1; }   // a miss ray's samples are one point: the last one carries the weight
-}
-
-// the stratified sample (renderer.py:27-41 + :111-114), in the reference's op order
-struct SamplePt { float x[3], d[3], zv; };
-__device__ __forceinline__ SamplePt sample_point(const float* __restrict__ r8, float zstep, float jit, float fstep, float half_diag) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(r8)), b = __ldg(reinterpret_cast<const float4*>(r8) + 1);
-  const float o[3] = {a.x, a.y, a.z};
-  SamplePt s;
-  s.d[0] = a.w; s.d[1] = b.x; s.d[2] = b.y;
-  const float near = b.z, far = b.w;
-  const float zs = __fadd_rn(zstep, __fmul_rn(jit, fstep));
-  const float zc = __fadd_rn(__fmul_rn(near, __fsub_rn(1.f, zs)), __fmul_rn(far, zs));
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    s.x[i] = __fadd_rn(o[i], __fmul_rn(zc, s.d[i]));
-    const float m = __fmul_rn(__fsub_rn(s.x[i], o[i]), half_diag);
-    q = __fadd_rn(q, __fmul_rn(m, m));
-  }
-  s.zv = sqrtf(q);
-  return s;
-}
-
 __global__ void __launch_bounds__(256) rb_gather_kernel(const float* __restrict__ rays8, const float* __restrict__ box,
                                                        const float* __restrict__ z_steps, const float* __restrict__ jitter,
                                                        const int32_t* __restrict__ order_all, const ObjCounts* __restrict__ counts,
@@ -202,12 +164,36 @@ __global__ void __launch_bounds__(256) rb_gather_kernel(const float* __restrict_
 }
 
 // --------------------------------------------------------------------------------------------------------------- compositing
+// z_vals of a lane's 4 samples (+ the next one) recomputed from the ray: the forward keeps no per-row coordinates or depths in HBM
+__device__ __forceinline__ void lane_z_from_ray(const float* __restrict__ r8, const float* __restrict__ jit_row, const float* __restrict__ z_steps,
+                                                int k0, int S, float fstep, float half_diag, float (&z)[5]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(r8)), b = __ldg(reinterpret_cast<const float4*>(r8) + 1);
+  const float o[3] = {a.x, a.y, a.z}, d[3] = {a.w, b.x, b.y};
+  if (k0 < S) {
+    const float4 j4 = __ldg(reinterpret_cast<const float4*>(jit_row + k0)), s4 = __ldg(reinterpret_cast<const float4*>(z_steps + k0));
+    z[0] = sample_zv(o, d, b.z, b.w, s4.x, j4.x, fstep, half_diag);
+    z[1] = sample_zv(o, d, b.z, b.w, s4.y, j4.y, fstep, half_diag);
+    z[2] = sample_zv(o, d, b.z, b.w, s4.z, j4.z, fstep, half_diag);
+    z[3] = sample_zv(o, d, b.z, b.w, s4.w, j4.w, fstep, half_diag);
+    z[4] = (k0 + 4 < S) ? sample_zv(o, d, b.z, b.w, __ldg(z_steps + k0 + 4), __ldg(jit_row + k0 + 4), fstep, half_diag) : 0.f;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 5; ++j) z[j] = 0.f;
+  }
+}
+
+struct ZSrc {   // z_c != NULL: depths of the compact rows are read; else recomputed from the rays
+  const float* z_c; const float* rays8; const float* box; const float* z_steps; const float* jitter;
+};
+
 template <int LPR>
 __global__ void __launch_bounds__(256) rb_composite_fwd_kernel(const float* __restrict__ sigma_c, const float* __restrict__ rgb_c,
-                                                              const float* __restrict__ z_c, const int32_t* __restrict__ order_all,
+                                                              const ZSrc zs, const int32_t* __restrict__ order_all,
                                                               const ObjCounts* __restrict__ counts, int64_t N, int S, int flags,
                                                               float* __restrict__ out_rgb, float* __restrict__ out_depth,
                                                               float* __restrict__ out_acc) {
+  const float* __restrict__ z_c = zs.z_c;
+  const float fstep = (float)(1.0 / (double)S);
   constexpr int RPW = 32 / LPR;
   const int b = blockIdx.y;
   const ObjCounts c = counts[b];
@@ -222,7 +208,11 @@ __global__ void __launch_bounds__(256) rb_composite_fwd_kernel(const float* __re
     const bool rv = seg < c.n_hit;
     const int64_t rr = rv ? seg : c.n_hit - 1;
     const int64_t row0 = c.row_start + rr * S;
-    const Lane4 L = load_lane4<LPR>(sigma_c + row0, rgb_c + row0 * 3, z_c + row0, k0, S);
+    Lane4 L = load_lane4<LPR>(sigma_c + row0, rgb_c + row0 * 3, z_c ? z_c + row0 : nullptr, k0, S);
+    if (z_c == nullptr) {
+      const int64_t gi = (int64_t)b * N + order[rr];
+      lane_z_from_ray(zs.rays8 + 8 * gi, zs.jitter + gi * S, zs.z_steps, k0, S, fstep, __ldg(zs.box + 4 * b), L.z);
+    }
     float al[4], tl[4], tp = 1.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -255,7 +245,9 @@ __global__ void __launch_bounds__(256) rb_composite_fwd_kernel(const float* __re
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < c.n_miss; j += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = mbase + j;
     const int64_t ray = (int64_t)b * N + order[c.n_hit + j];
-    const float zk = __ldg(z_c + row);
+    float zk;
+    if (z_c != nullptr) zk = __ldg(z_c + row);
+    else zk = sample_point(zs.rays8 + 8 * ray, __ldg(zs.z_steps + S - 1), __ldg(zs.jitter + ray * S + S - 1), fstep, __ldg(zs.box + 4 * b)).zv;
     const SampleTerms q = sample_terms(__ldg(sigma_c + row), zk, 0.f, true, relu);
     const float w = q.alpha;   // T = 1
     float cr = w * __ldg(rgb_c + 3 * row), cg = w * __ldg(rgb_c + 3 * row + 1), cb = w * __ldg(rgb_c + 3 * row + 2);
@@ -658,7 +650,9 @@ namespace {
 
 inline size_t al(size_t bytes) { return (bytes + 255) & ~size_t(255); }
 
-// forward workspace (kept for the backward).  Mmax = B * pad256(N * S): every object's rows if all of its rays hit
+// forward workspace (kept for the backward).  Mmax = B * pad256(N * S): every object's rows if all of its rays hit.  With the fused
+// sampler (SNB_BATCH_FUSED_SAMPLER) the forward keeps NO per-row coordinates: the decoder computes them from rays8 + jitter (K1), the
+// compositing recomputes the depths, and the backward re-materialises them in its scratch
 struct BatchLayout {
   size_t meta, counts, tile_start, rays8, hit, order, pos, xyz_c, vrep_c, z_c, sigma_c, rgb_c, mlp, total;
   int64_t Mmax;
@@ -674,9 +668,10 @@ struct BatchLayout {
     hit = o; o += al(BN);
     order = o; o += al(BN * 4);
     pos = o; o += al(BN * 4);
-    xyz_c = o; o += al(M * 12);
-    vrep_c = o; o += al(M * 12);
-    z_c = o; o += al(M * 4);
+    const size_t Mc = (d.flags & SNB_BATCH_FUSED_SAMPLER) ? 0 : M;
+    xyz_c = o; o += al(Mc * 12);
+    vrep_c = o; o += al(Mc * 12);
+    z_c = o; o += al(Mc * 4);
     sigma_c = o; o += al(M * 4);
     rgb_c = o; o += al(M * 12);
     mlp = o; o += al(tc_workspace_bytes(h, Mmax, (int64_t)B));
@@ -684,12 +679,17 @@ struct BatchLayout {
   }
 };
 
-// backward scratch
+// backward scratch: the executed rows' coordinates and depths are re-materialised here (rb_gather_kernel: the decoder backward folds
+// d PE through sin / cos of the coordinates), then the gradients
 struct BatchScratch {
-  size_t g_sigma_c, g_rgb_c, g_z_c, g_xyz_c, g_vrep_c, acc64, tickets, mlp, total;
+  size_t xyz_c, vrep_c, z_c, g_sigma_c, g_rgb_c, g_z_c, g_xyz_c, g_vrep_c, acc64, tickets, mlp, total;
   BatchScratch(snb_handle h, const snb_batch_desc& d, int64_t Mmax) {
     const size_t M = (size_t)Mmax, B = (size_t)d.n_objs;
     size_t o = 0;
+    const size_t Mc = (d.flags & SNB_BATCH_FUSED_SAMPLER) ? M : 0;
+    xyz_c = o; o += al(Mc * 12);
+    vrep_c = o; o += al(Mc * 12);
+    z_c = o; o += al(Mc * 4);
     g_sigma_c = o; o += al(M * 4);
     g_rgb_c = o; o += al(M * 12);
     g_z_c = o; o += al(M * 4);
@@ -707,7 +707,8 @@ int check_batch(snb_handle h, const snb_batch_desc* d, const char* who) {
   SNB_REQUIRE(d->n_objs >= 1 && d->n_objs <= rb::kMaxObjs && d->rays_per_obj >= 1, "%s: bad sizes", who);
   SNB_REQUIRE(d->n_samples >= 4 && d->n_samples % 4 == 0 && d->n_samples <= 128,
               "%s: the batched render needs n_samples in {4, 8, ..., 128} (vectorised compositing)", who);
-  SNB_REQUIRE(d->rays_per_obj < ((int64_t)1 << 30), "%s: too many rays per object", who);
+  SNB_REQUIRE(d->rays_per_obj < ((int64_t)1 << 30) && d->rays_per_obj * d->n_samples < ((int64_t)1 << 31) &&
+              (int64_t)d->n_objs * d->rays_per_obj < ((int64_t)1 << 31), "%s: too many rays", who);
   SNB_REQUIRE(tc_two_tile_active(h), "%s: the batched render runs on the two-tile tcgen05 decoder (CodeNeRF family, W = 256, "
                                      "shape_blocks + texture_blocks <= 4); render the objects one by one for this architecture", who);
   return 0;
@@ -762,20 +763,37 @@ extern "C" int snb_render_batch_fwd(snb_handle h, const snb_batch_desc* d, const
                                         at<rb::ObjCounts>(ws, L.counts), at<int32_t>(ws, L.tile_start), at<rb::Meta>(ws, L.meta));
   SNB_LAUNCH_CHECK();
   if (out_hit) SNB_CHECK_CUDA(cudaMemcpyAsync(out_hit, at<uint8_t>(ws, L.hit), (size_t)BN, cudaMemcpyDeviceToDevice, st));
-  rb::rb_gather_kernel<<<ew_grid(L.Mmax, 8), 256, 0, st>>>(at<float>(ws, L.rays8), box, z_steps, jitter, at<int32_t>(ws, L.order),
-                                                          at<rb::ObjCounts>(ws, L.counts), at<rb::Meta>(ws, L.meta), B, N, S,
-                                                          at<float>(ws, L.xyz_c), at<float>(ws, L.vrep_c), at<float>(ws, L.z_c));
-  SNB_LAUNCH_CHECK();
-  if (tc_forward(h, at<float>(ws, L.xyz_c), at<float>(ws, L.vrep_c), L.Mmax, B, shape_latent, texture_latent, at<float>(ws, L.sigma_c),
-                 at<float>(ws, L.rgb_c), at<uint8_t>(ws, L.mlp), st, false, &at<rb::Meta>(ws, L.meta)->total_rows, at<int32_t>(ws, L.tile_start)))
-    return 1;
+  const bool fused = (d->flags & SNB_BATCH_FUSED_SAMPLER) != 0;
+  rb::ZSrc zsrc{nullptr, at<float>(ws, L.rays8), box, z_steps, jitter};
+  if (fused) {
+    // K1: no sampler kernel on the forward path -- the decoder's epilogue warps compute every row's stratified sample from the ray
+    // (32 B per ray) and its jitter (4 B per row) and build PE(xyz) / PE(viewdir) straight in shared memory; compositing recomputes z
+    rb::RowSrc rs;
+    rs.rays8 = at<float>(ws, L.rays8); rs.box = box; rs.z_steps = z_steps; rs.jitter = jitter; rs.order = at<int32_t>(ws, L.order);
+    rs.counts = at<rb::ObjCounts>(ws, L.counts); rs.N = N; rs.S = S;
+    if (tc_forward(h, nullptr, nullptr, L.Mmax, B, shape_latent, texture_latent, at<float>(ws, L.sigma_c), at<float>(ws, L.rgb_c),
+                   at<uint8_t>(ws, L.mlp), st, false, &at<rb::Meta>(ws, L.meta)->total_rows, at<int32_t>(ws, L.tile_start), &rs))
+      return 1;
+  } else {
+    // default: the stratified samples of the EXECUTED rows are written once (28 B per row) and read back by the decoder -- measured
+    // faster than the fused sampler: the extra ~150 instructions per row sit on the decoder's critical tile-boundary chain
+    rb::rb_gather_kernel<<<ew_grid(L.Mmax, 8), 256, 0, st>>>(at<float>(ws, L.rays8), box, z_steps, jitter, at<int32_t>(ws, L.order),
+                                                            at<rb::ObjCounts>(ws, L.counts), at<rb::Meta>(ws, L.meta), B, N, S,
+                                                            at<float>(ws, L.xyz_c), at<float>(ws, L.vrep_c), at<float>(ws, L.z_c));
+    SNB_LAUNCH_CHECK();
+    if (tc_forward(h, at<float>(ws, L.xyz_c), at<float>(ws, L.vrep_c), L.Mmax, B, shape_latent, texture_latent, at<float>(ws, L.sigma_c),
+                   at<float>(ws, L.rgb_c), at<uint8_t>(ws, L.mlp), st, false, &at<rb::Meta>(ws, L.meta)->total_rows,
+                   at<int32_t>(ws, L.tile_start)))
+      return 1;
+    zsrc.z_c = at<float>(ws, L.z_c);
+  }
   const int lpr = S <= 32 ? 8 : (S <= 64 ? 16 : 32);
   int gx = (int)ceil_div(ceil_div(N, 32 / lpr), 8);
   const int cap = (sms * 8 + B - 1) / B;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   const dim3 grid((unsigned)gx, (unsigned)B);
-#define SNB_RBF(LL) rb::rb_composite_fwd_kernel<LL><<<grid, 256, 0, st>>>(at<float>(ws, L.sigma_c), at<float>(ws, L.rgb_c), at<float>(ws, L.z_c), \
+#define SNB_RBF(LL) rb::rb_composite_fwd_kernel<LL><<<grid, 256, 0, st>>>(at<float>(ws, L.sigma_c), at<float>(ws, L.rgb_c), zsrc, \
     at<int32_t>(ws, L.order), at<rb::ObjCounts>(ws, L.counts), N, S, d->flags, out_rgb, out_depth, out_acc)
   if (lpr == 8) SNB_RBF(8); else if (lpr == 16) SNB_RBF(16); else SNB_RBF(32);
 #undef SNB_RBF
@@ -809,13 +827,22 @@ extern "C" int snb_render_batch_bwd(snb_handle h, const snb_batch_desc* d, const
   if (gx < 1) gx = 1;
   const dim3 grid((unsigned)gx, (unsigned)B);
   float* gz = pose ? at<float>(sc, G.g_z_c) : nullptr;
-#define SNB_RBB(LL) rb::rb_composite_bwd_kernel<LL><<<grid, 256, 0, st>>>(at<float>(ws, L.sigma_c), at<float>(ws, L.rgb_c), at<float>(ws, L.z_c), \
+  const bool fused = (d->flags & SNB_BATCH_FUSED_SAMPLER) != 0;
+  const float *xyz_c = at<float>(ws, L.xyz_c), *vrep_c = at<float>(ws, L.vrep_c), *z_c = at<float>(ws, L.z_c);
+  if (fused) {   // the executed rows' coordinates and depths for the backward (the forward kept none)
+    rb::rb_gather_kernel<<<ew_grid(L.Mmax, 8), 256, 0, st>>>(at<float>(ws, L.rays8), box, z_steps, jitter, at<int32_t>(ws, L.order),
+                                                            at<rb::ObjCounts>(ws, L.counts), at<rb::Meta>(ws, L.meta), B, N, S,
+                                                            at<float>(sc, G.xyz_c), at<float>(sc, G.vrep_c), at<float>(sc, G.z_c));
+    SNB_LAUNCH_CHECK();
+    xyz_c = at<float>(sc, G.xyz_c); vrep_c = at<float>(sc, G.vrep_c); z_c = at<float>(sc, G.z_c);
+  }
+#define SNB_RBB(LL) rb::rb_composite_bwd_kernel<LL><<<grid, 256, 0, st>>>(at<float>(ws, L.sigma_c), at<float>(ws, L.rgb_c), z_c, \
     at<int32_t>(ws, L.order), at<rb::ObjCounts>(ws, L.counts), N, S, d->flags, g_rgb, g_depth, g_acc, at<float>(sc, G.g_sigma_c), \
     at<float>(sc, G.g_rgb_c), gz)
   if (lpr == 8) SNB_RBB(8); else if (lpr == 16) SNB_RBB(16); else SNB_RBB(32);
 #undef SNB_RBB
   SNB_LAUNCH_CHECK();
-  if (tc_backward(h, at<float>(ws, L.xyz_c), at<float>(ws, L.vrep_c), L.Mmax, B, shape_latent, texture_latent, at<float>(ws, L.sigma_c),
+  if (tc_backward(h, xyz_c, vrep_c, L.Mmax, B, shape_latent, texture_latent, at<float>(ws, L.sigma_c),
                   at<float>(sc, G.g_sigma_c), at<float>(sc, G.g_rgb_c), at<uint8_t>(ws, L.mlp), at<uint8_t>(sc, G.mlp),
                   pose ? at<float>(sc, G.g_xyz_c) : nullptr, pose ? at<float>(sc, G.g_vrep_c) : nullptr, g_shape_latent, g_texture_latent,
                   nullptr, st, false, &at<rb::Meta>(ws, L.meta)->total_rows, at<int32_t>(ws, L.tile_start)))

@@ -579,7 +579,7 @@ class _RenderBoxBatch(torch.autograd.Function):
         b, n = px.shape
         dev = px.device
         desc = _lib.SnbBatchDesc(int(b), int(n_samples), int(n), int(flags), 0)
-        key = ("batch", b, n, int(n_samples))
+        key = ("batch", b, n, int(n_samples), int(flags) & FUSED_SAMPLER)
         cache = handle.__dict__.setdefault("_render_sizes", {})
         sizes = cache.get(key)
         if sizes is None:
@@ -625,16 +625,22 @@ class _RenderBoxBatch(torch.autograd.Function):
         return (None,) * 6 + (g_c2w, None, None, None, g_sl if need[10] else None, g_tl if need[11] else None)
 
 
-def render_box_batch(handle, n_samples, white_bkgd, px, py, K, c2w, box, z_steps, jitter, shape_latent, texture_latent, weights):
+FUSED_SAMPLER = 4   # SNB_BATCH_FUSED_SAMPLER
+
+
+def render_box_batch(handle, n_samples, white_bkgd, px, py, K, c2w, box, z_steps, jitter, shape_latent, texture_latent, weights,
+                     fused_sampler=False):
     """B objects through ONE launch set.  px, py (B,N); K (B,3,3); c2w (B,3,4); box (B,4) = {diag/2, l/diag, w/diag, h/diag}
     (box_constants per object); jitter (B,N,S); latents (B,D).  -> rgb (B,N,3), depth (B,N), acc (B,N), hit (B,N) bool.
-    Frozen weights only (refine mode); bf16 decoder."""
+    Frozen weights only (refine mode); bf16 decoder.  fused_sampler: the decoder's forward computes every row's stratified sample
+    from its ray itself (north-star kernel K1: no sampler kernel, no per-row coordinates in HBM on the forward path); bit-identical
+    results, measured ~0.7 % slower per forward + backward step than the default, which writes the executed rows' samples once."""
     for w in weights:
         if w.requires_grad:
             raise RuntimeError("render_box_batch: the batched render is the frozen-weight (refine) path; "
                                "model.requires_grad_(False), or render the objects one by one")
     handle.use_frozen(weights, PREC["bf16"])
-    flags = (WHITE_BKGD if white_bkgd else 0) | SIGMA_RELU
+    flags = (WHITE_BKGD if white_bkgd else 0) | SIGMA_RELU | (FUSED_SAMPLER if fused_sampler else 0)
     return _RenderBoxBatch.apply(handle, n_samples, flags, px, py, K, c2w, box, z_steps, jitter, shape_latent, texture_latent)
 
 

@@ -133,7 +133,7 @@ class NeRFRenderer(torch.nn.Module):
         return RayBatch(torch.stack(pxs), torch.stack(pys), Ks.to(device, torch.float32, non_blocking=True).contiguous(),
                         torch.tensor(boxes, dtype=torch.float32).to(device, non_blocking=True), rgb_tgt, occ_pixels)
 
-    def render_batch(self, model, batch, cam_poses, shapecodes, texturecodes, jitter=None):
+    def render_batch(self, model, batch, cam_poses, shapecodes, texturecodes, jitter=None, fused_sampler=False):
         """B objects of a prepared ``RayBatch`` in ONE launch set (csrc/render_batch.cu).  cam_poses (B,3,4); shapecodes /
         texturecodes (B,D).  -> rgb (B,N,3), depth (B,N), acc (B,N).  One torch.rand_like of (B,N,S) per call."""
         if not isinstance(model, models._DecoderBase):
@@ -145,18 +145,18 @@ class NeRFRenderer(torch.nn.Module):
         rgb, dep, acc, _hit = ops.render_box_batch(model._handle(device), self.n_samples, self.white_bkgd, batch.px, batch.py, batch.K,
                                                    cam_poses.to(device, non_blocking=True), batch.box, _z_steps_on(device, self.n_samples),
                                                    jitter, shapecodes.to(device, non_blocking=True),
-                                                   texturecodes.to(device, non_blocking=True), model._weights())
+                                                   texturecodes.to(device, non_blocking=True), model._weights(), fused_sampler=fused_sampler)
         return rgb, dep, acc
 
     def render_rays_batch(self, model, device, imgs, masks_occ, cam_poses, obj_szs, Ks, rois, shapecodes, texturecodes, im_sz=64,
-                          jitter=None):
+                          jitter=None, fused_sampler=False):
         """``render_rays`` (renderer.py:117-167, ``n_rays=None``) of B objects in ONE launch set -- what the reference does with a
         Python loop over the objects of a scene (optimizer_nuscenes.py:716-726; configs[1]: 16 objects per step).
         cam_poses (B,3,4); obj_szs B x (w,l,h); Ks (B,3,3) or one (3,3); rois B x (4,); shapecodes / texturecodes (B,D).
         -> rgb (B,N,3), depth (B,N), acc (B,N), rgb_tgt (B,N,3), occ_pixels (B,N,1).  Frozen weights, bf16 decoder (no CPU or
         per-object fallback)."""
         batch = self.make_batch(device, imgs, masks_occ, obj_szs, Ks, rois, im_sz)
-        rgb, dep, acc = self.render_batch(model, batch, cam_poses, shapecodes, texturecodes, jitter)
+        rgb, dep, acc = self.render_batch(model, batch, cam_poses, shapecodes, texturecodes, jitter, fused_sampler)
         return rgb, dep, acc, batch.rgb_tgt, batch.occ_pixels
 
     @staticmethod

@@ -386,12 +386,14 @@ def test_cta_group2_kernels_equal_cta_group1_kernels(B, n, S_):
     assert parity_ok("g1_2", g1[2], g0[2], 1e-5) and parity_ok("g1_3", g1[3], g0[3], 1e-5)      # latent gradients: atomically accumulated sums
 
 
-@pytest.mark.parametrize("n_obj,im,S_", [(3, 32, 64), (2, 16, 16), (5, 24, 128)])
-def test_batched_render_equals_per_object_render(n_obj, im, S_):
+@pytest.mark.parametrize("n_obj,im,S_,fused", [(3, 32, 64, False), (2, 16, 16, False), (5, 24, 128, False), (3, 32, 64, True), (2, 16, 16, True),
+                                               (5, 24, 128, True)])
+def test_batched_render_equals_per_object_render(n_obj, im, S_, fused):
     """NeRFRenderer.render_rays_batch + losses.refine_loss_batch (csrc/render_batch.cu: ONE launch set for all objects, compositing
     on the compact rows) against the per-object fused render of the same library: hit masks and hit-ray renders bit-identical (same
     per-row arithmetic), miss rays to 1e-6 (their single sample in closed form instead of S samples an ulp of z apart), gradients to
-    summation order -- and against the fp32 CPU oracle within the bf16 budget."""
+    summation order -- and against the fp32 CPU oracle within the bf16 budget.  fused = the north star's K1: the decoder's forward
+    computes every row's stratified sample from its ray (no sampler kernel, no coordinates in HBM on the forward path)."""
     S = snb()
     sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=61)
     m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
@@ -418,7 +420,7 @@ def test_batched_render_equals_per_object_render(n_obj, im, S_):
     texs = torch.cat([l[1] for l in lat]).to(DEV).requires_grad_()
     rgb, dep, acc, tgt, occ = R.render_rays_batch(m, DEV, [o["img"] for o in objs], [o["mask_occ"] for o in objs], cams,
                                                   [o["wlh"] for o in objs], torch.stack([o["K"] for o in objs]), [o["roi"] for o in objs],
-                                                  shps, texs, im_sz=im, jitter=jit.to(DEV))
+                                                  shps, texs, im_sz=im, jitter=jit.to(DEV), fused_sampler=fused)
     losses, parts = S.losses.refine_loss_batch(rgb, acc, tgt, occ, 0.1)
     losses.sum().backward()
     assert rgb.shape == (n_obj, n, 3) and dep.shape == (n_obj, n) and losses.shape == (n_obj,)
