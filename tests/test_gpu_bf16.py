@@ -492,3 +492,95 @@ def test_packed_weight_staleness_and_single_input_gradient():
     m2(xyz, vd, shp, tex)                           # second forward re-packs
     with pytest.raises(RuntimeError):
         (sig.sum() + rgbs.sum()).backward()
+
+
+def test_batched_render_full_c2_size_16_objects():
+    """configs[1] at FULL size through ONE launch set (16 objects x 128x128 rays x 64 samples = the bench's step): two of the objects
+    against their per-object renders (hit rays bit-identical, gradients to summation order), one against the fp32 CPU oracle on a
+    strided ray subsample (bf16 budget), every object's hit mask against the oracle's slab test, losses finite."""
+    S = snb()
+    B, im, S_ = 16, 128, 64
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=0)
+    m = model_from_state(S.AutoRFMix, sd, 3, 1, 256)
+    m.precision = "bf16"
+    m.requires_grad_(False)
+    R = S.renderer.NeRFRenderer(n_samples=S_)
+    objs = [oracle.synthetic_object(100 + i, im_sz=im) for i in range(B)]
+    lat = [oracle.synthetic_latents(100 + i, 1) for i in range(B)]
+    n = im * im
+    torch.manual_seed(5)
+    torch.cuda.manual_seed(5)
+    jit = torch.rand(B, n, S_, device=DEV)
+    cams = torch.stack([o["cam_pose"] for o in objs]).to(DEV).requires_grad_()
+    shps = torch.cat([l[0] for l in lat]).to(DEV).requires_grad_()
+    texs = torch.cat([l[1] for l in lat]).to(DEV).requires_grad_()
+    batch = R.make_batch(DEV, torch.stack([o["img"] for o in objs]), torch.stack([o["mask_occ"] for o in objs]), [o["wlh"] for o in objs],
+                         torch.stack([o["K"] for o in objs]), [o["roi"] for o in objs], im)
+    rgb, dep, acc = R.render_batch(m, batch, cams, shps, texs, jitter=jit)
+    # loss over a strided subsample of object 3's rays only (so that its gradients can be compared with the oracle's)
+    ids = torch.arange(0, n, n // 256)
+    sel = torch.zeros(B, n, 1, device=DEV)
+    sel[3, ids.to(DEV)] = 1.0
+    losses, parts = S.losses.refine_loss_batch(rgb, acc, batch.rgb_tgt, batch.occ_pixels * sel, 0.1)
+    losses[3].backward()
+    assert bool(torch.isfinite(parts).all())
+    o = objs[3]
+    cam_o = o["cam_pose"].clone().requires_grad_()
+    s_o, t_o = lat[3][0].clone().requires_grad_(), lat[3][1].clone().requires_grad_()
+    o_rgb, o_dep, o_acc, _ = oracle.render_rays_box(sd, o["K"], cam_o, o["wlh"], o["roi"], im, S_, s_o, t_o, jit[3][ids.to(DEV)].cpu(), ray_ids=ids)
+    oracle.refine_losses(o_rgb, o_acc, o["img"].reshape(-1, 3)[ids], o["mask_occ"].reshape(-1, 1)[ids])[0].backward()
+    parity("obj3_rgb_vs_oracle", rgb[3][ids.to(DEV)], o_rgb, TOL, rows=B * n * S_)
+    parity("obj3_depth_vs_oracle", dep[3][ids.to(DEV)], o_dep, TOL)
+    parity("obj3_g_pose_vs_oracle", cams.grad[3], cam_o.grad, TOL)
+    parity("obj3_g_shape_vs_oracle", shps.grad[3], s_o.grad[0], TOL)
+    parity("obj3_g_texture_vs_oracle", texs.grad[3], t_o.grad[0], TOL)
+    assert float(cams.grad[0].abs().max()) == 0.0 and float(shps.grad[7].abs().max()) == 0.0   # objects outside the loss: zero gradients
+    for i in (0, 9):   # per-object render of the same library on the same jitter
+        with forced_rand_like(jit[i]):
+            r1, d1, a1, _, _ = R.render_rays(m, DEV, objs[i]["img"], objs[i]["mask_occ"], objs[i]["cam_pose"].to(DEV), objs[i]["wlh"],
+                                             objs[i]["K"].to(DEV), objs[i]["roi"], lat[i][0].to(DEV), lat[i][1].to(DEV), im_sz=im)
+        ro, vd = oracle.get_rays(objs[i]["K"], objs[i]["cam_pose"], objs[i]["roi"], uv_steps=[im, im])
+        diag, half = oracle.box_constants(objs[i]["wlh"])
+        hb = torch.from_numpy(half)
+        _, _, hit = oracle.ray_box_intersection(ro / (diag / 2), vd, -hb.expand_as(ro), hb.expand_as(ro))
+        hit = hit.to(DEV)
+        assert torch.equal(rgb[i].detach()[hit], r1.detach()[hit]) and torch.equal(dep[i].detach()[hit], d1.detach()[hit])
+        parity("obj%d_miss_rays_rgb" % i, rgb[i].detach()[~hit], r1.detach()[~hit], 1e-6)
+        assert bool((acc[i].detach()[~hit] == 1.0).all())
+
+
+def test_tc_training_mode_c5_size_weight_grads_vs_fp32_oracle():
+    """bf16 TRAINING mode at config C5's real size (8 objects x 1024 rays x 64 samples = 524 288 rows through one decoder call +
+    volume_rendering_batch + the trainer's losses, trainer_unified_nuscenes.py:120-146): EVERY weight / bias gradient and the code
+    gradients against the fp32 CPU ORACLE (not the repo's own fp32 back end), bf16 budget."""
+    S = snb()
+    B, n, S_ = 8, 1024, 64
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=5)
+    g = torch.Generator().manual_seed(5)
+    xyz = (torch.rand(B, n, S_, 3, generator=g) - 0.5) * 1.2
+    vd = torch.nn.functional.normalize(torch.randn(B, n, 1, 3, generator=g), dim=-1).repeat(1, 1, S_, 1)
+    z = torch.rand(B, S_, generator=g).sort(-1).values * 4 + 8
+    tgt, occ = torch.rand(B, n, 3, generator=g), torch.randint(-1, 2, (B, n, 1), generator=g).float()
+    shp0, tex0 = oracle.synthetic_latents(5, B)
+
+    def losses_of(sig, rgbs, zv, tg, oc, comp):
+        rgb, dep, acc = comp(sig.reshape(B, n, S_, 1), rgbs.reshape(B, n, S_, 3), zv)
+        den = torch.sum(torch.abs(oc), dim=[-2, -1]) + 1e-9
+        l_rgb = (torch.sum((rgb - tg) ** 2 * torch.abs(oc), dim=[-2, -1]) / den).mean()
+        l_occ = (torch.sum(torch.exp(-oc * (0.5 - acc.unsqueeze(-1))) * torch.abs(oc), dim=[-2, -1]) / den).mean()
+        return l_rgb + 0.1 * l_occ
+    # fp32 CPU oracle
+    sdr = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    s_o, t_o = shp0.clone().requires_grad_(), tex0.clone().requires_grad_()
+    sig, rgbs = oracle.codenerf_decoder(sdr, xyz.reshape(-1, S_, 3), vd.reshape(-1, S_, 3), s_o, t_o)
+    losses_of(sig, rgbs, z, tgt, occ, lambda a, b, c: oracle.composite(a.squeeze(-1), b, c.unsqueeze(1).expand(B, n, S_), False)).backward()
+    # bf16 training mode on the GPU
+    m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
+    m.precision = "bf16"
+    s_g, t_g = shp0.to(DEV).requires_grad_(), tex0.to(DEV).requires_grad_()
+    sig2, rgbs2 = m(xyz.reshape(-1, S_, 3).to(DEV), vd.reshape(-1, S_, 3).to(DEV), s_g, t_g)
+    losses_of(sig2, rgbs2, z.to(DEV), tgt.to(DEV), occ.to(DEV), S.utils.volume_rendering_batch).backward()
+    parity("g_shapecode", s_g.grad, s_o.grad, TOL, rows=B * n * S_)
+    parity("g_texturecode", t_g.grad, t_o.grad, TOL)
+    for k, p_ in m.named_parameters():
+        parity("gw_" + k, p_.grad, sdr[k].grad, TOL)
