@@ -419,7 +419,10 @@ def run_ours(args):
             sup.precision = args.precision
             sup.requires_grad_(False)
 
-            def refiner_for(k, max_iters):
+            def refiner_uncaptured(k, max_iters):
+                return refiner_for(k, max_iters, capture=False)
+
+            def refiner_for(k, max_iters, capture=True):
                 o = make_objects(300 + k, 1, 32)[0]
                 c2o = o["cam_pose"]
                 r_obj = c2o[:, :3].t().contiguous().double()
@@ -429,9 +432,10 @@ def run_ours(args):
                 rot_vec = (w / (2 * torch.sin(ang).clamp_min(1e-12)) * ang).float()
                 rs = _np.random.RandomState(300 + k)   # 64 "lidar" pixels of the crop: their no-grad depth render is part of every iteration
                 lidar = (rs.randint(0, o["img"].shape[1], 64), rs.randint(0, o["img"].shape[0], 64))
-                return snb.refine.ObjectRefiner(sup, dev, o["img"].to(dev), o["mask_occ"].to(dev), o["K"], o["roi"],
-                                                _np.linalg.norm(o["wlh"]).astype(_np.float32), o["shapecode"], o["texturecode"], rot_vec,
-                                                t_obj, n_samples=N_SAMPLES, im_sz=32, max_iters=max_iters, lidar_xy=lidar).capture()
+                r_ = snb.refine.ObjectRefiner(sup, dev, o["img"].to(dev), o["mask_occ"].to(dev), o["K"], o["roi"],
+                                              _np.linalg.norm(o["wlh"]).astype(_np.float32), o["shapecode"], o["texturecode"], rot_vec,
+                                              t_obj, n_samples=N_SAMPLES, im_sz=32, max_iters=max_iters, lidar_xy=lidar)
+                return r_.capture() if capture else r_
 
             ref = refiner_for(0, 60)
             ref.run(5)
@@ -457,6 +461,17 @@ def run_ours(args):
             refine_it["four_objects_side_by_side"] = {
                 "ms_per_refine_iteration": round(a0.elapsed_time(a1) / (4 * 50), 4), "objects": 4, "iterations": 50, "cuda_streams": 4,
                 "note": "per object-iteration: elapsed / (4 objects x 50 iterations) (configs[2]: 4 objects per GPU), refine.run_objects"}
+            # ... and from ONE CUDA graph per iteration whose four branches the device schedules (refine.ObjectGroup)
+            grp = snb.refine.ObjectGroup([refiner_uncaptured(k, 60) for k in range(4)]).capture()
+            grp.run(5)
+            torch.cuda.synchronize()
+            a0.record()
+            grp.run(50)
+            a1.record()
+            torch.cuda.synchronize()
+            refine_it["four_objects_one_graph"] = {
+                "ms_per_refine_iteration": round(a0.elapsed_time(a1) / (4 * 50), 4), "objects": 4, "iterations": 50,
+                "note": "refine.ObjectGroup: the 4 objects' iterations forked / joined inside one captured graph, one graph launch per iteration"}
         except Exception as exc:
             refine_it = {"error": str(exc)}
     # the collective-bearing modes of the north star (configs[3], configs[4]): run at every N (N = 1 anchors the strong-scaling curve)

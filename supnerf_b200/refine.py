@@ -287,3 +287,62 @@ def run_objects(refiners, iters, n_streams=4):
     for s in streams:
         main.wait_stream(s)
     return [r.loss for r in refiners]
+
+
+class ObjectGroup:
+    """Several INDEPENDENT objects (config C3: a GPU's 4 of the 32 objects) refined side by side from ONE CUDA graph per iteration:
+    the capture forks the objects' iterations onto one stream each and joins them, so a replay is a single graph launch whose
+    branches the device schedules concurrently (one object's ~30 small kernels under another's decoder kernel) -- instead of one
+    graph launch per object per iteration issued round-robin from the host (run_objects)."""
+
+    def __init__(self, refiners):
+        if not refiners:
+            raise ValueError("ObjectGroup needs at least one refiner")
+        self.refiners = list(refiners)
+        self.device = self.refiners[0].device
+        self.graph = None
+
+    def capture(self, warmup=3):
+        dev = self.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):   # warm-up (allocator, weight packing, AdamW state), then undo it -- as ObjectRefiner.capture does
+            for r in self.refiners:
+                snapshot = [t.detach().clone() for t in (r.shapecode, r.texturecode, r.rot_vec, r.trans_vec)]
+                for _ in range(warmup):
+                    r.step()
+                with torch.no_grad():
+                    for t, v in zip((r.shapecode, r.texturecode, r.rot_vec, r.trans_vec), snapshot):
+                        t.copy_(v)
+                    if r.fused:
+                        r.opt.reset()
+                    else:
+                        for st in r.opt.state.values():
+                            for v in st.values():
+                                if torch.is_tensor(v):
+                                    v.zero_()
+                    r.it.zero_()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        streams = [torch.cuda.Stream(device=dev) for _ in self.refiners]
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            main = torch.cuda.current_stream(dev)
+            for s_, r in zip(streams, self.refiners):
+                s_.wait_stream(main)                 # fork
+                with torch.cuda.stream(s_):
+                    r.step()
+            for s_ in streams:
+                main.wait_stream(s_)                 # join
+        return self
+
+    def run(self, iters):
+        """`iters` iterations of every object.  -> the objects' last [loss, loss_rgb, loss_occ] tensors."""
+        if any(int(iters) > r.jitter.shape[0] for r in self.refiners):
+            raise ValueError("iters exceeds the pre-drawn jitter table (max_iters)")
+        for _ in range(int(iters)):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                for r in self.refiners:
+                    r.step()
+        return [r.loss for r in self.refiners]

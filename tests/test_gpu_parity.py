@@ -881,3 +881,33 @@ def test_scene_compositor_against_the_reference_vis_scene(prec):
     from conftest import parity
     parity("canvas_uint8", canvas.astype(np.float32), ref.astype(np.float32), 1e-2 if prec == "fp32" else 2e-2)
     assert frac >= 0.999, (frac, int(diff.max()))
+
+
+def test_object_group_one_graph_equals_sequential_refiners():
+    """refine.ObjectGroup (all objects' iterations forked / joined inside ONE captured CUDA graph) leaves every object in the state
+    its own sequential loop would."""
+    S = snb()
+    import tools.refine_bench as rb
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=52)
+    m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
+    m.requires_grad_(False)
+    iters = 5
+
+    def make(seed):
+        obj = oracle.synthetic_object(seed, im_sz=32)
+        shp0, tex0 = oracle.synthetic_latents(seed, 1)
+        c2o = obj["cam_pose"]
+        R_obj = c2o[:, :3].t().contiguous()
+        t_obj = -(R_obj @ c2o[:, 3:]).reshape(3)
+        torch.manual_seed(seed)
+        return S.refine.ObjectRefiner(m, DEV, obj["img"], obj["mask_occ"], obj["K"], obj["roi"], np.linalg.norm(obj["wlh"]).astype(np.float32),
+                                      shp0, tex0, rb.matrix_to_axis_angle(R_obj), t_obj, n_samples=64, im_sz=32, max_iters=iters)
+    seq = [make(70 + k).capture() for k in range(3)]
+    for r in seq:
+        r.run(iters)
+    grp = S.refine.ObjectGroup([make(70 + k) for k in range(3)]).capture()
+    grp.run(iters)
+    torch.cuda.synchronize()
+    for a, b in zip(seq, grp.refiners):
+        assert parity_ok("b_loss", b.loss, a.loss, 1e-4)
+        assert parity_ok("b_shapecode", b.shapecode, a.shapecode, 2e-2) and parity_ok("b_rot_vec", b.rot_vec, a.rot_vec, 1e-3)
