@@ -314,6 +314,42 @@ int snb_adamw_step(int32_t n_groups, float* const* params, const float* const* g
                    float* const* exp_avg_sq, const int32_t* sizes, const float* lrs, float beta1, float beta2, float eps,
                    float weight_decay, float* step, void* stream);
 
+/* ---- the same glue for B objects side by side (one GPU's share of config C3: 32 objects over 8 GPUs) ----------------
+ * snb_refine_pose_batch_fwd/bwd: rot_vec, trans_vec (B,3) -> cam (B,3,4) and, if z != NULL, every object's shared sample
+ * vector z (B,S) from obj_diag (B, device).  jitter: (B,S), or -- step_counter != NULL -- a table (B, table_rows, S) whose row
+ * int(*step_counter) is used (the AdamW step counter of snb_adamw_step: a captured iteration then needs neither an
+ * index_select nor a counter launch).  z2 / jitter2: a second sample vector from the same pose and another draw (the
+ * lidar-pixel evaluation of optimizer_nuscenes.py:759-769); both NULL = not wanted.
+ * snb_render_shell_batch_fwd/bwd: utils.render_rays_v2 (utils.py:435-502) for B objects in one launch set: px, py (B,N); K
+ * (B,3,3); c2w (B,3,4); z (B,S); obj_diag (B); latents (B,D) -> rgb (B,N,3), depth, acc (B,N).  Frozen weights; bf16 needs
+ * N * S to be a multiple of 128.  Backward: g_rgb (B,N,3), g_depth, g_acc (B,N) -> g_c2w (B,3,4; NULL = not wanted),
+ * g_shape_latent, g_texture_latent (B,D).  Workspace / scratch: 256-byte aligned, sizes from the *_bytes calls. */
+typedef struct snb_shell_batch_desc {
+  int32_t n_objs;
+  int32_t n_samples;
+  int64_t rays_per_obj;
+  int32_t precision;     /* SNB_PREC_FP32 | SNB_PREC_BF16 */
+  int32_t flags;         /* SNB_SIGMA_RELU [| SNB_WHITE_BKGD] */
+  int32_t shapenet_swap;
+  int32_t reserved;
+} snb_shell_batch_desc;
+int snb_refine_pose_batch_fwd(const float* rot_vec, const float* trans_vec, int32_t n_objs, int32_t opt_cam_pose,
+                              const float* obj_diag, int32_t n_samples, const float* jitter, const float* jitter2,
+                              const float* step_counter, int32_t table_rows, float* cam, float* z, float* z2, void* stream);
+int snb_refine_pose_batch_bwd(const float* rot_vec, const float* trans_vec, int32_t n_objs, int32_t opt_cam_pose,
+                              const float* g_cam, float* g_rot, float* g_trans, void* stream);
+size_t snb_render_shell_batch_workspace_bytes(snb_handle h, const snb_shell_batch_desc* d);
+size_t snb_render_shell_batch_scratch_bytes(snb_handle h, const snb_shell_batch_desc* d);
+int snb_render_shell_batch_fwd(snb_handle h, const snb_shell_batch_desc* d, const float* px, const float* py, const float* K,
+                               const float* c2w, const float* z, const float* obj_diag, const float* shape_latent,
+                               const float* texture_latent, float* out_rgb, float* out_depth, float* out_acc, void* workspace,
+                               void* stream);
+int snb_render_shell_batch_bwd(snb_handle h, const snb_shell_batch_desc* d, const float* px, const float* py, const float* K,
+                               const float* c2w, const float* z, const float* obj_diag, const float* shape_latent,
+                               const float* texture_latent, const void* workspace, const float* g_rgb, const float* g_depth,
+                               const float* g_acc, void* scratch, float* g_c2w, float* g_shape_latent, float* g_texture_latent,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

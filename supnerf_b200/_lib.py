@@ -27,6 +27,11 @@ class SnbBatchDesc(ctypes.Structure):
     _fields_ = [("n_objs", c_i32), ("n_samples", c_i32), ("rays_per_obj", c_i64), ("flags", c_i32), ("reserved", c_i32)]
 
 
+class SnbShellBatchDesc(ctypes.Structure):
+    _fields_ = [("n_objs", c_i32), ("n_samples", c_i32), ("rays_per_obj", c_i64), ("precision", c_i32), ("flags", c_i32),
+                ("shapenet_swap", c_i32), ("reserved", c_i32)]
+
+
 # name -> (restype, argtypes); mirrors include/supnerf_b200.h one to one
 SIGNATURES = {
     "snb_abi_version": (c_i32, []),
@@ -85,6 +90,12 @@ SIGNATURES = {
     "snb_refine_loss_batch_scratch_bytes": (c_sz, [c_i32]),
     "snb_refine_loss_batch_fwd": (c_i32, [c_f, c_f, c_f, c_f, c_i32, c_i64, c_flt, c_f, c_f, c_f]),
     "snb_refine_loss_batch_bwd": (c_i32, [c_f, c_f, c_f, c_f, c_i32, c_i64, c_flt, c_f, c_f, c_f, c_f, c_f]),
+    "snb_refine_pose_batch_fwd": (c_i32, [c_f, c_f, c_i32, c_i32, c_f, c_i32, c_f, c_f, c_f, c_i32, c_f, c_f, c_f, c_f]),
+    "snb_refine_pose_batch_bwd": (c_i32, [c_f, c_f, c_i32, c_i32, c_f, c_f, c_f, c_f]),
+    "snb_render_shell_batch_workspace_bytes": (c_sz, [ctypes.c_void_p, ctypes.POINTER(SnbShellBatchDesc)]),
+    "snb_render_shell_batch_scratch_bytes": (c_sz, [ctypes.c_void_p, ctypes.POINTER(SnbShellBatchDesc)]),
+    "snb_render_shell_batch_fwd": (c_i32, [ctypes.c_void_p, ctypes.POINTER(SnbShellBatchDesc)] + [c_f] * 13),
+    "snb_render_shell_batch_bwd": (c_i32, [ctypes.c_void_p, ctypes.POINTER(SnbShellBatchDesc)] + [c_f] * 17),
 }
 
 _lib = None

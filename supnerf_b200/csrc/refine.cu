@@ -46,10 +46,18 @@ __device__ __forceinline__ void rodrigues(const double v[3], const Rod& r, doubl
   for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0 ? 1.0 : 0.0) + r.a * K[i] + r.b * K2[i];
 }
 
+// One block per object.  obj_diag: a host scalar (obj_diag_dev null) or one value per object on the device.  The sample-vector jitter is
+// either the vector itself (it == nullptr: jitter (B,S)) or row int(*it) of a per-object table (B, T, S) -- `it` being the optimiser's
+// device-side step counter, so a captured iteration needs neither an index_select nor a counter-increment launch.  z2 / jitter2: a second
+// sample vector from the same pose and another draw (the per-iteration lidar-pixel evaluation, optimizer_nuscenes.py:759-769).
 __global__ void __launch_bounds__(1024) refine_pose_fwd_kernel(const float* __restrict__ rot_vec, const float* __restrict__ trans_vec,
-                                                              int opt_cam_pose, float obj_diag, int S, const float* __restrict__ jitter,
-                                                              float* __restrict__ cam, float* __restrict__ z) {
+                                                              int opt_cam_pose, float obj_diag_host, const float* __restrict__ obj_diag_dev,
+                                                              int S, const float* __restrict__ jitter, const float* __restrict__ jitter2,
+                                                              const float* __restrict__ it, int T, float* __restrict__ cam,
+                                                              float* __restrict__ z, float* __restrict__ z2) {
   __shared__ double tn;
+  const int b = blockIdx.x;
+  rot_vec += 3 * b; trans_vec += 3 * b; cam += 12 * b;
   if (threadIdx.x == 0) {
     const double v[3] = {rot_vec[0], rot_vec[1], rot_vec[2]}, t[3] = {trans_vec[0], trans_vec[1], trans_vec[2]};
     double R[9];
@@ -69,20 +77,24 @@ __global__ void __launch_bounds__(1024) refine_pose_fwd_kernel(const float* __re
   __syncthreads();
   if (z != nullptr) {
     // utils.py:468-469 + :154-167: near/far python floats (double), torch.linspace's fp32 formula, jitter scaled by (far-near)/(2S)
+    const float obj_diag = obj_diag_dev ? obj_diag_dev[b] : obj_diag_host;
     const double half = (double)obj_diag / 2.0, near = tn - half, far = tn + half, dist = (far - near) / (2.0 * S);
     const float start = (float)(near + dist), end = (float)(far - dist);
     const float step = S > 1 ? (end - start) / (float)(S - 1) : 0.f;
     const float scale = (float)((far - near) / (2.0 * S));
+    const int64_t row = it ? ((int64_t)b * T + (int64_t)(*it)) : (int64_t)b;
     for (int i = threadIdx.x; i < S; i += blockDim.x) {
       const float lin = i < S / 2 ? __fadd_rn(start, __fmul_rn(step, (float)i)) : __fsub_rn(end, __fmul_rn(step, (float)(S - 1 - i)));
-      z[i] = __fadd_rn(lin, __fmul_rn(jitter[i], scale));
+      z[(int64_t)b * S + i] = __fadd_rn(lin, __fmul_rn(jitter[row * S + i], scale));
+      if (z2 != nullptr) z2[(int64_t)b * S + i] = __fadd_rn(lin, __fmul_rn(jitter2[row * S + i], scale));
     }
   }
 }
 
 __global__ void refine_pose_bwd_kernel(const float* __restrict__ rot_vec, const float* __restrict__ trans_vec, int opt_cam_pose,
                                        const float* __restrict__ g_cam, float* __restrict__ g_rot, float* __restrict__ g_trans) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (threadIdx.x != 0) return;
+  rot_vec += 3 * blockIdx.x; trans_vec += 3 * blockIdx.x; g_cam += 12 * blockIdx.x; g_rot += 3 * blockIdx.x; g_trans += 3 * blockIdx.x;   // one block per object
   const double v[3] = {rot_vec[0], rot_vec[1], rot_vec[2]}, t[3] = {trans_vec[0], trans_vec[1], trans_vec[2]};
   const Rod r = rod_coeffs(v);
   double R[9], K[9], K2[9];
@@ -159,7 +171,33 @@ extern "C" int snb_refine_pose_fwd(const float* rot_vec, const float* trans_vec,
   SNB_REQUIRE(z == nullptr || (jitter != nullptr && n_samples >= 1), "refine_pose_fwd: the sample vector needs jitter and n_samples >= 1");
   SNB_REQUIRE(sm_count() > 0, "refine_pose_fwd: no CUDA device (there is no CPU fallback)");
   const int threads = z ? ((n_samples + 31) / 32 * 32 < 1024 ? (n_samples + 31) / 32 * 32 : 1024) : 32;
-  refine_pose_fwd_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(rot_vec, trans_vec, opt_cam_pose, obj_diag, n_samples, jitter, cam, z);
+  refine_pose_fwd_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(rot_vec, trans_vec, opt_cam_pose, obj_diag, nullptr, n_samples, jitter, nullptr,
+                                                                  nullptr, 0, cam, z, nullptr);
+  SNB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int snb_refine_pose_batch_fwd(const float* rot_vec, const float* trans_vec, int32_t n_objs, int32_t opt_cam_pose,
+                                         const float* obj_diag, int32_t n_samples, const float* jitter, const float* jitter2,
+                                         const float* step_counter, int32_t table_rows, float* cam, float* z, float* z2, void* stream) {
+  SNB_REQUIRE(n_objs >= 1 && rot_vec && trans_vec && cam, "refine_pose_batch_fwd: bad arguments");
+  SNB_REQUIRE(z == nullptr || (jitter != nullptr && obj_diag != nullptr && n_samples >= 1),
+              "refine_pose_batch_fwd: the sample vectors need jitter, obj_diag and n_samples >= 1");
+  SNB_REQUIRE(z2 == nullptr || (z != nullptr && jitter2 != nullptr), "refine_pose_batch_fwd: z2 needs z and jitter2");
+  SNB_REQUIRE(step_counter == nullptr || table_rows >= 1, "refine_pose_batch_fwd: a jitter table needs its row count");
+  SNB_REQUIRE(sm_count() > 0, "refine_pose_batch_fwd: no CUDA device (there is no CPU fallback)");
+  const int threads = z ? ((n_samples + 31) / 32 * 32 < 1024 ? (n_samples + 31) / 32 * 32 : 1024) : 32;
+  refine_pose_fwd_kernel<<<n_objs, threads, 0, (cudaStream_t)stream>>>(rot_vec, trans_vec, opt_cam_pose, 0.f, obj_diag, n_samples, jitter, jitter2,
+                                                                       step_counter, table_rows, cam, z, z2);
+  SNB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int snb_refine_pose_batch_bwd(const float* rot_vec, const float* trans_vec, int32_t n_objs, int32_t opt_cam_pose,
+                                         const float* g_cam, float* g_rot, float* g_trans, void* stream) {
+  SNB_REQUIRE(n_objs >= 1 && rot_vec && trans_vec && g_cam && g_rot && g_trans, "refine_pose_batch_bwd: bad arguments");
+  SNB_REQUIRE(sm_count() > 0, "refine_pose_batch_bwd: no CUDA device (there is no CPU fallback)");
+  refine_pose_bwd_kernel<<<n_objs, 32, 0, (cudaStream_t)stream>>>(rot_vec, trans_vec, opt_cam_pose, g_cam, g_rot, g_trans);
   SNB_LAUNCH_CHECK();
   return 0;
 }

@@ -562,6 +562,86 @@ __global__ void __launch_bounds__(256) rb_shell_prep_kernel(const float* __restr
   }
 }
 
+// Backward of rb_shell_prep_kernel through to the poses: per ray the fold of sample_shell_bwd_kernel (g_o = sum g_xyz / diag,
+// g_d = sum z g_xyz / diag + sum g_viewdir, axis swap undone) and get_rays_bwd_kernel's g_r = (g_d - d (g_d . d)) / |r| (sampler.cu),
+// then per-object fp64 block sums -> g_c2w (B,3,4), finished by the object's last block.  One warp per ray, lanes over samples; grid (x, B).
+__global__ void __launch_bounds__(256) rb_shell_rays_bwd_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                                               const float* __restrict__ K, const float* __restrict__ c2w,
+                                                               const float* __restrict__ z, const float* __restrict__ obj_diag,
+                                                               int64_t N, int S, int swap, const float* __restrict__ g_xyz,
+                                                               const float* __restrict__ g_vrep, double* __restrict__ acc64,
+                                                               unsigned int* __restrict__ tickets, float* __restrict__ g_c2w) {
+  const int b = blockIdx.y;
+  const float* Kb = K + 9 * b;
+  const float* P = c2w + 12 * b;
+  const float cx = __ldg(Kb + 2), cy = __ldg(Kb + 5), fx = __ldg(Kb), fy = __ldg(Kb + 4);
+  const float diag = __ldg(obj_diag + b);
+  const float* zb = z + (int64_t)b * S;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double acc[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) acc[i] = 0.0;
+  for (int64_t ray = (int64_t)blockIdx.x * 8 + wib; ray < N; ray += (int64_t)gridDim.x * 8) {
+    const int64_t gi = (int64_t)b * N + ray;
+    float go[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f};
+    for (int k = lane; k < S; k += 32) {
+      const int64_t idx = gi * S + k;
+      const float zk = __ldg(zb + k);
+      float gx[3] = {__ldg(g_xyz + 3 * idx), __ldg(g_xyz + 3 * idx + 1), __ldg(g_xyz + 3 * idx + 2)};
+      float gv[3] = {__ldg(g_vrep + 3 * idx), __ldg(g_vrep + 3 * idx + 1), __ldg(g_vrep + 3 * idx + 2)};
+      if (swap) {  // out = (-in_y, in_x, in_z)
+        float t0 = gx[1], t1 = -gx[0]; gx[0] = t0; gx[1] = t1;
+        t0 = gv[1]; t1 = -gv[0]; gv[0] = t0; gv[1] = t1;
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float g = gx[a] / diag;
+        go[a] += g; gd[a] += g * zk + gv[a];
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { go[a] = warp_sum(go[a]); gd[a] = warp_sum(gd[a]); }
+    if (lane == 0) {
+      const float pp[3] = {(__ldg(px + gi) - cx) / fx, (__ldg(py + gi) - cy) / fy, 1.f};
+      float r[3], dd[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) r[a] = pp[0] * __ldg(P + 4 * a) + pp[1] * __ldg(P + 4 * a + 1) + pp[2] * __ldg(P + 4 * a + 2);
+      const float inv = 1.f / sqrtf(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) dd[a] = r[a] * inv;
+      const float dot = gd[0] * dd[0] + gd[1] * dd[1] + gd[2] * dd[2];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float gr = (gd[a] - dd[a] * dot) * inv;
+        acc[4 * a + 0] += (double)(gr * pp[0]);
+        acc[4 * a + 1] += (double)(gr * pp[1]);
+        acc[4 * a + 2] += (double)(gr * pp[2]);
+        acc[4 * a + 3] += (double)go[a];
+      }
+    }
+  }
+  __shared__ double red[8][12];
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) red[wib][i] = acc[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    double v = 0.0;
+    for (int k = 0; k < 8; ++k) v += red[k][threadIdx.x];
+    atomicAdd(acc64 + 12 * b + threadIdx.x, v);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(tickets + b, 1u);
+    if (t == gridDim.x - 1) {
+      __threadfence();
+      for (int i = 0; i < 12; ++i) g_c2w[12 * b + i] = (float)atomicAdd(acc64 + 12 * b + i, 0.0);
+    }
+  }
+}
+
 // --------------------------------------------------------------------------------------------------------------- batched losses
 // optimizer_nuscenes.py:729-736 per object (see loss.cu): grid (chunks, B)
 struct LossAccB { double num_rgb, num_occ, den; unsigned int ticket, pad; double den_final; };
@@ -907,6 +987,116 @@ extern "C" int snb_prepare_samples_batch(const float* px, const float* py, const
   if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
   rb::rb_shell_prep_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(px, py, K, c2w, z, obj_diag, flip, rays_per_obj, n_samples,
                                                                            shapenet_swap, total, xyz, viewdir_rep);
+  SNB_LAUNCH_CHECK();
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------------------- batched shell render
+// The utils.py stack (utils.render_rays_v2, utils.py:435-502: shared sample vector per object, xyz / obj_diag, optional shapenet axis
+// swap, volume_rendering2) for B objects in ONE launch set -- what render.cu's shell mode enqueues per object.  Dense rows (no slab test
+// in this stack): B * N * S decoder rows, N * S a multiple of 128 in bf16 mode.
+namespace snb {
+namespace {
+struct ShellLayout {   // forward workspace, kept for the backward
+  size_t xyz, vrep, sigma, rgb, mlp, total;
+  ShellLayout(snb_handle h, const snb_shell_batch_desc& d) {
+    const size_t M = (size_t)d.n_objs * (size_t)d.rays_per_obj * (size_t)d.n_samples;
+    size_t o = 0;
+    xyz = o; o += al(M * 12);
+    vrep = o; o += al(M * 12);
+    sigma = o; o += al(M * 4);
+    rgb = o; o += al(M * 12);
+    mlp = o; o += al(snb_mlp_workspace_bytes(h, (int64_t)M, d.n_objs, d.precision));
+    total = o;
+  }
+};
+struct ShellScratch {
+  size_t g_sigma, g_rgbs, g_xyz, g_vrep, acc64, tickets, mlp, total;
+  ShellScratch(snb_handle h, const snb_shell_batch_desc& d) {
+    const size_t B = (size_t)d.n_objs, M = B * (size_t)d.rays_per_obj * (size_t)d.n_samples;
+    size_t o = 0;
+    g_sigma = o; o += al(M * 4);
+    g_rgbs = o; o += al(M * 12);
+    g_xyz = o; o += al(M * 12);
+    g_vrep = o; o += al(M * 12);
+    acc64 = o; o += al(B * 12 * 8);
+    tickets = o; o += al(B * 4);
+    mlp = o; o += al(snb_mlp_bwd_scratch_bytes(h, (int64_t)M, d.n_objs, d.precision));
+    total = o;
+  }
+};
+int check_shell(snb_handle h, const snb_shell_batch_desc* d, const char* who) {
+  SNB_REQUIRE(h != nullptr && d != nullptr, "%s: null handle or descriptor", who);
+  SNB_REQUIRE(d->n_objs >= 1 && d->n_objs <= rb::kMaxObjs && d->rays_per_obj >= 1 && d->n_samples >= 1, "%s: bad sizes", who);
+  SNB_REQUIRE(d->precision == SNB_PREC_FP32 || d->precision == SNB_PREC_BF16, "%s: precision must be fp32 or bf16 (frozen weights)", who);
+  SNB_REQUIRE((int64_t)d->n_objs * d->rays_per_obj * d->n_samples < ((int64_t)1 << 40), "%s: too many rows", who);
+  return 0;
+}
+}  // namespace
+}  // namespace snb
+
+extern "C" size_t snb_render_shell_batch_workspace_bytes(snb_handle h, const snb_shell_batch_desc* d) {
+  if (!h || !d || d->n_objs < 1 || d->rays_per_obj < 1 || d->n_samples < 1) return 0;
+  return ShellLayout(h, *d).total + 256;
+}
+
+extern "C" size_t snb_render_shell_batch_scratch_bytes(snb_handle h, const snb_shell_batch_desc* d) {
+  if (!h || !d || d->n_objs < 1 || d->rays_per_obj < 1 || d->n_samples < 1) return 0;
+  return ShellScratch(h, *d).total + 256;
+}
+
+extern "C" int snb_render_shell_batch_fwd(snb_handle h, const snb_shell_batch_desc* d, const float* px, const float* py, const float* K,
+                                          const float* c2w, const float* z, const float* obj_diag, const float* shape_latent,
+                                          const float* texture_latent, float* out_rgb, float* out_depth, float* out_acc, void* workspace,
+                                          void* stream) {
+  if (check_shell(h, d, "render_shell_batch_fwd")) return 2;
+  SNB_REQUIRE(px && py && K && c2w && z && obj_diag && shape_latent && texture_latent && out_rgb && out_depth && out_acc && workspace,
+              "render_shell_batch_fwd: null pointer");
+  SNB_REQUIRE(((uintptr_t)workspace & 255) == 0, "render_shell_batch_fwd: workspace must be 256-byte aligned");
+  const ShellLayout L(h, *d);
+  void* ws = workspace;
+  const int64_t N = d->rays_per_obj, BN = (int64_t)d->n_objs * N, M = BN * d->n_samples;
+  if (snb_prepare_samples_batch(px, py, K, c2w, z, obj_diag, nullptr, d->n_objs, N, d->n_samples, d->shapenet_swap, at<float>(ws, L.xyz),
+                                at<float>(ws, L.vrep), stream)) return 1;
+  if (snb_mlp_fwd(h, d->precision, at<float>(ws, L.xyz), at<float>(ws, L.vrep), M, d->n_objs, shape_latent, texture_latent,
+                  at<float>(ws, L.sigma), at<float>(ws, L.rgb), at<uint8_t>(ws, L.mlp), stream)) return 1;
+  return snb_composite_fwd(at<float>(ws, L.sigma), at<float>(ws, L.rgb), z, N, BN, d->n_samples, d->flags, out_rgb, out_depth, out_acc, stream);
+}
+
+extern "C" int snb_render_shell_batch_bwd(snb_handle h, const snb_shell_batch_desc* d, const float* px, const float* py, const float* K,
+                                          const float* c2w, const float* z, const float* obj_diag, const float* shape_latent,
+                                          const float* texture_latent, const void* workspace, const float* g_rgb, const float* g_depth,
+                                          const float* g_acc, void* scratch, float* g_c2w, float* g_shape_latent, float* g_texture_latent,
+                                          void* stream) {
+  if (check_shell(h, d, "render_shell_batch_bwd")) return 2;
+  SNB_REQUIRE(px && py && K && c2w && z && obj_diag && shape_latent && texture_latent && workspace && g_rgb && g_depth && g_acc && scratch &&
+              g_shape_latent && g_texture_latent, "render_shell_batch_bwd: null pointer");
+  SNB_REQUIRE((((uintptr_t)workspace | (uintptr_t)scratch) & 255) == 0, "render_shell_batch_bwd: workspace/scratch must be 256-byte aligned");
+  const ShellLayout L(h, *d);
+  const ShellScratch G(h, *d);
+  cudaStream_t st = (cudaStream_t)stream;
+  const void* ws = workspace;
+  void* sc = scratch;
+  const int B = d->n_objs;
+  const int64_t N = d->rays_per_obj, BN = (int64_t)B * N, M = BN * d->n_samples;
+  const bool pose = g_c2w != nullptr;
+  // the shared sample vectors are built from detached python floats (utils.py:468-469): no gradient through z
+  if (snb_composite_bwd(at<float>(ws, L.sigma), at<float>(ws, L.rgb), z, N, BN, d->n_samples, d->flags, g_rgb, g_depth, g_acc,
+                        at<float>(sc, G.g_sigma), at<float>(sc, G.g_rgbs), nullptr, stream)) return 1;
+  if (snb_mlp_bwd(h, d->precision, at<float>(ws, L.xyz), at<float>(ws, L.vrep), M, B, shape_latent, texture_latent, at<float>(ws, L.sigma),
+                  at<float>(sc, G.g_sigma), at<float>(sc, G.g_rgbs), at<uint8_t>(ws, L.mlp), at<uint8_t>(sc, G.mlp),
+                  pose ? at<float>(sc, G.g_xyz) : nullptr, pose ? at<float>(sc, G.g_vrep) : nullptr, g_shape_latent, g_texture_latent, nullptr,
+                  stream)) return 1;
+  if (!pose) return 0;
+  const int sms = sm_count();
+  SNB_REQUIRE(sms > 0, "render_shell_batch_bwd: no CUDA device (there is no CPU fallback)");
+  SNB_CHECK_CUDA(cudaMemsetAsync(at<uint8_t>(sc, G.acc64), 0, G.mlp - G.acc64, st));   // fp64 sums + tickets
+  int gx = (int)ceil_div(N, 8);
+  const int cap = (sms * 8 + B - 1) / B;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  rb::rb_shell_rays_bwd_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, st>>>(px, py, K, c2w, z, obj_diag, N, d->n_samples, d->shapenet_swap,
+      at<float>(sc, G.g_xyz), at<float>(sc, G.g_vrep), at<double>(sc, G.acc64), at<unsigned int>(sc, G.tickets), g_c2w);
   SNB_LAUNCH_CHECK();
   return 0;
 }

@@ -644,6 +644,76 @@ def render_box_batch(handle, n_samples, white_bkgd, px, py, K, c2w, box, z_steps
     return _RenderBoxBatch.apply(handle, n_samples, flags, px, py, K, c2w, box, z_steps, jitter, shape_latent, texture_latent)
 
 
+class _RenderShellBatch(torch.autograd.Function):
+    """utils.render_rays_v2's stack (utils.py:435-502) for B objects: two C-ABI calls (snb_render_shell_batch_fwd / bwd), ~5 launches
+    forward and ~7 backward whatever B is.  Frozen weights.  Differentiable to the poses (B,3,4) and the latents (B,D)."""
+
+    @staticmethod
+    def forward(ctx, handle, precision, n_samples, swap, px, py, K, c2w, z, obj_diag, shape_latent, texture_latent):
+        lib = _lib.load()
+        require_cuda(px, py, K, c2w, z, obj_diag, shape_latent, texture_latent)
+        px, py, K, c2w, z, obj_diag = f32c(px), f32c(py), f32c(K), f32c(c2w), f32c(z), f32c(obj_diag)
+        shape_latent, texture_latent = f32c(shape_latent), f32c(texture_latent)
+        b, n = px.shape
+        dev = px.device
+        desc = _lib.SnbShellBatchDesc(int(b), int(n_samples), int(n), int(precision), SIGMA_RELU, int(bool(swap)), 0)
+        key = ("shell_batch", b, n, int(n_samples), int(precision))
+        cache = handle.__dict__.setdefault("_render_sizes", {})
+        sizes = cache.get(key)
+        if sizes is None:
+            sizes = (lib.snb_render_shell_batch_workspace_bytes(handle.h, ctypes.byref(desc)),
+                     lib.snb_render_shell_batch_scratch_bytes(handle.h, ctypes.byref(desc)))
+            cache[key] = sizes
+        ws = torch.empty(sizes[0], dtype=torch.uint8, device=dev)
+        o_rgb = torch.empty(b, n, 3, device=dev, dtype=torch.float32)
+        o_dep = torch.empty(b, n, device=dev, dtype=torch.float32)
+        o_acc = torch.empty(b, n, device=dev, dtype=torch.float32)
+        with on_device(dev):
+            check(lib.snb_render_shell_batch_fwd(handle.h, ctypes.byref(desc), ptr(px), ptr(py), ptr(K), ptr(c2w), ptr(z), ptr(obj_diag),
+                                                 ptr(shape_latent), ptr(texture_latent), ptr(o_rgb), ptr(o_dep), ptr(o_acc), ptr(ws),
+                                                 stream_ptr()), "snb_render_shell_batch_fwd")
+        ctx.save_for_backward(px, py, K, c2w, z, obj_diag, shape_latent, texture_latent, ws)
+        ctx.meta = (handle, desc, sizes[1], handle._frozen)
+        ctx.set_materialize_grads(False)
+        return o_rgb, o_dep, o_acc
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_dep, g_acc):
+        lib = _lib.load()
+        px, py, K, c2w, z, obj_diag, shape_latent, texture_latent, ws = ctx.saved_tensors
+        handle, desc, scratch_bytes, frozen = ctx.meta
+        dev = px.device
+        b, n = px.shape
+        g_rgb = f32c(g_rgb) if g_rgb is not None else _zeros_like_cached(dev, 3 * b * n)
+        g_dep = f32c(g_dep) if g_dep is not None else _zeros_like_cached(dev, b * n)
+        g_acc = f32c(g_acc) if g_acc is not None else _zeros_like_cached(dev, b * n)
+        need = ctx.needs_input_grad
+        g_c2w = torch.empty(b, 3, 4, device=dev, dtype=torch.float32) if need[7] else None
+        g_sl = torch.empty_like(shape_latent)
+        g_tl = torch.empty_like(texture_latent)
+        if frozen is not handle._frozen:
+            handle.use_frozen(frozen, desc.precision)
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
+        with on_device(dev):
+            check(lib.snb_render_shell_batch_bwd(handle.h, ctypes.byref(desc), ptr(px), ptr(py), ptr(K), ptr(c2w), ptr(z), ptr(obj_diag),
+                                                 ptr(shape_latent), ptr(texture_latent), ptr(ws), ptr(g_rgb), ptr(g_dep), ptr(g_acc),
+                                                 ptr(scratch), ptr(g_c2w), ptr(g_sl), ptr(g_tl), stream_ptr()), "snb_render_shell_batch_bwd")
+        return (None,) * 7 + (g_c2w, None, None, g_sl if need[10] else None, g_tl if need[11] else None)
+
+
+def render_shell_batch(handle, precision, n_samples, shapenet_swap, px, py, K, c2w, z_vals, obj_diag, shape_latent, texture_latent, weights):
+    """utils.render_rays_v2 (utils.py:435-502) for B objects through ONE launch set.  px, py (B,N); K (B,3,3); c2w (B,3,4); z_vals (B,S)
+    every object's shared sample vector; obj_diag (B) on the device; latents (B,D).  -> rgb (B,N,3), depth (B,N), acc (B,N).
+    Frozen weights only (the refine loops); the bf16 decoder needs N * S to be a multiple of 128."""
+    for w in weights:
+        if w.requires_grad:
+            raise RuntimeError("render_shell_batch: the batched render is the frozen-weight (refine) path; "
+                               "model.requires_grad_(False), or render the objects one by one")
+    prec = PREC[precision] if isinstance(precision, str) else precision
+    handle.use_frozen(weights, prec)
+    return _RenderShellBatch.apply(handle, prec, n_samples, shapenet_swap, px, py, K, c2w, z_vals, obj_diag, shape_latent, texture_latent)
+
+
 def box_constants(obj_sz):
     """renderer.py:92-100: diag and the AABB half extents (l,w,h)/diag, rounded to float32 on the host."""
     obj_sz = np.asarray(obj_sz)

@@ -346,3 +346,187 @@ class ObjectGroup:
                 for r in self.refiners:
                     r.step()
         return [r.loss for r in self.refiners]
+
+
+class _PoseAndSamplesBatch(torch.autograd.Function):
+    """(B,3) rot_vec, trans_vec -> cam2opt (B,3,4) + every object's shared sample vector z (B,S) [+ a second one, z2, from another jitter
+    table] in ONE launch (csrc/refine.cu: snb_refine_pose_batch_fwd); the jitter row is picked on the device by the optimiser's step counter."""
+
+    @staticmethod
+    def forward(ctx, rot_vec, trans_vec, jitter, jitter2, step_t, obj_diag, opt_cam_pose, n_samples):
+        lib = _lib.load()
+        require_cuda(rot_vec, trans_vec, jitter, step_t, obj_diag)
+        rot_vec, trans_vec = f32c(rot_vec), f32c(trans_vec)
+        b, t, s = jitter.shape
+        dev = rot_vec.device
+        cam = torch.empty(b, 3, 4, device=dev, dtype=torch.float32)
+        z = torch.empty(b, s, device=dev, dtype=torch.float32)
+        z2 = torch.empty(b, s, device=dev, dtype=torch.float32) if jitter2 is not None else None
+        with on_device(dev):
+            check(lib.snb_refine_pose_batch_fwd(ptr(rot_vec), ptr(trans_vec), int(b), int(bool(opt_cam_pose)), ptr(obj_diag), int(n_samples),
+                                                ptr(jitter), ptr(jitter2), ptr(step_t), int(t), ptr(cam), ptr(z), ptr(z2), stream_ptr()),
+                  "snb_refine_pose_batch_fwd")
+        ctx.save_for_backward(rot_vec, trans_vec)
+        ctx.opt_cam_pose = int(bool(opt_cam_pose))
+        ctx.set_materialize_grads(False)
+        if z2 is None:
+            ctx.mark_non_differentiable(z)
+            return cam, z
+        ctx.mark_non_differentiable(z, z2)
+        return cam, z, z2
+
+    @staticmethod
+    def backward(ctx, g_cam, *_):
+        lib = _lib.load()
+        rot_vec, trans_vec = ctx.saved_tensors
+        if g_cam is None:
+            return (None,) * 8
+        g_cam = f32c(g_cam)
+        g_rot, g_trans = torch.empty_like(rot_vec), torch.empty_like(trans_vec)
+        with on_device(rot_vec.device):
+            check(lib.snb_refine_pose_batch_bwd(ptr(rot_vec), ptr(trans_vec), int(rot_vec.shape[0]), ctx.opt_cam_pose, ptr(g_cam), ptr(g_rot),
+                                                ptr(g_trans), stream_ptr()), "snb_refine_pose_batch_bwd")
+        return (g_rot, g_trans) + (None,) * 6
+
+
+class BatchRefiner:
+    """The refine loops of B INDEPENDENT objects (one GPU's share of config C3) as ONE launch set per iteration: every stage of
+    ObjectRefiner.step -- pose map + sample vectors, the utils.py-stack render, the losses, their backward, the per-iteration
+    evaluation (loss_rgb2, lidar-pixel depths) and the AdamW update -- runs once over all objects (ops.render_shell_batch,
+    losses.refine_loss_batch, snb_refine_pose_batch_*), ~25 launches per iteration whatever B is instead of ~30 per object.  The objects
+    stay independent: per-object pose, codes, rays, targets, jitter draws, losses (the summed loss has block-diagonal gradients) and
+    elementwise AdamW state with one shared step count.
+
+    Built from ObjectRefiners (which hold the per-object inputs and the jitter tables drawn in the reference's order); they must agree on
+    n_samples, crop size, learning rates, loss coefficient, axis convention and decoder.  ``write_back()`` copies the optimised
+    state into them."""
+
+    def __init__(self, refiners):
+        if not refiners:
+            raise ValueError("BatchRefiner needs at least one refiner")
+        r0 = refiners[0]
+        same = lambda f: all(f(r) == f(r0) for r in refiners)   # noqa: E731
+        if not (same(lambda r: (r.n_samples, r.im_sz, r.coef, r.swap, r.opt_cam_pose, r.fused, tuple(r.opt.lrs) if r.fused else None,
+                                r.jitter.shape[0])) and all(r.model is r0.model and r.device == r0.device for r in refiners)):
+            raise ValueError("BatchRefiner: the objects must share the decoder, device, n_samples, crop size, loss and optimiser settings")
+        if not r0.fused:
+            raise ValueError("BatchRefiner builds on the fused refiners (fused=True)")
+        self.refiners = list(refiners)
+        self.model, self.device = r0.model, r0.device
+        dev = self.device
+        self.n_samples, self.coef, self.swap, self.opt_cam_pose = r0.n_samples, r0.coef, r0.swap, r0.opt_cam_pose
+        st = lambda f: torch.stack([f(r) for r in refiners]).contiguous()   # noqa: E731
+        self.px, self.py = st(lambda r: r.px.reshape(-1)), st(lambda r: r.py.reshape(-1))
+        self.K = st(lambda r: r.K)
+        self.rgb_tgt, self.occ = st(lambda r: r.rgb_tgt), st(lambda r: r.occ.reshape(-1))
+        self.occ_pos = self.occ.clamp_min(0.0)
+        self.obj_diag = torch.tensor([float(r.obj_diag) for r in refiners], device=dev, dtype=torch.float32)
+        self.shapecode = st(lambda r: r.shapecode.detach().reshape(-1)).requires_grad_()
+        self.texturecode = st(lambda r: r.texturecode.detach().reshape(-1)).requires_grad_()
+        self.rot_vec = st(lambda r: r.rot_vec.detach()).requires_grad_()
+        self.trans_vec = st(lambda r: r.trans_vec.detach()).requires_grad_()
+        lrs = r0.opt.lrs
+        self.opt = FusedAdamW([{"params": self.shapecode, "lr": lrs[0]}, {"params": self.texturecode, "lr": lrs[1]},
+                               {"params": self.rot_vec, "lr": lrs[2]}, {"params": self.trans_vec, "lr": lrs[3]}],
+                              betas=r0.opt.betas, eps=r0.opt.eps, weight_decay=r0.opt.weight_decay)
+        self.jitter = st(lambda r: r.jitter)                                  # (B, T, S)
+        self.max_iters = int(self.jitter.shape[1])
+        # lidar pixels: every object's list padded to one length (a multiple of 4 rays = 256 decoder rows at 64 samples) with copies of
+        # its last pixel; the copies' depths are sliced off again.  Objects without lidar pixels render a dummy pixel and report nothing.
+        self.n_lidar = [r.n_lidar if r.lidar is not None else 0 for r in refiners]
+        self.lidar, self.jitter_lidar = None, None
+        if any(self.n_lidar):
+            width = -(-max(self.n_lidar) // 4) * 4
+            lx, ly, jl = [], [], []
+            for r, n in zip(refiners, self.n_lidar):
+                if n:
+                    x, y = r.lidar[0][:n], r.lidar[1][:n]
+                    jl.append(r.jitter_lidar)
+                else:
+                    x, y = r.px.reshape(-1)[:1], r.py.reshape(-1)[:1]
+                    jl.append(torch.zeros_like(r.jitter))
+                lx.append(torch.cat([x, x[-1:].expand(width - x.numel())]))
+                ly.append(torch.cat([y, y[-1:].expand(width - y.numel())]))
+            self.lidar = (torch.stack(lx).contiguous(), torch.stack(ly).contiguous())
+            self.jitter_lidar = torch.stack(jl).contiguous()
+        b = len(refiners)
+        self._ones = torch.ones(b, device=dev)
+        self.loss = torch.zeros(b, 3, device=dev)
+        self.loss_rgb2 = torch.zeros(b, device=dev)
+        self.depth_pred = None
+        self.it = 0              # host-side count of issued iterations (the device-side row index is the optimiser's step counter)
+        self.graph = None
+
+    def _params(self):
+        return (self.shapecode, self.texturecode, self.rot_vec, self.trans_vec)
+
+    def step(self):
+        """One iteration of every object (no host synchronisation anywhere)."""
+        if self.shapecode.grad is not None:
+            self.opt.zero_grad()
+        out = _PoseAndSamplesBatch.apply(self.rot_vec, self.trans_vec, self.jitter, self.jitter_lidar, self.opt.step_t, self.obj_diag,
+                                         self.opt_cam_pose, self.n_samples)
+        cam, z = out[0], out[1]
+        prec = self.model.precision or models.get_default_precision()
+        h, w = self.model._handle(self.device), self.model._weights()
+        rgb, _dep, acc = ops.render_shell_batch(h, prec, self.n_samples, self.swap, self.px, self.py, self.K, cam, z, self.obj_diag,
+                                                self.shapecode, self.texturecode, w)
+        loss, parts = losses.refine_loss_batch(rgb, acc, self.rgb_tgt, self.occ, self.coef)
+        torch.autograd.backward(loss, self._ones)
+        with torch.no_grad():       # the per-iteration evaluation (optimizer_nuscenes.py:740-769), before the parameter update as there
+            self.loss_rgb2 = losses.refine_loss_batch(rgb.detach(), acc.detach(), self.rgb_tgt, self.occ_pos, 0.0)[1][:, 1]
+            if self.lidar is not None:
+                _, dep2, _ = ops.render_shell_batch(h, prec, self.n_samples, self.swap, self.lidar[0], self.lidar[1], self.K, cam.detach(),
+                                                    out[2], self.obj_diag, self.shapecode.detach(), self.texturecode.detach(), w)
+                self.depth_pred = dep2           # (B, width): object b's lidar depths are depth_pred[b, :n_lidar[b]]
+        self.opt.step()
+        self.loss = parts           # (B,3) = [loss, loss_rgb, loss_occ] per object
+        return self.loss
+
+    def capture(self, warmup=3):
+        """Warm up on a side stream (allocator, weight packing), undo the warm-up updates, then capture one iteration."""
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            snapshot = [t.detach().clone() for t in self._params()]
+            for _ in range(warmup):
+                self.step()
+            with torch.no_grad():
+                for t, v in zip(self._params(), snapshot):
+                    t.copy_(v)
+                self.opt.reset()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.step()
+        return self
+
+    def run(self, iters):
+        """`iters` iterations of every object (graph replays if captured).  -> (B,3) last [loss, loss_rgb, loss_occ] per object."""
+        if self.it + int(iters) > self.max_iters:
+            raise ValueError("iters exceeds the pre-drawn jitter tables (max_iters)")
+        for _ in range(int(iters)):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self.step()
+        self.it += int(iters)
+        return self.loss
+
+    def lidar_depths(self):
+        """Per object: the depths at its lidar pixels from the last iteration's evaluation (None for an object without lidar pixels)."""
+        if self.depth_pred is None:
+            return [None] * len(self.refiners)
+        return [self.depth_pred[b, :n] if n else None for b, n in enumerate(self.n_lidar)]
+
+    def write_back(self):
+        """Copy the optimised codes and pose parameters into the ObjectRefiners this batch was built from."""
+        with torch.no_grad():
+            for b, r in enumerate(self.refiners):
+                r.shapecode.copy_(self.shapecode[b].reshape(r.shapecode.shape))
+                r.texturecode.copy_(self.texturecode[b].reshape(r.texturecode.shape))
+                r.rot_vec.copy_(self.rot_vec[b])
+                r.trans_vec.copy_(self.trans_vec[b])
+                r.loss = self.loss[b]
+                r.loss_rgb2 = self.loss_rgb2[b]
+        return self.refiners

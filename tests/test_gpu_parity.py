@@ -911,3 +911,65 @@ def test_object_group_one_graph_equals_sequential_refiners():
     for a, b in zip(seq, grp.refiners):
         assert parity_ok("b_loss", b.loss, a.loss, 1e-4)
         assert parity_ok("b_shapecode", b.shapecode, a.shapecode, 2e-2) and parity_ok("b_rot_vec", b.rot_vec, a.rot_vec, 1e-3)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_batch_refiner_one_launch_set_equals_per_object_refiners(prec):
+    """refine.BatchRefiner (B objects' refine iterations as ONE launch set: batched pose map, shell render, losses, AdamW; config C3's
+    per-GPU share) against every object's own ObjectRefiner loop: per-iteration losses, the masked PSNR loss, lidar-pixel depths
+    (ragged pixel counts, one object without any), and the optimised codes / pose parameters."""
+    S = snb()
+    import tools.refine_bench as rb
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=53)
+    m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
+    m.precision = prec
+    m.requires_grad_(False)
+    iters = 6
+    n_lidar = [37, 0, 64, 5]
+
+    def make(k):
+        seed = 80 + k
+        obj = oracle.synthetic_object(seed, im_sz=32)
+        shp0, tex0 = oracle.synthetic_latents(seed, 1)
+        c2o = obj["cam_pose"]
+        R_obj = c2o[:, :3].t().contiguous()
+        t_obj = -(R_obj @ c2o[:, 3:]).reshape(3)
+        rng = np.random.RandomState(seed)
+        roi = [int(v) for v in obj["roi"]]
+        xy = None
+        if n_lidar[k]:
+            xy = (rng.randint(0, roi[2] - roi[0], n_lidar[k]), rng.randint(0, roi[3] - roi[1], n_lidar[k]))
+        torch.manual_seed(seed)
+        return S.refine.ObjectRefiner(m, DEV, obj["img"], obj["mask_occ"], obj["K"], obj["roi"], np.linalg.norm(obj["wlh"]).astype(np.float32),
+                                      shp0, tex0, rb.matrix_to_axis_angle(R_obj), t_obj, n_samples=64, im_sz=32, max_iters=iters, lidar_xy=xy)
+    seq = [make(k) for k in range(4)]
+    bat = S.refine.BatchRefiner([make(k) for k in range(4)])
+    tol1 = 1e-5 if prec == "fp32" else 1e-4       # one iteration: same kernels on the same rows; only summation orders differ
+    for it in range(iters):
+        for r in seq:
+            r.run(1)
+        bat.run(1)
+        torch.cuda.synchronize()
+        tol = tol1 if it == 0 else (1e-3 if prec == "fp32" else 5e-3)     # later: the trajectories' own sensitivity (see the 50-iteration test)
+        for b, r in enumerate(seq):
+            assert parity_ok("it%d_loss" % it, bat.loss[b], r.loss, tol)
+            assert parity_ok("it%d_loss_rgb2" % it, bat.loss_rgb2[b], r.loss_rgb2, tol)
+            d = bat.lidar_depths()[b]
+            if n_lidar[b]:
+                assert d.shape == r.depth_pred.shape and parity_ok("it%d_lidar_depth" % it, d, r.depth_pred, tol)
+            else:
+                assert d is None
+            if it == 0:
+                assert parity_ok("it0_shapecode", bat.shapecode[b], r.shapecode.reshape(-1), tol1)
+                assert parity_ok("it0_rot_vec", bat.rot_vec[b], r.rot_vec, tol1) and parity_ok("it0_trans_vec", bat.trans_vec[b], r.trans_vec, tol1)
+    for b, r in enumerate(bat.write_back()):
+        assert parity_ok("end_shapecode", r.shapecode, seq[b].shapecode, 2e-2) and parity_ok("end_texturecode", r.texturecode, seq[b].texturecode, 2e-2)
+        assert parity_ok("end_rot_vec", r.rot_vec, seq[b].rot_vec, 5e-3) and parity_ok("end_trans_vec", r.trans_vec, seq[b].trans_vec, 5e-3)
+    # the captured graph replays the same iteration
+    cap = S.refine.BatchRefiner([make(k) for k in range(4)]).capture()
+    cap.run(iters)
+    torch.cuda.synchronize()
+    # (not bit-equal: the fp32 / fp64 atomics of the reductions land in another order, and AdamW's g / sqrt(v) amplifies that)
+    assert parity_ok("graph_loss", cap.loss, bat.loss, 1e-4) and parity_ok("graph_shapecode", cap.shapecode, bat.shapecode, 2e-2)
+    with pytest.raises(ValueError):
+        cap.run(1)            # the jitter tables hold max_iters rows

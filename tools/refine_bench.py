@@ -45,6 +45,8 @@ def main():
     ap.add_argument("--samples", type=int, default=64)
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--streams", type=int, default=1, help="with --graph: refine this rank's objects side by side over this many CUDA streams (refine.run_objects)")
+    ap.add_argument("--batch", action="store_true", help="supnerf_b200.refine.BatchRefiner: this rank's objects as ONE launch set per iteration (one CUDA graph)")
+    ap.add_argument("--eager", action="store_true", help="with --batch: do not capture (one launch per kernel: for ncu launch lists)")
     ap.add_argument("--graph", action="store_true", help="supnerf_b200.refine.ObjectRefiner: one CUDA graph per iteration, no host sync")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -89,13 +91,15 @@ def main():
             opt.step()
         return loss
 
-    if a.graph:
+    if a.graph or a.batch:
         refiners = []
         for o in objs:
             torch.manual_seed(1000 + len(refiners))
             refiners.append(snb.refine.ObjectRefiner(model, dev, o["img"], o["mask"], o["K"], o["roi"], o["obj_diag"], o["shapecode"],
                                                      o["texturecode"], o["rot_vec"], o["trans_vec"], n_samples=a.samples, im_sz=a.im,
-                                                     max_iters=a.iters).capture())
+                                                     max_iters=a.iters + 8))
+            if a.graph:
+                refiners[-1].capture()
 
         def refine(o, iters):   # noqa: F811
             return refiners[[id(x) for x in objs].index(id(o))].run(iters)[0]
@@ -108,8 +112,16 @@ def main():
     if world > 1:
         torch.distributed.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if a.batch:
+        bat = snb.refine.BatchRefiner(refiners)
+        if not a.eager:
+            bat.capture()
+        bat.run(3)
+        torch.cuda.synchronize()
     e0.record()
-    if a.graph and a.streams > 1:
+    if a.batch:
+        last = list(bat.run(a.iters)[:, 0])
+    elif a.graph and a.streams > 1:
         last = [l[0] for l in snb.refine.run_objects(refiners, a.iters, a.streams)]
     else:
         last = [refine(o, a.iters) for o in objs]
@@ -127,7 +139,7 @@ def main():
                           "n_gpus": world, "ms_total": round(ms, 2), "ms_per_refine_iteration": round(ms / max(n_local * a.iters, 1), 4),
                           "objects_per_gpu": n_local, "rays_per_s": round(a.objects * a.iters * a.im * a.im / (ms / 1e3), 1),
                           "loss_first_object": {"before": round(l0, 5), "after": round(float(last[0].detach()), 5)}, "precision": a.precision,
-                          "mode": ("one CUDA graph per iteration (refine.ObjectRefiner)" + (", objects side by side over %d streams (refine.run_objects)" % a.streams if a.streams > 1 else "")) if a.graph else "eager reference-API loop (render_rays_v2 + torch AdamW)"}))
+                          "mode": ("one CUDA graph per iteration (refine.ObjectRefiner)" + (", objects side by side over %d streams (refine.run_objects)" % a.streams if a.streams > 1 else "")) if a.graph else "refine.BatchRefiner: one launch set per iteration for the rank's objects" if a.batch else "eager reference-API loop (render_rays_v2 + torch AdamW)"}))
     if world > 1:
         torch.distributed.destroy_process_group()
 
