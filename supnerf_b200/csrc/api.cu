@@ -40,12 +40,12 @@ size_t tc_workspace_bytes(const snb_handle_s* h, int64_t M, int64_t B);
 size_t tc_bwd_scratch_bytes(const snb_handle_s* h, int64_t M, int64_t B);
 int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, void* ws, cudaStream_t st, bool train,
-               const int64_t* m_dev, const int32_t* tile_start = nullptr, const rb::RowSrc* rs = nullptr);
+               const int64_t* m_dev, const int32_t* tile_start = nullptr, const rb::RowSrc* rs = nullptr, bool split = false);
 int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                 const float* shape_latent, const float* texture_latent, const float* sigma, const float* g_sigma,
                 const float* g_rgb, const void* ws, void* scratch, float* g_xyz, float* g_viewdir, float* g_shape_latent,
                 float* g_texture_latent, float* const* g_weights, cudaStream_t st, bool train, const int64_t* m_dev,
-                const int32_t* tile_start = nullptr);
+                const int32_t* tile_start = nullptr, bool split = false);
 size_t tc_train_workspace_extra(const snb_handle_s* h, int64_t M);
 size_t tc_train_scratch_extra(const snb_handle_s* h, int64_t M);
 
@@ -158,7 +158,7 @@ extern "C" int snb_pack_weights(snb_handle h, void* packed, void* stream) {
 static int check_mlp_args(snb_handle h, int32_t precision, int64_t M, int64_t B) {
   SNB_REQUIRE(h != nullptr, "mlp: null handle");
   SNB_REQUIRE(h->weights_set, "mlp: weights not set");
-  SNB_REQUIRE(precision == SNB_PREC_FP32 || precision == SNB_PREC_BF16 || precision == SNB_PREC_BF16_TRAIN,
+  SNB_REQUIRE(precision == SNB_PREC_FP32 || precision == SNB_PREC_BF16 || precision == SNB_PREC_BF16_TRAIN || precision == SNB_PREC_FP32_TC,
               "mlp: unknown precision %d", precision);
   SNB_REQUIRE(M >= 0 && B >= 1 && M % B == 0, "mlp: n_rows (%lld) must be a multiple of n_objs (%lld)", (long long)M, (long long)B);
   SNB_REQUIRE(sm_count() > 0, "mlp: no CUDA device (there is no CPU fallback)");
@@ -167,14 +167,14 @@ static int check_mlp_args(snb_handle h, int32_t precision, int64_t M, int64_t B)
 
 extern "C" size_t snb_mlp_workspace_bytes(snb_handle h, int64_t M, int64_t B, int32_t precision) {
   if (!h) return 0;
-  if (precision == SNB_PREC_BF16) return tc_workspace_bytes(h, M, B);
+  if (precision == SNB_PREC_BF16 || precision == SNB_PREC_FP32_TC) return tc_workspace_bytes(h, M, B);
   if (precision == SNB_PREC_BF16_TRAIN) return tc_workspace_bytes(h, M, B) + tc_train_workspace_extra(h, M);
   return f32_workspace_floats(h, M, B) * sizeof(float);
 }
 
 extern "C" size_t snb_mlp_bwd_scratch_bytes(snb_handle h, int64_t M, int64_t B, int32_t precision) {
   if (!h) return 0;
-  if (precision == SNB_PREC_BF16) return tc_bwd_scratch_bytes(h, M, B);
+  if (precision == SNB_PREC_BF16 || precision == SNB_PREC_FP32_TC) return tc_bwd_scratch_bytes(h, M, B);
   if (precision == SNB_PREC_BF16_TRAIN) return tc_bwd_scratch_bytes(h, M, B) + tc_train_scratch_extra(h, M);
   return f32_bwd_scratch_floats(h, M, B) * sizeof(float);
 }
@@ -187,7 +187,7 @@ extern "C" int snb_mlp_fwd(snb_handle h, int32_t precision, const float* xyz, co
   SNB_REQUIRE(xyz && viewdir && shape_latent && texture_latent && sigma && rgb && workspace, "mlp_fwd: null pointer");
   if (precision != SNB_PREC_FP32)
     return tc_forward(h, xyz, viewdir, M, B, shape_latent, texture_latent, sigma, rgb, workspace, (cudaStream_t)stream,
-                      precision == SNB_PREC_BF16_TRAIN, nullptr);
+                      precision == SNB_PREC_BF16_TRAIN, nullptr, nullptr, nullptr, precision == SNB_PREC_FP32_TC);
   return f32_forward(h, xyz, viewdir, M, B, shape_latent, texture_latent, sigma, rgb, (float*)workspace, (cudaStream_t)stream);
 }
 
@@ -213,7 +213,7 @@ extern "C" int snb_mlp_bwd(snb_handle h, int32_t precision, const float* xyz, co
   if (precision != SNB_PREC_FP32)
     return tc_backward(h, xyz, viewdir, M, B, shape_latent, texture_latent, sigma, g_sigma, g_rgb, workspace, scratch, g_xyz,
                        g_viewdir, g_shape_latent, g_texture_latent, g_weights, (cudaStream_t)stream,
-                       precision == SNB_PREC_BF16_TRAIN, nullptr);
+                       precision == SNB_PREC_BF16_TRAIN, nullptr, nullptr, precision == SNB_PREC_FP32_TC);
   return f32_backward(h, xyz, viewdir, M, B, shape_latent, texture_latent, sigma, g_sigma, g_rgb, (const float*)workspace,
                       (float*)scratch, g_xyz, g_viewdir, g_shape_latent, g_texture_latent, g_weights, (cudaStream_t)stream);
 }

@@ -29,11 +29,11 @@ int sample_box_bwd_compact(const float* rays_o, const float* viewdir, const floa
 bool tc_two_tile_active(const snb_handle_s* h);
 int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, void* ws, cudaStream_t st, bool train,
-               const int64_t* m_dev, const int32_t* tile_start = nullptr, const rb::RowSrc* rs = nullptr);
+               const int64_t* m_dev, const int32_t* tile_start = nullptr, const rb::RowSrc* rs = nullptr, bool split = false);
 int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                 const float* shape_latent, const float* texture_latent, const float* sigma, const float* g_sigma,
                 const float* g_rgb, const void* ws, void* scratch, float* g_xyz, float* g_viewdir, float* g_shape_latent,
                 float* g_texture_latent, float* const* g_weights, cudaStream_t st, bool train, const int64_t* m_dev,
-                const int32_t* tile_start = nullptr);
+                const int32_t* tile_start = nullptr, bool split = false);
 
 }  // namespace snb

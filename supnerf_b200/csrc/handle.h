@@ -20,6 +20,7 @@ struct snb_handle_s {
   // per-handle caches of pure functions of the architecture (built on first use; a handle is used by one host thread at a time)
   mutable std::shared_ptr<void> tc2_programs;   // mlp_tc2.cu: the step programs of the two-tile kernels
   mutable size_t v1_packed_bytes_cache = 0;     // mlp_tc.cu: size of the first-generation packed image
+  mutable size_t x3_packed_bytes_cache = 0;     // mlp_tc.cu: size of the split-precision (fp16 hi / lo) packed image
   // test / tuning / measurement hooks, per handle (a handle is used by one host thread at a time; nothing here is process-global)
   float* dbg_acts = nullptr;                    // snb_tc_set_debug
   long long* trace = nullptr;                   // snb_tc_set_trace

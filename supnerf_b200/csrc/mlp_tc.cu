@@ -28,25 +28,38 @@ namespace snb {
 namespace tc {
 
 constexpr int kStages = 3;
-constexpr uint32_t kStageBytes = 32768;   // [256 n][64 k] bf16
 constexpr int kMaxSteps = 16;
 constexpr int kMaxFwdSteps = 12;
 constexpr int kThreads = 320;
 constexpr int kMaxLatentSlots = 8;
 
+// Split mode (template parameter X = true; SNB_PREC_FP32_TC): fp32-grade arithmetic on the same tensor-core pipeline.  Every MMA
+// operand is held as TWO fp16 parts (x = hi + lo, |lo| <= 2^-12 |x|) and each product is issued as three MMAs (hi*hi, lo*hi, hi*lo;
+// lo*lo ~ 2^-24 is dropped) accumulating into the same fp32 TMEM columns.  Weights are packed as 256 * w (a power of two keeps the low
+// part out of fp16's subnormal range; |w| < 255), forward A operands are the activations themselves (|a| < 65504), backward A operands
+// are each row's gradient normalised by a power of two taken from its upstream gradient (the backward pass is linear in it), undone
+// where values leave the tile (latent column sums, d xyz, d viewdir).  Shared memory: every logical 64-column A chunk is a (hi, lo)
+// pair of physical chunks, the weight ring carries [128 n][64 k] stages (hi and lo of each N half, one after the other) and the
+// bias / latent tables are read through L1 instead (tools/experiments/split_precision_emulation.py: errors vs fp64 on par with fp32 FFMA).
+constexpr float kWScale = 256.f, kWScaleInv = 1.f / 256.f;
+
 // shared-memory map (bytes from the 1024-aligned base)
-constexpr uint32_t SM_W = 5 * kChunkBytes;                       // A chunks 0..3, AUX chunk 4, then the weight ring
-constexpr uint32_t SM_TAB = SM_W + kStages * kStageBytes;        // fp32 tables
-constexpr uint32_t TAB_BIAS = 0;                                 // fwd: [kMaxFwdSteps][256]   bwd: colsum [8][256] at the same place
-constexpr uint32_t TAB_Z = TAB_BIAS + kMaxFwdSteps * 256 * 4;    // fwd: [8][256] latent vectors of the current object
-constexpr uint32_t TAB_WSIG = TAB_Z + kMaxLatentSlots * 256 * 4; // [256]
-constexpr uint32_t TAB_W2 = TAB_WSIG + 256 * 4;                  // [3][128]
-constexpr uint32_t TAB_PART = TAB_W2 + 384 * 4;                  // fwd: sig_part [2][128] + rgb_part [2][128][3]; bwd: xyz_part [2][128][3]
-constexpr uint32_t TAB_BYTES = TAB_PART + (256 + 768) * 4;
-constexpr uint32_t SM_BARS = SM_TAB + TAB_BYTES;
-constexpr uint32_t SM_TOTAL = SM_BARS + 32 * 8 + 16;
-constexpr uint32_t SM_ALLOC = SM_TOTAL + 1024;                   // + alignment slack
-static_assert(SM_ALLOC <= 232448, "shared memory budget");
+template <bool X> struct Map {
+  static constexpr uint32_t kAChunks = X ? 10u : 5u;                 // A chunks 0..3, AUX chunk 4 (split: physical chunk 2c + part)
+  static constexpr uint32_t kStageBytes = X ? 16384u : 32768u;       // [256 n][64 k] bf16, split: [128 n][64 k] fp16
+  static constexpr uint32_t SM_W = kAChunks * kChunkBytes;           // then the weight ring
+  static constexpr uint32_t SM_TAB = SM_W + kStages * kStageBytes;   // fp32 tables
+  static constexpr uint32_t TAB_BIAS = 0;                            // fwd: [kMaxFwdSteps][256] (split: none)  bwd: colsum [8][256]
+  static constexpr uint32_t TAB_Z = TAB_BIAS + (X ? kMaxLatentSlots : kMaxFwdSteps) * 256 * 4;   // fwd: [8][256] per-object effective biases (split: none)
+  static constexpr uint32_t TAB_WSIG = TAB_Z + (X ? 0 : kMaxLatentSlots * 256 * 4);   // [256]
+  static constexpr uint32_t TAB_W2 = TAB_WSIG + 256 * 4;             // [3][128]
+  static constexpr uint32_t TAB_PART = TAB_W2 + 384 * 4;             // fwd: sig_part [2][128] + rgb_part [2][128][3]; bwd: xyz_part [2][128][3]
+  static constexpr uint32_t TAB_BYTES = TAB_PART + (256 + 768) * 4;
+  static constexpr uint32_t SM_BARS = SM_TAB + TAB_BYTES;
+  static constexpr uint32_t SM_TOTAL = SM_BARS + 32 * 8 + 16;
+  static constexpr uint32_t SM_ALLOC = SM_TOTAL + 1024;              // + alignment slack
+};
+static_assert(Map<false>::SM_ALLOC <= 232448 && Map<true>::SM_ALLOC <= 232448, "shared memory budget");
 
 enum Epi : int { EPI_RELU = 0, EPI_LINEAR_SIGMA = 1, EPI_RGB_HEAD = 2, EPI_B_MASK = 3, EPI_B_EV = 4, EPI_B_XYZ = 5 };
 
@@ -77,18 +90,34 @@ struct Params {
   const float* sigma_in; const float* g_sigma; const float* g_rgb;
   float* g_xyz; float* g_viewdir; float* g_zlat;   // g_zlat [(Bs+Bt)][B][256], accumulated with atomics
   int r0_mask_slot, n_latent, ev_step;
+  const int64_t* m_dev;         // split mode: device-side row count (a multiple of 128, <= M) or null
+  const int32_t* tile_start;    // split mode: per-object first tile (B + 1 ints) or null = M / B rows per object
   Program prog;
 };
 
-struct Smem {
+template <bool X> struct SmemT {
+  using M = Map<X>;
   uint8_t* base;
   uint32_t base_u32;
-  __device__ uint8_t* chunk(int c) const { return base + (uint32_t)c * kChunkBytes; }
-  __device__ uint32_t chunk_u32(int c) const { return base_u32 + (uint32_t)c * kChunkBytes; }
-  __device__ uint32_t stage_u32(int s) const { return base_u32 + SM_W + (uint32_t)s * kStageBytes; }
-  __device__ float* tab(uint32_t off) const { return reinterpret_cast<float*>(base + SM_TAB + off); }
-  __device__ uint32_t bar(int i) const { return base_u32 + SM_BARS + 8u * i; }
+  // logical A chunk c (0..4); split mode: part 0 = hi, 1 = lo
+  __device__ uint8_t* chunk(int c, int part = 0) const { return base + (uint32_t)(X ? 2 * c + part : c) * kChunkBytes; }
+  __device__ uint32_t chunk_u32(int c, int part = 0) const { return base_u32 + (uint32_t)(X ? 2 * c + part : c) * kChunkBytes; }
+  __device__ uint32_t stage_u32(int s) const { return base_u32 + M::SM_W + (uint32_t)s * M::kStageBytes; }
+  __device__ float* tab(uint32_t off) const { return reinterpret_cast<float*>(base + M::SM_TAB + off); }
+  __device__ uint32_t bar(int i) const { return base_u32 + M::SM_BARS + 8u * i; }
 };
+
+__device__ __forceinline__ int64_t rows_present(const Params& p) { return p.m_dev ? *p.m_dev : p.M; }
+// the object a tile belongs to: binary search of the per-object first tiles (batched render), else uniform rows per object
+__device__ __forceinline__ int64_t obj_of_tile(const Params& p, int64_t tile) {
+  if (p.tile_start == nullptr) return (tile * kTileM) / p.rows_per_obj;
+  int lo = 0, hi = (int)p.B - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if ((int64_t)__ldg(p.tile_start + mid) <= tile) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
 // barrier indices
 constexpr int BAR_WFULL = 0, BAR_WEMPTY = 4, BAR_AREADY = 8, BAR_ACC = 13;
 
@@ -100,21 +129,28 @@ struct EpiCtx {
 };
 
 // ------------------------------------------------------------------------------------------ roles shared by fwd / bwd
-__device__ __forceinline__ void producer_loop(const Params& p, const Smem& sm, int64_t n_tiles, uint32_t lane) {
+// weight stages of one K chunk of an MMA group: plain mode one [n][64 k] image; split mode per N half (<= 128 columns) the hi image,
+// then the lo image
+__device__ __forceinline__ uint32_t n_half_of(uint32_t n) { return n < 128u ? n : 128u; }
+
+template <bool X>
+__device__ __forceinline__ void producer_loop(const Params& p, const SmemT<X>& sm, int64_t n_tiles, uint32_t lane) {
   uint32_t it = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     for (int si = 0; si < p.prog.n_steps; ++si) {
       const Step& st = p.prog.s[si];
       const int groups = st.n2_out ? 2 : 1;
       for (int g = 0; g < groups; ++g) {
-        const uint32_t bytes = (uint32_t)(g == 0 ? st.n_out : st.n2_out) * 128u;
+        const uint32_t n = (uint32_t)(g == 0 ? st.n_out : st.n2_out);
+        const uint32_t bytes = (X ? n_half_of(n) : n) * 128u;
         const uint32_t off0 = g == 0 ? st.w_off : st.w2_off;
-        for (int kc = 0; kc < st.n_chunks; ++kc, ++it) {
+        const int entries = (int)st.n_chunks * (X ? 3 * (int)(n / n_half_of(n)) : 1);   // split: see mma_loop for the order
+        for (int e = 0; e < entries; ++e, ++it) {
           const uint32_t stage = it % kStages, ph = (it / kStages) & 1u;
           if (lane == 0) {
             mbar_wait(sm.bar(BAR_WEMPTY + stage), ph ^ 1u);
             mbar_expect_tx(sm.bar(BAR_WFULL + stage), bytes);
-            bulk_g2s(sm.stage_u32(stage), p.packed + off0 + (size_t)kc * bytes, bytes, sm.bar(BAR_WFULL + stage));
+            bulk_g2s(sm.stage_u32(stage), p.packed + off0 + (size_t)e * bytes, bytes, sm.bar(BAR_WFULL + stage));
           }
           __syncwarp();
         }
@@ -123,7 +159,8 @@ __device__ __forceinline__ void producer_loop(const Params& p, const Smem& sm, i
   }
 }
 
-__device__ __forceinline__ void mma_loop(const Params& p, const Smem& sm, int64_t n_tiles, uint32_t lane, uint32_t tmem_base) {
+template <bool X>
+__device__ __forceinline__ void mma_loop(const Params& p, const SmemT<X>& sm, int64_t n_tiles, uint32_t lane, uint32_t tmem_base) {
   uint32_t it = 0, gstep = 0;
   uint32_t a_phase = 0;  // bit c = parity of the next completion of a_ready[c] to wait for
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -134,22 +171,80 @@ __device__ __forceinline__ void mma_loop(const Params& p, const Smem& sm, int64_
       for (int g = 0; g < groups; ++g) {
         const uint32_t n = g == 0 ? st.n_out : st.n2_out;
         const uint32_t d_tmem = tmem_base + (g == 0 ? half : (half ^ 1u)) * 256u;
-        const uint32_t idesc = umma_idesc(128, n);
-        for (int kc = 0; kc < st.n_chunks; ++kc, ++it) {
-          const int ac = st.a_chunk[kc];
-          const uint32_t stage = it % kStages, ph = (it / kStages) & 1u;
-          if (lane == 0) {
-            if (g == 0) mbar_wait(sm.bar(BAR_AREADY + ac), (a_phase >> ac) & 1u);
-            mbar_wait(sm.bar(BAR_WFULL + stage), ph);
-            tc_fence_after();
-            const uint32_t a0 = sm.chunk_u32(ac), b0 = sm.stage_u32(stage);
+        if (!X) {
+          const uint32_t idesc = umma_idesc(128, n);
+          for (int kc = 0; kc < st.n_chunks; ++kc, ++it) {
+            const int ac = st.a_chunk[kc];
+            const uint32_t stage = it % kStages, ph = (it / kStages) & 1u;
+            if (lane == 0) {
+              if (g == 0) mbar_wait(sm.bar(BAR_AREADY + ac), (a_phase >> ac) & 1u);
+              mbar_wait(sm.bar(BAR_WFULL + stage), ph);
+              tc_fence_after();
+              const uint32_t a0 = sm.chunk_u32(ac), b0 = sm.stage_u32(stage);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_bf16(d_tmem, umma_desc(a0 + kk * 32), umma_desc(b0 + kk * 32), idesc, (kc > 0 || kk > 0) ? 1u : 0u);
-            umma_commit(sm.bar(BAR_WEMPTY + stage));
+              for (int kk = 0; kk < 4; ++kk)
+                umma_bf16(d_tmem, umma_desc(a0 + kk * 32), umma_desc(b0 + kk * 32), idesc, (kc > 0 || kk > 0) ? 1u : 0u);
+              umma_commit(sm.bar(BAR_WEMPTY + stage));
+            }
+            if (g == 0) a_phase ^= 1u << ac;
+            __syncwarp();
           }
-          if (g == 0) a_phase ^= 1u << ac;
-          __syncwarp();
+        } else {
+          // Per N half: FIRST every K chunk's correction products (a_lo * w_hi, a_hi * w_lo), THEN the leading products (a_hi * w_hi).
+          // The tensor core truncates the fp32 accumulator after every instruction (an error of up to one ulp of its CURRENT
+          // magnitude each): the 2 x 16 correction instructions run while it only holds the ~2^-11 times smaller correction sum, so
+          // only the 16 leading instructions truncate at full scale.  (The hi image of every chunk is streamed twice for this.)
+          const uint32_t nh_n = n_half_of(n), halves = n / nh_n;
+          const uint32_t idesc = umma_idesc_f16(128, nh_n);
+          for (uint32_t nh = 0; nh < halves; ++nh) {
+            const uint32_t d = d_tmem + nh * 128u;
+            for (int kc = 0; kc < st.n_chunks; ++kc) {          // corrections
+              const int ac = st.a_chunk[kc];
+              const bool first_use = g == 0 && nh == 0;
+              const uint32_t a_hi = sm.chunk_u32(ac, 0), a_lo = sm.chunk_u32(ac, 1);
+              {  // W hi stage: a_lo * w_hi
+                const uint32_t stage = it % kStages, ph = (it / kStages) & 1u;
+                if (lane == 0) {
+                  if (first_use) mbar_wait(sm.bar(BAR_AREADY + ac), (a_phase >> ac) & 1u);
+                  mbar_wait(sm.bar(BAR_WFULL + stage), ph);
+                  tc_fence_after();
+                  const uint32_t b0 = sm.stage_u32(stage);
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(d, umma_desc(a_lo + kk * 32), umma_desc(b0 + kk * 32), idesc, (kc > 0 || kk > 0) ? 1u : 0u);
+                  umma_commit(sm.bar(BAR_WEMPTY + stage));
+                }
+                ++it;
+              }
+              {  // W lo stage: a_hi * w_lo
+                const uint32_t stage = it % kStages, ph = (it / kStages) & 1u;
+                if (lane == 0) {
+                  mbar_wait(sm.bar(BAR_WFULL + stage), ph);
+                  tc_fence_after();
+                  const uint32_t b0 = sm.stage_u32(stage);
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk) umma_bf16(d, umma_desc(a_hi + kk * 32), umma_desc(b0 + kk * 32), idesc, 1u);
+                  umma_commit(sm.bar(BAR_WEMPTY + stage));
+                }
+                ++it;
+              }
+              if (first_use) a_phase ^= 1u << ac;
+              __syncwarp();
+            }
+            for (int kc = 0; kc < st.n_chunks; ++kc, ++it) {    // leading products: W hi stage again, a_hi * w_hi
+              const uint32_t a_hi = sm.chunk_u32(st.a_chunk[kc], 0);
+              const uint32_t stage = it % kStages, ph = (it / kStages) & 1u;
+              if (lane == 0) {
+                mbar_wait(sm.bar(BAR_WFULL + stage), ph);
+                tc_fence_after();
+                const uint32_t b0 = sm.stage_u32(stage);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) umma_bf16(d, umma_desc(a_hi + kk * 32), umma_desc(b0 + kk * 32), idesc, 1u);
+                umma_commit(sm.bar(BAR_WEMPTY + stage));
+              }
+              __syncwarp();
+            }
+          }
         }
       }
       if (lane == 0) umma_commit(sm.bar(BAR_ACC + half));
@@ -159,7 +254,8 @@ __device__ __forceinline__ void mma_loop(const Params& p, const Smem& sm, int64_
 }
 
 // after this thread's generic-proxy stores into an A chunk: publish to the async proxy and signal the MMA warp
-__device__ __forceinline__ void publish_chunk(const Smem& sm, int c, uint32_t lane) {
+template <bool X>
+__device__ __forceinline__ void publish_chunk(const SmemT<X>& sm, int c, uint32_t lane) {
   tc_fence_before();
   fence_async_smem();
   __syncwarp();
@@ -174,12 +270,43 @@ __device__ __forceinline__ void store_row32(uint8_t* chunk, uint32_t row, uint32
   }
 }
 
-__device__ __forceinline__ void kernel_prologue(Smem& sm, uint8_t* smem_raw, uint32_t tid, uint32_t warp, uint32_t& tmem_base) {
+// A-operand writer of one 32-column half row: plain mode one bf16 chunk, split mode the fp16 (hi, lo) chunk pair
+template <bool X> struct RowPack {
+  uint32_t hi[16], lo[X ? 16 : 1];
+  __device__ __forceinline__ void set(int i, float a, float b) {   // word i = columns (2i, 2i + 1)
+    if constexpr (X) split_f16x2(a, b, hi[i], lo[i]); else hi[i] = pack_bf16(a, b);
+  }
+  __device__ __forceinline__ void set_relu(int i, float a, float b) {
+    if constexpr (X) split_f16x2(fmaxf(a, 0.f), fmaxf(b, 0.f), hi[i], lo[i]); else hi[i] = pack_bf16_relu(a, b);
+  }
+  __device__ __forceinline__ void store(const SmemT<X>& sm, int c, uint32_t row, uint32_t hh) const {
+    store_row32(sm.chunk(c, 0), row, hh, hi);
+    if constexpr (X) store_row32(sm.chunk(c, 1), row, hh, lo);
+  }
+};
+
+// PE(x) of this thread's half row into the AUX chunk (split mode: both parts)
+template <int DEG, bool X>
+__device__ __forceinline__ void write_pe(const SmemT<X>& sm, uint32_t row, uint32_t hh, const float x[3]) {
+  if constexpr (!X) {
+    write_pe_row<DEG>(sm.chunk(4), row, hh, x);
+  } else {
+    float v[32];
+    pe_half_f32<DEG>(x, hh, v);
+    RowPack<X> rp;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) rp.set(i, v[2 * i], v[2 * i + 1]);
+    rp.store(sm, 4, row, hh);
+  }
+}
+
+template <bool X>
+__device__ __forceinline__ void kernel_prologue(SmemT<X>& sm, uint8_t* smem_raw, uint32_t tid, uint32_t warp, uint32_t& tmem_base) {
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
   sm.base = smem_raw + pad;
   sm.base_u32 = raw + pad;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.base + SM_BARS + 32 * 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm.base + Map<X>::SM_BARS + 32 * 8);
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(sm.bar(BAR_WFULL + i), 1); mbar_init(sm.bar(BAR_WEMPTY + i), 1); }
     for (int i = 0; i < 5; ++i) mbar_init(sm.bar(BAR_AREADY + i), 8);
@@ -195,15 +322,17 @@ __device__ __forceinline__ void kernel_prologue(Smem& sm, uint8_t* smem_raw, uin
 
 // ------------------------------------------------------------------------------------------ forward epilogues
 // One layer's epilogue for this thread's row: TMEM -> (+bias, ReLU, mask bits, +latent) -> bf16 -> shared-memory A operand.
-// The TMEM load of chunk c+1 is in flight while chunk c is processed.
-template <int EPI, bool LAT, bool DBG>
-__device__ __forceinline__ void fwd_epilogue(const Params& p, const Smem& sm, const Step& st, int si, uint32_t half, const EpiCtx& e,
-                                             uint32_t* mask_tile, float& sig_acc, float (&rgb_acc)[3]) {
+// The TMEM load of chunk c+1 is in flight while chunk c is processed.  Split mode: accumulators carry the weight scale; the bias /
+// per-object effective bias is read through L1 from `bias_g` (every lane of a warp reads the same address).
+template <int EPI, bool LAT, bool DBG, bool X>
+__device__ __forceinline__ void fwd_epilogue(const Params& p, const SmemT<X>& sm, const Step& st, int si, uint32_t half, const EpiCtx& e,
+                                             uint32_t* mask_tile, float& sig_acc, float (&rgb_acc)[3], const float* bias_g) {
+  using MP = Map<X>;
   constexpr int NC = (EPI == EPI_RGB_HEAD) ? 2 : 4;
   // latent-conditioned layers read their per-object EFFECTIVE bias  b + W z_obj  (the latent add folded through the layer)
-  const float* bias_s = LAT ? sm.tab(TAB_Z) + st.latent_slot * 256 : sm.tab(TAB_BIAS) + si * 256;
-  const float* wsig_s = sm.tab(TAB_WSIG);
-  const float* w2_s = sm.tab(TAB_W2);
+  const float* bias_s = X ? bias_g : (LAT ? sm.tab(MP::TAB_Z) + st.latent_slot * 256 : sm.tab(MP::TAB_BIAS) + si * 256);
+  const float* wsig_s = sm.tab(MP::TAB_WSIG);
+  const float* w2_s = sm.tab(MP::TAB_W2);
   const uint32_t t0 = e.tmem_base + half * 256u + e.hh * 32u + e.lane_field;
   uint32_t ra[32], rb[32];
   tmem_ld32_issue(t0, ra);
@@ -213,12 +342,20 @@ __device__ __forceinline__ void fwd_epilogue(const Params& p, const Smem& sm, co
     tmem_ld_wait();
     if (c + 1 < NC) tmem_ld32_issue(t0 + (uint32_t)(c + 1) * 64u, (c & 1) ? ra : rb);
     const int col0 = c * 64 + (int)e.hh * 32;
-    uint32_t pk[16], nmask = 0;   // nmask collects SIGN bits (1 = negative pre-activation); stored inverted
+    RowPack<X> rp;
+    uint32_t nmask = 0;   // nmask collects SIGN bits (1 = negative pre-activation); stored inverted
 #pragma unroll
     for (int i4 = 0; i4 < 8; ++i4) {
-      const float4 bb = *reinterpret_cast<const float4*>(bias_s + col0 + 4 * i4);
-      float v[4] = {__uint_as_float(r[4 * i4]) + bb.x, __uint_as_float(r[4 * i4 + 1]) + bb.y,
-                    __uint_as_float(r[4 * i4 + 2]) + bb.z, __uint_as_float(r[4 * i4 + 3]) + bb.w};
+      const float4 bb = X ? __ldg(reinterpret_cast<const float4*>(bias_s + col0 + 4 * i4))
+                          : *reinterpret_cast<const float4*>(bias_s + col0 + 4 * i4);
+      float v[4];
+      if (X) {
+        v[0] = fmaf(__uint_as_float(r[4 * i4]), kWScaleInv, bb.x); v[1] = fmaf(__uint_as_float(r[4 * i4 + 1]), kWScaleInv, bb.y);
+        v[2] = fmaf(__uint_as_float(r[4 * i4 + 2]), kWScaleInv, bb.z); v[3] = fmaf(__uint_as_float(r[4 * i4 + 3]), kWScaleInv, bb.w);
+      } else {
+        v[0] = __uint_as_float(r[4 * i4]) + bb.x; v[1] = __uint_as_float(r[4 * i4 + 1]) + bb.y;
+        v[2] = __uint_as_float(r[4 * i4 + 2]) + bb.z; v[3] = __uint_as_float(r[4 * i4 + 3]) + bb.w;
+      }
       if (EPI != EPI_LINEAR_SIGMA) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) nmask = __funnelshift_l(__float_as_uint(v[u]), nmask, 1);
@@ -242,93 +379,99 @@ __device__ __forceinline__ void fwd_epilogue(const Params& p, const Smem& sm, co
         }
       }
       if (EPI == EPI_LINEAR_SIGMA) {
-        pk[2 * i4] = pack_bf16(v[0], v[1]);
-        pk[2 * i4 + 1] = pack_bf16(v[2], v[3]);
+        rp.set(2 * i4, v[0], v[1]);
+        rp.set(2 * i4 + 1, v[2], v[3]);
       } else if (EPI == EPI_RELU) {
-        pk[2 * i4] = pack_bf16_relu(v[0], v[1]);
-        pk[2 * i4 + 1] = pack_bf16_relu(v[2], v[3]);
+        rp.set_relu(2 * i4, v[0], v[1]);
+        rp.set_relu(2 * i4 + 1, v[2], v[3]);
       }
     }
     const uint32_t mask = ~nmask;
     if (EPI != EPI_LINEAR_SIGMA) mask_tile[((size_t)st.mask_slot * 8 + c * 2 + e.hh) * 128 + e.row] = mask;
     if (EPI != EPI_RGB_HEAD) {
-      store_row32(sm.chunk(c), e.row, e.hh, pk);
+      rp.store(sm, c, e.row, e.hh);
       publish_chunk(sm, c, e.lane);
     }
   }
 }
 
-template <bool DBG>
-__device__ __forceinline__ void fwd_epilogue_dispatch(const Params& p, const Smem& sm, const Step& st, int si, uint32_t half,
-                                                      const EpiCtx& e, uint32_t* mask_tile, float& sig_acc, float (&rgb_acc)[3]) {
+template <bool DBG, bool X>
+__device__ __forceinline__ void fwd_epilogue_dispatch(const Params& p, const SmemT<X>& sm, const Step& st, int si, uint32_t half,
+                                                      const EpiCtx& e, uint32_t* mask_tile, float& sig_acc, float (&rgb_acc)[3],
+                                                      const float* bias_g) {
   if (st.epi == EPI_RELU) {
-    if (st.latent_slot >= 0) fwd_epilogue<EPI_RELU, true, DBG>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc);
-    else fwd_epilogue<EPI_RELU, false, DBG>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc);
+    if (st.latent_slot >= 0) fwd_epilogue<EPI_RELU, true, DBG, X>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc, bias_g);
+    else fwd_epilogue<EPI_RELU, false, DBG, X>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc, bias_g);
   } else if (st.epi == EPI_LINEAR_SIGMA) {
-    fwd_epilogue<EPI_LINEAR_SIGMA, false, DBG>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc);
+    fwd_epilogue<EPI_LINEAR_SIGMA, false, DBG, X>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc, bias_g);
   } else {
-    fwd_epilogue<EPI_RGB_HEAD, false, DBG>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc);
+    fwd_epilogue<EPI_RGB_HEAD, false, DBG, X>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc, bias_g);
   }
 }
 
 // ------------------------------------------------------------------------------------------ forward kernel
+template <bool X>
 __global__ void __launch_bounds__(kThreads, 1) tc_fwd_kernel(const __grid_constant__ Params p) {
+  using MP = Map<X>;
   extern __shared__ uint8_t smem_raw[];
-  Smem sm;
+  SmemT<X> sm;
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint32_t tmem_base;
-  {  // static tables: every layer's bias, the sigma / rgb head weights
+  {  // static tables: every layer's bias (plain mode), the sigma / rgb head weights
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* b = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-    float* bias_s = reinterpret_cast<float*>(b + SM_TAB + TAB_BIAS);
-    for (int i = tid; i < p.prog.n_steps * 256; i += kThreads) {
-      const int si = i >> 8, c = i & 255;
-      bias_s[i] = c < p.prog.s[si].n_out ? __ldg(p.prog.s[si].bias + c) : 0.f;
+    if (!X) {
+      float* bias_s = reinterpret_cast<float*>(b + MP::SM_TAB + MP::TAB_BIAS);
+      for (int i = tid; i < p.prog.n_steps * 256; i += kThreads) {
+        const int si = i >> 8, c = i & 255;
+        bias_s[i] = c < p.prog.s[si].n_out ? __ldg(p.prog.s[si].bias + c) : 0.f;
+      }
     }
-    float* wsig_s = reinterpret_cast<float*>(b + SM_TAB + TAB_WSIG);
+    float* wsig_s = reinterpret_cast<float*>(b + MP::SM_TAB + MP::TAB_WSIG);
     for (int i = tid; i < 256; i += kThreads) wsig_s[i] = __ldg(p.wsig + i);
-    float* w2_s = reinterpret_cast<float*>(b + SM_TAB + TAB_W2);
+    float* w2_s = reinterpret_cast<float*>(b + MP::SM_TAB + MP::TAB_W2);
     for (int i = tid; i < 384; i += kThreads) w2_s[i] = __ldg(p.w2 + i);
   }
   kernel_prologue(sm, smem_raw, tid, warp, tmem_base);
-  const int64_t n_tiles = (p.M + kTileM - 1) / kTileM;
+  const int64_t M = rows_present(p);
+  const int64_t n_tiles = (M + kTileM - 1) / kTileM;
 
   if (warp == 8) {
-    producer_loop(p, sm, n_tiles, lane);
+    producer_loop<X>(p, sm, n_tiles, lane);
   } else if (warp == 9) {
-    mma_loop(p, sm, n_tiles, lane, tmem_base);
+    mma_loop<X>(p, sm, n_tiles, lane, tmem_base);
   } else {
     EpiCtx e;
     e.lane = lane; e.hh = warp >> 2; e.row = (warp & 3u) * 32u + lane; e.lane_field = ((warp & 3u) * 32u) << 16;
     e.tmem_base = tmem_base;
-    float* sig_part = sm.tab(TAB_PART);          // [2][128]
-    float* rgb_part = sm.tab(TAB_PART) + 256;    // [2][128][3]
-    float* z_s = sm.tab(TAB_Z);
+    float* sig_part = sm.tab(MP::TAB_PART);          // [2][128]
+    float* rgb_part = sm.tab(MP::TAB_PART) + 256;    // [2][128][3]
+    float* z_s = sm.tab(MP::TAB_Z);
     uint32_t gstep = 0, acc_cnt[2] = {0, 0};
     const int nslots = p.prog.n_mask_slots;
     int64_t cur_obj = -1;
     // PE(xyz) of the first tile; later tiles are encoded one tile ahead (during the encoding_viewdir epilogue)
     if ((int64_t)blockIdx.x < n_tiles) {
       int64_t r0 = (int64_t)blockIdx.x * kTileM + e.row;
-      if (r0 > p.M - 1) r0 = p.M - 1;
+      if (r0 > M - 1) r0 = M - 1;
       const float x[3] = {__ldg(p.xyz + 3 * r0), __ldg(p.xyz + 3 * r0 + 1), __ldg(p.xyz + 3 * r0 + 2)};
-      write_pe_row<10>(sm.chunk(4), e.row, e.hh, x);
+      write_pe<10, X>(sm, e.row, e.hh, x);
       publish_chunk(sm, 4, lane);
     }
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       e.grow = tile * kTileM + e.row;
-      e.valid = e.grow < p.M;
-      const int64_t crow = e.valid ? e.grow : p.M - 1;
+      e.valid = e.grow < M;
+      const int64_t crow = e.valid ? e.grow : M - 1;
       const int64_t next_tile = tile + gridDim.x;
       float xn[3] = {0.f, 0.f, 0.f};
       if (next_tile < n_tiles) {  // prefetch the next tile's coordinates: consumed ~5 layers from now
         int64_t rn = next_tile * kTileM + e.row;
-        if (rn > p.M - 1) rn = p.M - 1;
+        if (rn > M - 1) rn = M - 1;
         xn[0] = __ldg(p.xyz + 3 * rn); xn[1] = __ldg(p.xyz + 3 * rn + 1); xn[2] = __ldg(p.xyz + 3 * rn + 2);
       }
       const float dir[3] = {__ldg(p.viewdir + 3 * crow), __ldg(p.viewdir + 3 * crow + 1), __ldg(p.viewdir + 3 * crow + 2)};
-      const int64_t obj = (tile * kTileM) / p.rows_per_obj;   // tiles never straddle objects (checked on the host)
-      if (obj != cur_obj) {  // (re)load the per-object latent vectors; all epilogue warps are between tiles here
+      const int64_t obj = obj_of_tile(p, tile);   // tiles never straddle objects (checked on the host)
+      if (!X && obj != cur_obj) {  // (re)load the per-object latent vectors; all epilogue warps are between tiles here
         cur_obj = obj;
         for (int i = tid; i < p.n_latent * 256; i += 256)
           z_s[i] = __ldg(p.zlat + ((size_t)(i >> 8) * p.B + obj) * 256 + (i & 255));
@@ -339,18 +482,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_fwd_kernel(const __grid_consta
       for (int si = 0; si < p.prog.n_steps; ++si, ++gstep) {
         const Step& st = p.prog.s[si];
         const uint32_t half = gstep & 1u;
+        const float* bias_g = nullptr;
+        if (X) bias_g = st.latent_slot >= 0 ? p.zlat + ((size_t)st.latent_slot * p.B + obj) * 256 : st.bias;
         mbar_wait(sm.bar(BAR_ACC + half), acc_cnt[half] & 1u);
         acc_cnt[half]++;
         tc_fence_after();
         if (si == 0) {  // layer 0's MMAs are done with PE(xyz): the AUX chunk now takes PE(viewdir)
-          write_pe_row<4>(sm.chunk(4), e.row, e.hh, dir);
+          write_pe<4, X>(sm, e.row, e.hh, dir);
           publish_chunk(sm, 4, lane);
         } else if (si == p.ev_step && next_tile < n_tiles) {  // encoding_viewdir's MMAs are done with PE(viewdir)
-          write_pe_row<10>(sm.chunk(4), e.row, e.hh, xn);
+          write_pe<10, X>(sm, e.row, e.hh, xn);
           publish_chunk(sm, 4, lane);
         }
-        if (p.dbg != nullptr) fwd_epilogue_dispatch<true>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc);
-        else fwd_epilogue_dispatch<false>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc);
+        if (p.dbg != nullptr) fwd_epilogue_dispatch<true, X>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc, bias_g);
+        else fwd_epilogue_dispatch<false, X>(p, sm, st, si, half, e, mask_tile, sig_acc, rgb_acc, bias_g);
         tc_fence_before();
       }
       sig_part[e.hh * 128 + e.row] = sig_acc;
@@ -379,13 +524,43 @@ __device__ __forceinline__ uint32_t mask_word(const uint32_t* mask_tile, int slo
 
 // acc = gradient w.r.t. the layer's input.  Optional: per-object column sums of it (latent gradient); then mask by the
 // producing layer's ReLU bits and hand on as the next A operand.  EV: add the sigma-head gradient first, no mask.
-template <bool EV, bool COLSUM, bool MASK, bool PRODUCE>
-__device__ __forceinline__ void bwd_epilogue(const Smem& sm, const Step& st, uint32_t half, const EpiCtx& e,
-                                             const uint32_t* mask_tile, float gsp) {
-  const float* wsig_s = sm.tab(TAB_WSIG);
-  float* colsum = sm.tab(TAB_BIAS);
+// Split mode: acc is the row's gradient in units of 2^rexp (times the weight scale); gsp is the TRUE sigma-head gradient.  Gradients
+// shrink (or grow) by a factor per layer, and an fp16 pair only resolves 2^-25 absolutely, so every layer re-centres the row: both
+// threads of a row read the same 32 sample columns of the accumulator, take the power of two that brings their largest magnitude
+// to [4, 8) (13 bits of headroom above the sample for the other columns) and fold it into rexp -- exact, and identical in both threads.
+template <bool EV, bool COLSUM, bool MASK, bool PRODUCE, bool X>
+__device__ __forceinline__ void bwd_epilogue(const SmemT<X>& sm, const Step& st, uint32_t half, const EpiCtx& e,
+                                             const uint32_t* mask_tile, float gsp, int& rexp) {
+  using MP = Map<X>;
+  const float* wsig_s = sm.tab(MP::TAB_WSIG);
+  float* colsum = sm.tab(MP::TAB_BIAS);
   const uint32_t t0 = e.tmem_base + half * 256u + e.hh * 32u + e.lane_field;
   uint32_t ra[32], rb[32];
+  float in_scale = 1.f, a_scale = 1.f, row_scale = 1.f;   // accumulator -> v; v -> A operand; v -> true gradient
+  if (X) {
+    in_scale = kWScaleInv;
+    row_scale = ldexpf(1.f, rexp);
+    if (EV) gsp *= ldexpf(1.f, -rexp);
+    if (PRODUCE) {
+      tmem_ld32(e.tmem_base + half * 256u + e.lane_field, ra);   // columns 0..31 of the row: the sample both of its threads see
+      float m = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float v = __uint_as_float(ra[i]) * kWScaleInv;
+        if (EV) v += gsp * wsig_s[i];
+        m = fmaxf(m, fabsf(v));
+      }
+      if (m > 0.f && m < 3.0e38f) {
+        int ex;
+        frexpf(m, &ex);
+        int shift = ex - 3;                                    // m * 2^-shift in [4, 8)
+        if (rexp + shift > 120) shift = 120 - rexp;
+        if (rexp + shift < -120) shift = -120 - rexp;
+        a_scale = ldexpf(1.f, -shift);
+        rexp += shift;
+      }
+    }
+  }
   tmem_ld32_issue(t0, ra);
   uint32_t mw_next = 0xffffffffu;
   if (MASK) mw_next = mask_word(mask_tile, st.mask_slot, (int)e.hh, e.row);
@@ -399,7 +574,7 @@ __device__ __forceinline__ void bwd_epilogue(const Smem& sm, const Step& st, uin
     const int col0 = c * 64 + (int)e.hh * 32;
     float v[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 32; ++i) v[i] = X ? __uint_as_float(r[i]) * in_scale : __uint_as_float(r[i]);
     if (EV) {
 #pragma unroll
       for (int i4 = 0; i4 < 8; ++i4) {
@@ -408,84 +583,107 @@ __device__ __forceinline__ void bwd_epilogue(const Smem& sm, const Step& st, uin
       }
     }
     if (PRODUCE) {
-      uint32_t pk[16];
+      RowPack<X> rp;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float a = (!MASK || mask_bit(mw, 2 * i)) ? v[2 * i] : 0.f;
-        const float b = (!MASK || mask_bit(mw, 2 * i + 1)) ? v[2 * i + 1] : 0.f;
-        pk[i] = pack_bf16(a, b);
+        float a = (!MASK || mask_bit(mw, 2 * i)) ? v[2 * i] : 0.f;
+        float b = (!MASK || mask_bit(mw, 2 * i + 1)) ? v[2 * i + 1] : 0.f;
+        if (X) { a *= a_scale; b *= a_scale; }
+        rp.set(i, a, b);
       }
-      store_row32(sm.chunk(c), e.row, e.hh, pk);
+      rp.store(sm, c, e.row, e.hh);
       publish_chunk(sm, c, e.lane);   // the MMA warp can start the next layer on this chunk while we reduce below
     }
     if (COLSUM) {
+      if (X) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= row_scale;
+      }
       const float cs = warp_colsum32(v, e.lane);
       atomicAdd(colsum + st.latent_slot * 256 + col0 + e.lane, cs);
     }
   }
 }
 
-__device__ __forceinline__ void bwd_epilogue_dispatch(const Smem& sm, const Step& st, uint32_t half, const EpiCtx& e,
-                                                      const uint32_t* mask_tile, float gsp) {
+template <bool X>
+__device__ __forceinline__ void bwd_epilogue_dispatch(const SmemT<X>& sm, const Step& st, uint32_t half, const EpiCtx& e,
+                                                      const uint32_t* mask_tile, float gsp, int& rexp) {
   if (st.epi == EPI_B_EV) {
-    bwd_epilogue<true, false, false, true>(sm, st, half, e, mask_tile, gsp);
+    bwd_epilogue<true, false, false, true, X>(sm, st, half, e, mask_tile, gsp, rexp);
   } else if (st.latent_slot >= 0) {
-    if (st.produce_a) bwd_epilogue<false, true, true, true>(sm, st, half, e, mask_tile, gsp);
-    else bwd_epilogue<false, true, false, false>(sm, st, half, e, mask_tile, gsp);
+    if (st.produce_a) bwd_epilogue<false, true, true, true, X>(sm, st, half, e, mask_tile, gsp, rexp);
+    else bwd_epilogue<false, true, false, false, X>(sm, st, half, e, mask_tile, gsp, rexp);
   } else {
-    bwd_epilogue<false, false, true, true>(sm, st, half, e, mask_tile, gsp);
+    bwd_epilogue<false, false, true, true, X>(sm, st, half, e, mask_tile, gsp, rexp);
   }
 }
 
 // ------------------------------------------------------------------------------------------ backward kernel
+template <bool X>
 __global__ void __launch_bounds__(kThreads, 1) tc_bwd_kernel(const __grid_constant__ Params p) {
+  using MP = Map<X>;
   extern __shared__ uint8_t smem_raw[];
-  Smem sm;
+  SmemT<X> sm;
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint32_t tmem_base;
   {
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* b = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-    float* colsum0 = reinterpret_cast<float*>(b + SM_TAB + TAB_BIAS);
+    float* colsum0 = reinterpret_cast<float*>(b + MP::SM_TAB + MP::TAB_BIAS);
     for (uint32_t i = tid; i < kMaxLatentSlots * 256; i += kThreads) colsum0[i] = 0.f;
-    float* wsig_s = reinterpret_cast<float*>(b + SM_TAB + TAB_WSIG);
+    float* wsig_s = reinterpret_cast<float*>(b + MP::SM_TAB + MP::TAB_WSIG);
     for (int i = tid; i < 256; i += kThreads) wsig_s[i] = __ldg(p.wsig + i);
-    float* w2_s = reinterpret_cast<float*>(b + SM_TAB + TAB_W2);
+    float* w2_s = reinterpret_cast<float*>(b + MP::SM_TAB + MP::TAB_W2);
     for (int i = tid; i < 384; i += kThreads) w2_s[i] = __ldg(p.w2 + i);
   }
   kernel_prologue(sm, smem_raw, tid, warp, tmem_base);
-  const int64_t n_tiles = (p.M + kTileM - 1) / kTileM;
+  const int64_t M = rows_present(p);
+  const int64_t n_tiles = (M + kTileM - 1) / kTileM;
 
   if (warp == 8) {
-    producer_loop(p, sm, n_tiles, lane);
+    producer_loop<X>(p, sm, n_tiles, lane);
   } else if (warp == 9) {
-    mma_loop(p, sm, n_tiles, lane, tmem_base);
+    mma_loop<X>(p, sm, n_tiles, lane, tmem_base);
   } else {
     EpiCtx e;
     e.lane = lane; e.hh = warp >> 2; e.row = (warp & 3u) * 32u + lane; e.lane_field = ((warp & 3u) * 32u) << 16;
     e.tmem_base = tmem_base;
-    float* xyz_part = sm.tab(TAB_PART);          // [2][128][3]
-    float* colsum = sm.tab(TAB_BIAS);            // [slots][256]
-    const float* w2_s = sm.tab(TAB_W2);
+    float* xyz_part = sm.tab(MP::TAB_PART);          // [2][128][3]
+    float* colsum = sm.tab(MP::TAB_BIAS);            // [slots][256]
+    const float* w2_s = sm.tab(MP::TAB_W2);
     uint32_t gstep = 0, acc_cnt[2] = {0, 0};
     const int nslots = p.prog.n_mask_slots;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       e.grow = tile * kTileM + e.row;
-      e.valid = e.grow < p.M;
-      const int64_t crow = e.valid ? e.grow : p.M - 1;
-      const int64_t obj = (tile * kTileM) / p.rows_per_obj;  // tiles never straddle objects (checked on the host)
+      e.valid = e.grow < M;
+      const int64_t crow = e.valid ? e.grow : M - 1;
+      const int64_t obj = obj_of_tile(p, tile);  // tiles never straddle objects (checked on the host)
       const uint32_t* mask_tile = p.masks + (size_t)tile * nslots * 8 * 128;
       const float gsg = e.valid ? __ldg(p.g_sigma + e.grow) : 0.f;
-      const float gsp = gsg * (-expm1f(-__ldg(p.sigma_in + crow)));   // d softplus = 1 - exp(-softplus)
+      float gsp = gsg * (-expm1f(-__ldg(p.sigma_in + crow)));   // d softplus = 1 - exp(-softplus)
+      float g3[3] = {0.f, 0.f, 0.f};
+      if (e.valid) { g3[0] = __ldg(p.g_rgb + 3 * e.grow); g3[1] = __ldg(p.g_rgb + 3 * e.grow + 1); g3[2] = __ldg(p.g_rgb + 3 * e.grow + 2); }
+      // split mode: the row's gradient is carried in units of 2^rexp (exact; the pass is linear in it): start with the upstream
+      // gradient at [16, 32)
+      int rexp = 0;
+      if (X) {
+        const float m = fmaxf(fmaxf(fabsf(gsp), fabsf(g3[0])), fmaxf(fabsf(g3[1]), fabsf(g3[2])));
+        if (m > 0.f && m < 3.0e38f) {
+          int ex;
+          frexpf(m, &ex);
+          ex = ex < -100 ? -100 : (ex > 100 ? 100 : ex);
+          rexp = ex - 5;
+          const float inv = ldexpf(1.f, -rexp);
+          g3[0] *= inv; g3[1] *= inv; g3[2] *= inv;
+        }
+      }
       // ---- prologue: d pre-activation of rgb.0 = (g_rgb W2) * mask -> A chunks 0,1 (128 columns)
       {
-        float g3[3] = {0.f, 0.f, 0.f};
-        if (e.valid) { g3[0] = __ldg(p.g_rgb + 3 * e.grow); g3[1] = __ldg(p.g_rgb + 3 * e.grow + 1); g3[2] = __ldg(p.g_rgb + 3 * e.grow + 2); }
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           const int col0 = c * 64 + (int)e.hh * 32;
           const uint32_t mw = mask_word(mask_tile, p.r0_mask_slot, c * 2 + e.hh, e.row);
-          uint32_t pk[16];
+          RowPack<X> rp;
 #pragma unroll
           for (int i4 = 0; i4 < 8; ++i4) {
             const float4 w0 = *reinterpret_cast<const float4*>(w2_s + col0 + 4 * i4);
@@ -495,10 +693,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_kernel(const __grid_consta
                           g3[0] * w0.z + g3[1] * w1.z + g3[2] * w2.z, g3[0] * w0.w + g3[1] * w1.w + g3[2] * w2.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) if (!mask_bit(mw, 4 * i4 + u)) v[u] = 0.f;
-            pk[2 * i4] = pack_bf16(v[0], v[1]);
-            pk[2 * i4 + 1] = pack_bf16(v[2], v[3]);
+            rp.set(2 * i4, v[0], v[1]);
+            rp.set(2 * i4 + 1, v[2], v[3]);
           }
-          store_row32(sm.chunk(c), e.row, e.hh, pk);
+          rp.store(sm, c, e.row, e.hh);
           publish_chunk(sm, c, lane);
         }
       }
@@ -508,13 +706,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_kernel(const __grid_consta
         mbar_wait(sm.bar(BAR_ACC + half), acc_cnt[half] & 1u);
         acc_cnt[half]++;
         tc_fence_after();
+        const float out_scale = X ? ldexpf(kWScaleInv, rexp) : 1.f;   // accumulator -> true gradient
         if (st.epi == EPI_B_XYZ) {
           // acc = d PE(xyz) (64 columns): fold to d xyz.  g_x = g_0 + sum_f 2^f (g_sin,f cos_f - g_cos,f sin_f)
           uint32_t r[32];
           tmem_ld32(e.tmem_base + half * 256u + e.hh * 32u + e.lane_field, r);
           const float x[3] = {__ldg(p.xyz + 3 * crow), __ldg(p.xyz + 3 * crow + 1), __ldg(p.xyz + 3 * crow + 2)};
           float s[10][3], c[10][3];
-          trig_ladder<10>(x, s, c);
+          trig_ladder<10, X>(x, s, c);
           float g[3] = {0.f, 0.f, 0.f};
           if (e.hh == 0) {  // columns 0..31: x (0-2), sin f=0..8 (3-29), sin f=9 a=0,1 (30,31)
 #pragma unroll
@@ -533,7 +732,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_kernel(const __grid_consta
             }
           }
 #pragma unroll
-          for (int a = 0; a < 3; ++a) xyz_part[(e.hh * 128 + e.row) * 3 + a] = g[a];
+          for (int a = 0; a < 3; ++a) xyz_part[(e.hh * 128 + e.row) * 3 + a] = g[a] * out_scale;
           tc_fence_before();
           continue;
         }
@@ -543,7 +742,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_kernel(const __grid_consta
           tmem_ld32(e.tmem_base + (half ^ 1u) * 256u + e.lane_field, r);
           const float d[3] = {__ldg(p.viewdir + 3 * crow), __ldg(p.viewdir + 3 * crow + 1), __ldg(p.viewdir + 3 * crow + 2)};
           float s[4][3], c[4][3];
-          trig_ladder<4>(d, s, c);
+          trig_ladder<4, X>(d, s, c);
           float g[3] = {0.f, 0.f, 0.f};
 #pragma unroll
           for (int i = 0; i < 27; ++i) {
@@ -552,14 +751,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_kernel(const __grid_consta
             else if (i < 15) { const int f = (i - 3) / 3, a = (i - 3) % 3; g[a] += gv * (float)(1 << f) * c[f][a]; }
             else { const int f = (i - 15) / 3, a = (i - 15) % 3; g[a] -= gv * (float)(1 << f) * s[f][a]; }
           }
-          if (e.valid && p.g_viewdir) { p.g_viewdir[3 * e.grow] = g[0]; p.g_viewdir[3 * e.grow + 1] = g[1]; p.g_viewdir[3 * e.grow + 2] = g[2]; }
+          if (e.valid && p.g_viewdir) {
+            p.g_viewdir[3 * e.grow] = g[0] * out_scale; p.g_viewdir[3 * e.grow + 1] = g[1] * out_scale; p.g_viewdir[3 * e.grow + 2] = g[2] * out_scale;
+          }
         }
-        bwd_epilogue_dispatch(sm, st, half, e, mask_tile, gsp);
+        bwd_epilogue_dispatch<X>(sm, st, half, e, mask_tile, gsp, rexp);
         tc_fence_before();
       }
       // ---- tile end: d xyz, and flush the latent column sums when the next tile belongs to another object
       const int64_t next = tile + gridDim.x;
-      const bool flush = next >= n_tiles || (next * kTileM) / p.rows_per_obj != obj;
+      const bool flush = next >= n_tiles || obj_of_tile(p, next) != obj;
       epi_bar_sync();
       if (p.g_xyz != nullptr && e.hh == 0 && e.valid) {
 #pragma unroll
@@ -583,22 +784,30 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_kernel(const __grid_consta
 // ------------------------------------------------------------------------------------------ weight packing
 struct PackJob {
   const float* src; int ld; int transposed; int n_valid; int n_pad; int k0; int k_limit; uint32_t dst_off;
+  int n0;      // first output row (split mode: N half)
+  int part;    // -1: bf16 image; 0 / 1: fp16 hi / lo image of kWScale * w
 };
 constexpr int kJobsPerLaunch = 64;
 struct PackJobs { int n; PackJob j[kJobsPerLaunch]; };
 
-// one block per job: dst[n][k] (128B-swizzled rows of 64 bf16) = src'(n, k0 + k), zero outside the valid range
+// one block per job: dst[n][k] (128B-swizzled rows of 64 16-bit values) = src'(n0 + n, k0 + k), zero outside the valid range
 __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackJobs jobs, uint8_t* __restrict__ packed) {
   const PackJob& jb = jobs.j[blockIdx.x];
   for (int e = threadIdx.x; e < jb.n_pad * 64; e += blockDim.x) {
     int n, k;
     if (jb.transposed) { k = e / jb.n_pad; n = e % jb.n_pad; }  // consecutive threads walk the contiguous source dimension
     else { n = e / 64; k = e % 64; }
-    const int kg = jb.k0 + k;
+    const int kg = jb.k0 + k, ng = jb.n0 + n;
     float v = 0.f;
-    if (n < jb.n_valid && kg < jb.k_limit) v = jb.transposed ? jb.src[(size_t)kg * jb.ld + n] : jb.src[(size_t)n * jb.ld + kg];
+    if (ng < jb.n_valid && kg < jb.k_limit) v = jb.transposed ? jb.src[(size_t)kg * jb.ld + ng] : jb.src[(size_t)ng * jb.ld + kg];
     const uint32_t off = jb.dst_off + (uint32_t)n * 128u + ((((uint32_t)k >> 3) ^ ((uint32_t)n & 7u)) << 4) + ((uint32_t)k & 7u) * 2u;
-    *reinterpret_cast<__nv_bfloat16*>(packed + off) = __float2bfloat16_rn(v);
+    if (jb.part < 0) {
+      *reinterpret_cast<__nv_bfloat16*>(packed + off) = __float2bfloat16_rn(v);
+    } else {
+      const float x = v * kWScale;
+      const __half hi = __float2half_rn(x);
+      *reinterpret_cast<__half*>(packed + off) = jb.part == 0 ? hi : __float2half_rn(x - __half2float(hi));
+    }
   }
 }
 
@@ -621,18 +830,40 @@ struct TcPlan {
   std::vector<PackJob> jobs;
   uint32_t total_bytes = 0;
   int r0_slot = 0;
+  bool split = false;   // fp16 (hi, lo) weight images of the split-precision mode
 };
+
+// one 64-wide K chunk of an MMA group's B operand: columns [k0, k0 + 64) of `src`, valid below k_limit
+struct ChunkSrc { const float* src; int k0; int k_limit; };
+
+static void add_chunk_list(TcPlan& pl, const std::vector<ChunkSrc>& chunks, int ld, bool transposed, int n_valid, int n_pad,
+                           uint32_t* first_off) {
+  *first_off = pl.total_bytes;
+  PackJob j;
+  j.ld = ld; j.transposed = transposed ? 1 : 0; j.n_valid = n_valid;
+  const int nh = (pl.split && n_pad > 128) ? 128 : n_pad;
+  auto push = [&](const ChunkSrc& c, int n0, int part) {
+    j.src = c.src; j.k0 = c.k0; j.k_limit = c.k_limit; j.n_pad = nh; j.n0 = n0; j.part = part; j.dst_off = pl.total_bytes;
+    pl.jobs.push_back(j);
+    pl.total_bytes += (uint32_t)nh * 128u;
+  };
+  if (!pl.split) {
+    for (const ChunkSrc& c : chunks) push(c, 0, -1);
+    return;
+  }
+  // split mode, in the order the MMA warp consumes the stages: per N half every K chunk's (hi, lo) pair -- the correction
+  // products -- and then every K chunk's hi image once more -- the leading products
+  for (int n0 = 0; n0 < n_pad; n0 += nh) {
+    for (const ChunkSrc& c : chunks) { push(c, n0, 0); push(c, n0, 1); }
+    for (const ChunkSrc& c : chunks) push(c, n0, 0);
+  }
+}
 
 static void add_chunks(TcPlan& pl, const float* src, int ld, bool transposed, int n_valid, int n_pad, int k_limit, int n_chunks,
                        uint32_t* first_off) {
-  *first_off = pl.total_bytes;
-  for (int c = 0; c < n_chunks; ++c) {
-    PackJob j;
-    j.src = src; j.ld = ld; j.transposed = transposed ? 1 : 0; j.n_valid = n_valid; j.n_pad = n_pad; j.k0 = c * 64;
-    j.k_limit = k_limit; j.dst_off = pl.total_bytes;
-    pl.jobs.push_back(j);
-    pl.total_bytes += (uint32_t)n_pad * 128u;
-  }
+  std::vector<ChunkSrc> chunks;
+  for (int c = 0; c < n_chunks; ++c) chunks.push_back({src, c * 64, k_limit});
+  add_chunk_list(pl, chunks, ld, transposed, n_valid, n_pad, first_off);
 }
 
 static Step make_step(int epi, int n_out, int n_chunks, std::initializer_list<int> chunks, int mask_slot, int latent_slot,
@@ -646,8 +877,9 @@ static Step make_step(int epi, int n_out, int n_chunks, std::initializer_list<in
 }
 
 // Builds the forward / backward step programs and the weight-image packing jobs for the handle's current pointers.
-static TcPlan build_plan(const snb_handle_s* h) {
+static TcPlan build_plan(const snb_handle_s* h, bool split = false) {
   TcPlan pl;
+  pl.split = split;
   const int Bs = h->arch.shape_blocks, Bt = h->arch.texture_blocks, W = 256, dv = h->d_dir(), dx = h->d_xyz();
   const auto& ly = h->layers;
   const int slot_vv = Bs + 1, slot_r = Bs + Bt + 2;
@@ -669,9 +901,9 @@ static TcPlan build_plan(const snb_handle_s* h) {
     push(f, s);
     s = make_step(EPI_RELU, 256, 5, {4, 0, 1, 2, 3}, slot_vv, -1, 1, ly[h->iEV].b);
     {  // chunk 0 = the PE(viewdir) columns [W, W+dv) of encoding_viewdir, chunks 1..4 = its first W columns
-      add_chunks(pl, ly[h->iEV].w + W, W + dv, false, 256, 256, dv, 1, &s.w_off);
-      uint32_t dummy;
-      add_chunks(pl, ly[h->iEV].w, W + dv, false, 256, 256, W, 4, &dummy);
+      std::vector<ChunkSrc> chunks = {{ly[h->iEV].w + W, 0, dv}};
+      for (int c = 0; c < 4; ++c) chunks.push_back({ly[h->iEV].w, c * 64, W});
+      add_chunk_list(pl, chunks, W + dv, false, 256, 256, &s.w_off);
     }
     push(f, s);
     for (int j = 1; j <= Bt; ++j) {
@@ -743,6 +975,12 @@ static size_t v1_packed_bytes(const snb_handle_s* h) {
   if (h->v1_packed_bytes_cache == 0) h->v1_packed_bytes_cache = ((size_t)build_plan(h).total_bytes + 1024 + 1023) & ~size_t(1023);
   return h->v1_packed_bytes_cache;
 }
+// split-precision images: behind the first- and second-generation ones
+static size_t x3_packed_bytes(const snb_handle_s* h) {
+  if (h->x3_packed_bytes_cache == 0) h->x3_packed_bytes_cache = ((size_t)build_plan(h, true).total_bytes + 1024 + 1023) & ~size_t(1023);
+  return h->x3_packed_bytes_cache;
+}
+static size_t x3_packed_off(const snb_handle_s* h) { return (v1_packed_bytes(h) + tc2_packed_bytes(h) + 1023) & ~size_t(1023); }
 static bool use_v2(const snb_handle_s* h) {
   static const bool force_v1 = [] { const char* e = getenv("SNB_TC_V1"); return e && atoi(e) != 0; }();
   return !force_v1 && tc2_supported(h);
@@ -753,20 +991,23 @@ bool tc_two_tile_active(const snb_handle_s* h) { const char* why; return tc_supp
 size_t tc_packed_bytes(const snb_handle_s* h) {
   const char* why;
   if (!tc_supported(h, &why)) return 16;
-  return v1_packed_bytes(h) + tc2_packed_bytes(h);
+  return x3_packed_off(h) + x3_packed_bytes(h);
 }
 
 int tc_pack_weights(snb_handle_s* h, void* packed, cudaStream_t st) {
   const char* why = "";
   SNB_REQUIRE(tc_supported(h, &why), "snb_pack_weights: %s", why);
   SNB_REQUIRE(((uintptr_t)packed & 15) == 0, "snb_pack_weights: buffer must be 16-byte aligned");
-  TcPlan pl = build_plan(h);
-  for (size_t i = 0; i < pl.jobs.size(); i += kJobsPerLaunch) {
-    PackJobs jb;
-    jb.n = (int)std::min<size_t>(kJobsPerLaunch, pl.jobs.size() - i);
-    for (int k = 0; k < jb.n; ++k) jb.j[k] = pl.jobs[i + k];
-    pack_kernel<<<jb.n, 256, 0, st>>>(jb, (uint8_t*)packed);
-    SNB_LAUNCH_CHECK();
+  for (int split = 0; split < 2; ++split) {   // the bf16 images, then the fp16 (hi, lo) images of the split-precision mode
+    TcPlan pl = build_plan(h, split != 0);
+    uint8_t* dst = (uint8_t*)packed + (split ? x3_packed_off(h) : 0);
+    for (size_t i = 0; i < pl.jobs.size(); i += kJobsPerLaunch) {
+      PackJobs jb;
+      jb.n = (int)std::min<size_t>(kJobsPerLaunch, pl.jobs.size() - i);
+      for (int k = 0; k < jb.n; ++k) jb.j[k] = pl.jobs[i + k];
+      pack_kernel<<<jb.n, 256, 0, st>>>(jb, dst);
+      SNB_LAUNCH_CHECK();
+    }
   }
   if (tc2_supported(h) && tc2_pack_weights(h, (uint8_t*)packed + v1_packed_bytes(h), st)) return 1;
   h->packed = packed;
@@ -850,8 +1091,28 @@ struct ScopedKernelTimer {
 
 int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, void* ws, cudaStream_t st,
-               bool train, const int64_t* m_dev, const int32_t* tile_start, const rb::RowSrc* rs) {
+               bool train, const int64_t* m_dev, const int32_t* tile_start, const rb::RowSrc* rs, bool split) {
   if (tc_common_checks(h, M, B, "mlp_fwd(bf16)", tile_start != nullptr)) return 2;
+  if (split) {   // SNB_PREC_FP32_TC: fp16 (hi, lo) operands, three MMAs per product, on the one-tile kernels (frozen weights)
+    SNB_REQUIRE(!train && rs == nullptr && xyz != nullptr && viewdir != nullptr, "mlp_fwd(fp32_tc): frozen weights and explicit coordinates only");
+    SNB_REQUIRE(tile_start == nullptr || m_dev != nullptr, "mlp_fwd(fp32_tc): per-object tile offsets need a device-side row count");
+    float* ebias = (float*)((uint8_t*)ws + ws_zlat_bytes(h, B));
+    uint32_t* masks = (uint32_t*)((uint8_t*)ws + ws_masks_off(h, B));
+    if (latent_forward_fused(h, B, shape_latent, texture_latent, (float*)ws, ebias, st, nullptr)) return 1;
+    TcPlan pl = build_plan(h, true);
+    Params p;
+    fill_common(p, h, xyz, viewdir, M, B, ebias, masks);
+    p.packed = (const uint8_t*)h->packed + x3_packed_off(h);
+    p.m_dev = m_dev; p.tile_start = tile_start;
+    p.sigma = sigma; p.rgb = rgb; p.dbg = h->dbg_acts;
+    p.prog = pl.fwd;
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Map<true>::SM_ALLOC));
+    ScopedKernelTimer tm(st, h->timing_on);
+    tc_fwd_kernel<true><<<tc_grid(M), kThreads, Map<true>::SM_ALLOC, st>>>(p);
+    tm.stop(const_cast<snb_handle_s*>(h)->ev_fwd);
+    SNB_LAUNCH_CHECK();
+    return 0;
+  }
   SNB_REQUIRE(rs == nullptr || (tile_start != nullptr && rs->rays8 && rs->box && rs->z_steps && rs->jitter && rs->order && rs->counts),
               "mlp_fwd(bf16): a row source needs per-object tile offsets and all of its pointers");
   SNB_REQUIRE(rs != nullptr || (xyz != nullptr && viewdir != nullptr), "mlp_fwd(bf16): null coordinates");
@@ -879,9 +1140,9 @@ int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, in
   fill_common(p, h, xyz, viewdir, M, B, ebias, masks);
   p.sigma = sigma; p.rgb = rgb; p.dbg = h->dbg_acts;
   p.prog = pl.fwd;
-  SNB_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
+  SNB_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Map<false>::SM_ALLOC));
   ScopedKernelTimer tm(st, h->timing_on);
-  tc_fwd_kernel<<<tc_grid(M), kThreads, SM_ALLOC, st>>>(p);
+  tc_fwd_kernel<false><<<tc_grid(M), kThreads, Map<false>::SM_ALLOC, st>>>(p);
   tm.stop(const_cast<snb_handle_s*>(h)->ev_fwd);
   SNB_LAUNCH_CHECK();
   return 0;
@@ -891,8 +1152,31 @@ int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, i
                 const float* shape_latent, const float* texture_latent, const float* sigma, const float* g_sigma,
                 const float* g_rgb, const void* ws, void* scratch, float* g_xyz, float* g_viewdir, float* g_shape_latent,
                 float* g_texture_latent, float* const* g_weights, cudaStream_t st, bool train, const int64_t* m_dev,
-                const int32_t* tile_start) {
+                const int32_t* tile_start, bool split) {
   if (tc_common_checks(h, M, B, "mlp_bwd(bf16)", tile_start != nullptr)) return 2;
+  if (split) {
+    SNB_REQUIRE(!train && g_weights == nullptr, "mlp_bwd(fp32_tc): frozen weights only (weight gradients: precision='fp32' runs the FFMA back end)");
+    SNB_REQUIRE((g_xyz == nullptr) == (g_viewdir == nullptr), "mlp_bwd(fp32_tc): request both g_xyz and g_viewdir or neither");
+    SNB_REQUIRE(tile_start == nullptr || m_dev != nullptr, "mlp_bwd(fp32_tc): per-object tile offsets need a device-side row count");
+    const float* zlat = (const float*)ws;
+    uint32_t* masks = (uint32_t*)((uint8_t*)ws + ws_masks_off(h, B));
+    float* g_zlat = (float*)scratch;
+    SNB_CHECK_CUDA(cudaMemsetAsync(g_zlat, 0, ws_zlat_bytes(h, B), st));
+    TcPlan pl = build_plan(h, true);
+    Params p;
+    fill_common(p, h, xyz, viewdir, M, B, zlat, masks);
+    p.packed = (const uint8_t*)h->packed + x3_packed_off(h);
+    p.m_dev = m_dev; p.tile_start = tile_start;
+    p.sigma_in = sigma; p.g_sigma = g_sigma; p.g_rgb = g_rgb; p.g_xyz = g_xyz; p.g_viewdir = g_viewdir; p.g_zlat = g_zlat;
+    p.r0_mask_slot = pl.r0_slot;
+    p.prog = g_xyz ? pl.bwd_full : pl.bwd_noxyz;
+    SNB_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Map<true>::SM_ALLOC));
+    ScopedKernelTimer tm(st, h->timing_on);
+    tc_bwd_kernel<true><<<tc_grid(M), kThreads, Map<true>::SM_ALLOC, st>>>(p);
+    tm.stop(const_cast<snb_handle_s*>(h)->ev_bwd);
+    SNB_LAUNCH_CHECK();
+    return latent_backward_fused(h, B, zlat, g_zlat, g_shape_latent, g_texture_latent, st);
+  }
   SNB_REQUIRE(m_dev == nullptr || (use_v2(h) && (B == 1 || tile_start != nullptr)),
               "mlp_bwd(bf16): a device-side row count needs the two-tile kernels and one object (or per-object tile offsets)");
   SNB_REQUIRE(tile_start == nullptr || (use_v2(h) && m_dev != nullptr && !train), "mlp_bwd(bf16): per-object tile offsets need the two-tile kernels, frozen weights and a device-side row count");
@@ -936,9 +1220,9 @@ int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, i
   p.sigma_in = sigma; p.g_sigma = g_sigma; p.g_rgb = g_rgb; p.g_xyz = g_xyz; p.g_viewdir = g_viewdir; p.g_zlat = g_zlat;
   p.r0_mask_slot = pl.r0_slot;
   p.prog = g_xyz ? pl.bwd_full : pl.bwd_noxyz;
-  SNB_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC));
+  SNB_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Map<false>::SM_ALLOC));
   ScopedKernelTimer tm(st, h->timing_on);
-  tc_bwd_kernel<<<tc_grid(M), kThreads, SM_ALLOC, st>>>(p);
+  tc_bwd_kernel<false><<<tc_grid(M), kThreads, Map<false>::SM_ALLOC, st>>>(p);
   tm.stop(const_cast<snb_handle_s*>(h)->ev_bwd);
   SNB_LAUNCH_CHECK();
   return latent_backward_fused(h, B, zlat, g_zlat, g_shape_latent, g_texture_latent, st);

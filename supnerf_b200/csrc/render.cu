@@ -20,7 +20,9 @@ inline int64_t decoder_rows(snb_handle h, const snb_render_desc& d);
 // Miss-ray compaction (compact.cu) applies to the box render on the two-tile tensor-core decoder; SNB_NO_COMPACT=1 disables it.
 bool use_compaction(snb_handle h, const snb_render_desc& d) {
   static const bool off = [] { const char* e = getenv("SNB_NO_COMPACT"); return e && atoi(e) != 0; }();
-  return !off && d.mode == SNB_RENDER_BOX && d.precision != SNB_PREC_FP32 && tc_two_tile_active(h) && d.n_rays > 0;
+  if (off || d.mode != SNB_RENDER_BOX || d.n_rays <= 0) return false;
+  if (d.precision == SNB_PREC_FP32_TC) return true;   // the split-precision kernels take the device-side row count themselves
+  return d.precision != SNB_PREC_FP32 && tc_two_tile_active(h);
 }
 
 // forward workspace (kept for the backward): rays_o, viewdir (N,3) | xyz, vrep (M,3) | z_vals (M) | sigma (M) | rgb (M,3) | mlp ws
@@ -86,8 +88,8 @@ inline int64_t decoder_rows(snb_handle h, const snb_render_desc& d) {
 int check_desc(snb_handle h, const snb_render_desc* d, const char* who) {
   SNB_REQUIRE(h != nullptr && d != nullptr, "%s: null handle or descriptor", who);
   SNB_REQUIRE(d->n_rays >= 0 && d->n_samples >= 1, "%s: bad sizes", who);
-  SNB_REQUIRE(d->precision == SNB_PREC_FP32 || d->precision == SNB_PREC_BF16 || d->precision == SNB_PREC_BF16_TRAIN,
-              "%s: unknown precision %d", who, d->precision);
+  SNB_REQUIRE(d->precision == SNB_PREC_FP32 || d->precision == SNB_PREC_BF16 || d->precision == SNB_PREC_BF16_TRAIN ||
+              d->precision == SNB_PREC_FP32_TC, "%s: unknown precision %d", who, d->precision);
   SNB_REQUIRE(d->mode == SNB_RENDER_BOX || d->mode == SNB_RENDER_SHELL, "%s: unknown mode %d", who, d->mode);
   return 0;
 }
@@ -139,7 +141,7 @@ extern "C" int snb_render_fwd(snb_handle h, const snb_render_desc* d, const floa
     if (compact_plan(wsb + L.hit, N, d->n_samples, order, pos, counts, st)) return 1;
     if (compact_gather(F(ws, L.xyz), F(ws, L.vrep), order, counts, N, d->n_samples, F(ws, L.xyz_c), F(ws, L.vrep_c), st)) return 1;
     if (tc_forward(h, F(ws, L.xyz_c), F(ws, L.vrep_c), decoder_rows(h, *d), 1, shape_latent, texture_latent, F(ws, L.sigma_c), F(ws, L.rgb_c),
-                   wsb + L.mlp, st, d->precision == SNB_PREC_BF16_TRAIN, counts + 3)) return 1;
+                   wsb + L.mlp, st, d->precision == SNB_PREC_BF16_TRAIN, counts + 3, nullptr, nullptr, d->precision == SNB_PREC_FP32_TC)) return 1;
     if (compact_expand(F(ws, L.sigma_c), F(ws, L.rgb_c), wsb + L.hit, pos, counts, N, d->n_samples, F(ws, L.sigma), F(ws, L.rgb), st))
       return 1;
   } else if (snb_mlp_fwd(h, d->precision, F(ws, L.xyz), F(ws, L.vrep), M, 1, shape_latent, texture_latent, F(ws, L.sigma),
@@ -189,7 +191,7 @@ extern "C" int snb_render_bwd(snb_handle h, const snb_render_desc* d, const floa
     if (tc_backward(h, F(ws, L.xyz_c), F(ws, L.vrep_c), decoder_rows(h, *d), 1, shape_latent, texture_latent, F(ws, L.sigma_c), F(sc, G.g_sigma_c),
                     F(sc, G.g_rgb_c), wsb + L.mlp, static_cast<uint8_t*>(sc) + G.mlp, pose ? F(sc, G.g_xyz_c) : nullptr,
                     pose ? F(sc, G.g_vrep_c) : nullptr, g_shape_latent, g_texture_latent, g_weights, st,
-                    d->precision == SNB_PREC_BF16_TRAIN, counts + 3)) return 1;
+                    d->precision == SNB_PREC_BF16_TRAIN, counts + 3, nullptr, d->precision == SNB_PREC_FP32_TC)) return 1;
     if (!pose) return 0;
     if (sample_box_bwd_compact(F(ws, L.rays_o), F(ws, L.viewdir), z_steps, jitter, N, d->n_samples, d->half_diag, d->aabb_half,
                                F(sc, G.g_xyz_c), F(sc, G.g_vrep_c), F(sc, G.g_z), pos, counts, F(sc, G.g_rays_o), F(sc, G.g_viewdir), st))

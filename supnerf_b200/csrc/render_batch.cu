@@ -1028,7 +1028,8 @@ struct ShellScratch {
 int check_shell(snb_handle h, const snb_shell_batch_desc* d, const char* who) {
   SNB_REQUIRE(h != nullptr && d != nullptr, "%s: null handle or descriptor", who);
   SNB_REQUIRE(d->n_objs >= 1 && d->n_objs <= rb::kMaxObjs && d->rays_per_obj >= 1 && d->n_samples >= 1, "%s: bad sizes", who);
-  SNB_REQUIRE(d->precision == SNB_PREC_FP32 || d->precision == SNB_PREC_BF16, "%s: precision must be fp32 or bf16 (frozen weights)", who);
+  SNB_REQUIRE(d->precision == SNB_PREC_FP32 || d->precision == SNB_PREC_BF16 || d->precision == SNB_PREC_FP32_TC,
+              "%s: precision must be fp32, fp32_tc or bf16 (frozen weights)", who);
   SNB_REQUIRE((int64_t)d->n_objs * d->rays_per_obj * d->n_samples < ((int64_t)1 << 40), "%s: too many rows", who);
   return 0;
 }

@@ -3,6 +3,7 @@
 #pragma once
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdint.h>
 
@@ -111,6 +112,18 @@ __device__ __forceinline__ uint32_t umma_idesc(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// the same with A/B fp16 (format field 0): the split-precision mode's operands
+__device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t M, uint32_t N) { return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24); }
+
+// two fp32 values -> fp16x2 words of their leading parts and of the remainders: x = hi + lo up to 2^-22 |x| (lo normal) / 2^-25 (subnormal)
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -147,8 +160,9 @@ __device__ __forceinline__ void mask_shifts(uint32_t mw, uint32_t (&sh)[8]) {
 // byte offset of 16-byte unit `unit` (0..7) of row `row` inside a 128B-swizzled [rows][64] bf16 chunk
 __device__ __forceinline__ uint32_t swz(uint32_t row, uint32_t unit) { return row * 128u + ((unit ^ (row & 7u)) << 4); }
 
-// sin/cos(2^f x), f < DEG, by the double-angle recurrence from one accurate sincosf (error ~2^f * 1e-7: far below bf16)
-template <int DEG>
+// sin/cos(2^f x), f < DEG, by the double-angle recurrence from one accurate sincosf (error ~2^f * 1e-7: far below bf16), or --
+// ACCURATE, the split-precision (fp32-grade) mode -- one sincosf per frequency (2^f x is exact in fp32)
+template <int DEG, bool ACCURATE = false>
 __device__ __forceinline__ void trig_ladder(const float x[3], float s[DEG][3], float c[DEG][3]) {
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
@@ -157,8 +171,13 @@ __device__ __forceinline__ void trig_ladder(const float x[3], float s[DEG][3], f
     s[0][a] = sv; c[0][a] = cv;
 #pragma unroll
     for (int f = 1; f < DEG; ++f) {
-      s[f][a] = 2.f * s[f - 1][a] * c[f - 1][a];
-      c[f][a] = 1.f - 2.f * s[f - 1][a] * s[f - 1][a];
+      if (ACCURATE) {
+        sincosf(x[a] * (float)(1 << f), &sv, &cv);
+        s[f][a] = sv; c[f][a] = cv;
+      } else {
+        s[f][a] = 2.f * s[f - 1][a] * c[f - 1][a];
+        c[f][a] = 1.f - 2.f * s[f - 1][a] * s[f - 1][a];
+      }
     }
   }
 }
@@ -166,11 +185,10 @@ __device__ __forceinline__ void trig_ladder(const float x[3], float s[DEG][3], f
 // PE(x) (model_codenerf.py:4-10 column order) as one bf16 row of 64 columns; this thread owns the 4 units of its column half
 // `hh` (columns 32*hh .. 32*hh+31); columns >= 3+6*DEG are zero.  pe_half computes them (16 packed words), store_pe_half writes
 // them into a 128B-swizzled chunk -- split so that the arithmetic can run before the chunk is free.
-template <int DEG>
-__device__ __forceinline__ void pe_half(const float x[3], uint32_t hh, uint32_t (&pk)[16]) {
+template <int DEG, bool ACCURATE = false>
+__device__ __forceinline__ void pe_row_f32(const float x[3], float (&v)[64]) {
   float s[DEG][3], c[DEG][3];
-  trig_ladder<DEG>(x, s, c);
-  float v[64];
+  trig_ladder<DEG, ACCURATE>(x, s, c);
 #pragma unroll
   for (int i = 0; i < 64; ++i) v[i] = 0.f;
 #pragma unroll
@@ -182,8 +200,21 @@ __device__ __forceinline__ void pe_half(const float x[3], uint32_t hh, uint32_t 
       v[3 + 3 * f + a] = s[f][a];
       v[3 + 3 * DEG + 3 * f + a] = c[f][a];
     }
+}
+template <int DEG>
+__device__ __forceinline__ void pe_half(const float x[3], uint32_t hh, uint32_t (&pk)[16]) {
+  float v[64];
+  pe_row_f32<DEG>(x, v);
 #pragma unroll
   for (int i = 0; i < 16; ++i) pk[i] = hh ? pack_bf16(v[32 + 2 * i], v[33 + 2 * i]) : pack_bf16(v[2 * i], v[2 * i + 1]);
+}
+// the fp32 values of this thread's column half (split-precision mode packs them itself)
+template <int DEG>
+__device__ __forceinline__ void pe_half_f32(const float x[3], uint32_t hh, float (&o)[32]) {
+  float v[64];
+  pe_row_f32<DEG, true>(x, v);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) o[i] = hh ? v[32 + i] : v[i];
 }
 __device__ __forceinline__ void store_pe_half(uint8_t* aux, uint32_t row, uint32_t hh, const uint32_t (&pk)[16]) {
 #pragma unroll

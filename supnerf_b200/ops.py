@@ -3,6 +3,7 @@
 All tensors handed to the library are CUDA fp32 contiguous; outputs are fresh tensors attached to the
 autograd graph.  No function here has a CPU or eager-PyTorch fallback."""
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -13,6 +14,19 @@ from ._lib import check, f32c, on_device, ptr, require_cuda, stream_ptr
 WHITE_BKGD, SIGMA_RELU = 1, 2
 PREC = {"fp32": 0, "bf16": 1}
 PREC_BF16_TRAIN = 2  # selected automatically in bf16 mode when a weight requires grad (SNB_PREC_BF16_TRAIN)
+PREC_FP32_TC = 3     # selected automatically in fp32 mode when NO weight takes a gradient (SNB_PREC_FP32_TC): the same 1e-5 parity
+#                      on the tensor cores (two fp16 parts per operand, three MMAs per product), ~20x the FFMA back end's throughput
+FP32_TENSOR_CORES = os.environ.get("SNB_FP32_SIMT", "0") in ("", "0")   # False: fp32 mode always runs the FFMA kernels
+
+
+def _fp32_tc(handle, prec, rows_per_obj=None):
+    """fp32 mode with frozen weights -> the split-precision tensor-core kernels where they apply (CodeNeRF family, W = 256; dense row
+    counts a multiple of the 128-row tile).  rows_per_obj None: the caller's rows are compacted on the device (any count)."""
+    if prec != PREC["fp32"] or not FP32_TENSOR_CORES or not handle.tc_ok:
+        return prec
+    if rows_per_obj is not None and (rows_per_obj <= 0 or rows_per_obj % 128 != 0):
+        return prec
+    return PREC_FP32_TC
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -296,6 +310,7 @@ class DecoderHandle:
         self._packed_key = None
         self._keep = None
         self._frozen = None
+        self.tc_ok = lib.snb_packed_bytes(self.h) > 16      # the tensor-core back ends cover this architecture
 
     def __del__(self):
         try:
@@ -364,10 +379,14 @@ class _Decoder(torch.autograd.Function):
         m = xyz.numel() // 3
         dev = xyz.device
         handle.set_weights(weights)
+        if precision == PREC["fp32"] and not any(ctx.needs_input_grad[7:]):
+            precision = _fp32_tc(handle, precision, m // max(n_objs, 1))
         if precision == PREC["bf16"]:
             handle.ensure_packed(weights)
             if any(ctx.needs_input_grad[7:]):
                 precision = PREC_BF16_TRAIN   # keep the operand tiles: the backward produces the weight gradients on the tensor core
+        elif precision == PREC_FP32_TC:
+            handle.ensure_packed(weights)
         ws = torch.empty(lib.snb_mlp_workspace_bytes(handle.h, m, n_objs, precision), dtype=torch.uint8, device=dev)
         sigma = torch.empty(m, device=dev, dtype=torch.float32)
         rgb = torch.empty(m, 3, device=dev, dtype=torch.float32)
@@ -419,7 +438,9 @@ def decoder(handle, precision, xyz, viewdir, shape_latent, texture_latent, weigh
     n_objs = shape_latent.shape[0]
     prec = PREC[precision] if isinstance(precision, str) else precision
     m = xyz.shape[0]
-    if prec == PREC["bf16"] and n_objs == 1 and m % 128 != 0 and m > 0:
+    frozen = not (torch.is_grad_enabled() and any(w.requires_grad for w in weights))
+    tc_rows = prec == PREC["bf16"] or (frozen and _fp32_tc(handle, prec) == PREC_FP32_TC)
+    if tc_rows and n_objs == 1 and m % 128 != 0 and m > 0:
         # the tensor-core decoder works on 128-row tiles: pad a single object's rows with copies of its last row (outputs
         # sliced off again, so the copies get zero upstream gradient).  Batched latents must bring tile-aligned row counts.
         pad = 128 - m % 128
@@ -540,6 +561,10 @@ def _render_apply(handle, prec, n_samples, flags, geom, px, py, K, c2w, z_steps,
         if w.requires_grad:
             break
     else:
+        if geom[0] == "box" and os.environ.get("SNB_NO_COMPACT", "0") in ("", "0"):
+            prec = _fp32_tc(handle, prec)                                  # rows compacted on the device: any count
+        else:
+            prec = _fp32_tc(handle, prec, px.numel() * int(n_samples))    # dense rows
         handle.use_frozen(weights, prec)
         return _RenderBox.apply(handle, prec, n_samples, flags, geom, px, py, K, c2w, z_steps, jitter, shape_latent, texture_latent)
     return _RenderBox.apply(handle, prec, n_samples, flags, geom, px, py, K, c2w, z_steps, jitter, shape_latent, texture_latent, *weights)
@@ -709,7 +734,7 @@ def render_shell_batch(handle, precision, n_samples, shapenet_swap, px, py, K, c
         if w.requires_grad:
             raise RuntimeError("render_shell_batch: the batched render is the frozen-weight (refine) path; "
                                "model.requires_grad_(False), or render the objects one by one")
-    prec = PREC[precision] if isinstance(precision, str) else precision
+    prec = _fp32_tc(handle, PREC[precision] if isinstance(precision, str) else precision, px.shape[1] * int(n_samples))
     handle.use_frozen(weights, prec)
     return _RenderShellBatch.apply(handle, prec, n_samples, shapenet_swap, px, py, K, c2w, z_vals, obj_diag, shape_latent, texture_latent)
 

@@ -973,3 +973,46 @@ def test_batch_refiner_one_launch_set_equals_per_object_refiners(prec):
     assert parity_ok("graph_loss", cap.loss, bat.loss, 1e-4) and parity_ok("graph_shapecode", cap.shapecode, bat.shapecode, 2e-2)
     with pytest.raises(ValueError):
         cap.run(1)            # the jitter tables hold max_iters rows
+
+
+@pytest.mark.parametrize("blocks,B,n,S_", [((3, 1), 1, 128, 16), ((3, 1), 4, 64, 8), ((5, 3), 2, 32, 8), ((2, 1), 1, 37, 5)])
+def test_decoder_fp32_on_tensor_cores_vs_oracle(blocks, B, n, S_):
+    """SNB_PREC_FP32_TC (fp32 mode with frozen weights: two fp16 parts per MMA operand, three tcgen05 MMAs per product) against the fp32
+    oracle at the fp32 tolerance -- outputs, d xyz, d viewdir and the latent gradients -- with per-row upstream gradients spread over 12
+    orders of magnitude (compositing weights do that) and a few all-zero rows, and beside the FFMA back end's own errors."""
+    S = snb()
+    sd = oracle.init_codenerf_state(shape_blocks=blocks[0], texture_blocks=blocks[1], seed=blocks[0] + 20)
+    xyz, vd, shp, tex, up_s, up_c = _decoder_case(None, sd, None, B, n, S_, seed=blocks[0] * 10 + B + 3)
+    g = torch.Generator().manual_seed(9)
+    row_mag = 10.0 ** (torch.rand(B * n, S_, 1, generator=g) * 12 - 9)
+    row_mag[::7] = 0.0
+    up_s, up_c = up_s * row_mag, up_c * row_mag
+
+    def run_oracle(dt):
+        sdd = {k: v.to(dt) for k, v in sd.items()}
+        ins = [t.detach().clone().to(dt).requires_grad_() for t in (xyz, vd, shp, tex)]
+        sig, rgbs = oracle.codenerf_decoder(sdd, *ins)
+        ((sig * up_s.to(dt)).sum() + (rgbs * up_c.to(dt)).sum()).backward()
+        return [sig.detach(), rgbs.detach()] + [t.grad for t in ins]
+    ref, truth = run_oracle(torch.float32), run_oracle(torch.float64)
+    m = model_from_state(S.CodeNeRF, sd, shape_blocks=blocks[0], texture_blocks=blocks[1])
+    m.precision = "fp32"
+    m.requires_grad_(False)
+
+    def run_gpu(tensor_cores):
+        old = S.ops.FP32_TENSOR_CORES
+        S.ops.FP32_TENSOR_CORES = tensor_cores
+        try:
+            gin = [t.detach().clone().to(DEV).requires_grad_() for t in (xyz, vd, shp, tex)]
+            before = S._lib.load().snb_launch_count()
+            sig2, rgbs2 = m(*gin)
+            ((sig2 * up_s.to(DEV)).sum() + (rgbs2 * up_c.to(DEV)).sum()).backward()
+            return [sig2.detach(), rgbs2.detach()] + [t.grad for t in gin], S._lib.load().snb_launch_count() - before
+        finally:
+            S.ops.FP32_TENSOR_CORES = old
+    got, launches_tc = run_gpu(True)
+    simt, launches_simt = run_gpu(False)
+    assert launches_tc < launches_simt            # the tensor-core path is 2 decoder kernels + the latent layers, not one SGEMM per layer
+    for name, a, s_, r, t in zip(("sigma", "rgb", "g_xyz", "g_viewdir", "g_shape", "g_texture"), got, simt, ref, truth):
+        assert close_vs_truth(a, r, t, name="tc_" + name)[0], (name, close_vs_truth(a, r, t))
+        parity_ok("simt_" + name, s_, r, 1.0)     # ledger only: the FFMA back end's error on the same case
