@@ -165,7 +165,8 @@ def run_ours(args):
                           shp=o["shapecode"].to(dev).requires_grad_(), tex=o["texturecode"].to(dev).requires_grad_()))
         hobjs.append(dict(K=o["K"].pin_memory(), cam=o["cam_pose"].pin_memory(), wlh=o["wlh"], roi=o["roi"], img=o["img"].pin_memory(),
                           mask=o["mask_occ"].pin_memory(), shp=o["shapecode"].pin_memory(), tex=o["texturecode"].pin_memory()))
-    batched = args.batched and args.precision == "bf16"
+    fp32_tc = args.precision == "fp32" and snb.ops.FP32_TENSOR_CORES      # fp32 mode on the split-precision tensor-core kernels
+    batched = args.batched and (args.precision == "bf16" or fp32_tc)
 
     # Objects are independent.  Default: ALL 16 objects of the step go through ONE launch set (NeRFRenderer.render_batch ->
     # snb_render_batch_fwd / bwd, csrc/render_batch.cu; the batched refine losses).  --per-object keeps round 1's path: one fused
@@ -319,7 +320,7 @@ def run_ours(args):
             ro, vd = snb.utils.get_rays(d["K"], d["cam"], d["roi"], uv_steps=[IM_SZ, IM_SZ])
             hit = R.prepare_sampled_rays(ro, vd, d["wlh"])[3]
             nh = int(hit.sum().item())
-            compacted = args.precision == "bf16" and os.environ.get("SNB_NO_COMPACT", "0") in ("", "0")
+            compacted = (args.precision == "bf16" or fp32_tc) and os.environ.get("SNB_NO_COMPACT", "0") in ("", "0")
             pad = 256 if batched else 128
             rows_exec.append(-(-(nh * N_SAMPLES + (n_rays - nh)) // pad) * pad if compacted else rows_full)
             d["hit_fraction"] = nh / n_rays
@@ -336,7 +337,8 @@ def run_ours(args):
             roof[which] = dict(ms=avg, tflops=float(np.sum([2.0 * MAC_PER_SAMPLE * r_ for r_ in per_launch]) / (np.sum(ts) / 1e3) / 1e12),
                                n=len(ts), total_ms=float(np.sum(ts)), tflops_min=float(min(tf)), tflops_max=float(max(tf)))
     dom = max(roof, key=lambda k: roof[k]["total_ms"]) if roof else None
-    peak = pk["tf_sustained"] if args.precision == "bf16" else None
+    # fp32 on the tensor cores issues three fp16 MMAs per product: its ceiling in fp32-equivalent FLOP/s is a third of the MMA peak
+    peak = pk["tf_sustained"] if args.precision == "bf16" else (round(pk["tf_sustained"] / 3, 1) if fp32_tc else None)
     roofline = None
     traffic = None
     try:   # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture (scaled by samples per launch)
@@ -346,11 +348,12 @@ def run_ours(args):
     except Exception:
         traffic = None
     if dom:
-        roofline = {"bound": "tensor", "kernel": "tc2_%s_kernel" % dom if args.precision == "bf16" else "sgemm_kernel (fp32 SIMT)",
+        roofline = {"bound": "tensor", "kernel": "tc2_%s_kernel" % dom if args.precision == "bf16" else
+                    ("tc_%s_kernel<split> (SNB_PREC_FP32_TC: two fp16 parts per operand, three tcgen05 MMAs per product)" % dom if fp32_tc else "sgemm_kernel (fp32 SIMT)"),
                     "achieved": round(roof[dom]["tflops"], 2), "peak": peak, "unit": "TFLOP/s",
                     "frac": round(roof[dom]["tflops"] / peak, 4) if peak else None,
-                    "frac_vs_burst_peak": round(roof[dom]["tflops"] / pk["tf_burst"], 4) if args.precision == "bf16" else None, "traffic": traffic if args.precision == "bf16" else None,
-                    "peak_source": pk["source"] + ", sustained bf16", "flop_per_launch": flop_per_launch,
+                    "frac_vs_burst_peak": round(roof[dom]["tflops"] / (pk["tf_burst"] / (3 if fp32_tc else 1)), 4) if (args.precision == "bf16" or fp32_tc) else None, "traffic": traffic if args.precision == "bf16" else None,
+                    "peak_source": pk["source"] + (", sustained bf16" if not fp32_tc else ", sustained bf16 / 3 (three MMAs per fp32-grade product)"), "flop_per_launch": flop_per_launch,
                     "rows_executed_per_launch": rows, "rows_reference_semantics": rows_full, "hit_fraction": round(hit_fraction, 4),
                     "accounting": "achieved = 2 x 449664 MAC x rows the decoder EXECUTED (S per hit ray + 1 per miss ray, 128-row padded) / kernel time; "
                                   "value (rays/s) counts all rays, as the reference pushes all N x S rows through its MLP",
@@ -505,11 +508,13 @@ def run_ours(args):
         return
     # the CPU arm is timed on rank 0 at N = 1 only (at N > 1 the other ranks' processes share the host cores)
     # secondary measurements in child processes (N = 1 only): (a) the same step WITHOUT miss-ray compaction (SNB_NO_COMPACT=1: every
-    # one of the N x S rows goes through the decoder, the reference's semantics row for row), (b) the fp32 (1e-5 parity) back end
+    # one of the N x S rows goes through the decoder, the reference's semantics row for row), (b) the fp32 (1e-5 parity) mode on the
+    # split-precision tensor-core kernels (SNB_PREC_FP32_TC), (c) the same mode on the FFMA kernels (what weight training uses)
     extras = {}
     if world == 1 and not args.no_extras:
         for key, extra_args, env_add in (("dense_rows_no_compaction", ["--per-object", "--precision", "bf16"], {"SNB_NO_COMPACT": "1"}),
-                                         ("fp32_parity_mode", ["--per-object", "--precision", "fp32"], {})):
+                                         ("fp32_parity_mode", ["--precision", "fp32"], {}),
+                                         ("fp32_parity_mode_ffma", ["--per-object", "--precision", "fp32"], {"SNB_FP32_SIMT": "1"})):
             try:
                 env = dict(os.environ, **env_add)
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), "--skip-modes", "--no-extras", "--steps", "3", "--warmup", "3"] + extra_args,
@@ -517,7 +522,8 @@ def run_ours(args):
                 sub = json.loads(r.stdout.strip().splitlines()[-1])
                 extras[key] = {"value": sub["value"], "unit": "rays/s", "ms_per_step": sub["ms_per_step"], "e2e": sub["e2e"]["value"],
                                "precision": sub["config"]["precision"], "launch_sets": sub["config"].get("launch_sets"),
-                               "decoder_tflops": (sub.get("roofline") or {}).get("other"), "steps": sub["steps"]}
+                               "decoder_tflops": (sub.get("roofline") or {}).get("other"), "decoder_kernel": (sub.get("roofline") or {}).get("kernel"),
+                               "steps": sub["steps"]}
             except Exception as exc:   # noqa: BLE001
                 extras[key] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
     cpu = cpu_baseline(steps=3, warmup=1) if (world == 1 and not args.no_extras) else None
@@ -531,7 +537,9 @@ def run_ours(args):
                        "launch_sets": "one batched launch set for the 16 objects (snb_render_batch_fwd/bwd)" if batched else "one fused render per object",
                        "l2": "working set larger than L2 (126 MB): a step executes ~7 M decoder rows; per row 28 B of sample coordinates + z, 16 B of decoder outputs, as much again of gradients, and 224 B of ReLU mask bits (7 mask slots x 32 B) written by the forward and read by the backward: ~2 GB through HBM per step",
                        "hit_fraction": round(hit_fraction, 4),
-                       "precision": args.precision},
+                       "precision": args.precision,
+                       "decoder_arithmetic": "bf16 x bf16 -> fp32 (tcgen05)" if args.precision == "bf16" else
+                                             ("fp32-grade: fp16 (hi, lo) operand pairs, 3 tcgen05 MMAs per product -> fp32" if fp32_tc else "fp32 FFMA")},
             "e2e": {"value": round(e2e_value, 1), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
             "roofline_compositing": comp, "refine_iteration": refine_it, "gpu_launches": int(launches), "clocks": dict(clk.summary(), e2e_region=clk2.summary()), "roofline": roofline, "cpu_baseline": cpu, "gpu_eager_baseline": eager}

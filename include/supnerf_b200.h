@@ -237,13 +237,16 @@ typedef struct snb_batch_desc {
   int32_t n_objs;
   int32_t n_samples;
   int64_t rays_per_obj;
-  int32_t flags;        /* SNB_WHITE_BKGD | SNB_SIGMA_RELU [| SNB_BATCH_FUSED_SAMPLER] */
+  int32_t flags;        /* SNB_WHITE_BKGD | SNB_SIGMA_RELU [| SNB_BATCH_FUSED_SAMPLER | SNB_BATCH_FP32_TC] */
   int32_t reserved;
 } snb_batch_desc;
 /* opt-in: the forward decoder computes every row's stratified sample itself from the ray (32 B) and its jitter (4 B) -- no sampler
  * kernel and no per-row coordinates in HBM on the forward path; the backward re-materialises them in its scratch.  Bit-identical
  * results; measured ~0.7 % slower per forward + backward step than the default. */
 #define SNB_BATCH_FUSED_SAMPLER 4
+/* the decoder of the batched render in SNB_PREC_FP32_TC arithmetic (fp32-grade on the tensor cores) instead of bf16; not together
+ * with SNB_BATCH_FUSED_SAMPLER */
+#define SNB_BATCH_FP32_TC 8
 size_t snb_render_batch_workspace_bytes(snb_handle h, const snb_batch_desc* d);
 size_t snb_render_batch_scratch_bytes(snb_handle h, const snb_batch_desc* d);
 int snb_render_batch_fwd(snb_handle h, const snb_batch_desc* d, const float* px, const float* py, const float* K,

@@ -37,7 +37,20 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _flags_changed():
+    """True when the objects on disk were compiled with other flags (a tuning build left behind): everything is rebuilt."""
+    stamp = os.path.join(OBJ, "flags.txt")
+    want = " ".join(NVCC_FLAGS)
+    have = open(stamp).read() if os.path.exists(stamp) else None
+    if have == want:
+        return False
+    os.makedirs(OBJ, exist_ok=True)
+    open(stamp, "w").write(want)
+    return have is not None or os.path.exists(LIB) and bool(os.environ.get("SNB_EXTRA_NVCC_FLAGS"))
+
+
 def build(force=False, verbose=False):
+    force = force or _flags_changed()
     if not force and not needs_build():
         return LIB
     os.makedirs(OBJ, exist_ok=True)

@@ -27,6 +27,7 @@ int sample_box_bwd_compact(const float* rays_o, const float* viewdir, const floa
 // tile_start (optional, B + 1 device ints, ascending, even): object b owns the 128-row tiles [tile_start[b], tile_start[b+1]) -- the
 // batched render's objects own different numbers of rows (render_batch.cu)
 bool tc_two_tile_active(const snb_handle_s* h);
+bool tc_one_tile_supported(const snb_handle_s* h);   // the architecture the one-tile kernels (bf16 and split-precision) cover
 int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, int64_t M, int64_t B,
                const float* shape_latent, const float* texture_latent, float* sigma, float* rgb, void* ws, cudaStream_t st, bool train,
                const int64_t* m_dev, const int32_t* tile_start = nullptr, const rb::RowSrc* rs = nullptr, bool split = false);

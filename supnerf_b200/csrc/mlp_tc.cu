@@ -42,6 +42,12 @@ constexpr int kMaxLatentSlots = 8;
 // pair of physical chunks, the weight ring carries [128 n][64 k] stages (hi and lo of each N half, one after the other) and the
 // bias / latent tables are read through L1 instead (tools/experiments/split_precision_emulation.py: errors vs fp64 on par with fp32 FFMA).
 constexpr float kWScale = 256.f, kWScaleInv = 1.f / 256.f;
+// Order of the three products of a K chunk.  true: per N half all correction products first, then the leading ones (the hi weight image
+// is streamed twice: 3 stages per chunk and N half); false: chunk by chunk (2 stages).  See mma_loop.
+#ifndef SNB_SPLIT_CORR_FIRST
+#define SNB_SPLIT_CORR_FIRST 1
+#endif
+constexpr bool kCorrFirst = SNB_SPLIT_CORR_FIRST != 0;
 
 // shared-memory map (bytes from the 1024-aligned base)
 template <bool X> struct Map {
@@ -144,7 +150,7 @@ __device__ __forceinline__ void producer_loop(const Params& p, const SmemT<X>& s
         const uint32_t n = (uint32_t)(g == 0 ? st.n_out : st.n2_out);
         const uint32_t bytes = (X ? n_half_of(n) : n) * 128u;
         const uint32_t off0 = g == 0 ? st.w_off : st.w2_off;
-        const int entries = (int)st.n_chunks * (X ? 3 * (int)(n / n_half_of(n)) : 1);   // split: see mma_loop for the order
+        const int entries = (int)st.n_chunks * (X ? (kCorrFirst ? 3 : 2) * (int)(n / n_half_of(n)) : 1);   // split: see mma_loop for the order
         for (int e = 0; e < entries; ++e, ++it) {
           const uint32_t stage = it % kStages, ph = (it / kStages) & 1u;
           if (lane == 0) {
@@ -190,58 +196,51 @@ __device__ __forceinline__ void mma_loop(const Params& p, const SmemT<X>& sm, in
             __syncwarp();
           }
         } else {
-          // Per N half: FIRST every K chunk's correction products (a_lo * w_hi, a_hi * w_lo), THEN the leading products (a_hi * w_hi).
+          // FIRST every K chunk's correction products (a_lo * w_hi, a_hi * w_lo), THEN the leading products (a_hi * w_hi).
           // The tensor core truncates the fp32 accumulator after every instruction (an error of up to one ulp of its CURRENT
           // magnitude each): the 2 x 16 correction instructions run while it only holds the ~2^-11 times smaller correction sum, so
           // only the 16 leading instructions truncate at full scale.  (The hi image of every chunk is streamed twice for this.)
           const uint32_t nh_n = n_half_of(n), halves = n / nh_n;
           const uint32_t idesc = umma_idesc_f16(128, nh_n);
-          for (uint32_t nh = 0; nh < halves; ++nh) {
-            const uint32_t d = d_tmem + nh * 128u;
-            for (int kc = 0; kc < st.n_chunks; ++kc) {          // corrections
-              const int ac = st.a_chunk[kc];
-              const bool first_use = g == 0 && nh == 0;
-              const uint32_t a_hi = sm.chunk_u32(ac, 0), a_lo = sm.chunk_u32(ac, 1);
-              {  // W hi stage: a_lo * w_hi
-                const uint32_t stage = it % kStages, ph = (it / kStages) & 1u;
-                if (lane == 0) {
-                  if (first_use) mbar_wait(sm.bar(BAR_AREADY + ac), (a_phase >> ac) & 1u);
-                  mbar_wait(sm.bar(BAR_WFULL + stage), ph);
-                  tc_fence_after();
-                  const uint32_t b0 = sm.stage_u32(stage);
+          // one weight stage: `n_mma` products per 16-wide K step against it
+          auto run_stage = [&](uint32_t d, uint32_t a_first, uint32_t a_second, bool two, bool fresh, int wait_chunk) {
+            const uint32_t stage = it % kStages, ph = (it / kStages) & 1u;
+            if (lane == 0) {
+              if (wait_chunk >= 0) mbar_wait(sm.bar(BAR_AREADY + wait_chunk), (a_phase >> wait_chunk) & 1u);
+              mbar_wait(sm.bar(BAR_WFULL + stage), ph);
+              tc_fence_after();
+              const uint32_t b0 = sm.stage_u32(stage);
 #pragma unroll
-                  for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16(d, umma_desc(a_lo + kk * 32), umma_desc(b0 + kk * 32), idesc, (kc > 0 || kk > 0) ? 1u : 0u);
-                  umma_commit(sm.bar(BAR_WEMPTY + stage));
-                }
-                ++it;
+              for (int kk = 0; kk < 4; ++kk) {
+                umma_bf16(d, umma_desc(a_first + kk * 32), umma_desc(b0 + kk * 32), idesc, (fresh && kk == 0) ? 0u : 1u);
+                if (two) umma_bf16(d, umma_desc(a_second + kk * 32), umma_desc(b0 + kk * 32), idesc, 1u);
               }
-              {  // W lo stage: a_hi * w_lo
-                const uint32_t stage = it % kStages, ph = (it / kStages) & 1u;
-                if (lane == 0) {
-                  mbar_wait(sm.bar(BAR_WFULL + stage), ph);
-                  tc_fence_after();
-                  const uint32_t b0 = sm.stage_u32(stage);
-#pragma unroll
-                  for (int kk = 0; kk < 4; ++kk) umma_bf16(d, umma_desc(a_hi + kk * 32), umma_desc(b0 + kk * 32), idesc, 1u);
-                  umma_commit(sm.bar(BAR_WEMPTY + stage));
-                }
-                ++it;
-              }
-              if (first_use) a_phase ^= 1u << ac;
-              __syncwarp();
+              umma_commit(sm.bar(BAR_WEMPTY + stage));
             }
-            for (int kc = 0; kc < st.n_chunks; ++kc, ++it) {    // leading products: W hi stage again, a_hi * w_hi
-              const uint32_t a_hi = sm.chunk_u32(st.a_chunk[kc], 0);
-              const uint32_t stage = it % kStages, ph = (it / kStages) & 1u;
-              if (lane == 0) {
-                mbar_wait(sm.bar(BAR_WFULL + stage), ph);
-                tc_fence_after();
-                const uint32_t b0 = sm.stage_u32(stage);
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) umma_bf16(d, umma_desc(a_hi + kk * 32), umma_desc(b0 + kk * 32), idesc, 1u);
-                umma_commit(sm.bar(BAR_WEMPTY + stage));
+            ++it;
+          };
+          // K chunk by K chunk (a chunk's products start as soon as the epilogue has published it), both N halves per chunk
+          for (int kc = 0; kc < st.n_chunks; ++kc) {
+            const int ac = st.a_chunk[kc];
+            const uint32_t a_hi = sm.chunk_u32(ac, 0), a_lo = sm.chunk_u32(ac, 1);
+            for (uint32_t nh = 0; nh < halves; ++nh) {
+              const uint32_t d = d_tmem + nh * 128u;
+              const int wait_chunk = (g == 0 && nh == 0) ? ac : -1;
+              if (kCorrFirst) {   // corrections only: a_lo * w_hi, a_hi * w_lo
+                run_stage(d, a_lo, 0u, false, kc == 0, wait_chunk);
+                run_stage(d, a_hi, 0u, false, false, -1);
+              } else {            // all three: (a_lo, a_hi) * w_hi, a_hi * w_lo
+                run_stage(d, a_lo, a_hi, true, kc == 0, wait_chunk);
+                run_stage(d, a_hi, 0u, false, false, -1);
               }
+            }
+            if (g == 0) a_phase ^= 1u << ac;
+            __syncwarp();
+          }
+          if (kCorrFirst) {       // the leading products, once every correction sits in the (still small) accumulators
+            for (int kc = 0; kc < st.n_chunks; ++kc) {
+              const uint32_t a_hi = sm.chunk_u32(st.a_chunk[kc], 0);
+              for (uint32_t nh = 0; nh < halves; ++nh) run_stage(d_tmem + nh * 128u, a_hi, 0u, false, false, -1);
               __syncwarp();
             }
           }
@@ -851,12 +850,13 @@ static void add_chunk_list(TcPlan& pl, const std::vector<ChunkSrc>& chunks, int 
     for (const ChunkSrc& c : chunks) push(c, 0, -1);
     return;
   }
-  // split mode, in the order the MMA warp consumes the stages: per N half every K chunk's (hi, lo) pair -- the correction
-  // products -- and then every K chunk's hi image once more -- the leading products
-  for (int n0 = 0; n0 < n_pad; n0 += nh) {
-    for (const ChunkSrc& c : chunks) { push(c, n0, 0); push(c, n0, 1); }
-    for (const ChunkSrc& c : chunks) push(c, n0, 0);
-  }
+  // split mode, in the order the MMA warp consumes the stages: K chunk by K chunk, per N half the (hi, lo) pair; with corrections
+  // first, every chunk's hi image follows once more for the leading products
+  for (const ChunkSrc& c : chunks)
+    for (int n0 = 0; n0 < n_pad; n0 += nh) { push(c, n0, 0); push(c, n0, 1); }
+  if (kCorrFirst)
+    for (const ChunkSrc& c : chunks)
+      for (int n0 = 0; n0 < n_pad; n0 += nh) push(c, n0, 0);
 }
 
 static void add_chunks(TcPlan& pl, const float* src, int ld, bool transposed, int n_valid, int n_pad, int k_limit, int n_chunks,
@@ -986,6 +986,7 @@ static bool use_v2(const snb_handle_s* h) {
   return !force_v1 && tc2_supported(h);
 }
 
+bool tc_one_tile_supported(const snb_handle_s* h) { const char* why; return tc_supported(h, &why); }
 bool tc_two_tile_active(const snb_handle_s* h) { const char* why; return tc_supported(h, &why) && use_v2(h); }
 
 size_t tc_packed_bytes(const snb_handle_s* h) {

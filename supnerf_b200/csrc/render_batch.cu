@@ -789,8 +789,13 @@ int check_batch(snb_handle h, const snb_batch_desc* d, const char* who) {
               "%s: the batched render needs n_samples in {4, 8, ..., 128} (vectorised compositing)", who);
   SNB_REQUIRE(d->rays_per_obj < ((int64_t)1 << 30) && d->rays_per_obj * d->n_samples < ((int64_t)1 << 31) &&
               (int64_t)d->n_objs * d->rays_per_obj < ((int64_t)1 << 31), "%s: too many rays", who);
-  SNB_REQUIRE(tc_two_tile_active(h), "%s: the batched render runs on the two-tile tcgen05 decoder (CodeNeRF family, W = 256, "
-                                     "shape_blocks + texture_blocks <= 4); render the objects one by one for this architecture", who);
+  if (d->flags & SNB_BATCH_FP32_TC) {
+    SNB_REQUIRE(tc_one_tile_supported(h), "%s: the fp32 tensor-core decoder covers the CodeNeRF family with W = 256", who);
+    SNB_REQUIRE(!(d->flags & SNB_BATCH_FUSED_SAMPLER), "%s: SNB_BATCH_FP32_TC and SNB_BATCH_FUSED_SAMPLER exclude each other", who);
+  } else {
+    SNB_REQUIRE(tc_two_tile_active(h), "%s: the batched render runs on the two-tile tcgen05 decoder (CodeNeRF family, W = 256, "
+                                       "shape_blocks + texture_blocks <= 4); render the objects one by one for this architecture", who);
+  }
   return 0;
 }
 
@@ -863,7 +868,7 @@ extern "C" int snb_render_batch_fwd(snb_handle h, const snb_batch_desc* d, const
     SNB_LAUNCH_CHECK();
     if (tc_forward(h, at<float>(ws, L.xyz_c), at<float>(ws, L.vrep_c), L.Mmax, B, shape_latent, texture_latent, at<float>(ws, L.sigma_c),
                    at<float>(ws, L.rgb_c), at<uint8_t>(ws, L.mlp), st, false, &at<rb::Meta>(ws, L.meta)->total_rows,
-                   at<int32_t>(ws, L.tile_start)))
+                   at<int32_t>(ws, L.tile_start), nullptr, (d->flags & SNB_BATCH_FP32_TC) != 0))
       return 1;
     zsrc.z_c = at<float>(ws, L.z_c);
   }
@@ -925,7 +930,7 @@ extern "C" int snb_render_batch_bwd(snb_handle h, const snb_batch_desc* d, const
   if (tc_backward(h, xyz_c, vrep_c, L.Mmax, B, shape_latent, texture_latent, at<float>(ws, L.sigma_c),
                   at<float>(sc, G.g_sigma_c), at<float>(sc, G.g_rgb_c), at<uint8_t>(ws, L.mlp), at<uint8_t>(sc, G.mlp),
                   pose ? at<float>(sc, G.g_xyz_c) : nullptr, pose ? at<float>(sc, G.g_vrep_c) : nullptr, g_shape_latent, g_texture_latent,
-                  nullptr, st, false, &at<rb::Meta>(ws, L.meta)->total_rows, at<int32_t>(ws, L.tile_start)))
+                  nullptr, st, false, &at<rb::Meta>(ws, L.meta)->total_rows, at<int32_t>(ws, L.tile_start), (d->flags & SNB_BATCH_FP32_TC) != 0))
     return 1;
   if (!pose) return 0;
   SNB_CHECK_CUDA(cudaMemsetAsync(at<uint8_t>(sc, G.acc64), 0, G.mlp - G.acc64, st));   // fp64 sums + tickets

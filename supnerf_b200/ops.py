@@ -604,7 +604,7 @@ class _RenderBoxBatch(torch.autograd.Function):
         b, n = px.shape
         dev = px.device
         desc = _lib.SnbBatchDesc(int(b), int(n_samples), int(n), int(flags), 0)
-        key = ("batch", b, n, int(n_samples), int(flags) & FUSED_SAMPLER)
+        key = ("batch", b, n, int(n_samples), int(flags) & (FUSED_SAMPLER | BATCH_FP32_TC))
         cache = handle.__dict__.setdefault("_render_sizes", {})
         sizes = cache.get(key)
         if sizes is None:
@@ -641,7 +641,7 @@ class _RenderBoxBatch(torch.autograd.Function):
         g_sl = torch.empty_like(shape_latent)
         g_tl = torch.empty_like(texture_latent)
         if frozen is not handle._frozen:
-            handle.use_frozen(frozen, PREC["bf16"])
+            handle.use_frozen(frozen, PREC_FP32_TC if desc.flags & BATCH_FP32_TC else PREC["bf16"])
         scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
         with on_device(dev):
             check(lib.snb_render_batch_bwd(handle.h, ctypes.byref(desc), ptr(px), ptr(py), ptr(K), ptr(c2w), ptr(box), ptr(z_steps), ptr(jitter),
@@ -651,21 +651,32 @@ class _RenderBoxBatch(torch.autograd.Function):
 
 
 FUSED_SAMPLER = 4   # SNB_BATCH_FUSED_SAMPLER
+BATCH_FP32_TC = 8   # SNB_BATCH_FP32_TC
 
 
 def render_box_batch(handle, n_samples, white_bkgd, px, py, K, c2w, box, z_steps, jitter, shape_latent, texture_latent, weights,
-                     fused_sampler=False):
+                     fused_sampler=False, precision="bf16"):
     """B objects through ONE launch set.  px, py (B,N); K (B,3,3); c2w (B,3,4); box (B,4) = {diag/2, l/diag, w/diag, h/diag}
     (box_constants per object); jitter (B,N,S); latents (B,D).  -> rgb (B,N,3), depth (B,N), acc (B,N), hit (B,N) bool.
-    Frozen weights only (refine mode); bf16 decoder.  fused_sampler: the decoder's forward computes every row's stratified sample
+    Frozen weights only (refine mode).  precision "bf16" (the two-tile kernels) or "fp32" (the split-precision tensor-core kernels,
+    SNB_PREC_FP32_TC: fp32-grade results).  fused_sampler (bf16 only): the decoder's forward computes every row's stratified sample
     from its ray itself (north-star kernel K1: no sampler kernel, no per-row coordinates in HBM on the forward path); bit-identical
     results, measured ~0.7 % slower per forward + backward step than the default, which writes the executed rows' samples once."""
     for w in weights:
         if w.requires_grad:
             raise RuntimeError("render_box_batch: the batched render is the frozen-weight (refine) path; "
                                "model.requires_grad_(False), or render the objects one by one")
-    handle.use_frozen(weights, PREC["bf16"])
-    flags = (WHITE_BKGD if white_bkgd else 0) | SIGMA_RELU | (FUSED_SAMPLER if fused_sampler else 0)
+    prec = PREC[precision] if isinstance(precision, str) else precision
+    flags = (WHITE_BKGD if white_bkgd else 0) | SIGMA_RELU
+    if prec == PREC["bf16"]:
+        flags |= FUSED_SAMPLER if fused_sampler else 0
+        handle.use_frozen(weights, PREC["bf16"])
+    else:
+        if fused_sampler or not handle.tc_ok:
+            raise RuntimeError("render_box_batch(precision='fp32'): runs on the split-precision tensor-core decoder (CodeNeRF family, "
+                               "W = 256), without the fused sampler; render the objects one by one otherwise")
+        flags |= BATCH_FP32_TC
+        handle.use_frozen(weights, PREC_FP32_TC)
     return _RenderBoxBatch.apply(handle, n_samples, flags, px, py, K, c2w, box, z_steps, jitter, shape_latent, texture_latent)
 
 

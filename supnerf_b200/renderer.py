@@ -145,7 +145,8 @@ class NeRFRenderer(torch.nn.Module):
         rgb, dep, acc, _hit = ops.render_box_batch(model._handle(device), self.n_samples, self.white_bkgd, batch.px, batch.py, batch.K,
                                                    cam_poses.to(device, non_blocking=True), batch.box, _z_steps_on(device, self.n_samples),
                                                    jitter, shapecodes.to(device, non_blocking=True),
-                                                   texturecodes.to(device, non_blocking=True), model._weights(), fused_sampler=fused_sampler)
+                                                   texturecodes.to(device, non_blocking=True), model._weights(), fused_sampler=fused_sampler,
+                                                   precision=model.precision or models.get_default_precision())
         return rgb, dep, acc
 
     def render_rays_batch(self, model, device, imgs, masks_occ, cam_poses, obj_szs, Ks, rois, shapecodes, texturecodes, im_sz=64,
@@ -153,8 +154,8 @@ class NeRFRenderer(torch.nn.Module):
         """``render_rays`` (renderer.py:117-167, ``n_rays=None``) of B objects in ONE launch set -- what the reference does with a
         Python loop over the objects of a scene (optimizer_nuscenes.py:716-726; configs[1]: 16 objects per step).
         cam_poses (B,3,4); obj_szs B x (w,l,h); Ks (B,3,3) or one (3,3); rois B x (4,); shapecodes / texturecodes (B,D).
-        -> rgb (B,N,3), depth (B,N), acc (B,N), rgb_tgt (B,N,3), occ_pixels (B,N,1).  Frozen weights, bf16 decoder (no CPU or
-        per-object fallback)."""
+        -> rgb (B,N,3), depth (B,N), acc (B,N), rgb_tgt (B,N,3), occ_pixels (B,N,1).  Frozen weights; the model's precision picks the
+        bf16 or the fp32-grade (split-precision) tensor-core decoder (no CPU or per-object fallback)."""
         batch = self.make_batch(device, imgs, masks_occ, obj_szs, Ks, rois, im_sz)
         rgb, dep, acc = self.render_batch(model, batch, cam_poses, shapecodes, texturecodes, jitter, fused_sampler)
         return rgb, dep, acc, batch.rgb_tgt, batch.occ_pixels

@@ -1016,3 +1016,59 @@ def test_decoder_fp32_on_tensor_cores_vs_oracle(blocks, B, n, S_):
     for name, a, s_, r, t in zip(("sigma", "rgb", "g_xyz", "g_viewdir", "g_shape", "g_texture"), got, simt, ref, truth):
         assert close_vs_truth(a, r, t, name="tc_" + name)[0], (name, close_vs_truth(a, r, t))
         parity_ok("simt_" + name, s_, r, 1.0)     # ledger only: the FFMA back end's error on the same case
+
+
+def test_batched_render_fp32_tensor_cores_vs_per_object_and_oracle():
+    """The batched box render with the decoder in SNB_PREC_FP32_TC arithmetic (model.precision = 'fp32', frozen weights): against the
+    per-object fused render of the same precision (same per-row arithmetic: hit rays bit-identical) and against the fp32 / fp64 CPU
+    oracle at the fp32 tolerance -- render, loss and the pose / code gradients."""
+    S = snb()
+    n_obj, im, S_ = 3, 24, 32
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=62)
+    m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
+    m.precision = "fp32"
+    m.requires_grad_(False)
+    R = S.renderer.NeRFRenderer(n_samples=S_)
+    objs = [oracle.synthetic_object(230 + 7 * i, im_sz=im) for i in range(n_obj)]
+    lat = [oracle.synthetic_latents(230 + 7 * i, 1) for i in range(n_obj)]
+    n = im * im
+    jit = torch.rand(n_obj, n, S_, generator=torch.Generator().manual_seed(62))
+    per = []
+    for i, o in enumerate(objs):
+        cam = o["cam_pose"].to(DEV).requires_grad_()
+        shp, tex = lat[i][0].to(DEV).requires_grad_(), lat[i][1].to(DEV).requires_grad_()
+        with forced_rand_like(jit[i]):
+            rgb, dep, acc, tgt, occ = R.render_rays(m, DEV, o["img"], o["mask_occ"], cam, o["wlh"], o["K"].to(DEV), o["roi"], shp, tex, im_sz=im)
+        S.losses.refine_loss(rgb, acc, tgt, occ, 0.1)[0].backward()
+        per.append((rgb.detach(), dep.detach(), acc.detach(), cam.grad, shp.grad, tex.grad))
+    cams = torch.stack([o["cam_pose"] for o in objs]).to(DEV).requires_grad_()
+    shps = torch.cat([l[0] for l in lat]).to(DEV).requires_grad_()
+    texs = torch.cat([l[1] for l in lat]).to(DEV).requires_grad_()
+    before = S._lib.load().snb_launch_count()
+    rgb, dep, acc, tgt, occ = R.render_rays_batch(m, DEV, [o["img"] for o in objs], [o["mask_occ"] for o in objs], cams,
+                                                  [o["wlh"] for o in objs], torch.stack([o["K"] for o in objs]), [o["roi"] for o in objs],
+                                                  shps, texs, im_sz=im, jitter=jit.to(DEV))
+    losses, _ = S.losses.refine_loss_batch(rgb, acc, tgt, occ, 0.1)
+    losses.sum().backward()
+    assert S._lib.load().snb_launch_count() - before <= 30          # one launch set for the three objects (per object: ~24 each)
+    for i, o in enumerate(objs):
+        ro, vd = oracle.get_rays(o["K"], o["cam_pose"], o["roi"], uv_steps=[im, im])
+        diag, half = oracle.box_constants(o["wlh"])
+        hb = torch.from_numpy(half)
+        hit = oracle.ray_box_intersection(ro / (diag / 2), vd, -hb.expand_as(ro), hb.expand_as(ro))[2].to(DEV)
+        for a, b_ in zip((rgb[i], dep[i], acc[i]), per[i][:3]):
+            assert torch.equal(a[hit], b_[hit])
+        assert parity_ok("obj%d_g_shape_vs_per_object" % i, shps.grad[i], per[i][4][0], 1e-4)
+        assert parity_ok("obj%d_g_pose_vs_per_object" % i, cams.grad[i], per[i][3], 1e-3)
+        res = {}
+        for dt in (torch.float32, torch.float64):
+            sdd = {k: v.to(dt) for k, v in sd.items()}
+            cam_o = o["cam_pose"].to(dt).clone().requires_grad_()
+            s_o, t_o = lat[i][0].to(dt).clone().requires_grad_(), lat[i][1].to(dt).clone().requires_grad_()
+            r_o = oracle.render_rays_box(sdd, o["K"].to(dt), cam_o, o["wlh"], o["roi"], im, S_, s_o, t_o, jit[i].to(dt))
+            l_o = oracle.refine_losses(r_o[0], r_o[2], o["img"].reshape(-1, 3).to(dt), o["mask_occ"].reshape(-1, 1).to(dt))[0]
+            l_o.backward()
+            res[dt] = (r_o[0].detach(), r_o[1].detach(), l_o.detach(), cam_o.grad, s_o.grad[0], t_o.grad[0])
+        got = (rgb[i], dep[i], losses[i], cams.grad[i], shps.grad[i], texs.grad[i])
+        for name, a, r32, r64 in zip(("rgb", "depth", "loss", "g_pose", "g_shape", "g_texture"), got, res[torch.float32], res[torch.float64]):
+            assert close_vs_truth(a, r32, r64, name="obj%d_%s_vs_oracle" % (i, name))[0], (i, name, close_vs_truth(a, r32, r64))
