@@ -19,12 +19,18 @@ PREC_FP32_TC = 3     # selected automatically in fp32 mode when NO weight takes 
 FP32_TENSOR_CORES = os.environ.get("SNB_FP32_SIMT", "0") in ("", "0")   # False: fp32 mode always runs the FFMA kernels
 
 
-def _fp32_tc(handle, prec, rows_per_obj=None):
+FP32_TC_MAX_WEIGHT = 255.0   # 256 * w must stay inside fp16's range (csrc/mlp_tc.cu: kWScale)
+
+
+def _fp32_tc(handle, prec, rows_per_obj=None, weights=None):
     """fp32 mode with frozen weights -> the split-precision tensor-core kernels where they apply (CodeNeRF family, W = 256; dense row
-    counts a multiple of the 128-row tile).  rows_per_obj None: the caller's rows are compacted on the device (any count)."""
+    counts a multiple of the 128-row tile; every |weight| < 255 -- checked once per weight version).  rows_per_obj None: the caller's
+    rows are compacted on the device (any count)."""
     if prec != PREC["fp32"] or not FP32_TENSOR_CORES or not handle.tc_ok:
         return prec
     if rows_per_obj is not None and (rows_per_obj <= 0 or rows_per_obj % 128 != 0):
+        return prec
+    if weights is not None and not handle.weights_in_fp16_range(weights):
         return prec
     return PREC_FP32_TC
 
@@ -345,6 +351,21 @@ class DecoderHandle:
         if self.__dict__.get("_frozen") is not tensors:
             self._frozen = tensors
 
+    def weights_in_fp16_range(self, tensors):
+        """True when every weight is finite and below FP32_TC_MAX_WEIGHT in magnitude (the split-precision kernels hold 256 * w in
+        fp16 pairs).  One device reduction + read-back per weight version; the answer is cached with the version key."""
+        key = self.packed_key(tensors)
+        hit = self.__dict__.get("_range_key")
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        if torch.cuda.is_current_stream_capturing():
+            return True      # no read-back inside a capture: the warm-up iterations before it have answered for these weights
+        with torch.no_grad():
+            biggest = float(torch.stack([t.detach().abs().max() for t in tensors if t.numel()]).max())
+        ok = biggest == biggest and biggest < FP32_TC_MAX_WEIGHT
+        self._range_key = (key, ok)
+        return ok
+
     def invalidate_packed(self):
         """Force a re-pack of the bf16 weight images at the next call.  Needed after weight edits autograd's version counter does
         not see (``p.data.copy_(...)``, ``p.data.mul_(...)``: EMA updates, manual checkpoint loading idioms); ordinary in-place
@@ -380,7 +401,7 @@ class _Decoder(torch.autograd.Function):
         dev = xyz.device
         handle.set_weights(weights)
         if precision == PREC["fp32"] and not any(ctx.needs_input_grad[7:]):
-            precision = _fp32_tc(handle, precision, m // max(n_objs, 1))
+            precision = _fp32_tc(handle, precision, m // max(n_objs, 1), weights)
         if precision == PREC["bf16"]:
             handle.ensure_packed(weights)
             if any(ctx.needs_input_grad[7:]):
@@ -439,7 +460,7 @@ def decoder(handle, precision, xyz, viewdir, shape_latent, texture_latent, weigh
     prec = PREC[precision] if isinstance(precision, str) else precision
     m = xyz.shape[0]
     frozen = not (torch.is_grad_enabled() and any(w.requires_grad for w in weights))
-    tc_rows = prec == PREC["bf16"] or (frozen and _fp32_tc(handle, prec) == PREC_FP32_TC)
+    tc_rows = prec == PREC["bf16"] or (frozen and _fp32_tc(handle, prec, None, weights) == PREC_FP32_TC)
     if tc_rows and n_objs == 1 and m % 128 != 0 and m > 0:
         # the tensor-core decoder works on 128-row tiles: pad a single object's rows with copies of its last row (outputs
         # sliced off again, so the copies get zero upstream gradient).  Batched latents must bring tile-aligned row counts.
@@ -562,9 +583,9 @@ def _render_apply(handle, prec, n_samples, flags, geom, px, py, K, c2w, z_steps,
             break
     else:
         if geom[0] == "box" and os.environ.get("SNB_NO_COMPACT", "0") in ("", "0"):
-            prec = _fp32_tc(handle, prec)                                  # rows compacted on the device: any count
+            prec = _fp32_tc(handle, prec, None, weights)                   # rows compacted on the device: any count
         else:
-            prec = _fp32_tc(handle, prec, px.numel() * int(n_samples))    # dense rows
+            prec = _fp32_tc(handle, prec, px.numel() * int(n_samples), weights)    # dense rows
         handle.use_frozen(weights, prec)
         return _RenderBox.apply(handle, prec, n_samples, flags, geom, px, py, K, c2w, z_steps, jitter, shape_latent, texture_latent)
     return _RenderBox.apply(handle, prec, n_samples, flags, geom, px, py, K, c2w, z_steps, jitter, shape_latent, texture_latent, *weights)
@@ -672,9 +693,9 @@ def render_box_batch(handle, n_samples, white_bkgd, px, py, K, c2w, box, z_steps
         flags |= FUSED_SAMPLER if fused_sampler else 0
         handle.use_frozen(weights, PREC["bf16"])
     else:
-        if fused_sampler or not handle.tc_ok:
+        if fused_sampler or not handle.tc_ok or not handle.weights_in_fp16_range(weights):
             raise RuntimeError("render_box_batch(precision='fp32'): runs on the split-precision tensor-core decoder (CodeNeRF family, "
-                               "W = 256), without the fused sampler; render the objects one by one otherwise")
+                               "W = 256, |weights| < 255), without the fused sampler; render the objects one by one otherwise")
         flags |= BATCH_FP32_TC
         handle.use_frozen(weights, PREC_FP32_TC)
     return _RenderBoxBatch.apply(handle, n_samples, flags, px, py, K, c2w, box, z_steps, jitter, shape_latent, texture_latent)
@@ -745,7 +766,7 @@ def render_shell_batch(handle, precision, n_samples, shapenet_swap, px, py, K, c
         if w.requires_grad:
             raise RuntimeError("render_shell_batch: the batched render is the frozen-weight (refine) path; "
                                "model.requires_grad_(False), or render the objects one by one")
-    prec = _fp32_tc(handle, PREC[precision] if isinstance(precision, str) else precision, px.shape[1] * int(n_samples))
+    prec = _fp32_tc(handle, PREC[precision] if isinstance(precision, str) else precision, px.shape[1] * int(n_samples), weights)
     handle.use_frozen(weights, prec)
     return _RenderShellBatch.apply(handle, prec, n_samples, shapenet_swap, px, py, K, c2w, z_vals, obj_diag, shape_latent, texture_latent)
 

@@ -1072,3 +1072,25 @@ def test_batched_render_fp32_tensor_cores_vs_per_object_and_oracle():
         got = (rgb[i], dep[i], losses[i], cams.grad[i], shps.grad[i], texs.grad[i])
         for name, a, r32, r64 in zip(("rgb", "depth", "loss", "g_pose", "g_shape", "g_texture"), got, res[torch.float32], res[torch.float64]):
             assert close_vs_truth(a, r32, r64, name="obj%d_%s_vs_oracle" % (i, name))[0], (i, name, close_vs_truth(a, r32, r64))
+
+
+def test_fp32_tensor_core_mode_steps_aside_for_weights_outside_fp16_range():
+    """The split-precision kernels hold 256 * w in fp16 pairs: a weight set with |w| >= 255 must run on the FFMA kernels instead (checked
+    once per weight version on the device) -- same results as ever, no inf."""
+    S = snb()
+    sd = oracle.init_codenerf_state(shape_blocks=2, texture_blocks=1, seed=31)
+    sd["shape_layer_1.0.weight"] = sd["shape_layer_1.0.weight"].clone()
+    sd["shape_layer_1.0.weight"][3, 5] = 300.0
+    xyz, vd, shp, tex, _, _ = _decoder_case(None, sd, None, 1, 64, 8, seed=12)
+    sig, rgbs = oracle.codenerf_decoder(sd, xyz, vd, shp, tex)
+    m = model_from_state(S.CodeNeRF, sd, shape_blocks=2, texture_blocks=1)
+    m.precision = "fp32"
+    m.requires_grad_(False)
+    h = m._handle(torch.device(DEV, torch.cuda.current_device()))
+    assert h.tc_ok and not h.weights_in_fp16_range(m._weights())
+    sig2, rgbs2 = m(xyz.to(DEV), vd.to(DEV), shp.to(DEV), tex.to(DEV))
+    assert bool(torch.isfinite(sig2).all()) and bool(torch.isfinite(rgbs2).all())
+    assert parity_ok("sigma", sig2, sig, TOL) and parity_ok("rgb", rgbs2, rgbs, TOL)
+    with torch.no_grad():
+        m.get_parameter("shape_layer_1.0.weight")[3, 5] = 0.01      # an in-place update bumps the version: re-checked, back on the tensor cores
+    assert h.weights_in_fp16_range(m._weights())
