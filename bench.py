@@ -489,6 +489,22 @@ def run_ours(args):
                     "ms_per_batched_iteration": round(a0.elapsed_time(a1) / 50, 4), "loss_after_obj0": round(float(lastb[0, 0]), 5),
                     "note": "refine.BatchRefiner: every stage of the iteration (incl. the lidar-pixel evaluation) once over all objects, "
                             "one captured graph; per object-iteration = elapsed / (objects x 50)"}
+            # the same iteration in fp32 (1e-5 parity) mode: the split-precision tensor-core decoder, since no weight takes a gradient
+            if args.precision == "bf16":
+                sup.precision = "fp32"
+                try:
+                    r32 = refiner_for(0, 60)
+                    r32.run(5)
+                    torch.cuda.synchronize()
+                    a0.record()
+                    last32 = r32.run(50)
+                    a1.record()
+                    torch.cuda.synchronize()
+                    refine_it["fp32_mode"] = {"ms_per_refine_iteration": round(a0.elapsed_time(a1) / 50, 4), "iterations": 50,
+                                              "loss_after": round(float(last32[0]), 5),
+                                              "note": "one object, precision='fp32' (SNB_PREC_FP32_TC decoder kernels), one CUDA graph per iteration"}
+                finally:
+                    sup.precision = args.precision
         except Exception as exc:
             refine_it = dict(refine_it or {}, error=str(exc))
     # the collective-bearing modes of the north star (configs[3], configs[4]): run at every N (N = 1 anchors the strong-scaling curve)
