@@ -27,7 +27,10 @@
 namespace snb {
 namespace tc {
 
-constexpr int kStages = 3;
+#ifndef SNB_TC_STAGES
+#define SNB_TC_STAGES 3
+#endif
+constexpr int kStages = SNB_TC_STAGES;   // weight-ring depth (tuning builds: -DSNB_TC_STAGES=2 measures the ring's share of the time)
 constexpr int kMaxSteps = 16;
 constexpr int kMaxFwdSteps = 12;
 constexpr int kThreads = 320;
@@ -48,6 +51,7 @@ constexpr float kWScale = 256.f, kWScaleInv = 1.f / 256.f;
 #define SNB_SPLIT_CORR_FIRST 1
 #endif
 constexpr bool kCorrFirst = SNB_SPLIT_CORR_FIRST != 0;
+constexpr int kSplitBiasSteps = 8;   // split mode, forward: steps whose (effective) bias sits in shared memory (the 8 KB the backward uses for column sums)
 
 // shared-memory map (bytes from the 1024-aligned base)
 template <bool X> struct Map {
@@ -345,8 +349,7 @@ __device__ __forceinline__ void fwd_epilogue(const Params& p, const SmemT<X>& sm
     uint32_t nmask = 0;   // nmask collects SIGN bits (1 = negative pre-activation); stored inverted
 #pragma unroll
     for (int i4 = 0; i4 < 8; ++i4) {
-      const float4 bb = X ? __ldg(reinterpret_cast<const float4*>(bias_s + col0 + 4 * i4))
-                          : *reinterpret_cast<const float4*>(bias_s + col0 + 4 * i4);
+      const float4 bb = *reinterpret_cast<const float4*>(bias_s + col0 + 4 * i4);
       float v[4];
       if (X) {
         v[0] = fmaf(__uint_as_float(r[4 * i4]), kWScaleInv, bb.x); v[1] = fmaf(__uint_as_float(r[4 * i4 + 1]), kWScaleInv, bb.y);
@@ -419,9 +422,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_fwd_kernel(const __grid_consta
   {  // static tables: every layer's bias (plain mode), the sigma / rgb head weights
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* b = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-    if (!X) {
+    {  // split mode: the table has room for the first kSplitBiasSteps steps (every shipped decoder has 8); later steps read L1 / L2
       float* bias_s = reinterpret_cast<float*>(b + MP::SM_TAB + MP::TAB_BIAS);
-      for (int i = tid; i < p.prog.n_steps * 256; i += kThreads) {
+      const int n_tab = X ? (p.prog.n_steps < kSplitBiasSteps ? p.prog.n_steps : kSplitBiasSteps) : p.prog.n_steps;
+      for (int i = tid; i < n_tab * 256; i += kThreads) {
         const int si = i >> 8, c = i & 255;
         bias_s[i] = c < p.prog.s[si].n_out ? __ldg(p.prog.s[si].bias + c) : 0.f;
       }
@@ -470,10 +474,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_fwd_kernel(const __grid_consta
       }
       const float dir[3] = {__ldg(p.viewdir + 3 * crow), __ldg(p.viewdir + 3 * crow + 1), __ldg(p.viewdir + 3 * crow + 2)};
       const int64_t obj = obj_of_tile(p, tile);   // tiles never straddle objects (checked on the host)
-      if (!X && obj != cur_obj) {  // (re)load the per-object latent vectors; all epilogue warps are between tiles here
+      if (obj != cur_obj) {  // (re)load the per-object effective biases; all epilogue warps are between tiles here
         cur_obj = obj;
-        for (int i = tid; i < p.n_latent * 256; i += 256)
-          z_s[i] = __ldg(p.zlat + ((size_t)(i >> 8) * p.B + obj) * 256 + (i & 255));
+        if (!X) {
+          for (int i = tid; i < p.n_latent * 256; i += 256)
+            z_s[i] = __ldg(p.zlat + ((size_t)(i >> 8) * p.B + obj) * 256 + (i & 255));
+        } else {   // split mode: into the latent-conditioned steps' rows of the bias table
+          float* bias_tab = sm.tab(MP::TAB_BIAS);
+          for (int si = 0; si < p.prog.n_steps && si < kSplitBiasSteps; ++si) {
+            const int slot = p.prog.s[si].latent_slot;
+            if (slot >= 0) bias_tab[si * 256 + tid] = __ldg(p.zlat + ((size_t)slot * p.B + obj) * 256 + tid);
+          }
+        }
         epi_bar_sync();
       }
       uint32_t* mask_tile = p.masks + (size_t)tile * nslots * 8 * 128;
@@ -481,8 +493,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_fwd_kernel(const __grid_consta
       for (int si = 0; si < p.prog.n_steps; ++si, ++gstep) {
         const Step& st = p.prog.s[si];
         const uint32_t half = gstep & 1u;
-        const float* bias_g = nullptr;
-        if (X) bias_g = st.latent_slot >= 0 ? p.zlat + ((size_t)st.latent_slot * p.B + obj) * 256 : st.bias;
+        const float* bias_g = nullptr;   // split mode: the step's (effective) bias, from the shared-memory table or through L1
+        if (X) bias_g = si < kSplitBiasSteps ? sm.tab(MP::TAB_BIAS) + si * 256
+                                             : (st.latent_slot >= 0 ? p.zlat + ((size_t)st.latent_slot * p.B + obj) * 256 : st.bias);
         mbar_wait(sm.bar(BAR_ACC + half), acc_cnt[half] & 1u);
         acc_cnt[half]++;
         tc_fence_after();
@@ -1058,7 +1071,9 @@ static void fill_common(Params& p, const snb_handle_s* h, const float* xyz, cons
 }
 
 static int tc_grid(int64_t M) {
-  const int sms = sm_count();
+  static const int cap = [] { const char* e = getenv("SNB_TC_GRID_CAP"); return e ? atoi(e) : 0; }();   // tuning: fewer CTAs than SMs
+  int sms = sm_count();
+  if (cap > 0 && cap < sms) sms = cap;
   const int64_t t = tiles_of(M);
   return (int)(t < sms ? t : sms);
 }
