@@ -960,8 +960,14 @@ def test_batch_refiner_one_launch_set_equals_per_object_refiners(prec):
             else:
                 assert d is None
             if it == 0:
-                assert parity_ok("it0_shapecode", bat.shapecode[b], r.shapecode.reshape(-1), tol1)
-                assert parity_ok("it0_rot_vec", bat.rot_vec[b], r.rot_vec, tol1) and parity_ok("it0_trans_vec", bat.trans_vec[b], r.trans_vec, tol1)
+                # the gradients themselves (AdamW's first step is ~ lr * sign(g): an element whose gradient is at rounding level may
+                # legitimately land 2 lr apart in two summation orders, so the updated codes are held to the trajectory tolerance)
+                assert parity_ok("it0_g_shapecode", bat.shapecode.grad[b], r.shapecode.grad.reshape(-1), tol1)
+                assert parity_ok("it0_g_texturecode", bat.texturecode.grad[b], r.texturecode.grad.reshape(-1), tol1)
+                assert parity_ok("it0_g_rot_vec", bat.rot_vec.grad[b], r.rot_vec.grad, 10 * tol1)
+                assert parity_ok("it0_g_trans_vec", bat.trans_vec.grad[b], r.trans_vec.grad, 10 * tol1)
+                assert parity_ok("it0_shapecode", bat.shapecode[b], r.shapecode.reshape(-1), 2e-2)
+                assert parity_ok("it0_rot_vec", bat.rot_vec[b], r.rot_vec, 5e-3) and parity_ok("it0_trans_vec", bat.trans_vec[b], r.trans_vec, 5e-3)
     for b, r in enumerate(bat.write_back()):
         assert parity_ok("end_shapecode", r.shapecode, seq[b].shapecode, 2e-2) and parity_ok("end_texturecode", r.texturecode, seq[b].texturecode, 2e-2)
         assert parity_ok("end_rot_vec", r.rot_vec, seq[b].rot_vec, 5e-3) and parity_ok("end_trans_vec", r.trans_vec, seq[b].trans_vec, 5e-3)
@@ -1023,6 +1029,8 @@ def test_batched_render_fp32_tensor_cores_vs_per_object_and_oracle():
     per-object fused render of the same precision (same per-row arithmetic: hit rays bit-identical) and against the fp32 / fp64 CPU
     oracle at the fp32 tolerance -- render, loss and the pose / code gradients."""
     S = snb()
+    if not S.ops.FP32_TENSOR_CORES:
+        pytest.skip("SNB_FP32_SIMT=1: the per-object render runs on the FFMA kernels, nothing to compare bit for bit")
     n_obj, im, S_ = 3, 24, 32
     sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=62)
     m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
