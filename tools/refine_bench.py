@@ -115,8 +115,9 @@ def main():
     if a.batch:
         bat = snb.refine.BatchRefiner(refiners)
         if not a.eager:
-            bat.capture()
-        bat.run(3)
+            bat.capture()      # warms up and restores the initial state itself
+        else:
+            bat.run(3)
         torch.cuda.synchronize()
     e0.record()
     if a.batch:
