@@ -32,9 +32,9 @@ namespace tc {
 #endif
 constexpr int kStages = SNB_TC_STAGES;   // weight-ring depth (tuning builds: -DSNB_TC_STAGES=2 measures the ring's share of the time)
 constexpr int kMaxSteps = 16;
-constexpr int kMaxFwdSteps = 12;
+constexpr int kMaxFwdSteps = 14;        // 5 + 5 blocks (the SUPNeRF() / AutoRFMix() class defaults): 1 + 5 + 1 + 1 + 5 + 1
 constexpr int kThreads = 320;
-constexpr int kMaxLatentSlots = 8;
+constexpr int kMaxLatentSlots = 10;
 
 // Split mode (template parameter X = true; SNB_PREC_FP32_TC): fp32-grade arithmetic on the same tensor-core pipeline.  Every MMA
 // operand is held as TWO fp16 parts (x = hi + lo, |lo| <= 2^-12 |x|) and each product is issued as three MMAs (hi*hi, lo*hi, hi*lo;
@@ -51,7 +51,7 @@ constexpr float kWScale = 256.f, kWScaleInv = 1.f / 256.f;
 #define SNB_SPLIT_CORR_FIRST 1
 #endif
 constexpr bool kCorrFirst = SNB_SPLIT_CORR_FIRST != 0;
-constexpr int kSplitBiasSteps = 8;   // split mode, forward: steps whose (effective) bias sits in shared memory (the 8 KB the backward uses for column sums)
+constexpr int kSplitBiasSteps = kMaxLatentSlots;   // split mode, forward: steps whose (effective) bias sits in shared memory (the 8 KB the backward uses for column sums)
 
 // shared-memory map (bytes from the 1024-aligned base)
 template <bool X> struct Map {
@@ -59,7 +59,7 @@ template <bool X> struct Map {
   static constexpr uint32_t kStageBytes = X ? 16384u : 32768u;       // [256 n][64 k] bf16, split: [128 n][64 k] fp16
   static constexpr uint32_t SM_W = kAChunks * kChunkBytes;           // then the weight ring
   static constexpr uint32_t SM_TAB = SM_W + kStages * kStageBytes;   // fp32 tables
-  static constexpr uint32_t TAB_BIAS = 0;                            // fwd: [kMaxFwdSteps][256] (split: none)  bwd: colsum [8][256]
+  static constexpr uint32_t TAB_BIAS = 0;                            // fwd: [kMaxFwdSteps][256] (split: [kSplitBiasSteps][256])  bwd: colsum [slots][256]
   static constexpr uint32_t TAB_Z = TAB_BIAS + (X ? kMaxLatentSlots : kMaxFwdSteps) * 256 * 4;   // fwd: [8][256] per-object effective biases (split: none)
   static constexpr uint32_t TAB_WSIG = TAB_Z + (X ? 0 : kMaxLatentSlots * 256 * 4);   // [256]
   static constexpr uint32_t TAB_W2 = TAB_WSIG + 256 * 4;             // [3][128]
@@ -100,8 +100,8 @@ struct Params {
   const float* sigma_in; const float* g_sigma; const float* g_rgb;
   float* g_xyz; float* g_viewdir; float* g_zlat;   // g_zlat [(Bs+Bt)][B][256], accumulated with atomics
   int r0_mask_slot, n_latent, ev_step;
-  const int64_t* m_dev;         // split mode: device-side row count (a multiple of 128, <= M) or null
-  const int32_t* tile_start;    // split mode: per-object first tile (B + 1 ints) or null = M / B rows per object
+  const int64_t* m_dev;         // device-side row count (a multiple of 128, <= M) or null
+  const int32_t* tile_start;    // per-object first tile (B + 1 ints) or null = M / B rows per object
   Program prog;
 };
 
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_fwd_kernel(const __grid_consta
   {  // static tables: every layer's bias (plain mode), the sigma / rgb head weights
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* b = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-    {  // split mode: the table has room for the first kSplitBiasSteps steps (every shipped decoder has 8); later steps read L1 / L2
+    {  // split mode: the table has room for the first kSplitBiasSteps steps; later steps (more than 10: no supported architecture) read L1 / L2
       float* bias_s = reinterpret_cast<float*>(b + MP::SM_TAB + MP::TAB_BIAS);
       const int n_tab = X ? (p.prog.n_steps < kSplitBiasSteps ? p.prog.n_steps : kSplitBiasSteps) : p.prog.n_steps;
       for (int i = tid; i < n_tab * 256; i += kThreads) {
@@ -833,7 +833,7 @@ static bool tc_supported(const snb_handle_s* h, const char** why) {
   if (a.arch != SNB_ARCH_CODENERF) { *why = "bf16 mode covers the CodeNeRF/AutoRFMix/SUPNeRF decoder only"; return false; }
   if (a.W != 256) { *why = "bf16 mode needs W == 256"; return false; }
   if (a.num_xyz_freq != 10 || a.num_dir_freq != 4) { *why = "bf16 mode needs num_xyz_freq == 10 and num_dir_freq == 4"; return false; }
-  if (a.shape_blocks + a.texture_blocks > kMaxLatentSlots) { *why = "bf16 mode needs shape_blocks + texture_blocks <= 8"; return false; }
+  if (a.shape_blocks + a.texture_blocks > kMaxLatentSlots) { *why = "the tensor-core back ends need shape_blocks + texture_blocks <= 10"; return false; }
   return true;
 }
 
@@ -1132,9 +1132,10 @@ int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, in
   SNB_REQUIRE(rs == nullptr || (tile_start != nullptr && rs->rays8 && rs->box && rs->z_steps && rs->jitter && rs->order && rs->counts),
               "mlp_fwd(bf16): a row source needs per-object tile offsets and all of its pointers");
   SNB_REQUIRE(rs != nullptr || (xyz != nullptr && viewdir != nullptr), "mlp_fwd(bf16): null coordinates");
-  SNB_REQUIRE(m_dev == nullptr || (use_v2(h) && (B == 1 || tile_start != nullptr)),
-              "mlp_fwd(bf16): a device-side row count needs the two-tile kernels and one object (or per-object tile offsets)");
-  SNB_REQUIRE(tile_start == nullptr || (use_v2(h) && m_dev != nullptr && !train), "mlp_fwd(bf16): per-object tile offsets need the two-tile kernels, frozen weights and a device-side row count");
+  SNB_REQUIRE(m_dev == nullptr || B == 1 || tile_start != nullptr,
+              "mlp_fwd(bf16): a device-side row count needs one object (or per-object tile offsets)");
+  SNB_REQUIRE(tile_start == nullptr || (m_dev != nullptr && !train), "mlp_fwd(bf16): per-object tile offsets need frozen weights and a device-side row count");
+  SNB_REQUIRE(rs == nullptr || use_v2(h), "mlp_fwd(bf16): the fused sampler needs the two-tile kernels");
   SNB_REQUIRE(!train || use_v2(h), "mlp_fwd(bf16, training): weight gradients need the two-tile tcgen05 kernels (W = 256, "
                                     "shape_blocks + texture_blocks <= 4); use precision='fp32' for this architecture");
   uint8_t* fsave = train ? align1k((uint8_t*)ws + tc_workspace_bytes(h, M, B)) : nullptr;
@@ -1154,6 +1155,7 @@ int tc_forward(const snb_handle_s* h, const float* xyz, const float* viewdir, in
   TcPlan pl = build_plan(h);
   Params p;
   fill_common(p, h, xyz, viewdir, M, B, ebias, masks);
+  p.m_dev = m_dev; p.tile_start = tile_start;
   p.sigma = sigma; p.rgb = rgb; p.dbg = h->dbg_acts;
   p.prog = pl.fwd;
   SNB_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Map<false>::SM_ALLOC));
@@ -1193,9 +1195,9 @@ int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, i
     SNB_LAUNCH_CHECK();
     return latent_backward_fused(h, B, zlat, g_zlat, g_shape_latent, g_texture_latent, st);
   }
-  SNB_REQUIRE(m_dev == nullptr || (use_v2(h) && (B == 1 || tile_start != nullptr)),
-              "mlp_bwd(bf16): a device-side row count needs the two-tile kernels and one object (or per-object tile offsets)");
-  SNB_REQUIRE(tile_start == nullptr || (use_v2(h) && m_dev != nullptr && !train), "mlp_bwd(bf16): per-object tile offsets need the two-tile kernels, frozen weights and a device-side row count");
+  SNB_REQUIRE(m_dev == nullptr || B == 1 || tile_start != nullptr,
+              "mlp_bwd(bf16): a device-side row count needs one object (or per-object tile offsets)");
+  SNB_REQUIRE(tile_start == nullptr || (m_dev != nullptr && !train), "mlp_bwd(bf16): per-object tile offsets need frozen weights and a device-side row count");
   SNB_REQUIRE(g_weights == nullptr || (train && use_v2(h)),
               "mlp_bwd(bf16): weight gradients need the forward to have run in training mode (SNB_PREC_BF16_TRAIN: the python "
               "modules select it when a weight requires grad) on an architecture the two-tile kernels cover; otherwise freeze "
@@ -1233,6 +1235,7 @@ int tc_backward(const snb_handle_s* h, const float* xyz, const float* viewdir, i
   TcPlan pl = build_plan(h);
   Params p;
   fill_common(p, h, xyz, viewdir, M, B, zlat, masks);
+  p.m_dev = m_dev; p.tile_start = tile_start;
   p.sigma_in = sigma; p.g_sigma = g_sigma; p.g_rgb = g_rgb; p.g_xyz = g_xyz; p.g_viewdir = g_viewdir; p.g_zlat = g_zlat;
   p.r0_mask_slot = pl.r0_slot;
   p.prog = g_xyz ? pl.bwd_full : pl.bwd_noxyz;

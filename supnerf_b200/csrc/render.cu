@@ -21,8 +21,9 @@ inline int64_t decoder_rows(snb_handle h, const snb_render_desc& d);
 bool use_compaction(snb_handle h, const snb_render_desc& d) {
   static const bool off = [] { const char* e = getenv("SNB_NO_COMPACT"); return e && atoi(e) != 0; }();
   if (off || d.mode != SNB_RENDER_BOX || d.n_rays <= 0) return false;
-  if (d.precision == SNB_PREC_FP32_TC) return true;   // the split-precision kernels take the device-side row count themselves
-  return d.precision != SNB_PREC_FP32 && tc_two_tile_active(h);
+  if (d.precision == SNB_PREC_FP32) return false;     // FFMA back end: dense rows
+  if (d.precision == SNB_PREC_BF16_TRAIN) return tc_two_tile_active(h);
+  return tc_one_tile_supported(h);                    // frozen weights: every tensor-core kernel takes the device-side row count
 }
 
 // forward workspace (kept for the backward): rays_o, viewdir (N,3) | xyz, vrep (M,3) | z_vals (M) | sigma (M) | rgb (M,3) | mlp ws

@@ -789,13 +789,12 @@ int check_batch(snb_handle h, const snb_batch_desc* d, const char* who) {
               "%s: the batched render needs n_samples in {4, 8, ..., 128} (vectorised compositing)", who);
   SNB_REQUIRE(d->rays_per_obj < ((int64_t)1 << 30) && d->rays_per_obj * d->n_samples < ((int64_t)1 << 31) &&
               (int64_t)d->n_objs * d->rays_per_obj < ((int64_t)1 << 31), "%s: too many rays", who);
-  if (d->flags & SNB_BATCH_FP32_TC) {
-    SNB_REQUIRE(tc_one_tile_supported(h), "%s: the fp32 tensor-core decoder covers the CodeNeRF family with W = 256", who);
+  SNB_REQUIRE(tc_one_tile_supported(h), "%s: the batched render runs on the tcgen05 decoder kernels (CodeNeRF family, W = 256, "
+                                        "shape_blocks + texture_blocks <= 10); render the objects one by one for this architecture", who);
+  if (d->flags & SNB_BATCH_FP32_TC)
     SNB_REQUIRE(!(d->flags & SNB_BATCH_FUSED_SAMPLER), "%s: SNB_BATCH_FP32_TC and SNB_BATCH_FUSED_SAMPLER exclude each other", who);
-  } else {
-    SNB_REQUIRE(tc_two_tile_active(h), "%s: the batched render runs on the two-tile tcgen05 decoder (CodeNeRF family, W = 256, "
-                                       "shape_blocks + texture_blocks <= 4); render the objects one by one for this architecture", who);
-  }
+  if (d->flags & SNB_BATCH_FUSED_SAMPLER)
+    SNB_REQUIRE(tc_two_tile_active(h), "%s: the fused sampler needs the two-tile kernels (shape_blocks + texture_blocks <= 4)", who);
   return 0;
 }
 

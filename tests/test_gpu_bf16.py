@@ -51,7 +51,7 @@ def test_tc_forward_layer_by_layer():
     assert parity_ok("sig2", sig2, sig, TOL) and parity_ok("rgbs2", rgbs2, rgbs, TOL)
 
 
-@pytest.mark.parametrize("blocks,B,n,S_", [((2, 1), 1, 128, 16), ((3, 1), 4, 32, 8), ((5, 3), 2, 16, 16)])
+@pytest.mark.parametrize("blocks,B,n,S_", [((2, 1), 1, 128, 16), ((3, 1), 4, 32, 8), ((5, 3), 2, 16, 16), ((5, 5), 2, 16, 16)])
 def test_tc_decoder_fwd_bwd_vs_oracle(blocks, B, n, S_):
     S = snb()
     sd = oracle.init_codenerf_state(shape_blocks=blocks[0], texture_blocks=blocks[1], seed=blocks[0])
@@ -584,3 +584,51 @@ def test_tc_training_mode_c5_size_weight_grads_vs_fp32_oracle():
     parity("g_texturecode", t_g.grad, t_o.grad, TOL)
     for k, p_ in m.named_parameters():
         parity("gw_" + k, p_.grad, sdr[k].grad, TOL)
+
+
+def test_class_default_decoder_5_5_blocks_on_the_tensor_cores():
+    """SUPNeRF()'s class defaults (5 shape + 5 texture blocks, 842 880 MAC / sample) are beyond the two-tile kernels' 4 latent slots:
+    the one-tile tcgen05 kernels take them -- per-object fused render with miss-ray compaction and the batched launch set alike --
+    in bf16 and (frozen weights) in the fp32-grade split precision.  Batched vs per-object: the same per-row arithmetic (hit rays
+    bit-identical); against the fp32 CPU oracle within each mode's budget."""
+    S = snb()
+    n_obj, im, S_ = 2, 16, 32
+    sd = oracle.init_codenerf_state(shape_blocks=5, texture_blocks=5, seed=77)
+    objs = [oracle.synthetic_object(260 + 7 * i, im_sz=im) for i in range(n_obj)]
+    lat = [oracle.synthetic_latents(260 + 7 * i, 1) for i in range(n_obj)]
+    n = im * im
+    jit = torch.rand(n_obj, n, S_, generator=torch.Generator().manual_seed(77))
+    R = S.renderer.NeRFRenderer(n_samples=S_)
+    for prec, tol in (("bf16", TOL), ("fp32", 1e-5)):
+        m = model_from_state(S.SUPNeRF, sd, 5, 5, 3, 3, 256)
+        m.precision = prec
+        m.requires_grad_(False)
+        per = []
+        for i, o in enumerate(objs):
+            cam = o["cam_pose"].to(DEV).requires_grad_()
+            shp, tex = lat[i][0].to(DEV).requires_grad_(), lat[i][1].to(DEV).requires_grad_()
+            with forced_rand_like(jit[i]):
+                rgb, dep, acc, tgt, occ = R.render_rays(m, DEV, o["img"], o["mask_occ"], cam, o["wlh"], o["K"].to(DEV), o["roi"], shp, tex, im_sz=im)
+            S.losses.refine_loss(rgb, acc, tgt, occ, 0.1)[0].backward()
+            per.append((rgb.detach(), dep.detach(), cam.grad, shp.grad))
+        cams = torch.stack([o["cam_pose"] for o in objs]).to(DEV).requires_grad_()
+        shps = torch.cat([l[0] for l in lat]).to(DEV).requires_grad_()
+        texs = torch.cat([l[1] for l in lat]).to(DEV).requires_grad_()
+        rgb, dep, acc, tgt, occ = R.render_rays_batch(m, DEV, [o["img"] for o in objs], [o["mask_occ"] for o in objs], cams,
+                                                      [o["wlh"] for o in objs], torch.stack([o["K"] for o in objs]), [o["roi"] for o in objs],
+                                                      shps, texs, im_sz=im, jitter=jit.to(DEV))
+        S.losses.refine_loss_batch(rgb, acc, tgt, occ, 0.1)[0].sum().backward()
+        for i, o in enumerate(objs):
+            ro, vd = oracle.get_rays(o["K"], o["cam_pose"], o["roi"], uv_steps=[im, im])
+            diag, half = oracle.box_constants(o["wlh"])
+            hb = torch.from_numpy(half)
+            hit = oracle.ray_box_intersection(ro / (diag / 2), vd, -hb.expand_as(ro), hb.expand_as(ro))[2].to(DEV)
+            assert torch.equal(rgb[i][hit], per[i][0][hit]) and torch.equal(dep[i][hit], per[i][1][hit])
+            parity("%s_obj%d_g_shape_vs_per_object" % (prec, i), shps.grad[i], per[i][3][0], 1e-4)
+            cam_o = o["cam_pose"].clone().requires_grad_()
+            s_o, t_o = lat[i][0].clone().requires_grad_(), lat[i][1].clone().requires_grad_()
+            rgb_o, dep_o, acc_o, _ = oracle.render_rays_box(sd, o["K"], cam_o, o["wlh"], o["roi"], im, S_, s_o, t_o, jit[i])
+            oracle.refine_losses(rgb_o, acc_o, o["img"].reshape(-1, 3), o["mask_occ"].reshape(-1, 1))[0].backward()
+            parity("%s_obj%d_rgb_vs_oracle" % (prec, i), rgb[i], rgb_o, tol)
+            parity("%s_obj%d_depth_vs_oracle" % (prec, i), dep[i], dep_o, tol)
+            parity("%s_obj%d_g_shape_vs_oracle" % (prec, i), shps.grad[i], s_o.grad[0], tol if prec == "bf16" else 1e-4)

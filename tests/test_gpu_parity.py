@@ -981,7 +981,7 @@ def test_batch_refiner_one_launch_set_equals_per_object_refiners(prec):
         cap.run(1)            # the jitter tables hold max_iters rows
 
 
-@pytest.mark.parametrize("blocks,B,n,S_", [((3, 1), 1, 128, 16), ((3, 1), 4, 64, 8), ((5, 3), 2, 32, 8), ((2, 1), 1, 37, 5)])
+@pytest.mark.parametrize("blocks,B,n,S_", [((3, 1), 1, 128, 16), ((3, 1), 4, 64, 8), ((5, 5), 2, 32, 8), ((2, 1), 1, 37, 5)])
 def test_decoder_fp32_on_tensor_cores_vs_oracle(blocks, B, n, S_):
     """SNB_PREC_FP32_TC (fp32 mode with frozen weights: two fp16 parts per MMA operand, three tcgen05 MMAs per product) against the fp32
     oracle at the fp32 tolerance -- outputs, d xyz, d viewdir and the latent gradients -- with per-row upstream gradients spread over 12
