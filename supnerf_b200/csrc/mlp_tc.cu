@@ -45,12 +45,18 @@ constexpr int kMaxLatentSlots = 10;
 // pair of physical chunks, the weight ring carries [128 n][64 k] stages (hi and lo of each N half, one after the other) and the
 // bias / latent tables are read through L1 instead (tools/experiments/split_precision_emulation.py: errors vs fp64 on par with fp32 FFMA).
 constexpr float kWScale = 256.f, kWScaleInv = 1.f / 256.f;
-// Order of the three products of a K chunk.  true: per N half all correction products first, then the leading ones (the hi weight image
-// is streamed twice: 3 stages per chunk and N half); false: chunk by chunk (2 stages).  See mma_loop.
+// Order of the three products of a layer's K chunks (see mma_loop).  1: every chunk's correction products first, then all leading ones
+// (the hi weight image is streamed twice: 3 stages per chunk and N half); 0: chunk by chunk (2 stages); 2: corrections first for all
+// chunks but the LAST one the epilogue publishes, whose three products are issued together -- the leading products of the earlier
+// chunks then run while the epilogue still works on the last chunk.
 #ifndef SNB_SPLIT_CORR_FIRST
 #define SNB_SPLIT_CORR_FIRST 1
 #endif
-constexpr bool kCorrFirst = SNB_SPLIT_CORR_FIRST != 0;
+constexpr int kOrder = SNB_SPLIT_CORR_FIRST;
+constexpr bool kCorrFirst = kOrder != 0;
+__host__ __device__ constexpr int split_stages_per_half(int n_chunks) {
+  return kOrder == 0 ? 2 * n_chunks : (kOrder == 1 ? 3 * n_chunks : 3 * (n_chunks - 1) + 2);
+}
 constexpr int kSplitBiasSteps = kMaxLatentSlots;   // split mode, forward: steps whose (effective) bias sits in shared memory (the 8 KB the backward uses for column sums)
 
 // shared-memory map (bytes from the 1024-aligned base)
@@ -154,7 +160,7 @@ __device__ __forceinline__ void producer_loop(const Params& p, const SmemT<X>& s
         const uint32_t n = (uint32_t)(g == 0 ? st.n_out : st.n2_out);
         const uint32_t bytes = (X ? n_half_of(n) : n) * 128u;
         const uint32_t off0 = g == 0 ? st.w_off : st.w2_off;
-        const int entries = (int)st.n_chunks * (X ? (kCorrFirst ? 3 : 2) * (int)(n / n_half_of(n)) : 1);   // split: see mma_loop for the order
+        const int entries = X ? split_stages_per_half((int)st.n_chunks) * (int)(n / n_half_of(n)) : (int)st.n_chunks;   // split: see mma_loop
         for (int e = 0; e < entries; ++e, ++it) {
           const uint32_t stage = it % kStages, ph = (it / kStages) & 1u;
           if (lane == 0) {
@@ -224,29 +230,33 @@ __device__ __forceinline__ void mma_loop(const Params& p, const SmemT<X>& sm, in
             ++it;
           };
           // K chunk by K chunk (a chunk's products start as soon as the epilogue has published it), both N halves per chunk
-          for (int kc = 0; kc < st.n_chunks; ++kc) {
+          const int n_corr = kOrder == 1 ? (int)st.n_chunks : (kOrder == 2 ? (int)st.n_chunks - 1 : 0);   // chunks whose corrections go first
+          for (int kc = 0; kc < n_corr; ++kc) {              // corrections only: a_lo * w_hi, a_hi * w_lo
             const int ac = st.a_chunk[kc];
             const uint32_t a_hi = sm.chunk_u32(ac, 0), a_lo = sm.chunk_u32(ac, 1);
             for (uint32_t nh = 0; nh < halves; ++nh) {
               const uint32_t d = d_tmem + nh * 128u;
-              const int wait_chunk = (g == 0 && nh == 0) ? ac : -1;
-              if (kCorrFirst) {   // corrections only: a_lo * w_hi, a_hi * w_lo
-                run_stage(d, a_lo, 0u, false, kc == 0, wait_chunk);
-                run_stage(d, a_hi, 0u, false, false, -1);
-              } else {            // all three: (a_lo, a_hi) * w_hi, a_hi * w_lo
-                run_stage(d, a_lo, a_hi, true, kc == 0, wait_chunk);
-                run_stage(d, a_hi, 0u, false, false, -1);
-              }
+              run_stage(d, a_lo, 0u, false, kc == 0, (g == 0 && nh == 0) ? ac : -1);
+              run_stage(d, a_hi, 0u, false, false, -1);
             }
             if (g == 0) a_phase ^= 1u << ac;
             __syncwarp();
           }
-          if (kCorrFirst) {       // the leading products, once every correction sits in the (still small) accumulators
-            for (int kc = 0; kc < st.n_chunks; ++kc) {
-              const uint32_t a_hi = sm.chunk_u32(st.a_chunk[kc], 0);
-              for (uint32_t nh = 0; nh < halves; ++nh) run_stage(d_tmem + nh * 128u, a_hi, 0u, false, false, -1);
-              __syncwarp();
+          for (int kc = 0; kc < n_corr; ++kc) {              // their leading products, into accumulators that hold the corrections
+            const uint32_t a_hi = sm.chunk_u32(st.a_chunk[kc], 0);
+            for (uint32_t nh = 0; nh < halves; ++nh) run_stage(d_tmem + nh * 128u, a_hi, 0u, false, false, -1);
+            __syncwarp();
+          }
+          for (int kc = n_corr; kc < st.n_chunks; ++kc) {    // the remaining chunks: all three products, (a_lo, a_hi) * w_hi, a_hi * w_lo
+            const int ac = st.a_chunk[kc];
+            const uint32_t a_hi = sm.chunk_u32(ac, 0), a_lo = sm.chunk_u32(ac, 1);
+            for (uint32_t nh = 0; nh < halves; ++nh) {
+              const uint32_t d = d_tmem + nh * 128u;
+              run_stage(d, a_lo, a_hi, true, kc == 0, (g == 0 && nh == 0) ? ac : -1);
+              run_stage(d, a_hi, 0u, false, false, -1);
             }
+            if (g == 0) a_phase ^= 1u << ac;
+            __syncwarp();
           }
         }
       }
@@ -863,13 +873,16 @@ static void add_chunk_list(TcPlan& pl, const std::vector<ChunkSrc>& chunks, int 
     for (const ChunkSrc& c : chunks) push(c, 0, -1);
     return;
   }
-  // split mode, in the order the MMA warp consumes the stages: K chunk by K chunk, per N half the (hi, lo) pair; with corrections
-  // first, every chunk's hi image follows once more for the leading products
-  for (const ChunkSrc& c : chunks)
-    for (int n0 = 0; n0 < n_pad; n0 += nh) { push(c, n0, 0); push(c, n0, 1); }
-  if (kCorrFirst)
-    for (const ChunkSrc& c : chunks)
-      for (int n0 = 0; n0 < n_pad; n0 += nh) push(c, n0, 0);
+  // split mode, in the order the MMA warp consumes the stages (mma_loop): the chunks whose corrections go first -- per chunk and N half
+  // the (hi, lo) pair --, their hi images once more for the leading products, then the remaining chunks' (hi, lo) pairs
+  const int n = (int)chunks.size();
+  const int n_corr = kOrder == 1 ? n : (kOrder == 2 ? n - 1 : 0);
+  for (int c = 0; c < n_corr; ++c)
+    for (int n0 = 0; n0 < n_pad; n0 += nh) { push(chunks[c], n0, 0); push(chunks[c], n0, 1); }
+  for (int c = 0; c < n_corr; ++c)
+    for (int n0 = 0; n0 < n_pad; n0 += nh) push(chunks[c], n0, 0);
+  for (int c = n_corr; c < n; ++c)
+    for (int n0 = 0; n0 < n_pad; n0 += nh) { push(chunks[c], n0, 0); push(chunks[c], n0, 1); }
 }
 
 static void add_chunks(TcPlan& pl, const float* src, int ld, bool transposed, int n_valid, int n_pad, int k_limit, int n_chunks,
