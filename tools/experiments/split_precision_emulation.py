@@ -5,7 +5,11 @@ issued?  Products of 16-bit parts are exact in fp32; accumulation is emulated in
     fp16 x 2 parts, 3 MMAs (hh, hl, lh)        <- candidate: a third of the bf16 rate
     bf16 x 3 parts, 6 MMAs (i + j <= 2)        <- a sixth
     bf16 x 2 parts, 3 MMAs
-Forward outputs and input / latent gradients, error metric = tests/conftest.py:rel_err.  python tools/experiments/split_precision_emulation.py"""
+Forward outputs and input / latent gradients, error metric = tests/conftest.py:rel_err.
+    python tools/experiments/split_precision_emulation.py [--rz [--corr-first]]
+--rz: the accumulator is truncated (round toward zero) after every K = 16 instruction, as the tensor core does; --corr-first: the
+kernels' product order (all correction products of a layer before its leading products).  Gradients in --rz mode are dominated by
+single ReLU gates that open in one arithmetic and not in the other (see fp32_tc_row_errors.py for the per-row picture)."""
 import os
 import sys
 
@@ -17,6 +21,7 @@ from oracle import oracle  # noqa: E402
 
 
 RZ_ACCUMULATE = "--rz" in sys.argv
+CORR_FIRST = "--corr-first" in sys.argv
 
 
 def rz32(x64):
@@ -49,9 +54,13 @@ def make_mm(mode):
         if RZ_ACCUMULATE:
             # the tensor core's accumulator: every K = 16 instruction adds its (exact) block sum and TRUNCATES to fp32 (round toward zero)
             acc = torch.zeros(a.shape[0], b.shape[1], dtype=torch.float64)
-            for k0 in range(0, a.shape[1], 16):
-                for i, j in ((1, 0), (0, 0), (0, 1)) if parts == 2 else [(i, j) for i in range(parts) for j in range(parts) if i + j <= keep]:
-                    acc = rz32(acc + pa[i][:, k0:k0 + 16].double() @ pb[j][k0:k0 + 16].double())
+            terms = ((1, 0), (0, 0), (0, 1)) if parts == 2 else [(i, j) for i in range(parts) for j in range(parts) if i + j <= keep]
+            if CORR_FIRST:   # every K block's correction products first (the accumulator is still ~2^-11 of its final size), then the leading ones
+                order = [(k0, t) for t in terms if t != (0, 0) for k0 in range(0, a.shape[1], 16)] + [(k0, (0, 0)) for k0 in range(0, a.shape[1], 16)]
+            else:            # K block by K block
+                order = [(k0, t) for k0 in range(0, a.shape[1], 16) for t in terms]
+            for k0, (i, j) in order:
+                acc = rz32(acc + pa[i][:, k0:k0 + 16].double() @ pb[j][k0:k0 + 16].double())
             return acc.float() * (sa * sb)
         acc = torch.zeros(a.shape[0], b.shape[1], dtype=torch.float32)
         for i in reversed(range(parts)):           # small terms first
@@ -101,24 +110,31 @@ def rel(a, b):
     return ((a.double() - b.double()).abs().max() / b.double().abs().max()).item()
 
 
-def main():
-    torch.manual_seed(0)
+def run(n=4096, modes=("fp32", "fp16x2", "bf16x3", "bf16x2"), rz=False, corr_first=False, seed=0):
+    """-> {mode: {tensor: (error vs the fp32 run, error vs the fp64 run)}} for the shipped 3 / 1 / 256 decoder on n random samples."""
+    global RZ_ACCUMULATE, CORR_FIRST
+    RZ_ACCUMULATE, CORR_FIRST = rz, corr_first
+    torch.manual_seed(seed)
     sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=7)
-    n = 4096
     xyz0 = (torch.rand(n, 3) - 0.5)
     vd0 = torch.nn.functional.normalize(torch.randn(n, 3), dim=-1)
     sl0, tl0 = oracle.synthetic_latents(5, 1)
     gs, gr = torch.randn(n, 1), torch.randn(n, 3)
     res = {}
-    for mode in ("fp64", "fp32", "fp16x2", "bf16x3", "bf16x2"):
+    for mode in ("fp64", "fp32") + tuple(m for m in modes if m != "fp32"):
         xyz, vd, sl, tl = [t.clone().requires_grad_() for t in (xyz0, vd0, sl0, tl0)]
         sig, rgb = decoder(sd, xyz, vd, sl.expand(n, -1), tl.expand(n, -1), mode)
         ((sig.double() * gs.double()).sum() + (rgb.double() * gr.double()).sum()).backward()
         res[mode] = dict(sigma=sig.detach(), rgb=rgb.detach(), g_xyz=xyz.grad, g_vd=vd.grad, g_shape=sl.grad, g_tex=tl.grad)
+    return {mode: {k: (rel(res[mode][k], res["fp32"][k]), rel(res[mode][k], res["fp64"][k])) for k in res[mode]} for mode in modes}
+
+
+def main():
+    out = run(rz="--rz" in sys.argv, corr_first="--corr-first" in sys.argv)
     print("%-8s %-8s %12s %12s" % ("mode", "tensor", "vs fp32", "vs fp64"))
-    for mode in ("fp32", "fp16x2", "bf16x3", "bf16x2"):
-        for k in res[mode]:
-            print("%-8s %-8s %12.3g %12.3g" % (mode, k, rel(res[mode][k], res["fp32"][k]), rel(res[mode][k], res["fp64"][k])))
+    for mode, d in out.items():
+        for k, (e32, e64) in d.items():
+            print("%-8s %-8s %12.3g %12.3g" % (mode, k, e32, e64))
 
 
 if __name__ == "__main__":
