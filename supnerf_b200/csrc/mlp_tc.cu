@@ -1,9 +1,10 @@
-// K2 / K2b, SNB_PREC_BF16 back end: the CodeNeRF-family decoder as ONE persistent, warp-specialised
+// K2 / K2b, one-tile tensor-core back end (SNB_PREC_BF16 for decoders the two-tile kernels of mlp_tc2.cu do not cover, and
+// SNB_PREC_FP32_TC, the split-precision mode described below): the CodeNeRF-family decoder as ONE persistent, warp-specialised
 // tcgen05 kernel per direction.  A 128-sample tile enters as fp32 xyz / viewdir; the positional
 // encoding is built straight into shared memory as bf16 (never to HBM); every layer is a
 // tcgen05.mma (bf16 x bf16 -> fp32 in TMEM, M=128, N<=256) whose A operand is the previous layer's
 // epilogue output kept in shared memory and whose B operand (pre-tiled, pre-swizzled bf16 weight
-// images) is streamed from L2 by the bulk-copy engine (cp.async.bulk + mbarrier) through a 4-stage
+// images) is streamed from L2 by the bulk-copy engine (cp.async.bulk + mbarrier) through a 3-stage
 // ring.  Accumulators ping-pong between the two 256-column halves of TMEM so that the epilogue of
 // layer l (bias, ReLU, latent add, mask bits, bf16 pack) overlaps the MMAs of layer l+1 chunk by
 // chunk.  The 256->1 (sigma) and 128->3 (rgb) heads run on CUDA cores inside the epilogues.
@@ -42,8 +43,9 @@ constexpr int kMaxLatentSlots = 10;
 // part out of fp16's subnormal range; |w| < 255), forward A operands are the activations themselves (|a| < 65504), backward A operands
 // are each row's gradient normalised by a power of two taken from its upstream gradient (the backward pass is linear in it), undone
 // where values leave the tile (latent column sums, d xyz, d viewdir).  Shared memory: every logical 64-column A chunk is a (hi, lo)
-// pair of physical chunks, the weight ring carries [128 n][64 k] stages (hi and lo of each N half, one after the other) and the
-// bias / latent tables are read through L1 instead (tools/experiments/split_precision_emulation.py: errors vs fp64 on par with fp32 FFMA).
+// pair of physical chunks, the weight ring carries [128 n][64 k] stages (hi and lo of each N half, one after the other), and one 10 KB
+// table holds the forward's (effective) biases / the backward's column sums (tools/experiments/split_precision_emulation.py and
+// tests/test_split_precision_numerics.py: the arithmetic's errors vs fp64 are on par with fp32 FFMA).
 constexpr float kWScale = 256.f, kWScaleInv = 1.f / 256.f;
 // Order of the three products of a layer's K chunks (see mma_loop).  1: every chunk's correction products first, then all leading ones
 // (the hi weight image is streamed twice: 3 stages per chunk and N half); 0: chunk by chunk (2 stages); 2: corrections first for all
