@@ -476,7 +476,7 @@ def run_ours(args):
                 "ms_per_refine_iteration": round(a0.elapsed_time(a1) / (4 * 50), 4), "objects": 4, "iterations": 50,
                 "note": "refine.ObjectGroup: the 4 objects' iterations forked / joined inside one captured graph, one graph launch per iteration"}
             # ... and as ONE launch set per iteration for all objects (refine.BatchRefiner: batched pose map, render, losses, AdamW)
-            for nb in (4, 16):
+            for nb in (1, 4, 16):
                 bat = snb.refine.BatchRefiner([refiner_uncaptured(k, 60) for k in range(nb)]).capture()
                 bat.run(5)
                 torch.cuda.synchronize()
@@ -484,7 +484,7 @@ def run_ours(args):
                 lastb = bat.run(50)
                 a1.record()
                 torch.cuda.synchronize()
-                refine_it["%d_objects_one_launch_set" % nb] = {
+                refine_it["%d_object%s_one_launch_set" % (nb, "" if nb == 1 else "s")] = {
                     "ms_per_refine_iteration": round(a0.elapsed_time(a1) / (nb * 50), 4), "objects": nb, "iterations": 50,
                     "ms_per_batched_iteration": round(a0.elapsed_time(a1) / 50, 4), "loss_after_obj0": round(float(lastb[0, 0]), 5),
                     "note": "refine.BatchRefiner: every stage of the iteration (incl. the lidar-pixel evaluation) once over all objects, "
