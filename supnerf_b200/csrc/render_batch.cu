@@ -389,64 +389,75 @@ __global__ void __launch_bounds__(256) rb_rays_bwd_kernel(const float* __restric
 #pragma unroll
   for (int i = 0; i < 12; ++i) acc[i] = 0.0;
   for (int64_t base = (int64_t)blockIdx.x * 256 + wib * 32; base < N; base += (int64_t)gridDim.x * 256) {
-    // ---- phase 1: the warp's 32 rays, one after the other; lane j keeps ray j's sums
+    // ---- phase 1: the warp's 32 rays, FOUR at a time: 8 lanes walk one ray's samples, a 3-step butterfly inside the group sums them,
+    // one shuffle hands ray j's sums to lane j (the first version walked one ray per iteration with a 5-step butterfly over 32 lanes:
+    // 224 warp instructions per ray, 198 us per step)
     float k_gon[3] = {0.f, 0.f, 0.f}, k_gd[3] = {0.f, 0.f, 0.f}, k_gzabs = 0.f, k_gnear = 0.f, k_gfar = 0.f;
     const int n_here = (int)((N - base) < 32 ? (N - base) : 32);
-    for (int j = 0; j < n_here; ++j) {
-      const int64_t gi = (int64_t)b * N + base + j;
-      const float4 ra = __ldg(reinterpret_cast<const float4*>(rays8 + 8 * gi)), rb_ = __ldg(reinterpret_cast<const float4*>(rays8 + 8 * gi) + 1);
-      const float d[3] = {ra.w, rb_.x, rb_.y};
-      const bool h = hit[gi] != 0;
-      const float near = rb_.z, far = rb_.w;
-      const int p = pos_all[gi];
-      const float dn = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-      float gon[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f}, gzabs = 0.f, gnear = 0.f, gfar = 0.f;
-      if (h) {
-        for (int k = lane; k < S; k += 32) {
+    const int grp = lane >> 3, l8 = lane & 7;
+    for (int jj = 0; jj < n_here; jj += 4) {
+      const int j = jj + grp;
+      float v[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // gon[3], gd[3], gzabs, gnear, gfar of ray j (this lane's share)
+      if (j < n_here) {
+        const int64_t gi = (int64_t)b * N + base + j;
+        const float4 ra = __ldg(reinterpret_cast<const float4*>(rays8 + 8 * gi)), rb_ = __ldg(reinterpret_cast<const float4*>(rays8 + 8 * gi) + 1);
+        const float d[3] = {ra.w, rb_.x, rb_.y};
+        const bool h = hit[gi] != 0;
+        const float near = rb_.z, far = rb_.w;
+        const int p = pos_all[gi];
+        const float dn = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        if (h) {
+          for (int k = l8; k < S; k += 8) {
+            const float zs = __fadd_rn(__ldg(z_steps + k), __fmul_rn(__ldg(jitter + gi * S + k), fstep));
+            const float zc = __fadd_rn(__fmul_rn(near, __fsub_rn(1.f, zs)), __fmul_rn(far, zs));
+            const int64_t gidx = c.row_start + (int64_t)p * S + k;
+            const float gx[3] = {__ldg(g_xyz_c + 3 * gidx), __ldg(g_xyz_c + 3 * gidx + 1), __ldg(g_xyz_c + 3 * gidx + 2)};
+            float gz = gx[0] * d[0] + gx[1] * d[1] + gx[2] * d[2];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { v[a] += gx[a]; v[3 + a] += zc * gx[a]; }
+            v[3] += __ldg(g_vrep_c + 3 * gidx); v[4] += __ldg(g_vrep_c + 3 * gidx + 1); v[5] += __ldg(g_vrep_c + 3 * gidx + 2);
+            if (g_z_c != nullptr) {
+              const float gv = __ldg(g_z_c + gidx);
+              const float sgn = (zc > 0.f) ? 1.f : ((zc < 0.f) ? -1.f : 0.f);
+              gz += gv * sgn * dn * half_diag;
+              v[6] += gv * fabsf(zc);
+            }
+            v[7] += gz * (1.f - zs);
+            v[8] += gz * zs;
+          }
+        } else if (l8 == 0) {
+          // a miss ray's single row stands for all its samples and is credited to the last one (k = S - 1)
+          const int k = S - 1;
           const float zs = __fadd_rn(__ldg(z_steps + k), __fmul_rn(__ldg(jitter + gi * S + k), fstep));
           const float zc = __fadd_rn(__fmul_rn(near, __fsub_rn(1.f, zs)), __fmul_rn(far, zs));
-          const int64_t gidx = c.row_start + (int64_t)p * S + k;
+          const int64_t gidx = c.row_start + c.n_hit * S + p;
           const float gx[3] = {__ldg(g_xyz_c + 3 * gidx), __ldg(g_xyz_c + 3 * gidx + 1), __ldg(g_xyz_c + 3 * gidx + 2)};
           float gz = gx[0] * d[0] + gx[1] * d[1] + gx[2] * d[2];
 #pragma unroll
-          for (int a = 0; a < 3; ++a) { gon[a] += gx[a]; gd[a] += zc * gx[a]; }
-          gd[0] += __ldg(g_vrep_c + 3 * gidx); gd[1] += __ldg(g_vrep_c + 3 * gidx + 1); gd[2] += __ldg(g_vrep_c + 3 * gidx + 2);
+          for (int a = 0; a < 3; ++a) { v[a] = gx[a]; v[3 + a] = zc * gx[a]; }
+          v[3] += __ldg(g_vrep_c + 3 * gidx); v[4] += __ldg(g_vrep_c + 3 * gidx + 1); v[5] += __ldg(g_vrep_c + 3 * gidx + 2);
           if (g_z_c != nullptr) {
             const float gv = __ldg(g_z_c + gidx);
             const float sgn = (zc > 0.f) ? 1.f : ((zc < 0.f) ? -1.f : 0.f);
             gz += gv * sgn * dn * half_diag;
-            gzabs += gv * fabsf(zc);
+            v[6] = gv * fabsf(zc);
           }
-          gnear += gz * (1.f - zs);
-          gfar += gz * zs;
+          v[7] = gz * (1.f - zs);
+          v[8] = gz * zs;
         }
-#pragma unroll
-        for (int a = 0; a < 3; ++a) { gon[a] = warp_sum(gon[a]); gd[a] = warp_sum(gd[a]); }
-        gzabs = warp_sum(gzabs); gnear = warp_sum(gnear); gfar = warp_sum(gfar);
-      } else if (lane == j) {
-        // a miss ray's single row stands for all its samples and is credited to the last one (k = S - 1)
-        const int k = S - 1;
-        const float zs = __fadd_rn(__ldg(z_steps + k), __fmul_rn(__ldg(jitter + gi * S + k), fstep));
-        const float zc = __fadd_rn(__fmul_rn(near, __fsub_rn(1.f, zs)), __fmul_rn(far, zs));
-        const int64_t gidx = c.row_start + c.n_hit * S + p;
-        const float gx[3] = {__ldg(g_xyz_c + 3 * gidx), __ldg(g_xyz_c + 3 * gidx + 1), __ldg(g_xyz_c + 3 * gidx + 2)};
-        float gz = gx[0] * d[0] + gx[1] * d[1] + gx[2] * d[2];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) { gon[a] = gx[a]; gd[a] = zc * gx[a]; }
-        gd[0] += __ldg(g_vrep_c + 3 * gidx); gd[1] += __ldg(g_vrep_c + 3 * gidx + 1); gd[2] += __ldg(g_vrep_c + 3 * gidx + 2);
-        if (g_z_c != nullptr) {
-          const float gv = __ldg(g_z_c + gidx);
-          const float sgn = (zc > 0.f) ? 1.f : ((zc < 0.f) ? -1.f : 0.f);
-          gz += gv * sgn * dn * half_diag;
-          gzabs = gv * fabsf(zc);
-        }
-        gnear = gz * (1.f - zs);
-        gfar = gz * zs;
       }
-      if (lane == j) {
+      const int src = ((lane - jj) & 3) * 8;            // lanes jj .. jj+3 take their ray's sums from the group that walked it
+      const bool mine = (lane >> 2) == (jj >> 2);
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { k_gon[a] = gon[a]; k_gd[a] = gd[a]; }
-        k_gzabs = gzabs; k_gnear = gnear; k_gfar = gfar;
+      for (int i = 0; i < 9; ++i) {
+        float t = v[i];
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        t += __shfl_xor_sync(0xffffffffu, t, 4);
+        t = __shfl_sync(0xffffffffu, t, src);
+        if (mine) {
+          if (i < 3) k_gon[i] = t; else if (i < 6) k_gd[i - 3] = t; else if (i == 6) k_gzabs = t; else if (i == 7) k_gnear = t; else k_gfar = t;
+        }
       }
     }
     // ---- phase 2: every lane finishes its own ray
