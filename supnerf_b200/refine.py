@@ -431,12 +431,14 @@ class BatchRefiner:
                               betas=r0.opt.betas, eps=r0.opt.eps, weight_decay=r0.opt.weight_decay)
         self.jitter = st(lambda r: r.jitter)                                  # (B, T, S)
         self.max_iters = int(self.jitter.shape[1])
-        # lidar pixels: every object's list padded to one length (a multiple of 4 rays = 256 decoder rows at 64 samples) with copies of
+        # lidar pixels: every object's list padded to one length (a whole number of 256-row decoder super tiles: 4 rays at 64 samples) with copies of
         # its last pixel; the copies' depths are sliced off again.  Objects without lidar pixels render a dummy pixel and report nothing.
         self.n_lidar = [r.n_lidar if r.lidar is not None else 0 for r in refiners]
         self.lidar, self.jitter_lidar = None, None
         if any(self.n_lidar):
-            width = -(-max(self.n_lidar) // 4) * 4
+            import math
+            q = 256 // math.gcd(256, self.n_samples)          # rays per 256 decoder rows (4 at 64 samples)
+            width = -(-max(self.n_lidar) // q) * q
             lx, ly, jl = [], [], []
             for r, n in zip(refiners, self.n_lidar):
                 if n:
