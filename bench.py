@@ -223,7 +223,18 @@ def run_ours(args):
     # pinned result buffers: per object the loss (1) + d cam_pose (12) + d shapecode (256) + d texturecode (256)
     res_host = torch.empty(N_OBJ, 1 + 12 + 512, dtype=torch.float32).pin_memory()
 
+    # e2e, batched path: renderer.GraphedBatchStep -- the step's H2D copies from the pinned host buffers, the batched render, the
+    # losses, their backward and the D2H copy of the result replayed as ONE CUDA graph per step (--eager-e2e: the same step issued
+    # call by call through render_rays_batch, as round 2's earlier lines were measured)
+    stepper = None
+    if batched and not args.eager_e2e:
+        stepper = snb.renderer.GraphedBatchStep(R, model, dev, h_img, h_mask, h_cam, wlhs, h_K, rois, h_shp, h_tex, im_sz=IM_SZ, loss_occ_coef=0.1)
+
     def step_e2e():
+        if stepper is not None:
+            res = stepper.run()
+            torch.cuda.synchronize()     # the step's losses and gradients are on the host when the step ends
+            return float(res[:, 0].sum().item())
         if batched:
             # H2D of the step's inputs from pinned memory (crops, masks, poses, intrinsics, codes), the drop-in call, D2H of the result
             cam = h_cam.to(dev, non_blocking=True).requires_grad_()
@@ -557,7 +568,10 @@ def run_ours(args):
                        "decoder_arithmetic": "bf16 x bf16 -> fp32 (tcgen05)" if args.precision == "bf16" else
                                              ("fp32-grade: fp16 (hi, lo) operand pairs, 3 tcgen05 MMAs per product -> fp32" if fp32_tc else "fp32 FFMA")},
             "e2e": {"value": round(e2e_value, 1), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(ms_e2e / args.steps, 3)},
+                    "ms_per_step": round(ms_e2e / args.steps, 3),
+                    "api": ("renderer.GraphedBatchStep.run(): pinned host inputs -> H2D, render_batch, refine_loss_batch, backward, D2H of the losses and "
+                            "gradients into pinned memory, one CUDA graph launch per step, torch.cuda.synchronize() after every step") if stepper is not None
+                           else "render_rays_batch / render_rays + refine losses + backward call by call, synchronize after every step"},
             "roofline_compositing": comp, "refine_iteration": refine_it, "gpu_launches": int(launches), "clocks": dict(clk.summary(), e2e_region=clk2.summary()), "roofline": roofline, "cpu_baseline": cpu, "gpu_eager_baseline": eager}
     line.update(extras)
     line.update(modes)
@@ -1055,6 +1069,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--eager-e2e", action="store_true", help="e2e through render_rays_batch call by call instead of renderer.GraphedBatchStep (one CUDA graph per step)")
     ap.add_argument("--per-object", dest="batched", action="store_false",
                     help="round 1's path: one fused render per object over --streams CUDA streams (default: all objects in one launch set)")
     ap.add_argument("--fused-sampler", action="store_true",

@@ -275,6 +275,69 @@ class NeRFRenderer(torch.nn.Module):
         return out
 
 
+class GraphedBatchStep:
+    """One refine-style step of B objects as ONE CUDA-graph launch: the host->device copy of the step's inputs from the caller's
+    pinned host buffers (crops, occupancy masks, intrinsics, poses, codes), ``NeRFRenderer.render_batch``, the batched refine losses
+    (optimizer_nuscenes.py:729-736), their backward to the poses and codes, and the device->host copy of
+    ``[loss, d cam_pose (12), d shapecode (D), d texturecode (D)]`` per object into a pinned result buffer -- what the loop around
+    ``render_rays`` does per iteration (optimizer_nuscenes.py:716-737), without ~0.3 ms of per-step Python and launch latency on the
+    host.  Shapes, crops' rois and object sizes are fixed at construction (a refine loop re-renders the same crops); the CONTENT of
+    the host buffers may change between steps.  ``run()`` enqueues a step; ``result`` (B, 1 + 12 + 2 D, pinned) is valid after a
+    synchronisation of the stream (``torch.cuda.current_stream().synchronize()``).  Frozen weights (refine mode)."""
+
+    def __init__(self, renderer, model, device, imgs, masks_occ, cam_poses, obj_szs, Ks, rois, shapecodes, texturecodes, im_sz=64,
+                 loss_occ_coef=0.1, jitter=None, warmup=2):
+        from . import losses
+        device = torch.device(device)
+        host = dict(imgs=imgs, masks_occ=masks_occ, cam_poses=cam_poses, Ks=Ks, shapecodes=shapecodes, texturecodes=texturecodes)
+        for k, t in host.items():
+            if not (torch.is_tensor(t) and t.device.type == "cpu" and t.is_pinned() and t.dtype == torch.float32 and t.is_contiguous()):
+                raise ValueError("GraphedBatchStep: %s must be a contiguous pinned float32 host tensor" % k)
+        b = cam_poses.shape[0]
+        if tuple(imgs.shape) != (b, im_sz, im_sz, 3) or tuple(masks_occ.shape)[:3] != (b, im_sz, im_sz) or tuple(Ks.shape) != (b, 3, 3):
+            raise ValueError("GraphedBatchStep: imgs (B,im_sz,im_sz,3), masks_occ (B,im_sz,im_sz[,1]) and Ks (B,3,3) at the render size")
+        self.host, self.device, self.renderer, self.model = host, device, renderer, model
+        d = shapecodes.shape[1]
+        self.batch = renderer.make_batch(device, imgs, masks_occ, obj_szs, Ks, rois, im_sz)      # pixel grids, box constants; the rest is refreshed per step
+        self.cam = torch.empty(b, 3, 4, device=device).requires_grad_()
+        self.shp = torch.empty(b, d, device=device).requires_grad_()
+        self.tex = torch.empty(b, d, device=device).requires_grad_()
+        self._mask = torch.empty(b, im_sz * im_sz, 1, device=device)
+        self.result = torch.empty(b, 1 + 12 + 2 * d, dtype=torch.float32).pin_memory()
+        self._ones = torch.ones(b, device=device)
+        self._jitter, self._coef, self._losses = jitter, float(loss_occ_coef), losses
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):        # warm-up on a side stream (allocator, weight packing), as torch.cuda.graph requires
+            for _ in range(max(1, int(warmup))):
+                self._step()
+        torch.cuda.current_stream(device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step()
+
+    def _step(self):
+        h, bt = self.host, self.batch
+        with torch.no_grad():
+            self.cam.copy_(h["cam_poses"], non_blocking=True)
+            self.shp.copy_(h["shapecodes"], non_blocking=True)
+            self.tex.copy_(h["texturecodes"], non_blocking=True)
+            bt.K.copy_(h["Ks"], non_blocking=True)
+            bt.rgb_tgt.copy_(h["imgs"].reshape(bt.rgb_tgt.shape), non_blocking=True)
+            self._mask.copy_(h["masks_occ"].reshape(self._mask.shape), non_blocking=True)
+            bt.occ_pixels = self._mask.type(torch.int32).type(torch.float32)          # renderer.py:133
+        rgb, _dep, acc = self.renderer.render_batch(self.model, bt, self.cam, self.shp, self.tex, jitter=self._jitter)
+        loss, parts = self._losses.refine_loss_batch(rgb, acc, bt.rgb_tgt, bt.occ_pixels, self._coef)
+        g_cam, g_shp, g_tex = torch.autograd.grad(loss, [self.cam, self.shp, self.tex], grad_outputs=self._ones)
+        b = self.cam.shape[0]
+        self.result.copy_(torch.cat([parts[:, :1], g_cam.reshape(b, 12), g_shp, g_tex], 1), non_blocking=True)
+
+    def run(self):
+        """Enqueue one step on the current stream (one graph launch).  -> the pinned result buffer (valid after a stream synchronisation)."""
+        self.graph.replay()
+        return self.result
+
+
 def volume_rendering3(sigmas, rgbs, z_vals, white_bkgd=False):
     """renderer.py:355-379: sigmas (N,S,1), rgbs (N,S,3), z_vals (N,S)."""
     return U._composite_any(sigmas, rgbs, z_vals, white_bkgd, True)

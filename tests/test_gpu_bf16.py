@@ -632,3 +632,41 @@ def test_class_default_decoder_5_5_blocks_on_the_tensor_cores():
             parity("%s_obj%d_rgb_vs_oracle" % (prec, i), rgb[i], rgb_o, tol)
             parity("%s_obj%d_depth_vs_oracle" % (prec, i), dep[i], dep_o, tol)
             parity("%s_obj%d_g_shape_vs_oracle" % (prec, i), shps.grad[i], s_o.grad[0], tol if prec == "bf16" else 1e-4)
+
+
+def test_graphed_batch_step_equals_the_call_by_call_step():
+    """renderer.GraphedBatchStep (H2D of the inputs from pinned host buffers, batched render, losses, backward, D2H of the result as one
+    CUDA graph) against the same step issued call by call, under the same jitter; and it follows the CONTENT of the host buffers."""
+    S = snb()
+    n_obj, im, S_ = 3, 16, 32
+    sd = oracle.init_codenerf_state(shape_blocks=3, texture_blocks=1, seed=91)
+    m = model_from_state(S.SUPNeRF, sd, 3, 1, 3, 3, 256)
+    m.precision = "bf16"
+    m.requires_grad_(False)
+    R = S.renderer.NeRFRenderer(n_samples=S_)
+    objs = [oracle.synthetic_object(300 + 7 * i, im_sz=im) for i in range(n_obj)]
+    lat = [oracle.synthetic_latents(300 + 7 * i, 1) for i in range(n_obj)]
+    pin = lambda t: t.contiguous().float().pin_memory()   # noqa: E731
+    h_img, h_mask = pin(torch.stack([o["img"] for o in objs])), pin(torch.stack([o["mask_occ"] for o in objs]))
+    h_cam, h_K = pin(torch.stack([o["cam_pose"] for o in objs])), pin(torch.stack([o["K"] for o in objs]))
+    h_shp, h_tex = pin(torch.cat([l[0] for l in lat])), pin(torch.cat([l[1] for l in lat]))
+    wlhs, rois = [o["wlh"] for o in objs], [o["roi"] for o in objs]
+    jit = torch.rand(n_obj, im * im, S_, generator=torch.Generator().manual_seed(91)).to(DEV)
+    step = S.renderer.GraphedBatchStep(R, m, DEV, h_img, h_mask, h_cam, wlhs, h_K, rois, h_shp, h_tex, im_sz=im, jitter=jit)
+
+    def eager():
+        cam, shp, tex = [t.to(DEV).requires_grad_() for t in (h_cam, h_shp, h_tex)]
+        rgb, dep, acc, tgt, occ = R.render_rays_batch(m, DEV, h_img, h_mask, cam, wlhs, h_K, rois, shp, tex, im_sz=im, jitter=jit)
+        loss, parts = S.losses.refine_loss_batch(rgb, acc, tgt, occ, 0.1)
+        loss.backward(gradient=torch.ones(n_obj, device=DEV))
+        return torch.cat([parts[:, :1], cam.grad.reshape(n_obj, 12), shp.grad, tex.grad], 1).cpu()
+    for rep in range(2):
+        got = step.run()
+        torch.cuda.synchronize()
+        ref = eager()
+        parity("rep%d_loss" % rep, got[:, 0], ref[:, 0], 1e-6)
+        parity("rep%d_g_pose" % rep, got[:, 1:13], ref[:, 1:13], 1e-4)
+        parity("rep%d_g_codes" % rep, got[:, 13:], ref[:, 13:], 1e-5)
+        assert float(got[:, 0].abs().min()) > 0
+        h_cam[:, :, 3] += 0.05          # new content in the same pinned buffers: the next replay must see it
+        h_shp.mul_(0.9)
