@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import T, close_vs_truth, load_golden, parity_ok, rel_err
+from conftest import ADAM_OUTLIERS, T, close_vs_truth, load_golden, parity_ok, rel_err
 from oracle import oracle
 
 pytestmark = pytest.mark.gpu
@@ -610,10 +610,10 @@ def test_object_refiner_matches_reference_api_loop_and_graph_replay():
         assert r.depth_pred.shape == depth_ref.shape and parity_ok("lidar_depth", r.depth_pred, depth_ref, 1e-4)
         # Adam's g / sqrt(v) turns last-ulp differences of near-zero gradient components into O(lr) parameter differences:
         # the codes are compared at 2e-2 of their scale, the loss trajectory and the (well-conditioned) pose tightly
-        assert parity_ok("r_shapecode", r.shapecode, shp, 2e-2) and parity_ok("r_texturecode", r.texturecode, tex, 2e-2)
+        assert parity_ok("r_shapecode", r.shapecode, shp, 2e-2, outliers=ADAM_OUTLIERS) and parity_ok("r_texturecode", r.texturecode, tex, 2e-2, outliers=ADAM_OUTLIERS)
         assert parity_ok("r_rot_vec", r.rot_vec, rv, 1e-3) and parity_ok("r_trans_vec", r.trans_vec, tv, 1e-3)
     for o in outs[1:]:
-        assert parity_ok("o_0_shapecode", o[0].shapecode, outs[0][0].shapecode, 2e-2) and parity_ok("o_1", o[1], outs[0][1], 1e-4)
+        assert parity_ok("o_0_shapecode", o[0].shapecode, outs[0][0].shapecode, 2e-2, outliers=ADAM_OUTLIERS) and parity_ok("o_1", o[1], outs[0][1], 1e-4)
 
 
 @pytest.mark.parametrize("prec,tol_loss", [("fp32", 1e-3), ("bf16", 5e-3)])
@@ -717,7 +717,7 @@ def test_run_objects_side_by_side_equals_one_after_the_other():
     for a, b in zip(seq, par):
         # (the decoder's latent-gradient column sums are accumulated with atomics: equal to rounding, not bit for bit)
         assert parity_ok("b_loss", b.loss, a.loss, 1e-4)
-        assert parity_ok("b_shapecode", b.shapecode, a.shapecode, 2e-2) and parity_ok("b_texturecode", b.texturecode, a.texturecode, 2e-2)
+        assert parity_ok("b_shapecode", b.shapecode, a.shapecode, 2e-2, outliers=ADAM_OUTLIERS) and parity_ok("b_texturecode", b.texturecode, a.texturecode, 2e-2, outliers=ADAM_OUTLIERS)
         assert parity_ok("b_rot_vec", b.rot_vec, a.rot_vec, 1e-3) and parity_ok("b_trans_vec", b.trans_vec, a.trans_vec, 1e-3)
 
 
@@ -910,7 +910,7 @@ def test_object_group_one_graph_equals_sequential_refiners():
     torch.cuda.synchronize()
     for a, b in zip(seq, grp.refiners):
         assert parity_ok("b_loss", b.loss, a.loss, 1e-4)
-        assert parity_ok("b_shapecode", b.shapecode, a.shapecode, 2e-2) and parity_ok("b_rot_vec", b.rot_vec, a.rot_vec, 1e-3)
+        assert parity_ok("b_shapecode", b.shapecode, a.shapecode, 2e-2, outliers=ADAM_OUTLIERS) and parity_ok("b_rot_vec", b.rot_vec, a.rot_vec, 1e-3)
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
@@ -966,17 +966,17 @@ def test_batch_refiner_one_launch_set_equals_per_object_refiners(prec):
                 assert parity_ok("it0_g_texturecode", bat.texturecode.grad[b], r.texturecode.grad.reshape(-1), tol1)
                 assert parity_ok("it0_g_rot_vec", bat.rot_vec.grad[b], r.rot_vec.grad, 10 * tol1)
                 assert parity_ok("it0_g_trans_vec", bat.trans_vec.grad[b], r.trans_vec.grad, 10 * tol1)
-                assert parity_ok("it0_shapecode", bat.shapecode[b], r.shapecode.reshape(-1), 2e-2)
+                assert parity_ok("it0_shapecode", bat.shapecode[b], r.shapecode.reshape(-1), 2e-2, outliers=ADAM_OUTLIERS)
                 assert parity_ok("it0_rot_vec", bat.rot_vec[b], r.rot_vec, 5e-3) and parity_ok("it0_trans_vec", bat.trans_vec[b], r.trans_vec, 5e-3)
     for b, r in enumerate(bat.write_back()):
-        assert parity_ok("end_shapecode", r.shapecode, seq[b].shapecode, 2e-2) and parity_ok("end_texturecode", r.texturecode, seq[b].texturecode, 2e-2)
+        assert parity_ok("end_shapecode", r.shapecode, seq[b].shapecode, 2e-2, outliers=ADAM_OUTLIERS) and parity_ok("end_texturecode", r.texturecode, seq[b].texturecode, 2e-2, outliers=ADAM_OUTLIERS)
         assert parity_ok("end_rot_vec", r.rot_vec, seq[b].rot_vec, 5e-3) and parity_ok("end_trans_vec", r.trans_vec, seq[b].trans_vec, 5e-3)
     # the captured graph replays the same iteration
     cap = S.refine.BatchRefiner([make(k) for k in range(4)]).capture()
     cap.run(iters)
     torch.cuda.synchronize()
     # (not bit-equal: the fp32 / fp64 atomics of the reductions land in another order, and AdamW's g / sqrt(v) amplifies that)
-    assert parity_ok("graph_loss", cap.loss, bat.loss, 1e-4) and parity_ok("graph_shapecode", cap.shapecode, bat.shapecode, 2e-2)
+    assert parity_ok("graph_loss", cap.loss, bat.loss, 1e-4) and parity_ok("graph_shapecode", cap.shapecode, bat.shapecode, 2e-2, outliers=ADAM_OUTLIERS)
     with pytest.raises(ValueError):
         cap.run(1)            # the jitter tables hold max_iters rows
 
