@@ -19,6 +19,7 @@ The render, loss and their backward are the package's fused kernels (ops.render_
 snb_refine_pose_fwd/bwd, snb_adamw_step); ``fused=False`` keeps them as torch ops (torch.optim.AdamW(capturable=True)) --
 the tests check both against the loop written with the reference-shaped API.  CUDA only."""
 import ctypes
+import math
 
 import numpy as np
 import torch
@@ -436,7 +437,6 @@ class BatchRefiner:
         self.n_lidar = [r.n_lidar if r.lidar is not None else 0 for r in refiners]
         self.lidar, self.jitter_lidar = None, None
         if any(self.n_lidar):
-            import math
             q = 256 // math.gcd(256, self.n_samples)          # rays per 256 decoder rows (4 at 64 samples)
             width = -(-max(self.n_lidar) // q) * q
             lx, ly, jl = [], [], []
